@@ -1,0 +1,259 @@
+"""CPU restatement of RecyclingKrylovSolvers (TEST INFRASTRUCTURE): pcg, defpcg, eigpcg,
+eigdefpcg, following cg.jl:67-109, defcg.jl:242-308, eigcg.jl:143-267 and defcg.jl:337-473.
+
+``A`` and ``M`` are callables (x -> A x, r -> M \\ r), standing for the reference's
+LinearMaps.FunctionMap and preconditioner objects.  ``EPS`` is the reference's hard-wired
+relative residual tolerance (RecyclingKrylovSolvers.jl:21).  As in the reference, ``it`` starts
+at 1 (it = iterations + 1), ``res_norm`` has ``it`` entries and ``x`` is updated in place.
+"""
+import numpy as np
+
+EPS = 1e-7  # RecyclingKrylovSolvers.jl:21
+
+
+def pcg(A, b, x, M, maxit=0, eps=EPS):
+    """cg.jl:67-109."""
+    n = x.size
+    maxit = n if maxit == 0 else maxit                       # :81
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)                                             # :83
+    rTr = r @ r
+    z = M(r)                                                 # :85
+    rTz = r @ z
+    p = z.copy()
+    res_norm[it - 1] = np.sqrt(rTr)
+    tol = eps * np.linalg.norm(b)                            # :89-90
+    while it < maxit and res_norm[it - 1] > tol:             # :92
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        p = beta * p + z
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+    return x, it, res_norm[:it].copy()
+
+
+def _julia_rank(Y):
+    """LinearAlgebra.rank default: #singular values > min(size)*eps*sigma_max."""
+    s = np.linalg.svd(Y, compute_uv=False)
+    if s.size == 0 or s[0] == 0.0:
+        return 0
+    tol = min(Y.shape) * np.finfo(np.float64).eps * s[0]
+    return int((s > tol).sum())
+
+
+def _rayleigh_ritz(Tm, Tm_minor, nvec):
+    """Shared restart algebra of eigcg.jl:220-228 / defcg.jl:425-432: returns (Q Z, vals, nev)."""
+    m = Tm.shape[0]
+    Y = np.zeros((m, 2 * nvec))
+    Y[:, :nvec] = np.linalg.eigh(Tm)[1][:, :nvec]
+    Y[:m - 1, nvec:] = np.linalg.eigh(Tm_minor)[1][:, :nvec]
+    nev = _julia_rank(Y)
+    Q = np.linalg.svd(Y, full_matrices=False)[0][:, :nev]
+    H = Q.T @ (Tm @ Q)
+    H = np.triu(H) + np.triu(H, 1).T                         # Symmetric(H)
+    vals, Z = np.linalg.eigh(H)
+    return Q @ Z, vals, nev
+
+
+def _sym(U):
+    """Symmetric(U): mirror the upper triangle."""
+    return np.triu(U) + np.triu(U, 1).T
+
+
+def defpcg(A, b, x, W, M, maxit=0, eps=EPS):
+    """defcg.jl:242-308."""
+    n, nvec = W.shape
+    WtA = np.empty((nvec, n))
+    for iv in range(nvec):                                   # :261-264
+        WtA[iv, :] = A(W[:, iv])
+    WtAW = WtA @ W                                           # :268
+    r = b - A(x)
+    mu = np.linalg.solve(WtAW, W.T @ r)                      # :272-274
+    x += W @ mu
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    res_norm[0] = np.sqrt(rTr)
+    z = M(r)
+    rTz = r @ z
+    mu = np.linalg.solve(WtAW, WtA @ z)                      # :284
+    p = z - W @ mu
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:             # :290
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        mu = np.linalg.solve(WtAW, WtA @ z)                  # :301
+        p = beta * p + z - W @ mu                            # :302
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+    return x, it, res_norm[:it].copy()
+
+
+def eigpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """eigcg.jl:143-267.  Returns (x, it, res_norm, V[:, :nvec])."""
+    n = x.size
+    V = np.zeros((n, spdim))
+    AV = np.empty((n, spdim))
+    VtAV = np.zeros((spdim, spdim))
+    tvec = np.zeros(n)
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    z = M(r)
+    rTz = r @ z
+    p = z.copy()
+    res_norm[0] = np.sqrt(rTr)
+    ivec = 0                                                 # 0-based column cursor (:178)
+    V[:, ivec] = z / np.sqrt(rTz)
+    just_restarted = False
+    hlpr = 0.0
+    nev = 0
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:             # :185
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        rTr = r @ r
+        z = M(r)
+        if just_restarted:
+            hlpr = np.sqrt(rTz)                              # :194-196
+        rTz = r @ z
+        beta *= rTz
+        if ivec == spdim - 1:
+            tvec -= beta * Ap                                # :199-201
+        p = beta * p + z
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+        VtAV[ivec, ivec] += 1.0 / alpha                      # :206
+        if just_restarted:
+            tvec += Ap                                       # :208
+            nev = ivec
+            VtAV[:nev, ivec] = V[:, :nev].T @ (tvec / hlpr)  # :210
+            just_restarted = False
+        if ivec == spdim - 1:                                # :214
+            for jv in range(spdim):
+                AV[:, jv] = A(V[:, jv])
+            VtAV[:, :] = V.T @ AV                            # :222
+            Tm = _sym(VtAV)
+            QZ, vals, nev = _rayleigh_ritz(Tm, Tm[:spdim - 1, :spdim - 1], nvec)
+            V[:, :nev] = V @ QZ                              # :231
+            ivec = nev
+            V[:, ivec] = z / np.sqrt(rTz)
+            VtAV[:, :] = 0.0
+            VtAV[np.arange(nev), np.arange(nev)] = vals
+            VtAV[ivec, ivec] = beta / alpha
+            tvec = -beta * Ap                                # :240
+            just_restarted = True
+        else:
+            ivec += 1
+            V[:, ivec] = z / np.sqrt(rTz)
+            VtAV[ivec - 1, ivec] = -np.sqrt(beta) / alpha
+            VtAV[ivec, ivec] = beta / alpha
+    if not just_restarted:                                   # :251
+        if ivec + 1 > nvec:
+            m = ivec                                         # reference: ivec -= 1 (1-based) => m columns
+            Tm = _sym(VtAV[:m, :m])
+            QZ, vals, nev = _rayleigh_ritz(Tm, Tm[:m - 1, :m - 1], nvec)
+            V[:, :nev] = V[:, :m] @ QZ
+    return x, it, res_norm[:it].copy(), V[:, :nvec].copy()
+
+
+def eigdefpcg(A, b, x, M, W, spdim, maxit=0, eps=EPS):
+    """defcg.jl:337-473.  Returns (x, it, res_norm, V[:, :nvec])."""
+    n, nvec = W.shape
+    WtA = np.empty((nvec, n))
+    for iv in range(nvec):                                   # :357-360
+        WtA[iv, :] = A(W[:, iv])
+    WtAW = WtA @ W
+    WtW = W.T @ W
+    r = b - A(x)
+    mu = np.linalg.solve(WtAW, W.T @ r)
+    x += W @ mu
+    V = np.zeros((n, spdim))
+    VtAV = np.zeros((spdim, spdim))
+    first_restart = True
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    z = M(r)
+    rTz = r @ z
+    mu = np.linalg.solve(WtAW, WtA @ z)
+    p = z - W @ mu
+    res_norm[0] = np.sqrt(rTr)
+    VtAV[:nvec, :nvec] = WtAW                                # :390
+    V[:, :nvec] = W
+    just_restarted = False
+    ivec = nvec                                              # 0-based cursor (:394)
+    V[:, ivec] = z / np.sqrt(rTz)
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:             # :400
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        r -= W @ np.linalg.solve(WtW, W.T @ r)               # :407
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        mu = np.linalg.solve(WtAW, WtA @ z)
+        p = beta * p + z - W @ mu
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+        VtAV[ivec, ivec] += 1.0 / alpha                      # :417
+        if ivec == spdim - 1:                                # :419
+            if first_restart:
+                VtAV[:nvec, nvec:spdim] = WtA @ V[:, nvec:spdim]
+                first_restart = False
+            Tm = _sym(VtAV)
+            QZ, vals, nev = _rayleigh_ritz(Tm, Tm[:spdim - 1, :spdim - 1], nvec)
+            V[:, :nev] = V @ QZ
+            ivec = nev
+            V[:, ivec] = z / np.sqrt(rTz)
+            VtAV[:, :] = 0.0
+            VtAV[np.arange(nev), np.arange(nev)] = vals
+            VtAV[ivec, ivec] = beta / alpha
+            just_restarted = True
+        else:
+            just_restarted = False
+            ivec += 1
+            V[:, ivec] = z / np.sqrt(rTz)
+            VtAV[ivec - 1, ivec] = -np.sqrt(beta) / alpha
+            VtAV[ivec, ivec] = beta / alpha
+    if not just_restarted:                                   # :450
+        if ivec + 1 > nvec:
+            m = ivec
+            if first_restart:
+                VtAV[:nvec, nvec:m] = WtA @ V[:, nvec:m]
+            Tm = _sym(VtAV[:m, :m])
+            QZ, vals, nev = _rayleigh_ritz(Tm, Tm[:m - 1, :m - 1], nvec)
+            V[:, :nev] = V[:, :m] @ QZ
+    return x, it, res_norm[:it].copy(), V[:, :nvec].copy()
