@@ -1,0 +1,138 @@
+/* libkrylov_b200.so -- C ABI of the B200-native Schur-complement PCG hot path.
+ *
+ * Drop-in boundary for venkovic/julia-phd-krylov-spdes: the reference's Julia API keeps its
+ * call shapes and `ccall`s these entry points for everything executed per PCG iteration
+ * (INTEGRATION.md shows the Julia binding).  Each entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative kb200_status otherwise; the message
+ *    is available from kb200_last_error() (thread-local); nothing throws or exits across the ABI;
+ *  - sparse matrices are Julia-native SparseMatrixCSC{Float64,Int}: Int64 **1-based** colptr /
+ *    rowval + Float64 nzval; index maps are Int64 1-based; dense matrices are column-major;
+ *  - the library copies every input during the call and never keeps or frees caller memory;
+ *  - one handle = one GPU = one calling thread at a time (Julia's synchronous ccall model);
+ *  - there is no CPU fallback: without a usable CUDA device kb200_create fails.
+ */
+#ifndef KRYLOV_B200_H
+#define KRYLOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb200_ctx* kb200_handle;
+
+typedef enum {
+  KB200_OK = 0,
+  KB200_ERR_INVALID = -1,   /* bad argument / call order */
+  KB200_ERR_CUDA = -2,      /* CUDA runtime error */
+  KB200_ERR_NCCL = -3,      /* NCCL error */
+  KB200_ERR_INPUT = -4,     /* malformed matrix / factor */
+  KB200_ERR_NOT_SPD = -5,   /* p'Ap <= 0 met during a solve (reported, solve stopped) */
+  KB200_ERR_INTERNAL = -6
+} kb200_status;
+
+/* Per-solve measurements (device times from CUDA events on the library's stream). */
+typedef struct {
+  double solve_ms;          /* whole solve on the device, host<->device copies excluded */
+  double schur_ms;          /* sum over launches of the local-Schur stream kernel */
+  double nn_ms;             /* sum over launches of the Neumann-Neumann GEMV kernel */
+  int64_t schur_launches;
+  int64_t nn_launches;
+  int64_t kernel_launches;  /* every kernel of this library launched by the call */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} kb200_timings;
+
+const char* kb200_last_error(void);
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Single-process handle on device `device_id`. */
+int kb200_create(int device_id, kb200_handle* out);
+/* One process per GPU: `nccl_id` is the 128-byte ncclUniqueId produced on rank 0 by
+ * kb200_nccl_unique_id and distributed by the host (torch.distributed / MPI / files).  Subdomains
+ * are sharded over ranks; every apply ends in one NCCL all-reduce of the interface vector
+ * (reference sketch: Fem/EllipticPdePllDomainDecomposition.jl:1-18, `@distributed (+)`). */
+int kb200_nccl_unique_id(void* out128);
+int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, kb200_handle* out);
+int kb200_destroy(kb200_handle h);
+/* Tunables: "csize" (CTAs per subdomain cluster: 1,2,4,8), "profile" (0/1: time the two
+ * dominant kernels with CUDA events), "check_every" (iterations between convergence polls). */
+int kb200_set_option(kb200_handle h, const char* name, int64_t value);
+
+/* ---- setup (once per mesh / per realization) ------------------------------------------------- */
+/* Flattened outputs of set_subdomains (Fem/EllipticPdeDomainDecomposition.jl:86-193):
+ * gamma_l2g[d][l] = interface id of local interface node l of subdomain d, i.e. the inverse of the
+ * Dict ind_Γd_Γ2l[d] (cf. ind_Γd_l2Γ at :1090-1095); node_gamma_cnt = node_Γ_cnt. */
+int kb200_set_topology(kb200_handle h, int64_t ndom, int64_t n_gamma, const int64_t* n_I,
+                       const int64_t* n_gd, const int64_t* const* gamma_l2g,
+                       const int64_t* node_gamma_cnt);
+/* Subdomains [d0, d1) (0-based) live on this handle's GPU (all of them without NCCL). Uploads for
+ * other subdomains are accepted and ignored. */
+int kb200_local_range(kb200_handle h, int64_t* d0, int64_t* d1);
+/* Blocks of prepare_local_schurs (:389-546) for subdomain d (0-based): A_IΓ,d (n_I x n_gd, local
+ * interface columns) and A_ΓΓ,d (n_gd x n_gd). */
+int kb200_upload_local_blocks(kb200_handle h, int64_t d,
+                              const int64_t* AIG_colptr, const int64_t* AIG_rowval, const double* AIG_nzval,
+                              const int64_t* AGG_colptr, const int64_t* AGG_rowval, const double* AGG_nzval);
+/* Exact interior solve A_II,d^{-1} = P' L^-T L^-1 P from F = cholesky(A_IIdd[d]) (:1536;
+ * MyPreconditioners/CholPreconditioners.jl:11): perm = F.p, L = sparse(F.L) (lower, diagonal
+ * stored, sorted rows).  Replaces the inner IterativeSolvers.cg(A_IIdd, ., Pl=...) of :648-650. */
+int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm,
+                          const int64_t* L_colptr, const int64_t* L_rowval, const double* L_nzval);
+/* ΠSd[d] of NeumannNeumannSchurPreconditioner (:1125), n_gd x n_gd column-major. */
+int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS);
+/* Dense local Schur complement S_d (assemble_local_schurs, :667-695), n_gd x n_gd column-major. */
+int kb200_upload_dense_local_schur(kb200_handle h, int64_t d, const double* Sd);
+/* Host analysis (level schedules, cluster mapping) + upload to the GPU.  Called implicitly by the
+ * first operation that needs it. */
+int kb200_finalize(kb200_handle h);
+
+/* ---- operators (host vectors in, host vectors out) -------------------------------------------- */
+/* y = S x, matrix-free: apply_local_schurs (:711-747).  x, y: n_gamma x nrhs column-major. */
+int kb200_apply_schur(kb200_handle h, const double* x, double* y, int64_t nrhs);
+/* y = S x with the dense S_d: apply_local_schurs assembled variant (:761-785). */
+int kb200_apply_schur_assembled(kb200_handle h, const double* x, double* y, int64_t nrhs);
+/* z = M \ r: apply_neumann_neumann_schur / `\` / ldiv! (:1361-1403). */
+int kb200_apply_nn(kb200_handle h, const double* r, double* z, int64_t nrhs);
+/* b_schur = b_Γ - Σ_d R_d' A_ΓI,d A_II,d^{-1} b_I,d : get_schur_rhs (:835-864).
+ * b_I_concat = [b_Id[1]; b_Id[2]; ...] (all subdomains, every rank). */
+int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_gamma, double* b_schur);
+/* u_I,d = A_II,d^{-1} (b_I,d - A_IΓ,d u_Γ): get_subdomain_solutions (:1014-1025). */
+int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b_I_concat,
+                          double* u_I_concat);
+/* Dense S_d of every local subdomain computed on the device column by column and kept for
+ * kb200_apply_schur_assembled: assemble_local_schurs (:667-695; Symmetric() of the upper triangle
+ * as at :692).  kb200_get_dense_local_schur copies one block out (column-major). */
+int kb200_assemble_local_schurs(kb200_handle h);
+int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out);
+
+/* ---- solvers (whole solve on the device) ------------------------------------------------------- */
+/* pcg(A, b, x, M; maxit) of RecyclingKrylovSolvers/cg.jl:67-109 with A = the Schur operator
+ * (assembled != 0: the dense-S_d variant) and M = the Neumann-Neumann preconditioner
+ * (precond == 0: identity, i.e. cg.jl:14-50).  x is updated in place; *it and res_norm[0..*it)
+ * follow the reference (it = iterations + 1); rtol is RecyclingKrylovSolvers.jl:21 (1e-7);
+ * maxit == 0 means n_gamma.  res_norm must hold maxit (or n_gamma) + 1 entries. */
+int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled,
+              int precond, int64_t* it, double* res_norm, kb200_timings* timings);
+
+/* ---- introspection (tests / benchmarks) -------------------------------------------------------- */
+/* stats[0..n): 0 Σ nnz(L) strictly lower, 1 Σ stream entries, 2 Σ rows, 3 Σ slices,
+ * 4 stream bytes read per Schur apply, 5 max levels, 6 max top size, 7 shared memory per CTA,
+ * 8 CTAs per launch, 9 cluster size, 10 dense bytes read per NN apply. */
+int kb200_get_stats(kb200_handle h, double* stats, int64_t n);
+/* Gather / scatter maps the device uses, for bit-for-bit comparison with the reference's
+ * (0-based): adj_ptr (n_gamma+1), adj_dom / adj_loc (Σ n_gd): contributions to each interface
+ * node in ascending subdomain order. */
+int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom, int64_t* adj_loc);
+/* Average device time (ms) of `reps` back-to-back launches of one kernel on resident data:
+ * which = 0 Schur stream kernel, 1 NN GEMV kernel, 2 assembled-Schur GEMV kernel. */
+int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRYLOV_B200_H */

@@ -1,0 +1,243 @@
+"""ctypes binding of include/krylov_b200.h -- one Python call per C entry point, mirroring the
+``ccall`` stubs of julia/KrylovB200.jl one-to-one.  There is no CPU fallback: loading fails loudly
+when libkrylov_b200.so is missing and every call raises ``KB200Error`` on a non-zero status."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkrylov_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+SYMBOLS = [
+    "kb200_last_error", "kb200_create", "kb200_nccl_unique_id", "kb200_create_dist", "kb200_destroy",
+    "kb200_set_option", "kb200_set_topology", "kb200_local_range", "kb200_upload_local_blocks",
+    "kb200_upload_cholesky", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
+    "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
+    "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
+    "kb200_get_dense_local_schur", "kb200_pcg", "kb200_get_stats", "kb200_get_interface_maps",
+    "kb200_time_kernel",
+]
+
+
+class KB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libkrylov_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Timings(C.Structure):
+    _fields_ = [("solve_ms", C.c_double), ("schur_ms", C.c_double), ("nn_ms", C.c_double),
+                ("schur_launches", C.c_int64), ("nn_launches", C.c_int64),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+def build(force=False, with_nccl=True):
+    """Compile libkrylov_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "plan.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h")] + \
+        [os.path.join(_HERE, "..", "include", "krylov_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and \
+            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared"] + srcs + ["-o", LIB_PATH]
+    if with_nccl:
+        cmd += ["-DKB200_WITH_NCCL", "-lnccl"]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KB200Error(-100, f"{LIB_PATH} not built: run __graft_entry__.build() "
+                                   "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.kb200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise KB200Error(rc, lib().kb200_last_error().decode())
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _csc_julia(A):
+    """scipy CSC -> Julia SparseMatrixCSC arrays (Int64 1-based colptr / rowval, Float64 nzval)."""
+    A = A.tocsc()
+    A.sort_indices()
+    return _i64(A.indptr) + 1, _i64(A.indices) + 1, _f64(A.data)
+
+
+class Handle:
+    """Owns one kb200_handle."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+        self.h = C.c_void_p()
+        if world > 1:
+            buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+            _chk(lib().kb200_create_dist(device, rank, world, buf, C.byref(self.h)))
+        else:
+            _chk(lib().kb200_create(device, C.byref(self.h)))
+        self.n_gamma = 0
+        self.ndom = 0
+        self.n_I = None
+        self.n_gd = None
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        _chk(lib().kb200_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            _chk(lib().kb200_destroy(self.h))
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        _chk(lib().kb200_set_option(self.h, name.encode(), C.c_int64(int(value))))
+
+    def set_topology(self, n_I, n_gd, gamma_l2g_1based, node_gamma_cnt):
+        self.ndom = len(n_I)
+        self.n_gamma = len(node_gamma_cnt)
+        self.n_I, self.n_gd = _i64(n_I), _i64(n_gd)
+        maps = [_i64(g) for g in gamma_l2g_1based]
+        ptrs = (C.POINTER(C.c_int64) * self.ndom)(*[_p(m, C.c_int64) for m in maps])
+        cnt = _i64(node_gamma_cnt)
+        _chk(lib().kb200_set_topology(self.h, C.c_int64(self.ndom), C.c_int64(self.n_gamma),
+                                      _p(self.n_I, C.c_int64), _p(self.n_gd, C.c_int64), ptrs,
+                                      _p(cnt, C.c_int64)))
+
+    def local_range(self):
+        a, b = C.c_int64(), C.c_int64()
+        _chk(lib().kb200_local_range(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def upload_local_blocks(self, d, A_IG, A_GG):
+        gp, gi, gx = _csc_julia(A_IG)
+        hp, hi, hx = _csc_julia(A_GG)
+        _chk(lib().kb200_upload_local_blocks(self.h, C.c_int64(d), _p(gp, C.c_int64), _p(gi, C.c_int64),
+                                             _p(gx, C.c_double), _p(hp, C.c_int64), _p(hi, C.c_int64),
+                                             _p(hx, C.c_double)))
+
+    def upload_cholesky(self, d, perm0, L):
+        lp, li, lx = _csc_julia(L)
+        p1 = _i64(perm0) + 1
+        _chk(lib().kb200_upload_cholesky(self.h, C.c_int64(d), _p(p1, C.c_int64), _p(lp, C.c_int64),
+                                         _p(li, C.c_int64), _p(lx, C.c_double)))
+
+    def upload_nn_pinv(self, d, PiS):
+        M = np.asfortranarray(PiS, dtype=np.float64)
+        _chk(lib().kb200_upload_nn_pinv(self.h, C.c_int64(d), _p(M, C.c_double)))
+
+    def upload_dense_local_schur(self, d, Sd):
+        M = np.asfortranarray(Sd, dtype=np.float64)
+        _chk(lib().kb200_upload_dense_local_schur(self.h, C.c_int64(d), _p(M, C.c_double)))
+
+    def finalize(self):
+        _chk(lib().kb200_finalize(self.h))
+
+    def _apply(self, fn, x):
+        x = np.asfortranarray(x, dtype=np.float64)
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        if x.shape[0] != self.n_gamma:
+            raise ValueError("vector length must equal n_gamma")
+        y = np.empty_like(x, order="F")
+        _chk(fn(self.h, _p(x, C.c_double), _p(y, C.c_double), C.c_int64(nrhs)))
+        return y
+
+    def apply_schur(self, x):
+        return self._apply(lib().kb200_apply_schur, x)
+
+    def apply_schur_assembled(self, x):
+        return self._apply(lib().kb200_apply_schur_assembled, x)
+
+    def apply_nn(self, r):
+        return self._apply(lib().kb200_apply_nn, r)
+
+    def schur_rhs(self, b_I_concat, b_gamma):
+        bi, bg = _f64(b_I_concat), _f64(b_gamma)
+        out = np.empty(self.n_gamma)
+        _chk(lib().kb200_schur_rhs(self.h, _p(bi, C.c_double), _p(bg, C.c_double), _p(out, C.c_double)))
+        return out
+
+    def back_substitute(self, u_gamma, b_I_concat):
+        ug, bi = _f64(u_gamma), _f64(b_I_concat)
+        out = np.zeros(int(self.n_I.sum()))
+        _chk(lib().kb200_back_substitute(self.h, _p(ug, C.c_double), _p(bi, C.c_double), _p(out, C.c_double)))
+        return out
+
+    def assemble_local_schurs(self):
+        _chk(lib().kb200_assemble_local_schurs(self.h))
+
+    def get_dense_local_schur(self, d):
+        n = int(self.n_gd[d])
+        out = np.empty((n, n), order="F")
+        _chk(lib().kb200_get_dense_local_schur(self.h, C.c_int64(d), _p(out, C.c_double)))
+        return out
+
+    def pcg(self, b, x, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        """Returns (x, it, res_norm, Timings); x is also updated in place when it is a float64
+        contiguous array (reference semantics, cg.jl:97)."""
+        b = _f64(b)
+        xin = x
+        x = _f64(x)
+        n = self.n_gamma
+        cap = (maxit if maxit else n) + 1
+        res = np.empty(cap)
+        it = C.c_int64()
+        tm = Timings()
+        _chk(lib().kb200_pcg(self.h, _p(b, C.c_double), _p(x, C.c_double), C.c_int64(maxit),
+                             C.c_double(rtol), int(assembled), int(precond), C.byref(it),
+                             _p(res, C.c_double), C.byref(tm)))
+        if isinstance(xin, np.ndarray) and xin is not x:
+            xin[...] = x
+        return x, it.value, res[:it.value].copy(), tm
+
+    def stats(self):
+        s = np.zeros(16)
+        _chk(lib().kb200_get_stats(self.h, _p(s, C.c_double), C.c_int64(16)))
+        keys = ["nnz_L", "stream_entries", "stream_rows", "stream_slices", "stream_bytes", "max_levels",
+                "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes"]
+        return {k: s[i] for i, k in enumerate(keys)}
+
+    def interface_maps(self):
+        total = int(self.n_gd.sum())
+        ptr = np.empty(self.n_gamma + 1, dtype=np.int64)
+        dom = np.empty(total, dtype=np.int64)
+        loc = np.empty(total, dtype=np.int64)
+        _chk(lib().kb200_get_interface_maps(self.h, _p(ptr, C.c_int64), _p(dom, C.c_int64), _p(loc, C.c_int64)))
+        n = int(ptr[-1])
+        return ptr, dom[:n], loc[:n]
+
+    def time_kernel(self, which, reps=10):
+        ms = C.c_double()
+        _chk(lib().kb200_time_kernel(self.h, which, reps, C.byref(ms)))
+        return ms.value

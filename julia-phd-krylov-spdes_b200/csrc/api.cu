@@ -1,0 +1,1000 @@
+// libkrylov_b200.so: context, uploads, host analysis driver, operators and solvers behind the C ABI
+// declared in include/krylov_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#ifdef KB200_WITH_NCCL
+#include <nccl.h>
+#endif
+
+#include "../../include/krylov_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct KbError : std::runtime_error {
+  int code;
+  KbError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      throw KbError(KB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+#ifdef KB200_WITH_NCCL
+#define NCCL_TRY(expr)                                                                         \
+  do {                                                                                         \
+    ncclResult_t r__ = (expr);                                                                 \
+    if (r__ != ncclSuccess)                                                                    \
+      throw KbError(KB200_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(r__));      \
+  } while (0)
+#endif
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, size_t pad = 0) {
+    release();
+    n = count;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(1, count + pad) * sizeof(T)));
+    if (pad) CUDA_TRY(cudaMemset(p + count, 0, pad * sizeof(T)));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s, size_t pad = 0) {
+    alloc(v.size(), pad);
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct DomHost {
+  int64_t n_I = 0, n_gd = 0;
+  std::vector<int32_t> l2g;  // 0-based interface ids
+  kb::DomainIn in;           // perm, L, AIG, AGG
+  bool have_blocks = false, have_chol = false;
+  std::vector<double> PiS, Sd;  // row-major copies of the column-major inputs
+};
+
+void csc_from_julia(kb::Csc& m, int64_t nrow, int64_t ncol, const int64_t* colptr, const int64_t* rowval,
+                    const double* nzval, const char* what) {
+  if (!colptr || colptr[0] != 1) throw KbError(KB200_ERR_INPUT, std::string(what) + ": colptr must be 1-based");
+  const int64_t nnz = colptr[ncol] - 1;
+  if (nnz < 0 || nnz > INT32_MAX) throw KbError(KB200_ERR_INPUT, std::string(what) + ": bad nnz");
+  if (nnz > 0 && (!rowval || !nzval)) throw KbError(KB200_ERR_INPUT, std::string(what) + ": null arrays");
+  m.nrow = (int32_t)nrow;
+  m.ncol = (int32_t)ncol;
+  m.colptr.resize(ncol + 1);
+  for (int64_t j = 0; j <= ncol; ++j) {
+    if (j > 0 && colptr[j] < colptr[j - 1]) throw KbError(KB200_ERR_INPUT, std::string(what) + ": colptr not monotone");
+    m.colptr[j] = (int32_t)(colptr[j] - 1);
+  }
+  m.rowval.resize(nnz);
+  m.nzval.assign(nzval, nzval + nnz);
+  for (int64_t p = 0; p < nnz; ++p) {
+    const int64_t r = rowval[p] - 1;
+    if (r < 0 || r >= nrow) throw KbError(KB200_ERR_INPUT, std::string(what) + ": row index out of range");
+    m.rowval[p] = (int32_t)r;
+  }
+}
+
+}  // namespace
+
+struct kb200_ctx {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+#ifdef KB200_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  // options
+  int csize = 4, profile = 0, check_every = 8, min_block = -1;
+  // topology
+  int64_t ndom = 0, n_gamma = 0;
+  std::vector<DomHost> doms;
+  std::vector<int32_t> cnt;
+  int64_t d0 = 0, d1 = 0;  // local subdomain range
+  bool topo = false, finalized = false, have_pinv = false, have_sd = false;
+  // host-side tables of the local subdomains
+  std::vector<int64_t> I_base, G_base;          // per local subdomain (+1): offsets in concatenated vectors
+  std::vector<int64_t> I_base_global;           // per subdomain (+1): offsets in the caller's b_I_concat
+  std::vector<int64_t> mat_off;                 // dense block offsets (local)
+  std::vector<int32_t> adj_ptr, adj_src, adj_dom, adj_loc;
+  int max_gd = 0, smem_bytes = 0, n_cta = 0;
+  double stats[16] = {0};
+  // device pools
+  DevBuf<kb::CtaDesc> d_ctas;
+  DevBuf<kb::SliceHdr> d_slices;
+  DevBuf<kb::RowRec> d_rows;
+  DevBuf<double> d_vals;
+  DevBuf<uint16_t> d_cols;
+  DevBuf<int32_t> d_l2g, d_imap, d_adj_ptr, d_adj_src, d_ngd;
+  DevBuf<int64_t> d_G_base, d_mat_off;
+  DevBuf<double> d_pinv, d_sd, d_inv_cnt;
+  // device vectors
+  DevBuf<double> d_x, d_b, d_r, d_z, d_p, d_Ap, d_loc, d_bI, d_uI, d_partA, d_partB, d_partC, d_res;
+  DevBuf<kb::PcgState> d_state;
+  int nb = 0;  // blocks of the interface-vector kernels
+  int64_t launches = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  double* h_pinned = nullptr;  // staging for small reads
+};
+
+namespace {
+
+using Ctx = kb200_ctx;
+
+void require(bool ok, const char* msg) {
+  if (!ok) throw KbError(KB200_ERR_INVALID, msg);
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return KB200_OK;
+  } catch (const KbError& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return KB200_ERR_INTERNAL;
+  } catch (...) {
+    g_err = "unknown error";
+    return KB200_ERR_INTERNAL;
+  }
+}
+
+void use_device(Ctx* c) { CUDA_TRY(cudaSetDevice(c->device)); }
+
+bool is_local(const Ctx* c, int64_t d) { return d >= c->d0 && d < c->d1; }
+
+// ---- finalize: build plans, upload -------------------------------------------------------------
+void finalize(Ctx* c) {
+  if (c->finalized) return;
+  require(c->topo, "kb200_set_topology must be called first");
+  use_device(c);
+  const int64_t nloc = c->d1 - c->d0;
+  for (int64_t d = c->d0; d < c->d1; ++d)
+    require(c->doms[d].have_blocks && c->doms[d].have_chol,
+            "every local subdomain needs kb200_upload_local_blocks and kb200_upload_cholesky");
+  std::vector<kb::DomainPlan> plans(nloc);
+  kb::BuildOptions opt;
+  opt.csize = c->csize;
+  if (c->min_block >= 0) opt.min_block = c->min_block;
+  {
+    std::atomic<int64_t> next(0);
+    std::string first_err;
+    std::atomic<bool> failed(false);
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(nt);
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        for (;;) {
+          const int64_t k = next.fetch_add(1);
+          if (k >= nloc || failed.load()) break;
+          try {
+            kb::build_domain_plan(c->doms[c->d0 + k].in, opt, plans[k]);
+          } catch (const std::exception& e) {
+            errs[t] = "subdomain " + std::to_string(c->d0 + k) + ": " + e.what();
+            failed.store(true);
+          }
+        }
+      });
+    for (auto& t : th) t.join();
+    if (failed.load())
+      for (auto& e : errs)
+        if (!e.empty()) throw KbError(KB200_ERR_INPUT, e);
+  }
+  // offsets
+  c->I_base.assign(nloc + 1, 0);
+  c->G_base.assign(nloc + 1, 0);
+  c->mat_off.assign(nloc + 1, 0);
+  std::vector<uint64_t> so(nloc + 1, 0), ro(nloc + 1, 0), eo(nloc + 1, 0), mo(nloc + 1, 0);
+  int max_smem = 0, max_gd = 0, max_lev = 0, max_top = 0;
+  double nnzL = 0;
+  for (int64_t k = 0; k < nloc; ++k) {
+    const DomHost& dh = c->doms[c->d0 + k];
+    c->I_base[k + 1] = c->I_base[k] + dh.n_I;
+    c->G_base[k + 1] = c->G_base[k] + dh.n_gd;
+    c->mat_off[k + 1] = c->mat_off[k] + dh.n_gd * dh.n_gd;
+    so[k + 1] = so[k] + plans[k].slices.size();
+    ro[k + 1] = ro[k] + plans[k].rows.size();
+    eo[k + 1] = eo[k] + plans[k].vals.size();
+    mo[k + 1] = mo[k] + plans[k].imap.size();
+    for (auto& D : plans[k].ctas) max_smem = std::max(max_smem, D.smem_doubles);
+    max_gd = std::max<int>(max_gd, (int)dh.n_gd);
+    max_lev = std::max(max_lev, plans[k].max_levels);
+    max_top = std::max(max_top, plans[k].n_top);
+    nnzL += (double)plans[k].nnz_L;
+  }
+  c->max_gd = max_gd;
+  c->smem_bytes = max_smem * 8;
+  c->n_cta = (int)(nloc * c->csize);
+  // descriptors with global offsets
+  std::vector<kb::CtaDesc> ctas;
+  ctas.reserve(c->n_cta);
+  for (int64_t k = 0; k < nloc; ++k)
+    for (auto D : plans[k].ctas) {
+      D.dom = (int32_t)k;
+      D.l2g_off = c->G_base[k];
+      D.ownmap_off += (int64_t)mo[k];
+      D.topmap_off += (int64_t)mo[k];
+      D.I_base = c->I_base[k];
+      D.G_base = c->G_base[k];
+      D.out_g_off = 0;
+      for (int w = 0; w < kb::kWarps; ++w) {
+        D.slice_base[w] += so[k];
+        D.row_base[w] += ro[k];
+        D.ent_base[w] += eo[k];
+      }
+      ctas.push_back(D);
+    }
+  cudaStream_t s = c->stream;
+  c->d_ctas.upload(ctas, s);
+  const size_t epad = kb::kPrefetchAhead + 70000;
+  c->d_slices.alloc(so[nloc], 256);
+  c->d_rows.alloc(ro[nloc], 256);
+  c->d_vals.alloc(eo[nloc], epad);
+  c->d_cols.alloc(eo[nloc], epad);
+  c->d_imap.alloc(mo[nloc]);
+  for (int64_t k = 0; k < nloc; ++k) {
+    auto& P = plans[k];
+    if (!P.slices.empty())
+      CUDA_TRY(cudaMemcpyAsync(c->d_slices.p + so[k], P.slices.data(), P.slices.size() * sizeof(kb::SliceHdr),
+                               cudaMemcpyHostToDevice, s));
+    if (!P.rows.empty())
+      CUDA_TRY(cudaMemcpyAsync(c->d_rows.p + ro[k], P.rows.data(), P.rows.size() * sizeof(kb::RowRec),
+                               cudaMemcpyHostToDevice, s));
+    if (!P.vals.empty()) {
+      CUDA_TRY(cudaMemcpyAsync(c->d_vals.p + eo[k], P.vals.data(), P.vals.size() * 8, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(c->d_cols.p + eo[k], P.cols.data(), P.cols.size() * 2, cudaMemcpyHostToDevice, s));
+    }
+    if (!P.imap.empty())
+      CUDA_TRY(cudaMemcpyAsync(c->d_imap.p + mo[k], P.imap.data(), P.imap.size() * 4, cudaMemcpyHostToDevice, s));
+  }
+  // interface maps (local subdomains only), ascending subdomain order per interface node
+  {
+    const int64_t ng = c->n_gamma;
+    std::vector<int32_t> l2g_all;
+    l2g_all.reserve(c->G_base[nloc]);
+    c->adj_ptr.assign(ng + 1, 0);
+    for (int64_t k = 0; k < nloc; ++k)
+      for (int32_t g : c->doms[c->d0 + k].l2g) {
+        l2g_all.push_back(g);
+        c->adj_ptr[g + 1]++;
+      }
+    for (int64_t g = 0; g < ng; ++g) c->adj_ptr[g + 1] += c->adj_ptr[g];
+    c->adj_src.assign(c->adj_ptr[ng], 0);
+    c->adj_dom.assign(c->adj_ptr[ng], 0);
+    c->adj_loc.assign(c->adj_ptr[ng], 0);
+    std::vector<int32_t> fill(c->adj_ptr.begin(), c->adj_ptr.end() - 1);
+    for (int64_t k = 0; k < nloc; ++k) {
+      const auto& l2g = c->doms[c->d0 + k].l2g;
+      for (size_t l = 0; l < l2g.size(); ++l) {
+        const int32_t q = fill[l2g[l]]++;
+        c->adj_src[q] = (int32_t)(c->G_base[k] + (int64_t)l);
+        c->adj_dom[q] = (int32_t)(c->d0 + k);
+        c->adj_loc[q] = (int32_t)l;
+      }
+    }
+    c->d_l2g.upload(l2g_all, s);
+    c->d_adj_ptr.upload(c->adj_ptr, s);
+    c->d_adj_src.upload(c->adj_src, s);
+    std::vector<double> inv_cnt(ng);
+    for (int64_t g = 0; g < ng; ++g) inv_cnt[g] = 1.0 / (double)c->cnt[g];
+    c->d_inv_cnt.upload(inv_cnt, s);
+    std::vector<int32_t> ngd(nloc);
+    for (int64_t k = 0; k < nloc; ++k) ngd[k] = (int32_t)c->doms[c->d0 + k].n_gd;
+    c->d_ngd.upload(ngd, s);
+    std::vector<int64_t> gb(c->G_base.begin(), c->G_base.end()), mo2(c->mat_off.begin(), c->mat_off.end());
+    c->d_G_base.upload(gb, s);
+    c->d_mat_off.upload(mo2, s);
+  }
+  // dense blocks
+  auto upload_dense = [&](DevBuf<double>& buf, bool pinv) {
+    buf.alloc(c->mat_off[nloc]);
+    for (int64_t k = 0; k < nloc; ++k) {
+      const DomHost& dh = c->doms[c->d0 + k];
+      const auto& M = pinv ? dh.PiS : dh.Sd;
+      if (!M.empty())
+        CUDA_TRY(cudaMemcpyAsync(buf.p + c->mat_off[k], M.data(), M.size() * 8, cudaMemcpyHostToDevice, s));
+    }
+  };
+  if (c->have_pinv) upload_dense(c->d_pinv, true);
+  if (c->have_sd) upload_dense(c->d_sd, false);
+  // vectors
+  const int64_t ng = c->n_gamma;
+  c->nb = (int)((ng + kb::kVecThreads - 1) / kb::kVecThreads);
+  for (DevBuf<double>* v : {&c->d_x, &c->d_b, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap}) v->alloc(ng);
+  c->d_loc.alloc(c->G_base[nloc]);
+  c->d_bI.alloc(c->I_base[nloc]);
+  c->d_uI.alloc(c->I_base[nloc]);
+  c->d_partA.alloc(c->nb);
+  c->d_partB.alloc(c->nb);
+  c->d_partC.alloc(c->nb);
+  c->d_state.alloc(1);
+  CUDA_TRY(cudaMemsetAsync(c->d_state.p, 0, sizeof(kb::PcgState), s));
+  // kernel attributes
+  auto set_attr = [&](const void* fn) {
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
+    if (c->csize > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  };
+  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY>);
+  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS>);
+  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB>);
+  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT>);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  // stats
+  c->stats[0] = nnzL;
+  c->stats[1] = (double)eo[nloc];
+  c->stats[2] = (double)ro[nloc];
+  c->stats[3] = (double)so[nloc];
+  c->stats[4] = (double)eo[nloc] * 10.0 + (double)ro[nloc] * 16.0 + (double)so[nloc] * 8.0;
+  c->stats[5] = max_lev;
+  c->stats[6] = max_top;
+  c->stats[7] = c->smem_bytes;
+  c->stats[8] = c->n_cta;
+  c->stats[9] = c->csize;
+  c->stats[10] = (double)c->mat_off[nloc] * 8.0;
+  c->finalized = true;
+  // the per-subdomain host copies of L are no longer needed
+  for (int64_t d = c->d0; d < c->d1; ++d) {
+    c->doms[d].in.L = kb::Csc();
+  }
+}
+
+// ---- launches ----------------------------------------------------------------------------------
+template <int MODE>
+void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, double* out_loc, const int* done_at,
+                   int iter, int unit_col0 = 0, int ncols = 1) {
+  if (c->n_cta == 0) return;
+  kb::StreamParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.ctas = c->d_ctas.p;
+  P.slices = c->d_slices.p;
+  P.rows = c->d_rows.p;
+  P.vals = c->d_vals.p;
+  P.cols = c->d_cols.p;
+  P.l2g = c->d_l2g.p;
+  P.imap = c->d_imap.p;
+  P.x_gamma = x_gamma;
+  P.bI = bI;
+  P.uI = uI;
+  P.out_loc = out_loc;
+  P.sd_pool = c->d_sd.p;
+  P.sd_off = c->d_mat_off.p;
+  P.done_at = done_at;
+  P.iter = iter;
+  P.n_vals = c->d_vals.n;
+  P.n_rows = c->d_rows.n;
+  P.n_slices = c->d_slices.n;
+  P.unit_col0 = unit_col0;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)c->n_cta, (unsigned)ncols, 1);
+  cfg.blockDim = dim3(kb::kWarps * 32, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)c->smem_bytes;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)c->csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE>, P));
+  c->launches++;
+}
+
+void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double* out_loc, const int* done_at,
+                 int iter) {
+  const int64_t nloc = c->d1 - c->d0;
+  if (nloc == 0) return;
+  kb::GemvParams P;
+  P.mats = mats;
+  P.mat_off = c->d_mat_off.p;
+  P.n_gd = c->d_ngd.p;
+  P.G_base = c->d_G_base.p;
+  P.l2g = c->d_l2g.p;
+  P.x = x;
+  P.inv_cnt = scale ? c->d_inv_cnt.p : nullptr;
+  P.out_loc = out_loc;
+  P.done_at = done_at;
+  P.iter = iter;
+  dim3 grid((unsigned)((c->max_gd + kb::kGemvRowsPerCta - 1) / kb::kGemvRowsPerCta), (unsigned)nloc, 1);
+  kb::dense_gemv_kernel<<<grid, 256, (size_t)c->max_gd * 8, c->stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+}
+
+void allreduce(Ctx* c, double* v, int64_t n) {
+#ifdef KB200_WITH_NCCL
+  if (c->world > 1) NCCL_TRY(ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+#else
+  (void)c; (void)v; (void)n;
+#endif
+}
+
+// y = sum_d R_d' loc_d (+ base), optionally partial dot with q.  In multi-rank mode the interface
+// vector is all-reduced and the dot is taken afterwards so that every rank sees identical scalars.
+void assemble(Ctx* c, const double* loc, const double* base, double* y, const double* q, double* part,
+              const int* done_at, int iter) {
+  const int n = (int)c->n_gamma;
+  if (c->world == 1) {
+    kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base, y, q,
+                                                                 part, done_at, iter);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return;
+  }
+  kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
+                                                               c->rank == 0 ? base : nullptr, y, nullptr, nullptr,
+                                                               done_at, iter);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  allreduce(c, y, n);
+  if (q != nullptr) {
+    kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, y, q, part, done_at, iter);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+}
+
+enum OpKind { OP_SCHUR = 0, OP_SCHUR_DENSE = 1, OP_NN = 2 };
+
+struct KernelTimer {
+  Ctx* c;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[2];
+  size_t used = 0;
+  explicit KernelTimer(Ctx* ctx) : c(ctx) {}
+  cudaEvent_t get() {
+    if (used == c->ev_pool.size()) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[used++];
+  }
+  void begin(int which, cudaEvent_t& a) {
+    a = get();
+    CUDA_TRY(cudaEventRecord(a, c->stream));
+    (void)which;
+  }
+  void end(int which, cudaEvent_t a) {
+    cudaEvent_t b = get();
+    CUDA_TRY(cudaEventRecord(b, c->stream));
+    spans[which].emplace_back(a, b);
+  }
+  double total(int which) {
+    double t = 0;
+    for (auto& s : spans[which]) {
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, s.first, s.second));
+      t += ms;
+    }
+    return t;
+  }
+};
+
+// out = Op(in) on device interface vectors (no host traffic)
+void apply_op(Ctx* c, OpKind op, const double* in, double* out, const double* q, double* part, const int* done_at,
+              int iter, KernelTimer* kt) {
+  cudaEvent_t a = nullptr;
+  const bool timed = kt != nullptr && c->profile;
+  if (op == OP_SCHUR) {
+    if (timed) kt->begin(0, a);
+    launch_stream<kb::MODE_APPLY>(c, in, nullptr, nullptr, c->d_loc.p, done_at, iter);
+    if (timed) kt->end(0, a);
+  } else if (op == OP_SCHUR_DENSE) {
+    require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
+    if (timed) kt->begin(0, a);
+    launch_gemv(c, c->d_sd.p, in, false, c->d_loc.p, done_at, iter);
+    if (timed) kt->end(0, a);
+  } else {
+    require(c->have_pinv, "kb200_upload_nn_pinv was not called");
+    if (timed) kt->begin(1, a);
+    launch_gemv(c, c->d_pinv.p, in, true, c->d_loc.p, done_at, iter);
+    if (timed) kt->end(1, a);
+  }
+  assemble(c, c->d_loc.p, nullptr, out, q, part, done_at, iter);
+}
+
+void h2d(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = nullptr) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  if (t) t->h2d_bytes += n * 8;
+}
+void d2h(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = nullptr) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (t) t->d2h_bytes += n * 8;
+}
+
+void host_apply(Ctx* c, OpKind op, const double* x, double* y, int64_t nrhs) {
+  require(x && y && nrhs >= 1, "null vector or nrhs < 1");
+  finalize(c);
+  use_device(c);
+  const int64_t n = c->n_gamma;
+  for (int64_t k = 0; k < nrhs; ++k) {
+    h2d(c, c->d_x.p, x + k * n, n);
+    apply_op(c, op, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, nullptr);
+    d2h(c, y + k * n, c->d_Ap.p, n);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+}
+
+// Gather the local part of the caller's concatenated interior vector / scatter it back.
+void bI_to_device(Ctx* c, const double* b_I_concat) {
+  const int64_t off = c->I_base_global[c->d0], len = c->I_base_global[c->d1] - off;
+  h2d(c, c->d_bI.p, b_I_concat + off, len);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* kb200_last_error(void) { return g_err.c_str(); }
+
+int kb200_create(int device_id, kb200_handle* out) {
+  return guarded([&]() {
+    require(out != nullptr, "null handle pointer");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0 || device_id < 0 || device_id >= ndev)
+      throw KbError(KB200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    std::unique_ptr<Ctx> c(new Ctx());
+    c->device = device_id;
+    CUDA_TRY(cudaSetDevice(device_id));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev_a));
+    CUDA_TRY(cudaEventCreate(&c->ev_b));
+    CUDA_TRY(cudaMallocHost(&c->h_pinned, 4096));
+    *out = c.release();
+  });
+}
+
+int kb200_nccl_unique_id(void* out128) {
+  return guarded([&]() {
+#ifdef KB200_WITH_NCCL
+    require(out128 != nullptr, "null buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(ncclGetUniqueId(&id));
+    std::memcpy(out128, &id, 128);
+#else
+    (void)out128;
+    throw KbError(KB200_ERR_NCCL, "library built without NCCL");
+#endif
+  });
+}
+
+int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, kb200_handle* out) {
+  int rc = kb200_create(device_id, out);
+  if (rc != KB200_OK) return rc;
+  return guarded([&]() {
+    Ctx* c = *out;
+    require(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+    c->rank = rank;
+    c->world = world;
+    if (world > 1) {
+#ifdef KB200_WITH_NCCL
+      require(nccl_id != nullptr, "null nccl id");
+      ncclUniqueId id;
+      std::memcpy(&id, nccl_id, 128);
+      NCCL_TRY(ncclCommInitRank(&c->comm, world, id, rank));
+#else
+      (void)nccl_id;
+      throw KbError(KB200_ERR_NCCL, "library built without NCCL");
+#endif
+    }
+  });
+}
+
+int kb200_destroy(kb200_handle h) {
+  return guarded([&]() {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+#ifdef KB200_WITH_NCCL
+    if (h->comm) ncclCommDestroy(h->comm);
+#endif
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    cudaStream_t s = h->stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+  });
+}
+
+int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
+  return guarded([&]() {
+    require(h && name, "null argument");
+    const std::string k(name);
+    if (k == "csize") {
+      require(!h->finalized, "csize must be set before the first operation");
+      require(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "csize must be 1, 2, 4, 8 or 16");
+      h->csize = (int)value;
+    } else if (k == "min_block") {
+      require(!h->finalized, "min_block must be set before the first operation");
+      h->min_block = (int)value;
+    } else if (k == "profile") {
+      h->profile = value != 0;
+    } else if (k == "check_every") {
+      require(value >= 1, "check_every must be >= 1");
+      h->check_every = (int)value;
+    } else {
+      throw KbError(KB200_ERR_INVALID, "unknown option " + k);
+    }
+  });
+}
+
+int kb200_set_topology(kb200_handle h, int64_t ndom, int64_t n_gamma, const int64_t* n_I, const int64_t* n_gd,
+                       const int64_t* const* gamma_l2g, const int64_t* node_gamma_cnt) {
+  return guarded([&]() {
+    require(h && n_I && n_gd && gamma_l2g && node_gamma_cnt, "null argument");
+    require(!h->topo, "topology already set");
+    require(ndom >= 1 && n_gamma >= 0 && n_gamma < INT32_MAX, "bad sizes");
+    h->ndom = ndom;
+    h->n_gamma = n_gamma;
+    h->doms.assign(ndom, DomHost());
+    h->cnt.resize(n_gamma);
+    std::vector<int32_t> seen(n_gamma, 0);
+    h->I_base_global.assign(ndom + 1, 0);
+    for (int64_t d = 0; d < ndom; ++d) {
+      DomHost& dh = h->doms[d];
+      require(n_I[d] >= 0 && n_gd[d] >= 0 && n_I[d] < INT32_MAX, "bad subdomain size");
+      dh.n_I = n_I[d];
+      dh.n_gd = n_gd[d];
+      h->I_base_global[d + 1] = h->I_base_global[d] + n_I[d];
+      dh.l2g.resize(n_gd[d]);
+      for (int64_t l = 0; l < n_gd[d]; ++l) {
+        const int64_t g = gamma_l2g[d][l] - 1;
+        if (g < 0 || g >= n_gamma) throw KbError(KB200_ERR_INPUT, "gamma_l2g entry out of range (must be 1-based)");
+        dh.l2g[l] = (int32_t)g;
+        seen[g]++;
+      }
+    }
+    for (int64_t g = 0; g < n_gamma; ++g) {
+      if (node_gamma_cnt[g] != seen[g])
+        throw KbError(KB200_ERR_INPUT, "node_gamma_cnt disagrees with the number of subdomains touching a node");
+      h->cnt[g] = (int32_t)node_gamma_cnt[g];
+    }
+    // contiguous, equal-count shards
+    h->d0 = (ndom * h->rank) / h->world;
+    h->d1 = (ndom * (h->rank + 1)) / h->world;
+    h->topo = true;
+  });
+}
+
+int kb200_local_range(kb200_handle h, int64_t* d0, int64_t* d1) {
+  return guarded([&]() {
+    require(h && d0 && d1 && h->topo, "topology not set");
+    *d0 = h->d0;
+    *d1 = h->d1;
+  });
+}
+
+int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colptr, const int64_t* AIG_rowval,
+                              const double* AIG_nzval, const int64_t* AGG_colptr, const int64_t* AGG_rowval,
+                              const double* AGG_nzval) {
+  return guarded([&]() {
+    require(h && h->topo, "topology not set");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    require(!h->finalized, "already finalized");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    dh.in.n_I = (int32_t)dh.n_I;
+    dh.in.n_gd = (int32_t)dh.n_gd;
+    csc_from_julia(dh.in.AIG, dh.n_I, dh.n_gd, AIG_colptr, AIG_rowval, AIG_nzval, "A_IG");
+    csc_from_julia(dh.in.AGG, dh.n_gd, dh.n_gd, AGG_colptr, AGG_rowval, AGG_nzval, "A_GG");
+    dh.have_blocks = true;
+  });
+}
+
+int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const int64_t* L_colptr,
+                          const int64_t* L_rowval, const double* L_nzval) {
+  return guarded([&]() {
+    require(h && h->topo, "topology not set");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    require(!h->finalized, "already finalized");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    require(perm != nullptr || dh.n_I == 0, "null perm");
+    dh.in.perm.resize(dh.n_I);
+    std::vector<char> hit(dh.n_I, 0);
+    for (int64_t k = 0; k < dh.n_I; ++k) {
+      const int64_t v = perm[k] - 1;
+      if (v < 0 || v >= dh.n_I || hit[v]) throw KbError(KB200_ERR_INPUT, "perm is not a 1-based permutation");
+      hit[v] = 1;
+      dh.in.perm[k] = (int32_t)v;
+    }
+    csc_from_julia(dh.in.L, dh.n_I, dh.n_I, L_colptr, L_rowval, L_nzval, "L");
+    dh.have_chol = true;
+  });
+}
+
+static void store_dense(Ctx* h, int64_t d, const double* M, bool pinv) {
+  require(h && h->topo, "topology not set");
+  require(d >= 0 && d < h->ndom, "subdomain index out of range");
+  if (!is_local(h, d)) return;
+  DomHost& dh = h->doms[d];
+  require(M != nullptr || dh.n_gd == 0, "null matrix");
+  const int64_t n = dh.n_gd;
+  std::vector<double>& dst = pinv ? dh.PiS : dh.Sd;
+  dst.resize(n * n);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t j = 0; j < n; ++j) dst[i * n + j] = M[i + j * n];  // column-major -> row-major
+  if (pinv) h->have_pinv = true; else h->have_sd = true;
+  if (h->finalized) {
+    use_device(h);
+    DevBuf<double>& buf = pinv ? h->d_pinv : h->d_sd;
+    const int64_t nloc = h->d1 - h->d0;
+    if (buf.p == nullptr) {
+      buf.alloc(h->mat_off[nloc]);
+      CUDA_TRY(cudaMemsetAsync(buf.p, 0, (size_t)h->mat_off[nloc] * 8, h->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(buf.p + h->mat_off[d - h->d0], dst.data(), dst.size() * 8, cudaMemcpyHostToDevice,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+}
+
+int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS) {
+  return guarded([&]() { store_dense(h, d, PiS, true); });
+}
+int kb200_upload_dense_local_schur(kb200_handle h, int64_t d, const double* Sd) {
+  return guarded([&]() { store_dense(h, d, Sd, false); });
+}
+
+int kb200_finalize(kb200_handle h) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    finalize(h);
+  });
+}
+
+int kb200_apply_schur(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  return guarded([&]() { require(h, "null handle"); host_apply(h, OP_SCHUR, x, y, nrhs); });
+}
+int kb200_apply_schur_assembled(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  return guarded([&]() { require(h, "null handle"); host_apply(h, OP_SCHUR_DENSE, x, y, nrhs); });
+}
+int kb200_apply_nn(kb200_handle h, const double* r, double* z, int64_t nrhs) {
+  return guarded([&]() { require(h, "null handle"); host_apply(h, OP_NN, r, z, nrhs); });
+}
+
+int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_gamma, double* b_schur) {
+  return guarded([&]() {
+    require(h && b_I_concat && b_gamma && b_schur, "null argument");
+    finalize(h);
+    use_device(h);
+    const int64_t n = h->n_gamma;
+    bI_to_device(h, b_I_concat);
+    h2d(h, h->d_b.p, b_gamma, n);
+    launch_stream<kb::MODE_RHS>(h, nullptr, h->d_bI.p, nullptr, h->d_loc.p, nullptr, 0);
+    assemble(h, h->d_loc.p, h->d_b.p, h->d_Ap.p, nullptr, nullptr, nullptr, 0);
+    d2h(h, b_schur, h->d_Ap.p, n);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b_I_concat, double* u_I_concat) {
+  return guarded([&]() {
+    require(h && u_gamma && b_I_concat && u_I_concat, "null argument");
+    finalize(h);
+    use_device(h);
+    bI_to_device(h, b_I_concat);
+    h2d(h, h->d_x.p, u_gamma, h->n_gamma);
+    launch_stream<kb::MODE_BACKSUB>(h, h->d_x.p, h->d_bI.p, h->d_uI.p, nullptr, nullptr, 0);
+    const int64_t off = h->I_base_global[h->d0], len = h->I_base_global[h->d1] - off;
+    d2h(h, u_I_concat + off, h->d_uI.p, len);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int kb200_assemble_local_schurs(kb200_handle h) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    finalize(h);
+    use_device(h);
+    const int64_t nloc = h->d1 - h->d0;
+    if (h->d_sd.p == nullptr) h->d_sd.alloc(h->mat_off[nloc]);
+    const int chunk = 64;
+    for (int col0 = 0; col0 < h->max_gd; col0 += chunk) {
+      const int nc = std::min(chunk, h->max_gd - col0);
+      launch_stream<kb::MODE_UNIT>(h, nullptr, nullptr, nullptr, nullptr, nullptr, 0, col0, nc);
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // Symmetric(): mirror the upper triangle (EllipticPdeDomainDecomposition.jl:692), then keep a
+    // row-major copy on the device.  Done on the host: setup path, n_gd^2 per subdomain.
+    std::vector<double> buf;
+    for (int64_t k = 0; k < nloc; ++k) {
+      DomHost& dh = h->doms[h->d0 + k];
+      const int64_t n = dh.n_gd;
+      buf.resize(n * n);
+      CUDA_TRY(cudaMemcpy(buf.data(), h->d_sd.p + h->mat_off[k], (size_t)(n * n) * 8, cudaMemcpyDeviceToHost));
+      dh.Sd.resize(n * n);
+      for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j < n; ++j) {
+          const double v = (i <= j) ? buf[i + j * n] : buf[j + i * n];  // column-major device block
+          dh.Sd[i * n + j] = v;                                          // symmetric => layout-free
+        }
+      CUDA_TRY(cudaMemcpy(h->d_sd.p + h->mat_off[k], dh.Sd.data(), (size_t)(n * n) * 8, cudaMemcpyHostToDevice));
+    }
+    h->have_sd = true;
+  });
+}
+
+int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out) {
+  return guarded([&]() {
+    require(h && Sd_out && h->topo, "null argument");
+    require(is_local(h, d), "subdomain is not local to this handle");
+    const DomHost& dh = h->doms[d];
+    require((int64_t)dh.Sd.size() == dh.n_gd * dh.n_gd, "dense local Schur not available");
+    const int64_t n = dh.n_gd;
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t j = 0; j < n; ++j) Sd_out[i + j * n] = dh.Sd[i * n + j];
+  });
+}
+
+int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled, int precond,
+              int64_t* it_out, double* res_norm, kb200_timings* tm) {
+  return guarded([&]() {
+    require(h && b && x && it_out && res_norm, "null argument");
+    finalize(h);
+    use_device(h);
+    Ctx* c = h;
+    const int n = (int)c->n_gamma;
+    if (maxit == 0) maxit = n;
+    require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+    kb200_timings T;
+    std::memset(&T, 0, sizeof(T));
+    const int64_t launches0 = c->launches;
+    const OpKind A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
+    if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
+    KernelTimer kt(c);
+    kb::PcgState* st = c->d_state.p;
+    const int* done_at = &st->done_at;
+    h2d(c, c->d_b.p, b, n, &T);
+    h2d(c, c->d_x.p, x, n, &T);
+    CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+    // r = b - A x ; z = M \ r ; p = z                                                 (cg.jl:83-90)
+    apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
+    kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p,
+                                                                          c->d_partA.p, c->d_partB.p);
+    c->launches++;
+    if (precond) {
+      apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, nullptr, 0, &kt);
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, nullptr, 0);
+      c->launches++;
+    }
+    kb::pcg_init_direction_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(
+        n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p, c->d_partC.p, st, c->d_res.p, rtol, (int)maxit);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int* h_flag = reinterpret_cast<int*>(c->h_pinned);
+    int k = 1;
+    bool done = false;
+    while (!done) {
+      const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
+      for (; k < kend; ++k) {
+        // Ap = A p ; d = p.Ap                                                          (cg.jl:93-94)
+        apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);
+        kb::pcg_update_xr_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p,
+                                                                          c->d_r.p, c->d_partA.p, c->d_partB.p, st, k);
+        c->launches++;
+        // z = M \ r ; rTz = r.z                                                        (cg.jl:100-101)
+        if (precond) {
+          apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, done_at, k, &kt);
+        } else {
+          CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+          kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, done_at, k);
+          c->launches++;
+        }
+        kb::pcg_update_p_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p,
+                                                                         c->d_partC.p, st, c->d_res.p, nullptr, k);
+        c->launches++;
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(h_flag, &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      // h_flag = {it, done_at, maxit, fail}
+      done = (h_flag[1] != INT_MAX) || (h_flag[3] != 0) || (k >= maxit);
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+    const int it = h_flag[0];
+    const int fail = h_flag[3];
+    d2h(c, x, c->d_x.p, n, &T);
+    d2h(c, res_norm, c->d_res.p, it, &T);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *it_out = it;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+    T.solve_ms = ms;
+    if (c->profile) {
+      T.schur_ms = kt.total(0);
+      T.nn_ms = kt.total(1);
+      T.schur_launches = (int64_t)kt.spans[0].size();
+      T.nn_launches = (int64_t)kt.spans[1].size();
+    }
+    T.kernel_launches = c->launches - launches0;
+    if (tm) *tm = T;
+    if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+  });
+}
+
+int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
+  return guarded([&]() {
+    require(h && stats, "null argument");
+    finalize(h);
+    for (int64_t i = 0; i < n && i < 16; ++i) stats[i] = h->stats[i];
+  });
+}
+
+int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom, int64_t* adj_loc) {
+  return guarded([&]() {
+    require(h && adj_ptr && adj_dom && adj_loc, "null argument");
+    finalize(h);
+    for (size_t i = 0; i < h->adj_ptr.size(); ++i) adj_ptr[i] = h->adj_ptr[i];
+    for (size_t i = 0; i < h->adj_dom.size(); ++i) {
+      adj_dom[i] = h->adj_dom[i];
+      adj_loc[i] = h->adj_loc[i];
+    }
+  });
+}
+
+int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
+  return guarded([&]() {
+    require(h && avg_ms && reps >= 1, "bad argument");
+    finalize(h);
+    use_device(h);
+    Ctx* c = h;
+    auto once = [&]() {
+      if (which == 0) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, nullptr, 0);
+      else if (which == 1) launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, nullptr, 0);
+      else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, nullptr, 0);
+    };
+    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd), "kernel inputs not uploaded");
+    once();
+    CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+    for (int i = 0; i < reps; ++i) once();
+    CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+    *avg_ms = ms / reps;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,608 @@
+// Host-side plan builder: see plan.h for the design.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <queue>
+#include <stdexcept>
+
+namespace kb {
+namespace {
+
+struct TmpRow {
+  uint16_t dst;
+  double diag;
+  int32_t level;
+  int32_t kind;  // 0: S[dst] = (S[dst] - sign*acc)/diag ; 1: S[dst] = -sign*acc/diag
+  uint32_t ebeg;  // into the builder's scratch entry arrays
+  uint32_t len;
+};
+
+struct Scratch {
+  std::vector<uint16_t> cols;
+  std::vector<double> vals;
+};
+
+struct WarpStream {
+  std::vector<SliceHdr> slices;
+  std::vector<RowRec> rows;
+  std::vector<double> vals;
+  std::vector<uint16_t> cols;
+};
+
+inline int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+inline int ilog2(int p) {
+  int l = 0;
+  while ((1 << l) < p) ++l;
+  return l;
+}
+
+// Distribute the rows of one section over the warps of a CTA and append them to the streams.
+void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, int target_k, WarpStream* ws,
+                  uint32_t* sec_begin, uint32_t* sec_end, uint32_t& nlevels) {
+  for (int w = 0; w < kWarps; ++w) sec_begin[w] = (uint32_t)ws[w].slices.size();
+  int maxlev = -1;
+  for (auto& r : rows) maxlev = std::max(maxlev, r.level);
+  nlevels = (uint32_t)(maxlev + 1);
+  if (!rows.empty()) {
+    // stable order: by level, then by decreasing length
+    std::vector<uint32_t> ord(rows.size());
+    std::iota(ord.begin(), ord.end(), 0u);
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+      if (rows[a].level != rows[b].level) return rows[a].level < rows[b].level;
+      return rows[a].len > rows[b].len;
+    });
+    for (auto& r : rows)
+      if (r.level < 0) throw std::runtime_error("internal: negative level");
+    size_t i = 0;
+    std::vector<uint32_t> wrows[kWarps];
+    while (i < ord.size()) {
+      size_t j = i;
+      int lev = rows[ord[i]].level;
+      while (j < ord.size() && rows[ord[j]].level == lev) ++j;
+      // longest-processing-time assignment of rows [i, j) to warps (cost = entries + overhead)
+      uint64_t load[kWarps] = {0};
+      for (int w = 0; w < kWarps; ++w) wrows[w].clear();
+      for (size_t k = i; k < j; ++k) {
+        int best = 0;
+        for (int w = 1; w < kWarps; ++w)
+          if (load[w] < load[best]) best = w;
+        load[best] += rows[ord[k]].len + 8;
+        wrows[best].push_back(ord[k]);
+      }
+      for (int w = 0; w < kWarps; ++w) {
+        auto& lst = wrows[w];
+        // rows of one slice share the update kind
+        std::stable_sort(lst.begin(), lst.end(), [&](uint32_t a, uint32_t b) { return rows[a].kind < rows[b].kind; });
+        size_t p = 0;
+        while (p < lst.size()) {
+          int remaining = 0;
+          while (p + remaining < lst.size() && rows[lst[p + remaining]].kind == rows[lst[p]].kind) ++remaining;
+          int len = (int)rows[lst[p]].len;
+          int t_len = std::min(32, pow2ceil((len + target_k - 1) / std::max(1, target_k)));
+          int t_fill = std::max(1, 32 / pow2ceil(remaining));
+          int t = std::max(t_len, std::min(t_fill, pow2ceil(std::max(1, len))));
+          t = std::min(32, std::max(1, t));
+          int cap = 32 / t;
+          int take = std::min(cap, remaining);
+          SliceHdr h;
+          h.row0 = (uint32_t)ws[w].rows.size();
+          h.level = (uint16_t)lev;
+          h.tlog2 = (uint8_t)(ilog2(t) | (rows[lst[p]].kind ? 0x80 : 0));
+          h.nrows = (uint8_t)take;
+          ws[w].slices.push_back(h);
+          for (int q = 0; q < take; ++q) {
+            const TmpRow& tr = rows[lst[p + q]];
+            RowRec rr;
+            rr.ebeg = (uint32_t)ws[w].vals.size();
+            rr.len = (uint16_t)tr.len;
+            rr.dst = tr.dst;
+            rr.diag = tr.diag;
+            ws[w].rows.push_back(rr);
+            ws[w].vals.insert(ws[w].vals.end(), sc.vals.begin() + tr.ebeg,
+                              sc.vals.begin() + tr.ebeg + tr.len);
+            ws[w].cols.insert(ws[w].cols.end(), sc.cols.begin() + tr.ebeg,
+                              sc.cols.begin() + tr.ebeg + tr.len);
+          }
+          p += take;
+        }
+      }
+      i = j;
+    }
+  }
+  for (int w = 0; w < kWarps; ++w) sec_end[w] = (uint32_t)ws[w].slices.size();
+}
+
+}  // namespace
+
+void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& out) {
+  const int n = in.n_I, ng = in.n_gd, C = std::max(1, opt.csize);
+  const Csc& L = in.L;
+  if (L.nrow != n || L.ncol != n) throw std::runtime_error("L has wrong dimensions");
+  if ((int)in.perm.size() != n) throw std::runtime_error("perm has wrong length");
+
+  // ---- structure of L: diagonal, strictly-lower CSR, elimination tree -------------------------
+  std::vector<double> diag(n);
+  std::vector<int32_t> rptr(n + 1, 0);
+  for (int j = 0; j < n; ++j) {
+    int p0 = L.colptr[j], p1 = L.colptr[j + 1];
+    if (p0 >= p1 || L.rowval[p0] != j) throw std::runtime_error("L: missing diagonal entry");
+    diag[j] = L.nzval[p0];
+    if (!(diag[j] > 0.0)) throw std::runtime_error("L: non-positive diagonal");
+    for (int p = p0 + 1; p < p1; ++p) {
+      if (L.rowval[p] <= L.rowval[p - 1] || L.rowval[p] >= n)
+        throw std::runtime_error("L: column rows must be sorted, unique and below the diagonal");
+      rptr[L.rowval[p] + 1]++;
+    }
+  }
+  for (int i = 0; i < n; ++i) rptr[i + 1] += rptr[i];
+  const int64_t nnzl = rptr[n];
+  std::vector<int32_t> rcol(nnzl);
+  std::vector<double> rval(nnzl);
+  {
+    std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+    for (int j = 0; j < n; ++j)
+      for (int p = L.colptr[j] + 1; p < L.colptr[j + 1]; ++p) {
+        int i = L.rowval[p];
+        rcol[fill[i]] = j;
+        rval[fill[i]] = L.nzval[p];
+        fill[i]++;
+      }
+  }
+  std::vector<int32_t> parent(n, -1);
+  for (int j = 0; j < n; ++j)
+    if (L.colptr[j] + 1 < L.colptr[j + 1]) parent[j] = L.rowval[L.colptr[j] + 1];
+
+  // ---- subtree weights -------------------------------------------------------------------------
+  std::vector<int64_t> wt(n), sub(n);
+  for (int j = 0; j < n; ++j) {
+    wt[j] = (int64_t)(rptr[j + 1] - rptr[j]) + (L.colptr[j + 1] - L.colptr[j] - 1) + 4;
+    sub[j] = wt[j];
+  }
+  for (int j = 0; j < n; ++j)
+    if (parent[j] >= 0) sub[parent[j]] += sub[j];
+  std::vector<int32_t> cptr(n + 1, 0), child(n > 0 ? n : 1);
+  for (int j = 0; j < n; ++j)
+    if (parent[j] >= 0) cptr[parent[j] + 1]++;
+  for (int j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+  {
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int j = 0; j < n; ++j)
+      if (parent[j] >= 0) child[fill[parent[j]]++] = j;
+  }
+
+  // ---- cut the forest into subtrees (bins) + top -----------------------------------------------
+  std::vector<char> is_top(n, 0);
+  std::vector<int32_t> bin_of_root(n, -1);
+  {
+    std::vector<int32_t> Q;
+    for (int j = 0; j < n; ++j)
+      if (parent[j] < 0) Q.push_back(j);
+    auto lpt = [&](const std::vector<int32_t>& q, std::vector<int32_t>* assign) -> int64_t {
+      std::vector<int32_t> o(q.size());
+      std::iota(o.begin(), o.end(), 0);
+      std::sort(o.begin(), o.end(), [&](int a, int b) {
+        if (sub[q[a]] != sub[q[b]]) return sub[q[a]] > sub[q[b]];
+        return q[a] < q[b];
+      });
+      std::vector<int64_t> load(C, 0);
+      if (assign) assign->assign(q.size(), 0);
+      for (int k : o) {
+        int best = 0;
+        for (int c = 1; c < C; ++c)
+          if (load[c] < load[best]) best = c;
+        load[best] += sub[q[k]];
+        if (assign) (*assign)[k] = best;
+      }
+      return *std::max_element(load.begin(), load.end());
+    };
+    if (C > 1 && n > 0) {
+      // cost of a cut = heaviest bin + serial top work; explore successive splits of the heaviest
+      // subtree and keep the best cut seen
+      std::vector<int32_t> order;  // nodes moved to top, in order
+      int64_t top_w = 0;
+      int64_t best_cost = lpt(Q, nullptr);
+      size_t best_k = 0;
+      std::vector<int32_t> Qw = Q;
+      const size_t max_splits = (size_t)std::min<int64_t>(n / 4, 4096);
+      for (size_t step = 0; step < max_splits; ++step) {
+        size_t hi = 0;
+        for (size_t k = 1; k < Qw.size(); ++k)
+          if (sub[Qw[k]] > sub[Qw[hi]]) hi = k;
+        int r = Qw[hi];
+        if (cptr[r + 1] == cptr[r]) break;  // heaviest subtree is a single node
+        Qw[hi] = Qw.back();
+        Qw.pop_back();
+        for (int p = cptr[r]; p < cptr[r + 1]; ++p) Qw.push_back(child[p]);
+        order.push_back(r);
+        // a top node costs its row and column once per sweep, processed by rank 0 alone while
+        // the other CTAs wait (over-estimate: its entries in subtree columns run in parallel)
+        top_w += 2 * wt[r];
+        if (top_w >= best_cost) break;  // cannot improve any more
+        if (cptr[r + 1] - cptr[r] >= 2) {  // the cost only drops at branching nodes
+          int64_t cost = lpt(Qw, nullptr) + top_w;
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_k = order.size();
+          }
+        }
+      }
+      for (size_t k = 0; k < best_k; ++k) is_top[order[k]] = 1;
+      Q.clear();
+      for (int j = 0; j < n; ++j)
+        if (!is_top[j] && (parent[j] < 0 || is_top[parent[j]])) Q.push_back(j);
+    }
+    std::vector<int32_t> assign;
+    lpt(Q, &assign);
+    for (size_t k = 0; k < Q.size(); ++k) bin_of_root[Q[k]] = assign[k];
+  }
+  std::vector<int32_t> owner(n);  // CTA rank, or -1 for top
+  for (int j = n - 1; j >= 0; --j) {
+    if (is_top[j]) owner[j] = -1;
+    else if (parent[j] < 0 || is_top[parent[j]]) owner[j] = bin_of_root[j];
+    else owner[j] = owner[parent[j]];
+  }
+
+  // ---- supernode chains with dense diagonal blocks -> inverted blocks ---------------------------
+  // A chain a..b of the elimination tree with parent[j] = j+1 and nested column structures has a
+  // dense lower-triangular diagonal block D; with Dinv = D^{-1} precomputed, the b-a+1 dependent
+  // rows collapse into two parallel steps (off-block sums, then a dense triangular product), in
+  // both sweeps.  blk[i] = block index or -1.
+  std::vector<int32_t> blk(n, -1);
+  struct Block { int a, b; std::vector<double> Dinv; };  // Dinv row-major s x s (lower)
+  std::vector<Block> blocks;
+  if (opt.min_block > 0) {
+    auto ccount = [&](int j) { return L.colptr[j + 1] - L.colptr[j]; };
+    int a = 0;
+    while (a < n) {
+      int b = a;
+      while (b + 1 < n && parent[b] == b + 1 && ccount(b) == ccount(b + 1) + 1 && owner[b] == owner[b + 1] &&
+             (b + 1 - a + 1) <= opt.max_block)
+        ++b;
+      const int sz = b - a + 1;
+      bool ok = sz >= opt.min_block;
+      if (ok)
+        for (int j = a; j <= b && ok; ++j)
+          for (int t = 0; t <= b - j; ++t)
+            if (L.rowval[L.colptr[j] + t] != j + t) { ok = false; break; }
+      if (ok) {
+        Block B;
+        B.a = a;
+        B.b = b;
+        std::vector<double> D((size_t)sz * sz, 0.0);
+        for (int j = a; j <= b; ++j)
+          for (int t = 0; t <= b - j; ++t) D[(size_t)(j + t - a) * sz + (j - a)] = L.nzval[L.colptr[j] + t];
+        B.Dinv.assign((size_t)sz * sz, 0.0);
+        for (int c0 = 0; c0 < sz; ++c0) {
+          B.Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
+          for (int i = c0 + 1; i < sz; ++i) {
+            double acc = 0.0;
+            for (int k = c0; k < i; ++k) acc += D[(size_t)i * sz + k] * B.Dinv[(size_t)k * sz + c0];
+            B.Dinv[(size_t)i * sz + c0] = -acc / D[(size_t)i * sz + i];
+          }
+        }
+        for (int j = a; j <= b; ++j) blk[j] = (int)blocks.size();
+        blocks.push_back(std::move(B));
+      }
+      a = b + 1;
+    }
+  }
+
+  // ---- dependency levels -----------------------------------------------------------------------
+  // fe[i] / be[i]: level at which the (last) step producing x_i / v_i runs; a value is available
+  // to steps of strictly higher levels.  For a block, step A (off-block sums) runs at level e-1 and
+  // step B (Dinv product) at level e.
+  std::vector<int32_t> fe(n, 0), be(n, 0);
+  auto same_scope = [&](int i, int j) { return (owner[i] >= 0) == (owner[j] >= 0); };
+  for (int i = 0; i < n; ++i) {
+    if (blk[i] >= 0 && i != blocks[blk[i]].a) continue;  // handled with the block head
+    const int lo = i, hi = blk[i] >= 0 ? blocks[blk[i]].b : i;
+    int l = 0;
+    for (int r = lo; r <= hi; ++r)
+      for (int p = rptr[r]; p < rptr[r + 1]; ++p) {
+        const int j = rcol[p];
+        if (j >= lo) continue;  // inside the block: absorbed by Dinv
+        if (same_scope(r, j)) {
+          if (owner[r] >= 0 && owner[j] != owner[r])
+            throw std::runtime_error("internal: row dependency crosses subtrees");
+          l = std::max(l, fe[j] + 1);
+        } else if (owner[r] >= 0) {
+          throw std::runtime_error("internal: subtree row depends on a top node");
+        }
+      }
+    if (blk[i] >= 0) l += 1;  // step A at l, step B at l+1
+    for (int r = lo; r <= hi; ++r) fe[r] = l;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    if (blk[i] >= 0 && i != blocks[blk[i]].b) continue;
+    const int hi = i, lo = blk[i] >= 0 ? blocks[blk[i]].a : i;
+    int l = 0;
+    for (int r = lo; r <= hi; ++r)
+      for (int p = L.colptr[r] + 1; p < L.colptr[r + 1]; ++p) {
+        const int k = L.rowval[p];
+        if (k <= hi) continue;
+        if (owner[r] < 0) {
+          if (owner[k] >= 0) throw std::runtime_error("internal: ancestor of a top node is not top");
+          l = std::max(l, be[k] + 1);
+        } else if (owner[k] >= 0) {
+          l = std::max(l, be[k] + 1);
+        }
+      }
+    if (blk[i] >= 0) l += 1;
+    for (int r = lo; r <= hi; ++r) be[r] = l;
+  }
+
+  // ---- positions in the shared vectors ---------------------------------------------------------
+  // every node has a slot; nodes of inverted blocks have a second (scratch) slot.
+  std::vector<int32_t> n_own(C, 0), own_sz(C, 0);
+  std::vector<int32_t> pos(n, -1), scr(n, -1);
+  int n_top = 0, top_sz = 0;
+  {
+    std::vector<std::vector<int32_t>> own_nodes(C);
+    for (int i = 0; i < n; ++i) {
+      if (owner[i] < 0) pos[i] = n_top++;
+      else own_nodes[owner[i]].push_back(i);
+    }
+    top_sz = n_top;
+    for (int i = 0; i < n; ++i)
+      if (owner[i] < 0 && blk[i] >= 0) scr[i] = top_sz++;
+    for (int c = 0; c < C; ++c) {
+      auto& v = own_nodes[c];
+      std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return fe[a] < fe[b]; });
+      for (size_t k = 0; k < v.size(); ++k) pos[v[k]] = (int)k;
+      n_own[c] = (int)v.size();
+      int q = n_own[c];
+      for (int node : v)
+        if (blk[node] >= 0) scr[node] = q++;
+      own_sz[c] = q;
+    }
+  }
+  const int part_off = 0, top_off = n_top, out_off = n_top + top_sz, xd_off = out_off + ng,
+            own_off = xd_off + ng;
+  int max_own = *std::max_element(own_sz.begin(), own_sz.end());
+  if (own_off + max_own > opt.max_smem_doubles || own_off + max_own > 65535)
+    throw std::runtime_error("subdomain does not fit the shared-memory vector: use a larger cluster size");
+
+  // slot of b_i / v_i, scratch slot, and where the forward result x_i lives
+  auto sidx = [&](int node) -> uint16_t {
+    return (uint16_t)(owner[node] < 0 ? top_off + pos[node] : own_off + pos[node]);
+  };
+  auto scridx = [&](int node) -> uint16_t {
+    return (uint16_t)(owner[node] < 0 ? top_off + scr[node] : own_off + scr[node]);
+  };
+  auto xidx = [&](int node) -> uint16_t { return blk[node] >= 0 ? scridx(node) : sidx(node); };
+
+  // ---- A_IG by permuted row, A_GG by row -------------------------------------------------------
+  std::vector<int32_t> pinv(n);
+  for (int k = 0; k < n; ++k) {
+    if (in.perm[k] < 0 || in.perm[k] >= n) throw std::runtime_error("perm out of range");
+    pinv[in.perm[k]] = k;
+  }
+  const Csc& G = in.AIG;
+  if (G.nrow != n || G.ncol != ng) throw std::runtime_error("A_IG has wrong dimensions");
+  std::vector<int32_t> gptr(n + 1, 0);
+  for (int32_t v : G.rowval) {
+    if (v < 0 || v >= n) throw std::runtime_error("A_IG row index out of range");
+    gptr[pinv[v] + 1]++;
+  }
+  for (int i = 0; i < n; ++i) gptr[i + 1] += gptr[i];
+  std::vector<int32_t> gcol(G.rowval.size());
+  std::vector<double> gval(G.rowval.size());
+  {
+    std::vector<int32_t> fill(gptr.begin(), gptr.end() - 1);
+    for (int l = 0; l < ng; ++l)
+      for (int p = G.colptr[l]; p < G.colptr[l + 1]; ++p) {
+        int i = pinv[G.rowval[p]];
+        gcol[fill[i]] = l;
+        gval[fill[i]] = G.nzval[p];
+        fill[i]++;
+      }
+  }
+  const Csc& GG = in.AGG;
+  if (GG.nrow != ng || GG.ncol != ng) throw std::runtime_error("A_GG has wrong dimensions");
+  std::vector<int32_t> ggptr(ng + 1, 0);
+  for (int32_t v : GG.rowval) ggptr[v + 1]++;
+  for (int i = 0; i < ng; ++i) ggptr[i + 1] += ggptr[i];
+  std::vector<int32_t> ggcol(GG.rowval.size());
+  std::vector<double> ggval(GG.rowval.size());
+  {
+    std::vector<int32_t> fill(ggptr.begin(), ggptr.end() - 1);
+    for (int m = 0; m < ng; ++m)
+      for (int p = GG.colptr[m]; p < GG.colptr[m + 1]; ++p) {
+        int l = GG.rowval[p];
+        ggcol[fill[l]] = m;
+        ggval[fill[l]] = GG.nzval[p];
+        fill[l]++;
+      }
+  }
+
+  // ---- emit ------------------------------------------------------------------------------------
+  out = DomainPlan();
+  out.nnz_L = nnzl;
+  out.n_top = n_top;
+  out.ctas.resize(C);
+  Scratch sc;
+  std::vector<TmpRow> rows;
+  auto begin_row = [&](uint16_t dst, double dg, int level, int kind) {
+    TmpRow r;
+    r.dst = dst;
+    r.diag = dg;
+    r.level = level;
+    r.kind = kind;
+    r.ebeg = (uint32_t)sc.vals.size();
+    r.len = 0;
+    rows.push_back(r);
+  };
+  auto push = [&](uint16_t col, double v) {
+    sc.cols.push_back(col);
+    sc.vals.push_back(v);
+    rows.back().len++;
+  };
+
+  for (int c = 0; c < C; ++c) {
+    WarpStream ws[kWarps];
+    CtaDesc& D = out.ctas[c];
+    std::memset(&D, 0, sizeof(D));
+    D.rank = c;
+    D.csize = C;
+    D.n_own = n_own[c];
+    D.n_top = n_top;
+    D.n_gd = ng;
+    D.part_off = part_off;
+    D.top_off = top_off;
+    D.out_off = out_off;
+    D.xd_off = xd_off;
+    D.own_off = own_off;
+    D.smem_doubles = own_off + max_own;
+    D.top_sz = top_sz;
+    auto section = [&](int s) {
+      emit_section(rows, sc, opt.target_k, ws, D.sec_begin[s], D.sec_end[s], D.sec_nlevels[s]);
+      rows.clear();
+      sc.cols.clear();
+      sc.vals.clear();
+    };
+    auto mine = [&](int node) { return owner[node] == c || (c == 0 && owner[node] < 0); };
+
+    // SEC_INIT
+    for (int i = 0; i < n; ++i)
+      if (mine(i) && gptr[i + 1] > gptr[i]) {
+        begin_row(sidx(i), 1.0, 0, 0);
+        for (int p = gptr[i]; p < gptr[i + 1]; ++p) push((uint16_t)(xd_off + gcol[p]), gval[p]);
+      }
+    section(SEC_INIT);
+    // forward / backward rows of the nodes selected by `sel` (own subtree nodes, or top nodes)
+    auto emit_forward = [&](auto sel) {
+      for (int i = 0; i < n; ++i) {
+        if (!sel(i)) continue;
+        if (blk[i] < 0) {
+          begin_row(sidx(i), diag[i], fe[i], 0);
+          for (int p = rptr[i]; p < rptr[i + 1]; ++p)
+            if (same_scope(i, rcol[p])) push(xidx(rcol[p]), rval[p]);
+        } else {
+          const Block& B = blocks[blk[i]];
+          const int sz = B.b - B.a + 1;
+          // step A: t_i = b_i - sum_{j < a} L_ij x_j   (in place in slot i)
+          bool any = false;
+          for (int p = rptr[i]; p < rptr[i + 1]; ++p) {
+            const int j = rcol[p];
+            if (j >= B.a || !same_scope(i, j)) continue;
+            if (!any) { begin_row(sidx(i), 1.0, fe[i] - 1, 0); any = true; }
+            push(xidx(j), rval[p]);
+          }
+          // step B: x_i = sum_{k in [a, i]} Dinv[i,k] t_k   (fresh write to the scratch slot)
+          begin_row(scridx(i), -1.0, fe[i], 1);
+          for (int k = B.a; k <= i; ++k) push(sidx(k), B.Dinv[(size_t)(i - B.a) * sz + (k - B.a)]);
+        }
+      }
+    };
+    auto emit_backward = [&](auto sel) {
+      for (int i = 0; i < n; ++i) {
+        if (!sel(i)) continue;
+        if (blk[i] < 0) {
+          begin_row(sidx(i), diag[i], be[i], 0);
+          for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) push(sidx(L.rowval[p]), L.nzval[p]);
+        } else {
+          const Block& B = blocks[blk[i]];
+          const int sz = B.b - B.a + 1;
+          // step A': t_i = y_i - sum_{k > b} L_ki v_k   (y_i lives in the scratch slot)
+          bool any = false;
+          for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) {
+            const int k = L.rowval[p];
+            if (k <= B.b) continue;
+            if (!any) { begin_row(scridx(i), 1.0, be[i] - 1, 0); any = true; }
+            push(sidx(k), L.nzval[p]);
+          }
+          // step B': v_i = sum_{k in [i, b]} Dinv[k,i] t_k   (fresh write to slot i)
+          begin_row(sidx(i), -1.0, be[i], 1);
+          for (int k = i; k <= B.b; ++k) push(scridx(k), B.Dinv[(size_t)(k - B.a) * sz + (i - B.a)]);
+        }
+      }
+    };
+    // SEC_FWD
+    emit_forward([&](int i) { return owner[i] == c; });
+    section(SEC_FWD);
+    // SEC_PART
+    for (int i = 0; i < n; ++i)
+      if (owner[i] < 0) {
+        bool any = false;
+        for (int p = rptr[i]; p < rptr[i + 1]; ++p)
+          if (owner[rcol[p]] == c) {
+            if (!any) {
+              begin_row((uint16_t)(part_off + pos[i]), 1.0, 0, 0);
+              any = true;
+            }
+            push(xidx(rcol[p]), rval[p]);
+          }
+      }
+    section(SEC_PART);
+    // SEC_TOPF / SEC_TOPB (rank 0)
+    if (c == 0) emit_forward([&](int i) { return owner[i] < 0; });
+    section(SEC_TOPF);
+    if (c == 0) emit_backward([&](int i) { return owner[i] < 0; });
+    section(SEC_TOPB);
+    // SEC_BWD
+    emit_backward([&](int i) { return owner[i] == c; });
+    section(SEC_BWD);
+    // SEC_GG (rank 0)
+    if (c == 0)
+      for (int l = 0; l < ng; ++l)
+        if (ggptr[l + 1] > ggptr[l]) {
+          begin_row((uint16_t)(out_off + l), 1.0, 0, 0);
+          for (int p = ggptr[l]; p < ggptr[l + 1]; ++p) push((uint16_t)(xd_off + ggcol[p]), ggval[p]);
+        }
+    section(SEC_GG);
+    // SEC_OUT
+    for (int l = 0; l < ng; ++l) {
+      bool any = false;
+      for (int p = G.colptr[l]; p < G.colptr[l + 1]; ++p) {
+        int i = pinv[G.rowval[p]];
+        if (mine(i)) {
+          if (!any) {
+            begin_row((uint16_t)(out_off + l), 1.0, 0, 0);
+            any = true;
+          }
+          push(sidx(i), G.nzval[p]);
+        }
+      }
+    }
+    section(SEC_OUT);
+
+    // concatenate the warp streams into the plan pools
+    int64_t cta_entries = 0;
+    for (int w = 0; w < kWarps; ++w) {
+      D.slice_base[w] = out.slices.size();
+      D.row_base[w] = out.rows.size();
+      D.ent_base[w] = out.vals.size();
+      D.n_ent[w] = (uint32_t)ws[w].vals.size();
+      out.slices.insert(out.slices.end(), ws[w].slices.begin(), ws[w].slices.end());
+      out.rows.insert(out.rows.end(), ws[w].rows.begin(), ws[w].rows.end());
+      out.vals.insert(out.vals.end(), ws[w].vals.begin(), ws[w].vals.end());
+      out.cols.insert(out.cols.end(), ws[w].cols.begin(), ws[w].cols.end());
+      cta_entries += (int64_t)ws[w].vals.size();
+    }
+    out.max_cta_entries = std::max(out.max_cta_entries, cta_entries);
+    for (int s = 0; s < NSEC; ++s) out.max_levels = std::max(out.max_levels, (int)D.sec_nlevels[s]);
+    // position -> original interior index maps
+    D.ownmap_off = (int64_t)out.imap.size();
+    {
+      std::vector<int32_t> m(n_own[c]);
+      for (int i = 0; i < n; ++i)
+        if (owner[i] == c) m[pos[i]] = in.perm[i];
+      out.imap.insert(out.imap.end(), m.begin(), m.end());
+    }
+    D.topmap_off = (int64_t)out.imap.size();
+    {
+      std::vector<int32_t> m(n_top);
+      for (int i = 0; i < n; ++i)
+        if (owner[i] < 0) m[pos[i]] = in.perm[i];
+      out.imap.insert(out.imap.end(), m.begin(), m.end());
+    }
+  }
+}
+
+}  // namespace kb

@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference's Fem API for the hot path: the two new types the Julia shim
+introduces (julia/KrylovB200.jl) with the same call shapes --
+
+  S = B200SchurOperator(...)      usable wherever the reference uses its LinearMaps.FunctionMap
+                                  (``S * x``, ``mul!(y, S, x)``, ``S.N``: cg.jl:83, 93; defcg.jl:263)
+  M = B200NeumannNeumann(S)       ``M \\ r``, ``ldiv!(z, M, r)``, ``ldiv!(M, r)``
+                                  (EllipticPdeDomainDecomposition.jl:1389-1403)
+
+plus get_schur_rhs / get_subdomain_solutions / assemble_local_schurs equivalents.  Everything
+numerical happens in libkrylov_b200.so."""
+import numpy as np
+
+from . import capi
+
+
+class B200SchurOperator:
+    def __init__(self, sd, blocks, factors, device=0, csize=None, rank=0, world=1, nccl_id=None,
+                 profile=False):
+        """sd: Subdomains (set_subdomains); blocks: LocalBlocks (prepare_local_schurs);
+        factors: [(perm, L)] Cholesky factors of A_II,d (F.p, sparse(F.L))."""
+        self.sd = sd
+        self.h = capi.Handle(device, rank, world, nccl_id)
+        if csize is not None:
+            self.h.set_option("csize", csize)
+        if profile:
+            self.h.set_option("profile", 1)
+        n_I = [v.size for v in sd.node_Id]
+        n_gd = [g.size for g in sd.gamma_l2g]
+        self.h.set_topology(n_I, n_gd, [g + 1 for g in sd.gamma_l2g], sd.node_gamma_cnt)
+        d0, d1 = self.h.local_range()
+        for d in range(d0, d1):
+            self.h.upload_local_blocks(d, blocks.A_IG[d], blocks.A_GG[d])
+            self.h.upload_cholesky(d, factors[d][0], factors[d][1])
+        self.local_range = (d0, d1)
+        self.N = sd.n_gamma
+        self.assembled = False
+
+    # LinearMaps.FunctionMap surface
+    def __matmul__(self, x):
+        return self.mul(x)
+
+    def __mul__(self, x):
+        return self.mul(x)
+
+    def mul(self, x):
+        return self.h.apply_schur_assembled(x) if self.assembled else self.h.apply_schur(x)
+
+    def mul_into(self, y, x):  # mul!(y, S, x)
+        y[...] = self.mul(x)
+        return y
+
+    # get_schur_rhs / get_subdomain_solutions (EllipticPdeDomainDecomposition.jl:835-864, 1014-1025)
+    def schur_rhs(self, b_I, b_gamma):
+        return self.h.schur_rhs(np.concatenate(b_I) if len(b_I) else np.zeros(0), b_gamma)
+
+    def subdomain_solutions(self, u_gamma, b_I):
+        u = self.h.back_substitute(u_gamma, np.concatenate(b_I))
+        ptr = np.concatenate([[0], np.cumsum([v.size for v in b_I])])
+        return [u[ptr[d]:ptr[d + 1]] for d in range(len(b_I))]
+
+    # assemble_local_schurs (:667-695): dense S_d computed on the device
+    def assemble_local_schurs(self):
+        self.h.assemble_local_schurs()
+        d0, d1 = self.local_range
+        return {d: self.h.get_dense_local_schur(d) for d in range(d0, d1)}
+
+
+class B200NeumannNeumann:
+    """NeumannNeumannSchurPreconditioner (EllipticPdeDomainDecomposition.jl:1111-1137) resident on
+    the GPU of ``S``; ``PiSd[d]`` as produced by prepare_neumann_neumann_schur_precond (:1201-1220)."""
+
+    def __init__(self, S, PiSd):
+        self.S = S
+        d0, d1 = S.local_range
+        for d in range(d0, d1):
+            S.h.upload_nn_pinv(d, PiSd[d])
+
+    def solve(self, r):        # M \ r
+        return self.S.h.apply_nn(r)
+
+    def ldiv_into(self, z, r):  # ldiv!(z, M, r)
+        z[...] = self.solve(r)
+        return z
+
+    def ldiv_inplace(self, r):  # ldiv!(M, r)
+        r[...] = self.solve(r.copy())
+        return r

@@ -1,0 +1,85 @@
+"""Workload builder: the host-side steps of Example03 / Example07 up to the point where the
+reference would call ``pcg`` (Example03_EllipticPdeDomainDecomposition.jl:34-150,
+Example07_PcgSchurStochasticEllipticPde.jl:34-204), on the synthetic inputs of SURVEY.md 8(d)."""
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+
+from . import chol, epdd_host, mesh
+
+
+@dataclass
+class Problem:
+    nx: int
+    ndom: int
+    cells: np.ndarray
+    points: np.ndarray
+    markers: np.ndarray
+    neighbors: np.ndarray
+    epart: np.ndarray
+    npart: np.ndarray
+    sd: epdd_host.Subdomains
+    blocks: epdd_host.LocalBlocks
+    factors: List[tuple]
+    f_vals: np.ndarray
+    u_dir: np.ndarray
+    coeff: np.ndarray
+
+    @property
+    def n_dof(self):
+        return int((self.markers == 0).sum())
+
+
+def build_mesh_and_partition(nx, ndom, jitter=0.2):
+    cells, points, markers, neighbors = mesh.structured_mesh(nx, jitter=jitter)
+    epart, npart = mesh.rcb_partition(cells, points, ndom)
+    sd = epdd_host.set_subdomains(cells, neighbors, epart, npart, markers == 1)
+    return cells, points, markers, neighbors, epart, npart, sd
+
+
+def realization(base, ireal=1, median=False, factorize=True):
+    """Blocks + factors for one coefficient realization on a prepared mesh/partition tuple."""
+    cells, points, markers, neighbors, epart, npart, sd = base
+    nnode = points.shape[1]
+    g = mesh.lognormal_field(points, ireal, median=median)
+    coeff = np.exp(g)
+    f_vals = -np.ones(nnode)            # f = -1     (Example07:65-67)
+    u_dir = 0.734 * np.ones(nnode)      # uexact     (Example07:69-71)
+    blocks = epdd_host.prepare_local_schurs(cells, points, epart, sd, coeff, f_vals, u_dir)
+    factors = chol.factor_subdomains(blocks.A_II, points, sd.node_Id) if factorize else []
+    nx = int(round(np.sqrt(nnode)))
+    return Problem(nx, sd.ndom, cells, points, markers, neighbors, epart, npart, sd, blocks, factors,
+                   f_vals, u_dir, coeff)
+
+
+def build_problem(nx, ndom, ireal=1, jitter=0.2, median=False):
+    return realization(build_mesh_and_partition(nx, ndom, jitter), ireal, median)
+
+
+def pinv_sym(S, rtol=None):
+    """pinv of a symmetric positive semi-definite block through its eigen-decomposition, with the
+    reference's cut-off rtol = sqrt(eps) relative to the largest singular value
+    (EllipticPdeDomainDecomposition.jl:1209-1213).  3x cheaper than the SVD route."""
+    rtol = np.sqrt(np.finfo(np.float64).eps) if rtol is None else rtol
+    w, V = np.linalg.eigh((S + S.T) * 0.5)
+    keep = np.abs(w) > rtol * np.abs(w).max()
+    Vk = V[:, keep]
+    return (Vk / w[keep]) @ Vk.T
+
+
+def algorithmic_bytes_per_iteration(prob: Problem):
+    """B_iter of SURVEY.md 8(d), evaluated from the actual nnz counts (int32 indices, FP64 values)."""
+    b = 0.0
+    parts = {"trisolve": 0.0, "spmv": 0.0, "nn": 0.0, "maps": 0.0, "vectors": 0.0}
+    for d in range(prob.ndom):
+        nI = prob.blocks.A_II[d].shape[0]
+        ng = prob.blocks.A_GG[d].shape[0]
+        nnzL = prob.factors[d][1].nnz
+        parts["trisolve"] += 2 * (12 * nnzL + 4 * (nI + 1) + 8 * 3 * nI)
+        parts["spmv"] += 2 * (12 * prob.blocks.A_IG[d].nnz + 4 * (nI + 1)) + 12 * prob.blocks.A_GG[d].nnz + 4 * (ng + 1)
+        parts["nn"] += 8 * ng * ng
+        parts["maps"] += 4 * 4 * ng + 8 * 4 * ng
+    parts["vectors"] = 8 * prob.sd.n_gamma * 12
+    b = sum(parts.values())
+    return b, parts

@@ -1,0 +1,33 @@
+"""Development probe: kernel timings at a given size for several cluster sizes."""
+import sys, time, json, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import krylov_b200
+from krylov_b200.hostprep import problem as PB
+from krylov_b200 import fem, solvers
+
+nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2001
+ndom = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+csizes = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [4]
+do_pcg = len(sys.argv) > 4 and sys.argv[4] == 'pcg'
+t = time.time(); pr = PB.build_problem(nx, ndom, ireal=1); print('host prep %.1fs' % (time.time() - t), flush=True)
+B, parts = PB.algorithmic_bytes_per_iteration(pr)
+print('B_iter GB', B / 1e9, {k: v / 1e9 for k, v in parts.items()}, flush=True)
+for cs in csizes:
+    t = time.time()
+    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=cs, profile=True)
+    S.h.finalize(); tf = time.time() - t
+    st = S.h.stats()
+    ms = S.h.time_kernel(0, 20)
+    alg = parts['trisolve'] + parts['spmv']
+    print(f"csize={cs} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
+    if do_pcg:
+        t = time.time(); Sd = S.assemble_local_schurs(); print('  assemble S_d %.1fs' % (time.time() - t), flush=True)
+        t = time.time(); Pi = [PB.pinv_sym(Sd[d]) for d in range(ndom)]; print('  pinv %.1fs' % (time.time() - t), flush=True)
+        M = fem.B200NeumannNeumann(S, Pi)
+        print('  nn kernel ms', S.h.time_kernel(1, 20), 'dense schur kernel ms', S.h.time_kernel(2, 20), flush=True)
+        bs = S.schur_rhs(pr.blocks.b_I, pr.blocks.b_G)
+        for rep in range(2):
+            t = time.time(); x, it, res, tm = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M, maxit=5000, return_timings=True); tw = time.time() - t
+            print(f"  pcg it {it} wall {tw*1e3:.1f} ms solve_ms {tm.solve_ms:.1f} schur {tm.schur_ms:.1f}/{tm.schur_launches} nn {tm.nn_ms:.1f}/{tm.nn_launches} per-it {tm.solve_ms/(it-1):.3f} ms  roofline(alg) {B*(it-1)/tm.solve_ms/1e6:.0f} GB/s  res {res[-1]/res[0]:.2e}", flush=True)
+    del S
