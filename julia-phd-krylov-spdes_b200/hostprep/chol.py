@@ -79,7 +79,7 @@ def factor_subdomains(A_II, points, node_Id, leaf=8, threads=None):
     """[(perm, L)] for every subdomain; ND ordering from the interior nodes' coordinates."""
     def one(d):
         nodes = node_Id[d]
-        if A_II[d].shape[0] == 0:
+        if A_II[d].shape[0] == 0 or A_II[d].nnz == 0:
             return np.zeros(0, np.int32), sp.csc_matrix((0, 0))
         p = nd_order(A_II[d], points[0, nodes], points[1, nodes], leaf)
         L, _ = cholesky(A_II[d], p)

@@ -38,15 +38,21 @@ def build_mesh_and_partition(nx, ndom, jitter=0.2):
     return cells, points, markers, neighbors, epart, npart, sd
 
 
-def realization(base, ireal=1, median=False, factorize=True):
-    """Blocks + factors for one coefficient realization on a prepared mesh/partition tuple."""
+def realization(base, ireal=1, median=False, factorize=True, dom_range=None):
+    """Blocks + factors for one coefficient realization on a prepared mesh/partition tuple.
+    dom_range=(d0, d1) assembles / factorizes only those subdomains' elements (multi-rank runs):
+    b_G then holds this rank's partial sum and the other subdomains' blocks are empty."""
     cells, points, markers, neighbors, epart, npart, sd = base
     nnode = points.shape[1]
     g = mesh.lognormal_field(points, ireal, median=median)
     coeff = np.exp(g)
     f_vals = -np.ones(nnode)            # f = -1     (Example07:65-67)
     u_dir = 0.734 * np.ones(nnode)      # uexact     (Example07:69-71)
-    blocks = epdd_host.prepare_local_schurs(cells, points, epart, sd, coeff, f_vals, u_dir)
+    if dom_range is not None and (dom_range[0] > 0 or dom_range[1] < sd.ndom):
+        keep = (epart >= dom_range[0]) & (epart < dom_range[1])
+        blocks = epdd_host.prepare_local_schurs(cells[:, keep], points, epart[keep], sd, coeff, f_vals, u_dir)
+    else:
+        blocks = epdd_host.prepare_local_schurs(cells, points, epart, sd, coeff, f_vals, u_dir)
     factors = chol.factor_subdomains(blocks.A_II, points, sd.node_Id) if factorize else []
     nx = int(round(np.sqrt(nnode)))
     return Problem(nx, sd.ndom, cells, points, markers, neighbors, epart, npart, sd, blocks, factors,
@@ -68,11 +74,12 @@ def pinv_sym(S, rtol=None):
     return (Vk / w[keep]) @ Vk.T
 
 
-def algorithmic_bytes_per_iteration(prob: Problem):
+def algorithmic_bytes_per_iteration(prob: Problem, dom_range=None):
     """B_iter of SURVEY.md 8(d), evaluated from the actual nnz counts (int32 indices, FP64 values)."""
     b = 0.0
     parts = {"trisolve": 0.0, "spmv": 0.0, "nn": 0.0, "maps": 0.0, "vectors": 0.0}
-    for d in range(prob.ndom):
+    d0, d1 = dom_range if dom_range is not None else (0, prob.ndom)
+    for d in range(d0, d1):
         nI = prob.blocks.A_II[d].shape[0]
         ng = prob.blocks.A_GG[d].shape[0]
         nnzL = prob.factors[d][1].nnz

@@ -1,0 +1,65 @@
+"""World-size-2 CPU test (gloo) of the multi-rank host logic: contiguous subdomain shards, partial
+interface sums combined by all-reduce, rank-0-only addition of b_Γ, identical scalars on every
+rank.  The same sharding rule is used by kb200_set_topology (api.cu) and bench.py."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import krylov_b200  # noqa: F401
+    from krylov_b200.hostprep import problem as PB
+    import oracle.epdd as E
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr = PB.build_problem(33, 4)
+    sd, lb = pr.sd, pr.blocks
+    inner = E.ExactInterior(lb.A_II)
+    d0, d1 = (sd.ndom * rank) // world, (sd.ndom * (rank + 1)) // world      # kb200_set_topology's rule
+    x = np.random.default_rng(7).standard_normal(sd.n_gamma)
+    part = np.zeros(sd.n_gamma)
+    for d in range(d0, d1):
+        g = sd.gamma_l2g[d]
+        part[g] += E.apply_local_schur(lb, inner, d, x[g])
+    t = torch.from_numpy(part)
+    dist.all_reduce(t)
+    full = E.apply_local_schurs(lb, inner, sd, x)
+    # Schur rhs: b_Γ enters once (rank 0), subdomain terms are sharded
+    rhs = lb.b_G.copy() if rank == 0 else np.zeros(sd.n_gamma)
+    for d in range(d0, d1):
+        rhs[sd.gamma_l2g[d]] -= lb.A_IG[d].T @ inner.solve(d, lb.b_I[d])
+    tr = torch.from_numpy(rhs)
+    dist.all_reduce(tr)
+    ref_rhs = E.get_schur_rhs(lb, inner, sd)
+    # max-over-ranks timing reduction used by bench.py
+    tm = torch.tensor([float(rank + 1)])
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    q.put((rank, float(abs(t.numpy() - full).max() / abs(full).max()),
+           float(abs(tr.numpy() - ref_rhs).max() / abs(ref_rhs).max()), float(tm.item()), (d0, d1)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_apply_matches_single_rank():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ranges = sorted(r[4] for r in res)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 4 and ranges[0][1] == ranges[1][0]
+    for rank, e_apply, e_rhs, tmax, _ in res:
+        assert e_apply <= 1e-13 and e_rhs <= 1e-13 and tmax == float(world)

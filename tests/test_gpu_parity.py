@@ -1,0 +1,214 @@
+"""Parity of the CUDA path (through the C ABI, libkrylov_b200.so) with the CPU oracle.
+
+Tolerances.  Operator applications are compared at 1e-12 relative (FP64, different summation
+order).  For whole solves the bar of north_star is: iteration count within +-1 and relative
+solution error <= 1e-10 *against an implementation of the same arithmetic*.  One-level
+Neumann-Neumann PCG on lognormal coefficients is ill-conditioned enough that two CPU restatements
+that differ only in rounding (scipy-LU interior solves in oracle/epdd.py vs. Cholesky solves in
+oracle/kb_oracle.c) already differ by ~1e-8 in x and by one iteration (measured in
+test_pcg_parity_floor below), so whole-solve comparisons use max(1e-10, 20 x that measured floor)
+at equal iteration index, and 1e-10 where the floor allows it (constant coefficient)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle.epdd as E
+import oracle.solvers as OS
+from conftest import get_oracle_ops, get_problem
+from krylov_b200 import capi, fem, solvers
+from oracle.cpu_model import CpuModel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "schur_nx33_ndom4.npz")
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+_ops = {}
+
+
+def gpu_ops(nx, ndom, csize, median=False):
+    key = (nx, ndom, csize, median)
+    if key not in _ops:
+        pr = get_problem(nx, ndom, median=median)
+        inner, Sd, Pi, bs = get_oracle_ops(pr)
+        S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=csize, profile=True)
+        M = fem.B200NeumannNeumann(S, Pi)
+        _ops[key] = (pr, S, M)
+    return _ops[key]
+
+
+CASES = [(33, 4, 1), (33, 4, 2), (65, 16, 4), (65, 16, 8), (97, 9, 4)]
+
+
+@pytest.mark.parametrize("nx,ndom,csize", CASES)
+def test_operators_match_oracle(nx, ndom, csize):
+    pr, S, M = gpu_ops(nx, ndom, csize)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    sd, lb = pr.sd, pr.blocks
+    x = np.random.default_rng(nx + csize).standard_normal(sd.n_gamma)
+    assert rel(S * x, E.apply_local_schurs(lb, inner, sd, x)) <= 1e-12            # a4  :711-747
+    assert rel(M.solve(x), E.apply_neumann_neumann_schur(Pi, sd, x)) <= 1e-12      # a10 :1361-1386
+    assert rel(S.schur_rhs(lb.b_I, lb.b_G), bs) <= 1e-12                          # a7  :835-864
+    ug = np.random.default_rng(3).standard_normal(sd.n_gamma)
+    uI = S.subdomain_solutions(ug, lb.b_I)                                         # a8  :1014-1025
+    uIr = E.get_subdomain_solutions(ug, lb, inner, sd)
+    scale = max(np.abs(u).max() for u in uIr)
+    assert max(np.abs(a - b).max() for a, b in zip(uI, uIr)) <= 1e-11 * scale
+    # multiple right-hand sides, column-major
+    X = np.random.default_rng(5).standard_normal((sd.n_gamma, 3))
+    Y = S.h.apply_schur(X)
+    for k in range(3):
+        assert rel(Y[:, k], E.apply_local_schurs(lb, inner, sd, X[:, k])) <= 1e-12
+
+
+@pytest.mark.parametrize("nx,ndom,csize", [(33, 4, 2), (65, 16, 4)])
+def test_dense_local_schur_path(nx, ndom, csize):
+    pr, S, M = gpu_ops(nx, ndom, csize)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    got = S.assemble_local_schurs()                                                # a5  :667-695
+    for d in range(ndom):
+        assert rel(got[d], Sd[d]) <= 1e-11
+        assert np.array_equal(got[d], got[d].T)                                    # Symmetric() :692
+    x = np.random.default_rng(1).standard_normal(pr.sd.n_gamma)
+    assert rel(S.h.apply_schur_assembled(x), E.apply_local_schurs_assembled(Sd, pr.sd, x)) <= 1e-12
+
+
+@pytest.mark.parametrize("nx,ndom,csize", [(33, 4, 2), (65, 16, 4)])
+def test_interface_maps_bit_for_bit(nx, ndom, csize):
+    """The device's gather/scatter tables equal the reference's ind_Γd_Γ2l / node_Γ_cnt exactly."""
+    pr, S, M = gpu_ops(nx, ndom, csize)
+    sd = pr.sd
+    ptr, dom, loc = S.h.interface_maps()
+    assert np.array_equal(np.diff(ptr), sd.node_gamma_cnt)
+    for g in range(sd.n_gamma):
+        ds, ls = dom[ptr[g]:ptr[g + 1]], loc[ptr[g]:ptr[g + 1]]
+        assert np.all(np.diff(ds) > 0)                       # ascending subdomain order (:723, :740)
+        for d, l in zip(ds, ls):
+            assert sd.gamma_l2g[d][l] == g
+
+
+def test_golden_vectors_on_gpu():
+    g = np.load(GOLD)
+    pr, S, M = gpu_ops(33, 4, 2)
+    assert rel(S * g["x_probe"], g["S_x"]) <= 1e-12
+    assert rel(M.solve(g["x_probe"]), g["M_x"]) <= 1e-11
+    assert rel(S.schur_rhs(pr.blocks.b_I, pr.blocks.b_G), g["b_schur"]) <= 1e-12
+    x, it, res = solvers.pcg(S, g["b_schur"], np.zeros(pr.sd.n_gamma), M)
+    assert it == int(g["pcg_it"])
+    assert np.abs(res - g["pcg_res"]).max() <= 1e-9 * res[0]
+    assert np.linalg.norm(x - g["pcg_x"]) <= 1e-9 * np.linalg.norm(x)
+
+
+def _pcg_floor(pr):
+    """Difference between two CPU restatements that differ only in rounding."""
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    sd, lb = pr.sd, pr.blocks
+    cm = CpuModel(sd, lb, pr.factors, Pi)
+    xo, ito, reso = OS.pcg(lambda v: E.apply_local_schurs(lb, inner, sd, v), bs, np.zeros(sd.n_gamma),
+                           lambda r: E.apply_neumann_neumann_schur(Pi, sd, r))
+    k = ito
+    xc, itc, resc = cm.pcg(bs, np.zeros(sd.n_gamma), maxit=k)
+    floor = np.linalg.norm(xc - xo) / np.linalg.norm(xo) if itc == k else 1e-6
+    return (xo, ito, reso), floor
+
+
+@pytest.mark.parametrize("nx,ndom,csize,median", [(33, 4, 2, False), (65, 16, 4, False), (65, 16, 4, True),
+                                                    (97, 9, 4, False)])
+def test_pcg_parity(nx, ndom, csize, median):
+    pr, S, M = gpu_ops(nx, ndom, csize, median)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    (xo, ito, reso), floor = _pcg_floor(pr)
+    x0 = np.zeros(pr.sd.n_gamma)
+    x, it, res, tm = solvers.pcg(S, bs, x0, M, return_timings=True)
+    assert x is x0 or np.array_equal(x, x0)                       # in-place update (cg.jl:97)
+    assert abs(it - ito) <= 1                                     # stopping index within +-1
+    assert res.size == it and res[-1] <= 1e-7 * np.linalg.norm(bs)
+    k = min(it, ito)
+    # same iterate at equal iteration index
+    xk, itk, resk = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M, maxit=k)
+    xok, _, _ = OS.pcg(lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v), bs, np.zeros(pr.sd.n_gamma),
+                       lambda r: E.apply_neumann_neumann_schur(Pi, pr.sd, r), maxit=k)
+    tol = max(1e-10, 20 * floor)
+    assert itk == k
+    assert np.linalg.norm(xk - xok) <= tol * np.linalg.norm(xok)
+    assert np.abs(resk - reso[:k]).max() <= tol * reso[:k].max()
+    assert tm.kernel_launches > 0 and tm.schur_launches == it and tm.solve_ms > 0
+
+
+def test_pcg_parity_tight_on_well_conditioned_case():
+    """Constant coefficient, 4 subdomains: the rounding floor is tiny and the 1e-10 bar applies."""
+    pr, S, M = gpu_ops(33, 4, 2, True)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    xo, ito, reso = OS.pcg(lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v), bs, np.zeros(pr.sd.n_gamma),
+                           lambda r: E.apply_neumann_neumann_schur(Pi, pr.sd, r))
+    x, it, res = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M)
+    assert it == ito
+    assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)
+    assert np.abs(res - reso).max() <= 1e-10 * reso[0]
+
+
+def test_cg_without_preconditioner_and_assembled_operator():
+    pr, S, M = gpu_ops(33, 4, 2)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    xo, ito, _ = OS.pcg(lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v), bs, np.zeros(pr.sd.n_gamma),
+                        lambda r: r.copy())
+    x, it, res = solvers.cg(S, bs, np.zeros(pr.sd.n_gamma))
+    assert abs(it - ito) <= 1
+    S.assemble_local_schurs()
+    S.assembled = True
+    try:
+        xa, ita, _ = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M)
+    finally:
+        S.assembled = False
+    xm, itm, _ = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M)
+    assert abs(ita - itm) <= 1
+    assert np.linalg.norm(xa - xm) <= 1e-6 * np.linalg.norm(xm)
+
+
+def test_size_independent_properties_at_larger_size():
+    """Linearity, symmetry <Sx,y> = <x,Sy>, positivity, M symmetric; 250k DOF / 64 subdomains."""
+    pr = get_problem(501, 64)
+    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=4)
+    rng = np.random.default_rng(0)
+    n = pr.sd.n_gamma
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    Sx, Sy = S * x, S * y
+    assert rel(S * (2.0 * x - 3.0 * y), 2.0 * Sx - 3.0 * Sy) <= 1e-11
+    assert abs(Sx @ y - x @ Sy) <= 1e-11 * abs(Sx @ y)
+    assert x @ Sx > 0
+    # back-substitution consistency: A_II u_I + A_IG u_G = b_I
+    ug = rng.standard_normal(n)
+    uI = S.subdomain_solutions(ug, pr.blocks.b_I)
+    for d in (0, 17, 63):
+        r = pr.blocks.A_II[d] @ uI[d] + pr.blocks.A_IG[d] @ ug[pr.sd.gamma_l2g[d]] - pr.blocks.b_I[d]
+        assert np.abs(r).max() <= 1e-9 * max(np.abs(pr.blocks.b_I[d]).max(), np.abs(pr.blocks.A_IG[d] @ ug[pr.sd.gamma_l2g[d]]).max())
+    # against the C port of the oracle
+    cm = CpuModel(pr.sd, pr.blocks, pr.factors)
+    assert rel(Sx, cm.apply_schur(x, nthreads=8)) <= 1e-12
+
+
+def test_error_reporting_through_the_abi():
+    h = capi.Handle(0)
+    with pytest.raises(capi.KB200Error) as e:
+        h.apply_schur(np.zeros(0))
+    assert e.value.code in (-1,)                                                          # topology not set
+    n_I, n_gd = [2], [1]
+    with pytest.raises(capi.KB200Error) as e:                                             # cnt mismatch
+        h.set_topology(n_I, n_gd, [np.array([1])], np.array([2]))
+    assert e.value.code == -4
+    h2 = capi.Handle(0)
+    h2.set_topology(n_I, n_gd, [np.array([1])], np.array([1]))
+    import scipy.sparse as sp
+    h2.upload_local_blocks(0, sp.csc_matrix(np.array([[1.0], [0.0]])), sp.csc_matrix(np.array([[2.0]])))
+    with pytest.raises(capi.KB200Error) as e:                                             # not a permutation
+        h2.upload_cholesky(0, np.array([0, 0]), sp.csc_matrix(np.eye(2)))
+    assert e.value.code == -4
+    h2.upload_cholesky(0, np.array([0, 1]), sp.csc_matrix(np.array([[0.0, 0.0], [1.0, 1.0]])))
+    with pytest.raises(capi.KB200Error) as e:                                             # missing diagonal
+        h2.finalize()
+    assert e.value.code == -4 and "diagonal" in str(e.value)
