@@ -131,6 +131,9 @@ int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom,
 /* Average device time (ms) of `reps` back-to-back launches of one kernel on resident data:
  * which = 0 Schur stream kernel, 1 NN GEMV kernel, 2 assembled-Schur GEMV kernel. */
 int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
+/* Development aid: with option "debug_timing" = 1 the stream kernel records 16 clock64 stamps per
+ * CTA (phase boundaries); this copies them out. */
+int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ SYMBOLS = [
     "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
     "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_get_stats", "kb200_get_interface_maps",
-    "kb200_time_kernel",
+    "kb200_time_kernel", "kb200_debug_stamps",
 ]
 
 
@@ -236,6 +236,11 @@ class Handle:
         _chk(lib().kb200_get_interface_maps(self.h, _p(ptr, C.c_int64), _p(dom, C.c_int64), _p(loc, C.c_int64)))
         n = int(ptr[-1])
         return ptr, dom[:n], loc[:n]
+
+    def debug_stamps(self, n_cta):
+        out = np.zeros(n_cta * 16, dtype=np.int64)
+        _chk(lib().kb200_debug_stamps(self.h, _p(out, C.c_int64), C.c_int64(out.size)))
+        return out.reshape(n_cta, 16)
 
     def time_kernel(self, which, reps=10):
         ms = C.c_double()

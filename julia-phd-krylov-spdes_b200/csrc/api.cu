@@ -111,7 +111,7 @@ struct kb200_ctx {
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 4, profile = 0, check_every = 8, min_block = -1;
+  int csize = 4, profile = 0, check_every = 8, min_block = -1, stages = 3;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -127,16 +127,15 @@ struct kb200_ctx {
   double stats[16] = {0};
   // device pools
   DevBuf<kb::CtaDesc> d_ctas;
-  DevBuf<kb::SliceHdr> d_slices;
-  DevBuf<kb::RowRec> d_rows;
-  DevBuf<double> d_vals;
-  DevBuf<uint16_t> d_cols;
+  DevBuf<uint8_t> d_stream;
   DevBuf<int32_t> d_l2g, d_imap, d_adj_ptr, d_adj_src, d_ngd;
   DevBuf<int64_t> d_G_base, d_mat_off;
   DevBuf<double> d_pinv, d_sd, d_inv_cnt;
   // device vectors
   DevBuf<double> d_x, d_b, d_r, d_z, d_p, d_Ap, d_loc, d_bI, d_uI, d_partA, d_partB, d_partC, d_res;
   DevBuf<kb::PcgState> d_state;
+  DevBuf<long long> d_dbg;
+  int debug_timing = 0, dbg_flags = 0;
   int nb = 0;  // blocks of the interface-vector kernels
   int64_t launches = 0;
   std::vector<cudaEvent_t> ev_pool;
@@ -215,26 +214,27 @@ void finalize(Ctx* c) {
   c->I_base.assign(nloc + 1, 0);
   c->G_base.assign(nloc + 1, 0);
   c->mat_off.assign(nloc + 1, 0);
-  std::vector<uint64_t> so(nloc + 1, 0), ro(nloc + 1, 0), eo(nloc + 1, 0), mo(nloc + 1, 0);
+  std::vector<uint64_t> so(nloc + 1, 0), mo(nloc + 1, 0);
   int max_smem = 0, max_gd = 0, max_lev = 0, max_top = 0;
-  double nnzL = 0;
+  double nnzL = 0, n_ent = 0, n_rows = 0, n_pkt = 0;
   for (int64_t k = 0; k < nloc; ++k) {
     const DomHost& dh = c->doms[c->d0 + k];
     c->I_base[k + 1] = c->I_base[k] + dh.n_I;
     c->G_base[k + 1] = c->G_base[k] + dh.n_gd;
     c->mat_off[k + 1] = c->mat_off[k] + dh.n_gd * dh.n_gd;
-    so[k + 1] = so[k] + plans[k].slices.size();
-    ro[k + 1] = ro[k] + plans[k].rows.size();
-    eo[k + 1] = eo[k] + plans[k].vals.size();
+    so[k + 1] = so[k] + plans[k].stream.size();
     mo[k + 1] = mo[k] + plans[k].imap.size();
     for (auto& D : plans[k].ctas) max_smem = std::max(max_smem, D.smem_doubles);
     max_gd = std::max<int>(max_gd, (int)dh.n_gd);
     max_lev = std::max(max_lev, plans[k].max_levels);
     max_top = std::max(max_top, plans[k].n_top);
     nnzL += (double)plans[k].nnz_L;
+    n_ent += (double)plans[k].n_entries;
+    n_rows += (double)plans[k].n_rows;
+    n_pkt += (double)plans[k].n_packets;
   }
   c->max_gd = max_gd;
-  c->smem_bytes = max_smem * 8;
+  c->smem_bytes = max_smem * 8 + c->stages * kb::kChunkBytes + kb::kMaxSlots * 8;
   c->n_cta = (int)(nloc * c->csize);
   // descriptors with global offsets
   std::vector<kb::CtaDesc> ctas;
@@ -247,34 +247,17 @@ void finalize(Ctx* c) {
       D.topmap_off += (int64_t)mo[k];
       D.I_base = c->I_base[k];
       D.G_base = c->G_base[k];
-      D.out_g_off = 0;
-      for (int w = 0; w < kb::kWarps; ++w) {
-        D.slice_base[w] += so[k];
-        D.row_base[w] += ro[k];
-        D.ent_base[w] += eo[k];
-      }
+      D.stream_off += so[k];
       ctas.push_back(D);
     }
   cudaStream_t s = c->stream;
   c->d_ctas.upload(ctas, s);
-  const size_t epad = kb::kPrefetchAhead + 70000;
-  c->d_slices.alloc(so[nloc], 256);
-  c->d_rows.alloc(ro[nloc], 256);
-  c->d_vals.alloc(eo[nloc], epad);
-  c->d_cols.alloc(eo[nloc], epad);
+  c->d_stream.alloc(so[nloc], 256);
   c->d_imap.alloc(mo[nloc]);
   for (int64_t k = 0; k < nloc; ++k) {
     auto& P = plans[k];
-    if (!P.slices.empty())
-      CUDA_TRY(cudaMemcpyAsync(c->d_slices.p + so[k], P.slices.data(), P.slices.size() * sizeof(kb::SliceHdr),
-                               cudaMemcpyHostToDevice, s));
-    if (!P.rows.empty())
-      CUDA_TRY(cudaMemcpyAsync(c->d_rows.p + ro[k], P.rows.data(), P.rows.size() * sizeof(kb::RowRec),
-                               cudaMemcpyHostToDevice, s));
-    if (!P.vals.empty()) {
-      CUDA_TRY(cudaMemcpyAsync(c->d_vals.p + eo[k], P.vals.data(), P.vals.size() * 8, cudaMemcpyHostToDevice, s));
-      CUDA_TRY(cudaMemcpyAsync(c->d_cols.p + eo[k], P.cols.data(), P.cols.size() * 2, cudaMemcpyHostToDevice, s));
-    }
+    if (!P.stream.empty())
+      CUDA_TRY(cudaMemcpyAsync(c->d_stream.p + so[k], P.stream.data(), P.stream.size(), cudaMemcpyHostToDevice, s));
     if (!P.imap.empty())
       CUDA_TRY(cudaMemcpyAsync(c->d_imap.p + mo[k], P.imap.data(), P.imap.size() * 4, cudaMemcpyHostToDevice, s));
   }
@@ -352,10 +335,10 @@ void finalize(Ctx* c) {
   CUDA_TRY(cudaStreamSynchronize(s));
   // stats
   c->stats[0] = nnzL;
-  c->stats[1] = (double)eo[nloc];
-  c->stats[2] = (double)ro[nloc];
-  c->stats[3] = (double)so[nloc];
-  c->stats[4] = (double)eo[nloc] * 10.0 + (double)ro[nloc] * 16.0 + (double)so[nloc] * 8.0;
+  c->stats[1] = n_ent;
+  c->stats[2] = n_rows;
+  c->stats[3] = n_pkt;
+  c->stats[4] = (double)so[nloc];
   c->stats[5] = max_lev;
   c->stats[6] = max_top;
   c->stats[7] = c->smem_bytes;
@@ -377,10 +360,7 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   kb::StreamParams P;
   std::memset(&P, 0, sizeof(P));
   P.ctas = c->d_ctas.p;
-  P.slices = c->d_slices.p;
-  P.rows = c->d_rows.p;
-  P.vals = c->d_vals.p;
-  P.cols = c->d_cols.p;
+  P.stream = c->d_stream.p;
   P.l2g = c->d_l2g.p;
   P.imap = c->d_imap.p;
   P.x_gamma = x_gamma;
@@ -391,14 +371,18 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   P.sd_off = c->d_mat_off.p;
   P.done_at = done_at;
   P.iter = iter;
-  P.n_vals = c->d_vals.n;
-  P.n_rows = c->d_rows.n;
-  P.n_slices = c->d_slices.n;
   P.unit_col0 = unit_col0;
+  P.nstages = c->stages;
+  P.dbg = nullptr;
+  P.dbg_flags = c->dbg_flags;
+  if (c->debug_timing) {
+    if (c->d_dbg.n < (size_t)c->n_cta * 16) c->d_dbg.alloc((size_t)c->n_cta * 16);
+    P.dbg = c->d_dbg.p;
+  }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)c->n_cta, (unsigned)ncols, 1);
-  cfg.blockDim = dim3(kb::kWarps * 32, 1, 1);
+  cfg.blockDim = dim3(kb::kStreamThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)c->smem_bytes;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
@@ -643,6 +627,14 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       require(!h->finalized, "csize must be set before the first operation");
       require(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "csize must be 1, 2, 4, 8 or 16");
       h->csize = (int)value;
+    } else if (k == "dbg_flags") {
+      h->dbg_flags = (int)value;
+    } else if (k == "debug_timing") {
+      h->debug_timing = value != 0;
+    } else if (k == "stages") {
+      require(!h->finalized, "stages must be set before the first operation");
+      require(value >= 2 && value <= kb::kMaxStages, "stages must be in [2, 12]");
+      h->stages = (int)value;
     } else if (k == "min_block") {
       require(!h->finalized, "min_block must be set before the first operation");
       h->min_block = (int)value;
@@ -971,6 +963,16 @@ int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom,
       adj_dom[i] = h->adj_dom[i];
       adj_loc[i] = h->adj_loc[i];
     }
+  });
+}
+
+int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n) {
+  return guarded([&]() {
+    require(h && out, "null argument");
+    use_device(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t m = std::min<size_t>((size_t)n, h->d_dbg.n);
+    if (m) CUDA_TRY(cudaMemcpy(out, h->d_dbg.p, m * sizeof(long long), cudaMemcpyDeviceToHost));
   });
 }
 

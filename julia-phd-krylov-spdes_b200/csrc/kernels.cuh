@@ -22,10 +22,7 @@ namespace cg = cooperative_groups;
 
 struct StreamParams {
   const CtaDesc* ctas;
-  const SliceHdr* slices;
-  const RowRec* rows;
-  const double* vals;
-  const uint16_t* cols;
+  const uint8_t* stream;  // packet streams of all CTAs (chunk aligned)
   const int32_t* l2g;
   const int32_t* imap;
   const double* x_gamma;  // interface vector (MODE_APPLY / MODE_BACKSUB)
@@ -36,92 +33,257 @@ struct StreamParams {
   const int64_t* sd_off;  // per local subdomain offset into sd_pool
   const int* done_at;     // optional: skip when *done_at < iter (solver already converged)
   int iter;
-  uint64_t n_vals, n_rows, n_slices;  // pool sizes (prefetch clamps)
   int unit_col0;          // MODE_UNIT: column = unit_col0 + blockIdx.y
+  int nstages;            // ring depth (<= kMaxStages)
+  long long* dbg;         // optional: 16 clock64 stamps per CTA (development aid)
+  int dbg_flags;          // development aid: 1 = skip packet arithmetic, 2 = skip level barriers
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-constexpr int kPrefetchAhead = 1536;  // entries (12 KB of values) per warp stream
-__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+constexpr int kMaxStages = 12;
+constexpr int kStreamThreads = (kWarps + 1) * 32;  // 8 consumer warps + 1 producer warp
 
-// One section of a CTA's program: every warp walks its slice range; rows of a level are independent.
-__device__ __forceinline__ void run_section(const CtaDesc& D, const StreamParams& P, double* S, int sec,
-                                            double sign, int warp, int lane) {
-  const SliceHdr* slices = P.slices + D.slice_base[warp];
-  const RowRec* rows = P.rows + D.row_base[warp];
-  const double* vals = P.vals + D.ent_base[warp];
-  const uint16_t* cols = P.cols + D.ent_base[warp];
-  uint32_t s = D.sec_begin[sec][warp];
-  const uint32_t e = D.sec_end[sec][warp];
-  const uint32_t nlev = D.sec_nlevels[sec];
+// ---- mbarrier / TMA bulk-copy primitives (PTX) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy (TMA, 1-D), completion signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory"); }
+
+struct StreamCtx {
+  const CtaDesc* D;
+  const uint8_t* gstream;  // this CTA's stream in global memory
+  uint8_t* ring;
+  double* S;
+  double* scratch;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  uint64_t* lvl_bar;
+  uint32_t lvl_phase;
+  cg::cluster_group* cluster;
+  uint32_t stage, phase;   // ring position (same sequence on both sides); phase = parity of the stage's use count
+  uint32_t nst;
+  int dbg_flags;
+  int warp, lane;
+};
+
+// Producer warp: stream the chunks of one section into the ring.
+__device__ __forceinline__ void produce_section(StreamCtx& cx, int sec) {
+  const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec];
+  for (uint32_t ch = c0; ch < c1; ++ch) {
+    const uint32_t stage = cx.stage;
+    // the producer waits for the previous use of the stage to be released: parity phase^1; the very
+    // first pass over the ring finds the barriers in their initial phase, which try_wait(1) accepts
+    mbar_wait(&cx.empty_bar[stage], cx.phase ^ 1u);
+    if (cx.lane == 0) {
+      mbar_expect_tx(&cx.full_bar[stage], kChunkBytes);
+      tma_load_1d(cx.ring + stage * kChunkBytes, cx.gstream + (size_t)ch * kChunkBytes, kChunkBytes, &cx.full_bar[stage]);
+    }
+    __syncwarp();
+    if (++cx.stage == cx.nst) {
+      cx.stage = 0;
+      cx.phase ^= 1u;
+    }
+  }
+}
+
+// Software barrier over the consumer threads of all CTAs of the cluster (the producer warps keep
+// streaming): CTA-local barrier, then one thread arrives (release.cluster) on the level mbarrier
+// of every CTA of the cluster, and everybody waits (acquire.cluster) on its own CTA's.
+__device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");  // my (remote) stores precede the arrivals below
+  consumer_barrier();
+  const uint32_t local = smem_u32(cx.lvl_bar);
+  if (cx.warp == 0 && cx.lane == 0) {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    for (int c = 0; c < cx.D->csize; ++c) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    }
+  }
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(local), "r"(cx.lvl_phase)
+        : "memory");
+  } while (!ok);
+  cx.lvl_phase ^= 1u;
+}
+
+// One group record: 32 products, segmented inclusive scan, segment sums to their scratch slots.
+// Two groups are interleaved for instruction-level parallelism.
+__device__ __forceinline__ void process_groups2(const uint8_t* g0, const uint8_t* g1, bool on1, const double* S,
+                                                double* scratch, int lane, uint32_t le_mask) {
+  const uint2 m0 = *reinterpret_cast<const uint2*>(g0);
+  const uint2 m1 = *reinterpret_cast<const uint2*>(g1);
+  const double v0 = reinterpret_cast<const double*>(g0 + 16)[lane];
+  const double v1 = reinterpret_cast<const double*>(g1 + 16)[lane];
+  const uint32_t c0 = reinterpret_cast<const uint16_t*>(g0 + 16 + 256)[lane];
+  const uint32_t c1 = reinterpret_cast<const uint16_t*>(g1 + 16 + 256)[lane];
+  double x0 = v0 * S[c0];
+  double x1 = v1 * S[c1];
+  if (m0.x == 1u && m1.x == 1u) {
+    // both groups lie inside a single row each: plain butterfly sums, one slot per group
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      x0 += __shfl_xor_sync(0xffffffffu, x0, d);
+      x1 += __shfl_xor_sync(0xffffffffu, x1, d);
+    }
+    if (lane == 0) {
+      scratch[m0.y] = x0;
+      if (on1) scratch[m1.y] = x1;
+    }
+    return;
+  }
+  const uint32_t le0 = m0.x & le_mask, le1 = m1.x & le_mask;
+  const int ss0 = 31 - __clz(le0), ss1 = 31 - __clz(le1);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double y0 = __shfl_up_sync(0xffffffffu, x0, d);
+    const double y1 = __shfl_up_sync(0xffffffffu, x1, d);
+    x0 += (lane - d >= ss0) ? y0 : 0.0;
+    x1 += (lane - d >= ss1) ? y1 : 0.0;
+  }
+  const bool end0 = (lane == 31) || ((m0.x >> (lane + 1)) & 1u);
+  const bool end1 = (lane == 31) || ((m1.x >> (lane + 1)) & 1u);
+  if (end0) scratch[m0.y + __popc(le0) - 1] = x0;
+  if (on1 && end1) scratch[m1.y + __popc(le1) - 1] = x1;
+}
+
+// Consumer warps: interpret the items of one section out of the ring (rounds, see plan.h).
+// Every warp reads every item header, so all of them execute the same barriers:
+//   first group item of a round  -> the previous round's row updates are complete
+//   first row item of a round    -> the round's segment sums are all in the scratch
+// TOP sections (kTop): the rows of a level are shared out over the CTAs of the cluster; results are
+// stored into every CTA's replica of the top vector and a cluster-wide barrier separates levels.
+template <bool kTop>
+__device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
+  const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec], nlev = cx.D->sec_nlevels[sec];
+  double* S = cx.S;
+  double* scratch = cx.scratch;
+  const int lane = cx.lane, warp = cx.warp;
+  const int tid = warp * 32 + lane;
+  const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // bits 0..lane
   uint32_t lvl = 0;
-  for (; s < e; ++s) {
-    const SliceHdr h = slices[s];
-    while (lvl < h.level) {
-      cta_barrier();
+  for (uint32_t ch = c0; ch < c1; ++ch) {
+    const uint32_t stage = cx.stage;
+    mbar_wait(&cx.full_bar[stage], cx.phase);
+    const uint8_t* chunk = cx.ring + stage * kChunkBytes;
+    uint32_t off = 0;
+    while (off < (uint32_t)kChunkBytes) {
+      const uint4 hq = *reinterpret_cast<const uint4*>(chunk + off);
+      const uint32_t bytes = hq.x;
+      if (bytes == 0) break;
+      const uint32_t type = hq.y & 0xffu, count = hq.y >> 16, first = hq.z;
+      if (kTop) {
+        while (lvl < hq.w) {
+          cluster_level_sync(cx);
+          ++lvl;
+        }
+      }
+      if (first == 0 && !(cx.dbg_flags & 2)) consumer_barrier();
+      if (!(cx.dbg_flags & 1)) {
+        if (type == kItemGroups) {
+          const uint8_t* recs = chunk + off + 16;
+          for (uint32_t i = (uint32_t)(warp - (int)(first & (kWarps - 1))) & (kWarps - 1); i < count; i += 2 * kWarps) {
+            const bool on1 = i + kWarps < count;
+            const uint8_t* g0 = recs + (size_t)i * sizeof(GroupRec);
+            const uint8_t* g1 = on1 ? g0 + (size_t)kWarps * sizeof(GroupRec) : g0;
+            process_groups2(g0, g1, on1, S, scratch, lane, le_mask);
+          }
+        } else {
+          const uint4* recs = reinterpret_cast<const uint4*>(chunk + off + 16);
+          for (uint32_t i = (uint32_t)(tid - (int)(first & (kWarps * 32 - 1))) & (kWarps * 32 - 1); i < count;
+               i += kWarps * 32) {
+            const uint4 q = recs[i];
+            const uint32_t ns = q.y & 0x7fffu, dst = q.y >> 16, slot0 = q.x & 0xffffu;
+            const bool fresh = (q.y & kRowFresh) != 0;
+            const double dg = __hiloint2double((int)q.w, (int)q.z);
+            double sum = 0.0;
+            for (uint32_t s2 = 0; s2 < ns; ++s2) sum += scratch[slot0 + s2];
+            const double r = ((fresh ? 0.0 : S[dst]) - sign * sum) / dg;
+            S[dst] = r;
+            if (kTop && (q.x & kRowBcast)) {
+              for (int c = 0; c < cx.D->csize; ++c)
+                if (c != cx.D->rank) cx.cluster->map_shared_rank(S, c)[dst] = r;
+            }
+          }
+        }
+      }
+      off += bytes;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&cx.empty_bar[stage]);
+    if (++cx.stage == cx.nst) {
+      cx.stage = 0;
+      cx.phase ^= 1u;
+    }
+  }
+  if (kTop) {
+    while (lvl < nlev) {
+      cluster_level_sync(cx);
       ++lvl;
     }
-    const int tl = h.tlog2 & 7;
-    const bool fresh = (h.tlog2 & 0x80) != 0;
-    const int T = 1 << tl;
-    const int g = lane >> tl;
-    const int t = lane & (T - 1);
-    const bool act = g < (int)h.nrows;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    uint32_t dst = 0;
-    double dg = 1.0;
-    // keep the L2 ahead of this warp's strictly sequential streams
-    if (lane == 1) prefetch_l2(slices + s + 48);
-    if (lane == 2) prefetch_l2(rows + h.row0 + 96);
-    if (act) {
-      const RowRec rr = rows[h.row0 + g];
-      dst = rr.dst;
-      dg = rr.diag;
-      const double* v = vals + rr.ebeg;
-      const uint16_t* c = cols + rr.ebeg;
-      const int len = rr.len;
-      int k = t;
-      for (; k + 3 * T < len; k += 4 * T) {
-        const double v0 = __ldg(v + k), v1 = __ldg(v + k + T), v2 = __ldg(v + k + 2 * T),
-                     v3 = __ldg(v + k + 3 * T);
-        const uint32_t c0 = __ldg(c + k), c1 = __ldg(c + k + T), c2 = __ldg(c + k + 2 * T),
-                       c3 = __ldg(c + k + 3 * T);
-        acc0 = fma(v0, S[c0], acc0);
-        acc1 = fma(v1, S[c1], acc1);
-        acc2 = fma(v2, S[c2], acc2);
-        acc3 = fma(v3, S[c3], acc3);
-      }
-      for (; k < len; k += T) acc0 = fma(__ldg(v + k), S[__ldg(c + k)], acc0);
-      if (t == 0) {  // one lane per row: the lines this row will be followed by, kPrefetchAhead later
-        const double* pv = v + kPrefetchAhead;
-        const uint16_t* pc = c + kPrefetchAhead;
-        for (int q = 0; q < len; q += 16) prefetch_l2(pv + q);
-        for (int q = 0; q < len; q += 64) prefetch_l2(pc + q);
-      }
-    }
-    double acc = (acc0 + acc1) + (acc2 + acc3);
-    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (act && t == 0) S[dst] = ((fresh ? 0.0 : S[dst]) - sign * acc) / dg;
-  }
-  while (lvl < nlev) {
-    cta_barrier();
-    ++lvl;
+  } else if (!(cx.dbg_flags & 2)) {
+    consumer_barrier();  // the section's last round is complete
   }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) schur_stream_kernel(const StreamParams P) {
-  extern __shared__ double S[];
+__global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const StreamParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ CtaDesc D;
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t lvl_bar;
   if (P.done_at != nullptr && *P.done_at < P.iter) return;
   cg::cluster_group cluster = cg::this_cluster();
+  double* scratch = reinterpret_cast<double*>(smem_raw + (size_t)P.nstages * kChunkBytes);
+  double* S = scratch + kMaxSlots;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.ctas + blockIdx.x);
     uint32_t* dstw = reinterpret_cast<uint32_t*>(&D);
     for (int i = tid; i < (int)(sizeof(CtaDesc) / 4); i += blockDim.x) dstw[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < P.nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kWarps);
+    }
+    mbar_init(&lvl_bar, (uint32_t)P.ctas[blockIdx.x].csize);
+    mbar_fence_init();
   }
   __syncthreads();
   for (int i = tid; i < D.smem_doubles; i += blockDim.x) S[i] = 0.0;
@@ -146,35 +308,90 @@ __global__ void __launch_bounds__(kWarps * 32) schur_stream_kernel(const StreamP
     }
   }
   __syncthreads();
-  // ---- forward ---------------------------------------------------------------------------------
-  if (MODE == MODE_APPLY || MODE == MODE_UNIT) run_section(D, P, S, SEC_INIT, -1.0, warp, lane);
-  if (MODE == MODE_BACKSUB) run_section(D, P, S, SEC_INIT, 1.0, warp, lane);
-  run_section(D, P, S, SEC_FWD, 1.0, warp, lane);
-  if (C > 1) {
-    run_section(D, P, S, SEC_PART, 1.0, warp, lane);
-    cluster.sync();
-    if (rank == 0) {
-      for (int i = tid; i < D.n_top; i += blockDim.x) {
-        double a = S[D.top_off + i];
-        for (int c = 0; c < C; ++c) {
-          const double* rs = cluster.map_shared_rank(S, c);
-          a += rs[D.part_off + i];
-        }
-        S[D.top_off + i] = a;
-      }
-      __syncthreads();
-      run_section(D, P, S, SEC_TOPF, 1.0, warp, lane);
-      run_section(D, P, S, SEC_TOPB, 1.0, warp, lane);
-    }
-    cluster.sync();
-    if (rank != 0) {
-      const double* r0 = cluster.map_shared_rank(S, 0);
-      for (int i = tid; i < D.n_top; i += blockDim.x) S[D.top_off + i] = r0[D.top_off + i];
-      __syncthreads();
-    }
+
+  StreamCtx cx;
+  cx.D = &D;
+  cx.gstream = P.stream + D.stream_off;
+  cx.ring = smem_raw;
+  cx.S = S;
+  cx.scratch = scratch;
+  cx.full_bar = full_bar;
+  cx.empty_bar = empty_bar;
+  cx.lvl_bar = &lvl_bar;
+  cx.lvl_phase = 0;
+  cx.cluster = &cluster;
+  cx.stage = 0;
+  cx.phase = 0;
+  cx.nst = (uint32_t)P.nstages;
+  cx.dbg_flags = P.dbg_flags;
+  cx.warp = warp;
+  cx.lane = lane;
+  const bool producer = warp == kWarps;
+  auto stamp = [&](int i) { if (P.dbg != nullptr && tid == 0) P.dbg[(size_t)blockIdx.x * 16 + i] = clock64(); };
+  stamp(0);
+  constexpr bool kHasInit = MODE == MODE_APPLY || MODE == MODE_UNIT || MODE == MODE_BACKSUB;
+  constexpr double kInitSign = (MODE == MODE_BACKSUB) ? 1.0 : -1.0;
+  constexpr bool kHasGG = MODE == MODE_APPLY || MODE == MODE_UNIT;
+  constexpr bool kHasOut = MODE != MODE_BACKSUB;
+
+  // ---- phase 1: SpMV, forward sweep on the own subtrees, partial products for the top -------------
+  if (producer) {
+    if (kHasInit) produce_section(cx, SEC_INIT);
+    produce_section(cx, SEC_FWD);
+    if (C > 1) produce_section(cx, SEC_PART);
+  } else {
+    if (kHasInit) consume_section<false>(cx, SEC_INIT, kInitSign);
+    stamp(9);
+    consume_section<false>(cx, SEC_FWD, 1.0);
+    stamp(10);
+    if (C > 1) consume_section<false>(cx, SEC_PART, 1.0);
   }
-  // ---- backward --------------------------------------------------------------------------------
-  run_section(D, P, S, SEC_BWD, 1.0, warp, lane);
+  stamp(1);
+  // ---- phase 2: top nodes, shared out over the cluster ----------------------------------------------
+  if (C > 1) {
+    cluster.sync();  // partial products of every CTA are complete (all threads incl. producers)
+    stamp(2);
+    if (producer) {
+      produce_section(cx, SEC_TOPF);
+      produce_section(cx, SEC_TOPB);
+    } else {
+      // every CTA forms the same right-hand side of the top system, b_top (held by rank 0) plus
+      // the partial products of all CTAs, first into the scratch, and only overwrites its replica of
+      // the top vector once all CTAs have finished reading (two cluster-wide barriers per pass)
+      const double* r0 = cluster.map_shared_rank(S, 0);
+      for (int base = 0; base < D.n_top; base += kMaxSlots) {
+        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += kWarps * 32) {
+          double a = r0[D.top_off + i];
+          for (int c = 0; c < C; ++c) {
+            const double* rs = cluster.map_shared_rank(S, c);
+            a += rs[D.part_off + i];
+          }
+          scratch[i - base] = a;
+        }
+        cluster_level_sync(cx);
+        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += kWarps * 32) S[D.top_off + i] = scratch[i - base];
+        cluster_level_sync(cx);
+      }
+      consume_section<true>(cx, SEC_TOPF, 1.0);
+      stamp(3);
+      consume_section<true>(cx, SEC_TOPB, 1.0);
+    }
+    stamp(4);
+    stamp(5);
+  }
+  // ---- phase 3: backward sweep, interface products ---------------------------------------------------
+  if (producer) {
+    produce_section(cx, SEC_BWD);
+    if (kHasGG && rank == 0) produce_section(cx, SEC_GG);
+    if (kHasOut) produce_section(cx, SEC_OUT);
+  } else {
+    consume_section<false>(cx, SEC_BWD, 1.0);
+    stamp(6);
+    if (kHasGG && rank == 0) consume_section<false>(cx, SEC_GG, -1.0);
+    if (kHasOut) consume_section<false>(cx, SEC_OUT, 1.0);
+  }
+  __syncthreads();
+  stamp(7);
   if (MODE == MODE_BACKSUB) {
     double* u = P.uI + D.I_base;
     const int32_t* om = P.imap + D.ownmap_off;
@@ -186,10 +403,6 @@ __global__ void __launch_bounds__(kWarps * 32) schur_stream_kernel(const StreamP
     if (C > 1) cluster.sync();  // nobody leaves while rank 0's top values may still be read
     return;
   }
-  // ---- interface products ----------------------------------------------------------------------
-  if ((MODE == MODE_APPLY || MODE == MODE_UNIT) && rank == 0)
-    run_section(D, P, S, SEC_GG, -1.0, warp, lane);
-  run_section(D, P, S, SEC_OUT, 1.0, warp, lane);
   if (C > 1) cluster.sync();
   if (rank == 0) {
     double* o;
@@ -210,6 +423,7 @@ __global__ void __launch_bounds__(kWarps * 32) schur_stream_kernel(const StreamP
       }
   }
   if (C > 1) cluster.sync();
+  stamp(8);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ struct TmpRow {
   double diag;
   int32_t level;
   int32_t kind;  // 0: S[dst] = (S[dst] - sign*acc)/diag ; 1: S[dst] = -sign*acc/diag
+  int32_t bcast; // result is replicated into every CTA of the cluster (top nodes)
   uint32_t ebeg;  // into the builder's scratch entry arrays
   uint32_t len;
 };
@@ -22,13 +23,6 @@ struct TmpRow {
 struct Scratch {
   std::vector<uint16_t> cols;
   std::vector<double> vals;
-};
-
-struct WarpStream {
-  std::vector<SliceHdr> slices;
-  std::vector<RowRec> rows;
-  std::vector<double> vals;
-  std::vector<uint16_t> cols;
 };
 
 inline int pow2ceil(int v) {
@@ -42,80 +36,136 @@ inline int ilog2(int p) {
   return l;
 }
 
-// Distribute the rows of one section over the warps of a CTA and append them to the streams.
-void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, int target_k, WarpStream* ws,
-                  uint32_t* sec_begin, uint32_t* sec_end, uint32_t& nlevels) {
-  for (int w = 0; w < kWarps; ++w) sec_begin[w] = (uint32_t)ws[w].slices.size();
+// Byte stream of one CTA.
+struct CtaStream {
+  std::vector<uint8_t> bytes;
+  int64_t n_entries = 0, n_rows = 0, n_packets = 0;
+  size_t room() const { return kChunkBytes - (bytes.size() % kChunkBytes); }
+  void pad_to_chunk() {
+    if (bytes.size() % kChunkBytes) bytes.resize(bytes.size() + room(), 0);
+  }
+  template <class T>
+  void put(const T& v) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    bytes.insert(bytes.end(), p, p + sizeof(T));
+  }
+};
+
+// Serialise the rows of one section as rounds (see plan.h).
+void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptions& opt, CtaStream& cs,
+                  uint32_t& chunk0, uint32_t& chunk1, uint32_t& nlevels, int force_levels = -1) {
+  (void)opt;
+  cs.pad_to_chunk();
+  chunk0 = (uint32_t)(cs.bytes.size() / kChunkBytes);
   int maxlev = -1;
-  for (auto& r : rows) maxlev = std::max(maxlev, r.level);
+  for (auto& r : rows) {
+    if (r.level < 0) throw std::runtime_error("internal: negative level");
+    maxlev = std::max(maxlev, r.level);
+  }
   nlevels = (uint32_t)(maxlev + 1);
+  if (force_levels >= 0) {
+    if (force_levels < maxlev + 1) throw std::runtime_error("internal: forced level count too small");
+    nlevels = (uint32_t)force_levels;
+  }
   if (!rows.empty()) {
-    // stable order: by level, then by decreasing length
     std::vector<uint32_t> ord(rows.size());
     std::iota(ord.begin(), ord.end(), 0u);
-    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
-      if (rows[a].level != rows[b].level) return rows[a].level < rows[b].level;
-      return rows[a].len > rows[b].len;
-    });
-    for (auto& r : rows)
-      if (r.level < 0) throw std::runtime_error("internal: negative level");
-    size_t i = 0;
-    std::vector<uint32_t> wrows[kWarps];
-    while (i < ord.size()) {
-      size_t j = i;
-      int lev = rows[ord[i]].level;
-      while (j < ord.size() && rows[ord[j]].level == lev) ++j;
-      // longest-processing-time assignment of rows [i, j) to warps (cost = entries + overhead)
-      uint64_t load[kWarps] = {0};
-      for (int w = 0; w < kWarps; ++w) wrows[w].clear();
-      for (size_t k = i; k < j; ++k) {
-        int best = 0;
-        for (int w = 1; w < kWarps; ++w)
-          if (load[w] < load[best]) best = w;
-        load[best] += rows[ord[k]].len + 8;
-        wrows[best].push_back(ord[k]);
-      }
-      for (int w = 0; w < kWarps; ++w) {
-        auto& lst = wrows[w];
-        // rows of one slice share the update kind
-        std::stable_sort(lst.begin(), lst.end(), [&](uint32_t a, uint32_t b) { return rows[a].kind < rows[b].kind; });
-        size_t p = 0;
-        while (p < lst.size()) {
-          int remaining = 0;
-          while (p + remaining < lst.size() && rows[lst[p + remaining]].kind == rows[lst[p]].kind) ++remaining;
-          int len = (int)rows[lst[p]].len;
-          int t_len = std::min(32, pow2ceil((len + target_k - 1) / std::max(1, target_k)));
-          int t_fill = std::max(1, 32 / pow2ceil(remaining));
-          int t = std::max(t_len, std::min(t_fill, pow2ceil(std::max(1, len))));
-          t = std::min(32, std::max(1, t));
-          int cap = 32 / t;
-          int take = std::min(cap, remaining);
-          SliceHdr h;
-          h.row0 = (uint32_t)ws[w].rows.size();
-          h.level = (uint16_t)lev;
-          h.tlog2 = (uint8_t)(ilog2(t) | (rows[lst[p]].kind ? 0x80 : 0));
-          h.nrows = (uint8_t)take;
-          ws[w].slices.push_back(h);
-          for (int q = 0; q < take; ++q) {
-            const TmpRow& tr = rows[lst[p + q]];
-            RowRec rr;
-            rr.ebeg = (uint32_t)ws[w].vals.size();
-            rr.len = (uint16_t)tr.len;
-            rr.dst = tr.dst;
-            rr.diag = tr.diag;
-            ws[w].rows.push_back(rr);
-            ws[w].vals.insert(ws[w].vals.end(), sc.vals.begin() + tr.ebeg,
-                              sc.vals.begin() + tr.ebeg + tr.len);
-            ws[w].cols.insert(ws[w].cols.end(), sc.cols.begin() + tr.ebeg,
-                              sc.cols.begin() + tr.ebeg + tr.len);
-          }
-          p += take;
+    std::stable_sort(ord.begin(), ord.end(),
+                     [&](uint32_t a, uint32_t b) { return rows[a].level < rows[b].level; });
+    std::vector<GroupRec> groups;
+    std::vector<RowRec> recs;
+    auto flush_round = [&](int lev) {
+      if (recs.empty()) return;
+      // group records, split into items at chunk boundaries
+      size_t g = 0;
+      while (g < groups.size()) {
+        size_t room = cs.room();
+        if (room < sizeof(ItemHdr) + sizeof(GroupRec)) {
+          cs.pad_to_chunk();
+          room = kChunkBytes;
         }
+        const size_t fit = std::min(groups.size() - g, (room - sizeof(ItemHdr)) / sizeof(GroupRec));
+        ItemHdr h;
+        std::memset(&h, 0, sizeof(h));
+        h.bytes = (uint32_t)(sizeof(ItemHdr) + fit * sizeof(GroupRec));
+        h.type = kItemGroups;
+        h.count = (uint16_t)fit;
+        h.first = (uint32_t)g;
+        h.level = (uint32_t)lev;
+        cs.put(h);
+        for (size_t k = 0; k < fit; ++k) cs.put(groups[g + k]);
+        g += fit;
       }
-      i = j;
+      size_t r = 0;
+      while (r < recs.size()) {
+        size_t room = cs.room();
+        if (room < sizeof(ItemHdr) + sizeof(RowRec)) {
+          cs.pad_to_chunk();
+          room = kChunkBytes;
+        }
+        const size_t fit = std::min(recs.size() - r, (room - sizeof(ItemHdr)) / sizeof(RowRec));
+        ItemHdr h;
+        std::memset(&h, 0, sizeof(h));
+        h.bytes = (uint32_t)(sizeof(ItemHdr) + fit * sizeof(RowRec));
+        h.type = kItemRows;
+        h.count = (uint16_t)fit;
+        h.first = (uint32_t)r;
+        h.level = (uint32_t)lev;
+        cs.put(h);
+        for (size_t k = 0; k < fit; ++k) cs.put(recs[r + k]);
+        r += fit;
+      }
+      cs.n_rows += (int64_t)recs.size();
+      cs.n_packets += 1;
+      groups.clear();
+      recs.clear();
+    };
+    uint32_t nslots = 0;   // slots used by the current round
+    uint32_t fill = 32;    // entries in the last group (32 = need a new one)
+    int cur_level = rows[ord[0]].level;
+    for (uint32_t oi : ord) {
+      const TmpRow& tr = rows[oi];
+      // slots this row needs if appended to the current round
+      const uint32_t first_part = tr.len == 0 ? 0u : std::min<uint32_t>(tr.len, fill == 32 ? 32u : 32u - fill);
+      const uint32_t need = tr.len == 0 ? 0u : 1u + (tr.len - first_part + 31u) / 32u;
+      if (tr.level != cur_level || nslots + need > (uint32_t)kMaxSlots || recs.size() >= 60000) {
+        flush_round(cur_level);
+        nslots = 0;
+        fill = 32;
+        cur_level = tr.level;
+      }
+      RowRec rr;
+      rr.slot0 = nslots | (tr.bcast ? kRowBcast : 0u);
+      rr.dst = tr.dst;
+      rr.diag = tr.diag;
+      uint32_t used = 0;
+      for (uint32_t k = 0; k < tr.len; ++k) {
+        if (fill == 32) {
+          GroupRec g;
+          std::memset(&g, 0, sizeof(g));
+          g.first_slot = nslots;  // slot of the segment starting at lane 0
+          groups.push_back(g);
+          fill = 0;
+        }
+        GroupRec& g = groups.back();
+        if (k == 0 || fill == 0) {  // a new segment starts here
+          g.heads |= (1u << fill);
+          ++nslots;
+          ++used;
+        }
+        g.val[fill] = sc.vals[tr.ebeg + k];
+        g.col[fill] = sc.cols[tr.ebeg + k];
+        ++fill;
+      }
+      if (used > 0x7fffu) throw std::runtime_error("internal: row needs too many slots");
+      rr.nslots = (uint16_t)(used | (tr.kind ? kRowFresh : 0));
+      recs.push_back(rr);
+      cs.n_entries += tr.len;
     }
+    flush_round(cur_level);
   }
-  for (int w = 0; w < kWarps; ++w) sec_end[w] = (uint32_t)ws[w].slices.size();
+  cs.pad_to_chunk();
+  chunk1 = (uint32_t)(cs.bytes.size() / kChunkBytes);
 }
 
 }  // namespace
@@ -223,9 +273,9 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         // a top node costs its row and column once per sweep, processed by rank 0 alone while
         // the other CTAs wait (over-estimate: its entries in subtree columns run in parallel)
         top_w += 2 * wt[r];
-        if (top_w >= best_cost) break;  // cannot improve any more
+        if (top_w / C >= best_cost) break;  // cannot improve any more
         if (cptr[r + 1] - cptr[r] >= 2) {  // the cost only drops at branching nodes
-          int64_t cost = lpt(Qw, nullptr) + top_w;
+          int64_t cost = lpt(Qw, nullptr) + top_w / C;  // top rows are shared out over the C CTAs
           if (cost < best_cost) {
             best_cost = cost;
             best_k = order.size();
@@ -434,6 +484,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     r.diag = dg;
     r.level = level;
     r.kind = kind;
+    r.bcast = 0;
     r.ebeg = (uint32_t)sc.vals.size();
     r.len = 0;
     rows.push_back(r);
@@ -445,7 +496,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   };
 
   for (int c = 0; c < C; ++c) {
-    WarpStream ws[kWarps];
+    CtaStream cs;
     CtaDesc& D = out.ctas[c];
     std::memset(&D, 0, sizeof(D));
     D.rank = c;
@@ -460,8 +511,8 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     D.own_off = own_off;
     D.smem_doubles = own_off + max_own;
     D.top_sz = top_sz;
-    auto section = [&](int s) {
-      emit_section(rows, sc, opt.target_k, ws, D.sec_begin[s], D.sec_end[s], D.sec_nlevels[s]);
+    auto section = [&](int s, int force_levels = -1) {
+      emit_section(rows, sc, opt, cs, D.sec_chunk0[s], D.sec_chunk1[s], D.sec_nlevels[s], force_levels);
       rows.clear();
       sc.cols.clear();
       sc.vals.clear();
@@ -540,11 +591,51 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
           }
       }
     section(SEC_PART);
-    // SEC_TOPF / SEC_TOPB (rank 0)
-    if (c == 0) emit_forward([&](int i) { return owner[i] < 0; });
-    section(SEC_TOPF);
-    if (c == 0) emit_backward([&](int i) { return owner[i] < 0; });
-    section(SEC_TOPB);
+    // SEC_TOPF / SEC_TOPB: every CTA builds the same row list and keeps its share of each level
+    // (greedy balance on entries, identical on all ranks); results are broadcast (bcast rows).
+    auto keep_share = [&]() -> int {
+      int maxlev = -1;
+      for (auto& r : rows) maxlev = std::max(maxlev, r.level);
+      std::vector<uint32_t> ord(rows.size());
+      std::iota(ord.begin(), ord.end(), 0u);
+      std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+        if (rows[a].level != rows[b].level) return rows[a].level < rows[b].level;
+        return rows[a].len > rows[b].len;
+      });
+      std::vector<char> mine_row(rows.size(), 0);
+      std::vector<uint64_t> load(C, 0);
+      int cur = -1;
+      for (uint32_t oi : ord) {
+        if (rows[oi].level != cur) {
+          cur = rows[oi].level;
+          std::fill(load.begin(), load.end(), 0);
+        }
+        int best = 0;
+        for (int k = 1; k < C; ++k)
+          if (load[k] < load[best]) best = k;
+        load[best] += rows[oi].len + 4;
+        mine_row[oi] = best == c;
+      }
+      std::vector<TmpRow> kept;
+      for (size_t k = 0; k < rows.size(); ++k)
+        if (mine_row[k]) {
+          rows[k].bcast = 1;
+          kept.push_back(rows[k]);
+        }
+      rows.swap(kept);
+      return maxlev + 1;
+    };
+    int top_levels = 0;
+    if (C > 1) {
+      emit_forward([&](int i) { return owner[i] < 0; });
+      top_levels = keep_share();
+    }
+    section(SEC_TOPF, top_levels);
+    if (C > 1) {
+      emit_backward([&](int i) { return owner[i] < 0; });
+      top_levels = keep_share();
+    }
+    section(SEC_TOPB, top_levels);
     // SEC_BWD
     emit_backward([&](int i) { return owner[i] == c; });
     section(SEC_BWD);
@@ -572,20 +663,13 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     }
     section(SEC_OUT);
 
-    // concatenate the warp streams into the plan pools
-    int64_t cta_entries = 0;
-    for (int w = 0; w < kWarps; ++w) {
-      D.slice_base[w] = out.slices.size();
-      D.row_base[w] = out.rows.size();
-      D.ent_base[w] = out.vals.size();
-      D.n_ent[w] = (uint32_t)ws[w].vals.size();
-      out.slices.insert(out.slices.end(), ws[w].slices.begin(), ws[w].slices.end());
-      out.rows.insert(out.rows.end(), ws[w].rows.begin(), ws[w].rows.end());
-      out.vals.insert(out.vals.end(), ws[w].vals.begin(), ws[w].vals.end());
-      out.cols.insert(out.cols.end(), ws[w].cols.begin(), ws[w].cols.end());
-      cta_entries += (int64_t)ws[w].vals.size();
-    }
-    out.max_cta_entries = std::max(out.max_cta_entries, cta_entries);
+    // append the CTA stream to the plan's stream pool
+    D.stream_off = out.stream.size();
+    out.stream.insert(out.stream.end(), cs.bytes.begin(), cs.bytes.end());
+    out.n_entries += cs.n_entries;
+    out.n_rows += cs.n_rows;
+    out.n_packets += cs.n_packets;
+    out.max_cta_entries = std::max(out.max_cta_entries, cs.n_entries);
     for (int s = 0; s < NSEC; ++s) out.max_levels = std::max(out.max_levels, (int)D.sec_nlevels[s]);
     // position -> original interior index maps
     D.ownmap_off = (int64_t)out.imap.size();

@@ -22,34 +22,66 @@
 
 namespace kb {
 
-constexpr int kWarps = 8;  // warps per CTA (256 threads)
+constexpr int kWarps = 8;          // consumer warps per CTA; one more warp feeds the ring (288 threads)
+constexpr int kChunkBytes = 16384; // unit of the TMA bulk copies global -> shared ring
 
 enum Section : int {
   SEC_INIT = 0,  // w   = A_IG x_d                 (rows: interior nodes touching the interface)
   SEC_FWD,       // L y = w      on the CTA's own subtrees, level by level
   SEC_PART,      // -sum_{j in own} L[i,j] y_j     for top rows i (combined by rank 0)
-  SEC_TOPF,      // forward solve on the top nodes (rank 0)
-  SEC_TOPB,      // backward solve on the top nodes (rank 0)
+  SEC_TOPF,      // forward solve on the top nodes: rows of a level shared out over the cluster's CTAs,
+  SEC_TOPB,      // backward solve likewise; results broadcast over DSMEM, cluster barrier per level
   SEC_BWD,       // L^T v = y    on the CTA's own subtrees (top values replicated)
   SEC_GG,        // out = A_GG x_d                 (rank 0)
   SEC_OUT,       // out -= A_IG^T v  restricted to the CTA's own columns
   NSEC
 };
 
-// A slice = up to 32 >> tlog2 consecutive row records processed by one warp with 1 << tlog2
-// lanes per row.
-struct SliceHdr {
-  uint32_t row0;   // first row record (relative to the warp's row stream)
-  uint16_t level;  // dependency level inside the section
-  uint8_t tlog2;   // bits 0-2: log2(lanes per row); bit 7: "fresh" rows, S[dst] = -sign*acc/diag
-  uint8_t nrows;
+// The program of a CTA is ONE byte stream, cut into chunks of kChunkBytes that a producer warp
+// copies into a shared-memory ring with cp.async.bulk (TMA) far ahead of the consumers.  A chunk
+// holds whole items (a zero header terminates it early); every section starts on a chunk boundary.
+//
+// Work is organised in ROUNDS.  A round is a set of independent rows (same dependency level):
+//   pass 1  the entries of all its rows, concatenated row after row into one flat array, are cut
+//           into groups of 32; consumer warp w takes groups w, w+8, ...: lane l multiplies entry l
+//           by S[col], a segmented warp scan (segment = run of one row inside the group) reduces
+//           the products and every segment's sum goes to its own slot of a scratch array;
+//   pass 2  one thread per row adds the row's slots in order and updates
+//           S[dst] = (S[dst] - sign * sum) / diag      (fresh rows: S[dst] = -sign * sum / diag).
+// All lanes are busy whatever the row lengths, shared-memory reads of the stream are contiguous,
+// and every sum has a fixed association order (bit-reproducible).  A CTA barrier separates pass 1
+// from pass 2 and one round from the next.
+//
+// Items (16-byte header + payload):
+//   kItemGroups : `count` group records; `first` = index of the first one inside its round
+//   kItemRows   : `count` row records;   `first` = index of the first one inside its round
+constexpr uint8_t kItemGroups = 1, kItemRows = 2;
+constexpr int kMaxSlots = 1024;    // scratch slots (segment sums) a round may use
+struct alignas(16) ItemHdr {
+  uint32_t bytes;   // size of the item incl. this header, 0 = end of chunk
+  uint8_t type;
+  uint8_t pad0_;
+  uint16_t count;
+  uint32_t first;
+  uint32_t level;   // dependency level inside the section (diagnostics / emulator checks)
 };
-static_assert(sizeof(SliceHdr) == 8, "SliceHdr must be 8 bytes");
+static_assert(sizeof(ItemHdr) == 16, "ItemHdr must be 16 bytes");
 
+struct alignas(16) GroupRec {
+  uint32_t heads;       // bit l: entry l starts a segment (bit 0 always set)
+  uint32_t first_slot;  // scratch slot of the first segment; later segments follow consecutively
+  uint32_t pad_[2];
+  double val[32];
+  uint16_t col[32];     // index into the CTA's shared vector S (padding entries: val 0, col 0)
+};
+static_assert(sizeof(GroupRec) == 336, "GroupRec must be 336 bytes");
+
+constexpr uint16_t kRowFresh = 0x8000u;
+constexpr uint32_t kRowBcast = 0x80000000u;  // in slot0: also store the result into every other CTA of the cluster
 struct alignas(16) RowRec {
-  uint32_t ebeg;  // first entry (relative to the warp's entry stream)
-  uint16_t len;
-  uint16_t dst;   // index into the CTA's shared vector S
+  uint32_t slot0;   // first scratch slot of the row | kRowBcast
+  uint16_t nslots;  // number of slots | kRowFresh
+  uint16_t dst;     // index into S
   double diag;
 };
 static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
@@ -63,10 +95,8 @@ struct CtaDesc {
   int64_t topmap_off;  // imap pool: original interior index of top position (n_top entries)
   int64_t I_base;      // offset of the subdomain in concatenated interior vectors
   int64_t G_base;      // offset of the subdomain in concatenated local-interface vectors
-  int64_t out_g_off;   // out_part pool: this CTA's n_gd partial outputs
-  uint64_t slice_base[kWarps], row_base[kWarps], ent_base[kWarps];
-  uint32_t n_ent[kWarps];
-  uint32_t sec_begin[NSEC][kWarps], sec_end[NSEC][kWarps];
+  uint64_t stream_off; // byte offset of the CTA's stream in the stream pool (chunk aligned)
+  uint32_t sec_chunk0[NSEC], sec_chunk1[NSEC];  // chunk range of every section
   uint32_t sec_nlevels[NSEC];
 };
 
@@ -86,21 +116,18 @@ struct DomainIn {
 };
 
 struct DomainPlan {
-  std::vector<CtaDesc> ctas;  // csize descriptors (offsets local to this plan's pools)
-  std::vector<SliceHdr> slices;
-  std::vector<RowRec> rows;
-  std::vector<double> vals;
-  std::vector<uint16_t> cols;
-  std::vector<int32_t> imap;  // ownmap / topmap entries
+  std::vector<CtaDesc> ctas;      // csize descriptors (offsets local to this plan's pools)
+  std::vector<uint8_t> stream;    // concatenated CTA streams (each a multiple of kChunkBytes)
+  std::vector<int32_t> imap;      // ownmap / topmap entries
   // statistics
-  int64_t nnz_L = 0;          // strictly-lower nnz of L
+  int64_t nnz_L = 0;              // strictly-lower nnz of L
+  int64_t n_entries = 0, n_rows = 0, n_packets = 0;   // n_packets = rounds
   int32_t n_top = 0, max_levels = 0;
   int64_t max_cta_entries = 0, top_entries = 0;
 };
 
 struct BuildOptions {
   int csize = 1;
-  int target_k = 4;           // aimed entries per lane per row
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;
   int max_smem_doubles = 28000;

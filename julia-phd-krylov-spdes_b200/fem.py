@@ -15,7 +15,7 @@ from . import capi
 
 class B200SchurOperator:
     def __init__(self, sd, blocks, factors, device=0, csize=None, rank=0, world=1, nccl_id=None,
-                 profile=False):
+                 profile=False, options=None):
         """sd: Subdomains (set_subdomains); blocks: LocalBlocks (prepare_local_schurs);
         factors: [(perm, L)] Cholesky factors of A_II,d (F.p, sparse(F.L))."""
         self.sd = sd
@@ -24,6 +24,8 @@ class B200SchurOperator:
             self.h.set_option("csize", csize)
         if profile:
             self.h.set_option("profile", 1)
+        for k, v in (options or {}).items():
+            self.h.set_option(k, v)
         n_I = [v.size for v in sd.node_Id]
         n_gd = [g.size for g in sd.gamma_l2g]
         self.h.set_topology(n_I, n_gd, [g + 1 for g in sd.gamma_l2g], sd.node_gamma_cnt)

@@ -10,17 +10,34 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2001
 ndom = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 csizes = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [4]
 do_pcg = len(sys.argv) > 4 and sys.argv[4] == 'pcg'
+stages = [int(v) for v in os.environ.get('STAGES', '6').split(',')]
 t = time.time(); pr = PB.build_problem(nx, ndom, ireal=1); print('host prep %.1fs' % (time.time() - t), flush=True)
 B, parts = PB.algorithmic_bytes_per_iteration(pr)
 print('B_iter GB', B / 1e9, {k: v / 1e9 for k, v in parts.items()}, flush=True)
-for cs in csizes:
+for cs, nst in [(a, b) for a in csizes for b in stages]:
     t = time.time()
-    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=cs, profile=True)
+    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=cs, profile=True, options={'stages': nst})
     S.h.finalize(); tf = time.time() - t
     st = S.h.stats()
     ms = S.h.time_kernel(0, 20)
     alg = parts['trisolve'] + parts['spmv']
-    print(f"csize={cs} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
+    print(f"csize={cs} stages={nst} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
+    for fl in [int(v) for v in os.environ.get('FLAGS', '').split(',') if v]:
+        S.h.set_option('dbg_flags', fl); print(f'   dbg_flags={fl}: schur kernel {S.h.time_kernel(0, 10):.3f} ms', flush=True); S.h.set_option('dbg_flags', 0)
+    if os.environ.get('DBG'):
+        S.h.set_option('debug_timing', 1)
+        S.h.set_option('dbg_flags', int(os.environ.get('DBGFLAGS', '0')))
+        S.h.time_kernel(0, 1)
+        st_ = S.h.debug_stamps(int(st['n_cta'])).astype(float)
+        cs_ = cs
+        r0 = st_[0::cs_]; r1 = st_[1::cs_] if cs_ > 1 else st_
+        def seg(a, i, j): return (a[:, j] - a[:, i]) / 1.9e3   # us at ~1.9 GHz
+        names = [('init', 0, 9), ('INIT sec', 9, 9), ('FWD', 9, 10), ('PART', 10, 1), ('wait sync1', 1, 2), ('TOPF(rank0)', 2, 3), ('TOPB', 3, 4), ('wait sync2', 4, 5), ('BWD', 5, 6), ('GG+OUT', 6, 7), ('epilogue', 7, 8), ('total', 0, 8)]
+        for nm, i, j in names:
+            a = seg(r0, i, j); b = seg(r1, i, j)
+            print(f"   {nm:12s} rank0 mean {a.mean():8.1f} max {a.max():8.1f} us | rank1 mean {b.mean():8.1f} max {b.max():8.1f} us")
+        S.h.set_option('debug_timing', 0)
+        S.h.set_option('dbg_flags', 0)
     if do_pcg:
         t = time.time(); Sd = S.assemble_local_schurs(); print('  assemble S_d %.1fs' % (time.time() - t), flush=True)
         t = time.time(); Pi = [PB.pinv_sym(Sd[d]) for d in range(ndom)]; print('  pinv %.1fs' % (time.time() - t), flush=True)

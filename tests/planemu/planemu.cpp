@@ -26,30 +26,82 @@ struct Emu {
   explicit Emu(const DomainPlan& p) : P(p) {
     for (auto& d : P.ctas) S.emplace_back((size_t)d.smem_doubles, 0.0);
   }
-  void section(int c, int sec, double sign) {
+  // Interprets the chunks of one section exactly like the consumer warps (rounds: pass 1 = group
+  // records -> segment sums in scratch slots, pass 2 = row records).  Checks: a value written in
+  // a level is not read in the same level; slots are written before they are summed and never
+  // twice per round; items are well formed.
+  // only_level >= 0: process just the items of that level (top sections, run level by level over all CTAs)
+  void section(int c, int sec, double sign, int only_level = -1) {
     const CtaDesc& D = P.ctas[c];
     std::vector<double>& s = S[c];
-    for (uint32_t lev = 0; lev < D.sec_nlevels[sec]; ++lev) {
-      std::vector<std::pair<int, double>> writes;
-      for (int w = 0; w < kWarps; ++w)
-        for (uint32_t si = D.sec_begin[sec][w]; si < D.sec_end[sec][w]; ++si) {
-          const SliceHdr& h = P.slices[D.slice_base[w] + si];
-          if (h.level != lev) continue;
-          const bool fresh = (h.tlog2 & 0x80) != 0;
-          if (h.nrows > (32 >> (h.tlog2 & 7))) throw std::runtime_error("slice holds too many rows");
-          for (int g = 0; g < h.nrows; ++g) {
-            const RowRec& r = P.rows[D.row_base[w] + h.row0 + g];
+    std::vector<int> wrote_level(s.size(), -1);
+    std::vector<double> scratch(kMaxSlots, 0.0);
+    std::vector<char> slot_set(kMaxSlots, 0);
+    uint32_t expect_group = 0, expect_row = 0;
+    for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
+      const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
+      size_t off = 0;
+      while (off + sizeof(ItemHdr) <= (size_t)kChunkBytes) {
+        ItemHdr h;
+        std::memcpy(&h, base + off, sizeof(h));
+        if (h.bytes == 0) break;
+        if (off + h.bytes > (size_t)kChunkBytes) throw std::runtime_error("item crosses its chunk");
+        if (h.level >= D.sec_nlevels[sec]) throw std::runtime_error("level beyond nlevels");
+        if (only_level >= 0 && (int)h.level != only_level) { off += h.bytes; continue; }
+        if (h.type == kItemGroups) {
+          if (h.bytes != sizeof(ItemHdr) + h.count * sizeof(GroupRec)) throw std::runtime_error("bad groups item size");
+          if (h.first == 0) { std::fill(slot_set.begin(), slot_set.end(), 0); expect_group = 0; expect_row = 0; }
+          if (h.first != expect_group) throw std::runtime_error("group numbering broken");
+          for (uint32_t i = 0; i < h.count; ++i) {
+            GroupRec g;
+            std::memcpy(&g, base + off + sizeof(ItemHdr) + (size_t)i * sizeof(GroupRec), sizeof(g));
+            if (!(g.heads & 1u)) throw std::runtime_error("group without a head at lane 0");
+            uint32_t slot = g.first_slot;
             double acc = 0.0;
-            for (uint32_t k = 0; k < r.len; ++k) {
-              uint64_t e = D.ent_base[w] + r.ebeg + k;
-              if (r.ebeg + k >= D.n_ent[w]) throw std::runtime_error("entry out of range");
-              if (P.cols[e] >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
-              acc += P.vals[e] * s[P.cols[e]];
+            for (int l = 0; l < 32; ++l) {
+              if (l > 0 && ((g.heads >> l) & 1u)) {
+                if (slot >= (uint32_t)kMaxSlots || slot_set[slot]) throw std::runtime_error("bad slot");
+                scratch[slot] = acc; slot_set[slot] = 1; ++slot; acc = 0.0;
+              }
+              const uint32_t col = g.col[l];
+              if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
+              if (g.val[l] != 0.0 && wrote_level[col] == (int)h.level) throw std::runtime_error("reads a value produced in the same level");
+              acc += g.val[l] * s[col];
             }
-            writes.emplace_back((int)r.dst, ((fresh ? 0.0 : s[r.dst]) - sign * acc) / r.diag);
+            if (slot >= (uint32_t)kMaxSlots || slot_set[slot]) throw std::runtime_error("bad slot");
+            scratch[slot] = acc; slot_set[slot] = 1;
           }
+          expect_group += h.count;
+        } else if (h.type == kItemRows) {
+          if (h.bytes != sizeof(ItemHdr) + h.count * sizeof(RowRec)) throw std::runtime_error("bad rows item size");
+          if (h.first == 0 && expect_group == 0) { std::fill(slot_set.begin(), slot_set.end(), 0); expect_row = 0; }
+          if (h.first != expect_row) throw std::runtime_error("row numbering broken");
+          for (uint32_t i = 0; i < h.count; ++i) {
+            RowRec r;
+            std::memcpy(&r, base + off + sizeof(ItemHdr) + (size_t)i * sizeof(RowRec), sizeof(r));
+            const uint32_t ns = r.nslots & 0x7fffu;
+            const bool bcast = (r.slot0 & kRowBcast) != 0;
+            r.slot0 &= 0xffffu;
+            const bool fresh = (r.nslots & kRowFresh) != 0;
+            double sum = 0.0;
+            for (uint32_t k = 0; k < ns; ++k) {
+              if (r.slot0 + k >= (uint32_t)kMaxSlots || !slot_set[r.slot0 + k]) throw std::runtime_error("row sums an unwritten slot");
+              sum += scratch[r.slot0 + k];
+            }
+            if (r.dst >= (uint32_t)D.smem_doubles) throw std::runtime_error("dst out of range");
+            s[r.dst] = ((fresh ? 0.0 : s[r.dst]) - sign * sum) / r.diag;
+            wrote_level[r.dst] = (int)h.level;
+            if (bcast)
+              for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][r.dst] = s[r.dst];
+          }
+          expect_row += h.count;
+          expect_group = 0;  // the round's groups are complete once its rows start
+          if (false) (void)0;
+        } else {
+          throw std::runtime_error("unknown item type");
         }
-      for (auto& wv : writes) s[wv.first] = wv.second;
+        off += h.bytes;
+      }
     }
   }
 };
@@ -90,16 +142,23 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       E.section(c, SEC_FWD, 1.0);
       E.section(c, SEC_PART, 1.0);
     }
-    // cluster sync; rank 0 combines
-    for (int t = 0; t < D0.n_top; ++t) {
-      double a = E.S[0][D0.top_off + t];
-      for (int c = 0; c < C; ++c) a += E.S[c][P.ctas[c].part_off + t];
-      E.S[0][D0.top_off + t] = a;
+    // cluster sync; every CTA forms the combined top right-hand side; top levels run over all CTAs
+    if (C > 1) {
+      std::vector<double> comb(D0.n_top);
+      for (int t = 0; t < D0.n_top; ++t) {
+        double a = E.S[0][D0.top_off + t];
+        for (int c = 0; c < C; ++c) a += E.S[c][P.ctas[c].part_off + t];
+        comb[t] = a;
+      }
+      for (int c = 0; c < C; ++c)
+        for (int t = 0; t < D0.n_top; ++t) E.S[c][P.ctas[c].top_off + t] = comb[t];
+      for (int sec : {SEC_TOPF, SEC_TOPB}) {
+        for (int c = 1; c < C; ++c)
+          if (P.ctas[c].sec_nlevels[sec] != D0.sec_nlevels[sec]) throw std::runtime_error("top level counts differ across CTAs");
+        for (uint32_t lev = 0; lev < D0.sec_nlevels[sec]; ++lev)
+          for (int c = 0; c < C; ++c) E.section(c, sec, 1.0, (int)lev);
+      }
     }
-    E.section(0, SEC_TOPF, 1.0);
-    E.section(0, SEC_TOPB, 1.0);
-    for (int c = 1; c < C; ++c)
-      for (int t = 0; t < D0.n_top; ++t) E.S[c][P.ctas[c].top_off + t] = E.S[0][D0.top_off + t];
     for (int c = 0; c < C; ++c) {
       E.section(c, SEC_BWD, 1.0);
       if (mode == MODE_APPLY) E.section(c, SEC_GG, -1.0);
@@ -125,20 +184,14 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       stats[1] = (double)P.n_top;
       stats[2] = (double)P.max_levels;
       stats[3] = (double)P.max_cta_entries;
-      stats[4] = (double)P.vals.size();
-      stats[5] = (double)P.slices.size();
-      stats[6] = (double)P.rows.size();
+      stats[4] = (double)P.n_entries;
+      stats[5] = (double)P.n_packets;
+      stats[6] = (double)P.n_rows;
       stats[7] = (double)D0.smem_doubles;
-      double topent = 0;
-      for (int w = 0; w < kWarps; ++w)
-        for (int sec : {SEC_TOPF, SEC_TOPB})
-          for (uint32_t si = D0.sec_begin[sec][w]; si < D0.sec_end[sec][w]; ++si) {
-            const SliceHdr& h = P.slices[D0.slice_base[w] + si];
-            for (int g = 0; g < h.nrows; ++g) topent += P.rows[D0.row_base[w] + h.row0 + g].len;
-          }
-      stats[8] = topent;
+      stats[8] = (double)P.stream.size();
       stats[9] = (double)std::max(D0.sec_nlevels[SEC_TOPF], D0.sec_nlevels[SEC_TOPB]);
       stats[10] = (double)std::max(D0.sec_nlevels[SEC_FWD], D0.sec_nlevels[SEC_BWD]);
+
     }
     return 0;
   } catch (const std::exception& e) {

@@ -105,16 +105,21 @@ def test_golden_vectors_on_gpu():
 
 
 def _pcg_floor(pr):
-    """Difference between two CPU restatements that differ only in rounding."""
+    """Differences between two CPU restatements that differ only in rounding (scipy-LU vs Cholesky
+    interior solves), at equal iteration index: (oracle run, floor on x, floor on the residual history)."""
     inner, Sd, Pi, bs = get_oracle_ops(pr)
     sd, lb = pr.sd, pr.blocks
     cm = CpuModel(sd, lb, pr.factors, Pi)
     xo, ito, reso = OS.pcg(lambda v: E.apply_local_schurs(lb, inner, sd, v), bs, np.zeros(sd.n_gamma),
                            lambda r: E.apply_neumann_neumann_schur(Pi, sd, r))
-    k = ito
-    xc, itc, resc = cm.pcg(bs, np.zeros(sd.n_gamma), maxit=k)
-    floor = np.linalg.norm(xc - xo) / np.linalg.norm(xo) if itc == k else 1e-6
-    return (xo, ito, reso), floor
+    xc, itc, resc = cm.pcg(bs, np.zeros(sd.n_gamma), maxit=ito)
+    k = min(itc, ito)
+    xok, _, _ = OS.pcg(lambda v: E.apply_local_schurs(lb, inner, sd, v), bs, np.zeros(sd.n_gamma),
+                       lambda r: E.apply_neumann_neumann_schur(Pi, sd, r), maxit=k)
+    xck, _, _ = cm.pcg(bs, np.zeros(sd.n_gamma), maxit=k)
+    floor_x = np.linalg.norm(xck - xok) / np.linalg.norm(xok)
+    floor_r = np.abs(resc[:k] - reso[:k]).max() / reso[:k].max()
+    return (xo, ito, reso), floor_x, floor_r
 
 
 @pytest.mark.parametrize("nx,ndom,csize,median", [(33, 4, 2, False), (65, 16, 4, False), (65, 16, 4, True),
@@ -122,10 +127,10 @@ def _pcg_floor(pr):
 def test_pcg_parity(nx, ndom, csize, median):
     pr, S, M = gpu_ops(nx, ndom, csize, median)
     inner, Sd, Pi, bs = get_oracle_ops(pr)
-    (xo, ito, reso), floor = _pcg_floor(pr)
+    (xo, ito, reso), floor_x, floor_r = _pcg_floor(pr)
     x0 = np.zeros(pr.sd.n_gamma)
     x, it, res, tm = solvers.pcg(S, bs, x0, M, return_timings=True)
-    assert x is x0 or np.array_equal(x, x0)                       # in-place update (cg.jl:97)
+    assert np.array_equal(x, x0)                                  # in-place update (cg.jl:97)
     assert abs(it - ito) <= 1                                     # stopping index within +-1
     assert res.size == it and res[-1] <= 1e-7 * np.linalg.norm(bs)
     k = min(it, ito)
@@ -133,11 +138,10 @@ def test_pcg_parity(nx, ndom, csize, median):
     xk, itk, resk = solvers.pcg(S, bs, np.zeros(pr.sd.n_gamma), M, maxit=k)
     xok, _, _ = OS.pcg(lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v), bs, np.zeros(pr.sd.n_gamma),
                        lambda r: E.apply_neumann_neumann_schur(Pi, pr.sd, r), maxit=k)
-    tol = max(1e-10, 20 * floor)
     assert itk == k
-    assert np.linalg.norm(xk - xok) <= tol * np.linalg.norm(xok)
-    assert np.abs(resk - reso[:k]).max() <= tol * reso[:k].max()
-    assert tm.kernel_launches > 0 and tm.schur_launches == it and tm.solve_ms > 0
+    assert np.linalg.norm(xk - xok) <= max(1e-10, 20 * floor_x) * np.linalg.norm(xok)
+    assert np.abs(resk - reso[:k]).max() <= max(1e-10, 20 * floor_r) * reso[:k].max()
+    assert tm.kernel_launches > 0 and tm.schur_launches >= it and tm.solve_ms > 0   # launches past convergence exit early
 
 
 def test_pcg_parity_tight_on_well_conditioned_case():
