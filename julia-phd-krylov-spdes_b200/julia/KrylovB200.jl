@@ -1,0 +1,176 @@
+# KrylovB200.jl -- ccall shim that puts libkrylov_b200.so behind the reference's own API.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI (the build image has no Julia).  Every ccall below has a
+# one-to-one, tested twin in ../capi.py (ctypes); the argument order, types and index conventions
+# are the ones declared in include/krylov_b200.h.
+#
+# Usage inside the reference (e.g. Example07_PcgSchurStochasticEllipticPde.jl, after
+# prepare_local_schurs / set_subdomains):
+#
+#   push!(LOAD_PATH, "path/to/julia-phd-krylov-spdes_b200/julia"); using KrylovB200
+#   F  = [cholesky(A_IIdd[d]) for d in 1:ndom]                       # host, CHOLMOD (as :1536)
+#   S  = B200SchurOperator(A_IΓdd, A_ΓΓdd, F, ind_Γd_Γ2l, node_Γ_cnt)  # replaces the LinearMap at Example07:128-136
+#   M  = B200NeumannNeumann(S, ΠSnn_0.ΠSd)                             # replaces ΠSnn_0 (Example07:152-154)
+#   u_Γ, it, res = pcg(S, b_schur, zeros(S.N), M)                      # same call as Example07:273
+#
+# New types are introduced (no method piracy on LinearMaps.FunctionMap); the solver methods dispatch
+# on them and run the whole solve on the GPU.
+module KrylovB200
+
+using SparseArrays, LinearAlgebra, SuiteSparse
+import Base: *, \, size
+import LinearAlgebra: mul!, ldiv!
+
+export B200SchurOperator, B200NeumannNeumann, pcg, cg, get_schur_rhs, get_subdomain_solutions,
+       assemble_local_schurs!
+
+const LIB = get(ENV, "KRYLOV_B200_LIB", joinpath(@__DIR__, "..", "libkrylov_b200.so"))
+
+struct KB200Error <: Exception
+  code::Cint
+  msg::String
+end
+function chk(rc::Cint)
+  rc == 0 && return
+  throw(KB200Error(rc, unsafe_string(ccall((:kb200_last_error, LIB), Cstring, ()))))
+end
+
+mutable struct Timings            # kb200_timings
+  solve_ms::Cdouble; schur_ms::Cdouble; nn_ms::Cdouble
+  schur_launches::Int64; nn_launches::Int64; kernel_launches::Int64; h2d_bytes::Int64; d2h_bytes::Int64
+  Timings() = new(0, 0, 0, 0, 0, 0, 0, 0)
+end
+
+mutable struct B200SchurOperator
+  h::Ptr{Cvoid}
+  N::Int                          # = n_Γ, as S.N of the reference's FunctionMap (cg.jl:76)
+  n_I::Vector{Int64}
+  assembled::Bool
+end
+size(S::B200SchurOperator) = (S.N, S.N)
+
+# Flatten ind_Γd_Γ2l[d] (Dict Γ-index => local index) exactly like ind_Γd_l2Γ at
+# Fem/EllipticPdeDomainDecomposition.jl:1090-1095.
+function flatten_l2Γ(ind_Γd_Γ2l::Dict{Int,Int})
+  out = Vector{Int64}(undef, length(ind_Γd_Γ2l))
+  for (lnode_in_Γ, lnode_in_Γd) in ind_Γd_Γ2l
+    out[lnode_in_Γd] = lnode_in_Γ
+  end
+  return out
+end
+
+"""
+    B200SchurOperator(A_IΓdd, A_ΓΓdd, F, ind_Γd_Γ2l, node_Γ_cnt; device=0, csize=4)
+
+`F[d]` is the CHOLMOD factor of `A_IIdd[d]` (`cholesky(A_IIdd[d])`): `F[d].p` and `sparse(F[d].L)`
+are uploaded once; the device applies `A_II,d⁻¹` with its own level-scheduled triangular solves.
+"""
+function B200SchurOperator(A_IΓdd::Vector{SparseMatrixCSC{Float64,Int}},
+                           A_ΓΓdd::Vector{SparseMatrixCSC{Float64,Int}},
+                           F::Vector, ind_Γd_Γ2l::Vector{Dict{Int,Int}}, node_Γ_cnt::Vector{Int};
+                           device::Int=0, csize::Int=4)
+  ndom = length(A_IΓdd)
+  hr = Ref{Ptr{Cvoid}}(C_NULL)
+  chk(ccall((:kb200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, hr))
+  h = hr[]
+  chk(ccall((:kb200_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h, "csize", csize))
+  n_I = Int64[A_IΓdd[d].m for d in 1:ndom]
+  n_gd = Int64[A_IΓdd[d].n for d in 1:ndom]
+  maps = [flatten_l2Γ(ind_Γd_Γ2l[d]) for d in 1:ndom]          # 1-based, as the ABI expects
+  ptrs = [pointer(m) for m in maps]
+  cnt = Vector{Int64}(node_Γ_cnt)
+  GC.@preserve maps begin
+    chk(ccall((:kb200_set_topology, LIB), Cint,
+              (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Int64}}, Ptr{Int64}),
+              h, ndom, length(cnt), n_I, n_gd, ptrs, cnt))
+  end
+  for d in 1:ndom
+    G, H = A_IΓdd[d], A_ΓΓdd[d]
+    chk(ccall((:kb200_upload_local_blocks, LIB), Cint,
+              (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+              h, d - 1, G.colptr, G.rowval, G.nzval, H.colptr, H.rowval, H.nzval))
+    L = sparse(F[d].L)                                        # simplicial lower factor, L*L' = A[p,p]
+    p = Vector{Int64}(F[d].p)
+    chk(ccall((:kb200_upload_cholesky, LIB), Cint,
+              (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+              h, d - 1, p, L.colptr, L.rowval, L.nzval))
+  end
+  chk(ccall((:kb200_finalize, LIB), Cint, (Ptr{Cvoid},), h))
+  S = B200SchurOperator(h, length(cnt), n_I, false)
+  finalizer(s -> ccall((:kb200_destroy, LIB), Cint, (Ptr{Cvoid},), s.h), S)
+  return S
+end
+
+# S * x and mul!(y, S, x): what cg.jl:83 and cg.jl:93 call on the reference's FunctionMap
+# (apply_local_schurs, EllipticPdeDomainDecomposition.jl:711-747 / :761-785).
+function mul!(y::Vector{Float64}, S::B200SchurOperator, x::Vector{Float64})
+  f = S.assembled ? :kb200_apply_schur_assembled : :kb200_apply_schur
+  if S.assembled
+    chk(ccall((:kb200_apply_schur_assembled, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), S.h, x, y, 1))
+  else
+    chk(ccall((:kb200_apply_schur, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), S.h, x, y, 1))
+  end
+  return y
+end
+*(S::B200SchurOperator, x::Vector{Float64}) = mul!(similar(x), S, x)
+
+"""assemble_local_schurs (:667-695) on the device; afterwards `S.assembled = true` selects the dense path."""
+function assemble_local_schurs!(S::B200SchurOperator)
+  chk(ccall((:kb200_assemble_local_schurs, LIB), Cint, (Ptr{Cvoid},), S.h))
+  return S
+end
+
+struct B200NeumannNeumann
+  S::B200SchurOperator
+end
+"""NeumannNeumannSchurPreconditioner (:1111-1137): uploads ΠSd[d] (column-major Matrix{Float64})."""
+function B200NeumannNeumann(S::B200SchurOperator, ΠSd::Vector{Matrix{Float64}})
+  for d in 1:length(ΠSd)
+    chk(ccall((:kb200_upload_nn_pinv, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), S.h, d - 1, ΠSd[d]))
+  end
+  return B200NeumannNeumann(S)
+end
+# `\`, ldiv!(z, M, r), ldiv!(M, r): EllipticPdeDomainDecomposition.jl:1389-1403
+function ldiv!(z::Vector{Float64}, M::B200NeumannNeumann, r::Vector{Float64})
+  chk(ccall((:kb200_apply_nn, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), M.S.h, r, z, 1))
+  return z
+end
+\(M::B200NeumannNeumann, r::Vector{Float64}) = ldiv!(similar(r), M, r)
+ldiv!(M::B200NeumannNeumann, r::Vector{Float64}) = (r .= M \ copy(r))
+
+# get_schur_rhs (:835-864) and get_subdomain_solutions (:1014-1025)
+function get_schur_rhs(S::B200SchurOperator, b_Id::Vector{Vector{Float64}}, b_Γ::Vector{Float64})
+  out = similar(b_Γ)
+  chk(ccall((:kb200_schur_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            S.h, vcat(b_Id...), b_Γ, out))
+  return out
+end
+function get_subdomain_solutions(S::B200SchurOperator, u_Γ::Vector{Float64}, b_Id::Vector{Vector{Float64}})
+  u = Vector{Float64}(undef, sum(S.n_I))
+  chk(ccall((:kb200_back_substitute, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            S.h, u_Γ, vcat(b_Id...), u))
+  off = cumsum(vcat(0, S.n_I))
+  return [u[off[d]+1:off[d+1]] for d in 1:length(S.n_I)]
+end
+
+const eps_rtol = 1e-7   # RecyclingKrylovSolvers.jl:21
+
+"""
+    pcg(S, b, x, M; maxit=0)   ->  (x, it, res_norm)      # cg.jl:67-109, whole solve on the GPU
+
+Same positional signature and return tuple as RecyclingKrylovSolvers.pcg; `x` is updated in place.
+"""
+function pcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, M::Union{B200NeumannNeumann,Nothing};
+             maxit::Int=0, timings::Union{Timings,Nothing}=nothing)
+  cap = (maxit == 0 ? S.N : maxit) + 1
+  res = Vector{Float64}(undef, cap)
+  it = Ref{Int64}(0)
+  tm = timings === nothing ? Timings() : timings
+  chk(ccall((:kb200_pcg, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, Cint, Cint, Ref{Int64}, Ptr{Float64}, Ref{Timings}),
+            S.h, b, x, maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1, it, res, tm))
+  return x, Int(it[]), res[1:it[]]
+end
+cg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}; maxit::Int=0) = pcg(S, b, x, nothing; maxit=maxit)
+
+end # module
