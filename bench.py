@@ -94,7 +94,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=2001, help="nodes per side (2001 -> 4.0M DOF)")
     ap.add_argument("--ndom", type=int, default=256)
-    ap.add_argument("--csize", type=int, default=4)
+    ap.add_argument("--csize", type=int, default=0, help="CTAs per subdomain cluster (0 = automatic)")
     ap.add_argument("--maxit", type=int, default=5000)
     ap.add_argument("--cpu-sample-iters", type=int, default=6)
     args = ap.parse_args()
@@ -143,7 +143,8 @@ def main():
     t0 = time.time()
     # constant preconditioner from the median realization (Example07:152-154): S_d assembled on the
     # device, pseudo-inverse on the host (LAPACK), uploaded once
-    S0 = fem.B200SchurOperator(sd, pr0.blocks, pr0.factors, device=local_rank, csize=args.csize)
+    S0 = fem.B200SchurOperator(sd, pr0.blocks, pr0.factors, device=local_rank, csize=args.csize,
+                               options={"shard_world": world, "shard_rank": rank})
     Sd0 = S0.assemble_local_schurs()
     PiS = {d: PB.pinv_sym(Sd0[d]) for d in range(d0, d1)}
     del S0, Sd0
@@ -204,7 +205,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("nx") == args.nx and tj.get("ndom") == args.ndom and tj.get("csize") == args.csize and world == 1:
+        if tj.get("nx") == args.nx and tj.get("ndom") == args.ndom and world == 1:
             traffic = tj.get("dram_bytes_per_launch")
     B_iter, parts = PB.algorithmic_bytes_per_iteration(pr, (d0, d1))
     out = {

@@ -119,6 +119,36 @@ int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out);
 int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled,
               int precond, int64_t* it, double* res_norm, kb200_timings* timings);
 
+/* ---- device-resident vectors and bases (deflated / recycling solvers) ----------------------------- */
+/* defpcg / eigpcg / eigdefpcg (RecyclingKrylovSolvers/defcg.jl:242-308, eigcg.jl:143-267,
+ * defcg.jl:337-473) keep their control flow -- including the Rayleigh-Ritz restarts on small dense
+ * matrices (LAPACK eigen / svd / rank, eigcg.jl:220-228) -- in the host language; every n_gamma-sized
+ * object (x, r, z, p, Ap, W, WtA', V, AV, tvec) lives on the GPU as a column of a block allocated
+ * here, and only scalars and nvec / spdim-sized dense data cross the boundary.
+ * A block is n_gamma x ncols, column-major, zero-initialised; (id, col) addresses one column. */
+int kb200_mat_alloc(kb200_handle h, int64_t ncols, int64_t* id);
+int kb200_mat_free(kb200_handle h, int64_t id);
+int kb200_mat_set(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, const double* host);
+int kb200_mat_get(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, double* host);
+/* dst[:, dcol+k] = Op * src[:, scol+k], k < ncols; which = 0 S matrix-free (`A * W[:, ivec]`,
+ * defcg.jl:263), 1 S assembled, 2 M \ . (Neumann-Neumann). */
+int kb200_op_apply(kb200_handle h, int which, int64_t src, int64_t scol, int64_t dst, int64_t dcol, int64_t ncols);
+/* y = a x + b y  (axpy! / axpby!, cg.jl:97-103) */
+int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, int64_t y, int64_t ycol);
+/* *out = x . y  (dot, cg.jl:94) */
+int kb200_op_dot(kb200_handle h, int64_t x, int64_t xcol, int64_t y, int64_t ycol, double* out);
+/* y_host[0:k] = A[:, col0:col0+k]' x        (WtA * z, W' * r: defcg.jl:272, 301) */
+int kb200_op_gemv_t(kb200_handle h, int64_t A, int64_t col0, int64_t k, int64_t x, int64_t xcol, double* y_host);
+/* y = b y + a A[:, col0:col0+k] mu_host     (W * mu: defcg.jl:275, 302) */
+int kb200_op_gemv_n(kb200_handle h, double a, int64_t A, int64_t col0, int64_t k, const double* mu_host, double b,
+                    int64_t y, int64_t ycol);
+/* C_host (ka x kb, column-major) = A[:, ca:ca+ka]' B[:, cb:cb+kb]   (WtA * W, V'AV: defcg.jl:268, eigcg.jl:219) */
+int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t B, int64_t cb, int64_t kb,
+                     double* C_host);
+/* C[:, cc:cc+kq] = A[:, ca:ca+ka] Q_host (ka x kq, column-major); C may alias A (V[:, 1:nev] = V*(Q*Z), eigcg.jl:228) */
+int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const double* Q_host, int64_t kq, int64_t C,
+                     int64_t cc);
+
 /* ---- introspection (tests / benchmarks) -------------------------------------------------------- */
 /* stats[0..n): 0 Σ nnz(L) strictly lower, 1 Σ stream entries, 2 Σ rows, 3 Σ slices,
  * 4 stream bytes read per Schur apply, 5 max levels, 6 max top size, 7 shared memory per CTA,

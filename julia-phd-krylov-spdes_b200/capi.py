@@ -18,7 +18,9 @@ SYMBOLS = [
     "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
     "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_get_stats", "kb200_get_interface_maps",
-    "kb200_time_kernel", "kb200_debug_stamps",
+    "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
+    "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
+    "kb200_op_gemm_tn", "kb200_op_gemm_nn",
 ]
 
 
@@ -220,6 +222,60 @@ class Handle:
         if isinstance(xin, np.ndarray) and xin is not x:
             xin[...] = x
         return x, it.value, res[:it.value].copy(), tm
+
+    # ---- device-resident blocks -------------------------------------------------------------------
+    def mat_alloc(self, ncols):
+        mid = C.c_int64()
+        _chk(lib().kb200_mat_alloc(self.h, C.c_int64(ncols), C.byref(mid)))
+        return mid.value
+
+    def mat_free(self, mid):
+        _chk(lib().kb200_mat_free(self.h, C.c_int64(mid)))
+
+    def mat_set(self, mid, col0, data):
+        data = np.asfortranarray(data, dtype=np.float64)
+        ncols = 1 if data.ndim == 1 else data.shape[1]
+        _chk(lib().kb200_mat_set(self.h, C.c_int64(mid), C.c_int64(col0), C.c_int64(ncols), _p(data, C.c_double)))
+
+    def mat_get(self, mid, col0, ncols=1):
+        out = np.empty((self.n_gamma, ncols), order="F")
+        _chk(lib().kb200_mat_get(self.h, C.c_int64(mid), C.c_int64(col0), C.c_int64(ncols), _p(out, C.c_double)))
+        return out[:, 0].copy() if ncols == 1 else out
+
+    def op_apply(self, which, src, scol, dst, dcol, ncols=1):
+        _chk(lib().kb200_op_apply(self.h, which, C.c_int64(src), C.c_int64(scol), C.c_int64(dst), C.c_int64(dcol),
+                                  C.c_int64(ncols)))
+
+    def op_axpby(self, a, x, xcol, b, y, ycol):
+        _chk(lib().kb200_op_axpby(self.h, C.c_double(a), C.c_int64(x), C.c_int64(xcol), C.c_double(b), C.c_int64(y),
+                                  C.c_int64(ycol)))
+
+    def op_dot(self, x, xcol, y, ycol):
+        out = C.c_double()
+        _chk(lib().kb200_op_dot(self.h, C.c_int64(x), C.c_int64(xcol), C.c_int64(y), C.c_int64(ycol), C.byref(out)))
+        return out.value
+
+    def op_gemv_t(self, A, col0, k, x, xcol):
+        out = np.empty(k)
+        _chk(lib().kb200_op_gemv_t(self.h, C.c_int64(A), C.c_int64(col0), C.c_int64(k), C.c_int64(x), C.c_int64(xcol),
+                                   _p(out, C.c_double)))
+        return out
+
+    def op_gemv_n(self, a, A, col0, k, mu, b, y, ycol):
+        mu = _f64(mu)
+        _chk(lib().kb200_op_gemv_n(self.h, C.c_double(a), C.c_int64(A), C.c_int64(col0), C.c_int64(k), _p(mu, C.c_double),
+                                   C.c_double(b), C.c_int64(y), C.c_int64(ycol)))
+
+    def op_gemm_tn(self, A, ca, ka, B, cb, kb):
+        out = np.empty((ka, kb), order="F")
+        _chk(lib().kb200_op_gemm_tn(self.h, C.c_int64(A), C.c_int64(ca), C.c_int64(ka), C.c_int64(B), C.c_int64(cb),
+                                    C.c_int64(kb), _p(out, C.c_double)))
+        return out
+
+    def op_gemm_nn(self, A, ca, ka, Q, Cm, cc):
+        Q = np.asfortranarray(Q, dtype=np.float64)
+        _chk(lib().kb200_op_gemm_nn(self.h, C.c_int64(A), C.c_int64(ca), C.c_int64(ka), _p(Q, C.c_double),
+                                    C.c_int64(Q.shape[1]), C.c_int64(Cm), C.c_int64(cc)))
 
     def stats(self):
         s = np.zeros(16)

@@ -105,13 +105,14 @@ void csc_from_julia(kb::Csc& m, int64_t nrow, int64_t ncol, const int64_t* colpt
 }  // namespace
 
 struct kb200_ctx {
-  int device = 0, rank = 0, world = 1;
+  int device = 0, rank = 0, world = 1;  // rank/world define the subdomain shard
+  bool has_comm = false;                // collectives only when an NCCL communicator exists
   cudaStream_t stream = nullptr;
 #ifdef KB200_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 4, profile = 0, check_every = 8, min_block = -1, stages = 3;
+  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -135,6 +136,10 @@ struct kb200_ctx {
   DevBuf<double> d_x, d_b, d_r, d_z, d_p, d_Ap, d_loc, d_bI, d_uI, d_partA, d_partB, d_partC, d_res;
   DevBuf<kb::PcgState> d_state;
   DevBuf<long long> d_dbg;
+  // device-resident n_gamma x ncols blocks handed out through kb200_mat_*
+  std::vector<std::unique_ptr<DevBuf<double>>> mats;
+  std::vector<int64_t> mat_cols;
+  DevBuf<double> d_small, d_small2;
   int debug_timing = 0, dbg_flags = 0;
   int nb = 0;  // blocks of the interface-vector kernels
   int64_t launches = 0;
@@ -183,6 +188,12 @@ void finalize(Ctx* c) {
             "every local subdomain needs kb200_upload_local_blocks and kb200_upload_cholesky");
   std::vector<kb::DomainPlan> plans(nloc);
   kb::BuildOptions opt;
+  if (c->csize == 0) {
+    // automatic cluster size: enough CTAs to fill the 148 SMs twice over, at most 8 per subdomain
+    int cs = 1;
+    while (cs < 8 && nloc * cs < 600) cs *= 2;
+    c->csize = cs;
+  }
   opt.csize = c->csize;
   if (c->min_block >= 0) opt.min_block = c->min_block;
   {
@@ -323,9 +334,17 @@ void finalize(Ctx* c) {
   c->d_partC.alloc(c->nb);
   c->d_state.alloc(1);
   CUDA_TRY(cudaMemsetAsync(c->d_state.p, 0, sizeof(kb::PcgState), s));
-  // kernel attributes
+  // kernel attributes: the dynamic shared-memory limit of a kernel is process-wide state, so always
+  // raise it to the device maximum instead of this handle's own requirement
+  int smem_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   auto set_attr = [&](const void* fn) {
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+    const int dyn_max = smem_optin - (int)fa.sharedSizeBytes;
+    if (c->smem_bytes > dyn_max)
+      throw KbError(KB200_ERR_INPUT, "subdomain too large for the shared-memory vector: raise csize");
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     if (c->csize > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   };
   set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY>);
@@ -419,7 +438,7 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
 
 void allreduce(Ctx* c, double* v, int64_t n) {
 #ifdef KB200_WITH_NCCL
-  if (c->world > 1) NCCL_TRY(ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+  if (c->has_comm) NCCL_TRY(ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
 #else
   (void)c; (void)v; (void)n;
 #endif
@@ -430,7 +449,7 @@ void allreduce(Ctx* c, double* v, int64_t n) {
 void assemble(Ctx* c, const double* loc, const double* base, double* y, const double* q, double* part,
               const int* done_at, int iter) {
   const int n = (int)c->n_gamma;
-  if (c->world == 1) {
+  if (!c->has_comm) {
     kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base, y, q,
                                                                  part, done_at, iter);
     CUDA_TRY(cudaGetLastError());
@@ -593,6 +612,7 @@ int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, k
       ncclUniqueId id;
       std::memcpy(&id, nccl_id, 128);
       NCCL_TRY(ncclCommInitRank(&c->comm, world, id, rank));
+      c->has_comm = true;
 #else
       (void)nccl_id;
       throw KbError(KB200_ERR_NCCL, "library built without NCCL");
@@ -625,8 +645,15 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     const std::string k(name);
     if (k == "csize") {
       require(!h->finalized, "csize must be set before the first operation");
-      require(value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "csize must be 1, 2, 4, 8 or 16");
+      require(value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16,
+              "csize must be 0 (automatic), 1, 2, 4, 8 or 16");
       h->csize = (int)value;
+    } else if (k == "shard_rank" || k == "shard_world") {
+      // shard the subdomains like rank `shard_rank` of `shard_world` WITHOUT a communicator
+      // (purely local operations such as kb200_assemble_local_schurs on a rank's own subdomains)
+      require(!h->topo && !h->has_comm, "shard options must precede kb200_set_topology and exclude NCCL handles");
+      if (k == "shard_rank") h->rank = (int)value; else h->world = (int)value;
+      require(h->world >= 1 && h->rank >= 0, "bad shard");
     } else if (k == "dbg_flags") {
       h->dbg_flags = (int)value;
     } else if (k == "debug_timing") {
@@ -943,6 +970,132 @@ int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double 
     T.kernel_launches = c->launches - launches0;
     if (tm) *tm = T;
     if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+  });
+}
+
+// ---- device-resident interface vectors / bases ----------------------------------------------------
+static double* mat_col(Ctx* h, int64_t id, int64_t col, int64_t ncols) {
+  require(id >= 0 && id < (int64_t)h->mats.size() && h->mats[id] != nullptr, "bad matrix id");
+  require(col >= 0 && ncols >= 0 && col + ncols <= h->mat_cols[id], "column range out of bounds");
+  return h->mats[id]->p + col * h->n_gamma;
+}
+
+int kb200_mat_alloc(kb200_handle h, int64_t ncols, int64_t* id) {
+  return guarded([&]() {
+    require(h && id && ncols >= 1, "bad argument");
+    finalize(h);
+    use_device(h);
+    std::unique_ptr<DevBuf<double>> b(new DevBuf<double>());
+    b->alloc((size_t)(h->n_gamma * ncols));
+    CUDA_TRY(cudaMemsetAsync(b->p, 0, (size_t)(h->n_gamma * ncols) * 8, h->stream));
+    h->mats.push_back(std::move(b));
+    h->mat_cols.push_back(ncols);
+    *id = (int64_t)h->mats.size() - 1;
+  });
+}
+int kb200_mat_free(kb200_handle h, int64_t id) {
+  return guarded([&]() {
+    require(h && id >= 0 && id < (int64_t)h->mats.size(), "bad matrix id");
+    use_device(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->mats[id].reset();
+  });
+}
+int kb200_mat_set(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, const double* host) {
+  return guarded([&]() {
+    require(h && host, "null argument");
+    use_device(h);
+    h2d(h, mat_col(h, id, col0, ncols), host, h->n_gamma * ncols);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+int kb200_mat_get(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, double* host) {
+  return guarded([&]() {
+    require(h && host, "null argument");
+    use_device(h);
+    d2h(h, host, mat_col(h, id, col0, ncols), h->n_gamma * ncols);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+int kb200_op_apply(kb200_handle h, int which, int64_t src, int64_t scol, int64_t dst, int64_t dcol, int64_t ncols) {
+  return guarded([&]() {
+    require(h && which >= 0 && which <= 2, "bad operator");
+    use_device(h);
+    for (int64_t k = 0; k < ncols; ++k)
+      apply_op(h, which == 0 ? OP_SCHUR : which == 1 ? OP_SCHUR_DENSE : OP_NN, mat_col(h, src, scol + k, 1),
+               mat_col(h, dst, dcol + k, 1), nullptr, nullptr, nullptr, 0, nullptr);
+  });
+}
+int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, int64_t y, int64_t ycol) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    use_device(h);
+    kb::axpby_kernel<<<h->nb, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, a, mat_col(h, x, xcol, 1), b,
+                                                               mat_col(h, y, ycol, 1));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  });
+}
+int kb200_op_gemv_t(kb200_handle h, int64_t A, int64_t col0, int64_t k, int64_t x, int64_t xcol, double* y_host) {
+  return guarded([&]() {
+    require(h && y_host && k >= 1, "bad argument");
+    use_device(h);
+    if ((int64_t)h->d_small.n < k) h->d_small.alloc((size_t)k);
+    kb::gemv_t_kernel<<<(unsigned)k, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, mat_col(h, A, col0, k), h->n_gamma,
+                                                                      mat_col(h, x, xcol, 1), h->d_small.p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    d2h(h, y_host, h->d_small.p, k);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+int kb200_op_dot(kb200_handle h, int64_t x, int64_t xcol, int64_t y, int64_t ycol, double* out) {
+  return kb200_op_gemv_t(h, x, xcol, 1, y, ycol, out);
+}
+int kb200_op_gemv_n(kb200_handle h, double a, int64_t A, int64_t col0, int64_t k, const double* mu_host, double b, int64_t y,
+                    int64_t ycol) {
+  return guarded([&]() {
+    require(h && mu_host && k >= 1, "bad argument");
+    use_device(h);
+    if ((int64_t)h->d_small2.n < k) h->d_small2.alloc((size_t)k);
+    CUDA_TRY(cudaMemcpyAsync(h->d_small2.p, mu_host, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
+    kb::gemv_n_kernel<<<h->nb, kb::kVecThreads, (size_t)k * 8, h->stream>>>((int)h->n_gamma, (int)k, a, mat_col(h, A, col0, k),
+                                                                           h->n_gamma, h->d_small2.p, b, mat_col(h, y, ycol, 1));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // mu_host may be reused by the caller
+  });
+}
+int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t B, int64_t cb, int64_t kb_, double* C_host) {
+  return guarded([&]() {
+    require(h && C_host && ka >= 1 && kb_ >= 1, "bad argument");
+    use_device(h);
+    if ((int64_t)h->d_small.n < ka * kb_) h->d_small.alloc((size_t)(ka * kb_));
+    dim3 grid((unsigned)((ka + 15) / 16), (unsigned)((kb_ + 15) / 16));
+    kb::gemm_tn_kernel<<<grid, 256, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kb_, mat_col(h, A, ca, ka), h->n_gamma,
+                                                    mat_col(h, B, cb, kb_), h->n_gamma, h->d_small.p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    d2h(h, C_host, h->d_small.p, ka * kb_);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const double* Q_host, int64_t kq, int64_t Cm, int64_t cc) {
+  return guarded([&]() {
+    require(h && Q_host && ka >= 1 && kq >= 1, "bad argument");
+    use_device(h);
+    if ((int64_t)h->d_small2.n < ka * kq) h->d_small2.alloc((size_t)(ka * kq));
+    CUDA_TRY(cudaMemcpyAsync(h->d_small2.p, Q_host, (size_t)(ka * kq) * 8, cudaMemcpyHostToDevice, h->stream));
+    // the result may overlap A (V[:, 1:nev] = V * QZ, eigcg.jl:228): go through a temporary block
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)(h->n_gamma * kq));
+    dim3 grid((unsigned)h->nb, (unsigned)kq);
+    kb::gemm_nn_kernel<<<grid, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kq, mat_col(h, A, ca, ka), h->n_gamma,
+                                                               h->d_small2.p, tmp.p, h->n_gamma);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(mat_col(h, Cm, cc, kq), tmp.p, (size_t)(h->n_gamma * kq) * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
   });
 }
 

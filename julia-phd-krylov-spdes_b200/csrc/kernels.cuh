@@ -656,4 +656,79 @@ pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* par
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Dense tall-skinny products with the deflation / recycling bases W, V (n_gamma x k, column-major):
+// reference defcg.jl:301-302 (WtA*z, W*mu), :407, eigcg.jl:219-228 (V'AV, V*(Q*Z)).  HBM-bound, FP64.
+// ---------------------------------------------------------------------------------------------
+// y = a*x + b*y
+__global__ void __launch_bounds__(kVecThreads) axpby_kernel(int n, double a, const double* x, double b, double* y) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) y[g] = (b == 0.0 ? 0.0 : b * y[g]) + a * x[g];
+}
+// out[j] = A[:, j] . x   (one block per column, fixed reduction order)
+__global__ void __launch_bounds__(kVecThreads) gemv_t_kernel(int n, const double* A, int64_t lda, const double* x, double* out) {
+  __shared__ double red[8];
+  const double* col = A + (int64_t)blockIdx.x * lda;
+  double s = 0.0;
+  for (int g = threadIdx.x; g < n; g += blockDim.x) s = fma(col[g], x[g], s);
+  const double t = block_reduce_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+// y = b*y + a * A[:, 0:k] * mu
+__global__ void __launch_bounds__(kVecThreads) gemv_n_kernel(int n, int k, double a, const double* A, int64_t lda, const double* mu,
+                                                           double b, double* y) {
+  extern __shared__ double smu[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) smu[j] = mu[j];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+  int j = 0;
+  for (; j + 1 < k; j += 2) {
+    s0 = fma(A[g + (int64_t)j * lda], smu[j], s0);
+    s1 = fma(A[g + (int64_t)(j + 1) * lda], smu[j + 1], s1);
+  }
+  if (j < k) s0 = fma(A[g + (int64_t)j * lda], smu[j], s0);
+  y[g] = (b == 0.0 ? 0.0 : b * y[g]) + a * (s0 + s1);
+}
+// C[i, j] = A[:, i] . B[:, j]  (ka x kb, column-major) -- 16x16 output tile per block, rows streamed in
+// 64-row panels through shared memory; fixed summation order.
+__global__ void __launch_bounds__(256) gemm_tn_kernel(int n, int ka, int kb, const double* A, int64_t lda, const double* B,
+                                                      int64_t ldb, double* Cm) {
+  __shared__ double sa[64][17], sb[64][17];
+  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * 16, j0 = blockIdx.y * 16;
+  double acc = 0.0;
+  for (int r0 = 0; r0 < n; r0 += 64) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e & 63, c = e >> 6;
+      const int g = r0 + r;
+      sa[r][c] = (g < n && i0 + c < ka) ? A[g + (int64_t)(i0 + c) * lda] : 0.0;
+      sb[r][c] = (g < n && j0 + c < kb) ? B[g + (int64_t)(j0 + c) * ldb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int r = 0; r < 64; ++r) acc = fma(sa[r][ti], sb[r][tj], acc);
+    __syncthreads();
+  }
+  if (i0 + ti < ka && j0 + tj < kb) Cm[(i0 + ti) + (int64_t)(j0 + tj) * ka] = acc;
+}
+// C[:, j] = A[:, 0:ka] * Q[:, j]   (n x kq); Q (ka x kq, column-major) in global memory
+__global__ void __launch_bounds__(kVecThreads) gemm_nn_kernel(int n, int ka, int kq, const double* A, int64_t lda, const double* Q,
+                                                            double* Cm, int64_t ldc) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (g >= n) return;
+  const double* q = Q + (int64_t)j * ka;
+  double s0 = 0.0, s1 = 0.0;
+  int kk = 0;
+  for (; kk + 1 < ka; kk += 2) {
+    s0 = fma(A[g + (int64_t)kk * lda], __ldg(q + kk), s0);
+    s1 = fma(A[g + (int64_t)(kk + 1) * lda], __ldg(q + kk + 1), s1);
+  }
+  if (kk < ka) s0 = fma(A[g + (int64_t)kk * lda], __ldg(q + kk), s0);
+  Cm[g + (int64_t)j * ldc] = s0 + s1;
+}
+
 }  // namespace kb

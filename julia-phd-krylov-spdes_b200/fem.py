@@ -24,7 +24,7 @@ class B200SchurOperator:
             self.h.set_option("csize", csize)
         if profile:
             self.h.set_option("profile", 1)
-        for k, v in (options or {}).items():
+        for k, v in (options or {}).items():   # "shard_world" before "shard_rank"
             self.h.set_option(k, v)
         n_I = [v.size for v in sd.node_Id]
         n_gd = [g.size for g in sd.gamma_l2g]

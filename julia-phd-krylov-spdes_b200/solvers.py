@@ -1,6 +1,13 @@
-"""RecyclingKrylovSolvers signatures dispatching on the B200 operator / preconditioner types:
-``pcg(S, b, x, M; maxit)`` (cg.jl:67-72) runs the whole solve on the device and returns the
-reference's tuple ``(x, it, res_norm)``."""
+"""RecyclingKrylovSolvers signatures dispatching on the B200 operator / preconditioner types.
+
+``pcg`` / ``cg`` (cg.jl:67-109, 14-50) run the whole solve inside libkrylov_b200.so.  ``defpcg``,
+``eigpcg`` and ``eigdefpcg`` (defcg.jl:242-308, eigcg.jl:143-267, defcg.jl:337-473) keep the
+reference's control flow here, line for line, but every n_Γ-sized object lives on the GPU (blocks of
+kb200_mat_alloc) and only scalars and nvec / spdim-sized dense data reach the host, where the small
+dense algebra (``WtAW \\ .``, the Rayleigh-Ritz restarts: eigen / svd / rank) uses LAPACK as the
+reference does.  Return tuples are the reference's: (x, it, res_norm[, V[:, 1:nvec]])."""
+import numpy as np
+
 from .fem import B200NeumannNeumann, B200SchurOperator
 
 EPS = 1e-7  # RecyclingKrylovSolvers.jl:21
@@ -16,3 +23,288 @@ def pcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann = None, maxit=0, retur
 def cg(A: B200SchurOperator, b, x, maxit=0):
     """cg.jl:14-50 (no preconditioner)."""
     return pcg(A, b, x, None, maxit)
+
+
+# --------------------------------------------------------------------------------------------------
+class _Dev:
+    """Device-resident work vectors of one solve: columns of one block."""
+    X, R, Z, P, AP, B, T = range(7)
+
+    def __init__(self, A, M):
+        self.h = A.h
+        self.op = 1 if A.assembled else 0
+        self.M = M
+        self.wk = self.h.mat_alloc(7)
+        self.blocks = [self.wk]
+
+    def block(self, ncols, data=None):
+        mid = self.h.mat_alloc(ncols)
+        self.blocks.append(mid)
+        if data is not None:
+            self.h.mat_set(mid, 0, data)
+        return mid
+
+    def free(self):
+        for mid in self.blocks:
+            self.h.mat_free(mid)
+
+    def set(self, col, v):
+        self.h.mat_set(self.wk, col, v)
+
+    def get(self, col):
+        return self.h.mat_get(self.wk, col)
+
+    def A(self, src, dst):                      # dst = A * src
+        self.h.op_apply(self.op, self.wk, src, self.wk, dst)
+
+    def Minv(self, src, dst):                   # dst = M \ src
+        if self.M is None:
+            self.h.op_axpby(1.0, self.wk, src, 0.0, self.wk, dst)
+        else:
+            self.h.op_apply(2, self.wk, src, self.wk, dst)
+
+    def axpby(self, a, x, b, y):                # y = a x + b y
+        self.h.op_axpby(a, self.wk, x, b, self.wk, y)
+
+    def dot(self, x, y):
+        return self.h.op_dot(self.wk, x, self.wk, y)
+
+    def residual(self):                         # r = b - A x
+        self.A(self.X, self.AP)
+        self.axpby(1.0, self.B, 0.0, self.R)
+        self.axpby(-1.0, self.AP, 1.0, self.R)
+
+
+def _julia_rank(Y):
+    """LinearAlgebra.rank default: #singular values > min(size) * eps * sigma_max."""
+    s = np.linalg.svd(Y, compute_uv=False)
+    if s.size == 0 or s[0] == 0.0:
+        return 0
+    return int((s > min(Y.shape) * np.finfo(np.float64).eps * s[0]).sum())
+
+
+def _sym(U):
+    return np.triu(U) + np.triu(U, 1).T          # Symmetric(U)
+
+
+def _rayleigh_ritz(Tm, nvec):
+    """Restart algebra of eigcg.jl:220-228 / defcg.jl:425-432 on the host: returns (Q*Z, vals, nev)."""
+    m = Tm.shape[0]
+    Y = np.zeros((m, 2 * nvec))
+    Y[:, :nvec] = np.linalg.eigh(Tm)[1][:, :nvec]
+    Y[:m - 1, nvec:] = np.linalg.eigh(Tm[:m - 1, :m - 1])[1][:, :nvec]
+    nev = _julia_rank(Y)
+    Q = np.linalg.svd(Y, full_matrices=False)[0][:, :nev]
+    H = _sym(Q.T @ (Tm @ Q))
+    vals, Z = np.linalg.eigh(H)
+    return Q @ Z, vals, nev
+
+
+def defpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None, maxit=0):
+    """defcg.jl:242-308."""
+    n, nvec = W.shape
+    dv = _Dev(A, M)
+    h = dv.h
+    try:
+        Wd = dv.block(nvec, W)
+        AWd = dv.block(nvec)
+        dv.set(dv.B, b)
+        dv.set(dv.X, x)
+        h.op_apply(dv.op, Wd, 0, AWd, 0, nvec)                      # WtA[ivec, :] = A * W[:, ivec]   :261-264
+        WtAW = h.op_gemm_tn(AWd, 0, nvec, Wd, 0, nvec)              # :268
+        dv.residual()
+        mu = np.linalg.solve(WtAW, h.op_gemv_t(Wd, 0, nvec, dv.wk, dv.R))      # :272-274
+        h.op_gemv_n(1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.X)        # x += W mu
+        maxit = n if maxit == 0 else maxit
+        res_norm = np.empty(maxit + 1)
+        it = 1
+        dv.residual()
+        rTr = dv.dot(dv.R, dv.R)
+        res_norm[0] = np.sqrt(rTr)
+        dv.Minv(dv.R, dv.Z)
+        rTz = dv.dot(dv.R, dv.Z)
+        mu = np.linalg.solve(WtAW, h.op_gemv_t(AWd, 0, nvec, dv.wk, dv.Z))     # :284
+        dv.axpby(1.0, dv.Z, 0.0, dv.P)
+        h.op_gemv_n(-1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.P)       # p = z - W mu
+        tol = EPS * np.linalg.norm(b)
+        while it < maxit and res_norm[it - 1] > tol:                # :290
+            dv.A(dv.P, dv.AP)
+            d = dv.dot(dv.P, dv.AP)
+            alpha = rTz / d
+            beta = 1.0 / rTz
+            dv.axpby(alpha, dv.P, 1.0, dv.X)
+            dv.axpby(-alpha, dv.AP, 1.0, dv.R)
+            rTr = dv.dot(dv.R, dv.R)
+            dv.Minv(dv.R, dv.Z)
+            rTz = dv.dot(dv.R, dv.Z)
+            beta *= rTz
+            mu = np.linalg.solve(WtAW, h.op_gemv_t(AWd, 0, nvec, dv.wk, dv.Z))  # :301
+            dv.axpby(1.0, dv.Z, beta, dv.P)
+            h.op_gemv_n(-1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.P)   # p = beta p + z - W mu   :302
+            it += 1
+            res_norm[it - 1] = np.sqrt(rTr)
+        x[...] = dv.get(dv.X)
+        return x, it, res_norm[:it].copy()
+    finally:
+        dv.free()
+
+
+def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0):
+    """eigcg.jl:143-267.  Returns (x, it, res_norm, V[:, 1:nvec])."""
+    n = x.size
+    dv = _Dev(A, M)
+    h = dv.h
+    try:
+        Vd = dv.block(spdim)
+        AVd = dv.block(spdim)
+        VtAV = np.zeros((spdim, spdim))
+        dv.set(dv.B, b)
+        dv.set(dv.X, x)
+        maxit = n if maxit == 0 else maxit
+        res_norm = np.empty(maxit + 1)
+        it = 1
+        dv.residual()
+        rTr = dv.dot(dv.R, dv.R)
+        dv.Minv(dv.R, dv.Z)
+        rTz = dv.dot(dv.R, dv.Z)
+        dv.axpby(1.0, dv.Z, 0.0, dv.P)
+        res_norm[0] = np.sqrt(rTr)
+        ivec = 0
+        h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)            # V[:, ivec] = z / sqrt(rTz)
+        just_restarted = False
+        hlpr = 0.0
+        tol = EPS * np.linalg.norm(b)
+        while it < maxit and res_norm[it - 1] > tol:                            # :185
+            dv.A(dv.P, dv.AP)
+            d = dv.dot(dv.P, dv.AP)
+            alpha = rTz / d
+            beta = 1.0 / rTz
+            dv.axpby(alpha, dv.P, 1.0, dv.X)
+            dv.axpby(-alpha, dv.AP, 1.0, dv.R)
+            rTr = dv.dot(dv.R, dv.R)
+            dv.Minv(dv.R, dv.Z)
+            if just_restarted:
+                hlpr = np.sqrt(rTz)                                             # :194-196
+            rTz = dv.dot(dv.R, dv.Z)
+            beta *= rTz
+            if ivec == spdim - 1:
+                dv.axpby(-beta, dv.AP, 1.0, dv.T)                               # tvec -= beta Ap   :199-201
+            dv.axpby(1.0, dv.Z, beta, dv.P)
+            it += 1
+            res_norm[it - 1] = np.sqrt(rTr)
+            VtAV[ivec, ivec] += 1.0 / alpha                                     # :206
+            if just_restarted:
+                dv.axpby(1.0, dv.AP, 1.0, dv.T)                                 # tvec += Ap        :208
+                nev = ivec
+                VtAV[:nev, ivec] = h.op_gemv_t(Vd, 0, nev, dv.wk, dv.T) / hlpr  # :210
+                just_restarted = False
+            if ivec == spdim - 1:                                               # :214
+                h.op_apply(dv.op, Vd, 0, AVd, 0, spdim)                         # AV = A V
+                VtAV[:, :] = h.op_gemm_tn(Vd, 0, spdim, AVd, 0, spdim)          # :222
+                QZ, vals, nev = _rayleigh_ritz(_sym(VtAV), nvec)
+                h.op_gemm_nn(Vd, 0, spdim, QZ, Vd, 0)                           # V[:, 1:nev] = V (Q Z)   :231
+                ivec = nev
+                h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
+                VtAV[:, :] = 0.0
+                VtAV[np.arange(nev), np.arange(nev)] = vals
+                VtAV[ivec, ivec] = beta / alpha
+                dv.axpby(-beta, dv.AP, 0.0, dv.T)                               # tvec = -beta Ap   :240
+                just_restarted = True
+            else:
+                ivec += 1
+                h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
+                VtAV[ivec - 1, ivec] = -np.sqrt(beta) / alpha
+                VtAV[ivec, ivec] = beta / alpha
+        if not just_restarted and ivec + 1 > nvec:                              # :251-264
+            m = ivec
+            QZ, vals, nev = _rayleigh_ritz(_sym(VtAV[:m, :m]), nvec)
+            h.op_gemm_nn(Vd, 0, m, QZ, Vd, 0)
+        x[...] = dv.get(dv.X)
+        return x, it, res_norm[:it].copy(), np.array(h.mat_get(Vd, 0, nvec))
+    finally:
+        dv.free()
+
+
+def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0):
+    """defcg.jl:337-473.  Returns (x, it, res_norm, V[:, 1:nvec])."""
+    n, nvec = W.shape
+    dv = _Dev(A, M)
+    h = dv.h
+    try:
+        Wd = dv.block(nvec, W)
+        AWd = dv.block(nvec)
+        Vd = dv.block(spdim)
+        dv.set(dv.B, b)
+        dv.set(dv.X, x)
+        h.op_apply(dv.op, Wd, 0, AWd, 0, nvec)                                  # :357-360
+        WtAW = h.op_gemm_tn(AWd, 0, nvec, Wd, 0, nvec)
+        WtW = h.op_gemm_tn(Wd, 0, nvec, Wd, 0, nvec)
+        dv.residual()
+        mu = np.linalg.solve(WtAW, h.op_gemv_t(Wd, 0, nvec, dv.wk, dv.R))
+        h.op_gemv_n(1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.X)
+        VtAV = np.zeros((spdim, spdim))
+        first_restart = True
+        maxit = n if maxit == 0 else maxit
+        res_norm = np.empty(maxit + 1)
+        it = 1
+        dv.residual()
+        rTr = dv.dot(dv.R, dv.R)
+        dv.Minv(dv.R, dv.Z)
+        rTz = dv.dot(dv.R, dv.Z)
+        mu = np.linalg.solve(WtAW, h.op_gemv_t(AWd, 0, nvec, dv.wk, dv.Z))
+        dv.axpby(1.0, dv.Z, 0.0, dv.P)
+        h.op_gemv_n(-1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.P)
+        res_norm[0] = np.sqrt(rTr)
+        VtAV[:nvec, :nvec] = WtAW                                               # :390
+        h.op_gemm_nn(Wd, 0, nvec, np.eye(nvec), Vd, 0)                          # V[:, 1:nvec] = W
+        just_restarted = False
+        ivec = nvec
+        h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
+        tol = EPS * np.linalg.norm(b)
+        while it < maxit and res_norm[it - 1] > tol:                            # :400
+            dv.A(dv.P, dv.AP)
+            d = dv.dot(dv.P, dv.AP)
+            alpha = rTz / d
+            beta = 1.0 / rTz
+            dv.axpby(alpha, dv.P, 1.0, dv.X)
+            dv.axpby(-alpha, dv.AP, 1.0, dv.R)
+            mu2 = np.linalg.solve(WtW, h.op_gemv_t(Wd, 0, nvec, dv.wk, dv.R))   # r -= W (WtW \ W'r)   :407
+            h.op_gemv_n(-1.0, Wd, 0, nvec, mu2, 1.0, dv.wk, dv.R)
+            rTr = dv.dot(dv.R, dv.R)
+            dv.Minv(dv.R, dv.Z)
+            rTz = dv.dot(dv.R, dv.Z)
+            beta *= rTz
+            mu = np.linalg.solve(WtAW, h.op_gemv_t(AWd, 0, nvec, dv.wk, dv.Z))
+            dv.axpby(1.0, dv.Z, beta, dv.P)
+            h.op_gemv_n(-1.0, Wd, 0, nvec, mu, 1.0, dv.wk, dv.P)
+            it += 1
+            res_norm[it - 1] = np.sqrt(rTr)
+            VtAV[ivec, ivec] += 1.0 / alpha                                     # :417
+            if ivec == spdim - 1:                                               # :419
+                if first_restart:
+                    VtAV[:nvec, nvec:spdim] = h.op_gemm_tn(AWd, 0, nvec, Vd, nvec, spdim - nvec)   # WtA V
+                    first_restart = False
+                QZ, vals, nev = _rayleigh_ritz(_sym(VtAV), nvec)
+                h.op_gemm_nn(Vd, 0, spdim, QZ, Vd, 0)
+                ivec = nev
+                h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
+                VtAV[:, :] = 0.0
+                VtAV[np.arange(nev), np.arange(nev)] = vals
+                VtAV[ivec, ivec] = beta / alpha
+                just_restarted = True
+            else:
+                just_restarted = False
+                ivec += 1
+                h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
+                VtAV[ivec - 1, ivec] = -np.sqrt(beta) / alpha
+                VtAV[ivec, ivec] = beta / alpha
+        if not just_restarted and ivec + 1 > nvec:                              # :450-466
+            m = ivec
+            if first_restart and m > nvec:
+                VtAV[:nvec, nvec:m] = h.op_gemm_tn(AWd, 0, nvec, Vd, nvec, m - nvec)
+            QZ, vals, nev = _rayleigh_ritz(_sym(VtAV[:m, :m]), nvec)
+            h.op_gemm_nn(Vd, 0, m, QZ, Vd, 0)
+        x[...] = dv.get(dv.X)
+        return x, it, res_norm[:it].copy(), np.array(h.mat_get(Vd, 0, nvec))
+    finally:
+        dv.free()

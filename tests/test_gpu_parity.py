@@ -216,3 +216,85 @@ def test_error_reporting_through_the_abi():
     with pytest.raises(capi.KB200Error) as e:                                             # missing diagonal
         h2.finalize()
     assert e.value.code == -4 and "diagonal" in str(e.value)
+
+
+# ---- deflated / recycling solvers (a12-a14) -----------------------------------------------------
+def _oracle_callables(pr):
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    Aop = lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v)
+    Mop = lambda r: E.apply_neumann_neumann_schur(Pi, pr.sd, r)
+    return Aop, Mop, bs
+
+
+def _subspace_gap(U, V):
+    """sin of the largest principal angle between span(U) and span(V)."""
+    Qu, _ = np.linalg.qr(U)
+    Qv, _ = np.linalg.qr(V)
+    s = np.linalg.svd(Qu.T @ Qv, compute_uv=False)
+    return float(np.sqrt(max(0.0, 1.0 - s.min() ** 2)))
+
+
+def test_device_block_primitives():
+    pr, S, M = gpu_ops(65, 16, 4)
+    h, n = S.h, pr.sd.n_gamma
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, 5))
+    B = rng.standard_normal((n, 3))
+    a, b = h.mat_alloc(5), h.mat_alloc(3)
+    h.mat_set(a, 0, A)
+    h.mat_set(b, 0, B)
+    assert np.array_equal(h.mat_get(a, 0, 5), A)
+    assert rel(h.op_gemm_tn(a, 0, 5, b, 0, 3), A.T @ B) <= 1e-13
+    assert rel(h.op_gemv_t(a, 1, 3, b, 2), A[:, 1:4].T @ B[:, 2]) <= 1e-13
+    assert abs(h.op_dot(a, 0, b, 1) - A[:, 0] @ B[:, 1]) <= 1e-12 * n
+    mu = rng.standard_normal(4)
+    h.op_gemv_n(2.0, a, 1, 4, mu, -0.5, b, 0)
+    assert rel(h.mat_get(b, 0), 2.0 * A[:, 1:5] @ mu - 0.5 * B[:, 0]) <= 1e-13
+    Q = rng.standard_normal((5, 2))
+    h.op_gemm_nn(a, 0, 5, Q, a, 0)                       # aliasing result
+    assert rel(h.mat_get(a, 0, 2), A @ Q) <= 1e-13
+    h.op_axpby(3.0, b, 1, 0.0, b, 2)
+    assert np.allclose(h.mat_get(b, 2), 3.0 * B[:, 1])
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    h.op_apply(0, b, 1, b, 2)
+    assert rel(h.mat_get(b, 2), E.apply_local_schurs(pr.blocks, inner, pr.sd, B[:, 1])) <= 1e-12
+    h.mat_free(a)
+    h.mat_free(b)
+
+
+def test_defpcg_matches_oracle():
+    pr, S, M = gpu_ops(65, 16, 4)
+    Aop, Mop, bs = _oracle_callables(pr)
+    n = pr.sd.n_gamma
+    Smat = np.column_stack([Aop(e) for e in np.eye(n)])
+    w, Vec = np.linalg.eigh((Smat + Smat.T) / 2)
+    W = Vec[:, :12]                                     # least dominant eigenvectors (Example03:206-215)
+    xo, ito, reso = OS.defpcg(Aop, bs, np.zeros(n), W, Mop)
+    x, it, res = solvers.defpcg(S, bs, np.zeros(n), W, M)
+    _, it_plain, _ = solvers.pcg(S, bs, np.zeros(n), M)
+    assert abs(it - ito) <= 1 and it < it_plain
+    k = min(it, ito)
+    assert np.abs(res[:k] - reso[:k]).max() <= 1e-6 * reso[:k].max()
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+
+
+def test_eigpcg_and_eigdefpcg_match_oracle():
+    pr, S, M = gpu_ops(65, 16, 4)
+    Aop, Mop, bs = _oracle_callables(pr)
+    n = pr.sd.n_gamma
+    nvec, spdim = 8, 24
+    xo, ito, reso, Vo = OS.eigpcg(Aop, bs, np.zeros(n), Mop, nvec, spdim)
+    x, it, res, V = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim)
+    assert V.shape == (n, nvec) and abs(it - ito) <= 1
+    assert res[-1] <= 1e-7 * np.linalg.norm(bs)
+    assert np.linalg.norm(x - xo) <= 1e-5 * np.linalg.norm(xo)
+    assert _subspace_gap(V[:, :4], Vo[:, :4]) <= 1e-3    # leading Ritz vectors span the same space
+    # next right-hand side: recycle the basis (Example09/11 usage)
+    b2 = Aop(np.random.default_rng(3).standard_normal(n))
+    x2o, it2o, res2o, V2o = OS.eigdefpcg(Aop, b2, np.zeros(n), Mop, Vo, spdim)
+    x2, it2, res2, V2 = solvers.eigdefpcg(S, b2, np.zeros(n), M, V, spdim)
+    _, it_plain, _ = solvers.pcg(S, b2, np.zeros(n), M)
+    assert abs(it2 - it2o) <= 2 and it2 <= it_plain
+    assert res2[-1] <= 1e-7 * np.linalg.norm(b2)
+    assert np.linalg.norm(x2 - x2o) <= 1e-5 * np.linalg.norm(x2o)
+    assert V2.shape == (n, nvec)
