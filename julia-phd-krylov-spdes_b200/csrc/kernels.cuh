@@ -141,60 +141,68 @@ __device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
   cx.lvl_phase ^= 1u;
 }
 
-// One group record: 32 products, segmented inclusive scan, segment sums to their scratch slots.
-// Two groups are interleaved for instruction-level parallelism.
-__device__ __forceinline__ void process_groups2(const uint8_t* g0, const uint8_t* g1, bool on1, const double* S,
-                                                double* scratch, int lane, uint32_t le_mask) {
-  const uint2 m0 = *reinterpret_cast<const uint2*>(g0);
-  const uint2 m1 = *reinterpret_cast<const uint2*>(g1);
-  const double v0 = reinterpret_cast<const double*>(g0 + 16)[lane];
-  const double v1 = reinterpret_cast<const double*>(g1 + 16)[lane];
-  const uint32_t c0 = reinterpret_cast<const uint16_t*>(g0 + 16 + 256)[lane];
-  const uint32_t c1 = reinterpret_cast<const uint16_t*>(g1 + 16 + 256)[lane];
-  double x0 = v0 * S[c0];
-  double x1 = v1 * S[c1];
-  if (m0.x == 1u && m1.x == 1u) {
-    // both groups lie inside a single row each: plain butterfly sums, one slot per group
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      x0 += __shfl_xor_sync(0xffffffffu, x0, d);
-      x1 += __shfl_xor_sync(0xffffffffu, x1, d);
-    }
-    if (lane == 0) {
-      scratch[m0.y] = x0;
-      if (on1) scratch[m1.y] = x1;
-    }
-    return;
+// One slice (see plan.h): T lanes per row, entries compacted per step.
+template <bool kTop>
+__device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, double sign) {
+  double* S = cx.S;
+  const int lane = cx.lane;
+  const uint4 hq = *reinterpret_cast<const uint4*>(sl);
+  const uint32_t nent = hq.x & 0xffffu, kmax = hq.x >> 16;
+  const int tl = (int)(hq.y & 0xffu), nrows = (int)((hq.y >> 8) & 0xffu);
+  const int T = 1 << tl;
+  const int g = lane >> tl, t = lane & (T - 1);
+  uint32_t dst = 0, flags = 0;
+  double dg = 1.0;
+  if (g < nrows) {
+    const uint4 q = *reinterpret_cast<const uint4*>(sl + 16 + 16 * g);
+    dst = q.x >> 16;
+    flags = q.y & 0xffffu;
+    dg = __hiloint2double((int)q.w, (int)q.z);
   }
-  const uint32_t le0 = m0.x & le_mask, le1 = m1.x & le_mask;
-  const int ss0 = 31 - __clz(le0), ss1 = 31 - __clz(le1);
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const double y0 = __shfl_up_sync(0xffffffffu, x0, d);
-    const double y1 = __shfl_up_sync(0xffffffffu, x1, d);
-    x0 += (lane - d >= ss0) ? y0 : 0.0;
-    x1 += (lane - d >= ss1) ? y1 : 0.0;
+  const double* v = reinterpret_cast<const double*>(sl + 16 + 16 * nrows);
+  const uint16_t* c = reinterpret_cast<const uint16_t*>(v + nent);
+  // entry (k, lane) at k * W + lane, W = nrows * T active lanes; padding entries are (0.0, col 0)
+  const int W = nrows << tl;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (lane < W) {
+    const double* vp = v + lane;
+    const uint16_t* cp = c + lane;
+    int k = 0;
+    for (; k + 4 <= (int)kmax; k += 4) {
+      const double v0 = vp[0], v1 = vp[W], v2 = vp[2 * W], v3 = vp[3 * W];
+      const uint32_t c0 = cp[0], c1 = cp[W], c2 = cp[2 * W], c3 = cp[3 * W];
+      a0 = fma(v0, S[c0], a0);
+      a1 = fma(v1, S[c1], a1);
+      a2 = fma(v2, S[c2], a2);
+      a3 = fma(v3, S[c3], a3);
+      vp += 4 * W;
+      cp += 4 * W;
+    }
+    // keep the association of the unrolled loop: step k feeds accumulator k & 3
+    if (k < (int)kmax) { a0 = fma(vp[0], S[cp[0]], a0); }
+    if (k + 1 < (int)kmax) { a1 = fma(vp[W], S[cp[W]], a1); }
+    if (k + 2 < (int)kmax) { a2 = fma(vp[2 * W], S[cp[2 * W]], a2); }
   }
-  const bool end0 = (lane == 31) || ((m0.x >> (lane + 1)) & 1u);
-  const bool end1 = (lane == 31) || ((m1.x >> (lane + 1)) & 1u);
-  if (end0) scratch[m0.y + __popc(le0) - 1] = x0;
-  if (on1 && end1) scratch[m1.y + __popc(le1) - 1] = x1;
+  double acc = (a0 + a1) + (a2 + a3);
+  for (int d = 1; d < T; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (g < nrows && t == 0) {
+    const double r = (((flags & kRowFresh) ? 0.0 : S[dst]) - sign * acc) / dg;
+    S[dst] = r;
+    if (kTop && (flags & kRowBcast)) {
+      for (int cc = 0; cc < cx.D->csize; ++cc)
+        if (cc != cx.D->rank) cx.cluster->map_shared_rank(S, cc)[dst] = r;
+    }
+  }
 }
 
-// Consumer warps: interpret the items of one section out of the ring (rounds, see plan.h).
-// Every warp reads every item header, so all of them execute the same barriers:
-//   first group item of a round  -> the previous round's row updates are complete
-//   first row item of a round    -> the round's segment sums are all in the scratch
+// Consumer warps: interpret the items of one section out of the ring (levels of slices, see plan.h).
+// Every warp reads every item header, so all of them execute the same barriers (one per level).
 // TOP sections (kTop): the rows of a level are shared out over the CTAs of the cluster; results are
 // stored into every CTA's replica of the top vector and a cluster-wide barrier separates levels.
 template <bool kTop>
 __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
   const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec], nlev = cx.D->sec_nlevels[sec];
-  double* S = cx.S;
-  double* scratch = cx.scratch;
   const int lane = cx.lane, warp = cx.warp;
-  const int tid = warp * 32 + lane;
-  const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // bits 0..lane
   uint32_t lvl = 0;
   for (uint32_t ch = c0; ch < c1; ++ch) {
     const uint32_t stage = cx.stage;
@@ -205,41 +213,19 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
       const uint4 hq = *reinterpret_cast<const uint4*>(chunk + off);
       const uint32_t bytes = hq.x;
       if (bytes == 0) break;
-      const uint32_t type = hq.y & 0xffu, count = hq.y >> 16, first = hq.z;
+      const uint32_t count = hq.y >> 16, first = hq.z;
       if (kTop) {
         while (lvl < hq.w) {
           cluster_level_sync(cx);
           ++lvl;
         }
+      } else if (first == 0 && !(cx.dbg_flags & 2)) {
+        consumer_barrier();  // a new level starts: the previous one is complete
       }
-      if (first == 0 && !(cx.dbg_flags & 2)) consumer_barrier();
       if (!(cx.dbg_flags & 1)) {
-        if (type == kItemGroups) {
-          const uint8_t* recs = chunk + off + 16;
-          for (uint32_t i = (uint32_t)(warp - (int)(first & (kWarps - 1))) & (kWarps - 1); i < count; i += 2 * kWarps) {
-            const bool on1 = i + kWarps < count;
-            const uint8_t* g0 = recs + (size_t)i * sizeof(GroupRec);
-            const uint8_t* g1 = on1 ? g0 + (size_t)kWarps * sizeof(GroupRec) : g0;
-            process_groups2(g0, g1, on1, S, scratch, lane, le_mask);
-          }
-        } else {
-          const uint4* recs = reinterpret_cast<const uint4*>(chunk + off + 16);
-          for (uint32_t i = (uint32_t)(tid - (int)(first & (kWarps * 32 - 1))) & (kWarps * 32 - 1); i < count;
-               i += kWarps * 32) {
-            const uint4 q = recs[i];
-            const uint32_t ns = q.y & 0x7fffu, dst = q.y >> 16, slot0 = q.x & 0xffffu;
-            const bool fresh = (q.y & kRowFresh) != 0;
-            const double dg = __hiloint2double((int)q.w, (int)q.z);
-            double sum = 0.0;
-            for (uint32_t s2 = 0; s2 < ns; ++s2) sum += scratch[slot0 + s2];
-            const double r = ((fresh ? 0.0 : S[dst]) - sign * sum) / dg;
-            S[dst] = r;
-            if (kTop && (q.x & kRowBcast)) {
-              for (int c = 0; c < cx.D->csize; ++c)
-                if (c != cx.D->rank) cx.cluster->map_shared_rank(S, c)[dst] = r;
-            }
-          }
-        }
+        const uint16_t* offs = reinterpret_cast<const uint16_t*>(chunk + off + 16);
+        for (uint32_t i = (uint32_t)(warp - (int)(first & (kWarps - 1))) & (kWarps - 1); i < count; i += kWarps)
+          process_slice<kTop>(cx, chunk + off + (uint32_t)offs[i] * 16u, sign);
       }
       off += bytes;
     }
@@ -256,7 +242,7 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
       ++lvl;
     }
   } else if (!(cx.dbg_flags & 2)) {
-    consumer_barrier();  // the section's last round is complete
+    consumer_barrier();  // the section's last level is complete
   }
 }
 

@@ -39,7 +39,7 @@ inline int ilog2(int p) {
 // Byte stream of one CTA.
 struct CtaStream {
   std::vector<uint8_t> bytes;
-  int64_t n_entries = 0, n_rows = 0, n_packets = 0;
+  int64_t n_entries = 0, n_rows = 0, n_packets = 0, lane_steps = 0;
   size_t room() const { return kChunkBytes - (bytes.size() % kChunkBytes); }
   void pad_to_chunk() {
     if (bytes.size() % kChunkBytes) bytes.resize(bytes.size() + room(), 0);
@@ -51,10 +51,9 @@ struct CtaStream {
   }
 };
 
-// Serialise the rows of one section as rounds (see plan.h).
+// Serialise the rows of one section as levels of slices (see plan.h).
 void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptions& opt, CtaStream& cs,
                   uint32_t& chunk0, uint32_t& chunk1, uint32_t& nlevels, int force_levels = -1) {
-  (void)opt;
   cs.pad_to_chunk();
   chunk0 = (uint32_t)(cs.bytes.size() / kChunkBytes);
   int maxlev = -1;
@@ -68,101 +67,123 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
     nlevels = (uint32_t)force_levels;
   }
   if (!rows.empty()) {
+    auto t_of = [&](uint32_t len) {
+      const int want = (int)((len + opt.lane_entries - 1) / std::max(1, opt.lane_entries));
+      return std::min(32, pow2ceil(std::max(1, want)));
+    };
     std::vector<uint32_t> ord(rows.size());
     std::iota(ord.begin(), ord.end(), 0u);
-    std::stable_sort(ord.begin(), ord.end(),
-                     [&](uint32_t a, uint32_t b) { return rows[a].level < rows[b].level; });
-    std::vector<GroupRec> groups;
-    std::vector<RowRec> recs;
-    auto flush_round = [&](int lev) {
-      if (recs.empty()) return;
-      // group records, split into items at chunk boundaries
-      size_t g = 0;
-      while (g < groups.size()) {
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+      if (rows[a].level != rows[b].level) return rows[a].level < rows[b].level;
+      return rows[a].len > rows[b].len;
+    });
+    std::vector<std::vector<uint8_t>> slices;  // serialised slices of the current level
+    size_t i = 0;
+    while (i < ord.size()) {
+      size_t j = i;
+      const int lev = rows[ord[i]].level;
+      while (j < ord.size() && rows[ord[j]].level == lev) ++j;
+      slices.clear();
+      size_t p = i;
+      while (p < j) {
+        const int T = t_of(rows[ord[p]].len);
+        const int cap = 32 / T;
+        size_t q = p;
+        while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T) ++q;
+        const int nr = (int)(q - p);
+        const uint32_t maxlen = rows[ord[p]].len;
+        const uint32_t kmax = (maxlen + T - 1) / T;
+        // entries in execution order: step k, the nr*T active lanes ascending; lanes whose row has
+        // run out get a zero entry (rows of a slice have similar lengths, so this padding is small)
+        std::vector<double> pv;
+        std::vector<uint16_t> pc;
+        int64_t real = 0;
+        for (uint32_t k = 0; k < kmax; ++k)
+          for (int lane = 0; lane < nr * T; ++lane) {
+            const int g = lane / T, t = lane % T;
+            const TmpRow& tr = rows[ord[p + g]];
+            const uint32_t idx = k * T + t;
+            if (idx < tr.len) {
+              pv.push_back(sc.vals[tr.ebeg + idx]);
+              pc.push_back(sc.cols[tr.ebeg + idx]);
+              ++real;
+            } else {
+              pv.push_back(0.0);
+              pc.push_back(0);
+            }
+          }
+        if (pv.size() > 65535u || kmax > 65535u) throw std::runtime_error("internal: slice too large");
+        std::vector<uint8_t> b;
+        auto put = [&](const void* ptr, size_t nb) {
+          const uint8_t* u = static_cast<const uint8_t*>(ptr);
+          b.insert(b.end(), u, u + nb);
+        };
+        SliceHdr sh;
+        std::memset(&sh, 0, sizeof(sh));
+        sh.nent = (uint16_t)pv.size();
+        sh.kmax = (uint16_t)kmax;
+        sh.tlog2 = (uint8_t)ilog2(T);
+        sh.nrows = (uint8_t)nr;
+        put(&sh, sizeof(sh));
+        for (int g = 0; g < nr; ++g) {
+          const TmpRow& tr = rows[ord[p + g]];
+          RowRec rr;
+          std::memset(&rr, 0, sizeof(rr));
+          rr.len = (uint16_t)tr.len;
+          rr.dst = tr.dst;
+          rr.flags = (uint16_t)((tr.kind ? kRowFresh : 0) | (tr.bcast ? kRowBcast : 0));
+          rr.diag = tr.diag;
+          put(&rr, sizeof(rr));
+        }
+        if (!pv.empty()) {
+          put(pv.data(), pv.size() * 8);
+          put(pc.data(), pc.size() * 2);
+        }
+        while (b.size() % 16) b.push_back(0);
+        if (b.size() + sizeof(ItemHdr) + 16 > (size_t)kChunkBytes) throw std::runtime_error("internal: slice exceeds a chunk");
+        slices.push_back(std::move(b));
+        cs.n_entries += real;
+        cs.n_rows += nr;
+        cs.n_packets += 1;
+        cs.lane_steps += 32 * (int64_t)kmax;
+        p = q;
+      }
+      // pack the level's slices into items
+      size_t s0 = 0;
+      while (s0 < slices.size()) {
+        auto item_bytes = [&](size_t a, size_t bnd) {
+          size_t tot = sizeof(ItemHdr) + (((bnd - a) * 2 + 15) / 16) * 16;
+          for (size_t k = a; k < bnd; ++k) tot += slices[k].size();
+          return tot;
+        };
         size_t room = cs.room();
-        if (room < sizeof(ItemHdr) + sizeof(GroupRec)) {
+        size_t s1 = s0;
+        while (s1 < slices.size() && item_bytes(s0, s1 + 1) <= room) ++s1;
+        if (s1 == s0) {
           cs.pad_to_chunk();
-          room = kChunkBytes;
+          continue;
         }
-        const size_t fit = std::min(groups.size() - g, (room - sizeof(ItemHdr)) / sizeof(GroupRec));
-        ItemHdr h;
-        std::memset(&h, 0, sizeof(h));
-        h.bytes = (uint32_t)(sizeof(ItemHdr) + fit * sizeof(GroupRec));
-        h.type = kItemGroups;
-        h.count = (uint16_t)fit;
-        h.first = (uint32_t)g;
-        h.level = (uint32_t)lev;
-        cs.put(h);
-        for (size_t k = 0; k < fit; ++k) cs.put(groups[g + k]);
-        g += fit;
-      }
-      size_t r = 0;
-      while (r < recs.size()) {
-        size_t room = cs.room();
-        if (room < sizeof(ItemHdr) + sizeof(RowRec)) {
-          cs.pad_to_chunk();
-          room = kChunkBytes;
+        ItemHdr ih;
+        std::memset(&ih, 0, sizeof(ih));
+        ih.bytes = (uint32_t)item_bytes(s0, s1);
+        ih.type = kItemSlices;
+        ih.count = (uint16_t)(s1 - s0);
+        ih.first = (uint32_t)s0;
+        ih.level = (uint32_t)lev;
+        cs.put(ih);
+        size_t offb = sizeof(ItemHdr) + (((s1 - s0) * 2 + 15) / 16) * 16;
+        std::vector<uint16_t> offs;
+        for (size_t k = s0; k < s1; ++k) {
+          offs.push_back((uint16_t)(offb / 16));
+          offb += slices[k].size();
         }
-        const size_t fit = std::min(recs.size() - r, (room - sizeof(ItemHdr)) / sizeof(RowRec));
-        ItemHdr h;
-        std::memset(&h, 0, sizeof(h));
-        h.bytes = (uint32_t)(sizeof(ItemHdr) + fit * sizeof(RowRec));
-        h.type = kItemRows;
-        h.count = (uint16_t)fit;
-        h.first = (uint32_t)r;
-        h.level = (uint32_t)lev;
-        cs.put(h);
-        for (size_t k = 0; k < fit; ++k) cs.put(recs[r + k]);
-        r += fit;
+        while ((offs.size() * 2) % 16) offs.push_back(0);
+        for (uint16_t o : offs) cs.put(o);
+        for (size_t k = s0; k < s1; ++k) cs.bytes.insert(cs.bytes.end(), slices[k].begin(), slices[k].end());
+        s0 = s1;
       }
-      cs.n_rows += (int64_t)recs.size();
-      cs.n_packets += 1;
-      groups.clear();
-      recs.clear();
-    };
-    uint32_t nslots = 0;   // slots used by the current round
-    uint32_t fill = 32;    // entries in the last group (32 = need a new one)
-    int cur_level = rows[ord[0]].level;
-    for (uint32_t oi : ord) {
-      const TmpRow& tr = rows[oi];
-      // slots this row needs if appended to the current round
-      const uint32_t first_part = tr.len == 0 ? 0u : std::min<uint32_t>(tr.len, fill == 32 ? 32u : 32u - fill);
-      const uint32_t need = tr.len == 0 ? 0u : 1u + (tr.len - first_part + 31u) / 32u;
-      if (tr.level != cur_level || nslots + need > (uint32_t)kMaxSlots || recs.size() >= 60000) {
-        flush_round(cur_level);
-        nslots = 0;
-        fill = 32;
-        cur_level = tr.level;
-      }
-      RowRec rr;
-      rr.slot0 = nslots | (tr.bcast ? kRowBcast : 0u);
-      rr.dst = tr.dst;
-      rr.diag = tr.diag;
-      uint32_t used = 0;
-      for (uint32_t k = 0; k < tr.len; ++k) {
-        if (fill == 32) {
-          GroupRec g;
-          std::memset(&g, 0, sizeof(g));
-          g.first_slot = nslots;  // slot of the segment starting at lane 0
-          groups.push_back(g);
-          fill = 0;
-        }
-        GroupRec& g = groups.back();
-        if (k == 0 || fill == 0) {  // a new segment starts here
-          g.heads |= (1u << fill);
-          ++nslots;
-          ++used;
-        }
-        g.val[fill] = sc.vals[tr.ebeg + k];
-        g.col[fill] = sc.cols[tr.ebeg + k];
-        ++fill;
-      }
-      if (used > 0x7fffu) throw std::runtime_error("internal: row needs too many slots");
-      rr.nslots = (uint16_t)(used | (tr.kind ? kRowFresh : 0));
-      recs.push_back(rr);
-      cs.n_entries += tr.len;
+      i = j;
     }
-    flush_round(cur_level);
   }
   cs.pad_to_chunk();
   chunk1 = (uint32_t)(cs.bytes.size() / kChunkBytes);
@@ -669,6 +690,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     out.n_entries += cs.n_entries;
     out.n_rows += cs.n_rows;
     out.n_packets += cs.n_packets;
+    out.lane_steps += cs.lane_steps;
     out.max_cta_entries = std::max(out.max_cta_entries, cs.n_entries);
     for (int s = 0; s < NSEC; ++s) out.max_levels = std::max(out.max_levels, (int)D.sec_nlevels[s]);
     // position -> original interior index maps

@@ -41,47 +41,48 @@ enum Section : int {
 // copies into a shared-memory ring with cp.async.bulk (TMA) far ahead of the consumers.  A chunk
 // holds whole items (a zero header terminates it early); every section starts on a chunk boundary.
 //
-// Work is organised in ROUNDS.  A round is a set of independent rows (same dependency level):
-//   pass 1  the entries of all its rows, concatenated row after row into one flat array, are cut
-//           into groups of 32; consumer warp w takes groups w, w+8, ...: lane l multiplies entry l
-//           by S[col], a segmented warp scan (segment = run of one row inside the group) reduces
-//           the products and every segment's sum goes to its own slot of a scratch array;
-//   pass 2  one thread per row adds the row's slots in order and updates
-//           S[dst] = (S[dst] - sign * sum) / diag      (fresh rows: S[dst] = -sign * sum / diag).
-// All lanes are busy whatever the row lengths, shared-memory reads of the stream are contiguous,
-// and every sum has a fixed association order (bit-reproducible).  A CTA barrier separates pass 1
-// from pass 2 and one round from the next.
+// Work is organised in LEVELS of independent rows; an item holds slices of one level.  A slice is
+// the unit of work of one consumer warp: 32 >> tlog2 rows of similar length, T = 1 << tlog2 lanes per
+// row.  Lane (g, t) accumulates entries t, t+T, t+2T, ... of row g (about 16 per lane), the T partial
+// sums are combined with log2(T) butterfly steps and lane t = 0 applies
+//   S[dst] = (S[dst] - sign * sum) / diag          (kRowFresh: S[dst] = -sign * sum / diag),
+// optionally storing the result into every other CTA of the cluster too (kRowBcast, top nodes).
+// Entries are stored step-major over the nrows*T active lanes: entry (k, lane) at k*nrows*T + lane,
+// zero-filled where a row has run out (rows of a slice have similar lengths; a padding entry has
+// val 0 and col 0).  Every sum has a fixed association order (bit-reproducible).  One CTA barrier
+// separates levels.
 //
-// Items (16-byte header + payload):
-//   kItemGroups : `count` group records; `first` = index of the first one inside its round
-//   kItemRows   : `count` row records;   `first` = index of the first one inside its round
-constexpr uint8_t kItemGroups = 1, kItemRows = 2;
-constexpr int kMaxSlots = 1024;    // scratch slots (segment sums) a round may use
+// Item:  [ItemHdr 16 B][count x uint16 slice offsets (16-byte units from the item start), padded to 16 B][slices]
+// Slice: [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][nent x uint16]  (+ padding to 16 B)
+// Slice i of the item is executed by consumer warp (first + i) % kWarps.
+constexpr uint8_t kItemSlices = 1;
+constexpr int kMaxSlots = 1024;    // scratch doubles used when the top right-hand side is combined
 struct alignas(16) ItemHdr {
   uint32_t bytes;   // size of the item incl. this header, 0 = end of chunk
   uint8_t type;
   uint8_t pad0_;
-  uint16_t count;
-  uint32_t first;
-  uint32_t level;   // dependency level inside the section (diagnostics / emulator checks)
+  uint16_t count;   // slices in the item
+  uint32_t first;   // index of the item's first slice inside its level (0: a new level starts)
+  uint32_t level;   // dependency level inside the section
 };
 static_assert(sizeof(ItemHdr) == 16, "ItemHdr must be 16 bytes");
 
-struct alignas(16) GroupRec {
-  uint32_t heads;       // bit l: entry l starts a segment (bit 0 always set)
-  uint32_t first_slot;  // scratch slot of the first segment; later segments follow consecutively
-  uint32_t pad_[2];
-  double val[32];
-  uint16_t col[32];     // index into the CTA's shared vector S (padding entries: val 0, col 0)
+struct alignas(16) SliceHdr {
+  uint16_t nent;    // stored entries = kmax * nrows * T
+  uint16_t kmax;    // steps = ceil(longest row / T)
+  uint8_t tlog2;
+  uint8_t nrows;
+  uint16_t pad0_;
+  uint32_t pad1_[2];
 };
-static_assert(sizeof(GroupRec) == 336, "GroupRec must be 336 bytes");
+static_assert(sizeof(SliceHdr) == 16, "SliceHdr must be 16 bytes");
 
-constexpr uint16_t kRowFresh = 0x8000u;
-constexpr uint32_t kRowBcast = 0x80000000u;  // in slot0: also store the result into every other CTA of the cluster
+constexpr uint16_t kRowFresh = 1, kRowBcast = 2;
 struct alignas(16) RowRec {
-  uint32_t slot0;   // first scratch slot of the row | kRowBcast
-  uint16_t nslots;  // number of slots | kRowFresh
+  uint16_t len;
   uint16_t dst;     // index into S
+  uint16_t flags;
+  uint16_t pad_;
   double diag;
 };
 static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
@@ -121,13 +122,15 @@ struct DomainPlan {
   std::vector<int32_t> imap;      // ownmap / topmap entries
   // statistics
   int64_t nnz_L = 0;              // strictly-lower nnz of L
-  int64_t n_entries = 0, n_rows = 0, n_packets = 0;   // n_packets = rounds
+  int64_t n_entries = 0, n_rows = 0, n_packets = 0;   // n_packets = slices
+  int64_t lane_steps = 0;                             // sum over slices of 32 * kmax (lane utilisation = n_entries / lane_steps)
   int32_t n_top = 0, max_levels = 0;
   int64_t max_cta_entries = 0, top_entries = 0;
 };
 
 struct BuildOptions {
   int csize = 1;
+  int lane_entries = 16;      // aimed entries per lane of a row
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;
   int max_smem_doubles = 28000;

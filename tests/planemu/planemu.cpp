@@ -3,6 +3,7 @@
 // csrc/kernels.cu does (same sections, same level barriers -- emulated with snapshot semantics so a
 // row that reads a value written in its own level is caught), so the host analysis can be
 // validated without a GPU.
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,18 +27,16 @@ struct Emu {
   explicit Emu(const DomainPlan& p) : P(p) {
     for (auto& d : P.ctas) S.emplace_back((size_t)d.smem_doubles, 0.0);
   }
-  // Interprets the chunks of one section exactly like the consumer warps (rounds: pass 1 = group
-  // records -> segment sums in scratch slots, pass 2 = row records).  Checks: a value written in
-  // a level is not read in the same level; slots are written before they are summed and never
-  // twice per round; items are well formed.
-  // only_level >= 0: process just the items of that level (top sections, run level by level over all CTAs)
+  // Interprets the chunks of one section exactly like the consumer warps (levels of slices).  Checks:
+  // items / slices are well formed, levels are monotone, a value written in a level is not read in
+  // the same level, no destination is written twice in a level.
+  // only_level >= 0: process just the items of that level (top sections run level by level over all CTAs)
   void section(int c, int sec, double sign, int only_level = -1) {
     const CtaDesc& D = P.ctas[c];
     std::vector<double>& s = S[c];
     std::vector<int> wrote_level(s.size(), -1);
-    std::vector<double> scratch(kMaxSlots, 0.0);
-    std::vector<char> slot_set(kMaxSlots, 0);
-    uint32_t expect_group = 0, expect_row = 0;
+    int cur_level = -1;
+    uint32_t expect_first = 0;
     for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
       const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
       size_t off = 0;
@@ -46,59 +45,58 @@ struct Emu {
         std::memcpy(&h, base + off, sizeof(h));
         if (h.bytes == 0) break;
         if (off + h.bytes > (size_t)kChunkBytes) throw std::runtime_error("item crosses its chunk");
+        if (h.type != kItemSlices) throw std::runtime_error("unknown item type");
         if (h.level >= D.sec_nlevels[sec]) throw std::runtime_error("level beyond nlevels");
+        if ((int)h.level < cur_level) throw std::runtime_error("levels not monotone in the stream");
+        if ((int)h.level > cur_level) {
+          if (h.first != 0) throw std::runtime_error("level does not start with first == 0");
+          cur_level = (int)h.level;
+          expect_first = 0;
+        }
+        if (h.first != expect_first) throw std::runtime_error("slice numbering broken");
+        expect_first += h.count;
         if (only_level >= 0 && (int)h.level != only_level) { off += h.bytes; continue; }
-        if (h.type == kItemGroups) {
-          if (h.bytes != sizeof(ItemHdr) + h.count * sizeof(GroupRec)) throw std::runtime_error("bad groups item size");
-          if (h.first == 0) { std::fill(slot_set.begin(), slot_set.end(), 0); expect_group = 0; expect_row = 0; }
-          if (h.first != expect_group) throw std::runtime_error("group numbering broken");
-          for (uint32_t i = 0; i < h.count; ++i) {
-            GroupRec g;
-            std::memcpy(&g, base + off + sizeof(ItemHdr) + (size_t)i * sizeof(GroupRec), sizeof(g));
-            if (!(g.heads & 1u)) throw std::runtime_error("group without a head at lane 0");
-            uint32_t slot = g.first_slot;
-            double acc = 0.0;
-            for (int l = 0; l < 32; ++l) {
-              if (l > 0 && ((g.heads >> l) & 1u)) {
-                if (slot >= (uint32_t)kMaxSlots || slot_set[slot]) throw std::runtime_error("bad slot");
-                scratch[slot] = acc; slot_set[slot] = 1; ++slot; acc = 0.0;
-              }
-              const uint32_t col = g.col[l];
+        const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
+        for (uint32_t i = 0; i < h.count; ++i) {
+          const uint8_t* sl = base + off + (size_t)offs[i] * 16;
+          SliceHdr sh;
+          std::memcpy(&sh, sl, sizeof(sh));
+          const int T = 1 << sh.tlog2;
+          if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
+          const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
+          const double* vals = reinterpret_cast<const double*>(sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
+          const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
+          if ((size_t)(reinterpret_cast<const uint8_t*>(cols + sh.nent) - (base + off)) > h.bytes) throw std::runtime_error("slice exceeds its item");
+          std::vector<double> acc(32, 0.0);   // per lane, 4 interleaved partial sums folded as on the device
+          std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
+          const uint32_t Wact = (uint32_t)sh.nrows * T;
+          if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
+          for (uint32_t k = 0; k < sh.kmax; ++k)
+            for (uint32_t lane = 0; lane < Wact; ++lane) {
+              const int g = lane / T, t = lane % T;
+              const uint32_t pos = k * Wact + lane;
+              const uint32_t col = cols[pos];
               if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
-              if (g.val[l] != 0.0 && wrote_level[col] == (int)h.level) throw std::runtime_error("reads a value produced in the same level");
-              acc += g.val[l] * s[col];
+              if (k * T + t < rr[g].len) {
+                if (wrote_level[col] == cur_level) throw std::runtime_error("reads a value produced in the same level");
+              } else if (vals[pos] != 0.0) {
+                throw std::runtime_error("non-zero padding entry");
+              }
+              part[lane][k & 3] += vals[pos] * s[col];
             }
-            if (slot >= (uint32_t)kMaxSlots || slot_set[slot]) throw std::runtime_error("bad slot");
-            scratch[slot] = acc; slot_set[slot] = 1;
-          }
-          expect_group += h.count;
-        } else if (h.type == kItemRows) {
-          if (h.bytes != sizeof(ItemHdr) + h.count * sizeof(RowRec)) throw std::runtime_error("bad rows item size");
-          if (h.first == 0 && expect_group == 0) { std::fill(slot_set.begin(), slot_set.end(), 0); expect_row = 0; }
-          if (h.first != expect_row) throw std::runtime_error("row numbering broken");
-          for (uint32_t i = 0; i < h.count; ++i) {
-            RowRec r;
-            std::memcpy(&r, base + off + sizeof(ItemHdr) + (size_t)i * sizeof(RowRec), sizeof(r));
-            const uint32_t ns = r.nslots & 0x7fffu;
-            const bool bcast = (r.slot0 & kRowBcast) != 0;
-            r.slot0 &= 0xffffu;
-            const bool fresh = (r.nslots & kRowFresh) != 0;
+          for (int g = 0; g < sh.nrows; ++g) {
+            if ((rr[g].len + T - 1) / T > sh.kmax) throw std::runtime_error("kmax too small");
             double sum = 0.0;
-            for (uint32_t k = 0; k < ns; ++k) {
-              if (r.slot0 + k >= (uint32_t)kMaxSlots || !slot_set[r.slot0 + k]) throw std::runtime_error("row sums an unwritten slot");
-              sum += scratch[r.slot0 + k];
-            }
-            if (r.dst >= (uint32_t)D.smem_doubles) throw std::runtime_error("dst out of range");
-            s[r.dst] = ((fresh ? 0.0 : s[r.dst]) - sign * sum) / r.diag;
-            wrote_level[r.dst] = (int)h.level;
-            if (bcast)
-              for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][r.dst] = s[r.dst];
+            for (int t = 0; t < T; ++t) sum += (part[g * T + t][0] + part[g * T + t][1]) + (part[g * T + t][2] + part[g * T + t][3]);
+            const int dst = rr[g].dst;
+            if (dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
+            if (wrote_level[dst] == cur_level) throw std::runtime_error("destination written twice in a level");
+            const bool fresh = (rr[g].flags & kRowFresh) != 0;
+            s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) / rr[g].diag;
+            wrote_level[dst] = cur_level;
+            if (rr[g].flags & kRowBcast)
+              for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
           }
-          expect_row += h.count;
-          expect_group = 0;  // the round's groups are complete once its rows start
-          if (false) (void)0;
-        } else {
-          throw std::runtime_error("unknown item type");
         }
         off += h.bytes;
       }
@@ -189,6 +187,7 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       stats[6] = (double)P.n_rows;
       stats[7] = (double)D0.smem_doubles;
       stats[8] = (double)P.stream.size();
+      stats[11] = (double)P.lane_steps;
       stats[9] = (double)std::max(D0.sec_nlevels[SEC_TOPF], D0.sec_nlevels[SEC_TOPB]);
       stats[10] = (double)std::max(D0.sec_nlevels[SEC_FWD], D0.sec_nlevels[SEC_BWD]);
 
