@@ -112,7 +112,7 @@ struct kb200_ctx {
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3;
+  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3, lane_entries = 0;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -196,6 +196,7 @@ void finalize(Ctx* c) {
   }
   opt.csize = c->csize;
   if (c->min_block >= 0) opt.min_block = c->min_block;
+  if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
   {
     std::atomic<int64_t> next(0);
     std::string first_err;
@@ -662,6 +663,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       require(!h->finalized, "stages must be set before the first operation");
       require(value >= 2 && value <= kb::kMaxStages, "stages must be in [2, 12]");
       h->stages = (int)value;
+    } else if (k == "lane_entries") {
+      require(!h->finalized && value >= 1 && value <= 256, "lane_entries must be set before the first operation");
+      h->lane_entries = (int)value;
     } else if (k == "min_block") {
       require(!h->finalized, "min_block must be set before the first operation");
       h->min_block = (int)value;

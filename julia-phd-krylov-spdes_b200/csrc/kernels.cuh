@@ -186,7 +186,7 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
   double acc = (a0 + a1) + (a2 + a3);
   for (int d = 1; d < T; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
   if (g < nrows && t == 0) {
-    const double r = (((flags & kRowFresh) ? 0.0 : S[dst]) - sign * acc) / dg;
+    const double r = (((flags & kRowFresh) ? 0.0 : S[dst]) - sign * acc) * dg;  // dg = 1 / diag
     S[dst] = r;
     if (kTop && (flags & kRowBcast)) {
       for (int cc = 0; cc < cx.D->csize; ++cc)

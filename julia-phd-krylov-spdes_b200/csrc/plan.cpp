@@ -132,7 +132,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
           rr.len = (uint16_t)tr.len;
           rr.dst = tr.dst;
           rr.flags = (uint16_t)((tr.kind ? kRowFresh : 0) | (tr.bcast ? kRowBcast : 0));
-          rr.diag = tr.diag;
+          rr.diag = 1.0 / tr.diag;  // the device multiplies by the reciprocal
           put(&rr, sizeof(rr));
         }
         if (!pv.empty()) {

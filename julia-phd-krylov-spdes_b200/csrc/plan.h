@@ -45,7 +45,7 @@ enum Section : int {
 // the unit of work of one consumer warp: 32 >> tlog2 rows of similar length, T = 1 << tlog2 lanes per
 // row.  Lane (g, t) accumulates entries t, t+T, t+2T, ... of row g (about 16 per lane), the T partial
 // sums are combined with log2(T) butterfly steps and lane t = 0 applies
-//   S[dst] = (S[dst] - sign * sum) / diag          (kRowFresh: S[dst] = -sign * sum / diag),
+//   S[dst] = (S[dst] - sign * sum) * (1/diag)      (kRowFresh: S[dst] = -sign * sum * (1/diag)),
 // optionally storing the result into every other CTA of the cluster too (kRowBcast, top nodes).
 // Entries are stored step-major over the nrows*T active lanes: entry (k, lane) at k*nrows*T + lane,
 // zero-filled where a row has run out (rows of a slice have similar lengths; a padding entry has
@@ -83,7 +83,7 @@ struct alignas(16) RowRec {
   uint16_t dst;     // index into S
   uint16_t flags;
   uint16_t pad_;
-  double diag;
+  double diag;      // RECIPROCAL of the row's divisor
 };
 static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
 

@@ -10,18 +10,19 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2001
 ndom = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 csizes = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [4]
 do_pcg = len(sys.argv) > 4 and sys.argv[4] == 'pcg'
-stages = [int(v) for v in os.environ.get('STAGES', '6').split(',')]
+stages = [int(v) for v in os.environ.get('STAGES', '3').split(',')]
+extra = [dict(kv.split('=') for kv in cfg.split('+')) for cfg in os.environ.get('OPTS', '').split(',') if cfg] or [{}]
 t = time.time(); pr = PB.build_problem(nx, ndom, ireal=1); print('host prep %.1fs' % (time.time() - t), flush=True)
 B, parts = PB.algorithmic_bytes_per_iteration(pr)
 print('B_iter GB', B / 1e9, {k: v / 1e9 for k, v in parts.items()}, flush=True)
-for cs, nst in [(a, b) for a in csizes for b in stages]:
+for cs, nst, ex in [(a, b, e) for a in csizes for b in stages for e in extra]:
     t = time.time()
-    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=cs, profile=True, options={'stages': nst})
+    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=cs, profile=True, options=dict({'stages': nst}, **{k: int(v) for k, v in ex.items()}))
     S.h.finalize(); tf = time.time() - t
     st = S.h.stats()
     ms = S.h.time_kernel(0, 20)
     alg = parts['trisolve'] + parts['spmv']
-    print(f"csize={cs} stages={nst} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
+    print(f"csize={cs} stages={nst} {ex} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
     for fl in [int(v) for v in os.environ.get('FLAGS', '').split(',') if v]:
         S.h.set_option('dbg_flags', fl); print(f'   dbg_flags={fl}: schur kernel {S.h.time_kernel(0, 10):.3f} ms', flush=True); S.h.set_option('dbg_flags', 0)
     if os.environ.get('DBG'):

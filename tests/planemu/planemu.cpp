@@ -92,7 +92,7 @@ struct Emu {
             if (dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
             if (wrote_level[dst] == cur_level) throw std::runtime_error("destination written twice in a level");
             const bool fresh = (rr[g].flags & kRowFresh) != 0;
-            s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) / rr[g].diag;
+            s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) * rr[g].diag;  // reciprocal stored
             wrote_level[dst] = cur_level;
             if (rr[g].flags & kRowBcast)
               for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
