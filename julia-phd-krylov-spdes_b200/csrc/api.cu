@@ -112,7 +112,7 @@ struct kb200_ctx {
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3, lane_entries = 0;
+  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3, lane_entries = 0, pad_tol_pct = -1;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -189,14 +189,17 @@ void finalize(Ctx* c) {
   std::vector<kb::DomainPlan> plans(nloc);
   kb::BuildOptions opt;
   if (c->csize == 0) {
-    // automatic cluster size: enough CTAs to fill the 148 SMs twice over, at most 8 per subdomain
-    int cs = 1;
-    while (cs < 8 && nloc * cs < 600) cs *= 2;
+    // automatic cluster size: 4 CTAs per subdomain measured best at 256 subdomains per GPU;
+    // 8 only when 4 would leave SMs without a CTA
+    int cs = 4;
+    if (nloc * 4 < 148) cs = 8;
+    if (nloc >= 2048) cs = 2;
     c->csize = cs;
   }
   opt.csize = c->csize;
   if (c->min_block >= 0) opt.min_block = c->min_block;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
+  if (c->pad_tol_pct >= 0) opt.pad_tol = c->pad_tol_pct / 100.0;
   {
     std::atomic<int64_t> next(0);
     std::string first_err;
@@ -663,6 +666,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       require(!h->finalized, "stages must be set before the first operation");
       require(value >= 2 && value <= kb::kMaxStages, "stages must be in [2, 12]");
       h->stages = (int)value;
+    } else if (k == "pad_tol_pct") {
+      require(!h->finalized && value >= 0 && value <= 100, "pad_tol_pct in [0, 100], before the first operation");
+      h->pad_tol_pct = (int)value;
     } else if (k == "lane_entries") {
       require(!h->finalized && value >= 1 && value <= 256, "lane_entries must be set before the first operation");
       h->lane_entries = (int)value;

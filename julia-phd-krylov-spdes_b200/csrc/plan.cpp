@@ -89,7 +89,12 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
         const int T = t_of(rows[ord[p]].len);
         const int cap = 32 / T;
         size_t q = p;
-        while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T) ++q;
+        // rows of a slice are padded to its longest row: stop when the next row is too much shorter
+        const uint32_t len0 = rows[ord[p]].len;
+        const uint32_t min_len = (uint32_t)(opt.pad_tol * (double)len0);
+        while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T &&
+               (rows[ord[q]].len >= min_len || len0 - rows[ord[q]].len <= 1))
+          ++q;
         const int nr = (int)(q - p);
         const uint32_t maxlen = rows[ord[p]].len;
         const uint32_t kmax = (maxlen + T - 1) / T;

@@ -131,6 +131,7 @@ struct DomainPlan {
 struct BuildOptions {
   int csize = 1;
   int lane_entries = 16;      // aimed entries per lane of a row
+  double pad_tol = 0.0;       // a slice only takes rows at least pad_tol x its longest row (0: no limit)
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;
   int max_smem_doubles = 28000;

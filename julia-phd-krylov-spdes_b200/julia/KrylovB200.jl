@@ -173,4 +173,81 @@ function pcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, M::Un
 end
 cg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}; maxit::Int=0) = pcg(S, b, x, nothing; maxit=maxit)
 
+
+# ---------------------------------------------------------------------------------------------------
+# Deflated / recycling solvers (defcg.jl:242-308, eigcg.jl:143-267, defcg.jl:337-473).
+# The reference's loops are kept; every n_Γ-sized array becomes a column of a device block
+# (kb200_mat_alloc) and the BLAS-1/2 calls become kb200_op_* calls.  `defpcg` below is the complete
+# pattern; eigpcg / eigdefpcg follow the Python mirror (../solvers.py) line for line with the same
+# primitives -- their Rayleigh-Ritz restarts stay the reference's own LAPACK lines
+# (eigvecs / rank / svd / eigen, eigcg.jl:220-228) applied to the small host matrix VtAV.
+# ---------------------------------------------------------------------------------------------------
+module DeviceOps
+using ..KrylovB200: LIB, chk, B200SchurOperator
+mat_alloc(S, ncols) = (id = Ref{Int64}(0); chk(ccall((:kb200_mat_alloc, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}), S.h, ncols, id)); id[])
+mat_free(S, id) = chk(ccall((:kb200_mat_free, LIB), Cint, (Ptr{Cvoid}, Int64), S.h, id))
+mat_set(S, id, col0, A::VecOrMat{Float64}) = chk(ccall((:kb200_mat_set, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}), S.h, id, col0, size(A, 2), A))
+mat_get!(out::VecOrMat{Float64}, S, id, col0) = (chk(ccall((:kb200_mat_get, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}), S.h, id, col0, size(out, 2), out)); out)
+apply(S, which, src, scol, dst, dcol, ncols=1) = chk(ccall((:kb200_op_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Int64), S.h, which, src, scol, dst, dcol, ncols))
+axpby(S, a, x, xc, b, y, yc) = chk(ccall((:kb200_op_axpby, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Float64, Int64, Int64), S.h, a, x, xc, b, y, yc))
+dot(S, x, xc, y, yc) = (o = Ref{Float64}(0); chk(ccall((:kb200_op_dot, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ref{Float64}), S.h, x, xc, y, yc, o)); o[])
+gemv_t(S, A, col0, k, x, xc) = (y = Vector{Float64}(undef, k); chk(ccall((:kb200_op_gemv_t, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}), S.h, A, col0, k, x, xc, y)); y)
+gemv_n(S, a, A, col0, k, mu, b, y, yc) = chk(ccall((:kb200_op_gemv_n, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Int64), S.h, a, A, col0, k, mu, b, y, yc))
+gemm_tn(S, A, ca, ka, B, cb, kb) = (C = Matrix{Float64}(undef, ka, kb); chk(ccall((:kb200_op_gemm_tn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}), S.h, A, ca, ka, B, cb, kb, C)); C)
+gemm_nn(S, A, ca, ka, Q::Matrix{Float64}, C, cc) = chk(ccall((:kb200_op_gemm_nn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64), S.h, A, ca, ka, Q, size(Q, 2), C, cc))
+end
+
+"""
+    defpcg(S, b, x, W, M; maxit=0) -> (x, it, res_norm)          # defcg.jl:242-308
+"""
+function defpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, W::Matrix{Float64},
+                M::Union{B200NeumannNeumann,Nothing}; maxit::Int=0)
+  D = DeviceOps
+  n, nvec = size(W)
+  op = S.assembled ? 1 : 0
+  X, R, Z, P, AP, B = 0, 1, 2, 3, 4, 5                       # columns of the work block (0-based)
+  wk = D.mat_alloc(S, 7); Wd = D.mat_alloc(S, nvec); AWd = D.mat_alloc(S, nvec)
+  try
+    D.mat_set(S, Wd, 0, W); D.mat_set(S, wk, B, b); D.mat_set(S, wk, X, x)
+    D.apply(S, op, Wd, 0, AWd, 0, nvec)                       # WtA[ivec, :] .= A * W[:, ivec]   (:261-264)
+    WtAW = D.gemm_tn(S, AWd, 0, nvec, Wd, 0, nvec)            # :268
+    resid!() = (D.apply(S, op, wk, X, wk, AP); D.axpby(S, 1.0, wk, B, 0.0, wk, R); D.axpby(S, -1.0, wk, AP, 1.0, wk, R))
+    precond!() = M === nothing ? D.axpby(S, 1.0, wk, R, 0.0, wk, Z) : D.apply(S, 2, wk, R, wk, Z)
+    resid!()
+    mu = WtAW \ D.gemv_t(S, Wd, 0, nvec, wk, R)               # :272-274
+    D.gemv_n(S, 1.0, Wd, 0, nvec, mu, 1.0, wk, X)             # x .+= W * mu
+    maxit == 0 ? maxit = n : nothing
+    res_norm = Vector{Float64}(undef, maxit + 1)
+    it = 1
+    resid!()
+    rTr = D.dot(S, wk, R, wk, R); res_norm[it] = sqrt(rTr)
+    precond!()
+    rTz = D.dot(S, wk, R, wk, Z)
+    mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)              # :284
+    D.axpby(S, 1.0, wk, Z, 0.0, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)
+    tol = eps_rtol * norm(b)
+    while (it < maxit) && (res_norm[it] > tol)                # :290
+      D.apply(S, op, wk, P, wk, AP)
+      d = D.dot(S, wk, P, wk, AP)
+      alpha = rTz / d
+      beta = 1. / rTz
+      D.axpby(S, alpha, wk, P, 1.0, wk, X)
+      D.axpby(S, -alpha, wk, AP, 1.0, wk, R)
+      rTr = D.dot(S, wk, R, wk, R)
+      precond!()
+      rTz = D.dot(S, wk, R, wk, Z)
+      beta *= rTz
+      mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)            # :301
+      D.axpby(S, 1.0, wk, Z, beta, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)   # :302
+      it += 1
+      res_norm[it] = sqrt(rTr)
+    end
+    D.mat_get!(x, S, wk, X)
+    return x, it, res_norm[1:it]
+  finally
+    D.mat_free(S, wk); D.mat_free(S, Wd); D.mat_free(S, AWd)
+  end
+end
+export defpcg
+
 end # module
