@@ -191,8 +191,7 @@ void finalize(Ctx* c) {
   if (c->csize == 0) {
     // automatic cluster size: 4 CTAs per subdomain measured best at 256 subdomains per GPU;
     // 8 only when 4 would leave SMs without a CTA
-    int cs = 4;
-    if (nloc * 4 < 148) cs = 8;
+    int cs = 4;  // 8 measured slower at every subdomain count tried
     if (nloc >= 2048) cs = 2;
     c->csize = cs;
   }

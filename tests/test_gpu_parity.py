@@ -298,3 +298,26 @@ def test_eigpcg_and_eigdefpcg_match_oracle():
     assert res2[-1] <= 1e-7 * np.linalg.norm(b2)
     assert np.linalg.norm(x2 - x2o) <= 1e-5 * np.linalg.norm(x2o)
     assert V2.shape == (n, nvec)
+
+
+def test_bitwise_reproducible_and_race_free():
+    """compute-sanitizer is closed on this pool, so races are hunted the other way: every sum in the
+    stream kernel has a fixed association order, hence repeated applies must be bit-identical --
+    across launches, cluster sizes sharing a plan, and ring depths (timing changes, results must not)."""
+    pr = get_problem(97, 9)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(pr.sd.n_gamma)
+    ref = None
+    for csize, stages in [(4, 3), (4, 2), (8, 3), (2, 3)]:
+        S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors, csize=csize, options={"stages": stages})
+        ys = [S * x for _ in range(12)]
+        for y in ys[1:]:
+            assert np.array_equal(y, ys[0])
+        bs = [S.schur_rhs(pr.blocks.b_I, pr.blocks.b_G) for _ in range(4)]
+        assert all(np.array_equal(b, bs[0]) for b in bs[1:])
+        if stages != 3:
+            assert np.array_equal(ys[0], ref[csize])          # ring depth does not change the arithmetic
+        else:
+            ref = {**(ref or {}), csize: ys[0]}
+    # different cluster sizes associate sums differently: equal to rounding only
+    assert rel(ref[8], ref[4]) <= 1e-13 and rel(ref[2], ref[4]) <= 1e-13
