@@ -83,6 +83,11 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d,
  * stored, sorted rows).  Replaces the inner IterativeSolvers.cg(A_IIdd, ., Pl=...) of :648-650. */
 int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm,
                           const int64_t* L_colptr, const int64_t* L_rowval, const double* L_nzval);
+/* New coefficient realization on the same mesh / partition / ordering (Example07:160-204 loop): same
+ * sparsity patterns, new values.  The uploads above may also simply be repeated.  The next operation
+ * re-runs the host analysis and refreshes the device streams (round 1: full rebuild, ~1-2 s at 4M DOF). */
+int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzval);
+int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval);
 /* ΠSd[d] of NeumannNeumannSchurPreconditioner (:1125), n_gd x n_gd column-major. */
 int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS);
 /* Dense local Schur complement S_d (assemble_local_schurs, :667-695), n_gd x n_gd column-major. */

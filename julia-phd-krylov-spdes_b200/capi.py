@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SYMBOLS = [
     "kb200_last_error", "kb200_create", "kb200_nccl_unique_id", "kb200_create_dist", "kb200_destroy",
     "kb200_set_option", "kb200_set_topology", "kb200_local_range", "kb200_upload_local_blocks",
-    "kb200_upload_cholesky", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
+    "kb200_upload_cholesky", "kb200_update_cholesky_values", "kb200_update_local_block_values", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
     "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
     "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_get_stats", "kb200_get_interface_maps",
@@ -154,6 +154,19 @@ class Handle:
         p1 = _i64(perm0) + 1
         _chk(lib().kb200_upload_cholesky(self.h, C.c_int64(d), _p(p1, C.c_int64), _p(lp, C.c_int64),
                                          _p(li, C.c_int64), _p(lx, C.c_double)))
+
+    def update_cholesky_values(self, d, L):
+        L = L.tocsc()
+        L.sort_indices()
+        lx = _f64(L.data)
+        _chk(lib().kb200_update_cholesky_values(self.h, C.c_int64(d), _p(lx, C.c_double)))
+
+    def update_local_block_values(self, d, A_IG, A_GG):
+        g, hh = A_IG.tocsc(), A_GG.tocsc()
+        g.sort_indices()
+        hh.sort_indices()
+        gx, hx = _f64(g.data), _f64(hh.data)
+        _chk(lib().kb200_update_local_block_values(self.h, C.c_int64(d), _p(gx, C.c_double), _p(hx, C.c_double)))
 
     def upload_nn_pinv(self, d, PiS):
         M = np.asfortranarray(PiS, dtype=np.float64)

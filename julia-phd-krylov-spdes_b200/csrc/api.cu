@@ -367,11 +367,7 @@ void finalize(Ctx* c) {
   c->stats[8] = c->n_cta;
   c->stats[9] = c->csize;
   c->stats[10] = (double)c->mat_off[nloc] * 8.0;
-  c->finalized = true;
-  // the per-subdomain host copies of L are no longer needed
-  for (int64_t d = c->d0; d < c->d1; ++d) {
-    c->doms[d].in.L = kb::Csc();
-  }
+  c->finalized = true;  // host copies of the inputs are kept: value updates re-run the analysis
 }
 
 // ---- launches ----------------------------------------------------------------------------------
@@ -737,8 +733,8 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colp
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
-    require(!h->finalized, "already finalized");
     if (!is_local(h, d)) return;
+    h->finalized = false;  // (re-)upload: the next operation re-runs the analysis
     DomHost& dh = h->doms[d];
     dh.in.n_I = (int32_t)dh.n_I;
     dh.in.n_gd = (int32_t)dh.n_gd;
@@ -753,8 +749,8 @@ int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const 
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
-    require(!h->finalized, "already finalized");
     if (!is_local(h, d)) return;
+    h->finalized = false;
     DomHost& dh = h->doms[d];
     require(perm != nullptr || dh.n_I == 0, "null perm");
     dh.in.perm.resize(dh.n_I);
@@ -767,6 +763,31 @@ int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const 
     }
     csc_from_julia(dh.in.L, dh.n_I, dh.n_I, L_colptr, L_rowval, L_nzval, "L");
     dh.have_chol = true;
+  });
+}
+
+int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzval) {
+  return guarded([&]() {
+    require(h && h->topo && L_nzval, "null argument");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    require(dh.have_chol, "kb200_upload_cholesky must come first");
+    std::copy(L_nzval, L_nzval + dh.in.L.nzval.size(), dh.in.L.nzval.begin());
+    h->finalized = false;
+  });
+}
+
+int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval) {
+  return guarded([&]() {
+    require(h && h->topo && AIG_nzval && AGG_nzval, "null argument");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    require(dh.have_blocks, "kb200_upload_local_blocks must come first");
+    std::copy(AIG_nzval, AIG_nzval + dh.in.AIG.nzval.size(), dh.in.AIG.nzval.begin());
+    std::copy(AGG_nzval, AGG_nzval + dh.in.AGG.nzval.size(), dh.in.AGG.nzval.begin());
+    h->finalized = false;
   });
 }
 

@@ -37,6 +37,14 @@ class B200SchurOperator:
         self.N = sd.n_gamma
         self.assembled = False
 
+    def update_realization(self, blocks, factors):
+        """New coefficient realization on the same mesh / partition / ordering (the loop of
+        Example07_PcgSchurStochasticEllipticPde.jl:160-204): values only."""
+        d0, d1 = self.local_range
+        for d in range(d0, d1):
+            self.h.update_local_block_values(d, blocks.A_IG[d], blocks.A_GG[d])
+            self.h.update_cholesky_values(d, factors[d][1])
+
     # LinearMaps.FunctionMap surface
     def __matmul__(self, x):
         return self.mul(x)

@@ -321,3 +321,22 @@ def test_bitwise_reproducible_and_race_free():
             ref = {**(ref or {}), csize: ys[0]}
     # different cluster sizes associate sums differently: equal to rounding only
     assert rel(ref[8], ref[4]) <= 1e-13 and rel(ref[2], ref[4]) <= 1e-13
+
+
+def test_update_realization_values_only():
+    """Second realization on the same mesh / partition / ordering: only values are re-sent."""
+    from krylov_b200.hostprep import problem as PB
+    base = PB.build_mesh_and_partition(65, 16)
+    pr1 = PB.realization(base, ireal=1)
+    pr2 = PB.realization(base, ireal=2)
+    for d in range(16):          # same ordering => same factor pattern
+        assert np.array_equal(pr1.factors[d][0], pr2.factors[d][0])
+        assert np.array_equal(pr1.factors[d][1].indices, pr2.factors[d][1].indices)
+    S = fem.B200SchurOperator(pr1.sd, pr1.blocks, pr1.factors, csize=4)
+    x = np.random.default_rng(2).standard_normal(pr1.sd.n_gamma)
+    y1 = S * x
+    S.update_realization(pr2.blocks, pr2.factors)
+    y2 = S * x
+    inner2 = E.ExactInterior(pr2.blocks.A_II)
+    assert rel(y2, E.apply_local_schurs(pr2.blocks, inner2, pr2.sd, x)) <= 1e-12
+    assert rel(y1, y2) > 1e-3
