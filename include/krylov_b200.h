@@ -124,6 +124,18 @@ int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out);
 int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled,
               int precond, int64_t* it, double* res_norm, kb200_timings* timings);
 
+/* pcg for nrhs right-hand sides (B, X: n_gamma x nrhs column-major): independent recurrences per RHS,
+ * i.e. the reference's sequential loop (Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179);
+ * its[k] and res_norm[k*res_stride ...] per RHS.  Round 1 solves one RHS after the other. */
+int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, int64_t maxit, double rtol,
+                    int assembled, int precond, int64_t* its, double* res_norm, int64_t res_stride);
+/* defpcg(A, b, x, W, M; maxit) of RecyclingKrylovSolvers/defcg.jl:242-308, whole solve on the device:
+ * W (n_gamma x nvec, column-major) is uploaded, WtA' = S W and WtAW are formed on the device, the
+ * small system WtAW \ . is applied per iteration as explicit inverse + one refinement step (no host
+ * round trip), p = beta p + z - W mu by a dense GEMV kernel. */
+int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t maxit,
+                 double rtol, int assembled, int precond, int64_t* it, double* res_norm, kb200_timings* timings);
+
 /* ---- device-resident vectors and bases (deflated / recycling solvers) ----------------------------- */
 /* defpcg / eigpcg / eigdefpcg (RecyclingKrylovSolvers/defcg.jl:242-308, eigcg.jl:143-267,
  * defcg.jl:337-473) keep their control flow -- including the Rayleigh-Ritz restarts on small dense

@@ -17,7 +17,7 @@ SYMBOLS = [
     "kb200_upload_cholesky", "kb200_update_cholesky_values", "kb200_update_local_block_values", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
     "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
     "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
-    "kb200_get_dense_local_schur", "kb200_pcg", "kb200_get_stats", "kb200_get_interface_maps",
+    "kb200_get_dense_local_schur", "kb200_pcg", "kb200_pcg_multi", "kb200_defpcg", "kb200_get_stats", "kb200_get_interface_maps",
     "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
     "kb200_op_gemm_tn", "kb200_op_gemm_nn",
@@ -235,6 +235,34 @@ class Handle:
         if isinstance(xin, np.ndarray) and xin is not x:
             xin[...] = x
         return x, it.value, res[:it.value].copy(), tm
+
+    def defpcg(self, b, x, W, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        b = _f64(b)
+        xin = x
+        x = _f64(x)
+        W = np.asfortranarray(W, dtype=np.float64)
+        cap = (maxit if maxit else self.n_gamma) + 1
+        res = np.empty(cap)
+        it = C.c_int64()
+        tm = Timings()
+        _chk(lib().kb200_defpcg(self.h, _p(b, C.c_double), _p(x, C.c_double), _p(W, C.c_double), C.c_int64(W.shape[1]),
+                                C.c_int64(maxit), C.c_double(rtol), int(assembled), int(precond), C.byref(it),
+                                _p(res, C.c_double), C.byref(tm)))
+        if isinstance(xin, np.ndarray) and xin is not x:
+            xin[...] = x
+        return x, it.value, res[:it.value].copy(), tm
+
+    def pcg_multi(self, B, X, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        B = np.asfortranarray(B, dtype=np.float64)
+        X = np.asfortranarray(X, dtype=np.float64)
+        nrhs = B.shape[1]
+        stride = (maxit if maxit else self.n_gamma) + 1
+        its = np.zeros(nrhs, dtype=np.int64)
+        res = np.zeros(nrhs * stride)
+        _chk(lib().kb200_pcg_multi(self.h, _p(B, C.c_double), _p(X, C.c_double), C.c_int64(nrhs), C.c_int64(maxit),
+                                   C.c_double(rtol), int(assembled), int(precond), _p(its, C.c_int64), _p(res, C.c_double),
+                                   C.c_int64(stride)))
+        return X, its, [res[k * stride:k * stride + its[k]].copy() for k in range(nrhs)]
 
     # ---- device-resident blocks -------------------------------------------------------------------
     def mat_alloc(self, ncols):

@@ -915,6 +915,137 @@ int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out) {
   });
 }
 
+// Deflation context of defpcg (defcg.jl:242-308), all on the device.
+struct Defl {
+  int k = 0;
+  const double* W = nullptr;    // n x k
+  const double* AW = nullptr;   // n x k   (WtA' : column ivec = A * W[:, ivec])
+  const double* Minv = nullptr; // k x k   inverse of WtAW
+  const double* M = nullptr;    // k x k   WtAW
+  double* y = nullptr;          // k
+  double* mu = nullptr;         // k
+};
+
+// Inverse of a small dense matrix by Gauss-Jordan elimination with partial pivoting (host, setup).
+static void invert_small(int k, std::vector<double> Ain, std::vector<double>& inv) {
+  inv.assign((size_t)k * k, 0.0);
+  for (int i = 0; i < k; ++i) inv[i + (size_t)i * k] = 1.0;
+  auto A = [&](int i, int j) -> double& { return Ain[i + (size_t)j * k]; };
+  auto B = [&](int i, int j) -> double& { return inv[i + (size_t)j * k]; };
+  for (int c = 0; c < k; ++c) {
+    int piv = c;
+    for (int i = c + 1; i < k; ++i)
+      if (std::fabs(A(i, c)) > std::fabs(A(piv, c))) piv = i;
+    if (A(piv, c) == 0.0) throw KbError(KB200_ERR_INPUT, "W' S W is singular: the deflation vectors are linearly dependent");
+    if (piv != c)
+      for (int j = 0; j < k; ++j) {
+        std::swap(A(piv, j), A(c, j));
+        std::swap(B(piv, j), B(c, j));
+      }
+    const double d = 1.0 / A(c, c);
+    for (int j = 0; j < k; ++j) {
+      A(c, j) *= d;
+      B(c, j) *= d;
+    }
+    for (int i = 0; i < k; ++i) {
+      if (i == c) continue;
+      const double f = A(i, c);
+      if (f == 0.0) continue;
+      for (int j = 0; j < k; ++j) {
+        A(i, j) -= f * A(c, j);
+        B(i, j) -= f * B(c, j);
+      }
+    }
+  }
+}
+
+static void defl_project(Ctx* c, const Defl& D, const double* basis, const double* v, const int* done_at, int iter) {
+  // mu = (W' S W)^{-1} (basis' v)
+  const int n = (int)c->n_gamma;
+  kb::gemv_t_kernel<<<(unsigned)D.k, kb::kVecThreads, 0, c->stream>>>(n, basis, n, v, D.y, done_at, iter);
+  kb::small_solve_kernel<<<1, 1024, (size_t)D.k * 3 * 8, c->stream>>>(D.k, D.Minv, D.M, D.y, D.mu, done_at, iter);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+}
+
+// PCG / deflated PCG recurrence on device-resident d_b, d_x (cg.jl:76-106, defcg.jl:277-305).
+// Returns {it, fail}; x in d_x, residual history in d_res.
+static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, const Defl* defl, KernelTimer& kt, int* it_out,
+                     int* fail_out) {
+  const int n = (int)c->n_gamma;
+  if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
+  kb::PcgState* st = c->d_state.p;
+  const int* done_at = &st->done_at;
+  // r = b - A x ; z = M \ r ; p = z (- W mu)                                         (cg.jl:83-90)
+  apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
+  kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
+                                                                        c->d_partB.p);
+  c->launches++;
+  auto precondition = [&](const int* da, int iter) {
+    if (precond) {
+      apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, da, iter, &kt);
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, da, iter);
+      c->launches++;
+    }
+  };
+  precondition(nullptr, 0);
+  kb::pcg_init_direction_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p,
+                                                                         c->d_partC.p, st, c->d_res.p, rtol, (int)maxit);
+  c->launches++;
+  if (defl) {  // p = z - W mu, mu = WtAW \ (WtA z)                                   (defcg.jl:284-285)
+    defl_project(c, *defl, defl->AW, c->d_z.p, nullptr, 0);
+    kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0, c->d_p.p);
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  int* h_flag = reinterpret_cast<int*>(c->h_pinned);
+  int k = 1;
+  bool done = false;
+  while (!done) {
+    const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
+    for (; k < kend; ++k) {
+      apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);    // Ap = A p ; d = p.Ap
+      kb::pcg_update_xr_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p, c->d_r.p,
+                                                                        c->d_partA.p, c->d_partB.p, st, k);
+      c->launches++;
+      precondition(done_at, k);                                                          // z = M \ r ; rTz
+      if (defl) defl_project(c, *defl, defl->AW, c->d_z.p, done_at, k);                  // mu               (defcg.jl:301)
+      kb::pcg_update_p_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p, c->d_partC.p,
+                                                                       st, c->d_res.p, nullptr, k);
+      c->launches++;
+      if (defl) {                                                                        // p -= W mu        (defcg.jl:302)
+        // pcg_update_p of iteration k may already have set done_at = k: the projection of this last
+        // direction is then irrelevant, and kernels of iteration k still run (done_at < k is false)
+        kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0,
+                                                                                     c->d_p.p, done_at, k);
+        c->launches++;
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_flag, &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    done = (h_flag[1] != INT_MAX) || (h_flag[3] != 0) || (k >= maxit);   // {it, done_at, maxit, fail}
+  }
+  *it_out = h_flag[0];
+  *fail_out = h_flag[3];
+}
+
+static void finish_timings(Ctx* c, KernelTimer& kt, kb200_timings& T, int64_t launches0, kb200_timings* tm) {
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+  T.solve_ms = ms;
+  if (c->profile) {
+    T.schur_ms = kt.total(0);
+    T.nn_ms = kt.total(1);
+    T.schur_launches = (int64_t)kt.spans[0].size();
+    T.nn_launches = (int64_t)kt.spans[1].size();
+  }
+  T.kernel_launches = c->launches - launches0;
+  if (tm) *tm = T;
+}
+
 int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled, int precond,
               int64_t* it_out, double* res_norm, kb200_timings* tm) {
   return guarded([&]() {
@@ -928,77 +1059,105 @@ int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double 
     kb200_timings T;
     std::memset(&T, 0, sizeof(T));
     const int64_t launches0 = c->launches;
-    const OpKind A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
-    if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
     KernelTimer kt(c);
-    kb::PcgState* st = c->d_state.p;
-    const int* done_at = &st->done_at;
     h2d(c, c->d_b.p, b, n, &T);
     h2d(c, c->d_x.p, x, n, &T);
     CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
-    // r = b - A x ; z = M \ r ; p = z                                                 (cg.jl:83-90)
-    apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
-    kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p,
-                                                                          c->d_partA.p, c->d_partB.p);
-    c->launches++;
-    if (precond) {
-      apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, nullptr, 0, &kt);
-    } else {
-      CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-      kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, nullptr, 0);
-      c->launches++;
-    }
-    kb::pcg_init_direction_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(
-        n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p, c->d_partC.p, st, c->d_res.p, rtol, (int)maxit);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    int* h_flag = reinterpret_cast<int*>(c->h_pinned);
-    int k = 1;
-    bool done = false;
-    while (!done) {
-      const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
-      for (; k < kend; ++k) {
-        // Ap = A p ; d = p.Ap                                                          (cg.jl:93-94)
-        apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);
-        kb::pcg_update_xr_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p,
-                                                                          c->d_r.p, c->d_partA.p, c->d_partB.p, st, k);
-        c->launches++;
-        // z = M \ r ; rTz = r.z                                                        (cg.jl:100-101)
-        if (precond) {
-          apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, done_at, k, &kt);
-        } else {
-          CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-          kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, done_at, k);
-          c->launches++;
-        }
-        kb::pcg_update_p_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p,
-                                                                         c->d_partC.p, st, c->d_res.p, nullptr, k);
-        c->launches++;
-      }
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaMemcpyAsync(h_flag, &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
-      // h_flag = {it, done_at, maxit, fail}
-      done = (h_flag[1] != INT_MAX) || (h_flag[3] != 0) || (k >= maxit);
-    }
+    int it = 0, fail = 0;
+    pcg_core(c, maxit, rtol, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, nullptr, kt, &it, &fail);
     CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
-    const int it = h_flag[0];
-    const int fail = h_flag[3];
     d2h(c, x, c->d_x.p, n, &T);
     d2h(c, res_norm, c->d_res.p, it, &T);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *it_out = it;
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
-    T.solve_ms = ms;
-    if (c->profile) {
-      T.schur_ms = kt.total(0);
-      T.nn_ms = kt.total(1);
-      T.schur_launches = (int64_t)kt.spans[0].size();
-      T.nn_launches = (int64_t)kt.spans[1].size();
+    finish_timings(c, kt, T, launches0, tm);
+    if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+  });
+}
+
+int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, int64_t maxit, double rtol, int assembled, int precond,
+                    int64_t* its, double* res_norm, int64_t res_stride) {
+  // independent recurrences per right-hand side (the reference's sequential loop over RHS,
+  // Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179); round 1: one solve after the other
+  if (!h || !B || !X || !its || nrhs < 1) {
+    g_err = "bad argument";
+    return KB200_ERR_INVALID;
+  }
+  const int64_t n = h->n_gamma;
+  for (int64_t k = 0; k < nrhs; ++k) {
+    std::vector<double> res((size_t)((maxit == 0 ? n : maxit) + 1));
+    int rc = kb200_pcg(h, B + k * n, X + k * n, maxit, rtol, assembled, precond, &its[k], res.data(), nullptr);
+    if (rc != KB200_OK) return rc;
+    if (res_norm) std::copy(res.begin(), res.begin() + std::min<int64_t>(its[k], res_stride), res_norm + k * res_stride);
+  }
+  return KB200_OK;
+}
+
+int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t maxit, double rtol,
+                 int assembled, int precond, int64_t* it_out, double* res_norm, kb200_timings* tm) {
+  return guarded([&]() {
+    require(h && b && x && W && it_out && res_norm && nvec >= 1 && nvec <= 4096, "bad argument");
+    finalize(h);
+    use_device(h);
+    Ctx* c = h;
+    const int n = (int)c->n_gamma;
+    const int k = (int)nvec;
+    if (maxit == 0) maxit = n;
+    require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+    kb200_timings T;
+    std::memset(&T, 0, sizeof(T));
+    const int64_t launches0 = c->launches;
+    const OpKind A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
+    KernelTimer kt(c);
+    DevBuf<double> dW, dAW, dMinv, dM, dy, dmu;
+    dW.alloc((size_t)n * k);
+    dAW.alloc((size_t)n * k);
+    dMinv.alloc((size_t)k * k);
+    dM.alloc((size_t)k * k);
+    dy.alloc(k);
+    dmu.alloc(k);
+    h2d(c, dW.p, W, (int64_t)n * k, &T);
+    h2d(c, c->d_b.p, b, n, &T);
+    h2d(c, c->d_x.p, x, n, &T);
+    CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+    // WtA[ivec, :] = A * W[:, ivec] ; WtAW = WtA * W                                  (defcg.jl:261-268)
+    for (int j = 0; j < k; ++j)
+      apply_op(c, A, dW.p + (size_t)j * n, dAW.p + (size_t)j * n, nullptr, nullptr, nullptr, 0, &kt);
+    {
+      dim3 grid((unsigned)((k + 15) / 16), (unsigned)((k + 15) / 16));
+      kb::gemm_tn_kernel<<<grid, 256, 0, c->stream>>>(n, k, k, dAW.p, n, dW.p, n, dM.p);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
     }
-    T.kernel_launches = c->launches - launches0;
-    if (tm) *tm = T;
+    std::vector<double> Mh((size_t)k * k), Minv;
+    CUDA_TRY(cudaMemcpyAsync(Mh.data(), dM.p, Mh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    invert_small(k, Mh, Minv);
+    CUDA_TRY(cudaMemcpyAsync(dMinv.p, Minv.data(), Minv.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    Defl D;
+    D.k = k;
+    D.W = dW.p;
+    D.AW = dAW.p;
+    D.Minv = dMinv.p;
+    D.M = dM.p;
+    D.y = dy.p;
+    D.mu = dmu.p;
+    // r = b - A x ; x += W (WtAW \ W'r)                                              (defcg.jl:270-275)
+    apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
+    kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
+                                                                          c->d_partB.p);
+    c->launches++;
+    defl_project(c, D, D.W, c->d_r.p, nullptr, 0);
+    kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)k * 8, c->stream>>>(n, k, 1.0, D.W, n, D.mu, 1.0, c->d_x.p);
+    c->launches++;
+    int it = 0, fail = 0;
+    pcg_core(c, maxit, rtol, A, precond, &D, kt, &it, &fail);
+    CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+    d2h(c, x, c->d_x.p, n, &T);
+    d2h(c, res_norm, c->d_res.p, it, &T);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *it_out = it;
+    finish_timings(c, kt, T, launches0, tm);
     if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
   });
 }

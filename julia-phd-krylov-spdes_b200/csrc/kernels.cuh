@@ -60,10 +60,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(a), "r"(parity), "r"(0x989680u)
+        : "r"(a), "r"(parity)
         : "memory");
   } while (!ok);
 }
@@ -653,8 +653,10 @@ __global__ void __launch_bounds__(kVecThreads) axpby_kernel(int n, double a, con
   if (g < n) y[g] = (b == 0.0 ? 0.0 : b * y[g]) + a * x[g];
 }
 // out[j] = A[:, j] . x   (one block per column, fixed reduction order)
-__global__ void __launch_bounds__(kVecThreads) gemv_t_kernel(int n, const double* A, int64_t lda, const double* x, double* out) {
+__global__ void __launch_bounds__(kVecThreads) gemv_t_kernel(int n, const double* A, int64_t lda, const double* x, double* out,
+                                                           const int* done_at = nullptr, int iter = 0) {
   __shared__ double red[8];
+  if (done_at != nullptr && *done_at < iter) return;
   const double* col = A + (int64_t)blockIdx.x * lda;
   double s = 0.0;
   for (int g = threadIdx.x; g < n; g += blockDim.x) s = fma(col[g], x[g], s);
@@ -663,8 +665,9 @@ __global__ void __launch_bounds__(kVecThreads) gemv_t_kernel(int n, const double
 }
 // y = b*y + a * A[:, 0:k] * mu
 __global__ void __launch_bounds__(kVecThreads) gemv_n_kernel(int n, int k, double a, const double* A, int64_t lda, const double* mu,
-                                                           double b, double* y) {
+                                                           double b, double* y, const int* done_at = nullptr, int iter = 0) {
   extern __shared__ double smu[];
+  if (done_at != nullptr && *done_at < iter) return;
   for (int j = threadIdx.x; j < k; j += blockDim.x) smu[j] = mu[j];
   __syncthreads();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -678,6 +681,38 @@ __global__ void __launch_bounds__(kVecThreads) gemv_n_kernel(int n, int k, doubl
   if (j < k) s0 = fma(A[g + (int64_t)j * lda], smu[j], s0);
   y[g] = (b == 0.0 ? 0.0 : b * y[g]) + a * (s0 + s1);
 }
+// mu = M^{-1} y for the small deflation system (defcg.jl:301, `WtAW \\ (WtA*z)`): explicit inverse
+// applied with one step of iterative refinement, mu = Minv y; mu += Minv (y - M mu), which recovers
+// the accuracy of a backward-stable solve without any host round trip.  One CTA; matrices k x k,
+// column-major, read coalesced.
+__global__ void __launch_bounds__(1024) small_solve_kernel(int k, const double* Minv, const double* M, const double* y, double* mu,
+                                                           const int* done_at, int iter) {
+  extern __shared__ double sh[];  // y | mu | r
+  if (done_at != nullptr && *done_at < iter) return;
+  double* sy = sh;
+  double* smu = sh + k;
+  double* sr = sh + 2 * k;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) sy[i] = y[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < k; ++j) s = fma(Minv[i + (int64_t)j * k], sy[j], s);
+    smu[i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    double s = sy[i];
+    for (int j = 0; j < k; ++j) s = fma(-M[i + (int64_t)j * k], smu[j], s);
+    sr[i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    double s = smu[i];
+    for (int j = 0; j < k; ++j) s = fma(Minv[i + (int64_t)j * k], sr[j], s);
+    mu[i] = s;
+  }
+}
+
 // C[i, j] = A[:, i] . B[:, j]  (ka x kb, column-major) -- 16x16 output tile per block, rows streamed in
 // 64-row panels through shared memory; fixed summation order.
 __global__ void __launch_bounds__(256) gemm_tn_kernel(int n, int ka, int kb, const double* A, int64_t lda, const double* B,

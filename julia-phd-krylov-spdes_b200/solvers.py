@@ -100,8 +100,15 @@ def _rayleigh_ritz(Tm, nvec):
     return Q @ Z, vals, nev
 
 
-def defpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None, maxit=0):
-    """defcg.jl:242-308."""
+def defpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None, maxit=0, return_timings=False):
+    """defcg.jl:242-308, whole solve inside the library (kb200_defpcg)."""
+    x, it, res, tm = A.h.defpcg(b, x, W, maxit=maxit, rtol=EPS, assembled=A.assembled, precond=M is not None)
+    return (x, it, res, tm) if return_timings else (x, it, res)
+
+
+def defpcg_hostloop(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None, maxit=0):
+    """defcg.jl:242-308 with the loop in the host language over device-resident blocks (the pattern
+    eigpcg / eigdefpcg use); kept as a cross-check of kb200_defpcg."""
     n, nvec = W.shape
     dv = _Dev(A, M)
     h = dv.h

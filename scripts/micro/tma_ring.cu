@@ -57,12 +57,12 @@ int main() {
   uint8_t* g; cudaMalloc(&g, total); cudaMemset(g, 0, total);
   double* out; cudaMalloc(&out, 8);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-  const int ncta = 1024;
+  const int ncta = getenv("NCTA") ? atoi(getenv("NCTA")) : 1024;
   const size_t stride = (total / ncta) & ~(size_t)16383;
   cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct Cfg { int chunk, nst, ncons, smem_pad_kb, touch, cluster; };
-  Cfg cfgs[] = {{8192, 6, 8, 56, 0, 1}, {8192, 6, 8, 56, 0, 4}, {8192, 6, 16, 56, 0, 1}, {8192, 6, 16, 56, 0, 4}, {8192, 6, 16, 56, 1, 4},
-                 {8192, 4, 16, 64, 0, 4}, {8192, 2, 16, 64, 0, 4}, {8192, 6, 4, 56, 0, 4}, {16384, 3, 16, 56, 0, 4}};
+  Cfg cfgs[] = {{16384, 3, 8, 64, 0, 4}, {16384, 6, 8, 64, 0, 4}, {16384, 12, 8, 16, 0, 4}, {16384, 3, 8, 64, 1, 4}, {16384, 12, 8, 16, 1, 4},
+                 {32768, 6, 8, 16, 0, 4}, {8192, 12, 8, 64, 0, 4}};
   for (auto& c : cfgs) {
     const int nchunk = (int)(stride / c.chunk);
     const size_t smem = (size_t)c.chunk * c.nst + (size_t)c.smem_pad_kb * 1024;

@@ -340,3 +340,26 @@ def test_update_realization_values_only():
     inner2 = E.ExactInterior(pr2.blocks.A_II)
     assert rel(y2, E.apply_local_schurs(pr2.blocks, inner2, pr2.sd, x)) <= 1e-12
     assert rel(y1, y2) > 1e-3
+
+
+def test_fused_defpcg_and_pcg_multi():
+    pr, S, M = gpu_ops(65, 16, 4)
+    Aop, Mop, bs = _oracle_callables(pr)
+    n = pr.sd.n_gamma
+    rng = np.random.default_rng(5)
+    W = np.linalg.qr(rng.standard_normal((n, 10)))[0]
+    xo, ito, reso = OS.defpcg(Aop, bs, np.zeros(n), W, Mop)
+    x, it, res, tm = solvers.defpcg(S, bs, np.zeros(n), W, M, return_timings=True)
+    xh, ith, resh = solvers.defpcg_hostloop(S, bs, np.zeros(n), W, M)
+    assert abs(it - ito) <= 1 and abs(ith - ito) <= 1 and tm.kernel_launches > 0
+    k = min(it, ito)
+    # random (non-invariant) W: histories agree to 1e-15 at first and drift with the conditioning
+    assert np.abs(res[:8] - reso[:8]).max() <= 1e-11 * reso[0]
+    assert np.abs(res[:k] - reso[:k]).max() <= 5e-5 * reso[:k].max()
+    assert np.abs(resh[:k] - reso[:k]).max() <= 5e-5 * reso[:k].max()
+    assert np.linalg.norm(x - xo) <= 5e-5 * np.linalg.norm(xo)
+    B = np.column_stack([bs, Aop(rng.standard_normal(n))])
+    X, its, ress = S.h.pcg_multi(B, np.zeros((n, 2)))
+    for j in range(2):
+        xj, itj, _ = solvers.pcg(S, B[:, j].copy(), np.zeros(n), M)
+        assert its[j] == itj and np.array_equal(X[:, j], xj) and ress[j].size == itj
