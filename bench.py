@@ -226,7 +226,7 @@ def main():
         "clocks": clocks,
     }
     if world == 1 and rank == 0:
-        out["cpu_baseline"] = cpu_baseline(args, pr, sd, PiS, b_schur, iters)
+        out["cpu_baseline"], out["parity_at_full_size"] = cpu_baseline(args, pr, sd, PiS, b_schur, iters, S=S, M=M)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -234,7 +234,7 @@ def main():
     return 0
 
 
-def cpu_baseline(args, pr, sd, PiS, b_schur, iters, threads=None):
+def cpu_baseline(args, pr, sd, PiS, b_schur, iters, threads=None, S=None, M=None):
     """The oracle's C port of the same algorithm (exact Cholesky interior solves) timed on this
     box's host cores on a bounded sample: `cpu_sample_iters` PCG iterations, extrapolated to the
     iteration count of the full solve."""
@@ -248,12 +248,20 @@ def cpu_baseline(args, pr, sd, PiS, b_schur, iters, threads=None):
     t0 = time.perf_counter()
     cm.pcg(b_schur, np.zeros(sd.n_gamma), maxit=3, nthreads=1)
     t_one = (time.perf_counter() - t0) / 3
+    parity = None
+    if S is not None:   # outside the timed region: the CUDA operators against the CPU port at the benchmark's own size
+        rng = np.random.default_rng(0)
+        v = rng.standard_normal(sd.n_gamma)
+        ys, yc = S * v, cm.apply_schur(v, nthreads=cores)
+        zs, zc = M.solve(v), cm.apply_nn(v, nthreads=cores)
+        parity = {"apply_schur_max_rel_err": float(np.abs(ys - yc).max() / np.abs(yc).max()),
+                  "apply_nn_max_rel_err": float(np.abs(zs - zc).max() / np.abs(zc).max())}
     return {"value": 1.0 / (t_all * (iters + 1)), "unit": "solves/s", "cores": cores, "kind": "port",
             "sample": f"{k} PCG iterations (+ initial residual) of the same workload with {cores} OpenMP threads over "
                       f"subdomains, {t_all * 1e3:.1f} ms/iteration, extrapolated to {iters} iterations",
             "single_core": {"value": 1.0 / (t_one * (iters + 1)), "ms_per_iteration": t_one * 1e3,
                             "sample": "2 PCG iterations, sequential for-idom loop as in the reference"},
-            "ms_per_iteration": t_all * 1e3}
+            "ms_per_iteration": t_all * 1e3}, parity
 
 
 def run_reference(args, config):
@@ -263,10 +271,10 @@ def run_reference(args, config):
     import oracle.epdd as E  # noqa: F401
     from oracle.cpu_model import CpuModel
     cores = os.cpu_count() or 1
+    config = dict(config, parallelism=f"CPU port of the reference algorithm, {cores} OpenMP threads over subdomains")
     base = PB.build_mesh_and_partition(args.nx, args.ndom)
     sd = base[-1]
     pr = PB.realization(base, ireal=1)
-    pr0 = PB.realization(base, ireal=0, median=True)
     # median preconditioner on the CPU: dense S_d by exact solves would take minutes at 4M DOF, so the
     # sample uses the realization's own dense blocks for a handful of subdomains' worth of time:
     # the per-iteration cost of M is identical whichever S_d the pseudo-inverse came from.

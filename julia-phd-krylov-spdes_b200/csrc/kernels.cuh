@@ -117,7 +117,8 @@ __device__ __forceinline__ void produce_section(StreamCtx& cx, int sec) {
 // streaming): CTA-local barrier, then one thread arrives (release.cluster) on the level mbarrier
 // of every CTA of the cluster, and everybody waits (acquire.cluster) on its own CTA's.
 __device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
-  asm volatile("fence.acq_rel.cluster;" ::: "memory");  // my (remote) stores precede the arrivals below
+  // the remote (DSMEM) stores of all consumer threads are ordered before thread 0's release-arrive by
+  // the CTA barrier (cumulativity of the fence + release below)
   consumer_barrier();
   const uint32_t local = smem_u32(cx.lvl_bar);
   if (cx.warp == 0 && cx.lane == 0) {
