@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrylov_b200.so")
+# KB200_LIB: development override (instrumented builds); the product library sits next to this file
+LIB_PATH = os.environ.get("KB200_LIB") or os.path.join(_HERE, "libkrylov_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 SYMBOLS = [
@@ -335,9 +336,9 @@ class Handle:
         return ptr, dom[:n], loc[:n]
 
     def debug_stamps(self, n_cta):
-        out = np.zeros(n_cta * 16, dtype=np.int64)
+        out = np.zeros(n_cta * 64, dtype=np.int64)
         _chk(lib().kb200_debug_stamps(self.h, _p(out, C.c_int64), C.c_int64(out.size)))
-        return out.reshape(n_cta, 16)
+        return out.reshape(n_cta, 64)
 
     def time_kernel(self, which, reps=10):
         ms = C.c_double()

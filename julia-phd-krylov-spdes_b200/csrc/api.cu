@@ -112,7 +112,9 @@ struct kb200_ctx {
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 3, lane_entries = 0, pad_tol_pct = -1;
+  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 0, lane_entries = 0, pad_tol_pct = -1;
+  int warp_private = -1, private_split = 0;
+  int warps = 0;  // consumer warps per CTA of the stream kernel: 8 or 16 (0: automatic)
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -196,9 +198,20 @@ void finalize(Ctx* c) {
     c->csize = cs;
   }
   opt.csize = c->csize;
+  // consumer warps of the stream kernel: 8 with two CTAs per SM; when the grid leaves every SM with at
+  // most one CTA anyway (few local subdomains: the multi-GPU shards), 16 warps and a deeper ring
+  {
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (c->warps == 0) c->warps = (nloc * c->csize <= sms) ? 16 : kb::kWarps;
+    if (c->stages == 0) c->stages = (c->warps == 16) ? 6 : 3;
+  }
+  opt.warps = c->warps;
   if (c->min_block >= 0) opt.min_block = c->min_block;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
   if (c->pad_tol_pct >= 0) opt.pad_tol = c->pad_tol_pct / 100.0;
+  if (c->warp_private >= 0) opt.warp_private = c->warp_private;
+  if (c->private_split > 0) opt.private_split = c->private_split;
   {
     std::atomic<int64_t> next(0);
     std::string first_err;
@@ -350,10 +363,17 @@ void finalize(Ctx* c) {
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     if (c->csize > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   };
-  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY>);
-  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS>);
-  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB>);
-  set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT>);
+  if (c->warps == kb::kWarps) {
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY, kb::kWarps>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS, kb::kWarps>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, kb::kWarps>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, kb::kWarps>);
+  } else {
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY, 16>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS, 16>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, 16>);
+    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, 16>);
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   // stats
   c->stats[0] = nnzL;
@@ -394,13 +414,16 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   P.dbg = nullptr;
   P.dbg_flags = c->dbg_flags;
   if (c->debug_timing) {
-    if (c->d_dbg.n < (size_t)c->n_cta * 16) c->d_dbg.alloc((size_t)c->n_cta * 16);
+    if (c->d_dbg.n < (size_t)c->n_cta * kb::kDbgSlots) {
+      c->d_dbg.alloc((size_t)c->n_cta * kb::kDbgSlots);
+      CUDA_TRY(cudaMemsetAsync(c->d_dbg.p, 0, (size_t)c->n_cta * kb::kDbgSlots * sizeof(long long), c->stream));
+    }
     P.dbg = c->d_dbg.p;
   }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)c->n_cta, (unsigned)ncols, 1);
-  cfg.blockDim = dim3(kb::kStreamThreads, 1, 1);
+  cfg.blockDim = dim3((unsigned)kb::stream_threads(c->warps), 1, 1);
   cfg.dynamicSmemBytes = (size_t)c->smem_bytes;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[1];
@@ -410,7 +433,8 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE>, P));
+  if (c->warps == kb::kWarps) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps>, P));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16>, P));
   c->launches++;
 }
 
@@ -659,7 +683,7 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       h->debug_timing = value != 0;
     } else if (k == "stages") {
       require(!h->finalized, "stages must be set before the first operation");
-      require(value >= 2 && value <= kb::kMaxStages, "stages must be in [2, 12]");
+      require(value == 0 || (value >= 2 && value <= kb::kMaxStages), "stages must be 0 (automatic) or in [2, 12]");
       h->stages = (int)value;
     } else if (k == "pad_tol_pct") {
       require(!h->finalized && value >= 0 && value <= 100, "pad_tol_pct in [0, 100], before the first operation");
@@ -667,6 +691,15 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "lane_entries") {
       require(!h->finalized && value >= 1 && value <= 256, "lane_entries must be set before the first operation");
       h->lane_entries = (int)value;
+    } else if (k == "warps") {
+      require(!h->finalized && (value == 0 || value == 8 || value == 16), "warps is 0 (automatic), 8 or 16, before the first operation");
+      h->warps = (int)value;
+    } else if (k == "warp_private") {
+      require(!h->finalized && (value == 0 || value == 1), "warp_private is 0 or 1, before the first operation");
+      h->warp_private = (int)value;
+    } else if (k == "private_split") {
+      require(!h->finalized && value >= 1 && value <= 64, "private_split in [1, 64], before the first operation");
+      h->private_split = (int)value;
     } else if (k == "min_block") {
       require(!h->finalized, "min_block must be set before the first operation");
       h->min_block = (int)value;

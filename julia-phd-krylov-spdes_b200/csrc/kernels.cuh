@@ -40,7 +40,15 @@ struct StreamParams {
 };
 
 constexpr int kMaxStages = 12;
-constexpr int kStreamThreads = (kWarps + 1) * 32;  // 8 consumer warps + 1 producer warp
+constexpr int kDbgSlots = 64;  // clock stamps per CTA: 16 phase stamps + 4 counters per consumer warp (KB200_SLICE_PROF)
+#ifdef KB200_SLICE_PROF
+#define KB_PROF(x) x
+#else
+#define KB_PROF(x)
+#endif
+// consumer warps per CTA: kWarps (8; two CTAs per SM) or 16 (one CTA per SM, for grids that leave SMs
+// with a single CTA anyway); one more warp feeds the ring
+constexpr int stream_threads(int nw) { return (nw + 1) * 32; }
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,7 +82,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory"); }
+template <int NW>
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
 
 struct StreamCtx {
   const CtaDesc* D;
@@ -91,6 +100,7 @@ struct StreamCtx {
   uint32_t nst;
   int dbg_flags;
   int warp, lane;
+  KB_PROF(long long t_slice; long long n_slice; long long t_bar; long long t_wait;)
 };
 
 // Producer warp: stream the chunks of one section into the ring.
@@ -114,31 +124,36 @@ __device__ __forceinline__ void produce_section(StreamCtx& cx, int sec) {
 }
 
 // Software barrier over the consumer threads of all CTAs of the cluster (the producer warps keep
-// streaming): CTA-local barrier, then one thread arrives (release.cluster) on the level mbarrier
-// of every CTA of the cluster, and everybody waits (acquire.cluster) on its own CTA's.
+// streaming): CTA-local barrier, then one thread releases at cluster scope (ONE fence: the membar
+// sequence it costs is paid once, not once per peer) and arrives (relaxed) on the level mbarrier of
+// every CTA of the cluster; everybody waits on its own CTA's barrier and acquires with the fence
+// restricted to shared::cluster memory -- the only data exchanged between levels lives in
+// (distributed) shared memory, so no L1 invalidation (CCTL.IVALL) is needed on the polling path.
+template <int NW>
 __device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
-  // the remote (DSMEM) stores of all consumer threads are ordered before thread 0's release-arrive by
-  // the CTA barrier (cumulativity of the fence + release below)
-  consumer_barrier();
+  // the remote (DSMEM) stores of all consumer threads happen before thread 0's release fence through
+  // the CTA barrier (the release pattern is cumulative)
+  consumer_barrier<NW>();
   const uint32_t local = smem_u32(cx.lvl_bar);
   if (cx.warp == 0 && cx.lane == 0) {
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    asm volatile("fence.release.cluster;" ::: "memory");
     for (int c = 0; c < cx.D->csize; ++c) {
       uint32_t remote;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
-      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+      asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
     }
   }
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(local), "r"(cx.lvl_phase)
         : "memory");
   } while (!ok);
+  asm volatile("fence.acquire.sync_restrict::shared::cluster.cluster;" ::: "memory");
   cx.lvl_phase ^= 1u;
 }
 
@@ -200,33 +215,60 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
 // Every warp reads every item header, so all of them execute the same barriers (one per level).
 // TOP sections (kTop): the rows of a level are shared out over the CTAs of the cluster; results are
 // stored into every CTA's replica of the top vector and a cluster-wide barrier separates levels.
-template <bool kTop>
+template <bool kTop, int NW>
 __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
   const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec], nlev = cx.D->sec_nlevels[sec];
   const int lane = cx.lane, warp = cx.warp;
   uint32_t lvl = 0;
   for (uint32_t ch = c0; ch < c1; ++ch) {
     const uint32_t stage = cx.stage;
+    KB_PROF(const long long tw0 = clock64();)
     mbar_wait(&cx.full_bar[stage], cx.phase);
+    KB_PROF(cx.t_wait += clock64() - tw0;)
     const uint8_t* chunk = cx.ring + stage * kChunkBytes;
     uint32_t off = 0;
+    uint4 hq = *reinterpret_cast<const uint4*>(chunk);
     while (off < (uint32_t)kChunkBytes) {
-      const uint4 hq = *reinterpret_cast<const uint4*>(chunk + off);
       const uint32_t bytes = hq.x;
       if (bytes == 0) break;
       const uint32_t count = hq.y >> 16, first = hq.z;
+      const uint32_t item_type = hq.y & 0xffu, item_level = hq.w;
+      // the next item header is fetched now, so its latency hides behind this item's slices
+      if (off + bytes < (uint32_t)kChunkBytes) hq = *reinterpret_cast<const uint4*>(chunk + off + bytes);
       if (kTop) {
-        while (lvl < hq.w) {
-          cluster_level_sync(cx);
+        while (lvl < item_level) {
+          cluster_level_sync<NW>(cx);
           ++lvl;
         }
       } else if (first == 0 && !(cx.dbg_flags & 2)) {
-        consumer_barrier();  // a new level starts: the previous one is complete
+        KB_PROF(const long long tb0 = clock64();)
+        consumer_barrier<NW>();  // a new level starts: the previous one is complete
+        KB_PROF(cx.t_bar += clock64() - tb0;)
       }
-      if (!(cx.dbg_flags & 1)) {
+      if (!kTop && item_type == kItemPrivate) {
+        // private item: this warp walks its own slices (rows of its subtrees, level by level); the
+        // lanes of the warp are the only readers / writers of these rows, __syncwarp() orders them
+        if (!(cx.dbg_flags & 1)) {
+          const uint16_t* wb = reinterpret_cast<const uint16_t*>(chunk + off + 16);
+          const uint16_t* offs = reinterpret_cast<const uint16_t*>(chunk + off + 16 + kPrivDirBytes);
+          // (the plan shares private rows out over kWarps warps; further consumer warps have none)
+          const uint32_t s1 = warp < kWarps ? wb[warp + 1] : 0u;
+          for (uint32_t i = warp < kWarps ? wb[warp] : 0u; i < s1; ++i) {
+            KB_PROF(const long long ts0 = clock64();)
+            process_slice<false>(cx, chunk + off + (uint32_t)offs[i] * 16u, sign);
+            __syncwarp();
+            KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
+          }
+        }
+      } else if (!(cx.dbg_flags & 1)) {
         const uint16_t* offs = reinterpret_cast<const uint16_t*>(chunk + off + 16);
-        for (uint32_t i = (uint32_t)(warp - (int)(first & (kWarps - 1))) & (kWarps - 1); i < count; i += kWarps)
-          process_slice<kTop>(cx, chunk + off + (uint32_t)offs[i] * 16u, sign);
+        for (uint32_t i = (uint32_t)(warp - (int)(first & (NW - 1))) & (NW - 1); i < count; i += NW) {
+          const uint32_t so = offs[i];
+          if (so == 0) continue;  // empty slot
+          KB_PROF(const long long ts0 = clock64();)
+          process_slice<kTop>(cx, chunk + off + so * 16u, sign);
+          KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
+        }
       }
       off += bytes;
     }
@@ -239,16 +281,16 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
   }
   if (kTop) {
     while (lvl < nlev) {
-      cluster_level_sync(cx);
+      cluster_level_sync<NW>(cx);
       ++lvl;
     }
   } else if (!(cx.dbg_flags & 2)) {
-    consumer_barrier();  // the section's last level is complete
+    consumer_barrier<NW>();  // the section's last level is complete
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const StreamParams P) {
+template <int MODE, int NW>
+__global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schur_stream_kernel(const StreamParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ CtaDesc D;
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -267,7 +309,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
   if (tid == 0) {
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kWarps);
+      mbar_init(&empty_bar[s], NW);
     }
     mbar_init(&lvl_bar, (uint32_t)P.ctas[blockIdx.x].csize);
     mbar_fence_init();
@@ -313,8 +355,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
   cx.dbg_flags = P.dbg_flags;
   cx.warp = warp;
   cx.lane = lane;
-  const bool producer = warp == kWarps;
-  auto stamp = [&](int i) { if (P.dbg != nullptr && tid == 0) P.dbg[(size_t)blockIdx.x * 16 + i] = clock64(); };
+  KB_PROF(cx.t_slice = 0; cx.n_slice = 0; cx.t_bar = 0; cx.t_wait = 0;)
+  const bool producer = warp == NW;
+  auto stamp = [&](int i) { if (P.dbg != nullptr && tid == 0) P.dbg[(size_t)blockIdx.x * kDbgSlots + i] = clock64(); };
   stamp(0);
   constexpr bool kHasInit = MODE == MODE_APPLY || MODE == MODE_UNIT || MODE == MODE_BACKSUB;
   constexpr double kInitSign = (MODE == MODE_BACKSUB) ? 1.0 : -1.0;
@@ -327,11 +370,11 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
     produce_section(cx, SEC_FWD);
     if (C > 1) produce_section(cx, SEC_PART);
   } else {
-    if (kHasInit) consume_section<false>(cx, SEC_INIT, kInitSign);
+    if (kHasInit) consume_section<false, NW>(cx, SEC_INIT, kInitSign);
     stamp(9);
-    consume_section<false>(cx, SEC_FWD, 1.0);
+    consume_section<false, NW>(cx, SEC_FWD, 1.0);
     stamp(10);
-    if (C > 1) consume_section<false>(cx, SEC_PART, 1.0);
+    if (C > 1) consume_section<false, NW>(cx, SEC_PART, 1.0);
   }
   stamp(1);
   // ---- phase 2: top nodes, shared out over the cluster ----------------------------------------------
@@ -347,7 +390,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
       // the top vector once all CTAs have finished reading (two cluster-wide barriers per pass)
       const double* r0 = cluster.map_shared_rank(S, 0);
       for (int base = 0; base < D.n_top; base += kMaxSlots) {
-        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += kWarps * 32) {
+        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += NW * 32) {
           double a = r0[D.top_off + i];
           for (int c = 0; c < C; ++c) {
             const double* rs = cluster.map_shared_rank(S, c);
@@ -355,13 +398,13 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
           }
           scratch[i - base] = a;
         }
-        cluster_level_sync(cx);
-        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += kWarps * 32) S[D.top_off + i] = scratch[i - base];
-        cluster_level_sync(cx);
+        cluster_level_sync<NW>(cx);
+        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += NW * 32) S[D.top_off + i] = scratch[i - base];
+        cluster_level_sync<NW>(cx);
       }
-      consume_section<true>(cx, SEC_TOPF, 1.0);
+      consume_section<true, NW>(cx, SEC_TOPF, 1.0);
       stamp(3);
-      consume_section<true>(cx, SEC_TOPB, 1.0);
+      consume_section<true, NW>(cx, SEC_TOPB, 1.0);
     }
     stamp(4);
     stamp(5);
@@ -372,13 +415,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) schur_stream_kernel(const S
     if (kHasGG && rank == 0) produce_section(cx, SEC_GG);
     if (kHasOut) produce_section(cx, SEC_OUT);
   } else {
-    consume_section<false>(cx, SEC_BWD, 1.0);
+    consume_section<false, NW>(cx, SEC_BWD, 1.0);
     stamp(6);
-    if (kHasGG && rank == 0) consume_section<false>(cx, SEC_GG, -1.0);
-    if (kHasOut) consume_section<false>(cx, SEC_OUT, 1.0);
+    if (kHasGG && rank == 0) consume_section<false, NW>(cx, SEC_GG, -1.0);
+    if (kHasOut) consume_section<false, NW>(cx, SEC_OUT, 1.0);
   }
   __syncthreads();
   stamp(7);
+  KB_PROF(if (P.dbg != nullptr && lane == 0 && warp < 8) {
+    long long* o = P.dbg + (size_t)blockIdx.x * kDbgSlots + 16 + warp * 4;
+    o[0] = cx.t_slice; o[1] = cx.n_slice; o[2] = cx.t_bar; o[3] = cx.t_wait;
+  })
   if (MODE == MODE_BACKSUB) {
     double* u = P.uI + D.I_base;
     const int32_t* om = P.imap + D.ownmap_off;

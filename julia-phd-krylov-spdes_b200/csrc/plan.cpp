@@ -16,6 +16,7 @@ struct TmpRow {
   int32_t level;
   int32_t kind;  // 0: S[dst] = (S[dst] - sign*acc)/diag ; 1: S[dst] = -sign*acc/diag
   int32_t bcast; // result is replicated into every CTA of the cluster (top nodes)
+  int32_t warp;  // consumer warp that owns the row (private phase), -1: rows of a CTA-wide level
   uint32_t ebeg;  // into the builder's scratch entry arrays
   uint32_t len;
 };
@@ -51,32 +52,124 @@ struct CtaStream {
   }
 };
 
-// Serialise the rows of one section as levels of slices (see plan.h).
+// Serialise one slice (rows ord[p..q) of `rows`, T lanes per row) -- layout in plan.h.
+std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const std::vector<uint32_t>& ord,
+                                size_t p, size_t q, int T, CtaStream& cs) {
+  const int nr = (int)(q - p);
+  const uint32_t maxlen = rows[ord[p]].len;
+  const uint32_t kmax = (maxlen + T - 1) / T;
+  // entries in execution order: step k, the nr*T active lanes ascending; lanes whose row has
+  // run out get a zero entry (rows of a slice have similar lengths, so this padding is small)
+  std::vector<double> pv;
+  std::vector<uint16_t> pc;
+  int64_t real = 0;
+  for (uint32_t k = 0; k < kmax; ++k)
+    for (int lane = 0; lane < nr * T; ++lane) {
+      const int g = lane / T, t = lane % T;
+      const TmpRow& tr = rows[ord[p + g]];
+      const uint32_t idx = k * T + t;
+      if (idx < tr.len) {
+        pv.push_back(sc.vals[tr.ebeg + idx]);
+        pc.push_back(sc.cols[tr.ebeg + idx]);
+        ++real;
+      } else {
+        pv.push_back(0.0);
+        pc.push_back(0);
+      }
+    }
+  if (pv.size() > 65535u || kmax > 65535u) throw std::runtime_error("internal: slice too large");
+  std::vector<uint8_t> b;
+  auto put = [&](const void* ptr, size_t nb) {
+    const uint8_t* u = static_cast<const uint8_t*>(ptr);
+    b.insert(b.end(), u, u + nb);
+  };
+  SliceHdr sh;
+  std::memset(&sh, 0, sizeof(sh));
+  sh.nent = (uint16_t)pv.size();
+  sh.kmax = (uint16_t)kmax;
+  sh.tlog2 = (uint8_t)ilog2(T);
+  sh.nrows = (uint8_t)nr;
+  put(&sh, sizeof(sh));
+  for (int g = 0; g < nr; ++g) {
+    const TmpRow& tr = rows[ord[p + g]];
+    RowRec rr;
+    std::memset(&rr, 0, sizeof(rr));
+    rr.len = (uint16_t)tr.len;
+    rr.dst = tr.dst;
+    rr.flags = (uint16_t)((tr.kind ? kRowFresh : 0) | (tr.bcast ? kRowBcast : 0));
+    rr.diag = 1.0 / tr.diag;  // the device multiplies by the reciprocal
+    put(&rr, sizeof(rr));
+  }
+  if (!pv.empty()) {
+    put(pv.data(), pv.size() * 8);
+    put(pc.data(), pc.size() * 2);
+  }
+  while (b.size() % 16) b.push_back(0);
+  if (b.size() + sizeof(ItemHdr) + kPrivDirBytes + 16 > (size_t)kChunkBytes)
+    throw std::runtime_error("internal: slice exceeds a chunk");
+  cs.n_entries += real;
+  cs.n_rows += nr;
+  cs.n_packets += 1;
+  cs.lane_steps += 32 * (int64_t)kmax;
+  return b;
+}
+
+// Serialise the rows of one section (see plan.h): the rows without a warp (`warp` < 0) as levels of
+// slices shared out over the consumer warps, the warp-private rows as private items, before
+// (private_first, forward sweep) or after (backward sweep) the shared levels.
 void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptions& opt, CtaStream& cs,
-                  uint32_t& chunk0, uint32_t& chunk1, uint32_t& nlevels, int force_levels = -1) {
+                  uint32_t& chunk0, uint32_t& chunk1, uint32_t& nlevels, int force_levels = -1,
+                  bool private_first = true, int64_t* n_private_rows = nullptr, int64_t* n_private_slices = nullptr) {
   cs.pad_to_chunk();
   chunk0 = (uint32_t)(cs.bytes.size() / kChunkBytes);
   int maxlev = -1;
+  bool any_private = false;
   for (auto& r : rows) {
     if (r.level < 0) throw std::runtime_error("internal: negative level");
-    maxlev = std::max(maxlev, r.level);
+    if (r.warp >= 0) any_private = true;
+    else maxlev = std::max(maxlev, r.level);
   }
   nlevels = (uint32_t)(maxlev + 1);
   if (force_levels >= 0) {
     if (force_levels < maxlev + 1) throw std::runtime_error("internal: forced level count too small");
+    if (any_private) throw std::runtime_error("internal: private rows in a section with forced levels");
     nlevels = (uint32_t)force_levels;
   }
-  if (!rows.empty()) {
-    auto t_of = [&](uint32_t len) {
-      const int want = (int)((len + opt.lane_entries - 1) / std::max(1, opt.lane_entries));
-      return std::min(32, pow2ceil(std::max(1, want)));
-    };
-    std::vector<uint32_t> ord(rows.size());
-    std::iota(ord.begin(), ord.end(), 0u);
+  auto t_of = [&](uint32_t len) {
+    const int want = (int)((len + opt.lane_entries - 1) / std::max(1, opt.lane_entries));
+    return std::min(32, pow2ceil(std::max(1, want)));
+  };
+  // slices of the rows ord[i..j) (one level, sorted by decreasing length)
+  auto level_slices = [&](const std::vector<uint32_t>& ord, size_t i, size_t j, std::vector<std::vector<uint8_t>>& slices) {
+    size_t p = i;
+    while (p < j) {
+      const int T = t_of(rows[ord[p]].len);
+      const int cap = 32 / T;
+      size_t q = p;
+      // rows of a slice are padded to its longest row: stop when the next row is too much shorter
+      const uint32_t len0 = rows[ord[p]].len;
+      const uint32_t min_len = (uint32_t)(opt.pad_tol * (double)len0);
+      while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T &&
+             (rows[ord[q]].len >= min_len || len0 - rows[ord[q]].len <= 1))
+        ++q;
+      slices.push_back(make_slice(rows, sc, ord, p, q, T, cs));
+      p = q;
+    }
+  };
+  auto sorted_order = [&](auto keep) {
+    std::vector<uint32_t> ord;
+    for (uint32_t k = 0; k < rows.size(); ++k)
+      if (keep(rows[k])) ord.push_back(k);
     std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
       if (rows[a].level != rows[b].level) return rows[a].level < rows[b].level;
       return rows[a].len > rows[b].len;
     });
+    return ord;
+  };
+
+  const int NW = (opt.warps == 16) ? 16 : kWarps;
+  auto emit_shared = [&]() {
+    const std::vector<uint32_t> ord = sorted_order([](const TmpRow& r) { return r.warp < 0; });
     std::vector<std::vector<uint8_t>> slices;  // serialised slices of the current level
     size_t i = 0;
     while (i < ord.size()) {
@@ -84,74 +177,36 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
       const int lev = rows[ord[i]].level;
       while (j < ord.size() && rows[ord[j]].level == lev) ++j;
       slices.clear();
-      size_t p = i;
-      while (p < j) {
-        const int T = t_of(rows[ord[p]].len);
-        const int cap = 32 / T;
-        size_t q = p;
-        // rows of a slice are padded to its longest row: stop when the next row is too much shorter
-        const uint32_t len0 = rows[ord[p]].len;
-        const uint32_t min_len = (uint32_t)(opt.pad_tol * (double)len0);
-        while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T &&
-               (rows[ord[q]].len >= min_len || len0 - rows[ord[q]].len <= 1))
-          ++q;
-        const int nr = (int)(q - p);
-        const uint32_t maxlen = rows[ord[p]].len;
-        const uint32_t kmax = (maxlen + T - 1) / T;
-        // entries in execution order: step k, the nr*T active lanes ascending; lanes whose row has
-        // run out get a zero entry (rows of a slice have similar lengths, so this padding is small)
-        std::vector<double> pv;
-        std::vector<uint16_t> pc;
-        int64_t real = 0;
-        for (uint32_t k = 0; k < kmax; ++k)
-          for (int lane = 0; lane < nr * T; ++lane) {
-            const int g = lane / T, t = lane % T;
-            const TmpRow& tr = rows[ord[p + g]];
-            const uint32_t idx = k * T + t;
-            if (idx < tr.len) {
-              pv.push_back(sc.vals[tr.ebeg + idx]);
-              pc.push_back(sc.cols[tr.ebeg + idx]);
-              ++real;
-            } else {
-              pv.push_back(0.0);
-              pc.push_back(0);
-            }
-          }
-        if (pv.size() > 65535u || kmax > 65535u) throw std::runtime_error("internal: slice too large");
-        std::vector<uint8_t> b;
-        auto put = [&](const void* ptr, size_t nb) {
-          const uint8_t* u = static_cast<const uint8_t*>(ptr);
-          b.insert(b.end(), u, u + nb);
+      level_slices(ord, i, j, slices);
+      // Slot k of the level's sequence is executed by consumer warp k % NW.  Balance the warps
+      // (longest-processing-time first on an estimate of the slice latency) and lay the slices out
+      // round by round; a warp with fewer slices leaves empty slots (offset 0 in the directory).
+      if ((int)slices.size() > NW) {
+        auto cost = [](const std::vector<uint8_t>& b) {
+          SliceHdr sh;
+          std::memcpy(&sh, b.data(), sizeof(sh));
+          return 400 + 30 * (int)sh.kmax + 40 * (int)sh.tlog2;
         };
-        SliceHdr sh;
-        std::memset(&sh, 0, sizeof(sh));
-        sh.nent = (uint16_t)pv.size();
-        sh.kmax = (uint16_t)kmax;
-        sh.tlog2 = (uint8_t)ilog2(T);
-        sh.nrows = (uint8_t)nr;
-        put(&sh, sizeof(sh));
-        for (int g = 0; g < nr; ++g) {
-          const TmpRow& tr = rows[ord[p + g]];
-          RowRec rr;
-          std::memset(&rr, 0, sizeof(rr));
-          rr.len = (uint16_t)tr.len;
-          rr.dst = tr.dst;
-          rr.flags = (uint16_t)((tr.kind ? kRowFresh : 0) | (tr.bcast ? kRowBcast : 0));
-          rr.diag = 1.0 / tr.diag;  // the device multiplies by the reciprocal
-          put(&rr, sizeof(rr));
+        std::vector<size_t> so(slices.size());
+        std::iota(so.begin(), so.end(), (size_t)0);
+        std::stable_sort(so.begin(), so.end(), [&](size_t a, size_t b) { return cost(slices[a]) > cost(slices[b]); });
+        std::vector<std::vector<size_t>> per_warp(NW);
+        std::vector<int64_t> load(NW, 0);
+        for (size_t k : so) {
+          int best = 0;
+          for (int w = 1; w < NW; ++w)
+            if (load[w] < load[best]) best = w;
+          load[best] += cost(slices[k]);
+          per_warp[best].push_back(k);
         }
-        if (!pv.empty()) {
-          put(pv.data(), pv.size() * 8);
-          put(pc.data(), pc.size() * 2);
-        }
-        while (b.size() % 16) b.push_back(0);
-        if (b.size() + sizeof(ItemHdr) + 16 > (size_t)kChunkBytes) throw std::runtime_error("internal: slice exceeds a chunk");
-        slices.push_back(std::move(b));
-        cs.n_entries += real;
-        cs.n_rows += nr;
-        cs.n_packets += 1;
-        cs.lane_steps += 32 * (int64_t)kmax;
-        p = q;
+        size_t rounds = 0;
+        for (auto& v : per_warp) rounds = std::max(rounds, v.size());
+        std::vector<std::vector<uint8_t>> seq;
+        for (size_t r = 0; r < rounds; ++r)
+          for (int w = 0; w < NW; ++w)
+            seq.push_back(r < per_warp[w].size() ? std::move(slices[per_warp[w][r]]) : std::vector<uint8_t>());
+        while (!seq.empty() && seq.back().empty()) seq.pop_back();
+        slices.swap(seq);
       }
       // pack the level's slices into items
       size_t s0 = 0;
@@ -179,7 +234,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
         size_t offb = sizeof(ItemHdr) + (((s1 - s0) * 2 + 15) / 16) * 16;
         std::vector<uint16_t> offs;
         for (size_t k = s0; k < s1; ++k) {
-          offs.push_back((uint16_t)(offb / 16));
+          offs.push_back(slices[k].empty() ? (uint16_t)0 : (uint16_t)(offb / 16));  // 0: empty slot
           offb += slices[k].size();
         }
         while ((offs.size() * 2) % 16) offs.push_back(0);
@@ -189,7 +244,104 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
       }
       i = j;
     }
-  }
+  };
+
+  auto emit_private = [&](bool barrier_before) {
+    // per warp: the slices of its rows in level order
+    std::vector<std::vector<std::vector<uint8_t>>> ws(kWarps);
+    std::vector<size_t> tot(kWarps, 0), nxt(kWarps, 0), rem(kWarps, 0);
+    for (int w = 0; w < kWarps; ++w) {
+      const std::vector<uint32_t> ord = sorted_order([w](const TmpRow& r) { return r.warp == w; });
+      size_t i = 0;
+      while (i < ord.size()) {
+        size_t j = i;
+        while (j < ord.size() && rows[ord[j]].level == rows[ord[i]].level) ++j;
+        level_slices(ord, i, j, ws[w]);
+        i = j;
+      }
+      for (auto& b : ws[w]) tot[w] += b.size();
+      rem[w] = tot[w];
+      if (n_private_rows) *n_private_rows += (int64_t)ord.size();
+      if (n_private_slices) *n_private_slices += (int64_t)ws[w].size();
+    }
+    bool first_item = true;
+    for (;;) {
+      bool left = false;
+      for (int w = 0; w < kWarps; ++w) left = left || nxt[w] < ws[w].size();
+      if (!left) break;
+      // every item takes from each warp a share proportional to what the warp has left, so that the
+      // warps advance through the chunks at the same pace: always extend the warp that lags most
+      const size_t room = cs.room();
+      std::vector<size_t> take(kWarps, 0);
+      size_t nsl = 0, payload = 0;
+      auto bytes_with = [&](size_t n_slices, size_t pay) {
+        return sizeof(ItemHdr) + (size_t)kPrivDirBytes + ((n_slices * 2 + 15) / 16) * 16 + pay;
+      };
+      std::vector<size_t> r2 = rem;
+      for (;;) {
+        int best = -1;
+        double bf = -1.0;
+        for (int w = 0; w < kWarps; ++w) {
+          const size_t k = nxt[w] + take[w];
+          if (k >= ws[w].size()) continue;
+          const double f = (double)r2[w] / (double)tot[w];
+          if (f > bf) {
+            bf = f;
+            best = w;
+          }
+        }
+        if (best < 0) break;
+        const size_t sz = ws[best][nxt[best] + take[best]].size();
+        if (bytes_with(nsl + 1, payload + sz) > room) break;
+        take[best]++;
+        nsl++;
+        payload += sz;
+        r2[best] -= sz;
+      }
+      if (nsl == 0) {
+        cs.pad_to_chunk();
+        continue;
+      }
+      ItemHdr ih;
+      std::memset(&ih, 0, sizeof(ih));
+      ih.bytes = (uint32_t)bytes_with(nsl, payload);
+      ih.type = kItemPrivate;
+      ih.count = (uint16_t)nsl;
+      ih.first = (first_item && barrier_before) ? 0u : 1u;
+      ih.level = 0;
+      cs.put(ih);
+      std::vector<uint16_t> dir(kPrivDirBytes / 2, 0);
+      size_t acc = 0;
+      for (int w = 0; w < kWarps; ++w) {
+        dir[w] = (uint16_t)acc;
+        acc += take[w];
+      }
+      dir[kWarps] = (uint16_t)acc;
+      for (uint16_t v : dir) cs.put(v);
+      size_t offb = sizeof(ItemHdr) + kPrivDirBytes + ((nsl * 2 + 15) / 16) * 16;
+      std::vector<uint16_t> offs;
+      for (int w = 0; w < kWarps; ++w)
+        for (size_t k = 0; k < take[w]; ++k) {
+          offs.push_back((uint16_t)(offb / 16));
+          offb += ws[w][nxt[w] + k].size();
+        }
+      while ((offs.size() * 2) % 16) offs.push_back(0);
+      for (uint16_t o : offs) cs.put(o);
+      for (int w = 0; w < kWarps; ++w) {
+        for (size_t k = 0; k < take[w]; ++k) {
+          const auto& b = ws[w][nxt[w] + k];
+          cs.bytes.insert(cs.bytes.end(), b.begin(), b.end());
+        }
+        nxt[w] += take[w];
+      }
+      rem = r2;
+      first_item = false;
+    }
+  };
+
+  if (any_private && private_first) emit_private(false);
+  emit_shared();
+  if (any_private && !private_first) emit_private(true);
   cs.pad_to_chunk();
   chunk1 = (uint32_t)(cs.bytes.size() / kChunkBytes);
 }
@@ -324,6 +476,56 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     else owner[j] = owner[parent[j]];
   }
 
+  // ---- warp-private subtrees: the bottom of every CTA's own forest, cut into subtrees that are
+  // bin-packed onto the consumer warps (wown = warp, or -1 for the "upper" own nodes and the top) ----
+  std::vector<int32_t> wown(n, -1);
+  if (opt.warp_private && n > 0) {
+    std::vector<char> upper(n, 0);
+    std::vector<int32_t> wroot(n, -1);
+    for (int c = 0; c < C; ++c) {
+      std::vector<int32_t> Qw;
+      int64_t total = 0;
+      for (int j = 0; j < n; ++j)
+        if (owner[j] == c && (parent[j] < 0 || owner[parent[j]] != c)) {
+          Qw.push_back(j);
+          total += sub[j];
+        }
+      if (Qw.empty()) continue;
+      const int64_t target = std::max<int64_t>(total / ((int64_t)kWarps * std::max(1, opt.private_split)), 64);
+      for (;;) {
+        size_t hi = 0;
+        for (size_t k = 1; k < Qw.size(); ++k)
+          if (sub[Qw[k]] > sub[Qw[hi]] || (sub[Qw[k]] == sub[Qw[hi]] && Qw[k] < Qw[hi])) hi = k;
+        const int r = Qw[hi];
+        if (sub[r] <= target || cptr[r + 1] == cptr[r]) break;
+        Qw[hi] = Qw.back();
+        Qw.pop_back();
+        upper[r] = 1;
+        for (int p = cptr[r]; p < cptr[r + 1]; ++p) Qw.push_back(child[p]);
+        if (Qw.empty()) break;
+      }
+      // longest-processing-time assignment of the subtrees to the warps
+      std::sort(Qw.begin(), Qw.end(), [&](int a, int b) {
+        if (sub[a] != sub[b]) return sub[a] > sub[b];
+        return a < b;
+      });
+      std::vector<int64_t> load(kWarps, 0);
+      for (int r : Qw) {
+        if (upper[r]) continue;
+        int best = 0;
+        for (int w = 1; w < kWarps; ++w)
+          if (load[w] < load[best]) best = w;
+        load[best] += sub[r];
+        wroot[r] = best;
+      }
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      if (owner[j] < 0 || upper[j]) wown[j] = -1;
+      else if (wroot[j] >= 0) wown[j] = wroot[j];
+      else wown[j] = wown[parent[j]];
+    }
+  }
+
   // ---- supernode chains with dense diagonal blocks -> inverted blocks ---------------------------
   // A chain a..b of the elimination tree with parent[j] = j+1 and nested column structures has a
   // dense lower-triangular diagonal block D; with Dinv = D^{-1} precomputed, the b-a+1 dependent
@@ -337,7 +539,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     int a = 0;
     while (a < n) {
       int b = a;
-      while (b + 1 < n && parent[b] == b + 1 && ccount(b) == ccount(b + 1) + 1 && owner[b] == owner[b + 1] &&
+      while (b + 1 < n && parent[b] == b + 1 && ccount(b) == ccount(b + 1) + 1 && owner[b] == owner[b + 1] && wown[b] == wown[b + 1] &&
              (b + 1 - a + 1) <= opt.max_block)
         ++b;
       const int sz = b - a + 1;
@@ -386,7 +588,11 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         if (same_scope(r, j)) {
           if (owner[r] >= 0 && owner[j] != owner[r])
             throw std::runtime_error("internal: row dependency crosses subtrees");
-          l = std::max(l, fe[j] + 1);
+          if (wown[r] >= 0 && wown[j] != wown[r])
+            throw std::runtime_error("internal: private row depends on another warp's subtree");
+          // the private phase of the forward sweep is complete before the first upper level
+          if (wown[r] < 0 && wown[j] >= 0) l = std::max(l, 0);
+          else l = std::max(l, fe[j] + 1);
         } else if (owner[r] >= 0) {
           throw std::runtime_error("internal: subtree row depends on a top node");
         }
@@ -406,7 +612,12 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
           if (owner[k] >= 0) throw std::runtime_error("internal: ancestor of a top node is not top");
           l = std::max(l, be[k] + 1);
         } else if (owner[k] >= 0) {
-          l = std::max(l, be[k] + 1);
+          if (wown[r] < 0 && wown[k] >= 0) throw std::runtime_error("internal: ancestor of an upper node is private");
+          if (wown[r] >= 0 && wown[k] >= 0 && wown[k] != wown[r])
+            throw std::runtime_error("internal: private row depends on another warp's subtree");
+          // the upper levels of the backward sweep are complete before the private phase
+          if (wown[r] >= 0 && wown[k] < 0) l = std::max(l, 0);
+          else l = std::max(l, be[k] + 1);
         }
       }
     if (blk[i] >= 0) l += 1;
@@ -504,8 +715,10 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   out.ctas.resize(C);
   Scratch sc;
   std::vector<TmpRow> rows;
+  int cur_warp = -1;  // warp of the rows being emitted (-1: CTA-wide levels)
   auto begin_row = [&](uint16_t dst, double dg, int level, int kind) {
     TmpRow r;
+    r.warp = cur_warp;
     r.dst = dst;
     r.diag = dg;
     r.level = level;
@@ -537,8 +750,9 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     D.own_off = own_off;
     D.smem_doubles = own_off + max_own;
     D.top_sz = top_sz;
-    auto section = [&](int s, int force_levels = -1) {
-      emit_section(rows, sc, opt, cs, D.sec_chunk0[s], D.sec_chunk1[s], D.sec_nlevels[s], force_levels);
+    auto section = [&](int s, int force_levels = -1, bool private_first = true) {
+      emit_section(rows, sc, opt, cs, D.sec_chunk0[s], D.sec_chunk1[s], D.sec_nlevels[s], force_levels, private_first,
+                   &out.n_private_rows, &out.n_private_slices);
       rows.clear();
       sc.cols.clear();
       sc.vals.clear();
@@ -556,6 +770,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     auto emit_forward = [&](auto sel) {
       for (int i = 0; i < n; ++i) {
         if (!sel(i)) continue;
+        cur_warp = wown[i];
         if (blk[i] < 0) {
           begin_row(sidx(i), diag[i], fe[i], 0);
           for (int p = rptr[i]; p < rptr[i + 1]; ++p)
@@ -580,6 +795,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     auto emit_backward = [&](auto sel) {
       for (int i = 0; i < n; ++i) {
         if (!sel(i)) continue;
+        cur_warp = wown[i];
         if (blk[i] < 0) {
           begin_row(sidx(i), diag[i], be[i], 0);
           for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) push(sidx(L.rowval[p]), L.nzval[p]);
@@ -602,7 +818,8 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     };
     // SEC_FWD
     emit_forward([&](int i) { return owner[i] == c; });
-    section(SEC_FWD);
+    cur_warp = -1;
+    section(SEC_FWD, -1, true);
     // SEC_PART
     for (int i = 0; i < n; ++i)
       if (owner[i] < 0) {
@@ -664,7 +881,8 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     section(SEC_TOPB, top_levels);
     // SEC_BWD
     emit_backward([&](int i) { return owner[i] == c; });
-    section(SEC_BWD);
+    cur_warp = -1;
+    section(SEC_BWD, -1, false);
     // SEC_GG (rank 0)
     if (c == 0)
       for (int l = 0; l < ng; ++l)

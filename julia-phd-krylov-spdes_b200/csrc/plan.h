@@ -54,8 +54,19 @@ enum Section : int {
 //
 // Item:  [ItemHdr 16 B][count x uint16 slice offsets (16-byte units from the item start), padded to 16 B][slices]
 // Slice: [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][nent x uint16]  (+ padding to 16 B)
-// Slice i of the item is executed by consumer warp (first + i) % kWarps.
-constexpr uint8_t kItemSlices = 1;
+// Slot i of the item is executed by consumer warp (first + i) % NW (NW = BuildOptions::warps); a slot
+// with offset 0 is empty (the plan balances the warps of a level, see emit_section).
+//
+// PRIVATE items (kItemPrivate) carry the bottom of the elimination forest: the CTA's own nodes are cut
+// once more into small subtrees that are bin-packed onto the consumer WARPS; a warp walks the rows of
+// its subtrees level by level with only __syncwarp() between its slices, so the many thin levels near
+// the leaves cost no CTA barrier.  Forward sweep: private items first, then the levels of the remaining
+// ("upper") own nodes; backward sweep: upper levels first, then the private items.
+// Private item: [ItemHdr 16 B][(kWarps+1) x uint16 first slice of every warp, padded to 32 B]
+//               [count x uint16 slice offsets, padded to 16 B][slices grouped by warp]
+// `first` == 0 asks for a CTA barrier before the item (values of the upper levels must be complete).
+constexpr uint8_t kItemSlices = 1, kItemPrivate = 2;
+constexpr int kPrivDirBytes = 32;  // bytes reserved for the per-warp slice ranges of a private item
 constexpr int kMaxSlots = 1024;    // scratch doubles used when the top right-hand side is combined
 struct alignas(16) ItemHdr {
   uint32_t bytes;   // size of the item incl. this header, 0 = end of chunk
@@ -125,6 +136,7 @@ struct DomainPlan {
   int64_t n_entries = 0, n_rows = 0, n_packets = 0;   // n_packets = slices
   int64_t lane_steps = 0;                             // sum over slices of 32 * kmax (lane utilisation = n_entries / lane_steps)
   int32_t n_top = 0, max_levels = 0;
+  int64_t n_private_rows = 0, n_private_slices = 0;   // rows / slices handled warp-privately
   int64_t max_cta_entries = 0, top_entries = 0;
 };
 
@@ -135,6 +147,9 @@ struct BuildOptions {
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;
   int max_smem_doubles = 28000;
+  int warps = kWarps;         // consumer warps of the kernel that will run the plan (8 or 16): slot k of a level -> warp k % warps
+  int warp_private = 0;       // 1: subtrees near the leaves are processed warp-privately (no CTA barriers)
+  int private_split = 2;      // aim at about private_split x kWarps private subtrees per CTA
 };
 
 // Throws std::runtime_error on malformed input (missing diagonal, not lower triangular, ...).

@@ -10,7 +10,7 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 2001
 ndom = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 csizes = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [4]
 do_pcg = len(sys.argv) > 4 and sys.argv[4] == 'pcg'
-stages = [int(v) for v in os.environ.get('STAGES', '3').split(',')]
+stages = [int(v) for v in os.environ.get('STAGES', '0').split(',')]
 extra = [dict(kv.split('=') for kv in cfg.split('+')) for cfg in os.environ.get('OPTS', '').split(',') if cfg] or [{}]
 t = time.time(); pr = PB.build_problem(nx, ndom, ireal=1); print('host prep %.1fs' % (time.time() - t), flush=True)
 B, parts = PB.algorithmic_bytes_per_iteration(pr)
@@ -37,6 +37,14 @@ for cs, nst, ex in [(a, b, e) for a in csizes for b in stages for e in extra]:
         for nm, i, j in names:
             a = seg(r0, i, j); b = seg(r1, i, j)
             print(f"   {nm:12s} rank0 mean {a.mean():8.1f} max {a.max():8.1f} us | rank1 mean {b.mean():8.1f} max {b.max():8.1f} us")
+        pf = st_[:, 16:48].reshape(-1, 8, 4)
+        if pf[:, :, 1].sum() > 0:
+            for nm, sel in (('rank0', pf[0::cs_]), ('rank1', pf[1::cs_] if cs_ > 1 else pf)):
+                tot = (st_[0::cs_][:, 7] - st_[0::cs_][:, 0]).mean() / 1.9e3
+                print(f"   prof {nm}: per warp mean: slices {sel[:, :, 1].mean():.0f} (max {sel[:, :, 1].max():.0f}), "
+                      f"in slices {sel[:, :, 0].mean() / 1.9e3:.1f} us (max warp {sel[:, :, 0].max(axis=1).mean() / 1.9e3:.1f}), "
+                      f"cycles/slice {sel[:, :, 0].sum() / max(1, sel[:, :, 1].sum()):.0f}, "
+                      f"in level barriers {sel[:, :, 2].mean() / 1.9e3:.1f} us, waiting for chunks {sel[:, :, 3].mean() / 1.9e3:.1f} us, kernel {tot:.1f} us")
         S.h.set_option('debug_timing', 0)
         S.h.set_option('dbg_flags', 0)
     if do_pcg:

@@ -34,9 +34,15 @@ struct Emu {
   void section(int c, int sec, double sign, int only_level = -1) {
     const CtaDesc& D = P.ctas[c];
     std::vector<double>& s = S[c];
-    std::vector<int> wrote_level(s.size(), -1);
+    // wrote_mark[slot] = marker of the synchronisation interval (level, or private slice) that wrote it
+    std::vector<long> wrote_mark(s.size(), -1);
+    std::vector<int> priv_writer(s.size(), -1);  // warp that writes the slot during the private phase
+    long next_mark = 1 << 20;
     int cur_level = -1;
+    long cur_mark = -1;
     uint32_t expect_first = 0;
+    bool seen_private = false, seen_shared = false;
+    // pre-pass: who writes what during the private phase
     for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
       const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
       size_t off = 0;
@@ -45,7 +51,99 @@ struct Emu {
         std::memcpy(&h, base + off, sizeof(h));
         if (h.bytes == 0) break;
         if (off + h.bytes > (size_t)kChunkBytes) throw std::runtime_error("item crosses its chunk");
+        if (h.type == kItemPrivate) {
+          const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
+          const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr) + kPrivDirBytes);
+          if (wb[0] != 0 || wb[kWarps] != h.count) throw std::runtime_error("private directory broken");
+          for (int w = 0; w < kWarps; ++w) {
+            if (wb[w] > wb[w + 1]) throw std::runtime_error("private directory not monotone");
+            for (uint32_t i = wb[w]; i < wb[w + 1]; ++i) {
+              const uint8_t* sl = base + off + (size_t)offs[i] * 16;
+              SliceHdr sh;
+              std::memcpy(&sh, sl, sizeof(sh));
+              const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
+              for (int g = 0; g < sh.nrows; ++g) {
+                if (rr[g].dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
+                if (priv_writer[rr[g].dst] >= 0 && priv_writer[rr[g].dst] != w)
+                  throw std::runtime_error("two warps write the same slot in the private phase");
+                priv_writer[rr[g].dst] = w;
+              }
+            }
+          }
+        }
+        off += h.bytes;
+      }
+    }
+    // one slice, interpreted like process_slice on the device; warp >= 0: private phase
+    auto run_slice = [&](const uint8_t* item, const ItemHdr& h, const uint8_t* sl, int warp) {
+      SliceHdr sh;
+      std::memcpy(&sh, sl, sizeof(sh));
+      const int T = 1 << sh.tlog2;
+      if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
+      const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
+      const double* vals = reinterpret_cast<const double*>(sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
+      const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
+      if ((size_t)(reinterpret_cast<const uint8_t*>(cols + sh.nent) - item) > h.bytes) throw std::runtime_error("slice exceeds its item");
+      std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
+      const uint32_t Wact = (uint32_t)sh.nrows * T;
+      if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
+      for (uint32_t k = 0; k < sh.kmax; ++k)
+        for (uint32_t lane = 0; lane < Wact; ++lane) {
+          const int g = lane / T, t = lane % T;
+          const uint32_t pos = k * Wact + lane;
+          const uint32_t col = cols[pos];
+          if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
+          if (k * T + t < rr[g].len) {
+            if (wrote_mark[col] == cur_mark) throw std::runtime_error("reads a value produced in the same level");
+            if (warp >= 0 && priv_writer[col] >= 0 && priv_writer[col] != warp)
+              throw std::runtime_error("private row reads a slot another warp writes in the private phase");
+          } else if (vals[pos] != 0.0) {
+            throw std::runtime_error("non-zero padding entry");
+          }
+          part[lane][k & 3] += vals[pos] * s[col];
+        }
+      for (int g = 0; g < sh.nrows; ++g) {
+        if ((rr[g].len + T - 1) / T > sh.kmax) throw std::runtime_error("kmax too small");
+        double sum = 0.0;
+        for (int t = 0; t < T; ++t) sum += (part[g * T + t][0] + part[g * T + t][1]) + (part[g * T + t][2] + part[g * T + t][3]);
+        const int dst = rr[g].dst;
+        if (dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
+        if (wrote_mark[dst] == cur_mark) throw std::runtime_error("destination written twice in a level");
+        if (warp < 0 && false) throw std::runtime_error("unreachable");
+        const bool fresh = (rr[g].flags & kRowFresh) != 0;
+        s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) * rr[g].diag;  // reciprocal stored
+        wrote_mark[dst] = cur_mark;
+        if (rr[g].flags & kRowBcast) {
+          if (warp >= 0) throw std::runtime_error("broadcast row in the private phase");
+          for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
+        }
+      }
+    };
+    for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
+      const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
+      size_t off = 0;
+      while (off + sizeof(ItemHdr) <= (size_t)kChunkBytes) {
+        ItemHdr h;
+        std::memcpy(&h, base + off, sizeof(h));
+        if (h.bytes == 0) break;
+        if (h.type == kItemPrivate) {
+          if (only_level >= 0) throw std::runtime_error("private item in a top section");
+          if (!seen_private && seen_shared && h.first != 0) throw std::runtime_error("private phase after shared levels lacks its barrier");
+          if (seen_private && h.first == 0) throw std::runtime_error("barrier inside the private phase");
+          seen_private = true;
+          const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
+          const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr) + kPrivDirBytes);
+          for (int w = 0; w < kWarps; ++w)
+            for (uint32_t i = wb[w]; i < wb[w + 1]; ++i) {
+              cur_mark = next_mark++;  // __syncwarp() separates the slices of a warp
+              run_slice(base + off, h, base + off + (size_t)offs[i] * 16, w);
+            }
+          off += h.bytes;
+          continue;
+        }
         if (h.type != kItemSlices) throw std::runtime_error("unknown item type");
+        if (seen_private && !seen_shared && cur_level != -1) throw std::runtime_error("internal emulator state");
+        seen_shared = true;
         if (h.level >= D.sec_nlevels[sec]) throw std::runtime_error("level beyond nlevels");
         if ((int)h.level < cur_level) throw std::runtime_error("levels not monotone in the stream");
         if ((int)h.level > cur_level) {
@@ -56,50 +154,16 @@ struct Emu {
         if (h.first != expect_first) throw std::runtime_error("slice numbering broken");
         expect_first += h.count;
         if (only_level >= 0 && (int)h.level != only_level) { off += h.bytes; continue; }
+        cur_mark = cur_level;
         const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
-        for (uint32_t i = 0; i < h.count; ++i) {
-          const uint8_t* sl = base + off + (size_t)offs[i] * 16;
-          SliceHdr sh;
-          std::memcpy(&sh, sl, sizeof(sh));
-          const int T = 1 << sh.tlog2;
-          if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
-          const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
-          const double* vals = reinterpret_cast<const double*>(sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
-          const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
-          if ((size_t)(reinterpret_cast<const uint8_t*>(cols + sh.nent) - (base + off)) > h.bytes) throw std::runtime_error("slice exceeds its item");
-          std::vector<double> acc(32, 0.0);   // per lane, 4 interleaved partial sums folded as on the device
-          std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
-          const uint32_t Wact = (uint32_t)sh.nrows * T;
-          if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
-          for (uint32_t k = 0; k < sh.kmax; ++k)
-            for (uint32_t lane = 0; lane < Wact; ++lane) {
-              const int g = lane / T, t = lane % T;
-              const uint32_t pos = k * Wact + lane;
-              const uint32_t col = cols[pos];
-              if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
-              if (k * T + t < rr[g].len) {
-                if (wrote_level[col] == cur_level) throw std::runtime_error("reads a value produced in the same level");
-              } else if (vals[pos] != 0.0) {
-                throw std::runtime_error("non-zero padding entry");
-              }
-              part[lane][k & 3] += vals[pos] * s[col];
-            }
-          for (int g = 0; g < sh.nrows; ++g) {
-            if ((rr[g].len + T - 1) / T > sh.kmax) throw std::runtime_error("kmax too small");
-            double sum = 0.0;
-            for (int t = 0; t < T; ++t) sum += (part[g * T + t][0] + part[g * T + t][1]) + (part[g * T + t][2] + part[g * T + t][3]);
-            const int dst = rr[g].dst;
-            if (dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
-            if (wrote_level[dst] == cur_level) throw std::runtime_error("destination written twice in a level");
-            const bool fresh = (rr[g].flags & kRowFresh) != 0;
-            s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) * rr[g].diag;  // reciprocal stored
-            wrote_level[dst] = cur_level;
-            if (rr[g].flags & kRowBcast)
-              for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
-          }
-        }
+        for (uint32_t i = 0; i < h.count; ++i)
+          if (offs[i] != 0) run_slice(base + off, h, base + off + (size_t)offs[i] * 16, -1);  // 0: empty slot
         off += h.bytes;
       }
+    }
+    if (seen_private && seen_shared) {
+      // shared levels after the private phase start with first == 0 (checked above through cur_level);
+      // nothing else to verify here
     }
   }
 };
@@ -119,6 +183,9 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     BuildOptions opt;
     opt.csize = csize;
     if (const char* e = std::getenv("KB200_MIN_BLOCK")) opt.min_block = std::atoi(e);
+    if (const char* e = std::getenv("KB200_WARPS")) opt.warps = std::atoi(e);
+    if (const char* e = std::getenv("KB200_WARP_PRIVATE")) opt.warp_private = std::atoi(e);
+    if (const char* e = std::getenv("KB200_PRIVATE_SPLIT")) opt.private_split = std::atoi(e);
     DomainPlan P;
     build_domain_plan(in, opt, P);
     Emu E(P);
@@ -188,6 +255,40 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       stats[7] = (double)D0.smem_doubles;
       stats[8] = (double)P.stream.size();
       stats[11] = (double)P.lane_steps;
+      stats[12] = (double)P.n_private_rows;
+      stats[13] = (double)P.n_private_slices;
+      if (std::getenv("EMU_LEVELS")) {
+        for (int sec : {SEC_FWD, SEC_BWD, SEC_TOPF, SEC_TOPB}) {
+          const CtaDesc& D = P.ctas[C > 1 ? 1 : 0];
+          std::vector<long> ent(D.sec_nlevels[sec], 0), nsl(D.sec_nlevels[sec], 0), nrw(D.sec_nlevels[sec], 0);
+          for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
+            const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
+            size_t off = 0;
+            while (off + 16 <= (size_t)kChunkBytes) {
+              ItemHdr h; std::memcpy(&h, base + off, 16);
+              if (!h.bytes) break;
+              if (h.type == kItemPrivate) {
+                const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + 16);
+                std::fprintf(stderr, " {private item: %u slices, per warp", (unsigned)h.count);
+                for (int w = 0; w < kWarps; ++w) std::fprintf(stderr, " %d", wb[w + 1] - wb[w]);
+                std::fprintf(stderr, "}");
+                off += h.bytes;
+                continue;
+              }
+              const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + 16);
+              for (uint32_t i = 0; i < h.count; ++i) {
+                if (!offs[i]) continue;
+                SliceHdr sh; std::memcpy(&sh, base + off + (size_t)offs[i] * 16, 16);
+                ent[h.level] += sh.nent; nsl[h.level] += 1; nrw[h.level] += sh.nrows;
+              }
+              off += h.bytes;
+            }
+          }
+          std::fprintf(stderr, "sec %d levels %zu:", sec, ent.size());
+          for (size_t l = 0; l < ent.size(); ++l) std::fprintf(stderr, " [%zu: %ld ent %ld sl %ld rows]", l, ent[l], nsl[l], nrw[l]);
+          std::fprintf(stderr, "\n");
+        }
+      }
       stats[9] = (double)std::max(D0.sec_nlevels[SEC_TOPF], D0.sec_nlevels[SEC_TOPB]);
       stats[10] = (double)std::max(D0.sec_nlevels[SEC_FWD], D0.sec_nlevels[SEC_BWD]);
 

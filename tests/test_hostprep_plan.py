@@ -30,7 +30,7 @@ def emu():
     return lib
 
 
-def run_emu(lib, p, L, G, GG, csize, mode, xd, bI, min_block=None):
+def run_emu(lib, p, L, G, GG, csize, mode, xd, bI, min_block=None, env=None):
     nI, ng = G.shape
     out, uI, st = np.zeros(ng), np.zeros(nI), np.zeros(16)
     err = C.create_string_buffer(256)
@@ -39,6 +39,8 @@ def run_emu(lib, p, L, G, GG, csize, mode, xd, bI, min_block=None):
         m.sort_indices()
     if min_block is not None:
         os.environ["KB200_MIN_BLOCK"] = str(min_block)
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
     try:
         rc = lib.planemu_run(nI, ng, p.astype(np.int32), L.indptr.astype(np.int32), L.indices.astype(np.int32),
                              np.ascontiguousarray(L.data), G.indptr.astype(np.int32), G.indices.astype(np.int32),
@@ -47,6 +49,8 @@ def run_emu(lib, p, L, G, GG, csize, mode, xd, bI, min_block=None):
                              np.ascontiguousarray(bI), out, uI, st, err, 256)
     finally:
         os.environ.pop("KB200_MIN_BLOCK", None)
+        for k in (env or {}):
+            os.environ.pop(k, None)
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return out, uI, st
@@ -88,6 +92,29 @@ def test_plan_program_matches_exact_solves(emu, csize, min_block):
     assert abs(u - ref_bs).max() <= 1e-12 * abs(ref_bs).max()
     if min_block:
         assert st[2] < 80          # block inversion collapses the supernode chains' levels
+
+
+@pytest.mark.parametrize("env", [{}, {"KB200_WARPS": 16}, {"KB200_WARP_PRIVATE": 1},
+                                 {"KB200_WARP_PRIVATE": 1, "KB200_PRIVATE_SPLIT": 4}])
+@pytest.mark.parametrize("csize", [1, 4])
+def test_plan_variants_on_a_large_subdomain(emu, env, csize):
+    """~4k interior nodes: levels hold more slices than consumer warps (balanced slots with empty
+    entries), 16-warp layout, warp-private bottom subtrees -- all against exact solves."""
+    pr = get_problem(129, 4)
+    d = 2
+    p, L = pr.factors[d]
+    A, G, GG = pr.blocks.A_II[d].tocsc(), pr.blocks.A_IG[d], pr.blocks.A_GG[d]
+    lu = spla.splu(A)
+    rng = np.random.default_rng(7)
+    xd, bI = rng.standard_normal(G.shape[1]), rng.standard_normal(G.shape[0])
+    o, _, st = run_emu(emu, p, L, G, GG, csize, 0, xd, bI, env=env)
+    ref = GG @ xd - G.T @ lu.solve(G @ xd)
+    assert abs(o - ref).max() <= 1e-12 * abs(ref).max()
+    _, u, _ = run_emu(emu, p, L, G, GG, csize, 2, xd, bI, env=env)
+    ref = lu.solve(bI - G @ xd)
+    assert abs(u - ref).max() <= 1e-12 * abs(ref).max()
+    if env.get("KB200_WARP_PRIVATE"):
+        assert st[12] > 0       # rows were handled warp-privately
 
 
 def test_plan_edge_cases(emu):
