@@ -106,7 +106,7 @@ def main():
         log(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}")
     workload = f"synthetic {args.nx}x{args.nx}-node unit-square P1 mesh, {args.ndom} RCB subdomains, lognormal a (sig2=1, L=0.1, realization 1), median NN preconditioner"
     config = {"workload": workload, "n_dof": (args.nx - 2) ** 2, "ndom": args.ndom, "tol": 1e-7,
-              "x0": "zeros", "l2": "inputs_larger_than_L2 (2.7 GB streamed per Schur apply)",
+              "x0": "zeros", "l2": "inputs_larger_than_L2 (3.5 GB streamed per Schur apply at N=1; >= 0.44 GB per GPU at N=8)",
               "parallelism": f"subdomains sharded over {max(world, 1)} GPU(s), NCCL all-reduce of the interface vector"}
 
     if args.impl == "reference":
@@ -155,6 +155,14 @@ def main():
                               for d in range(sd.ndom)])
     b_schur = S.h.schur_rhs(b_I_cat, pr.blocks.b_G)
     stats = S.h.stats()
+    if world > 1:
+        config["parallelism"] = (f"subdomains sharded over {world} GPUs; interface vectors combined by "
+                                 + ("the fused assemble + peer-memory exchange kernel (CUDA IPC over NVLink, no NCCL call per iteration)"
+                                    if stats["peer_exchange"] else "an NCCL all-reduce per operator application"))
+    else:
+        config["parallelism"] = "1 GPU, all subdomains local"
+    config["kernel"] = {"cluster_size": int(stats["csize"]), "consumer_warps": int(stats["consumer_warps"]),
+                        "ring_stages": int(stats["ring_stages"]), "ctas": int(stats["n_cta"])}
     log(f"[rank {rank}] device setup {time.time() - t0:.1f}s; stream {stats['stream_bytes'] / 1e9:.2f} GB, "
         f"levels {stats['max_levels']:.0f}, smem/CTA {stats['smem_bytes']:.0f} B, CTAs {stats['n_cta']:.0f}")
 

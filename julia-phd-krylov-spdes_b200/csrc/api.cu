@@ -115,6 +115,14 @@ struct kb200_ctx {
   int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 0, lane_entries = 0, pad_tol_pct = -1;
   int warp_private = -1, private_split = 0;
   int warps = 0;  // consumer warps per CTA of the stream kernel: 8 or 16 (0: automatic)
+  // interface exchange over peer memory (CUDA IPC, NVLink): fused into the assembly kernel
+  int peer_exchange = 1;  // option: 0 = always use the NCCL all-reduce
+  bool peer_ok = false;
+  void* xch_own = nullptr;             // this rank's receive buffer + flags
+  void* xch_peer[kb::kMaxPeers] = {};  // mapped buffers of all ranks (own included)
+  size_t xch_flags_off = 0;
+  int xch_npad = 0;
+  uint32_t xch_seq = 0;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -178,6 +186,8 @@ int guarded(F&& f) {
 void use_device(Ctx* c) { CUDA_TRY(cudaSetDevice(c->device)); }
 
 bool is_local(const Ctx* c, int64_t d) { return d >= c->d0 && d < c->d1; }
+
+void setup_peer_exchange(Ctx* c);
 
 // ---- finalize: build plans, upload -------------------------------------------------------------
 void finalize(Ctx* c) {
@@ -387,7 +397,86 @@ void finalize(Ctx* c) {
   c->stats[8] = c->n_cta;
   c->stats[9] = c->csize;
   c->stats[10] = (double)c->mat_off[nloc] * 8.0;
+  setup_peer_exchange(c);
+  c->stats[11] = c->peer_ok ? 1.0 : 0.0;
+  c->stats[12] = c->warps;
+  c->stats[13] = c->stages;
   c->finalized = true;  // host copies of the inputs are kept: value updates re-run the analysis
+}
+
+// ---- peer-memory interface exchange (multi-rank) -----------------------------------------------
+// Every rank allocates [2 slots][world][n_pad] doubles + [world][nb] flags, exports the allocation
+// with cudaIpcGetMemHandle; the handles travel through one ncclAllGather and are opened with
+// cudaIpcOpenMemHandle (peer access over NVLink).  Any failure on any rank (agreed through an
+// all-reduce) leaves the NCCL path in charge.
+void setup_peer_exchange(Ctx* c) {
+#ifdef KB200_WITH_NCCL
+  if (!c->has_comm || c->world < 2 || c->world > kb::kMaxPeers || !c->peer_exchange || c->xch_own) return;
+  const int W = c->world;
+  c->xch_npad = c->nb * kb::kVecThreads;
+  const size_t data_bytes = (size_t)2 * W * c->xch_npad * sizeof(double);
+  const size_t flag_bytes = (size_t)W * c->nb * sizeof(uint32_t);
+  c->xch_flags_off = data_bytes;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&c->xch_own, data_bytes + flag_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    c->xch_own = nullptr;
+    ok = 0;
+  }
+  if (ok) {
+    CUDA_TRY(cudaMemset(c->xch_own, 0, data_bytes + flag_bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (cudaIpcGetMemHandle(&mine, c->xch_own) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  DevBuf<uint8_t> d_send, d_recv;
+  DevBuf<int> d_ok;
+  d_send.alloc(64);
+  d_recv.alloc((size_t)64 * W);
+  d_ok.alloc(1);
+  CUDA_TRY(cudaMemcpyAsync(d_send.p, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(ncclAllGather(d_send.p, d_recv.p, 64, ncclChar, c->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_recv.p, (size_t)64 * W, cudaMemcpyDeviceToHost, c->stream));
+  auto agree = [&](int v) {
+    CUDA_TRY(cudaMemcpyAsync(d_ok.p, &v, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(ncclAllReduce(d_ok.p, d_ok.p, 1, ncclInt, ncclMin, c->comm, c->stream));
+    int r = 0;
+    CUDA_TRY(cudaMemcpyAsync(&r, d_ok.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return r;
+  };
+  ok = agree(ok);  // also orders every rank's memset before any peer's first store
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == c->rank) {
+        c->xch_peer[r] = c->xch_own;
+      } else if (cudaIpcOpenMemHandle(&c->xch_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        c->xch_peer[r] = nullptr;
+        ok = 0;
+      }
+    }
+    ok = agree(ok);
+  }
+  if (!ok) {
+    for (int r = 0; r < W; ++r)
+      if (r != c->rank && c->xch_peer[r]) cudaIpcCloseMemHandle(c->xch_peer[r]);
+    std::memset(c->xch_peer, 0, sizeof(c->xch_peer));
+    if (c->xch_own) cudaFree(c->xch_own);
+    c->xch_own = nullptr;
+    cudaGetLastError();
+  }
+  c->peer_ok = ok != 0;
+  c->xch_seq = 0;
+#else
+  (void)c;
+#endif
 }
 
 // ---- launches ----------------------------------------------------------------------------------
@@ -475,6 +564,27 @@ void assemble(Ctx* c, const double* loc, const double* base, double* y, const do
   if (!c->has_comm) {
     kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base, y, q,
                                                                  part, done_at, iter);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return;
+  }
+  if (c->peer_ok) {
+    // fused: assemble the local partial, exchange it over NVLink peer memory, sum, partial dot
+    kb::XchParams X;
+    std::memset(&X, 0, sizeof(X));
+    for (int r = 0; r < c->world; ++r) {
+      X.data[r] = reinterpret_cast<double*>(c->xch_peer[r]);
+      X.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->xch_peer[r]) + c->xch_flags_off);
+    }
+    X.world = c->world;
+    X.rank = c->rank;
+    X.seq = ++c->xch_seq;
+    X.slot = (int)(X.seq & 1u);
+    X.n_pad = c->xch_npad;
+    X.fail = &c->d_state.p->fail;
+    kb::assemble_exchange_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
+                                                                          c->rank == 0 ? base : nullptr, y, q, part,
+                                                                          done_at, iter, X);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return;
@@ -649,6 +759,9 @@ int kb200_destroy(kb200_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < kb::kMaxPeers; ++r)
+      if (h->xch_peer[r] && h->xch_peer[r] != h->xch_own) cudaIpcCloseMemHandle(h->xch_peer[r]);
+    if (h->xch_own) cudaFree(h->xch_own);
 #ifdef KB200_WITH_NCCL
     if (h->comm) ncclCommDestroy(h->comm);
 #endif
@@ -691,6 +804,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "lane_entries") {
       require(!h->finalized && value >= 1 && value <= 256, "lane_entries must be set before the first operation");
       h->lane_entries = (int)value;
+    } else if (k == "peer_exchange") {
+      require(!h->finalized && (value == 0 || value == 1), "peer_exchange is 0 or 1, before the first operation");
+      h->peer_exchange = (int)value;
     } else if (k == "warps") {
       require(!h->finalized && (value == 0 || value == 8 || value == 16), "warps is 0 (automatic), 8 or 16, before the first operation");
       h->warps = (int)value;
@@ -1104,6 +1220,7 @@ int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double 
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *it_out = it;
     finish_timings(c, kt, T, launches0, tm);
+    if (fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
     if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
   });
 }
@@ -1191,6 +1308,7 @@ int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, in
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *it_out = it;
     finish_timings(c, kt, T, launches0, tm);
+    if (fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
     if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
   });
 }

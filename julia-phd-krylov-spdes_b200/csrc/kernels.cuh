@@ -576,6 +576,82 @@ assemble_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const dou
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Interface assembly FUSED with the all-reduce over the GPUs of the node (subdomains are sharded over
+// the ranks, EllipticPdePllDomainDecomposition.jl:11 `@distributed (+)`): every rank owns a receive
+// buffer that its peers map through CUDA IPC (NVLink / NVSwitch peer memory).  Block b of every rank
+// assembles segment b of the rank's partial interface vector, stores it straight into the receive
+// buffers of ALL ranks (one-shot all-gather of partials: n_gamma * 8 B per peer, a few MB in total),
+// publishes a per-block sequence flag (release, system scope) at every peer, waits for the flags of
+// segment b from all ranks and sums the `world` partials in rank order -- identical bits on every rank,
+// so the PCG scalars and iteration counts agree without any further exchange.  The dot product with q
+// is taken on the fly.  No grid-wide barrier, no separate collective launch.
+// Buffers: two data slots used alternately (a rank can run at most one exchange ahead of a peer: it
+// cannot finish exchange k+1 before that peer has pushed k+1, i.e. has left the kernel of exchange k).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct XchParams {
+  double* data[kMaxPeers];     // receive buffer of every rank: [2 slots][world][n_pad] doubles
+  uint32_t* flags[kMaxPeers];  // flags of every rank: [world sources][nb blocks]
+  int world, rank, slot;
+  uint32_t seq;                // sequence number of this exchange (monotone, identical on all ranks)
+  int n_pad;                   // n rounded up to the block size
+  int* fail;                   // set to 2 when a peer does not show up (time-out instead of a hang)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
+                         double* y, const double* q, double* part, const int* done_at, int iter, const XchParams X) {
+  __shared__ double red[8];
+  if (done_at != nullptr && *done_at < iter) return;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = gridDim.x;
+  // partial of this rank (ascending local subdomain order; rank 0 carries `base`)
+  double a = 0.0;
+  if (g < n) {
+    a = (base != nullptr) ? base[g] : 0.0;
+    for (int k = adj_ptr[g]; k < adj_ptr[g + 1]; ++k) a += loc[adj_src[k]];
+  }
+  const size_t seg = ((size_t)X.slot * X.world + X.rank) * (size_t)X.n_pad + (size_t)g;
+  for (int r = 0; r < X.world; ++r) __stcg(X.data[r] + seg, a);
+  __syncthreads();
+  if ((int)threadIdx.x < X.world) {
+    const int r = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(X.flags[r] + (size_t)X.rank * nb + blockIdx.x, X.seq);
+    // wait for segment blockIdx.x of source rank r
+    const uint32_t* f = X.flags[X.rank] + (size_t)r * nb + blockIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - X.seq) < 0) {
+      if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer never arrived
+        if (X.fail != nullptr) *X.fail = 2;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  double sum = 0.0, prod = 0.0;
+  if (g < n) {
+    const double* mine = X.data[X.rank] + (size_t)X.slot * X.world * (size_t)X.n_pad + (size_t)g;
+    for (int r = 0; r < X.world; ++r) sum += __ldcg(mine + (size_t)r * X.n_pad);
+    y[g] = sum;
+    if (q != nullptr) prod = sum * q[g];
+  }
+  if (part != nullptr) {
+    const double s = block_reduce_sum(prod, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  }
+}
+
 // part[b] = block partial of dot(a, b)
 __global__ void __launch_bounds__(kVecThreads)
 dot_kernel(int n, const double* a, const double* b, double* part, const int* done_at, int iter) {
