@@ -114,6 +114,7 @@ struct kb200_ctx {
   // options
   int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 0, lane_entries = 0, pad_tol_pct = -1;
   int warp_private = -1, private_split = 0;
+  int adaptive_lanes = -1, lane_min = 0, lane_max = 0;
   int warps = 0;  // consumer warps per CTA of the stream kernel: 8 or 16 (0: automatic)
   // interface exchange over peer memory (CUDA IPC, NVLink): fused into the assembly kernel
   int peer_exchange = 1;  // option: 0 = always use the NCCL all-reduce
@@ -220,6 +221,9 @@ void finalize(Ctx* c) {
   if (c->min_block >= 0) opt.min_block = c->min_block;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
   if (c->pad_tol_pct >= 0) opt.pad_tol = c->pad_tol_pct / 100.0;
+  if (c->adaptive_lanes >= 0) opt.adaptive_lanes = c->adaptive_lanes;
+  if (c->lane_min > 0) opt.lane_min = c->lane_min;
+  if (c->lane_max > 0) opt.lane_max = c->lane_max;
   if (c->warp_private >= 0) opt.warp_private = c->warp_private;
   if (c->private_split > 0) opt.private_split = c->private_split;
   {
@@ -804,6 +808,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "lane_entries") {
       require(!h->finalized && value >= 1 && value <= 256, "lane_entries must be set before the first operation");
       h->lane_entries = (int)value;
+    } else if (k == "adaptive_lanes" || k == "lane_min" || k == "lane_max") {
+      require(!h->finalized && value >= 0 && value <= 256, "lane options must be set before the first operation");
+      (k == "adaptive_lanes" ? h->adaptive_lanes : k == "lane_min" ? h->lane_min : h->lane_max) = (int)value;
     } else if (k == "peer_exchange") {
       require(!h->finalized && (value == 0 || value == 1), "peer_exchange is 0 or 1, before the first operation");
       h->peer_exchange = (int)value;

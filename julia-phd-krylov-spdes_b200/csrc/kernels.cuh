@@ -211,66 +211,42 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
   }
 }
 
-// Consumer warps: interpret the items of one section out of the ring (levels of slices, see plan.h).
-// Every warp reads every item header, so all of them execute the same barriers (one per level).
-// TOP sections (kTop): the rows of a level are shared out over the CTAs of the cluster; results are
-// stored into every CTA's replica of the top vector and a cluster-wide barrier separates levels.
+// Consumer warps: run the warp programs of one section out of the ring (see plan.h).  A warp reads
+// only its own token list of every chunk: a token is a slice to process or the end of a level
+// (CTA barrier; TOP sections (kTop): barrier over the whole cluster, the rows of a level having been
+// shared out over the CTAs and their results stored into every CTA's replica of the top vector).
 template <bool kTop, int NW>
 __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
-  const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec], nlev = cx.D->sec_nlevels[sec];
+  const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec];
   const int lane = cx.lane, warp = cx.warp;
-  uint32_t lvl = 0;
   for (uint32_t ch = c0; ch < c1; ++ch) {
     const uint32_t stage = cx.stage;
     KB_PROF(const long long tw0 = clock64();)
     mbar_wait(&cx.full_bar[stage], cx.phase);
     KB_PROF(cx.t_wait += clock64() - tw0;)
     const uint8_t* chunk = cx.ring + stage * kChunkBytes;
-    uint32_t off = 0;
-    uint4 hq = *reinterpret_cast<const uint4*>(chunk);
-    while (off < (uint32_t)kChunkBytes) {
-      const uint32_t bytes = hq.x;
-      if (bytes == 0) break;
-      const uint32_t count = hq.y >> 16, first = hq.z;
-      const uint32_t item_type = hq.y & 0xffu, item_level = hq.w;
-      // the next item header is fetched now, so its latency hides behind this item's slices
-      if (off + bytes < (uint32_t)kChunkBytes) hq = *reinterpret_cast<const uint4*>(chunk + off + bytes);
-      if (kTop) {
-        while (lvl < item_level) {
-          cluster_level_sync<NW>(cx);
-          ++lvl;
-        }
-      } else if (first == 0 && !(cx.dbg_flags & 2)) {
-        KB_PROF(const long long tb0 = clock64();)
-        consumer_barrier<NW>();  // a new level starts: the previous one is complete
-        KB_PROF(cx.t_bar += clock64() - tb0;)
+    const uint32_t t0 = reinterpret_cast<const uint16_t*>(chunk)[warp];
+    const uint32_t dnext = reinterpret_cast<const uint16_t*>(chunk)[warp + 1];
+    const uint16_t* tok = reinterpret_cast<const uint16_t*>(chunk + kChunkDirBytes);
+    for (uint32_t i = t0; i < dnext; ++i) {
+      const uint32_t t = tok[i];
+      if (t == kTokBarrier) {
+#ifdef KB200_SLICE_PROF
+        if (kTop) cluster_level_sync<NW>(cx);
+        else if (!(cx.dbg_flags & 2)) consumer_barrier<NW>();
+#else
+        if (kTop) cluster_level_sync<NW>(cx);
+        else consumer_barrier<NW>();
+#endif
+      } else {
+#ifdef KB200_SLICE_PROF
+        if (cx.dbg_flags & 1) continue;
+#endif
+        KB_PROF(const long long ts0 = clock64();)
+        process_slice<kTop>(cx, chunk + t * 16u, sign);
+        __syncwarp();  // the warp's next slice may read these rows (warp-private subtrees)
+        KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
       }
-      if (!kTop && item_type == kItemPrivate) {
-        // private item: this warp walks its own slices (rows of its subtrees, level by level); the
-        // lanes of the warp are the only readers / writers of these rows, __syncwarp() orders them
-        if (!(cx.dbg_flags & 1)) {
-          const uint16_t* wb = reinterpret_cast<const uint16_t*>(chunk + off + 16);
-          const uint16_t* offs = reinterpret_cast<const uint16_t*>(chunk + off + 16 + kPrivDirBytes);
-          // (the plan shares private rows out over kWarps warps; further consumer warps have none)
-          const uint32_t s1 = warp < kWarps ? wb[warp + 1] : 0u;
-          for (uint32_t i = warp < kWarps ? wb[warp] : 0u; i < s1; ++i) {
-            KB_PROF(const long long ts0 = clock64();)
-            process_slice<false>(cx, chunk + off + (uint32_t)offs[i] * 16u, sign);
-            __syncwarp();
-            KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
-          }
-        }
-      } else if (!(cx.dbg_flags & 1)) {
-        const uint16_t* offs = reinterpret_cast<const uint16_t*>(chunk + off + 16);
-        for (uint32_t i = (uint32_t)(warp - (int)(first & (NW - 1))) & (NW - 1); i < count; i += NW) {
-          const uint32_t so = offs[i];
-          if (so == 0) continue;  // empty slot
-          KB_PROF(const long long ts0 = clock64();)
-          process_slice<kTop>(cx, chunk + off + so * 16u, sign);
-          KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
-        }
-      }
-      off += bytes;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&cx.empty_bar[stage]);
@@ -278,14 +254,6 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
       cx.stage = 0;
       cx.phase ^= 1u;
     }
-  }
-  if (kTop) {
-    while (lvl < nlev) {
-      cluster_level_sync<NW>(cx);
-      ++lvl;
-    }
-  } else if (!(cx.dbg_flags & 2)) {
-    consumer_barrier<NW>();  // the section's last level is complete
   }
 }
 

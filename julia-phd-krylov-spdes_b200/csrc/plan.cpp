@@ -105,7 +105,7 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
     put(pc.data(), pc.size() * 2);
   }
   while (b.size() % 16) b.push_back(0);
-  if (b.size() + sizeof(ItemHdr) + kPrivDirBytes + 16 > (size_t)kChunkBytes)
+  if (b.size() + (size_t)kChunkDirBytes + 16 > (size_t)kChunkBytes)
     throw std::runtime_error("internal: slice exceeds a chunk");
   cs.n_entries += real;
   cs.n_rows += nr;
@@ -114,18 +114,90 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
   return b;
 }
 
-// Serialise the rows of one section (see plan.h): the rows without a warp (`warp` < 0) as levels of
-// slices shared out over the consumer warps, the warp-private rows as private items, before
-// (private_first, forward sweep) or after (backward sweep) the shared levels.
+// Chunk under construction: per-warp token lists + slice payloads (see plan.h, "warp programs").
+struct ChunkBuilder {
+  int NW;
+  CtaStream& cs;
+  std::vector<std::vector<uint16_t>> tok;          // per warp: slice index (into `slices`) or kTokBarrier
+  std::vector<std::vector<uint8_t>> slices;
+  size_t payload = 0, ntok = 0;
+  ChunkBuilder(int nw, CtaStream& s) : NW(nw), cs(s), tok(nw) {}
+  static size_t table_bytes(size_t ntokens) { return (size_t)kChunkDirBytes + ((ntokens * 2 + 15) / 16) * 16; }
+  bool empty() const { return ntok == 0; }
+  bool fits(size_t more_tokens, size_t more_payload) const {
+    return table_bytes(ntok + more_tokens) + payload + more_payload <= (size_t)kChunkBytes;
+  }
+  void flush() {
+    if (empty()) return;
+    if (cs.bytes.size() % kChunkBytes) throw std::runtime_error("internal: chunk builder out of phase");
+    const size_t base = cs.bytes.size();
+    const size_t tb = table_bytes(ntok);
+    std::vector<size_t> off(slices.size());
+    size_t o = tb;
+    for (size_t k = 0; k < slices.size(); ++k) {
+      off[k] = o;
+      o += slices[k].size();
+    }
+    if (o > (size_t)kChunkBytes) throw std::runtime_error("internal: chunk overflow");
+    std::vector<uint16_t> dir(kChunkDirBytes / 2, 0);
+    size_t acc = 0;
+    for (int w = 0; w < NW; ++w) {
+      dir[w] = (uint16_t)acc;
+      acc += tok[w].size();
+    }
+    dir[NW] = (uint16_t)acc;
+    for (uint16_t v : dir) cs.put(v);
+    size_t written = 0;
+    for (int w = 0; w < NW; ++w)
+      for (uint16_t t : tok[w]) {
+        cs.put(t == kTokBarrier ? kTokBarrier : (uint16_t)(off[t] / 16));
+        ++written;
+      }
+    while ((written * 2) % 16) {
+      cs.put((uint16_t)0);
+      ++written;
+    }
+    for (auto& sl : slices) cs.bytes.insert(cs.bytes.end(), sl.begin(), sl.end());
+    if (cs.bytes.size() - base != o) throw std::runtime_error("internal: chunk size mismatch");
+    cs.pad_to_chunk();
+    for (auto& t : tok) t.clear();
+    slices.clear();
+    payload = 0;
+    ntok = 0;
+  }
+  void add_slice(int warp, std::vector<uint8_t>&& b) {
+    if (!fits(1, b.size())) flush();
+    if (!fits(1, b.size())) throw std::runtime_error("internal: slice exceeds a chunk");
+    if (slices.size() >= 0xfffe) throw std::runtime_error("internal: too many slices in a chunk");
+    tok[warp].push_back((uint16_t)slices.size());
+    payload += b.size();
+    slices.push_back(std::move(b));
+    ++ntok;
+  }
+  void add_barrier() {  // one barrier token in every warp's program
+    if (!fits((size_t)NW, 0)) flush();
+    for (int w = 0; w < NW; ++w) tok[w].push_back(kTokBarrier);
+    ntok += (size_t)NW;
+  }
+};
+
+// Serialise the rows of one section as warp programs (see plan.h).  Rows without a warp (`warp` < 0)
+// form CTA-wide dependency levels: the slices of a level are balanced over the NW consumer warps and
+// every warp's program gets a barrier token after each level (`force_levels`: top sections, where
+// every CTA of the cluster must execute the same number of barriers, also for levels in which it has
+// no rows).  Warp-private rows (`warp` >= 0) go to their warp in level order without barriers, before
+// (private_first, forward sweep) or after (backward sweep) the shared levels, fenced by one barrier.
 void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptions& opt, CtaStream& cs,
                   uint32_t& chunk0, uint32_t& chunk1, uint32_t& nlevels, int force_levels = -1,
                   bool private_first = true, int64_t* n_private_rows = nullptr, int64_t* n_private_slices = nullptr) {
   cs.pad_to_chunk();
   chunk0 = (uint32_t)(cs.bytes.size() / kChunkBytes);
+  const int NW = (opt.warps == 16) ? 16 : kWarps;
   int maxlev = -1;
   bool any_private = false;
   for (auto& r : rows) {
     if (r.level < 0) throw std::runtime_error("internal: negative level");
+    if (r.warp >= NW) throw std::runtime_error("internal: warp out of range");
     if (r.warp >= 0) any_private = true;
     else maxlev = std::max(maxlev, r.level);
   }
@@ -135,8 +207,9 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
     if (any_private) throw std::runtime_error("internal: private rows in a section with forced levels");
     nlevels = (uint32_t)force_levels;
   }
+  int lane_entries = std::max(1, opt.lane_entries);  // entries a lane of a row aims at (set per level below)
   auto t_of = [&](uint32_t len) {
-    const int want = (int)((len + opt.lane_entries - 1) / std::max(1, opt.lane_entries));
+    const int want = (int)((len + lane_entries - 1) / lane_entries);
     return std::min(32, pow2ceil(std::max(1, want)));
   };
   // slices of the rows ord[i..j) (one level, sorted by decreasing length)
@@ -166,91 +239,60 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
     });
     return ord;
   };
+  ChunkBuilder cb(NW, cs);
 
-  const int NW = (opt.warps == 16) ? 16 : kWarps;
   auto emit_shared = [&]() {
     const std::vector<uint32_t> ord = sorted_order([](const TmpRow& r) { return r.warp < 0; });
     std::vector<std::vector<uint8_t>> slices;  // serialised slices of the current level
     size_t i = 0;
-    while (i < ord.size()) {
+    for (int lev = 0; lev < (int)nlevels; ++lev) {
       size_t j = i;
-      const int lev = rows[ord[i]].level;
       while (j < ord.size() && rows[ord[j]].level == lev) ++j;
       slices.clear();
-      level_slices(ord, i, j, slices);
-      // Slot k of the level's sequence is executed by consumer warp k % NW.  Balance the warps
-      // (longest-processing-time first on an estimate of the slice latency) and lay the slices out
-      // round by round; a warp with fewer slices leaves empty slots (offset 0 in the directory).
-      if ((int)slices.size() > NW) {
-        auto cost = [](const std::vector<uint8_t>& b) {
-          SliceHdr sh;
-          std::memcpy(&sh, b.data(), sizeof(sh));
-          return 400 + 30 * (int)sh.kmax + 40 * (int)sh.tlog2;
-        };
-        std::vector<size_t> so(slices.size());
-        std::iota(so.begin(), so.end(), (size_t)0);
-        std::stable_sort(so.begin(), so.end(), [&](size_t a, size_t b) { return cost(slices[a]) > cost(slices[b]); });
-        std::vector<std::vector<size_t>> per_warp(NW);
-        std::vector<int64_t> load(NW, 0);
-        for (size_t k : so) {
-          int best = 0;
-          for (int w = 1; w < NW; ++w)
-            if (load[w] < load[best]) best = w;
-          load[best] += cost(slices[k]);
-          per_warp[best].push_back(k);
+      if (j > i) {
+        if (opt.adaptive_lanes) {
+          // spread the level's entries over all NW warps (about one slice per warp), between lane_min
+          // and lane_max entries per lane
+          int64_t ent = 0;
+          for (size_t k = i; k < j; ++k) ent += rows[ord[k]].len;
+          const int64_t per_lane = (ent + (int64_t)NW * 32 - 1) / ((int64_t)NW * 32);
+          lane_entries = (int)std::min<int64_t>(std::max<int64_t>(per_lane, opt.lane_min), opt.lane_max);
         }
-        size_t rounds = 0;
-        for (auto& v : per_warp) rounds = std::max(rounds, v.size());
-        std::vector<std::vector<uint8_t>> seq;
-        for (size_t r = 0; r < rounds; ++r)
-          for (int w = 0; w < NW; ++w)
-            seq.push_back(r < per_warp[w].size() ? std::move(slices[per_warp[w][r]]) : std::vector<uint8_t>());
-        while (!seq.empty() && seq.back().empty()) seq.pop_back();
-        slices.swap(seq);
+        level_slices(ord, i, j, slices);
+        lane_entries = std::max(1, opt.lane_entries);
       }
-      // pack the level's slices into items
-      size_t s0 = 0;
-      while (s0 < slices.size()) {
-        auto item_bytes = [&](size_t a, size_t bnd) {
-          size_t tot = sizeof(ItemHdr) + (((bnd - a) * 2 + 15) / 16) * 16;
-          for (size_t k = a; k < bnd; ++k) tot += slices[k].size();
-          return tot;
-        };
-        size_t room = cs.room();
-        size_t s1 = s0;
-        while (s1 < slices.size() && item_bytes(s0, s1 + 1) <= room) ++s1;
-        if (s1 == s0) {
-          cs.pad_to_chunk();
-          continue;
+      // balance the warps of the level: longest-processing-time first on an estimate of the slice latency
+      auto cost = [](const std::vector<uint8_t>& b) {
+        SliceHdr sh;
+        std::memcpy(&sh, b.data(), sizeof(sh));
+        return 150 + 30 * (int)sh.kmax + 40 * (int)sh.tlog2;
+      };
+      std::vector<size_t> so(slices.size());
+      std::iota(so.begin(), so.end(), (size_t)0);
+      std::stable_sort(so.begin(), so.end(), [&](size_t a, size_t b) { return cost(slices[a]) > cost(slices[b]); });
+      std::vector<int64_t> load(NW, 0);
+      // rotate the starting warp with the level so that no warp always gets the heaviest slice
+      for (size_t k : so) {
+        int best = lev % NW;
+        for (int d = 1; d < NW; ++d) {
+          const int w = (lev + d) % NW;
+          if (load[w] < load[best]) best = w;
         }
-        ItemHdr ih;
-        std::memset(&ih, 0, sizeof(ih));
-        ih.bytes = (uint32_t)item_bytes(s0, s1);
-        ih.type = kItemSlices;
-        ih.count = (uint16_t)(s1 - s0);
-        ih.first = (uint32_t)s0;
-        ih.level = (uint32_t)lev;
-        cs.put(ih);
-        size_t offb = sizeof(ItemHdr) + (((s1 - s0) * 2 + 15) / 16) * 16;
-        std::vector<uint16_t> offs;
-        for (size_t k = s0; k < s1; ++k) {
-          offs.push_back(slices[k].empty() ? (uint16_t)0 : (uint16_t)(offb / 16));  // 0: empty slot
-          offb += slices[k].size();
-        }
-        while ((offs.size() * 2) % 16) offs.push_back(0);
-        for (uint16_t o : offs) cs.put(o);
-        for (size_t k = s0; k < s1; ++k) cs.bytes.insert(cs.bytes.end(), slices[k].begin(), slices[k].end());
-        s0 = s1;
+        load[best] += cost(slices[k]);
+        cb.add_slice(best, std::move(slices[k]));
       }
+      cb.add_barrier();
       i = j;
     }
+    if (i != ord.size()) throw std::runtime_error("internal: rows beyond the last level");
   };
 
-  auto emit_private = [&](bool barrier_before) {
-    // per warp: the slices of its rows in level order
-    std::vector<std::vector<std::vector<uint8_t>>> ws(kWarps);
-    std::vector<size_t> tot(kWarps, 0), nxt(kWarps, 0), rem(kWarps, 0);
-    for (int w = 0; w < kWarps; ++w) {
+  auto emit_private = [&]() {
+    // per warp: the slices of its rows in level order; the chunks take from each warp a share
+    // proportional to what it has left, so that the warps advance through the ring at the same pace
+    std::vector<std::vector<std::vector<uint8_t>>> ws(NW);
+    std::vector<size_t> tot(NW, 0), nxt(NW, 0), rem(NW, 0);
+    for (int w = 0; w < NW; ++w) {
       const std::vector<uint32_t> ord = sorted_order([w](const TmpRow& r) { return r.warp == w; });
       size_t i = 0;
       while (i < ord.size()) {
@@ -264,84 +306,29 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
       if (n_private_rows) *n_private_rows += (int64_t)ord.size();
       if (n_private_slices) *n_private_slices += (int64_t)ws[w].size();
     }
-    bool first_item = true;
     for (;;) {
-      bool left = false;
-      for (int w = 0; w < kWarps; ++w) left = left || nxt[w] < ws[w].size();
-      if (!left) break;
-      // every item takes from each warp a share proportional to what the warp has left, so that the
-      // warps advance through the chunks at the same pace: always extend the warp that lags most
-      const size_t room = cs.room();
-      std::vector<size_t> take(kWarps, 0);
-      size_t nsl = 0, payload = 0;
-      auto bytes_with = [&](size_t n_slices, size_t pay) {
-        return sizeof(ItemHdr) + (size_t)kPrivDirBytes + ((n_slices * 2 + 15) / 16) * 16 + pay;
-      };
-      std::vector<size_t> r2 = rem;
-      for (;;) {
-        int best = -1;
-        double bf = -1.0;
-        for (int w = 0; w < kWarps; ++w) {
-          const size_t k = nxt[w] + take[w];
-          if (k >= ws[w].size()) continue;
-          const double f = (double)r2[w] / (double)tot[w];
-          if (f > bf) {
-            bf = f;
-            best = w;
-          }
+      int best = -1;
+      double bf = -1.0;
+      for (int w = 0; w < NW; ++w) {
+        if (nxt[w] >= ws[w].size()) continue;
+        const double f = (double)rem[w] / (double)tot[w];
+        if (f > bf) {
+          bf = f;
+          best = w;
         }
-        if (best < 0) break;
-        const size_t sz = ws[best][nxt[best] + take[best]].size();
-        if (bytes_with(nsl + 1, payload + sz) > room) break;
-        take[best]++;
-        nsl++;
-        payload += sz;
-        r2[best] -= sz;
       }
-      if (nsl == 0) {
-        cs.pad_to_chunk();
-        continue;
-      }
-      ItemHdr ih;
-      std::memset(&ih, 0, sizeof(ih));
-      ih.bytes = (uint32_t)bytes_with(nsl, payload);
-      ih.type = kItemPrivate;
-      ih.count = (uint16_t)nsl;
-      ih.first = (first_item && barrier_before) ? 0u : 1u;
-      ih.level = 0;
-      cs.put(ih);
-      std::vector<uint16_t> dir(kPrivDirBytes / 2, 0);
-      size_t acc = 0;
-      for (int w = 0; w < kWarps; ++w) {
-        dir[w] = (uint16_t)acc;
-        acc += take[w];
-      }
-      dir[kWarps] = (uint16_t)acc;
-      for (uint16_t v : dir) cs.put(v);
-      size_t offb = sizeof(ItemHdr) + kPrivDirBytes + ((nsl * 2 + 15) / 16) * 16;
-      std::vector<uint16_t> offs;
-      for (int w = 0; w < kWarps; ++w)
-        for (size_t k = 0; k < take[w]; ++k) {
-          offs.push_back((uint16_t)(offb / 16));
-          offb += ws[w][nxt[w] + k].size();
-        }
-      while ((offs.size() * 2) % 16) offs.push_back(0);
-      for (uint16_t o : offs) cs.put(o);
-      for (int w = 0; w < kWarps; ++w) {
-        for (size_t k = 0; k < take[w]; ++k) {
-          const auto& b = ws[w][nxt[w] + k];
-          cs.bytes.insert(cs.bytes.end(), b.begin(), b.end());
-        }
-        nxt[w] += take[w];
-      }
-      rem = r2;
-      first_item = false;
+      if (best < 0) break;
+      rem[best] -= ws[best][nxt[best]].size();
+      cb.add_slice(best, std::move(ws[best][nxt[best]]));
+      nxt[best]++;
     }
+    cb.add_barrier();
   };
 
-  if (any_private && private_first) emit_private(false);
+  if (any_private && private_first) emit_private();
   emit_shared();
-  if (any_private && !private_first) emit_private(true);
+  if (any_private && !private_first) emit_private();
+  cb.flush();
   cs.pad_to_chunk();
   chunk1 = (uint32_t)(cs.bytes.size() / kChunkBytes);
 }
@@ -479,6 +466,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   // ---- warp-private subtrees: the bottom of every CTA's own forest, cut into subtrees that are
   // bin-packed onto the consumer warps (wown = warp, or -1 for the "upper" own nodes and the top) ----
   std::vector<int32_t> wown(n, -1);
+  const int NWp = (opt.warps == 16) ? 16 : kWarps;
   if (opt.warp_private && n > 0) {
     std::vector<char> upper(n, 0);
     std::vector<int32_t> wroot(n, -1);
@@ -491,7 +479,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
           total += sub[j];
         }
       if (Qw.empty()) continue;
-      const int64_t target = std::max<int64_t>(total / ((int64_t)kWarps * std::max(1, opt.private_split)), 64);
+      const int64_t target = std::max<int64_t>(total / ((int64_t)NWp * std::max(1, opt.private_split)), 64);
       for (;;) {
         size_t hi = 0;
         for (size_t k = 1; k < Qw.size(); ++k)
@@ -509,11 +497,11 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         if (sub[a] != sub[b]) return sub[a] > sub[b];
         return a < b;
       });
-      std::vector<int64_t> load(kWarps, 0);
+      std::vector<int64_t> load(NWp, 0);
       for (int r : Qw) {
         if (upper[r]) continue;
         int best = 0;
-        for (int w = 1; w < kWarps; ++w)
+        for (int w = 1; w < NWp; ++w)
           if (load[w] < load[best]) best = w;
         load[best] += sub[r];
         wroot[r] = best;

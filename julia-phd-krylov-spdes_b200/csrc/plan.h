@@ -38,46 +38,37 @@ enum Section : int {
 };
 
 // The program of a CTA is ONE byte stream, cut into chunks of kChunkBytes that a producer warp
-// copies into a shared-memory ring with cp.async.bulk (TMA) far ahead of the consumers.  A chunk
-// holds whole items (a zero header terminates it early); every section starts on a chunk boundary.
+// copies into a shared-memory ring with cp.async.bulk (TMA) far ahead of the consumers; every
+// section starts on a chunk boundary.
 //
-// Work is organised in LEVELS of independent rows; an item holds slices of one level.  A slice is
-// the unit of work of one consumer warp: 32 >> tlog2 rows of similar length, T = 1 << tlog2 lanes per
-// row.  Lane (g, t) accumulates entries t, t+T, t+2T, ... of row g (about 16 per lane), the T partial
-// sums are combined with log2(T) butterfly steps and lane t = 0 applies
+// Work is organised in LEVELS of independent rows.  A slice is the unit of work of one consumer warp:
+// 32 >> tlog2 rows of similar length, T = 1 << tlog2 lanes per row.  Lane (g, t) accumulates entries
+// t, t+T, t+2T, ... of row g, the T partial sums are combined with log2(T) butterfly steps and lane
+// t = 0 applies
 //   S[dst] = (S[dst] - sign * sum) * (1/diag)      (kRowFresh: S[dst] = -sign * sum * (1/diag)),
 // optionally storing the result into every other CTA of the cluster too (kRowBcast, top nodes).
 // Entries are stored step-major over the nrows*T active lanes: entry (k, lane) at k*nrows*T + lane,
 // zero-filled where a row has run out (rows of a slice have similar lengths; a padding entry has
-// val 0 and col 0).  Every sum has a fixed association order (bit-reproducible).  One CTA barrier
-// separates levels.
+// val 0 and col 0).  Every sum has a fixed association order (bit-reproducible).
 //
-// Item:  [ItemHdr 16 B][count x uint16 slice offsets (16-byte units from the item start), padded to 16 B][slices]
-// Slice: [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][nent x uint16]  (+ padding to 16 B)
-// Slot i of the item is executed by consumer warp (first + i) % NW (NW = BuildOptions::warps); a slot
-// with offset 0 is empty (the plan balances the warps of a level, see emit_section).
+// WARP PROGRAMS.  A chunk carries, for each of the NW consumer warps (NW = BuildOptions::warps, 8 or
+// 16), a list of 16-bit tokens: the offset of a slice inside the chunk (16-byte units), or kTokBarrier
+// = "the level ends here" (a CTA barrier; in the top sections a barrier over the whole cluster).  A
+// warp only ever reads its own token list, so the per-level control cost is one token per warp
+// instead of a header walk by every warp; the host balances the slices of a level over the warps
+// (longest-processing-time first on a latency estimate).  Every warp's program holds the same
+// sequence of barrier tokens.
+// Chunk:  [kChunkDirBytes: (NW+1) x uint16 first token of every warp][tokens, padded to 16 B][slices]
+// Slice:  [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][nent x uint16]  (+ padding to 16 B)
 //
-// PRIVATE items (kItemPrivate) carry the bottom of the elimination forest: the CTA's own nodes are cut
-// once more into small subtrees that are bin-packed onto the consumer WARPS; a warp walks the rows of
-// its subtrees level by level with only __syncwarp() between its slices, so the many thin levels near
-// the leaves cost no CTA barrier.  Forward sweep: private items first, then the levels of the remaining
-// ("upper") own nodes; backward sweep: upper levels first, then the private items.
-// Private item: [ItemHdr 16 B][(kWarps+1) x uint16 first slice of every warp, padded to 32 B]
-//               [count x uint16 slice offsets, padded to 16 B][slices grouped by warp]
-// `first` == 0 asks for a CTA barrier before the item (values of the upper levels must be complete).
-constexpr uint8_t kItemSlices = 1, kItemPrivate = 2;
-constexpr int kPrivDirBytes = 32;  // bytes reserved for the per-warp slice ranges of a private item
+// Optionally (BuildOptions::warp_private) the bottom of the elimination forest is processed
+// warp-privately: the CTA's own nodes are cut once more into small subtrees that are bin-packed onto
+// the consumer warps; a warp walks the rows of its subtrees level by level with only __syncwarp()
+// between its slices (tokens without barriers).  Forward sweep: private part first, one barrier,
+// then the levels of the remaining ("upper") own nodes; backward sweep: upper levels first.
+constexpr uint16_t kTokBarrier = 0xffffu;
+constexpr int kChunkDirBytes = 48;  // room for (16 + 1) first-token indices, 16-byte aligned
 constexpr int kMaxSlots = 1024;    // scratch doubles used when the top right-hand side is combined
-struct alignas(16) ItemHdr {
-  uint32_t bytes;   // size of the item incl. this header, 0 = end of chunk
-  uint8_t type;
-  uint8_t pad0_;
-  uint16_t count;   // slices in the item
-  uint32_t first;   // index of the item's first slice inside its level (0: a new level starts)
-  uint32_t level;   // dependency level inside the section
-};
-static_assert(sizeof(ItemHdr) == 16, "ItemHdr must be 16 bytes");
-
 struct alignas(16) SliceHdr {
   uint16_t nent;    // stored entries = kmax * nrows * T
   uint16_t kmax;    // steps = ceil(longest row / T)
@@ -143,6 +134,8 @@ struct DomainPlan {
 struct BuildOptions {
   int csize = 1;
   int lane_entries = 16;      // aimed entries per lane of a row
+  int adaptive_lanes = 0;     // 1: per level, entries per lane = level entries / (warps * 32) clamped to [lane_min, lane_max]
+  int lane_min = 4, lane_max = 32;
   double pad_tol = 0.0;       // a slice only takes rows at least pad_tol x its longest row (0: no limit)
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;

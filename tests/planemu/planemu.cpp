@@ -23,149 +23,151 @@ static void to_csc(Csc& m, int nrow, int ncol, const int32_t* cp, const int32_t*
 
 struct Emu {
   const DomainPlan& P;
+  int NW;
   std::vector<std::vector<double>> S;
-  explicit Emu(const DomainPlan& p) : P(p) {
+  long n_barriers = 0, n_slices = 0;
+  Emu(const DomainPlan& p, int nw) : P(p), NW(nw) {
     for (auto& d : P.ctas) S.emplace_back((size_t)d.smem_doubles, 0.0);
   }
-  // Interprets the chunks of one section exactly like the consumer warps (levels of slices).  Checks:
-  // items / slices are well formed, levels are monotone, a value written in a level is not read in
-  // the same level, no destination is written twice in a level.
-  // only_level >= 0: process just the items of that level (top sections run level by level over all CTAs)
-  void section(int c, int sec, double sign, int only_level = -1) {
-    const CtaDesc& D = P.ctas[c];
-    std::vector<double>& s = S[c];
-    // wrote_mark[slot] = marker of the synchronisation interval (level, or private slice) that wrote it
-    std::vector<long> wrote_mark(s.size(), -1);
-    std::vector<int> priv_writer(s.size(), -1);  // warp that writes the slot during the private phase
-    long next_mark = 1 << 20;
-    int cur_level = -1;
-    long cur_mark = -1;
-    uint32_t expect_first = 0;
-    bool seen_private = false, seen_shared = false;
-    // pre-pass: who writes what during the private phase
-    for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
-      const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
-      size_t off = 0;
-      while (off + sizeof(ItemHdr) <= (size_t)kChunkBytes) {
-        ItemHdr h;
-        std::memcpy(&h, base + off, sizeof(h));
-        if (h.bytes == 0) break;
-        if (off + h.bytes > (size_t)kChunkBytes) throw std::runtime_error("item crosses its chunk");
-        if (h.type == kItemPrivate) {
-          const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
-          const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr) + kPrivDirBytes);
-          if (wb[0] != 0 || wb[kWarps] != h.count) throw std::runtime_error("private directory broken");
-          for (int w = 0; w < kWarps; ++w) {
-            if (wb[w] > wb[w + 1]) throw std::runtime_error("private directory not monotone");
-            for (uint32_t i = wb[w]; i < wb[w + 1]; ++i) {
-              const uint8_t* sl = base + off + (size_t)offs[i] * 16;
-              SliceHdr sh;
-              std::memcpy(&sh, sl, sizeof(sh));
-              const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
-              for (int g = 0; g < sh.nrows; ++g) {
-                if (rr[g].dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
-                if (priv_writer[rr[g].dst] >= 0 && priv_writer[rr[g].dst] != w)
-                  throw std::runtime_error("two warps write the same slot in the private phase");
-                priv_writer[rr[g].dst] = w;
-              }
-            }
-          }
-        }
-        off += h.bytes;
+  // position of one consumer warp in its program
+  struct Cursor {
+    uint32_t ch, tok, end;   // chunk, next token, one past the warp's last token in the chunk
+    bool done;
+  };
+  // Runs one section on the CTAs `ctas` in lock-step, exactly like the consumer warps: every warp walks its
+  // own token list chunk by chunk; a barrier token ends an EPOCH (CTA barrier, or cluster barrier when the
+  // section runs on several CTAs).  Checks: chunks / slices well formed; all warps (and CTAs) see the same
+  // number of barriers; inside an epoch no slot is written by two warps, no warp reads a slot another
+  // warp writes, and a slice does not read what it writes (same-warp slices are ordered by __syncwarp).
+  void section(const std::vector<int>& ctas, int sec, double sign) {
+    const size_t nc = ctas.size();
+    std::vector<std::vector<Cursor>> cur(nc, std::vector<Cursor>(NW));
+    auto chunk_ptr = [&](int c, uint32_t ch) { return P.stream.data() + P.ctas[c].stream_off + (size_t)ch * kChunkBytes; };
+    auto enter_chunk = [&](int c, int w, Cursor& k) {
+      const CtaDesc& D = P.ctas[c];
+      for (; k.ch < D.sec_chunk1[sec]; ++k.ch) {
+        const uint16_t* dir = reinterpret_cast<const uint16_t*>(chunk_ptr(c, k.ch));
+        if (dir[0] != 0) throw std::runtime_error("chunk directory does not start at 0");
+        for (int v = 0; v < NW; ++v)
+          if (dir[v] > dir[v + 1]) throw std::runtime_error("chunk directory not monotone");
+        if ((size_t)kChunkDirBytes + (size_t)dir[NW] * 2 > (size_t)kChunkBytes) throw std::runtime_error("token table too large");
+        k.tok = dir[w];
+        k.end = dir[w + 1];
+        if (k.tok < k.end) return;
       }
-    }
-    // one slice, interpreted like process_slice on the device; warp >= 0: private phase
-    auto run_slice = [&](const uint8_t* item, const ItemHdr& h, const uint8_t* sl, int warp) {
-      SliceHdr sh;
-      std::memcpy(&sh, sl, sizeof(sh));
-      const int T = 1 << sh.tlog2;
-      if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
-      const RowRec* rr = reinterpret_cast<const RowRec*>(sl + sizeof(SliceHdr));
-      const double* vals = reinterpret_cast<const double*>(sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
-      const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
-      if ((size_t)(reinterpret_cast<const uint8_t*>(cols + sh.nent) - item) > h.bytes) throw std::runtime_error("slice exceeds its item");
-      std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
-      const uint32_t Wact = (uint32_t)sh.nrows * T;
-      if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
-      for (uint32_t k = 0; k < sh.kmax; ++k)
-        for (uint32_t lane = 0; lane < Wact; ++lane) {
-          const int g = lane / T, t = lane % T;
-          const uint32_t pos = k * Wact + lane;
-          const uint32_t col = cols[pos];
-          if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
-          if (k * T + t < rr[g].len) {
-            if (wrote_mark[col] == cur_mark) throw std::runtime_error("reads a value produced in the same level");
-            if (warp >= 0 && priv_writer[col] >= 0 && priv_writer[col] != warp)
-              throw std::runtime_error("private row reads a slot another warp writes in the private phase");
-          } else if (vals[pos] != 0.0) {
-            throw std::runtime_error("non-zero padding entry");
-          }
-          part[lane][k & 3] += vals[pos] * s[col];
-        }
-      for (int g = 0; g < sh.nrows; ++g) {
-        if ((rr[g].len + T - 1) / T > sh.kmax) throw std::runtime_error("kmax too small");
-        double sum = 0.0;
-        for (int t = 0; t < T; ++t) sum += (part[g * T + t][0] + part[g * T + t][1]) + (part[g * T + t][2] + part[g * T + t][3]);
-        const int dst = rr[g].dst;
-        if (dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
-        if (wrote_mark[dst] == cur_mark) throw std::runtime_error("destination written twice in a level");
-        if (warp < 0 && false) throw std::runtime_error("unreachable");
-        const bool fresh = (rr[g].flags & kRowFresh) != 0;
-        s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) * rr[g].diag;  // reciprocal stored
-        wrote_mark[dst] = cur_mark;
-        if (rr[g].flags & kRowBcast) {
-          if (warp >= 0) throw std::runtime_error("broadcast row in the private phase");
-          for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
-        }
-      }
+      k.done = true;
     };
-    for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
-      const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
-      size_t off = 0;
-      while (off + sizeof(ItemHdr) <= (size_t)kChunkBytes) {
-        ItemHdr h;
-        std::memcpy(&h, base + off, sizeof(h));
-        if (h.bytes == 0) break;
-        if (h.type == kItemPrivate) {
-          if (only_level >= 0) throw std::runtime_error("private item in a top section");
-          if (!seen_private && seen_shared && h.first != 0) throw std::runtime_error("private phase after shared levels lacks its barrier");
-          if (seen_private && h.first == 0) throw std::runtime_error("barrier inside the private phase");
-          seen_private = true;
-          const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
-          const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr) + kPrivDirBytes);
-          for (int w = 0; w < kWarps; ++w)
-            for (uint32_t i = wb[w]; i < wb[w + 1]; ++i) {
-              cur_mark = next_mark++;  // __syncwarp() separates the slices of a warp
-              run_slice(base + off, h, base + off + (size_t)offs[i] * 16, w);
-            }
-          off += h.bytes;
-          continue;
-        }
-        if (h.type != kItemSlices) throw std::runtime_error("unknown item type");
-        if (seen_private && !seen_shared && cur_level != -1) throw std::runtime_error("internal emulator state");
-        seen_shared = true;
-        if (h.level >= D.sec_nlevels[sec]) throw std::runtime_error("level beyond nlevels");
-        if ((int)h.level < cur_level) throw std::runtime_error("levels not monotone in the stream");
-        if ((int)h.level > cur_level) {
-          if (h.first != 0) throw std::runtime_error("level does not start with first == 0");
-          cur_level = (int)h.level;
-          expect_first = 0;
-        }
-        if (h.first != expect_first) throw std::runtime_error("slice numbering broken");
-        expect_first += h.count;
-        if (only_level >= 0 && (int)h.level != only_level) { off += h.bytes; continue; }
-        cur_mark = cur_level;
-        const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + sizeof(ItemHdr));
-        for (uint32_t i = 0; i < h.count; ++i)
-          if (offs[i] != 0) run_slice(base + off, h, base + off + (size_t)offs[i] * 16, -1);  // 0: empty slot
-        off += h.bytes;
+    for (size_t i = 0; i < nc; ++i)
+      for (int w = 0; w < NW; ++w) {
+        cur[i][w] = Cursor{P.ctas[ctas[i]].sec_chunk0[sec], 0, 0, false};
+        enter_chunk(ctas[i], w, cur[i][w]);
       }
-    }
-    if (seen_private && seen_shared) {
-      // shared levels after the private phase start with first == 0 (checked above through cur_level);
-      // nothing else to verify here
+    struct Todo { size_t ci; int w; const uint8_t* chunk; const uint8_t* sl; };
+    for (;;) {
+      // gather the slices of this epoch, warp by warp
+      std::vector<Todo> todo;
+      int at_barrier = 0, finished = 0;
+      for (size_t i = 0; i < nc; ++i)
+        for (int w = 0; w < NW; ++w) {
+          Cursor& k = cur[i][w];
+          bool hit = false;
+          while (!k.done && !hit) {
+            const uint8_t* chunk = chunk_ptr(ctas[i], k.ch);
+            const uint16_t* tok = reinterpret_cast<const uint16_t*>(chunk + kChunkDirBytes);
+            const uint16_t t = tok[k.tok++];
+            if (t == kTokBarrier) hit = true;
+            else {
+              if ((size_t)t * 16 < (size_t)kChunkDirBytes || (size_t)t * 16 + 32 > (size_t)kChunkBytes) throw std::runtime_error("slice offset out of range");
+              todo.push_back(Todo{i, w, chunk, chunk + (size_t)t * 16});
+            }
+            if (k.tok >= k.end) {
+              ++k.ch;
+              enter_chunk(ctas[i], w, k);
+            }
+          }
+          if (hit) ++at_barrier;
+          else ++finished;
+        }
+      if (at_barrier != 0 && finished != 0) throw std::runtime_error("warps disagree on the number of barriers");
+      // writers of the epoch
+      std::vector<std::vector<int>> writer(P.ctas.size());
+      for (size_t c = 0; c < P.ctas.size(); ++c) writer[c].assign(S[c].size(), -1);
+      auto wid = [&](const Todo& t) { return (int)(t.ci * NW + t.w); };
+      for (const Todo& t : todo) {
+        const CtaDesc& D = P.ctas[ctas[t.ci]];
+        SliceHdr sh;
+        std::memcpy(&sh, t.sl, sizeof(sh));
+        const int T = 1 << sh.tlog2;
+        if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
+        const size_t bytes = sizeof(SliceHdr) + (size_t)sh.nrows * sizeof(RowRec) + (size_t)sh.nent * 10;
+        if ((size_t)(t.sl - t.chunk) + bytes > (size_t)kChunkBytes) throw std::runtime_error("slice exceeds its chunk");
+        const RowRec* rr = reinterpret_cast<const RowRec*>(t.sl + sizeof(SliceHdr));
+        for (int g = 0; g < sh.nrows; ++g) {
+          if (rr[g].dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
+          auto claim = [&](int c) {
+            if (writer[c][rr[g].dst] >= 0 && writer[c][rr[g].dst] != wid(t))
+              throw std::runtime_error("two warps write the same slot between barriers");
+            writer[c][rr[g].dst] = wid(t);
+          };
+          claim(ctas[t.ci]);
+          if (rr[g].flags & kRowBcast) {
+            if (nc == 1 && P.ctas.size() > 1) throw std::runtime_error("broadcast row outside a cluster-wide section");
+            for (size_t c2 = 0; c2 < P.ctas.size(); ++c2)
+              if ((int)c2 != ctas[t.ci]) claim((int)c2);
+          }
+        }
+      }
+      // execute
+      for (const Todo& t : todo) {
+        const int c = ctas[t.ci];
+        const CtaDesc& D = P.ctas[c];
+        std::vector<double>& s = S[c];
+        SliceHdr sh;
+        std::memcpy(&sh, t.sl, sizeof(sh));
+        const int T = 1 << sh.tlog2;
+        const RowRec* rr = reinterpret_cast<const RowRec*>(t.sl + sizeof(SliceHdr));
+        const double* vals = reinterpret_cast<const double*>(t.sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
+        const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
+        std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
+        const uint32_t Wact = (uint32_t)sh.nrows * T;
+        if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
+        std::vector<char> mine_dst(s.size(), 0);
+        for (int g = 0; g < sh.nrows; ++g) {
+          if (mine_dst[rr[g].dst]) throw std::runtime_error("destination written twice in a slice");
+          mine_dst[rr[g].dst] = 1;
+        }
+        for (uint32_t k = 0; k < sh.kmax; ++k)
+          for (uint32_t lane = 0; lane < Wact; ++lane) {
+            const int g = lane / T, tt = lane % T;
+            const uint32_t pos = k * Wact + lane;
+            const uint32_t col = cols[pos];
+            if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
+            if (k * T + tt < rr[g].len) {
+              if (mine_dst[col]) throw std::runtime_error("a slice reads a value it produces");
+              if (writer[c][col] >= 0 && writer[c][col] != wid(t))
+                throw std::runtime_error("reads a slot another warp writes before the next barrier");
+            } else if (vals[pos] != 0.0) {
+              throw std::runtime_error("non-zero padding entry");
+            }
+            part[lane][k & 3] += vals[pos] * s[col];
+          }
+        for (int g = 0; g < sh.nrows; ++g) {
+          if ((rr[g].len + T - 1) / T > sh.kmax) throw std::runtime_error("kmax too small");
+          double sum = 0.0;
+          for (int tt = 0; tt < T; ++tt) sum += (part[g * T + tt][0] + part[g * T + tt][1]) + (part[g * T + tt][2] + part[g * T + tt][3]);
+          const int dst = rr[g].dst;
+          const bool fresh = (rr[g].flags & kRowFresh) != 0;
+          s[dst] = ((fresh ? 0.0 : s[dst]) - sign * sum) * rr[g].diag;  // reciprocal stored
+          if (rr[g].flags & kRowBcast)
+            for (size_t c2 = 0; c2 < S.size(); ++c2) S[c2][dst] = s[dst];
+        }
+        ++n_slices;
+      }
+      if (at_barrier == 0) break;
+      ++n_barriers;
     }
   }
+  void section(int c, int sec, double sign) { section(std::vector<int>{c}, sec, sign); }
 };
 
 extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t* Lp, const int32_t* Li,
@@ -184,11 +186,13 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     opt.csize = csize;
     if (const char* e = std::getenv("KB200_MIN_BLOCK")) opt.min_block = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARPS")) opt.warps = std::atoi(e);
+    if (const char* e = std::getenv("KB200_ADAPTIVE_LANES")) opt.adaptive_lanes = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARP_PRIVATE")) opt.warp_private = std::atoi(e);
     if (const char* e = std::getenv("KB200_PRIVATE_SPLIT")) opt.private_split = std::atoi(e);
     DomainPlan P;
     build_domain_plan(in, opt, P);
-    Emu E(P);
+    const int NW = (opt.warps == 16) ? 16 : kWarps;
+    Emu E(P, NW);
     const int C = csize;
     const CtaDesc& D0 = P.ctas[0];
     for (int c = 0; c < C; ++c) {
@@ -217,12 +221,10 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       }
       for (int c = 0; c < C; ++c)
         for (int t = 0; t < D0.n_top; ++t) E.S[c][P.ctas[c].top_off + t] = comb[t];
-      for (int sec : {SEC_TOPF, SEC_TOPB}) {
-        for (int c = 1; c < C; ++c)
-          if (P.ctas[c].sec_nlevels[sec] != D0.sec_nlevels[sec]) throw std::runtime_error("top level counts differ across CTAs");
-        for (uint32_t lev = 0; lev < D0.sec_nlevels[sec]; ++lev)
-          for (int c = 0; c < C; ++c) E.section(c, sec, 1.0, (int)lev);
-      }
+      std::vector<int> all;
+      for (int c = 0; c < C; ++c) all.push_back(c);
+      E.section(all, SEC_TOPF, 1.0);
+      E.section(all, SEC_TOPB, 1.0);
     }
     for (int c = 0; c < C; ++c) {
       E.section(c, SEC_BWD, 1.0);
@@ -257,38 +259,8 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       stats[11] = (double)P.lane_steps;
       stats[12] = (double)P.n_private_rows;
       stats[13] = (double)P.n_private_slices;
-      if (std::getenv("EMU_LEVELS")) {
-        for (int sec : {SEC_FWD, SEC_BWD, SEC_TOPF, SEC_TOPB}) {
-          const CtaDesc& D = P.ctas[C > 1 ? 1 : 0];
-          std::vector<long> ent(D.sec_nlevels[sec], 0), nsl(D.sec_nlevels[sec], 0), nrw(D.sec_nlevels[sec], 0);
-          for (uint32_t ch = D.sec_chunk0[sec]; ch < D.sec_chunk1[sec]; ++ch) {
-            const uint8_t* base = P.stream.data() + D.stream_off + (size_t)ch * kChunkBytes;
-            size_t off = 0;
-            while (off + 16 <= (size_t)kChunkBytes) {
-              ItemHdr h; std::memcpy(&h, base + off, 16);
-              if (!h.bytes) break;
-              if (h.type == kItemPrivate) {
-                const uint16_t* wb = reinterpret_cast<const uint16_t*>(base + off + 16);
-                std::fprintf(stderr, " {private item: %u slices, per warp", (unsigned)h.count);
-                for (int w = 0; w < kWarps; ++w) std::fprintf(stderr, " %d", wb[w + 1] - wb[w]);
-                std::fprintf(stderr, "}");
-                off += h.bytes;
-                continue;
-              }
-              const uint16_t* offs = reinterpret_cast<const uint16_t*>(base + off + 16);
-              for (uint32_t i = 0; i < h.count; ++i) {
-                if (!offs[i]) continue;
-                SliceHdr sh; std::memcpy(&sh, base + off + (size_t)offs[i] * 16, 16);
-                ent[h.level] += sh.nent; nsl[h.level] += 1; nrw[h.level] += sh.nrows;
-              }
-              off += h.bytes;
-            }
-          }
-          std::fprintf(stderr, "sec %d levels %zu:", sec, ent.size());
-          for (size_t l = 0; l < ent.size(); ++l) std::fprintf(stderr, " [%zu: %ld ent %ld sl %ld rows]", l, ent[l], nsl[l], nrw[l]);
-          std::fprintf(stderr, "\n");
-        }
-      }
+      stats[14] = (double)E.n_barriers;
+      stats[15] = (double)E.n_slices;
       stats[9] = (double)std::max(D0.sec_nlevels[SEC_TOPF], D0.sec_nlevels[SEC_TOPB]);
       stats[10] = (double)std::max(D0.sec_nlevels[SEC_FWD], D0.sec_nlevels[SEC_BWD]);
 
