@@ -157,34 +157,32 @@ __device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
   cx.lvl_phase ^= 1u;
 }
 
-// One slice (see plan.h): T lanes per row, entries compacted per step.
+// One slice (see plan.h): T lanes per row, entries compacted per step.  Written for a short
+// instruction stream -- at ~270 entries per slice the fixed part (header decode, tail, butterfly,
+// row update) weighs as much as the entry loop: everything the header can precompute is precomputed
+// on the host, the row record and the old destination value are fetched before the loop, the loop is
+// kept at 4 steps per trip (no wide unrolling with its set-up code) and the tail is 2 + 1 steps.
 template <bool kTop>
 __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, double sign) {
   double* S = cx.S;
   const int lane = cx.lane;
   const uint4 hq = *reinterpret_cast<const uint4*>(sl);
-  const uint32_t nent = hq.x & 0xffffu, kmax = hq.x >> 16;
+  const int kmax = (int)(hq.x >> 16);
   const int tl = (int)(hq.y & 0xffu), nrows = (int)((hq.y >> 8) & 0xffu);
-  const int T = 1 << tl;
-  const int g = lane >> tl, t = lane & (T - 1);
-  uint32_t dst = 0, flags = 0;
-  double dg = 1.0;
-  if (g < nrows) {
-    const uint4 q = *reinterpret_cast<const uint4*>(sl + 16 + 16 * g);
-    dst = q.x >> 16;
-    flags = q.y & 0xffffu;
-    dg = __hiloint2double((int)q.w, (int)q.z);
-  }
-  const double* v = reinterpret_cast<const double*>(sl + 16 + 16 * nrows);
-  const uint16_t* c = reinterpret_cast<const uint16_t*>(v + nent);
-  // entry (k, lane) at k * W + lane, W = nrows * T active lanes; padding entries are (0.0, col 0)
-  const int W = nrows << tl;
+  const int W = (int)hq.z;                       // nrows << tl active lanes
+  const int g = min(lane >> tl, nrows - 1);      // row of this lane (clamped: idle lanes read a valid record)
+  const bool writer = lane < W && (lane & ((1 << tl) - 1)) == 0;
+  const uint4 q = *reinterpret_cast<const uint4*>(sl + 16 + 16 * g);
+  const uint32_t dst = q.x >> 16, flags = q.y & 0xffffu;
+  const double old = (flags & kRowFresh) ? 0.0 : S[dst];
+  // entry (k, lane) at k * W + lane; padding entries are (0.0, col 0)
+  const double* vp = reinterpret_cast<const double*>(sl + 16 + 16 * nrows) + lane;
+  const uint16_t* cp = reinterpret_cast<const uint16_t*>(sl + hq.w) + lane;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (lane < W) {
-    const double* vp = v + lane;
-    const uint16_t* cp = c + lane;
-    int k = 0;
-    for (; k + 4 <= (int)kmax; k += 4) {
+    int k = kmax;
+#pragma unroll 1
+    for (; k >= 4; k -= 4) {
       const double v0 = vp[0], v1 = vp[W], v2 = vp[2 * W], v3 = vp[3 * W];
       const uint32_t c0 = cp[0], c1 = cp[W], c2 = cp[2 * W], c3 = cp[3 * W];
       a0 = fma(v0, S[c0], a0);
@@ -194,15 +192,30 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
       vp += 4 * W;
       cp += 4 * W;
     }
-    // keep the association of the unrolled loop: step k feeds accumulator k & 3
-    if (k < (int)kmax) { a0 = fma(vp[0], S[cp[0]], a0); }
-    if (k + 1 < (int)kmax) { a1 = fma(vp[W], S[cp[W]], a1); }
-    if (k + 2 < (int)kmax) { a2 = fma(vp[2 * W], S[cp[2 * W]], a2); }
+    // association of the sums: step j feeds accumulator j & 3 (the emulator follows the same rule)
+    if (k & 2) {
+      const double v0 = vp[0], v1 = vp[W];
+      const uint32_t c0 = cp[0], c1 = cp[W];
+      a0 = fma(v0, S[c0], a0);
+      a1 = fma(v1, S[c1], a1);
+      vp += 2 * W;
+      cp += 2 * W;
+    }
+    if (k & 1) {
+      const double v0 = vp[0], s0 = S[cp[0]];
+      if (k & 2) a2 = fma(v0, s0, a2);
+      else a0 = fma(v0, s0, a0);
+    }
   }
   double acc = (a0 + a1) + (a2 + a3);
-  for (int d = 1; d < T; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  if (g < nrows && t == 0) {
-    const double r = (((flags & kRowFresh) ? 0.0 : S[dst]) - sign * acc) * dg;  // dg = 1 / diag
+  if (tl >= 1) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (tl >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (tl >= 3) acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (tl >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  if (tl >= 5) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  if (writer) {
+    const double dg = __hiloint2double((int)q.w, (int)q.z);  // 1 / diag
+    const double r = (old - sign * acc) * dg;
     S[dst] = r;
     if (kTop && (flags & kRowBcast)) {
       for (int cc = 0; cc < cx.D->csize; ++cc)

@@ -89,6 +89,8 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
   sh.kmax = (uint16_t)kmax;
   sh.tlog2 = (uint8_t)ilog2(T);
   sh.nrows = (uint8_t)nr;
+  sh.width = (uint32_t)(nr * T);
+  sh.cols_off = (uint32_t)(sizeof(SliceHdr) + (size_t)nr * sizeof(RowRec) + pv.size() * 8);
   put(&sh, sizeof(sh));
   for (int g = 0; g < nr; ++g) {
     const TmpRow& tr = rows[ord[p + g]];

@@ -75,7 +75,8 @@ struct alignas(16) SliceHdr {
   uint8_t tlog2;
   uint8_t nrows;
   uint16_t pad0_;
-  uint32_t pad1_[2];
+  uint32_t width;     // active lanes = nrows << tlog2 (precomputed for the device)
+  uint32_t cols_off;  // byte offset of the uint16 column indices from the slice start
 };
 static_assert(sizeof(SliceHdr) == 16, "SliceHdr must be 16 bytes");
 
