@@ -112,7 +112,7 @@ struct kb200_ctx {
   ncclComm_t comm = nullptr;
 #endif
   // options
-  int csize = 0, profile = 0, check_every = 8, min_block = -1, stages = 0, lane_entries = 0, pad_tol_pct = -1;
+  int csize = 0, profile = 0, check_every = 32, min_block = -1, stages = 0, lane_entries = 0, pad_tol_pct = -1;
   int warp_private = -1, private_split = 0;
   int adaptive_lanes = -1, lane_min = 0, lane_max = 0;
   int warps = 0;  // consumer warps per CTA of the stream kernel: 8 or 16 (0: automatic)
@@ -124,6 +124,9 @@ struct kb200_ctx {
   size_t xch_flags_off = 0;
   int xch_npad = 0;
   uint32_t xch_seq = 0;
+  int fuse_pcg = 1;                 // option: plain PCG runs its vector steps inside the assembly kernels
+  DevBuf<unsigned int> d_gsync;     // grid-wide arrival counter of the fused kernels
+  unsigned int gsync_launches = 0;
   // topology
   int64_t ndom = 0, n_gamma = 0;
   std::vector<DomHost> doms;
@@ -364,6 +367,9 @@ void finalize(Ctx* c) {
   c->d_partC.alloc(c->nb);
   c->d_state.alloc(1);
   CUDA_TRY(cudaMemsetAsync(c->d_state.p, 0, sizeof(kb::PcgState), s));
+  c->d_gsync.alloc(1);
+  CUDA_TRY(cudaMemsetAsync(c->d_gsync.p, 0, sizeof(unsigned int), s));
+  c->gsync_launches = 0;
   // kernel attributes: the dynamic shared-memory limit of a kernel is process-wide state, so always
   // raise it to the device maximum instead of this handle's own requirement
   int smem_optin = 0;
@@ -560,6 +566,24 @@ void allreduce(Ctx* c, double* v, int64_t n) {
 #endif
 }
 
+// Parameters of the next peer-memory exchange (sequence number / slot advance on every call; all ranks
+// issue the same sequence of exchanges).
+kb::XchParams next_exchange(Ctx* c) {
+  kb::XchParams X;
+  std::memset(&X, 0, sizeof(X));
+  for (int r = 0; r < c->world; ++r) {
+    X.data[r] = reinterpret_cast<double*>(c->xch_peer[r]);
+    X.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->xch_peer[r]) + c->xch_flags_off);
+  }
+  X.world = c->world;
+  X.rank = c->rank;
+  X.seq = ++c->xch_seq;
+  X.slot = (int)(X.seq & 1u);
+  X.n_pad = c->xch_npad;
+  X.fail = &c->d_state.p->fail;
+  return X;
+}
+
 // y = sum_d R_d' loc_d (+ base), optionally partial dot with q.  In multi-rank mode the interface
 // vector is all-reduced and the dot is taken afterwards so that every rank sees identical scalars.
 void assemble(Ctx* c, const double* loc, const double* base, double* y, const double* q, double* part,
@@ -574,18 +598,7 @@ void assemble(Ctx* c, const double* loc, const double* base, double* y, const do
   }
   if (c->peer_ok) {
     // fused: assemble the local partial, exchange it over NVLink peer memory, sum, partial dot
-    kb::XchParams X;
-    std::memset(&X, 0, sizeof(X));
-    for (int r = 0; r < c->world; ++r) {
-      X.data[r] = reinterpret_cast<double*>(c->xch_peer[r]);
-      X.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->xch_peer[r]) + c->xch_flags_off);
-    }
-    X.world = c->world;
-    X.rank = c->rank;
-    X.seq = ++c->xch_seq;
-    X.slot = (int)(X.seq & 1u);
-    X.n_pad = c->xch_npad;
-    X.fail = &c->d_state.p->fail;
+    const kb::XchParams X = next_exchange(c);
     kb::assemble_exchange_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
                                                                           c->rank == 0 ? base : nullptr, y, q, part,
                                                                           done_at, iter, X);
@@ -811,6 +824,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "adaptive_lanes" || k == "lane_min" || k == "lane_max") {
       require(!h->finalized && value >= 0 && value <= 256, "lane options must be set before the first operation");
       (k == "adaptive_lanes" ? h->adaptive_lanes : k == "lane_min" ? h->lane_min : h->lane_max) = (int)value;
+    } else if (k == "fuse_pcg") {
+      require(value == 0 || value == 1, "fuse_pcg is 0 or 1");
+      h->fuse_pcg = (int)value;
     } else if (k == "peer_exchange") {
       require(!h->finalized && (value == 0 || value == 1), "peer_exchange is 0 or 1, before the first operation");
       h->peer_exchange = (int)value;
@@ -1161,6 +1177,37 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   bool done = false;
   while (!done) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
+    const bool fused = c->fuse_pcg && precond && defl == nullptr && (!c->has_comm || c->peer_ok);
+    for (; fused && k < kend; ++k) {
+      // four launches per iteration: local operator, assembly (+exchange) fused with the vector update
+      const bool timed = c->profile != 0;
+      cudaEvent_t ev = nullptr;
+      if (timed) kt.begin(0, ev);
+      if (A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, done_at, k);
+      else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, done_at, k);
+      if (timed) kt.end(0, ev);
+      const unsigned int nbk = (unsigned int)c->nb;
+      if (c->peer_ok)
+        kb::pcg_fused_xr_kernel<true><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
+            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
+            c->d_partB.p, st, k, c->d_gsync.p, ++c->gsync_launches * nbk, next_exchange(c));
+      else
+        kb::pcg_fused_xr_kernel<false><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
+            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
+            c->d_partB.p, st, k, c->d_gsync.p, ++c->gsync_launches * nbk, kb::XchParams());
+      if (timed) kt.begin(1, ev);
+      launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, done_at, k);
+      if (timed) kt.end(1, ev);
+      if (c->peer_ok)
+        kb::pcg_fused_p_kernel<true><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
+            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_z.p, c->d_r.p, c->d_p.p, c->d_partB.p, c->d_partC.p, st,
+            c->d_res.p, nullptr, k, c->d_gsync.p, ++c->gsync_launches * nbk, next_exchange(c));
+      else
+        kb::pcg_fused_p_kernel<false><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
+            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_z.p, c->d_r.p, c->d_p.p, c->d_partB.p, c->d_partC.p, st,
+            c->d_res.p, nullptr, k, c->d_gsync.p, ++c->gsync_launches * nbk, kb::XchParams());
+      c->launches += 2;
+    }
     for (; k < kend; ++k) {
       apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);    // Ap = A p ; d = p.Ap
       kb::pcg_update_xr_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p, c->d_r.p,

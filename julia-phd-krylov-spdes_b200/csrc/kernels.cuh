@@ -589,19 +589,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kVecThreads)
-assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
-                         double* y, const double* q, double* part, const int* done_at, int iter, const XchParams X) {
-  __shared__ double red[8];
-  if (done_at != nullptr && *done_at < iter) return;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// Exchange step of one block (all threads must call): push the rank's partial `a` of entry g to every
+// rank, publish / await the per-block flags, return the sum of the `world` partials in rank order.
+__device__ __forceinline__ double exchange_sum(double a, int g, int n, const XchParams& X) {
   const int nb = gridDim.x;
-  // partial of this rank (ascending local subdomain order; rank 0 carries `base`)
-  double a = 0.0;
-  if (g < n) {
-    a = (base != nullptr) ? base[g] : 0.0;
-    for (int k = adj_ptr[g]; k < adj_ptr[g + 1]; ++k) a += loc[adj_src[k]];
-  }
   const size_t seg = ((size_t)X.slot * X.world + X.rank) * (size_t)X.n_pad + (size_t)g;
   for (int r = 0; r < X.world; ++r) __stcg(X.data[r] + seg, a);
   __syncthreads();
@@ -620,10 +611,34 @@ assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, 
     }
   }
   __syncthreads();
-  double sum = 0.0, prod = 0.0;
+  double sum = 0.0;
   if (g < n) {
     const double* mine = X.data[X.rank] + (size_t)X.slot * X.world * (size_t)X.n_pad + (size_t)g;
     for (int r = 0; r < X.world; ++r) sum += __ldcg(mine + (size_t)r * X.n_pad);
+  }
+  return sum;
+}
+
+// local partial of interface entry g: contributions of the local subdomains in ascending order (+ base)
+__device__ __forceinline__ double assemble_local(int g, int n, const int32_t* adj_ptr, const int32_t* adj_src,
+                                                 const double* loc, const double* base) {
+  double a = 0.0;
+  if (g < n) {
+    a = (base != nullptr) ? base[g] : 0.0;
+    for (int k = adj_ptr[g]; k < adj_ptr[g + 1]; ++k) a += loc[adj_src[k]];
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
+                         double* y, const double* q, double* part, const int* done_at, int iter, const XchParams X) {
+  __shared__ double red[8];
+  if (done_at != nullptr && *done_at < iter) return;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const double sum = exchange_sum(assemble_local(g, n, adj_ptr, adj_src, loc, base), g, n, X);
+  double prod = 0.0;
+  if (g < n) {
     y[g] = sum;
     if (q != nullptr) prod = sum * q[g];
   }
@@ -747,6 +762,124 @@ pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* par
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused PCG steps (plain preconditioned CG, cg.jl:93-105): the interface assembly (with the peer
+// exchange when kX), the dot product that needs it, and the vector update that needs the dot run in
+// ONE kernel -- a grid-wide arrival counter separates "every block has written its partial" from
+// "every block sums the partials" (all blocks of these small grids are co-resident).  Four launches
+// per iteration instead of six: stream kernel, fused_xr, dense GEMV, fused_p.
+// ---------------------------------------------------------------------------------------------
+// Arrive on the grid counter and wait until `target` arrivals have been counted (counter is monotone:
+// target = launches so far x blocks).  Kernels skipped after convergence still arrive (grid_skip).
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void grid_skip(unsigned int* counter) {
+  if (threadIdx.x == 0) atomicAdd(counter, 1u);
+}
+// fixed-order sum of per-block partials written by other blocks of this launch (read through L2)
+__device__ __forceinline__ double sum_partials_cg(const double* part, int nb, double* red) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) v += __ldcg(part + i);
+  return block_reduce_sum(v, red);
+}
+
+// Ap = sum_d R_d' loc_d ; d = p.Ap ; alpha = rTz / d ; x += alpha p ; r -= alpha Ap ; partB <- r.r
+template <bool kX>
+__global__ void __launch_bounds__(kVecThreads)
+pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, double* Ap, const double* p,
+                    double* x, double* r, double* partA, double* partB, PcgState* st, int iter, unsigned int* counter,
+                    unsigned int target, const XchParams X) {
+  __shared__ double red[8];
+  if (st->done_at < iter) {
+    grid_skip(counter);
+    return;
+  }
+  const int nb = gridDim.x;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
+  if (kX) a = exchange_sum(a, g, n, X);
+  double pv = 0.0;
+  if (g < n) {
+    Ap[g] = a;
+    pv = p[g];
+  }
+  const double s = block_reduce_sum(a * pv, red);
+  if (threadIdx.x == 0) partA[blockIdx.x] = s;
+  grid_arrive_wait(counter, target);
+  const double d = sum_partials_cg(partA, nb, red);
+  const double rTz = st->rTz;
+  const double alpha = rTz / d;
+  double rr = 0.0;
+  if (g < n) {
+    x[g] = fma(alpha, pv, x[g]);
+    const double rv = fma(-alpha, a, r[g]);
+    r[g] = rv;
+    rr = rv * rv;
+  }
+  const double s2 = block_reduce_sum(rr, red);
+  if (threadIdx.x == 0) {
+    partB[blockIdx.x] = s2;
+    if (blockIdx.x == 0) {
+      st->d = d;
+      st->alpha = alpha;
+      st->rTz_old = rTz;
+      if (!(d > 0.0)) st->fail = 1;  // operator not SPD along p: reported, not asserted
+    }
+  }
+}
+
+// z = sum_d R_d' loc_d ; rTz' = r.z ; beta = rTz' / rTz ; p = beta p + z ; it += 1 ; res_norm[it] = sqrt(r.r)
+template <bool kX>
+__global__ void __launch_bounds__(kVecThreads)
+pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, double* z, const double* r,
+                   double* p, const double* partB, double* partC, PcgState* st, double* res_norm, double* vcol, int iter,
+                   unsigned int* counter, unsigned int target, const XchParams X) {
+  __shared__ double red[8];
+  if (st->done_at < iter) {
+    grid_skip(counter);
+    return;
+  }
+  const int nb = gridDim.x;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
+  if (kX) a = exchange_sum(a, g, n, X);
+  double rv = 0.0;
+  if (g < n) {
+    z[g] = a;
+    rv = r[g];
+  }
+  const double s = block_reduce_sum(a * rv, red);
+  if (threadIdx.x == 0) partC[blockIdx.x] = s;
+  grid_arrive_wait(counter, target);
+  const double rTz_new = sum_partials_cg(partC, nb, red);
+  const double rTr = sum_partials_cg(partB, nb, red);
+  double beta = 1.0 / st->rTz_old;
+  beta *= rTz_new;
+  if (g < n) {
+    p[g] = fma(beta, p[g], a);
+    if (vcol != nullptr) vcol[g] = a / sqrt(rTz_new);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int it = st->it + 1;
+    st->it = it;
+    st->rTr = rTr;
+    st->rTz = rTz_new;
+    st->beta = beta;
+    res_norm[it - 1] = sqrt(rTr);
+    if (!((it < st->maxit) && (sqrt(rTr) > st->tol))) st->done_at = iter;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Dense tall-skinny products with the deflation / recycling bases W, V (n_gamma x k, column-major):

@@ -38,6 +38,11 @@ def _worker(rank, world, nccl_ids, q):
             bs = S.schur_rhs(lb.b_I, lb.b_G)
             xs, it, res = solvers.pcg(S, bs, np.zeros(sd.n_gamma), M)
             xs2, it2, res2 = solvers.pcg(S, bs, np.zeros(sd.n_gamma), M)   # bitwise repeatable
+            S.h.set_option("fuse_pcg", 0)                                  # separate assemble / update kernels
+            xs3, it3, res3 = solvers.pcg(S, bs, np.zeros(sd.n_gamma), M)
+            S.h.set_option("fuse_pcg", 1)
+            if not (np.array_equal(xs, xs3) and it == it3):
+                raise AssertionError(f"fused and unfused PCG steps differ in mode {mode}: it {it} vs {it3}")
             out[mode] = dict(y=y, z=z, bs=bs, x=xs, it=it, res=res, same=bool(np.array_equal(xs, xs2) and it == it2),
                              peer=S.h.stats()["peer_exchange"], local=S.local_range)
             del M, S

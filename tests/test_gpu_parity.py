@@ -367,3 +367,26 @@ def test_fused_defpcg_and_pcg_multi():
     for j in range(2):
         xj, itj, _ = solvers.pcg(S, B[:, j].copy(), np.zeros(n), M)
         assert its[j] == itj and np.array_equal(X[:, j], xj) and ress[j].size == itj
+
+
+def test_fused_pcg_steps_are_bit_identical_to_the_unfused_kernels():
+    """plain PCG: assembly + dot + vector update in one kernel (grid-wide arrival counter) against
+    the separate assemble / update kernels -- same partial sums, same order, same bits; also the
+    assembled-operator variant and a solve that stops at maxit."""
+    pr, S, M = gpu_ops(65, 16, 4)
+    _, _, _, bs = get_oracle_ops(pr)
+    n = pr.sd.n_gamma
+    out = {}
+    for fuse in (1, 0):
+        S.h.set_option("fuse_pcg", fuse)
+        x, it, res = solvers.pcg(S, bs, np.zeros(n), M)
+        x5, it5, res5 = solvers.pcg(S, bs, np.zeros(n), M, maxit=5)
+        out[fuse] = (x, it, res, x5, it5, res5)
+    S.h.set_option("fuse_pcg", 1)
+    assert out[1][1] == out[0][1] and np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][2], out[0][2])
+    assert out[1][4] == out[0][4] == 5 and np.array_equal(out[1][3], out[0][3]) and np.array_equal(out[1][5], out[0][5])
+    # different check intervals do not change the result (kernels past convergence are skipped on the device)
+    S.h.set_option("check_every", 3)
+    x3, it3, res3 = solvers.pcg(S, bs, np.zeros(n), M)
+    S.h.set_option("check_every", 32)
+    assert it3 == out[1][1] and np.array_equal(x3, out[1][0])
