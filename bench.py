@@ -184,7 +184,7 @@ def main():
     barrier()
     sampler.start()
     dev_ms = schur_ms = nn_ms = 0.0
-    schur_launches = launches = h2d = d2h = 0
+    schur_launches = nn_launches = launches = h2d = d2h = 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         x[:] = 0.0
@@ -193,16 +193,23 @@ def main():
         schur_ms += tm.schur_ms
         nn_ms += tm.nn_ms
         schur_launches += tm.schur_launches
+        nn_launches += tm.nn_launches
         launches += tm.kernel_launches
         h2d += tm.h2d_bytes
         d2h += tm.d2h_bytes
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    per_rank = None
     if world > 1:
         t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_s = float(t[0]), float(t[1])
+        # per-rank kernel times (the ranks meet at every interface exchange: the slowest one sets the pace)
+        mine = torch.tensor([schur_ms / max(schur_launches, 1), nn_ms / max(nn_launches, 1)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"schur_kernel_ms": [round(float(a[0]), 4) for a in allr], "nn_kernel_ms": [round(float(a[1]), 4) for a in allr]}
     iters = it - 1
     relres = float(res[-1] / np.linalg.norm(b_schur))
     peak, peak_src = measured_peak()
@@ -228,11 +235,16 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "schur_stream_kernel<MODE_APPLY>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
-                     "kernel_share_of_step": schur_ms / dev_ms,
+                     # launch durations are sampled (every 16th iteration is bracketed by events; an event between
+                     # two kernels would serialise the programmatic dependent launch chain of the others)
+                     "timed_launches": int(schur_launches),
+                     "kernel_share_of_step": avg_ms * (iters + 1) * args.steps / dev_ms,
                      "per_iteration": {"B_iter_bytes": B_iter, "achieved_GBs": B_iter * iters * args.steps / (dev_ms * 1e-3) / 1e9,
                                        "frac": B_iter * iters * args.steps / (dev_ms * 1e-3) / 1e9 / peak}},
         "clocks": clocks,
     }
+    if per_rank is not None:
+        out["per_rank"] = per_rank
     if world == 1 and rank == 0:
         out["cpu_baseline"], out["parity_at_full_size"] = cpu_baseline(args, pr, sd, PiS, b_schur, iters, S=S, M=M)
     if rank == 0:

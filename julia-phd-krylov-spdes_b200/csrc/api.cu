@@ -124,6 +124,9 @@ struct kb200_ctx {
   size_t xch_flags_off = 0;
   int xch_npad = 0;
   uint32_t xch_seq = 0;
+  int vec_threads = 0;              // block size of the interface-vector kernels (0: automatic, 256 or 1024)
+  int pdl = 0;                      // option: programmatic dependent launch inside the fused PCG loop
+  bool pdl_now = false;             // set while the fused loop enqueues (adjacent kernels only)
   int fuse_pcg = 1;                 // option: plain PCG runs its vector steps inside the assembly kernels
   DevBuf<unsigned int> d_gsync;     // grid-wide arrival counter of the fused kernels
   unsigned int gsync_launches = 0;
@@ -357,7 +360,10 @@ void finalize(Ctx* c) {
   if (c->have_sd) upload_dense(c->d_sd, false);
   // vectors
   const int64_t ng = c->n_gamma;
-  c->nb = (int)((ng + kb::kVecThreads - 1) / kb::kVecThreads);
+  // block size of the interface-vector kernels: few large blocks when every assembly ends in a peer
+  // exchange (fewer flags / fences / grid-barrier arrivals), many small ones on a single GPU
+  if (c->vec_threads == 0) c->vec_threads = c->has_comm ? 1024 : 256;
+  c->nb = (int)((ng + c->vec_threads - 1) / c->vec_threads);
   for (DevBuf<double>* v : {&c->d_x, &c->d_b, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap}) v->alloc(ng);
   c->d_loc.alloc(c->G_base[nloc]);
   c->d_bI.alloc(c->I_base[nloc]);
@@ -423,7 +429,7 @@ void setup_peer_exchange(Ctx* c) {
 #ifdef KB200_WITH_NCCL
   if (!c->has_comm || c->world < 2 || c->world > kb::kMaxPeers || !c->peer_exchange || c->xch_own) return;
   const int W = c->world;
-  c->xch_npad = c->nb * kb::kVecThreads;
+  c->xch_npad = c->nb * c->vec_threads;
   const size_t data_bytes = (size_t)2 * W * c->xch_npad * sizeof(double);
   const size_t flag_bytes = (size_t)W * c->nb * sizeof(uint32_t);
   c->xch_flags_off = data_bytes;
@@ -525,13 +531,15 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   cfg.blockDim = dim3((unsigned)kb::stream_threads(c->warps), 1, 1);
   cfg.dynamicSmemBytes = (size_t)c->smem_bytes;
   cfg.stream = c->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)c->csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = c->pdl_now ? 2 : 1;
   if (c->warps == kb::kWarps) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps>, P));
   else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16>, P));
   c->launches++;
@@ -552,8 +560,26 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
   P.out_loc = out_loc;
   P.done_at = done_at;
   P.iter = iter;
-  dim3 grid((unsigned)((c->max_gd + kb::kGemvRowsPerCta - 1) / kb::kGemvRowsPerCta), (unsigned)nloc, 1);
-  kb::dense_gemv_kernel<<<grid, 256, (size_t)c->max_gd * 8, c->stream>>>(P);
+  // rows per CTA: 32 when the grid is large anyway, 8 (one row per warp) when few subdomains are local
+  const int64_t tiles32 = (c->max_gd + kb::kGemvRowsPerCta - 1) / kb::kGemvRowsPerCta;
+  P.rows_per_cta = (tiles32 * nloc >= 2048) ? kb::kGemvRowsPerCta : 8;
+  dim3 grid((unsigned)((c->max_gd + P.rows_per_cta - 1) / P.rows_per_cta), (unsigned)nloc, 1);
+  if (c->pdl_now) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)c->max_gd * 8;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::dense_gemv_kernel, P));
+  } else {
+    kb::dense_gemv_kernel<<<grid, 256, (size_t)c->max_gd * 8, c->stream>>>(P);
+  }
   CUDA_TRY(cudaGetLastError());
   c->launches++;
 }
@@ -590,7 +616,7 @@ void assemble(Ctx* c, const double* loc, const double* base, double* y, const do
               const int* done_at, int iter) {
   const int n = (int)c->n_gamma;
   if (!c->has_comm) {
-    kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base, y, q,
+    kb::assemble_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base, y, q,
                                                                  part, done_at, iter);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
@@ -599,21 +625,21 @@ void assemble(Ctx* c, const double* loc, const double* base, double* y, const do
   if (c->peer_ok) {
     // fused: assemble the local partial, exchange it over NVLink peer memory, sum, partial dot
     const kb::XchParams X = next_exchange(c);
-    kb::assemble_exchange_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
+    kb::assemble_exchange_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
                                                                           c->rank == 0 ? base : nullptr, y, q, part,
                                                                           done_at, iter, X);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return;
   }
-  kb::assemble_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
+  kb::assemble_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
                                                                c->rank == 0 ? base : nullptr, y, nullptr, nullptr,
                                                                done_at, iter);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
   allreduce(c, y, n);
   if (q != nullptr) {
-    kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, y, q, part, done_at, iter);
+    kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, y, q, part, done_at, iter);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
   }
@@ -824,6 +850,12 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "adaptive_lanes" || k == "lane_min" || k == "lane_max") {
       require(!h->finalized && value >= 0 && value <= 256, "lane options must be set before the first operation");
       (k == "adaptive_lanes" ? h->adaptive_lanes : k == "lane_min" ? h->lane_min : h->lane_max) = (int)value;
+    } else if (k == "vec_threads") {
+      require(!h->finalized && (value == 0 || value == 256 || value == 512 || value == 1024), "vec_threads is 0, 256, 512 or 1024, before the first operation");
+      h->vec_threads = (int)value;
+    } else if (k == "pdl") {
+      require(value == 0 || value == 1, "pdl is 0 or 1");
+      h->pdl = (int)value;
     } else if (k == "fuse_pcg") {
       require(value == 0 || value == 1, "fuse_pcg is 0 or 1");
       h->fuse_pcg = (int)value;
@@ -1134,7 +1166,7 @@ static void invert_small(int k, std::vector<double> Ain, std::vector<double>& in
 static void defl_project(Ctx* c, const Defl& D, const double* basis, const double* v, const int* done_at, int iter) {
   // mu = (W' S W)^{-1} (basis' v)
   const int n = (int)c->n_gamma;
-  kb::gemv_t_kernel<<<(unsigned)D.k, kb::kVecThreads, 0, c->stream>>>(n, basis, n, v, D.y, done_at, iter);
+  kb::gemv_t_kernel<<<(unsigned)D.k, c->vec_threads, 0, c->stream>>>(n, basis, n, v, D.y, done_at, iter);
   kb::small_solve_kernel<<<1, 1024, (size_t)D.k * 3 * 8, c->stream>>>(D.k, D.Minv, D.M, D.y, D.mu, done_at, iter);
   CUDA_TRY(cudaGetLastError());
   c->launches += 2;
@@ -1150,7 +1182,7 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   const int* done_at = &st->done_at;
   // r = b - A x ; z = M \ r ; p = z (- W mu)                                         (cg.jl:83-90)
   apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
-  kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
+  kb::pcg_init_residual_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
                                                                         c->d_partB.p);
   c->launches++;
   auto precondition = [&](const int* da, int iter) {
@@ -1158,17 +1190,17 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
       apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, da, iter, &kt);
     } else {
       CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-      kb::dot_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, da, iter);
+      kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, da, iter);
       c->launches++;
     }
   };
   precondition(nullptr, 0);
-  kb::pcg_init_direction_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p,
+  kb::pcg_init_direction_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p,
                                                                          c->d_partC.p, st, c->d_res.p, rtol, (int)maxit);
   c->launches++;
   if (defl) {  // p = z - W mu, mu = WtAW \ (WtA z)                                   (defcg.jl:284-285)
     defl_project(c, *defl, defl->AW, c->d_z.p, nullptr, 0);
-    kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0, c->d_p.p);
+    kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0, c->d_p.p);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -1178,50 +1210,70 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   while (!done) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
     const bool fused = c->fuse_pcg && precond && defl == nullptr && (!c->has_comm || c->peer_ok);
-    for (; fused && k < kend; ++k) {
-      // four launches per iteration: local operator, assembly (+exchange) fused with the vector update
-      const bool timed = c->profile != 0;
-      cudaEvent_t ev = nullptr;
-      if (timed) kt.begin(0, ev);
-      if (A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, done_at, k);
-      else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, done_at, k);
-      if (timed) kt.end(0, ev);
+    if (fused) {
+      // four launches per iteration: local operator, assembly (+exchange) fused with the vector update;
+      // consecutive kernels are chained by programmatic dependent launch (launch latency and prologues
+      // overlap the predecessor's tail); kernel durations are sampled on every 16th iteration only,
+      // because an event between two kernels serialises them
+      cudaLaunchConfig_t vcfg;
+      std::memset(&vcfg, 0, sizeof(vcfg));
+      vcfg.gridDim = dim3((unsigned)c->nb, 1, 1);
+      vcfg.blockDim = dim3((unsigned)c->vec_threads, 1, 1);
+      vcfg.stream = c->stream;
+      cudaLaunchAttribute vattr[1];
+      vattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      vattr[0].val.programmaticStreamSerializationAllowed = 1;
+      vcfg.attrs = vattr;
+      vcfg.numAttrs = c->pdl ? 1 : 0;
       const unsigned int nbk = (unsigned int)c->nb;
-      if (c->peer_ok)
-        kb::pcg_fused_xr_kernel<true><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
-            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
-            c->d_partB.p, st, k, c->d_gsync.p, ++c->gsync_launches * nbk, next_exchange(c));
-      else
-        kb::pcg_fused_xr_kernel<false><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
-            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
-            c->d_partB.p, st, k, c->d_gsync.p, ++c->gsync_launches * nbk, kb::XchParams());
-      if (timed) kt.begin(1, ev);
-      launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, done_at, k);
-      if (timed) kt.end(1, ev);
-      if (c->peer_ok)
-        kb::pcg_fused_p_kernel<true><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
-            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_z.p, c->d_r.p, c->d_p.p, c->d_partB.p, c->d_partC.p, st,
-            c->d_res.p, nullptr, k, c->d_gsync.p, ++c->gsync_launches * nbk, next_exchange(c));
-      else
-        kb::pcg_fused_p_kernel<false><<<c->nb, kb::kVecThreads, 0, c->stream>>>(
-            n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_z.p, c->d_r.p, c->d_p.p, c->d_partB.p, c->d_partC.p, st,
-            c->d_res.p, nullptr, k, c->d_gsync.p, ++c->gsync_launches * nbk, kb::XchParams());
-      c->launches += 2;
+      const int* adj_ptr = c->d_adj_ptr.p;
+      const int* adj_src = c->d_adj_src.p;
+      const double* loc = c->d_loc.p;
+      double* nullvec = nullptr;
+      c->pdl_now = c->pdl != 0;
+      for (; k < kend; ++k) {
+        const bool timed = c->profile != 0 && (k % 16 == 1);
+        cudaEvent_t ev = nullptr;
+        if (timed) kt.begin(0, ev);
+        if (A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, done_at, k);
+        else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, done_at, k);
+        if (timed) kt.end(0, ev);
+        {
+          const unsigned int target = ++c->gsync_launches * nbk;
+          const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
+          auto fn = c->peer_ok ? kb::pcg_fused_xr_kernel<true> : kb::pcg_fused_xr_kernel<false>;
+          CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, c->d_Ap.p, (const double*)c->d_p.p, c->d_x.p,
+                                      c->d_r.p, c->d_partA.p, c->d_partB.p, st, k, c->d_gsync.p, target, X));
+        }
+        if (timed) kt.begin(1, ev);
+        launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, done_at, k);
+        if (timed) kt.end(1, ev);
+        {
+          const unsigned int target = ++c->gsync_launches * nbk;
+          const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
+          auto fn = c->peer_ok ? kb::pcg_fused_p_kernel<true> : kb::pcg_fused_p_kernel<false>;
+          CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, c->d_z.p, (const double*)c->d_r.p, c->d_p.p,
+                                      (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, nullvec, k, c->d_gsync.p,
+                                      target, X));
+        }
+        c->launches += 2;
+      }
+      c->pdl_now = false;
     }
     for (; k < kend; ++k) {
       apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);    // Ap = A p ; d = p.Ap
-      kb::pcg_update_xr_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p, c->d_r.p,
+      kb::pcg_update_xr_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p, c->d_r.p,
                                                                         c->d_partA.p, c->d_partB.p, st, k);
       c->launches++;
       precondition(done_at, k);                                                          // z = M \ r ; rTz
       if (defl) defl_project(c, *defl, defl->AW, c->d_z.p, done_at, k);                  // mu               (defcg.jl:301)
-      kb::pcg_update_p_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p, c->d_partC.p,
+      kb::pcg_update_p_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p, c->d_partC.p,
                                                                        st, c->d_res.p, nullptr, k);
       c->launches++;
       if (defl) {                                                                        // p -= W mu        (defcg.jl:302)
         // pcg_update_p of iteration k may already have set done_at = k: the projection of this last
         // direction is then irrelevant, and kernels of iteration k still run (done_at < k is false)
-        kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0,
+        kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0,
                                                                                      c->d_p.p, done_at, k);
         c->launches++;
       }
@@ -1348,11 +1400,11 @@ int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, in
     D.mu = dmu.p;
     // r = b - A x ; x += W (WtAW \ W'r)                                              (defcg.jl:270-275)
     apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
-    kb::pcg_init_residual_kernel<<<c->nb, kb::kVecThreads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
+    kb::pcg_init_residual_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
                                                                           c->d_partB.p);
     c->launches++;
     defl_project(c, D, D.W, c->d_r.p, nullptr, 0);
-    kb::gemv_n_kernel<<<c->nb, kb::kVecThreads, (size_t)k * 8, c->stream>>>(n, k, 1.0, D.W, n, D.mu, 1.0, c->d_x.p);
+    kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)k * 8, c->stream>>>(n, k, 1.0, D.W, n, D.mu, 1.0, c->d_x.p);
     c->launches++;
     int it = 0, fail = 0;
     pcg_core(c, maxit, rtol, A, precond, &D, kt, &it, &fail);
@@ -1424,7 +1476,7 @@ int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, 
   return guarded([&]() {
     require(h != nullptr, "null handle");
     use_device(h);
-    kb::axpby_kernel<<<h->nb, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, a, mat_col(h, x, xcol, 1), b,
+    kb::axpby_kernel<<<h->nb, h->vec_threads, 0, h->stream>>>((int)h->n_gamma, a, mat_col(h, x, xcol, 1), b,
                                                                mat_col(h, y, ycol, 1));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1435,7 +1487,7 @@ int kb200_op_gemv_t(kb200_handle h, int64_t A, int64_t col0, int64_t k, int64_t 
     require(h && y_host && k >= 1, "bad argument");
     use_device(h);
     if ((int64_t)h->d_small.n < k) h->d_small.alloc((size_t)k);
-    kb::gemv_t_kernel<<<(unsigned)k, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, mat_col(h, A, col0, k), h->n_gamma,
+    kb::gemv_t_kernel<<<(unsigned)k, h->vec_threads, 0, h->stream>>>((int)h->n_gamma, mat_col(h, A, col0, k), h->n_gamma,
                                                                       mat_col(h, x, xcol, 1), h->d_small.p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1453,7 +1505,7 @@ int kb200_op_gemv_n(kb200_handle h, double a, int64_t A, int64_t col0, int64_t k
     use_device(h);
     if ((int64_t)h->d_small2.n < k) h->d_small2.alloc((size_t)k);
     CUDA_TRY(cudaMemcpyAsync(h->d_small2.p, mu_host, (size_t)k * 8, cudaMemcpyHostToDevice, h->stream));
-    kb::gemv_n_kernel<<<h->nb, kb::kVecThreads, (size_t)k * 8, h->stream>>>((int)h->n_gamma, (int)k, a, mat_col(h, A, col0, k),
+    kb::gemv_n_kernel<<<h->nb, h->vec_threads, (size_t)k * 8, h->stream>>>((int)h->n_gamma, (int)k, a, mat_col(h, A, col0, k),
                                                                            h->n_gamma, h->d_small2.p, b, mat_col(h, y, ycol, 1));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1484,7 +1536,7 @@ int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const do
     DevBuf<double> tmp;
     tmp.alloc((size_t)(h->n_gamma * kq));
     dim3 grid((unsigned)h->nb, (unsigned)kq);
-    kb::gemm_nn_kernel<<<grid, kb::kVecThreads, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kq, mat_col(h, A, ca, ka), h->n_gamma,
+    kb::gemm_nn_kernel<<<grid, h->vec_threads, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kq, mat_col(h, A, ca, ka), h->n_gamma,
                                                                h->d_small2.p, tmp.p, h->n_gamma);
     CUDA_TRY(cudaGetLastError());
     h->launches++;

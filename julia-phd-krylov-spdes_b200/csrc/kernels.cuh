@@ -85,6 +85,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 template <int NW>
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory"); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; `pdl_trigger` lets OUR
+// successor be scheduled early, `pdl_wait` blocks until the predecessor has completed and flushed its
+// memory.  Both are no-ops for ordinary launches.  Every block triggers at its very start, so a
+// successor only begins to launch once all blocks of this grid are resident (the grid-wide and
+// cross-GPU spin barriers of the vector kernels rely on that).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct StreamCtx {
   const CtaDesc* D;
   const uint8_t* gstream;  // this CTA's stream in global memory
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t lvl_bar;
-  if (P.done_at != nullptr && *P.done_at < P.iter) return;
+  pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   double* scratch = reinterpret_cast<double*>(smem_raw + (size_t)P.nstages * kChunkBytes);
   double* S = scratch + kMaxSlots;
@@ -297,6 +306,10 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
   }
   __syncthreads();
   for (int i = tid; i < D.smem_doubles; i += blockDim.x) S[i] = 0.0;
+  // everything above touches only static data and this CTA's shared memory: with PDL it overlaps the
+  // tail of the previous kernel; from here on the kernel reads what its predecessors wrote
+  pdl_wait();
+  if (P.done_at != nullptr && *P.done_at < P.iter) return;  // uniform over the grid (and the cluster)
   __syncthreads();
   const int C = D.csize, rank = D.rank;
   // ---- inputs ---------------------------------------------------------------------------------
@@ -457,15 +470,19 @@ struct GemvParams {
   double* out_loc;
   const int* done_at;
   int iter;
+  int rows_per_cta;         // 32 on a full GPU; 8 when few subdomains are local (multi-GPU shards), for more CTAs
 };
 constexpr int kGemvRowsPerCta = 32;
 
 __global__ void __launch_bounds__(256) dense_gemv_kernel(const GemvParams P) {
   extern __shared__ double xs[];
+  pdl_trigger();
+  pdl_wait();
   if (P.done_at != nullptr && *P.done_at < P.iter) return;
   const int d = blockIdx.y;
   const int n = P.n_gd[d];
-  const int row0 = blockIdx.x * kGemvRowsPerCta;
+  const int rpc = P.rows_per_cta;
+  const int row0 = blockIdx.x * rpc;
   if (row0 >= n) return;
   const int64_t gb = P.G_base[d];
   const int32_t* l2g = P.l2g + gb;
@@ -478,7 +495,7 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const GemvParams P) {
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* M = P.mats + P.mat_off[d];
-  for (int r = warp; r < kGemvRowsPerCta; r += 8) {
+  for (int r = warp; r < rpc; r += 8) {
     const int i = row0 + r;
     if (i >= n) break;
     const double* mrow = M + (int64_t)i * n;
@@ -505,9 +522,9 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const GemvParams P) {
 // ---------------------------------------------------------------------------------------------
 // Block-level deterministic reductions
 // ---------------------------------------------------------------------------------------------
-constexpr int kVecThreads = 256;
+constexpr int kVecThreads = 1024;  // largest block size of the interface-vector kernels (the host picks 256 or 1024)
 
-__device__ __forceinline__ double block_reduce_sum(double v, double* red /*>=8*/) {
+__device__ __forceinline__ double block_reduce_sum(double v, double* red /*>= warps per block*/) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __syncthreads();
@@ -541,7 +558,7 @@ struct PcgState {
 __global__ void __launch_bounds__(kVecThreads)
 assemble_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
                 double* y, const double* q, double* part, const int* done_at, int iter) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (done_at != nullptr && *done_at < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   double prod = 0.0;
@@ -598,7 +615,8 @@ __device__ __forceinline__ double exchange_sum(double a, int g, int n, const Xch
   __syncthreads();
   if ((int)threadIdx.x < X.world) {
     const int r = threadIdx.x;
-    __threadfence_system();
+    // release at system scope: the block's stores to the peers (ordered before this thread by the
+    // barrier above) are visible to whoever acquires the flag
     st_release_sys(X.flags[r] + (size_t)X.rank * nb + blockIdx.x, X.seq);
     // wait for segment blockIdx.x of source rank r
     const uint32_t* f = X.flags[X.rank] + (size_t)r * nb + blockIdx.x;
@@ -633,7 +651,7 @@ __device__ __forceinline__ double assemble_local(int g, int n, const int32_t* ad
 __global__ void __launch_bounds__(kVecThreads)
 assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
                          double* y, const double* q, double* part, const int* done_at, int iter, const XchParams X) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (done_at != nullptr && *done_at < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const double sum = exchange_sum(assemble_local(g, n, adj_ptr, adj_src, loc, base), g, n, X);
@@ -651,7 +669,7 @@ assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, 
 // part[b] = block partial of dot(a, b)
 __global__ void __launch_bounds__(kVecThreads)
 dot_kernel(int n, const double* a, const double* b, double* part, const int* done_at, int iter) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (done_at != nullptr && *done_at < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const double prod = (g < n) ? a[g] * b[g] : 0.0;
@@ -662,7 +680,7 @@ dot_kernel(int n, const double* a, const double* b, double* part, const int* don
 // r = b - Ax ; partials of r.r (partA) and b.b (partB)                            (cg.jl:83-84, 89)
 __global__ void __launch_bounds__(kVecThreads)
 pcg_init_residual_kernel(int n, const double* b, const double* Ax, double* r, double* partA, double* partB) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   double rr = 0.0, bb = 0.0;
   if (g < n) {
@@ -683,7 +701,7 @@ pcg_init_residual_kernel(int n, const double* b, const double* Ax, double* r, do
 __global__ void __launch_bounds__(kVecThreads)
 pcg_init_direction_kernel(int n, int nb, const double* z, double* p, const double* partA, const double* partB,
                           const double* partC, PcgState* st, double* res_norm, double rtol, int maxit) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n) p[g] = z[g];
   if (blockIdx.x == 0) {
@@ -708,7 +726,7 @@ pcg_init_direction_kernel(int n, int nb, const double* z, double* p, const doubl
 __global__ void __launch_bounds__(kVecThreads)
 pcg_update_xr_kernel(int n, int nb, const double* p, const double* Ap, double* x, double* r, const double* partA,
                      double* partB, PcgState* st, int iter) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (st->done_at < iter) return;
   const double d = sum_partials(partA, nb, red);
   const double rTz = st->rTz;
@@ -738,7 +756,7 @@ pcg_update_xr_kernel(int n, int nb, const double* p, const double* Ap, double* x
 __global__ void __launch_bounds__(kVecThreads)
 pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* partB, const double* partC,
                     PcgState* st, double* res_norm, double* vcol, int iter) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (st->done_at < iter) return;
   const double rTr = sum_partials(partB, nb, red);
   const double rTz_new = sum_partials(partC, nb, red);
@@ -800,7 +818,9 @@ __global__ void __launch_bounds__(kVecThreads)
 pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, double* Ap, const double* p,
                     double* x, double* r, double* partA, double* partB, PcgState* st, int iter, unsigned int* counter,
                     unsigned int target, const XchParams X) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
+  pdl_trigger();
+  pdl_wait();
   if (st->done_at < iter) {
     grid_skip(counter);
     return;
@@ -845,7 +865,9 @@ __global__ void __launch_bounds__(kVecThreads)
 pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, double* z, const double* r,
                    double* p, const double* partB, double* partC, PcgState* st, double* res_norm, double* vcol, int iter,
                    unsigned int* counter, unsigned int target, const XchParams X) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
+  pdl_trigger();
+  pdl_wait();
   if (st->done_at < iter) {
     grid_skip(counter);
     return;
@@ -893,7 +915,7 @@ __global__ void __launch_bounds__(kVecThreads) axpby_kernel(int n, double a, con
 // out[j] = A[:, j] . x   (one block per column, fixed reduction order)
 __global__ void __launch_bounds__(kVecThreads) gemv_t_kernel(int n, const double* A, int64_t lda, const double* x, double* out,
                                                            const int* done_at = nullptr, int iter = 0) {
-  __shared__ double red[8];
+  __shared__ double red[kVecThreads / 32];
   if (done_at != nullptr && *done_at < iter) return;
   const double* col = A + (int64_t)blockIdx.x * lda;
   double s = 0.0;

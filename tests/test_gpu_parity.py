@@ -141,7 +141,7 @@ def test_pcg_parity(nx, ndom, csize, median):
     assert itk == k
     assert np.linalg.norm(xk - xok) <= max(1e-10, 20 * floor_x) * np.linalg.norm(xok)
     assert np.abs(resk - reso[:k]).max() <= max(1e-10, 20 * floor_r) * reso[:k].max()
-    assert tm.kernel_launches > 0 and tm.schur_launches >= it and tm.solve_ms > 0   # launches past convergence exit early
+    assert tm.kernel_launches >= 4 * (it - 1) and tm.schur_launches >= 1 and tm.solve_ms > 0   # launches past convergence exit early
 
 
 def test_pcg_parity_tight_on_well_conditioned_case():
