@@ -166,6 +166,21 @@ int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t 
 int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const double* Q_host, int64_t kq, int64_t C,
                      int64_t cc);
 
+/* Continue a (deflated) PCG recurrence for up to m iterations WITHOUT host synchronisation inside: the
+ * body of the loops eigcg.jl:185-246 / defcg.jl:400-448 between two restarts of the recycling solvers
+ * (cg.jl:93-105 per iteration, plus p -= W (WtAW \ (WtA z)) defcg.jl:301-302 when nvec > 0, plus
+ * r -= W (WtW \ (W'r)) defcg.jl:407 when WtW is given).  Vectors are columns 0..4 = x, r, z, p, Ap of block
+ * `wk`; W, AW are blocks of nvec columns; WtAW / WtW and their inverses are nvec x nvec column-major host
+ * arrays (the device applies the inverse with one step of iterative refinement).  After iteration j
+ * (0-based) the column V[:, vcol0 + j] receives z / sqrt(rTz) (eigcg.jl:242; V < 0: not stored) and
+ * alpha_out[j], beta_out[j], res_out[j] = alpha, beta, ||r||_2 of that iteration.  The recurrence starts from
+ * the host-side scalars rTz, `it0` (the reference's `it`) and stops like the reference's loop
+ * (it < maxit && ||r|| > tol).  n_done iterations were run; rTz_out is the final r'z. */
+int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int64_t W, int64_t AW, int64_t nvec,
+                    const double* WtAW, const double* WtAW_inv, const double* WtW, const double* WtW_inv, int64_t m,
+                    int64_t V, int64_t vcol0, double rTz, double tol, int64_t it0, int64_t maxit, double* alpha_out,
+                    double* beta_out, double* res_out, int64_t* n_done, double* rTz_out);
+
 /* ---- introspection (tests / benchmarks) -------------------------------------------------------- */
 /* stats[0..n): 0 Σ nnz(L) strictly lower, 1 Σ stream entries, 2 Σ rows, 3 Σ slices,
  * 4 stream bytes read per Schur apply, 5 max levels, 6 max top size, 7 shared memory per CTA,

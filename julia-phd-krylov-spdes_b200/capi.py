@@ -21,7 +21,7 @@ SYMBOLS = [
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_pcg_multi", "kb200_defpcg", "kb200_get_stats", "kb200_get_interface_maps",
     "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
-    "kb200_op_gemm_tn", "kb200_op_gemm_nn",
+    "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst",
 ]
 
 
@@ -318,6 +318,25 @@ class Handle:
         Q = np.asfortranarray(Q, dtype=np.float64)
         _chk(lib().kb200_op_gemm_nn(self.h, C.c_int64(A), C.c_int64(ca), C.c_int64(ka), _p(Q, C.c_double),
                                     C.c_int64(Q.shape[1]), C.c_int64(Cm), C.c_int64(cc)))
+
+    def pcg_burst(self, assembled, precond, wk, m, rTz, tol, it0, maxit, V=-1, vcol0=0, W=-1, AW=-1, nvec=0,
+                  WtAW=None, WtW=None):
+        """kb200_pcg_burst: up to m iterations of the (deflated) recurrence on the device without host
+        synchronisation; returns (n_done, alpha[n_done], beta[n_done], res[n_done], rTz)."""
+        al, be, rs = np.zeros(m), np.zeros(m), np.zeros(m)
+        nd, rz = C.c_int64(), C.c_double()
+        f = lambda M: None if M is None else np.asfortranarray(M, dtype=np.float64)
+        A1, A2 = f(WtAW), f(WtW)
+        A1i = None if A1 is None else np.asfortranarray(np.linalg.inv(A1))
+        A2i = None if A2 is None else np.asfortranarray(np.linalg.inv(A2))
+        ptr = lambda M: None if M is None else _p(M, C.c_double)
+        _chk(lib().kb200_pcg_burst(self.h, C.c_int(int(assembled)), C.c_int(int(precond)), C.c_int64(wk), C.c_int64(W),
+                                   C.c_int64(AW), C.c_int64(nvec), ptr(A1), ptr(A1i), ptr(A2), ptr(A2i), C.c_int64(m),
+                                   C.c_int64(V), C.c_int64(vcol0), C.c_double(rTz), C.c_double(tol), C.c_int64(it0),
+                                   C.c_int64(maxit), _p(al, C.c_double), _p(be, C.c_double), _p(rs, C.c_double),
+                                   C.byref(nd), C.byref(rz)))
+        k = nd.value
+        return k, al[:k], be[:k], rs[:k], rz.value
 
     def stats(self):
         s = np.zeros(16)

@@ -1172,6 +1172,109 @@ static void defl_project(Ctx* c, const Defl& D, const double* basis, const doubl
   c->launches += 2;
 }
 
+// One stretch of (deflated) PCG iterations on device-resident vectors, enqueued without any host
+// synchronisation (cg.jl:92-106, defcg.jl:290-305, :400-417).
+struct IterCtx {
+  OpKind A = OP_SCHUR;
+  int precond = 1;
+  double *x = nullptr, *r = nullptr, *z = nullptr, *p = nullptr, *Ap = nullptr;
+  const Defl* defl = nullptr;    // p <- beta p + z - W (WtAW \ (WtA z))                (defcg.jl:301-302)
+  const Defl* deflR = nullptr;   // r <- r - W (WtW \ (W' r)) after the update of r      (defcg.jl:407)
+  double* vbase = nullptr;       // V[:, vcol0 + (k - k0)] = z / sqrt(rTz) at the end of iteration k  (eigcg.jl:242)
+  int k0 = 1;
+  double* hist = nullptr;        // hist[2 it], hist[2 it + 1] = alpha, beta of the iteration that produced `it`
+};
+
+static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTimer* kt) {
+  const int n = (int)c->n_gamma;
+  kb::PcgState* st = c->d_state.p;
+  const int* done_at = &st->done_at;
+  auto vcol = [&](int kk) -> double* { return I.vbase ? I.vbase + (size_t)(kk - I.k0) * (size_t)n : nullptr; };
+  const bool fused = c->fuse_pcg && I.precond && I.defl == nullptr && I.deflR == nullptr && (!c->has_comm || c->peer_ok);
+  if (fused) {
+    // four launches per iteration: local operator, assembly (+exchange) fused with the vector update;
+    // kernel durations are sampled on every 16th iteration only (an event between two kernels would
+    // serialise an optional programmatic-dependent-launch chain)
+    cudaLaunchConfig_t vcfg;
+    std::memset(&vcfg, 0, sizeof(vcfg));
+    vcfg.gridDim = dim3((unsigned)c->nb, 1, 1);
+    vcfg.blockDim = dim3((unsigned)c->vec_threads, 1, 1);
+    vcfg.stream = c->stream;
+    cudaLaunchAttribute vattr[1];
+    vattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    vattr[0].val.programmaticStreamSerializationAllowed = 1;
+    vcfg.attrs = vattr;
+    vcfg.numAttrs = c->pdl ? 1 : 0;
+    const unsigned int nbk = (unsigned int)c->nb;
+    const int* adj_ptr = c->d_adj_ptr.p;
+    const int* adj_src = c->d_adj_src.p;
+    const double* loc = c->d_loc.p;
+    c->pdl_now = c->pdl != 0;
+    for (; k < kend; ++k) {
+      const bool timed = kt != nullptr && c->profile != 0 && (k % 16 == 1);
+      cudaEvent_t ev = nullptr;
+      if (timed) kt->begin(0, ev);
+      if (I.A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, I.p, nullptr, nullptr, c->d_loc.p, done_at, k);
+      else launch_gemv(c, c->d_sd.p, I.p, false, c->d_loc.p, done_at, k);
+      if (timed) kt->end(0, ev);
+      {
+        const unsigned int target = ++c->gsync_launches * nbk;
+        const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
+        auto fn = c->peer_ok ? kb::pcg_fused_xr_kernel<true> : kb::pcg_fused_xr_kernel<false>;
+        CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.Ap, (const double*)I.p, I.x, I.r, c->d_partA.p,
+                                    c->d_partB.p, st, k, c->d_gsync.p, target, X));
+      }
+      if (timed) kt->begin(1, ev);
+      launch_gemv(c, c->d_pinv.p, I.r, true, c->d_loc.p, done_at, k);
+      if (timed) kt->end(1, ev);
+      {
+        const unsigned int target = ++c->gsync_launches * nbk;
+        const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
+        auto fn = c->peer_ok ? kb::pcg_fused_p_kernel<true> : kb::pcg_fused_p_kernel<false>;
+        CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.z, (const double*)I.r, I.p,
+                                    (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, vcol(k), I.hist, k,
+                                    c->d_gsync.p, target, X));
+      }
+      c->launches += 2;
+    }
+    c->pdl_now = false;
+    return;
+  }
+  for (; k < kend; ++k) {
+    apply_op(c, I.A, I.p, I.Ap, I.p, c->d_partA.p, done_at, k, kt);                       // Ap = A p ; d = p.Ap
+    kb::pcg_update_xr_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, I.p, I.Ap, I.x, I.r, c->d_partA.p,
+                                                                      c->d_partB.p, st, k);
+    c->launches++;
+    if (I.deflR) {                                                                         // r -= W (WtW \ W'r) ; r.r
+      defl_project(c, *I.deflR, I.deflR->W, I.r, done_at, k);
+      kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)I.deflR->k * 8, c->stream>>>(n, I.deflR->k, -1.0, I.deflR->W, n,
+                                                                                      I.deflR->mu, 1.0, I.r, done_at, k);
+      kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, I.r, I.r, c->d_partB.p, done_at, k);
+      c->launches += 2;
+    }
+    if (I.precond) {                                                                       // z = M \ r ; rTz
+      apply_op(c, OP_NN, I.r, I.z, I.r, c->d_partC.p, done_at, k, kt);
+    } else {
+      // (a skipped iteration may still copy: z is not read again once done_at is set)
+      CUDA_TRY(cudaMemcpyAsync(I.z, I.r, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, I.r, I.z, c->d_partC.p, done_at, k);
+      c->launches++;
+    }
+    if (I.defl) defl_project(c, *I.defl, I.defl->AW, I.z, done_at, k);                     // mu               (defcg.jl:301)
+    kb::pcg_update_p_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, I.z, I.p, c->d_partB.p, c->d_partC.p, st,
+                                                                     c->d_res.p, vcol(k), I.hist, k);
+    c->launches++;
+    if (I.defl) {                                                                          // p -= W mu        (defcg.jl:302)
+      // pcg_update_p of iteration k may already have set done_at = k: the projection of this last
+      // direction is then irrelevant, and kernels of iteration k still run (done_at < k is false)
+      kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)I.defl->k * 8, c->stream>>>(n, I.defl->k, -1.0, I.defl->W, n,
+                                                                                     I.defl->mu, 1.0, I.p, done_at, k);
+      c->launches++;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
 // PCG / deflated PCG recurrence on device-resident d_b, d_x (cg.jl:76-106, defcg.jl:277-305).
 // Returns {it, fail}; x in d_x, residual history in d_res.
 static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, const Defl* defl, KernelTimer& kt, int* it_out,
@@ -1179,22 +1282,18 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   const int n = (int)c->n_gamma;
   if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
   kb::PcgState* st = c->d_state.p;
-  const int* done_at = &st->done_at;
   // r = b - A x ; z = M \ r ; p = z (- W mu)                                         (cg.jl:83-90)
   apply_op(c, A, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, &kt);
   kb::pcg_init_residual_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_b.p, c->d_Ap.p, c->d_r.p, c->d_partA.p,
                                                                         c->d_partB.p);
   c->launches++;
-  auto precondition = [&](const int* da, int iter) {
-    if (precond) {
-      apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, da, iter, &kt);
-    } else {
-      CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-      kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, da, iter);
-      c->launches++;
-    }
-  };
-  precondition(nullptr, 0);
+  if (precond) {
+    apply_op(c, OP_NN, c->d_r.p, c->d_z.p, c->d_r.p, c->d_partC.p, nullptr, 0, &kt);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(c->d_z.p, c->d_r.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_r.p, c->d_z.p, c->d_partC.p, nullptr, 0);
+    c->launches++;
+  }
   kb::pcg_init_direction_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partA.p, c->d_partB.p,
                                                                          c->d_partC.p, st, c->d_res.p, rtol, (int)maxit);
   c->launches++;
@@ -1204,80 +1303,22 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  IterCtx I;
+  I.A = A;
+  I.precond = precond;
+  I.x = c->d_x.p;
+  I.r = c->d_r.p;
+  I.z = c->d_z.p;
+  I.p = c->d_p.p;
+  I.Ap = c->d_Ap.p;
+  I.defl = defl;
   int* h_flag = reinterpret_cast<int*>(c->h_pinned);
   int k = 1;
   bool done = false;
   while (!done) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
-    const bool fused = c->fuse_pcg && precond && defl == nullptr && (!c->has_comm || c->peer_ok);
-    if (fused) {
-      // four launches per iteration: local operator, assembly (+exchange) fused with the vector update;
-      // consecutive kernels are chained by programmatic dependent launch (launch latency and prologues
-      // overlap the predecessor's tail); kernel durations are sampled on every 16th iteration only,
-      // because an event between two kernels serialises them
-      cudaLaunchConfig_t vcfg;
-      std::memset(&vcfg, 0, sizeof(vcfg));
-      vcfg.gridDim = dim3((unsigned)c->nb, 1, 1);
-      vcfg.blockDim = dim3((unsigned)c->vec_threads, 1, 1);
-      vcfg.stream = c->stream;
-      cudaLaunchAttribute vattr[1];
-      vattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      vattr[0].val.programmaticStreamSerializationAllowed = 1;
-      vcfg.attrs = vattr;
-      vcfg.numAttrs = c->pdl ? 1 : 0;
-      const unsigned int nbk = (unsigned int)c->nb;
-      const int* adj_ptr = c->d_adj_ptr.p;
-      const int* adj_src = c->d_adj_src.p;
-      const double* loc = c->d_loc.p;
-      double* nullvec = nullptr;
-      c->pdl_now = c->pdl != 0;
-      for (; k < kend; ++k) {
-        const bool timed = c->profile != 0 && (k % 16 == 1);
-        cudaEvent_t ev = nullptr;
-        if (timed) kt.begin(0, ev);
-        if (A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, done_at, k);
-        else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, done_at, k);
-        if (timed) kt.end(0, ev);
-        {
-          const unsigned int target = ++c->gsync_launches * nbk;
-          const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
-          auto fn = c->peer_ok ? kb::pcg_fused_xr_kernel<true> : kb::pcg_fused_xr_kernel<false>;
-          CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, c->d_Ap.p, (const double*)c->d_p.p, c->d_x.p,
-                                      c->d_r.p, c->d_partA.p, c->d_partB.p, st, k, c->d_gsync.p, target, X));
-        }
-        if (timed) kt.begin(1, ev);
-        launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, done_at, k);
-        if (timed) kt.end(1, ev);
-        {
-          const unsigned int target = ++c->gsync_launches * nbk;
-          const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
-          auto fn = c->peer_ok ? kb::pcg_fused_p_kernel<true> : kb::pcg_fused_p_kernel<false>;
-          CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, c->d_z.p, (const double*)c->d_r.p, c->d_p.p,
-                                      (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, nullvec, k, c->d_gsync.p,
-                                      target, X));
-        }
-        c->launches += 2;
-      }
-      c->pdl_now = false;
-    }
-    for (; k < kend; ++k) {
-      apply_op(c, A, c->d_p.p, c->d_Ap.p, c->d_p.p, c->d_partA.p, done_at, k, &kt);    // Ap = A p ; d = p.Ap
-      kb::pcg_update_xr_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_p.p, c->d_Ap.p, c->d_x.p, c->d_r.p,
-                                                                        c->d_partA.p, c->d_partB.p, st, k);
-      c->launches++;
-      precondition(done_at, k);                                                          // z = M \ r ; rTz
-      if (defl) defl_project(c, *defl, defl->AW, c->d_z.p, done_at, k);                  // mu               (defcg.jl:301)
-      kb::pcg_update_p_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, c->d_z.p, c->d_p.p, c->d_partB.p, c->d_partC.p,
-                                                                       st, c->d_res.p, nullptr, k);
-      c->launches++;
-      if (defl) {                                                                        // p -= W mu        (defcg.jl:302)
-        // pcg_update_p of iteration k may already have set done_at = k: the projection of this last
-        // direction is then irrelevant, and kernels of iteration k still run (done_at < k is false)
-        kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)defl->k * 8, c->stream>>>(n, defl->k, -1.0, defl->W, n, defl->mu, 1.0,
-                                                                                     c->d_p.p, done_at, k);
-        c->launches++;
-      }
-    }
+    run_iterations(c, I, k, kend, &kt);
+    k = kend;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_flag, &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1542,6 +1583,95 @@ int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const do
     h->launches++;
     CUDA_TRY(cudaMemcpyAsync(mat_col(h, Cm, cc, kq), tmp.p, (size_t)(h->n_gamma * kq) * 8, cudaMemcpyDeviceToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int64_t W, int64_t AW, int64_t nvec,
+                    const double* WtAW, const double* WtAW_inv, const double* WtW, const double* WtW_inv, int64_t m,
+                    int64_t V, int64_t vcol0, double rTz, double tol, int64_t it0, int64_t maxit, double* alpha_out,
+                    double* beta_out, double* res_out, int64_t* n_done, double* rTz_out) {
+  return guarded([&]() {
+    require(h && alpha_out && beta_out && res_out && n_done && rTz_out, "null argument");
+    require(m >= 1 && it0 >= 1 && maxit > it0 && maxit < INT_MAX && nvec >= 0 && nvec <= 4096, "bad argument");
+    require(nvec == 0 || (WtAW && WtAW_inv), "deflation needs WtAW and its inverse");
+    require((WtW == nullptr) == (WtW_inv == nullptr), "WtW and its inverse come together");
+    require(WtW == nullptr || nvec > 0, "projection of r needs W");
+    finalize(h);
+    use_device(h);
+    Ctx* c = h;
+    const int n = (int)c->n_gamma;
+    const int k = (int)nvec;
+    m = std::min<int64_t>(m, maxit - it0);
+    if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
+    IterCtx I;
+    I.A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
+    I.precond = precond;
+    I.x = mat_col(h, wk, 0, 5);
+    I.r = I.x + (size_t)n;
+    I.z = I.x + (size_t)2 * n;
+    I.p = I.x + (size_t)3 * n;
+    I.Ap = I.x + (size_t)4 * n;
+    if (precond) require(c->have_pinv, "kb200_upload_nn_pinv was not called");
+    if (assembled) require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
+    if (V >= 0) I.vbase = mat_col(h, V, vcol0, m);
+    DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2, dhist;
+    Defl D, DR;
+    if (k > 0) {
+      auto up = [&](DevBuf<double>& b, const double* src) {
+        b.alloc((size_t)k * k);
+        CUDA_TRY(cudaMemcpyAsync(b.p, src, (size_t)k * k * 8, cudaMemcpyHostToDevice, c->stream));
+      };
+      up(dM, WtAW);
+      up(dMinv, WtAW_inv);
+      dy.alloc(k);
+      dmu.alloc(k);
+      D.k = k;
+      D.W = mat_col(h, W, 0, k);
+      D.AW = mat_col(h, AW, 0, k);
+      D.M = dM.p;
+      D.Minv = dMinv.p;
+      D.y = dy.p;
+      D.mu = dmu.p;
+      I.defl = &D;
+      if (WtW) {
+        up(dM2, WtW);
+        up(dM2inv, WtW_inv);
+        dy2.alloc(k);
+        dmu2.alloc(k);
+        DR = D;
+        DR.M = dM2.p;
+        DR.Minv = dM2inv.p;
+        DR.y = dy2.p;
+        DR.mu = dmu2.p;
+        I.deflR = &DR;
+      }
+    }
+    const size_t nh = (size_t)2 * (size_t)(it0 + m + 2);
+    dhist.alloc(nh);
+    CUDA_TRY(cudaMemsetAsync(dhist.p, 0, nh * 8, c->stream));
+    I.hist = dhist.p;
+    I.k0 = 1;
+    kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, rTz, tol, (int)it0, (int)maxit);
+    c->launches++;
+    run_iterations(c, I, 1, (int)m + 1, nullptr);
+    // one synchronisation per burst: state, alpha/beta history, residual norms
+    std::vector<double> hh(nh), rr((size_t)m);
+    kb::PcgState hs;
+    CUDA_TRY(cudaMemcpyAsync(&hs, c->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hh.data(), dhist.p, nh * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(rr.data(), c->d_res.p + it0, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (hs.fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
+    if (hs.fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+    const int64_t done = (int64_t)hs.it - it0;
+    require(done >= 0 && done <= m, "internal: burst iteration count out of range");
+    for (int64_t j = 0; j < done; ++j) {
+      alpha_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1)];
+      beta_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1) + 1];
+      res_out[j] = rr[(size_t)j];
+    }
+    *n_done = done;
+    *rTz_out = hs.rTz;
   });
 }
 

@@ -755,7 +755,7 @@ pcg_update_xr_kernel(int n, int nb, const double* p, const double* Ap, double* x
 // Optionally stores vcol = z / sqrt(rTz') (eigcg.jl:242).
 __global__ void __launch_bounds__(kVecThreads)
 pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* partB, const double* partC,
-                    PcgState* st, double* res_norm, double* vcol, int iter) {
+                    PcgState* st, double* res_norm, double* vcol, double* hist, int iter) {
   __shared__ double red[kVecThreads / 32];
   if (st->done_at < iter) return;
   const double rTr = sum_partials(partB, nb, red);
@@ -776,6 +776,10 @@ pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* par
     st->rTz = rTz_new;
     st->beta = beta;
     res_norm[it - 1] = sqrt(rTr);
+    if (hist != nullptr) {  // alpha, beta of this iteration (the recycling solvers build V'AV from them)
+      hist[2 * it] = st->alpha;
+      hist[2 * it + 1] = beta;
+    }
     if (!((it < st->maxit) && (sqrt(rTr) > st->tol))) st->done_at = iter;
   }
 }
@@ -863,8 +867,8 @@ pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const
 template <bool kX>
 __global__ void __launch_bounds__(kVecThreads)
 pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, double* z, const double* r,
-                   double* p, const double* partB, double* partC, PcgState* st, double* res_norm, double* vcol, int iter,
-                   unsigned int* counter, unsigned int target, const XchParams X) {
+                   double* p, const double* partB, double* partC, PcgState* st, double* res_norm, double* vcol, double* hist,
+                   int iter, unsigned int* counter, unsigned int target, const XchParams X) {
   __shared__ double red[kVecThreads / 32];
   pdl_trigger();
   pdl_wait();
@@ -899,8 +903,23 @@ pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const 
     st->rTz = rTz_new;
     st->beta = beta;
     res_norm[it - 1] = sqrt(rTr);
+    if (hist != nullptr) {
+      hist[2 * it] = st->alpha;
+      hist[2 * it + 1] = beta;
+    }
     if (!((it < st->maxit) && (sqrt(rTr) > st->tol))) st->done_at = iter;
   }
+}
+
+// State of a recurrence continued from host-side scalars (kb200_pcg_burst)
+__global__ void pcg_burst_init_kernel(PcgState* st, double rTz, double tol, int it, int maxit) {
+  st->rTz = rTz;
+  st->rTz_old = rTz;
+  st->tol = tol;
+  st->it = it;
+  st->maxit = maxit;
+  st->fail = 0;
+  st->done_at = 0x7fffffff;
 }
 
 // ---------------------------------------------------------------------------------------------

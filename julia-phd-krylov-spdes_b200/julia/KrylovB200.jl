@@ -195,6 +195,23 @@ gemv_t(S, A, col0, k, x, xc) = (y = Vector{Float64}(undef, k); chk(ccall((:kb200
 gemv_n(S, a, A, col0, k, mu, b, y, yc) = chk(ccall((:kb200_op_gemv_n, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Int64), S.h, a, A, col0, k, mu, b, y, yc))
 gemm_tn(S, A, ca, ka, B, cb, kb) = (C = Matrix{Float64}(undef, ka, kb); chk(ccall((:kb200_op_gemm_tn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}), S.h, A, ca, ka, B, cb, kb, C)); C)
 gemm_nn(S, A, ca, ka, Q::Matrix{Float64}, C, cc) = chk(ccall((:kb200_op_gemm_nn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64), S.h, A, ca, ka, Q, size(Q, 2), C, cc))
+# Up to m iterations of the (deflated) recurrence on the device without host synchronisation: the body
+# of the loops eigcg.jl:185-246 / defcg.jl:400-448 between two restarts (see ../solvers.py: eigpcg,
+# eigdefpcg).  Returns (n_done, alpha, beta, res, rTz); V[:, vcol0 + j] receives z / sqrt(rTz).
+function pcg_burst(S, precond::Bool, wk, m, rTz, tol, it0, maxit; V=-1, vcol0=0, W=-1, AW=-1, nvec=0,
+                   WtAW::Union{Matrix{Float64},Nothing}=nothing, WtW::Union{Matrix{Float64},Nothing}=nothing)
+  al = Vector{Float64}(undef, m); be = similar(al); rs = similar(al)
+  nd = Ref{Int64}(0); rz = Ref{Float64}(0)
+  ptr(A) = A === nothing ? Ptr{Float64}(C_NULL) : pointer(A)
+  A1i = WtAW === nothing ? nothing : inv(WtAW); A2i = WtW === nothing ? nothing : inv(WtW)
+  GC.@preserve WtAW WtW A1i A2i chk(ccall((:kb200_pcg_burst, LIB), Cint,
+      (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64,
+       Int64, Int64, Float64, Float64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Float64}),
+      S.h, S.assembled ? 1 : 0, precond ? 1 : 0, wk, W, AW, nvec, ptr(WtAW), ptr(A1i), ptr(WtW), ptr(A2i), m,
+      V, vcol0, rTz, tol, it0, maxit, al, be, rs, nd, rz))
+  k = nd[]
+  return k, al[1:k], be[1:k], rs[1:k], rz[]
+end
 end
 
 """

@@ -156,8 +156,9 @@ def defpcg_hostloop(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None,
         dv.free()
 
 
-def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0):
-    """eigcg.jl:143-267.  Returns (x, it, res_norm, V[:, 1:nvec])."""
+def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, burst=True):
+    """eigcg.jl:143-267.  Returns (x, it, res_norm, V[:, 1:nvec]).  burst=False: every iteration driven
+    from the host (the cross-check of the device bursts)."""
     n = x.size
     dv = _Dev(A, M)
     h = dv.h
@@ -182,6 +183,19 @@ def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit
         hlpr = 0.0
         tol = EPS * np.linalg.norm(b)
         while it < maxit and res_norm[it - 1] > tol:                            # :185
+            if burst and not just_restarted and ivec < spdim - 1:
+                # the iterations up to the next restart are plain PCG steps that append a column to V and two
+                # entries to V'AV: run them on the device in one go (kb200_pcg_burst), one synchronisation
+                nd, al, be, rs, rTz = h.pcg_burst(A.assembled, M is not None, dv.wk, spdim - 1 - ivec, rTz, tol, it, maxit,
+                                                  V=Vd, vcol0=ivec + 1)
+                for j in range(nd):
+                    it += 1
+                    res_norm[it - 1] = rs[j]
+                    VtAV[ivec, ivec] += 1.0 / al[j]                             # :206
+                    ivec += 1                                                   # V[:, ivec] stored by the device
+                    VtAV[ivec - 1, ivec] = -np.sqrt(be[j]) / al[j]
+                    VtAV[ivec, ivec] = be[j] / al[j]
+                continue
             dv.A(dv.P, dv.AP)
             d = dv.dot(dv.P, dv.AP)
             alpha = rTz / d
@@ -232,8 +246,8 @@ def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit
         dv.free()
 
 
-def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0):
-    """defcg.jl:337-473.  Returns (x, it, res_norm, V[:, 1:nvec])."""
+def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0, burst=True):
+    """defcg.jl:337-473.  Returns (x, it, res_norm, V[:, 1:nvec]).  burst=False: host-driven iterations."""
     n, nvec = W.shape
     dv = _Dev(A, M)
     h = dv.h
@@ -269,6 +283,19 @@ def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit
         h.op_axpby(1.0 / np.sqrt(rTz), dv.wk, dv.Z, 0.0, Vd, ivec)
         tol = EPS * np.linalg.norm(b)
         while it < maxit and res_norm[it - 1] > tol:                            # :400
+            if burst and ivec < spdim - 1:
+                nd, al, be, rs, rTz = h.pcg_burst(A.assembled, M is not None, dv.wk, spdim - 1 - ivec, rTz, tol, it, maxit,
+                                                  V=Vd, vcol0=ivec + 1, W=Wd, AW=AWd, nvec=nvec, WtAW=WtAW, WtW=WtW)
+                for j in range(nd):
+                    it += 1
+                    res_norm[it - 1] = rs[j]
+                    VtAV[ivec, ivec] += 1.0 / al[j]                             # :417
+                    ivec += 1
+                    VtAV[ivec - 1, ivec] = -np.sqrt(be[j]) / al[j]
+                    VtAV[ivec, ivec] = be[j] / al[j]
+                if nd:
+                    just_restarted = False
+                continue
             dv.A(dv.P, dv.AP)
             d = dv.dot(dv.P, dv.AP)
             alpha = rTz / d
