@@ -124,6 +124,7 @@ struct kb200_ctx {
   size_t xch_flags_off = 0;
   int xch_npad = 0;
   uint32_t xch_seq = 0;
+  int gemv_rows = 0;                // rows per CTA of the dense GEMV (0: automatic)
   int vec_threads = 0;              // block size of the interface-vector kernels (0: automatic, 256 or 1024)
   int pdl = 0;                      // option: programmatic dependent launch inside the fused PCG loop
   bool pdl_now = false;             // set while the fused loop enqueues (adjacent kernels only)
@@ -560,9 +561,8 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
   P.out_loc = out_loc;
   P.done_at = done_at;
   P.iter = iter;
-  // rows per CTA: 32 when the grid is large anyway, 8 (one row per warp) when few subdomains are local
-  const int64_t tiles32 = (c->max_gd + kb::kGemvRowsPerCta - 1) / kb::kGemvRowsPerCta;
-  P.rows_per_cta = (tiles32 * nloc >= 2048) ? kb::kGemvRowsPerCta : 8;
+  // rows per CTA: 32 measured best from 32 to 256 local subdomains (8 / 16 / 64 slower: profiles/README.md)
+  P.rows_per_cta = c->gemv_rows > 0 ? c->gemv_rows : kb::kGemvRowsPerCta;
   dim3 grid((unsigned)((c->max_gd + P.rows_per_cta - 1) / P.rows_per_cta), (unsigned)nloc, 1);
   if (c->pdl_now) {
     cudaLaunchConfig_t cfg;
@@ -850,6 +850,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "adaptive_lanes" || k == "lane_min" || k == "lane_max") {
       require(!h->finalized && value >= 0 && value <= 256, "lane options must be set before the first operation");
       (k == "adaptive_lanes" ? h->adaptive_lanes : k == "lane_min" ? h->lane_min : h->lane_max) = (int)value;
+    } else if (k == "gemv_rows") {
+      require(value == 0 || value == 8 || value == 16 || value == 32 || value == 64, "gemv_rows is 0, 8, 16, 32 or 64");
+      h->gemv_rows = (int)value;
     } else if (k == "vec_threads") {
       require(!h->finalized && (value == 0 || value == 256 || value == 512 || value == 1024), "vec_threads is 0, 256, 512 or 1024, before the first operation");
       h->vec_threads = (int)value;

@@ -470,11 +470,11 @@ struct GemvParams {
   double* out_loc;
   const int* done_at;
   int iter;
-  int rows_per_cta;         // 32 on a full GPU; 8 when few subdomains are local (multi-GPU shards), for more CTAs
+  int rows_per_cta;         // 32 (kGemvRowsPerCta) unless overridden by the gemv_rows option
 };
 constexpr int kGemvRowsPerCta = 32;
 
-__global__ void __launch_bounds__(256) dense_gemv_kernel(const GemvParams P) {
+__global__ void __launch_bounds__(256, 4) dense_gemv_kernel(const GemvParams P) {
   extern __shared__ double xs[];
   pdl_trigger();
   pdl_wait();
@@ -500,16 +500,28 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const GemvParams P) {
     if (i >= n) break;
     const double* mrow = M + (int64_t)i * n;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int j = lane;
-    for (; j + 96 < n; j += 128) {
-      const double m0 = __ldg(mrow + j), m1 = __ldg(mrow + j + 32), m2 = __ldg(mrow + j + 64),
-                   m3 = __ldg(mrow + j + 96);
-      a0 = fma(m0, xs[j], a0);
-      a1 = fma(m1, xs[j + 32], a1);
-      a2 = fma(m2, xs[j + 64], a2);
-      a3 = fma(m3, xs[j + 96], a3);
+    // 16 loads per lane in flight (a whole row of up to 512 entries at once): the kernel is bound by memory
+    // latency, not by arithmetic; element j = j0 + lane + 32 u feeds accumulator u & 3 (fixed order)
+    for (int j0 = 0; j0 < n; j0 += 512) {
+      double m[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        // clamped address, unconditional volatile load: the 16 loads are issued back to back (left to the
+        // compiler, each load is sunk next to its FMA and the row is read one latency at a time)
+        const int j = min(j0 + lane + 32 * u, n - 1);
+        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(m[u]) : "l"(mrow + j));
+      }
+      __syncwarp();  // keeps the arithmetic below the block of loads
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        const int j = j0 + lane + 32 * u;
+        // (a clamped load beyond the row end multiplies a zero)
+        a0 = fma(m[u], (j < n) ? xs[j] : 0.0, a0);
+        a1 = fma(m[u + 1], (j + 32 < n) ? xs[j + 32] : 0.0, a1);
+        a2 = fma(m[u + 2], (j + 64 < n) ? xs[j + 64] : 0.0, a2);
+        a3 = fma(m[u + 3], (j + 96 < n) ? xs[j + 96] : 0.0, a3);
+      }
     }
-    for (; j < n; j += 32) a0 = fma(__ldg(mrow + j), xs[j], a0);
     double a = (a0 + a1) + (a2 + a3);
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) {

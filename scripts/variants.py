@@ -27,7 +27,13 @@ d0, d1 = (sd.ndom * rank) // world, (sd.ndom * (rank + 1)) // world
 pr = PB.realization(base, ireal=1, dom_range=(d0, d1))
 if world > 1:
     bg = torch.from_numpy(pr.blocks.b_G).cuda(); dist.all_reduce(bg); pr.blocks.b_G = bg.cpu().numpy()
-S = fem.B200SchurOperator(sd, pr.blocks, pr.factors, device=lr, rank=rank, world=world, nccl_id=nccl_id, profile=True)
+# OPTS="shard_world=8+shard_rank=3": emulate the per-GPU shard of a multi-GPU run on one GPU
+opts = {k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("OPTS", "").split("+") if kv)}
+if "shard_world" in opts:
+    d0, d1 = (sd.ndom * opts["shard_rank"]) // opts["shard_world"], (sd.ndom * (opts["shard_rank"] + 1)) // opts["shard_world"]
+    pr = PB.realization(base, ireal=1, dom_range=(d0, d1))
+S = fem.B200SchurOperator(sd, pr.blocks, pr.factors, device=lr, rank=rank, world=world, nccl_id=nccl_id, profile=True,
+                          options=opts)
 # identity-like preconditioner blocks are enough to time the kernels: the cost of M does not depend on its values
 rng = np.random.default_rng(0)
 PiS = {d: np.eye(sd.gamma_l2g[d].size) * 0.5 for d in range(d0, d1)}
