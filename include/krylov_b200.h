@@ -54,13 +54,23 @@ const char* kb200_last_error(void);
 int kb200_create(int device_id, kb200_handle* out);
 /* One process per GPU: `nccl_id` is the 128-byte ncclUniqueId produced on rank 0 by
  * kb200_nccl_unique_id and distributed by the host (torch.distributed / MPI / files).  Subdomains
- * are sharded over ranks; every apply ends in one NCCL all-reduce of the interface vector
- * (reference sketch: Fem/EllipticPdePllDomainDecomposition.jl:1-18, `@distributed (+)`). */
+ * are sharded over ranks; every apply ends in the sum of the ranks' partial interface vectors
+ * (reference sketch: Fem/EllipticPdePllDomainDecomposition.jl:1-18, `@distributed (+)`), carried out
+ * inside the assembly kernel over NVLink peer memory (CUDA IPC buffers exchanged through the
+ * communicator at the first operation) or, if that mapping is unavailable, by ncclAllReduce.
+ * All ranks must issue the same sequence of operator applications / solves. */
 int kb200_nccl_unique_id(void* out128);
 int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, kb200_handle* out);
 int kb200_destroy(kb200_handle h);
-/* Tunables: "csize" (CTAs per subdomain cluster: 1,2,4,8), "profile" (0/1: time the two
- * dominant kernels with CUDA events), "check_every" (iterations between convergence polls). */
+/* Tunables (0 = automatic where it applies): "csize" (CTAs per subdomain cluster: 1,2,4,8,16),
+ * "warps" (consumer warps of the stream kernel: 8, or 16 with one CTA per SM), "stages" (ring depth,
+ * 2..12), "lane_entries" / "pad_tol_pct" / "min_block" / "adaptive_lanes" / "warp_private" (host
+ * analysis of the stream, see csrc/plan.h), "profile" (0/1: sample the two dominant kernels with
+ * CUDA events), "check_every" (iterations between convergence polls, default 32), "fuse_pcg" (1:
+ * plain PCG runs assembly + dot + vector update in one kernel), "peer_exchange" (1: interface sums
+ * over NVLink peer memory; 0: NCCL all-reduce), "vec_threads" / "gemv_rows" (block shapes of the
+ * interface-vector / dense GEMV kernels), "pdl" (programmatic dependent launch, default 0),
+ * "shard_world" / "shard_rank" (hold one shard of the subdomains without a communicator). */
 int kb200_set_option(kb200_handle h, const char* name, int64_t value);
 
 /* ---- setup (once per mesh / per realization) ------------------------------------------------- */
