@@ -343,7 +343,7 @@ class Handle:
         _chk(lib().kb200_get_stats(self.h, _p(s, C.c_double), C.c_int64(16)))
         keys = ["nnz_L", "stream_entries", "stream_rows", "stream_slices", "stream_bytes", "max_levels",
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
-                "consumer_warps", "ring_stages"]
+                "consumer_warps", "ring_stages", "merge_depth", "min_block"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):

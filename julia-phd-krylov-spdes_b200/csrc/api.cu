@@ -124,6 +124,7 @@ struct kb200_ctx {
   size_t xch_flags_off = 0;
   int xch_npad = 0;
   uint32_t xch_seq = 0;
+  int merge_depth = 0;              // supernode grouping depth of the host analysis (0: automatic)
   int gemv_rows = 0;                // rows per CTA of the dense GEMV (0: automatic)
   int vec_threads = 0;              // block size of the interface-vector kernels (0: automatic, 256 or 1024)
   int pdl = 0;                      // option: programmatic dependent launch inside the fused PCG loop
@@ -225,7 +226,6 @@ void finalize(Ctx* c) {
     if (c->stages == 0) c->stages = (c->warps == 16) ? 6 : 3;
   }
   opt.warps = c->warps;
-  if (c->min_block >= 0) opt.min_block = c->min_block;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
   if (c->pad_tol_pct >= 0) opt.pad_tol = c->pad_tol_pct / 100.0;
   if (c->adaptive_lanes >= 0) opt.adaptive_lanes = c->adaptive_lanes;
@@ -233,9 +233,27 @@ void finalize(Ctx* c) {
   if (c->lane_max > 0) opt.lane_max = c->lane_max;
   if (c->warp_private >= 0) opt.warp_private = c->warp_private;
   if (c->private_split > 0) opt.private_split = c->private_split;
-  {
+  // Grouping of supernodes into inverted blocks (plan.cpp): deeper groups = fewer dependency levels but
+  // more scratch slots in the shared-memory vector.  With two CTAs per SM the vector must stay below half
+  // the SM's shared memory: the preferred grouping is tried first and the analysis falls back when a
+  // subdomain would push the kernel to one CTA per SM.
+  int smem_optin_build = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_optin_build, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+  const int64_t fixed_smem = (int64_t)c->stages * kb::kChunkBytes + kb::kMaxSlots * 8;
+  const int64_t two_cta_budget = (smem_optin_build - 2 * 1024) / 2 - 1024 - fixed_smem;  // bytes for S (1 KB/CTA reserved + static)
+  struct Try { int merge_depth, min_block; };
+  std::vector<Try> tries;
+  if (c->merge_depth > 0 || c->min_block >= 0) {
+    tries.push_back({c->merge_depth > 0 ? c->merge_depth : 1, c->min_block >= 0 ? c->min_block : 4});
+  } else if (c->warps == 16) {
+    tries.push_back({3, 4});   // one CTA per SM: room for the scratch slots of deep groups
+  } else {
+    tries.push_back({2, 4});
+    tries.push_back({2, 8});
+    tries.push_back({1, 4});
+  }
+  auto build_all = [&](const kb::BuildOptions& o) {
     std::atomic<int64_t> next(0);
-    std::string first_err;
     std::atomic<bool> failed(false);
     const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
     std::vector<std::thread> th;
@@ -246,7 +264,7 @@ void finalize(Ctx* c) {
           const int64_t k = next.fetch_add(1);
           if (k >= nloc || failed.load()) break;
           try {
-            kb::build_domain_plan(c->doms[c->d0 + k].in, opt, plans[k]);
+            kb::build_domain_plan(c->doms[c->d0 + k].in, o, plans[k]);
           } catch (const std::exception& e) {
             errs[t] = "subdomain " + std::to_string(c->d0 + k) + ": " + e.what();
             failed.store(true);
@@ -257,6 +275,17 @@ void finalize(Ctx* c) {
     if (failed.load())
       for (auto& e : errs)
         if (!e.empty()) throw KbError(KB200_ERR_INPUT, e);
+  };
+  for (size_t ti = 0; ti < tries.size(); ++ti) {
+    opt.merge_depth = tries[ti].merge_depth;
+    opt.min_block = tries[ti].min_block;
+    build_all(opt);
+    int ms = 0;
+    for (int64_t k = 0; k < nloc; ++k)
+      for (auto& D : plans[k].ctas) ms = std::max(ms, D.smem_doubles);
+    c->stats[14] = opt.merge_depth;
+    c->stats[15] = opt.min_block;
+    if (c->warps != kb::kWarps || (int64_t)ms * 8 <= two_cta_budget || ti + 1 == tries.size()) break;
   }
   // offsets
   c->I_base.assign(nloc + 1, 0);
@@ -850,6 +879,9 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "adaptive_lanes" || k == "lane_min" || k == "lane_max") {
       require(!h->finalized && value >= 0 && value <= 256, "lane options must be set before the first operation");
       (k == "adaptive_lanes" ? h->adaptive_lanes : k == "lane_min" ? h->lane_min : h->lane_max) = (int)value;
+    } else if (k == "merge_depth") {
+      require(!h->finalized && value >= 0 && value <= 8, "merge_depth in [0, 8], before the first operation");
+      h->merge_depth = (int)value;
     } else if (k == "gemv_rows") {
       require(value == 0 || value == 8 || value == 16 || value == 32 || value == 64, "gemv_rows is 0, 8, 16, 32 or 64");
       h->gemv_rows = (int)value;

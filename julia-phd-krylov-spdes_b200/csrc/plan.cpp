@@ -516,70 +516,125 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     }
   }
 
-  // ---- supernode chains with dense diagonal blocks -> inverted blocks ---------------------------
-  // A chain a..b of the elimination tree with parent[j] = j+1 and nested column structures has a
-  // dense lower-triangular diagonal block D; with Dinv = D^{-1} precomputed, the b-a+1 dependent
-  // rows collapse into two parallel steps (off-block sums, then a dense triangular product), in
-  // both sweeps.  blk[i] = block index or -1.
-  std::vector<int32_t> blk(n, -1);
-  struct Block { int a, b; std::vector<double> Dinv; };  // Dinv row-major s x s (lower)
+  // ---- supernodes with inverted diagonal blocks ---------------------------------------------------
+  // A chain a..b of the elimination tree with parent[j] = j+1 and nested column structures (a supernode)
+  // has a dense lower-triangular diagonal block D; with Dinv = D^{-1} precomputed, its b-a+1 dependent
+  // rows collapse into two parallel steps (off-block sums, then a triangular product), in both sweeps.
+  // The same holds for any set J of nodes that is closed along tree paths: x_J = L_JJ^{-1} (b_J - L_{J,rest}
+  // x_rest) only needs values of descendants outside J.  merge_depth > 1 groups every supernode at depth
+  // d (in the tree of supernodes of one CTA / warp / the top) with its descendants down to depth d +
+  // merge_depth - 1: the dependency levels of that part of the tree drop from 2 per supernode to 2 per
+  // group, for an inverse that is only as dense as the factor's own coupling between those supernodes.
+  // blk[i] = block index or -1; nodes of a block ascending.
+  std::vector<int32_t> blk(n, -1), pos_in_blk(n, -1);
+  struct Block { std::vector<int32_t> nodes; std::vector<double> Dinv; };  // Dinv row-major s x s (lower)
   std::vector<Block> blocks;
-  if (opt.min_block > 0) {
+  if (opt.min_block > 0 && n > 0) {
     auto ccount = [&](int j) { return L.colptr[j + 1] - L.colptr[j]; };
-    int a = 0;
-    while (a < n) {
-      int b = a;
-      while (b + 1 < n && parent[b] == b + 1 && ccount(b) == ccount(b + 1) + 1 && owner[b] == owner[b + 1] && wown[b] == wown[b + 1] &&
-             (b + 1 - a + 1) <= opt.max_block)
-        ++b;
-      const int sz = b - a + 1;
-      bool ok = sz >= opt.min_block;
-      if (ok)
-        for (int j = a; j <= b && ok; ++j)
-          for (int t = 0; t <= b - j; ++t)
-            if (L.rowval[L.colptr[j] + t] != j + t) { ok = false; break; }
-      if (ok) {
-        Block B;
-        B.a = a;
-        B.b = b;
-        std::vector<double> D((size_t)sz * sz, 0.0);
-        for (int j = a; j <= b; ++j)
-          for (int t = 0; t <= b - j; ++t) D[(size_t)(j + t - a) * sz + (j - a)] = L.nzval[L.colptr[j] + t];
-        B.Dinv.assign((size_t)sz * sz, 0.0);
-        for (int c0 = 0; c0 < sz; ++c0) {
-          B.Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
-          for (int i = c0 + 1; i < sz; ++i) {
-            double acc = 0.0;
-            for (int k = c0; k < i; ++k) acc += D[(size_t)i * sz + k] * B.Dinv[(size_t)k * sz + c0];
-            B.Dinv[(size_t)i * sz + c0] = -acc / D[(size_t)i * sz + i];
-          }
-        }
-        for (int j = a; j <= b; ++j) blk[j] = (int)blocks.size();
-        blocks.push_back(std::move(B));
+    // maximal chains
+    std::vector<int32_t> chain_of(n, -1), chain_a, chain_b;
+    for (int a0 = 0; a0 < n;) {
+      int b0 = a0;
+      while (b0 + 1 < n && parent[b0] == b0 + 1 && ccount(b0) == ccount(b0 + 1) + 1 && owner[b0] == owner[b0 + 1] &&
+             wown[b0] == wown[b0 + 1] && (b0 + 1 - a0 + 1) <= opt.max_block)
+        ++b0;
+      for (int j = a0; j <= b0; ++j) chain_of[j] = (int32_t)chain_a.size();
+      chain_a.push_back(a0);
+      chain_b.push_back(b0);
+      a0 = b0 + 1;
+    }
+    const int nch = (int)chain_a.size();
+    // tree of chains (within one scope: same CTA, same warp or the top), depths, groups
+    std::vector<int32_t> cpar(nch, -1), depth(nch, 0), groot(nch, -1);
+    for (int c = nch - 1; c >= 0; --c) {
+      const int pb = parent[chain_b[c]];
+      if (pb >= 0 && owner[pb] == owner[chain_b[c]] && wown[pb] == wown[chain_b[c]]) cpar[c] = chain_of[pb];
+      depth[c] = cpar[c] >= 0 ? depth[cpar[c]] + 1 : 0;
+      const int md = std::max(1, opt.merge_depth);
+      // chains shorter than min_block are leaves of the forest of supernodes in practice: they are not
+      // worth a block of their own, but they may ride with a group
+      groot[c] = (cpar[c] >= 0 && depth[c] % md != 0) ? groot[cpar[c]] : c;
+    }
+    // group sizes; oversized groups fall back to one block per chain
+    std::vector<int64_t> gsize(nch, 0);
+    for (int c = 0; c < nch; ++c) gsize[groot[c]] += chain_b[c] - chain_a[c] + 1;
+    for (int c = 0; c < nch; ++c)
+      if (gsize[groot[c]] > opt.max_block) groot[c] = -2 - c;  // marked: alone
+    for (int c = 0; c < nch; ++c)
+      if (groot[c] <= -2) groot[c] = c;
+    std::fill(gsize.begin(), gsize.end(), 0);
+    for (int c = 0; c < nch; ++c) gsize[groot[c]] += chain_b[c] - chain_a[c] + 1;
+    // a group of several chains must be closed along tree paths: true by construction unless an oversized
+    // group was dissolved above (members become their own roots, which keeps every remaining group closed)
+    std::vector<int32_t> block_of_group(nch, -1);
+    for (int c = 0; c < nch; ++c) {
+      const int g = groot[c];
+      if (gsize[g] < opt.min_block) continue;
+      if (block_of_group[g] < 0) {
+        block_of_group[g] = (int32_t)blocks.size();
+        blocks.emplace_back();
       }
-      a = b + 1;
+      Block& B = blocks[block_of_group[g]];
+      for (int j = chain_a[c]; j <= chain_b[c]; ++j) {
+        blk[j] = block_of_group[g];
+        B.nodes.push_back(j);  // chains are visited in ascending order: nodes ascending
+      }
+    }
+    for (auto& B : blocks) {
+      const int sz = (int)B.nodes.size();
+      for (int k = 0; k < sz; ++k) pos_in_blk[B.nodes[k]] = k;
+      std::vector<double> D((size_t)sz * sz, 0.0);
+      for (int k = 0; k < sz; ++k) {
+        const int j = B.nodes[k];
+        for (int p = L.colptr[j]; p < L.colptr[j + 1]; ++p) {
+          const int i = L.rowval[p];
+          if (blk[i] == blk[j]) D[(size_t)pos_in_blk[i] * sz + k] = L.nzval[p];
+        }
+      }
+      B.Dinv.assign((size_t)sz * sz, 0.0);
+      for (int c0 = 0; c0 < sz; ++c0) {
+        B.Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
+        for (int i = c0 + 1; i < sz; ++i) {
+          double acc = 0.0;
+          bool any = false;
+          for (int k = c0; k < i; ++k) {
+            const double d = D[(size_t)i * sz + k], v = B.Dinv[(size_t)k * sz + c0];
+            if (d != 0.0 && v != 0.0) {
+              acc += d * v;
+              any = true;
+            }
+          }
+          B.Dinv[(size_t)i * sz + c0] = any ? -acc / D[(size_t)i * sz + i] : 0.0;
+        }
+      }
     }
   }
 
   // ---- dependency levels -----------------------------------------------------------------------
   // fe[i] / be[i]: level at which the (last) step producing x_i / v_i runs; a value is available
   // to steps of strictly higher levels.  For a block, step A (off-block sums) runs at level e-1 and
-  // step B (Dinv product) at level e.
+  // step B (Dinv product) at level e.  A block is handled when its last node is reached: in the forward
+  // sweep all its outside dependencies (descendants) have smaller indices, in the backward sweep all of
+  // them (ancestors of the group's root) larger ones.
   std::vector<int32_t> fe(n, 0), be(n, 0);
   auto same_scope = [&](int i, int j) { return (owner[i] >= 0) == (owner[j] >= 0); };
+  std::vector<int32_t> single(1);
   for (int i = 0; i < n; ++i) {
-    if (blk[i] >= 0 && i != blocks[blk[i]].a) continue;  // handled with the block head
-    const int lo = i, hi = blk[i] >= 0 ? blocks[blk[i]].b : i;
+    if (blk[i] >= 0 && i != blocks[blk[i]].nodes.back()) continue;  // handled with the block's last node
+    single[0] = i;
+    const std::vector<int32_t>& rows_of = blk[i] >= 0 ? blocks[blk[i]].nodes : single;
     int l = 0;
-    for (int r = lo; r <= hi; ++r)
+    for (int r : rows_of)
       for (int p = rptr[r]; p < rptr[r + 1]; ++p) {
         const int j = rcol[p];
-        if (j >= lo) continue;  // inside the block: absorbed by Dinv
+        if (blk[i] >= 0 && blk[j] == blk[i]) continue;  // inside the block: absorbed by Dinv
         if (same_scope(r, j)) {
           if (owner[r] >= 0 && owner[j] != owner[r])
             throw std::runtime_error("internal: row dependency crosses subtrees");
           if (wown[r] >= 0 && wown[j] != wown[r])
             throw std::runtime_error("internal: private row depends on another warp's subtree");
+          if (blk[j] >= 0 && blocks[blk[j]].nodes.back() > i)
+            throw std::runtime_error("internal: block depends on a block that is not complete");
           // the private phase of the forward sweep is complete before the first upper level
           if (wown[r] < 0 && wown[j] >= 0) l = std::max(l, 0);
           else l = std::max(l, fe[j] + 1);
@@ -588,16 +643,18 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         }
       }
     if (blk[i] >= 0) l += 1;  // step A at l, step B at l+1
-    for (int r = lo; r <= hi; ++r) fe[r] = l;
+    for (int r : rows_of) fe[r] = l;
   }
   for (int i = n - 1; i >= 0; --i) {
-    if (blk[i] >= 0 && i != blocks[blk[i]].b) continue;
-    const int hi = i, lo = blk[i] >= 0 ? blocks[blk[i]].a : i;
+    if (blk[i] >= 0 && i != blocks[blk[i]].nodes.back()) continue;
+    single[0] = i;
+    const std::vector<int32_t>& rows_of = blk[i] >= 0 ? blocks[blk[i]].nodes : single;
     int l = 0;
-    for (int r = lo; r <= hi; ++r)
+    for (int r : rows_of)
       for (int p = L.colptr[r] + 1; p < L.colptr[r + 1]; ++p) {
         const int k = L.rowval[p];
-        if (k <= hi) continue;
+        if (blk[i] >= 0 && blk[k] == blk[i]) continue;
+        if (k < i) throw std::runtime_error("internal: block is not closed along tree paths");
         if (owner[r] < 0) {
           if (owner[k] >= 0) throw std::runtime_error("internal: ancestor of a top node is not top");
           l = std::max(l, be[k] + 1);
@@ -611,7 +668,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         }
       }
     if (blk[i] >= 0) l += 1;
-    for (int r = lo; r <= hi; ++r) be[r] = l;
+    for (int r : rows_of) be[r] = l;
   }
 
   // ---- positions in the shared vectors ---------------------------------------------------------
@@ -767,18 +824,22 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
             if (same_scope(i, rcol[p])) push(xidx(rcol[p]), rval[p]);
         } else {
           const Block& B = blocks[blk[i]];
-          const int sz = B.b - B.a + 1;
-          // step A: t_i = b_i - sum_{j < a} L_ij x_j   (in place in slot i)
+          const int sz = (int)B.nodes.size();
+          const int pi = pos_in_blk[i];
+          // step A: t_i = b_i - sum_{j outside the block} L_ij x_j   (in place in slot i)
           bool any = false;
           for (int p = rptr[i]; p < rptr[i + 1]; ++p) {
             const int j = rcol[p];
-            if (j >= B.a || !same_scope(i, j)) continue;
+            if (blk[j] == blk[i] || !same_scope(i, j)) continue;
             if (!any) { begin_row(sidx(i), 1.0, fe[i] - 1, 0); any = true; }
             push(xidx(j), rval[p]);
           }
           // step B: x_i = sum_{k in [a, i]} Dinv[i,k] t_k   (fresh write to the scratch slot)
           begin_row(scridx(i), -1.0, fe[i], 1);
-          for (int k = B.a; k <= i; ++k) push(sidx(k), B.Dinv[(size_t)(i - B.a) * sz + (k - B.a)]);
+          for (int pk = 0; pk <= pi; ++pk) {
+            const double v = B.Dinv[(size_t)pi * sz + pk];
+            if (v != 0.0) push(sidx(B.nodes[pk]), v);
+          }
         }
       }
     };
@@ -791,18 +852,22 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
           for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) push(sidx(L.rowval[p]), L.nzval[p]);
         } else {
           const Block& B = blocks[blk[i]];
-          const int sz = B.b - B.a + 1;
-          // step A': t_i = y_i - sum_{k > b} L_ki v_k   (y_i lives in the scratch slot)
+          const int sz = (int)B.nodes.size();
+          const int pi = pos_in_blk[i];
+          // step A': t_i = y_i - sum_{k outside the block} L_ki v_k   (y_i lives in the scratch slot)
           bool any = false;
           for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) {
             const int k = L.rowval[p];
-            if (k <= B.b) continue;
+            if (blk[k] == blk[i]) continue;
             if (!any) { begin_row(scridx(i), 1.0, be[i] - 1, 0); any = true; }
             push(sidx(k), L.nzval[p]);
           }
           // step B': v_i = sum_{k in [i, b]} Dinv[k,i] t_k   (fresh write to slot i)
           begin_row(sidx(i), -1.0, be[i], 1);
-          for (int k = i; k <= B.b; ++k) push(scridx(k), B.Dinv[(size_t)(k - B.a) * sz + (i - B.a)]);
+          for (int pk = pi; pk < sz; ++pk) {
+            const double v = B.Dinv[(size_t)pk * sz + pi];
+            if (v != 0.0) push(scridx(B.nodes[pk]), v);
+          }
         }
       }
     };

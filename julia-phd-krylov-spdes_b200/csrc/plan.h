@@ -68,7 +68,7 @@ enum Section : int {
 // then the levels of the remaining ("upper") own nodes; backward sweep: upper levels first.
 constexpr uint16_t kTokBarrier = 0xffffu;
 constexpr int kChunkDirBytes = 48;  // room for (16 + 1) first-token indices, 16-byte aligned
-constexpr int kMaxSlots = 1024;    // scratch doubles used when the top right-hand side is combined
+constexpr int kMaxSlots = 256;     // scratch doubles used when the top right-hand side is combined (passes of kMaxSlots)
 struct alignas(16) SliceHdr {
   uint16_t nent;    // stored entries = kmax * nrows * T
   uint16_t kmax;    // steps = ceil(longest row / T)
@@ -140,6 +140,7 @@ struct BuildOptions {
   double pad_tol = 0.0;       // a slice only takes rows at least pad_tol x its longest row (0: no limit)
   int min_block = 4;          // invert dense diagonal blocks of supernode chains at least this long (0: off)
   int max_block = 1024;
+  int merge_depth = 1;        // supernodes of `merge_depth` consecutive depths of the supernode tree share one inverted block
   int max_smem_doubles = 28000;
   int warps = kWarps;         // consumer warps of the kernel that will run the plan (8 or 16): slot k of a level -> warp k % warps
   int warp_private = 0;       // 1: subtrees near the leaves are processed warp-privately (no CTA barriers)

@@ -22,7 +22,7 @@ for cs, nst, ex in [(a, b, e) for a in csizes for b in stages for e in extra]:
     st = S.h.stats()
     ms = S.h.time_kernel(0, 20)
     alg = parts['trisolve'] + parts['spmv']
-    print(f"csize={cs} stages={nst} {ex} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
+    print(f"csize={cs} stages={nst} {ex} finalize {tf:.1f}s schur kernel {ms:.3f} ms  stream {st['stream_bytes']/1e9:.3f} GB -> {st['stream_bytes']/ms/1e6:.0f} GB/s actual, algorithmic {alg/ms/1e6:.0f} GB/s | md {st['merge_depth']:.0f} mb {st['min_block']:.0f} levels {st['max_levels']:.0f} top {st['max_top']:.0f} smem {st['smem_bytes']:.0f} ctas {st['n_cta']:.0f}", flush=True)
     for fl in [int(v) for v in os.environ.get('FLAGS', '').split(',') if v]:
         S.h.set_option('dbg_flags', fl); print(f'   dbg_flags={fl}: schur kernel {S.h.time_kernel(0, 10):.3f} ms', flush=True); S.h.set_option('dbg_flags', 0)
     if os.environ.get('DBG'):

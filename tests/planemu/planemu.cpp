@@ -186,6 +186,7 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     opt.csize = csize;
     if (const char* e = std::getenv("KB200_MIN_BLOCK")) opt.min_block = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARPS")) opt.warps = std::atoi(e);
+    if (const char* e = std::getenv("KB200_MERGE_DEPTH")) opt.merge_depth = std::atoi(e);
     if (const char* e = std::getenv("KB200_ADAPTIVE_LANES")) opt.adaptive_lanes = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARP_PRIVATE")) opt.warp_private = std::atoi(e);
     if (const char* e = std::getenv("KB200_PRIVATE_SPLIT")) opt.private_split = std::atoi(e);
