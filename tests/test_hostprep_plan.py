@@ -95,7 +95,9 @@ def test_plan_program_matches_exact_solves(emu, csize, min_block):
 
 
 @pytest.mark.parametrize("env", [{}, {"KB200_WARPS": 16}, {"KB200_WARP_PRIVATE": 1},
-                                 {"KB200_WARP_PRIVATE": 1, "KB200_PRIVATE_SPLIT": 4}])
+                                 {"KB200_WARP_PRIVATE": 1, "KB200_PRIVATE_SPLIT": 4},
+                                 {"KB200_MERGE_DEPTH": 2}, {"KB200_MERGE_DEPTH": 3, "KB200_WARPS": 16},
+                                 {"KB200_MERGE_DEPTH": 4, "KB200_WARP_PRIVATE": 1}])
 @pytest.mark.parametrize("csize", [1, 4])
 def test_plan_variants_on_a_large_subdomain(emu, env, csize):
     """~4k interior nodes: levels hold more slices than consumer warps (balanced slots with empty
@@ -115,6 +117,36 @@ def test_plan_variants_on_a_large_subdomain(emu, env, csize):
     assert abs(u - ref).max() <= 1e-12 * abs(ref).max()
     if env.get("KB200_WARP_PRIVATE"):
         assert st[12] > 0       # rows were handled warp-privately
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_plan_on_irregular_factors(emu, seed):
+    """Random sparse SPD matrices under random and banded orderings (elimination trees that look nothing
+    like a nested-dissection tree: long chains, bushy forests, several roots): every cluster size,
+    supernode grouping depth and block threshold against a dense solve."""
+    rng = np.random.default_rng(seed)
+    n, ng = 260 + 40 * seed, 23
+    B = sp.random(n, n, density=0.012, random_state=seed, format="csr")
+    A = (B + B.T + sp.diags(np.full(n, 1.0))).tocsr()
+    A = (A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel())).tocsc()      # strictly diagonally dominant
+    if seed == 2:   # a disconnected matrix: forest with several roots
+        A = sp.block_diag([A[:n // 2, :n // 2], A[n // 2:, n // 2:]]).tocsc()
+    perm = rng.permutation(n).astype(np.int32) if seed != 1 else np.arange(n, dtype=np.int32)
+    L, _ = chol.cholesky(A, perm)
+    G = sp.random(n, ng, density=0.05, random_state=seed + 10, format="csc")
+    GG = (sp.random(ng, ng, density=0.3, random_state=seed + 20) + sp.eye(ng) * 5.0).tocsc()
+    xd, bI = rng.standard_normal(ng), rng.standard_normal(n)
+    Ad = A.toarray()
+    ref_apply = GG @ xd - G.T @ np.linalg.solve(Ad, G @ xd)
+    ref_bs = np.linalg.solve(Ad, bI - G @ xd)
+    for csize in (1, 2, 4):
+        for md in (1, 2, 3):
+            for mb in (0, 2, 4):
+                env = {"KB200_MERGE_DEPTH": md}
+                o, _, _ = run_emu(emu, perm, L, G, GG, csize, 0, xd, bI, min_block=mb, env=env)
+                assert abs(o - ref_apply).max() <= 1e-11 * abs(ref_apply).max(), (csize, md, mb)
+                _, u, _ = run_emu(emu, perm, L, G, GG, csize, 2, xd, bI, min_block=mb, env=env)
+                assert abs(u - ref_bs).max() <= 1e-11 * abs(ref_bs).max(), (csize, md, mb)
 
 
 def test_plan_edge_cases(emu):
