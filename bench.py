@@ -216,12 +216,13 @@ def main():
     alg = schur_kernel_algorithmic_bytes(pr, d0, d1)
     avg_ms = schur_ms / max(schur_launches, 1)
     achieved = alg / (avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("nx") == args.nx and tj.get("ndom") == args.ndom and world == 1:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = tj.get("source")
     B_iter, parts = PB.algorithmic_bytes_per_iteration(pr, (d0, d1))
     out = {
         "metric": "schur_pcg_solves_per_sec", "value": args.steps / (dev_ms * 1e-3), "unit": "solves/s",
@@ -233,7 +234,8 @@ def main():
                 "d2h_bytes_per_step": d2h // args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "schur_stream_kernel<MODE_APPLY>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "stream_bytes_per_launch": float(stats["stream_bytes"]), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      # launch durations are sampled (every 16th iteration is bracketed by events; an event between
                      # two kernels would serialise the programmatic dependent launch chain of the others)
