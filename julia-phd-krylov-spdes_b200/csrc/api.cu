@@ -639,6 +639,18 @@ kb::XchParams next_exchange(Ctx* c) {
   return X;
 }
 
+// Launches skipped on the device after convergence consume exchange numbers without exchanging.  The two
+// receive slots must alternate between consecutive REAL exchanges (see kernels.cuh), so after a stretch of
+// iterations the host -- which knows how many of the enqueued iterations really ran, identically on every
+// rank -- re-aligns the counter: the next exchange takes the slot the last real one did not use.
+void realign_exchange_slots(Ctx* c, uint32_t seq_before, int64_t iters_enqueued, int64_t iters_run) {
+  if (!c->peer_ok || iters_enqueued <= 0) return;
+  const uint32_t per_iter = (c->xch_seq - seq_before) / (uint32_t)iters_enqueued;
+  if (per_iter == 0 || iters_run >= iters_enqueued) return;  // nothing skipped: parity already alternates
+  const uint32_t last_real = seq_before + per_iter * (uint32_t)std::max<int64_t>(iters_run, 0);
+  if (((c->xch_seq + 1u) & 1u) == (last_real & 1u)) c->xch_seq++;
+}
+
 // y = sum_d R_d' loc_d (+ base), optionally partial dot with q.  In multi-rank mode the interface
 // vector is all-reduced and the dot is taken afterwards so that every rank sees identical scalars.
 void assemble(Ctx* c, const double* loc, const double* base, double* y, const double* q, double* part,
@@ -1350,6 +1362,7 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   int* h_flag = reinterpret_cast<int*>(c->h_pinned);
   int k = 1;
   bool done = false;
+  const uint32_t seq_before = c->xch_seq;
   while (!done) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
     run_iterations(c, I, k, kend, &kt);
@@ -1361,6 +1374,7 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   }
   *it_out = h_flag[0];
   *fail_out = h_flag[3];
+  realign_exchange_slots(c, seq_before, (int64_t)k - 1, (int64_t)h_flag[0] - 1);   // it starts at 1
 }
 
 static void finish_timings(Ctx* c, KernelTimer& kt, kb200_timings& T, int64_t launches0, kb200_timings* tm) {
@@ -1688,6 +1702,7 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     I.k0 = 1;
     kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, rTz, tol, (int)it0, (int)maxit);
     c->launches++;
+    const uint32_t seq_before = c->xch_seq;
     run_iterations(c, I, 1, (int)m + 1, nullptr);
     // one synchronisation per burst: state, alpha/beta history, residual norms
     std::vector<double> hh(nh), rr((size_t)m);
@@ -1700,6 +1715,7 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     if (hs.fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
     const int64_t done = (int64_t)hs.it - it0;
     require(done >= 0 && done <= m, "internal: burst iteration count out of range");
+    realign_exchange_slots(c, seq_before, m, done);
     for (int64_t j = 0; j < done; ++j) {
       alpha_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1)];
       beta_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1) + 1];
