@@ -187,6 +187,8 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     if (const char* e = std::getenv("KB200_MIN_BLOCK")) opt.min_block = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARPS")) opt.warps = std::atoi(e);
     if (const char* e = std::getenv("KB200_MERGE_DEPTH")) opt.merge_depth = std::atoi(e);
+    if (const char* e = std::getenv("KB200_PAD_TOL_PCT")) opt.pad_tol = std::atoi(e) / 100.0;
+    if (const char* e = std::getenv("KB200_LANE_ENTRIES")) opt.lane_entries = std::atoi(e);
     if (const char* e = std::getenv("KB200_ADAPTIVE_LANES")) opt.adaptive_lanes = std::atoi(e);
     if (const char* e = std::getenv("KB200_WARP_PRIVATE")) opt.warp_private = std::atoi(e);
     if (const char* e = std::getenv("KB200_PRIVATE_SPLIT")) opt.private_split = std::atoi(e);
