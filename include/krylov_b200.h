@@ -201,7 +201,9 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n);
  * node in ascending subdomain order. */
 int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom, int64_t* adj_loc);
 /* Average device time (ms) of `reps` back-to-back launches of one kernel on resident data:
- * which = 0 Schur stream kernel, 1 NN GEMV kernel, 2 assembled-Schur GEMV kernel. */
+ * which = 0 Schur stream kernel, 1 NN GEMV kernel, 2 assembled-Schur GEMV kernel, 3 the fused assembly
+ * (+ peer exchange) / vector-update kernel (development probe: it leaves garbage in the work vectors; on
+ * several ranks every rank must make the call). */
 int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
 /* Development aid: with option "debug_timing" = 1 the stream kernel records 16 clock64 stamps per
  * CTA (phase boundaries); this copies them out. */

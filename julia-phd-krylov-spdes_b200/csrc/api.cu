@@ -1762,12 +1762,31 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
     finalize(h);
     use_device(h);
     Ctx* c = h;
+    const int n = (int)c->n_gamma;
     auto once = [&]() {
       if (which == 0) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, nullptr, 0);
       else if (which == 1) launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, nullptr, 0);
-      else launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, nullptr, 0);
+      else if (which == 2) launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, nullptr, 0);
+      else {
+        // which == 3: the fused assembly (+ peer exchange) / update kernel alone (development probe: the
+        // vectors it updates hold garbage afterwards; on several ranks every rank must make this call)
+        const unsigned int target = ++c->gsync_launches * (unsigned int)c->nb;
+        if (c->peer_ok)
+          kb::pcg_fused_xr_kernel<true><<<c->nb, c->vec_threads, 0, c->stream>>>(
+              n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
+              c->d_partB.p, c->d_state.p, 0, c->d_gsync.p, target, next_exchange(c));
+        else
+          kb::pcg_fused_xr_kernel<false><<<c->nb, c->vec_threads, 0, c->stream>>>(
+              n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_loc.p, c->d_Ap.p, c->d_p.p, c->d_x.p, c->d_r.p, c->d_partA.p,
+              c->d_partB.p, c->d_state.p, 0, c->d_gsync.p, target, kb::XchParams());
+        c->launches++;
+      }
     };
-    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd), "kernel inputs not uploaded");
+    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd) || which == 3, "kernel inputs not uploaded");
+    if (which == 3) {  // a state whose done_at does not skip the kernel
+      kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, 1.0, 0.0, 1, INT_MAX - 1);
+      CUDA_TRY(cudaGetLastError());
+    }
     once();
     CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
     for (int i = 0; i < reps; ++i) once();

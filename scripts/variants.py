@@ -57,5 +57,9 @@ for var in os.environ.get("VARIANTS", "pdl=1").split(","):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"{var:40s} it {it} ms/iteration {float(t[0]):.4f}  (schur {tm.schur_ms / max(tm.schur_launches, 1):.4f}, nn {tm.nn_ms / max(tm.nn_launches, 1):.4f}) res {res[-1] / res[0]:.2e}", flush=True)
+if os.environ.get("XCH"):   # the fused assembly (+ exchange) / update kernel alone, back to back
+    ms = S.h.time_kernel(3, 200)
+    if rank == 0:
+        print(f"fused assembly{' + peer exchange' if S.h.stats()['peer_exchange'] else ''} + update kernel alone: {ms * 1e3:.1f} us per launch", flush=True)
 if world > 1:
     dist.destroy_process_group()
