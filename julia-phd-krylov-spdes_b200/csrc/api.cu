@@ -21,6 +21,7 @@
 #include "../../include/krylov_b200.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "xchg_seq.h"
 
 namespace {
 
@@ -644,11 +645,8 @@ kb::XchParams next_exchange(Ctx* c) {
 // iterations the host -- which knows how many of the enqueued iterations really ran, identically on every
 // rank -- re-aligns the counter: the next exchange takes the slot the last real one did not use.
 void realign_exchange_slots(Ctx* c, uint32_t seq_before, int64_t iters_enqueued, int64_t iters_run) {
-  if (!c->peer_ok || iters_enqueued <= 0) return;
-  const uint32_t per_iter = (c->xch_seq - seq_before) / (uint32_t)iters_enqueued;
-  if (per_iter == 0 || iters_run >= iters_enqueued) return;  // nothing skipped: parity already alternates
-  const uint32_t last_real = seq_before + per_iter * (uint32_t)std::max<int64_t>(iters_run, 0);
-  if (((c->xch_seq + 1u) & 1u) == (last_real & 1u)) c->xch_seq++;
+  if (!c->peer_ok) return;
+  c->xch_seq = kb::realigned_exchange_seq(c->xch_seq, seq_before, iters_enqueued, iters_run);
 }
 
 // y = sum_d R_d' loc_d (+ base), optionally partial dot with q.  In multi-rank mode the interface

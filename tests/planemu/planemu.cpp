@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../julia-phd-krylov-spdes_b200/csrc/plan.h"
+#include "../../julia-phd-krylov-spdes_b200/csrc/xchg_seq.h"
 
 using namespace kb;
 
@@ -273,4 +274,9 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     if (err) std::snprintf(err, (size_t)errlen, "%s", e.what());
     return -1;
   }
+}
+
+// host-side bookkeeping of the multi-GPU exchange (csrc/xchg_seq.h), exposed for the CPU tests
+extern "C" uint32_t planemu_realigned_exchange_seq(uint32_t seq_now, uint32_t seq_before, int64_t enqueued, int64_t run) {
+  return kb::realigned_exchange_seq(seq_now, seq_before, enqueued, run);
 }

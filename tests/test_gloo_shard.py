@@ -63,3 +63,49 @@ def test_two_rank_sharded_apply_matches_single_rank():
     assert ranges[0][0] == 0 and ranges[-1][1] == 4 and ranges[0][1] == ranges[1][0]
     for rank, e_apply, e_rhs, tmax, _ in res:
         assert e_apply <= 1e-13 and e_rhs <= 1e-13 and tmax == float(world)
+
+
+def test_exchange_slots_alternate_across_solves_with_skipped_launches():
+    """Host-side bookkeeping of the peer-memory exchange (csrc/xchg_seq.h, used by api.cu): exchange number s
+    uses receive slot s & 1 and consecutive REAL exchanges must alternate slots, although launches skipped on
+    the device after convergence consume numbers.  Randomised solves (check intervals, iteration counts,
+    maxit stops, one or two exchanges per iteration) through the product's own function."""
+    import ctypes as C
+    import random
+    import subprocess
+    emu_dir = os.path.join(ROOT, "tests", "planemu")
+    so = os.path.join(emu_dir, "libplanemu.so")
+    srcs = [os.path.join(emu_dir, "planemu.cpp"), os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc", "plan.cpp")]
+    hdr = os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc", "xchg_seq.h")
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs + [hdr]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + srcs + ["-o", so])
+    lib = C.CDLL(so)
+    lib.planemu_realigned_exchange_seq.restype = C.c_uint32
+    lib.planemu_realigned_exchange_seq.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64]
+    for seed in range(100):
+        rng = random.Random(seed)
+        seq, last_slot = 0, None
+
+        def real(s):
+            nonlocal last_slot
+            assert last_slot is None or (s & 1) != last_slot, f"two real exchanges in a row on slot {s & 1}"
+            last_slot = s & 1
+        for _ in range(60):
+            per_iter = rng.choice([1, 2])
+            for _ in range(rng.choice([1, 2, 3])):          # initial residual / preconditioner applications
+                seq += 1
+                real(seq)
+            seq_before, check, maxit = seq, rng.choice([1, 3, 8, 32]), rng.choice([5, 40, 1000])
+            want = min(rng.randint(0, 70), maxit - 1)      # iterations until convergence
+            k, ran, done = 1, 0, False
+            while not done:
+                kend = min(k + check, maxit)
+                for _ in range(k, kend):
+                    for _ in range(per_iter):
+                        seq += 1
+                        if ran < want:
+                            real(seq)
+                    ran += ran < want
+                k = kend
+                done = ran >= want or k >= maxit
+            seq = lib.planemu_realigned_exchange_seq(seq, seq_before, k - 1, ran)
