@@ -1,0 +1,27 @@
+"""bench.py contract on the CPU: the reference arm (`--impl reference`, the CPU port of the reference
+algorithm on the host cores) prints one JSON line with the keys the driver reads; the GPU arm's line is
+checked on the GPU box by the driver itself."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nx", "101",
+                          "--ndom", "4", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "schur_pcg_solves_per_sec" and d["unit"] == "solves/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["value"] > 0 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
