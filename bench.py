@@ -162,7 +162,9 @@ def main():
     else:
         config["parallelism"] = "1 GPU, all subdomains local"
     config["kernel"] = {"cluster_size": int(stats["csize"]), "consumer_warps": int(stats["consumer_warps"]),
-                        "ring_stages": int(stats["ring_stages"]), "ctas": int(stats["n_cta"])}
+                        "ring_stages": int(stats["ring_stages"]), "ctas": int(stats["n_cta"]),
+                        "supernode_merge_depth": int(stats["merge_depth"]), "min_block": int(stats["min_block"]),
+                        "levels_per_sweep": int(stats["max_levels"])}
     log(f"[rank {rank}] device setup {time.time() - t0:.1f}s; stream {stats['stream_bytes'] / 1e9:.2f} GB, "
         f"levels {stats['max_levels']:.0f}, smem/CTA {stats['smem_bytes']:.0f} B, CTAs {stats['n_cta']:.0f}")
 
