@@ -93,6 +93,15 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d,
  * stored, sorted rows).  Replaces the inner IterativeSolvers.cg(A_IIdd, ., Pl=...) of :648-650. */
 int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm,
                           const int64_t* L_colptr, const int64_t* L_rowval, const double* L_nzval);
+/* prepare_global_schur variant (:212-369; operator apply_global_schur :596-625, the one Example03:175 checks
+ * against the local-column operator): A_IΓ,d with GLOBAL interface columns (n_I x n_gamma; every non-empty
+ * column must be an interface node of subdomain d) instead of kb200_upload_local_blocks, and the interface
+ * block as ONE assembled A_ΓΓ (n_gamma x n_gamma).  A handle fed this way applies
+ * Sx = A_ΓΓ x - Σ_d A_IΓd' A_IId^{-1} A_IΓd x in every operator application and solver. */
+int kb200_upload_global_blocks(kb200_handle h, int64_t d, const int64_t* AIGg_colptr, const int64_t* AIGg_rowval,
+                               const double* AIGg_nzval);
+int kb200_upload_global_interface_block(kb200_handle h, const int64_t* AGG_colptr, const int64_t* AGG_rowval,
+                                        const double* AGG_nzval);
 /* New coefficient realization on the same mesh / partition / ordering (Example07:160-204 loop): same
  * sparsity patterns, new values.  The uploads above may also simply be repeated.  The next operation
  * re-runs the host analysis and refreshes the device streams (round 1: full rebuild, ~1-2 s at 4M DOF). */
@@ -109,6 +118,8 @@ int kb200_finalize(kb200_handle h);
 /* ---- operators (host vectors in, host vectors out) -------------------------------------------- */
 /* y = S x, matrix-free: apply_local_schurs (:711-747).  x, y: n_gamma x nrhs column-major. */
 int kb200_apply_schur(kb200_handle h, const double* x, double* y, int64_t nrhs);
+/* y = S x, global-column operator: apply_global_schur (:596-625); needs the two kb200_upload_global_* calls. */
+int kb200_apply_global_schur(kb200_handle h, const double* x, double* y, int64_t nrhs);
 /* y = S x with the dense S_d: apply_local_schurs assembled variant (:761-785). */
 int kb200_apply_schur_assembled(kb200_handle h, const double* x, double* y, int64_t nrhs);
 /* z = M \ r: apply_neumann_neumann_schur / `\` / ldiv! (:1361-1403). */

@@ -15,7 +15,8 @@ CSRC = os.path.join(_HERE, "csrc")
 SYMBOLS = [
     "kb200_last_error", "kb200_create", "kb200_nccl_unique_id", "kb200_create_dist", "kb200_destroy",
     "kb200_set_option", "kb200_set_topology", "kb200_local_range", "kb200_upload_local_blocks",
-    "kb200_upload_cholesky", "kb200_update_cholesky_values", "kb200_update_local_block_values", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
+    "kb200_upload_cholesky", "kb200_upload_global_blocks", "kb200_upload_global_interface_block",
+    "kb200_apply_global_schur", "kb200_update_cholesky_values", "kb200_update_local_block_values", "kb200_upload_nn_pinv", "kb200_upload_dense_local_schur",
     "kb200_finalize", "kb200_apply_schur", "kb200_apply_schur_assembled", "kb200_apply_nn",
     "kb200_schur_rhs", "kb200_back_substitute", "kb200_assemble_local_schurs",
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_pcg_multi", "kb200_defpcg", "kb200_get_stats", "kb200_get_interface_maps",
@@ -40,7 +41,7 @@ class Timings(C.Structure):
 def build(force=False, with_nccl=True):
     """Compile libkrylov_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("api.cu", "plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_seq.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_seq.h", "xchg_tables.h")] + \
         [os.path.join(_HERE, "..", "include", "krylov_b200.h")]
     if not force and os.path.exists(LIB_PATH) and \
             all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
@@ -149,6 +150,17 @@ class Handle:
         _chk(lib().kb200_upload_local_blocks(self.h, C.c_int64(d), _p(gp, C.c_int64), _p(gi, C.c_int64),
                                              _p(gx, C.c_double), _p(hp, C.c_int64), _p(hi, C.c_int64),
                                              _p(hx, C.c_double)))
+
+    def upload_global_blocks(self, d, A_IG_global):
+        gp, gi, gx = _csc_julia(A_IG_global)
+        _chk(lib().kb200_upload_global_blocks(self.h, C.c_int64(d), _p(gp, C.c_int64), _p(gi, C.c_int64), _p(gx, C.c_double)))
+
+    def upload_global_interface_block(self, A_GG):
+        hp, hi, hx = _csc_julia(A_GG)
+        _chk(lib().kb200_upload_global_interface_block(self.h, _p(hp, C.c_int64), _p(hi, C.c_int64), _p(hx, C.c_double)))
+
+    def apply_global_schur(self, x):
+        return self._apply(lib().kb200_apply_global_schur, x)
 
     def upload_cholesky(self, d, perm0, L):
         lp, li, lx = _csc_julia(L)
@@ -339,11 +351,12 @@ class Handle:
         return k, al[:k], be[:k], rs[:k], rz.value
 
     def stats(self):
-        s = np.zeros(16)
-        _chk(lib().kb200_get_stats(self.h, _p(s, C.c_double), C.c_int64(16)))
+        s = np.zeros(32)
+        _chk(lib().kb200_get_stats(self.h, _p(s, C.c_double), C.c_int64(32)))
         keys = ["nnz_L", "stream_entries", "stream_rows", "stream_slices", "stream_bytes", "max_levels",
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
-                "consumer_warps", "ring_stages", "merge_depth", "min_block"]
+                "consumer_warps", "ring_stages", "merge_depth", "min_block", "fused_pcg_ok", "vec_blocks",
+                "vec_threads", "exchange_entries", "exchange_entries_sent"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "plan.h"
 #include "xchg_seq.h"
+#include "xchg_tables.h"
 
 namespace {
 
@@ -123,8 +124,12 @@ struct kb200_ctx {
   void* xch_own = nullptr;             // this rank's receive buffer + flags
   void* xch_peer[kb::kMaxPeers] = {};  // mapped buffers of all ranks (own included)
   size_t xch_flags_off = 0;
-  int xch_npad = 0;
+  int xch_mpad = 0;                    // entries per slot of the gathered array (all ranks' send entries)
+  int xch_snd_off = 0, xch_snd_n = 0;  // this rank's entries
+  int xch_flag_off = 0, xch_nflags = 0;
+  DevBuf<int32_t> d_snd_ptr, d_snd_src, d_snd_g, d_fin_ptr, d_fin_src;
   uint32_t xch_seq = 0;
+  bool fused_ok = true;                // the grid of the fused PCG kernels is co-resident (checked at finalize)
   int merge_depth = 0;              // supernode grouping depth of the host analysis (0: automatic)
   int gemv_rows = 0;                // rows per CTA of the dense GEMV (0: automatic)
   int vec_threads = 0;              // block size of the interface-vector kernels (0: automatic, 256 or 1024)
@@ -139,13 +144,20 @@ struct kb200_ctx {
   std::vector<int32_t> cnt;
   int64_t d0 = 0, d1 = 0;  // local subdomain range
   bool topo = false, finalized = false, have_pinv = false, have_sd = false;
+  // prepare_global_schur variant (EllipticPdeDomainDecomposition.jl:212-369): A_IΓ,d came with global
+  // interface columns and the interface block as ONE assembled A_ΓΓ (CSR copy on the device)
+  bool global_mode = false;
+  std::vector<int32_t> gg_ptr, gg_col;
+  std::vector<double> gg_val;
+  DevBuf<int32_t> d_gg_ptr, d_gg_col;
+  DevBuf<double> d_gg_val, d_gtmp;
   // host-side tables of the local subdomains
   std::vector<int64_t> I_base, G_base;          // per local subdomain (+1): offsets in concatenated vectors
   std::vector<int64_t> I_base_global;           // per subdomain (+1): offsets in the caller's b_I_concat
   std::vector<int64_t> mat_off;                 // dense block offsets (local)
   std::vector<int32_t> adj_ptr, adj_src, adj_dom, adj_loc;
   int max_gd = 0, smem_bytes = 0, n_cta = 0;
-  double stats[16] = {0};
+  double stats[32] = {0};
   // device pools
   DevBuf<kb::CtaDesc> d_ctas;
   DevBuf<uint8_t> d_stream;
@@ -159,7 +171,7 @@ struct kb200_ctx {
   // device-resident n_gamma x ncols blocks handed out through kb200_mat_*
   std::vector<std::unique_ptr<DevBuf<double>>> mats;
   std::vector<int64_t> mat_cols;
-  DevBuf<double> d_small, d_small2;
+  DevBuf<double> d_small, d_small2, d_xtmp;
   int debug_timing = 0, dbg_flags = 0;
   int nb = 0;  // blocks of the interface-vector kernels
   int64_t launches = 0;
@@ -195,9 +207,27 @@ int guarded(F&& f) {
 
 void use_device(Ctx* c) { CUDA_TRY(cudaSetDevice(c->device)); }
 
+// Failure codes a solve leaves in PcgState::fail -> errors of the ABI.
+void throw_on_fail(int fail) {
+  if (fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
+  if (fail == 3) throw KbError(KB200_ERR_INTERNAL, "grid-wide barrier of the fused PCG kernels timed out (grid not co-resident)");
+  if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+}
+
+
 bool is_local(const Ctx* c, int64_t d) { return d >= c->d0 && d < c->d1; }
 
+// A dense S_d assembled / uploaded for the previous coefficient realization must not survive new values:
+// the reference re-runs assemble_local_schurs per realization (EllipticPdeDomainDecomposition.jl:667-695).
+// The assembled operator reports "not assembled" until kb200_assemble_local_schurs /
+// kb200_upload_dense_local_schur is called again.
+void invalidate_dense_schur(Ctx* c, DomHost& dh) {
+  dh.Sd.clear();
+  c->have_sd = false;
+}
+
 void setup_peer_exchange(Ctx* c);
+void build_exchange_tables(Ctx* c);
 
 // ---- finalize: build plans, upload -------------------------------------------------------------
 void finalize(Ctx* c) {
@@ -387,14 +417,48 @@ void finalize(Ctx* c) {
         CUDA_TRY(cudaMemcpyAsync(buf.p + c->mat_off[k], M.data(), M.size() * 8, cudaMemcpyHostToDevice, s));
     }
   };
+  if (c->global_mode) {
+    require(!c->gg_ptr.empty(), "global-column blocks need kb200_upload_global_interface_block");
+    c->d_gg_ptr.upload(c->gg_ptr, s);
+    c->d_gg_col.upload(c->gg_col, s);
+    c->d_gg_val.upload(c->gg_val, s);
+    c->d_gtmp.alloc(c->n_gamma);
+  }
   if (c->have_pinv) upload_dense(c->d_pinv, true);
   if (c->have_sd) upload_dense(c->d_sd, false);
   // vectors
   const int64_t ng = c->n_gamma;
   // block size of the interface-vector kernels: few large blocks when every assembly ends in a peer
   // exchange (fewer flags / fences / grid-barrier arrivals), many small ones on a single GPU
-  if (c->vec_threads == 0) c->vec_threads = c->has_comm ? 1024 : 256;
-  c->nb = (int)((ng + c->vec_threads - 1) / c->vec_threads);
+  int sm_count = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  const bool auto_threads = c->vec_threads == 0;
+  if (auto_threads) c->vec_threads = c->has_comm ? 1024 : 256;
+  build_exchange_tables(c);  // multi-rank: send / gather tables of the compact exchange (sets xch_* sizes)
+  auto blocks_for = [&](int threads) {
+    int nb = (int)((ng + threads - 1) / threads);
+    if (c->has_comm) nb = std::max(nb, (c->xch_snd_n + threads - 1) / threads);  // send blocks are blocks of the same grid
+    return std::max(nb, 1);
+  };
+  // The fused PCG kernels synchronise their grid through an arrival counter: every block must be resident
+  // at the same time.  Check it against the device's occupancy; fall back to larger blocks, then to the
+  // unfused kernels (no grid-wide wait) when the interface is too large for that.
+  auto coresident = [&](int threads) {
+    int occ = 0;
+    int worst = INT_MAX;
+    for (const void* fn : {(const void*)kb::pcg_fused_xr_kernel<true>, (const void*)kb::pcg_fused_xr_kernel<false>,
+                           (const void*)kb::pcg_fused_p_kernel<true>, (const void*)kb::pcg_fused_p_kernel<false>}) {
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0));
+      worst = std::min(worst, occ);
+    }
+    return (int64_t)worst * sm_count >= (int64_t)blocks_for(threads);
+  };
+  c->fused_ok = coresident(c->vec_threads);
+  if (!c->fused_ok && auto_threads && c->vec_threads < 1024 && coresident(1024)) {
+    c->vec_threads = 1024;
+    c->fused_ok = true;
+  }
+  c->nb = blocks_for(c->vec_threads);
   for (DevBuf<double>* v : {&c->d_x, &c->d_b, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap}) v->alloc(ng);
   c->d_loc.alloc(c->G_base[nloc]);
   c->d_bI.alloc(c->I_base[nloc]);
@@ -431,6 +495,8 @@ void finalize(Ctx* c) {
     set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, 16>);
     set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, 16>);
   }
+  // nvec up to 4096 in the deflated solvers: 3 nvec doubles of dynamic shared memory
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kb::small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 24));
   CUDA_TRY(cudaStreamSynchronize(s));
   // stats
   c->stats[0] = nnzL;
@@ -448,11 +514,16 @@ void finalize(Ctx* c) {
   c->stats[11] = c->peer_ok ? 1.0 : 0.0;
   c->stats[12] = c->warps;
   c->stats[13] = c->stages;
+  c->stats[16] = c->fused_ok ? 1.0 : 0.0;
+  c->stats[17] = c->nb;
+  c->stats[18] = c->vec_threads;
+  c->stats[19] = c->xch_mpad;
+  c->stats[20] = c->xch_snd_n;
   c->finalized = true;  // host copies of the inputs are kept: value updates re-run the analysis
 }
 
 // ---- peer-memory interface exchange (multi-rank) -----------------------------------------------
-// Every rank allocates [2 slots][world][n_pad] doubles + [world][nb] flags, exports the allocation
+// Every rank allocates [2 slots][m_pad] doubles + one flag per send block of every rank, exports the allocation
 // with cudaIpcGetMemHandle; the handles travel through one ncclAllGather and are opened with
 // cudaIpcOpenMemHandle (peer access over NVLink).  Any failure on any rank (agreed through an
 // all-reduce) leaves the NCCL path in charge.
@@ -460,9 +531,8 @@ void setup_peer_exchange(Ctx* c) {
 #ifdef KB200_WITH_NCCL
   if (!c->has_comm || c->world < 2 || c->world > kb::kMaxPeers || !c->peer_exchange || c->xch_own) return;
   const int W = c->world;
-  c->xch_npad = c->nb * c->vec_threads;
-  const size_t data_bytes = (size_t)2 * W * c->xch_npad * sizeof(double);
-  const size_t flag_bytes = (size_t)W * c->nb * sizeof(uint32_t);
+  const size_t data_bytes = (size_t)2 * c->xch_mpad * sizeof(double);
+  const size_t flag_bytes = (size_t)std::max(c->xch_nflags, 1) * sizeof(uint32_t);
   c->xch_flags_off = data_bytes;
   int ok = 1;
   cudaIpcMemHandle_t mine;
@@ -524,6 +594,30 @@ void setup_peer_exchange(Ctx* c) {
 #else
   (void)c;
 #endif
+}
+
+// Send / gather tables of the owner-ordered compact exchange (kernels.cuh, xchg_tables.h).
+void build_exchange_tables(Ctx* c) {
+  if (!c->has_comm || c->world < 2) return;
+  std::vector<const std::vector<int32_t>*> l2g(c->ndom);
+  for (int64_t d = 0; d < c->ndom; ++d) l2g[d] = &c->doms[d].l2g;
+  kb::XchTables T;
+  try {
+    T = kb::build_xchg_tables(c->world, c->rank, l2g, c->n_gamma, c->vec_threads);
+  } catch (const std::exception& e) {
+    throw KbError(KB200_ERR_INTERNAL, e.what());
+  }
+  c->xch_mpad = ((T.m_total + 31) / 32) * 32 + 32;
+  c->xch_snd_off = T.off[c->rank];
+  c->xch_snd_n = T.off[c->rank + 1] - T.off[c->rank];
+  c->xch_flag_off = T.flag_off[c->rank];
+  c->xch_nflags = T.flag_off[c->world];
+  c->d_snd_ptr.upload(T.snd_ptr, c->stream);
+  c->d_snd_src.upload(T.snd_src, c->stream);
+  c->d_snd_g.upload(T.snd_g, c->stream);
+  c->d_fin_ptr.upload(T.fin_ptr, c->stream);
+  c->d_fin_src.upload(T.fin_src, c->stream);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
 // ---- launches ----------------------------------------------------------------------------------
@@ -631,11 +725,20 @@ kb::XchParams next_exchange(Ctx* c) {
     X.data[r] = reinterpret_cast<double*>(c->xch_peer[r]);
     X.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->xch_peer[r]) + c->xch_flags_off);
   }
+  X.snd_ptr = c->d_snd_ptr.p;
+  X.snd_src = c->d_snd_src.p;
+  X.snd_g = c->d_snd_g.p;
+  X.fin_ptr = c->d_fin_ptr.p;
+  X.fin_src = c->d_fin_src.p;
   X.world = c->world;
   X.rank = c->rank;
   X.seq = ++c->xch_seq;
   X.slot = (int)(X.seq & 1u);
-  X.n_pad = c->xch_npad;
+  X.m_pad = c->xch_mpad;
+  X.snd_off = c->xch_snd_off;
+  X.snd_n = c->xch_snd_n;
+  X.flag_off = c->xch_flag_off;
+  X.nflags = c->xch_nflags;
   X.fail = &c->d_state.p->fail;
   return X;
 }
@@ -664,24 +767,25 @@ void assemble(Ctx* c, const double* loc, const double* base, double* y, const do
   if (c->peer_ok) {
     // fused: assemble the local partial, exchange it over NVLink peer memory, sum, partial dot
     const kb::XchParams X = next_exchange(c);
-    kb::assemble_exchange_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
-                                                                          c->rank == 0 ? base : nullptr, y, q, part,
-                                                                          done_at, iter, X);
+    kb::assemble_exchange_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc, base,
+                                                                          y, q, part, done_at, iter, X);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return;
   }
+  // NCCL fallback: partial vector -> all-reduce -> guarded copy.  The all-reduce runs on a scratch vector so
+  // that launches skipped after convergence (the assembly and the copy exit early, the collective cannot)
+  // never touch y.
+  if (c->d_xtmp.n < (size_t)n) c->d_xtmp.alloc((size_t)n);
   kb::assemble_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_adj_ptr.p, c->d_adj_src.p, loc,
-                                                               c->rank == 0 ? base : nullptr, y, nullptr, nullptr,
+                                                               c->rank == 0 ? base : nullptr, c->d_xtmp.p, nullptr, nullptr,
                                                                done_at, iter);
   CUDA_TRY(cudaGetLastError());
   c->launches++;
-  allreduce(c, y, n);
-  if (q != nullptr) {
-    kb::dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, y, q, part, done_at, iter);
-    CUDA_TRY(cudaGetLastError());
-    c->launches++;
-  }
+  allreduce(c, c->d_xtmp.p, n);
+  kb::copy_dot_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->d_xtmp.p, y, q, part, done_at, iter);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
 }
 
 enum OpKind { OP_SCHUR = 0, OP_SCHUR_DENSE = 1, OP_NN = 2 };
@@ -725,6 +829,16 @@ void apply_op(Ctx* c, OpKind op, const double* in, double* out, const double* q,
               int iter, KernelTimer* kt) {
   cudaEvent_t a = nullptr;
   const bool timed = kt != nullptr && c->profile;
+  const double* base = nullptr;
+  if (op == OP_SCHUR && c->global_mode) {
+    // apply_global_schur (:596-625): Sx = A_ΓΓ x - sum_d A_IΓd' A_IId^{-1} A_IΓd x ; the assembled A_ΓΓ x is the
+    // base of the interface assembly, the subdomain terms come from the stream kernel (empty A_ΓΓ,d blocks)
+    kb::spmv_csr_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>((int)c->n_gamma, c->d_gg_ptr.p, c->d_gg_col.p, c->d_gg_val.p, in,
+                                                                 c->d_gtmp.p, done_at, iter);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    base = c->d_gtmp.p;
+  }
   if (op == OP_SCHUR) {
     if (timed) kt->begin(0, a);
     launch_stream<kb::MODE_APPLY>(c, in, nullptr, nullptr, c->d_loc.p, done_at, iter);
@@ -740,7 +854,7 @@ void apply_op(Ctx* c, OpKind op, const double* in, double* out, const double* q,
     launch_gemv(c, c->d_pinv.p, in, true, c->d_loc.p, done_at, iter);
     if (timed) kt->end(1, a);
   }
-  assemble(c, c->d_loc.p, nullptr, out, q, part, done_at, iter);
+  assemble(c, c->d_loc.p, base, out, q, part, done_at, iter);
 }
 
 void h2d(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = nullptr) {
@@ -989,6 +1103,7 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colp
     dh.in.n_gd = (int32_t)dh.n_gd;
     csc_from_julia(dh.in.AIG, dh.n_I, dh.n_gd, AIG_colptr, AIG_rowval, AIG_nzval, "A_IG");
     csc_from_julia(dh.in.AGG, dh.n_gd, dh.n_gd, AGG_colptr, AGG_rowval, AGG_nzval, "A_GG");
+    invalidate_dense_schur(h, dh);
     dh.have_blocks = true;
   });
 }
@@ -1011,7 +1126,81 @@ int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const 
       dh.in.perm[k] = (int32_t)v;
     }
     csc_from_julia(dh.in.L, dh.n_I, dh.n_I, L_colptr, L_rowval, L_nzval, "L");
+    invalidate_dense_schur(h, dh);
     dh.have_chol = true;
+  });
+}
+
+int kb200_upload_global_blocks(kb200_handle h, int64_t d, const int64_t* AIGg_colptr, const int64_t* AIGg_rowval,
+                               const double* AIGg_nzval) {
+  return guarded([&]() {
+    require(h && h->topo, "topology not set");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    h->global_mode = true;
+    if (!is_local(h, d)) return;
+    h->finalized = false;
+    DomHost& dh = h->doms[d];
+    require(AIGg_colptr && AIGg_colptr[0] == 1, "A_IG (global columns): colptr must be 1-based");
+    // compress the n_gamma global columns to the subdomain's local interface columns: every non-empty
+    // column must belong to Γ_d (prepare_global_schur fills exactly those, :300-340)
+    const int64_t ng = h->n_gamma;
+    std::vector<int64_t> cp(dh.n_gd + 1, 1);
+    std::vector<int32_t> g2l(ng, -1);
+    for (int64_t l = 0; l < dh.n_gd; ++l) g2l[dh.l2g[l]] = (int32_t)l;
+    for (int64_t g = 0; g < ng; ++g)
+      if (AIGg_colptr[g + 1] > AIGg_colptr[g] && g2l[g] < 0)
+        throw KbError(KB200_ERR_INPUT, "A_IG (global columns): a non-empty column is not an interface node of the subdomain");
+    const int64_t nnz = AIGg_colptr[ng] - 1;
+    std::vector<int64_t> rv((size_t)nnz);
+    std::vector<double> nz((size_t)nnz);
+    int64_t q = 0;
+    for (int64_t l = 0; l < dh.n_gd; ++l) {
+      const int64_t g = dh.l2g[l];
+      for (int64_t p = AIGg_colptr[g] - 1; p < AIGg_colptr[g + 1] - 1; ++p, ++q) {
+        rv[q] = AIGg_rowval[p];
+        nz[q] = AIGg_nzval[p];
+      }
+      cp[l + 1] = q + 1;
+    }
+    dh.in.n_I = (int32_t)dh.n_I;
+    dh.in.n_gd = (int32_t)dh.n_gd;
+    csc_from_julia(dh.in.AIG, dh.n_I, dh.n_gd, cp.data(), rv.data(), nz.data(), "A_IG (global columns)");
+    std::vector<int64_t> ecp(dh.n_gd + 1, 1);
+    csc_from_julia(dh.in.AGG, dh.n_gd, dh.n_gd, ecp.data(), nullptr, nullptr, "A_GG (empty)");
+    invalidate_dense_schur(h, dh);
+    dh.have_blocks = true;
+  });
+}
+
+int kb200_upload_global_interface_block(kb200_handle h, const int64_t* AGG_colptr, const int64_t* AGG_rowval,
+                                        const double* AGG_nzval) {
+  return guarded([&]() {
+    require(h && h->topo, "topology not set");
+    kb::Csc m;
+    csc_from_julia(m, h->n_gamma, h->n_gamma, AGG_colptr, AGG_rowval, AGG_nzval, "A_GG (assembled)");
+    // CSC -> CSR (rows of the product are read by one thread each)
+    const int64_t ng = h->n_gamma;
+    h->gg_ptr.assign(ng + 1, 0);
+    for (int32_t r : m.rowval) h->gg_ptr[r + 1]++;
+    for (int64_t i = 0; i < ng; ++i) h->gg_ptr[i + 1] += h->gg_ptr[i];
+    h->gg_col.resize(m.rowval.size());
+    h->gg_val.resize(m.rowval.size());
+    std::vector<int32_t> fill(h->gg_ptr.begin(), h->gg_ptr.end() - 1);
+    for (int64_t j = 0; j < ng; ++j)
+      for (int32_t p = m.colptr[j]; p < m.colptr[j + 1]; ++p) {
+        const int32_t q = fill[m.rowval[p]]++;
+        h->gg_col[q] = (int32_t)j;
+        h->gg_val[q] = m.nzval[p];
+      }
+    h->global_mode = true;
+    h->finalized = false;
+  });
+}
+
+int kb200_apply_global_schur(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  return guarded([&]() {
+    require(h && h->global_mode, "kb200_upload_global_blocks / kb200_upload_global_interface_block were not called");
+    host_apply(h, OP_SCHUR, x, y, nrhs);
   });
 }
 
@@ -1023,6 +1212,7 @@ int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzva
     DomHost& dh = h->doms[d];
     require(dh.have_chol, "kb200_upload_cholesky must come first");
     std::copy(L_nzval, L_nzval + dh.in.L.nzval.size(), dh.in.L.nzval.begin());
+    invalidate_dense_schur(h, dh);
     h->finalized = false;
   });
 }
@@ -1036,6 +1226,7 @@ int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG
     require(dh.have_blocks, "kb200_upload_local_blocks must come first");
     std::copy(AIG_nzval, AIG_nzval + dh.in.AIG.nzval.size(), dh.in.AIG.nzval.begin());
     std::copy(AGG_nzval, AGG_nzval + dh.in.AGG.nzval.size(), dh.in.AGG.nzval.begin());
+    invalidate_dense_schur(h, dh);
     h->finalized = false;
   });
 }
@@ -1235,7 +1426,7 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
   kb::PcgState* st = c->d_state.p;
   const int* done_at = &st->done_at;
   auto vcol = [&](int kk) -> double* { return I.vbase ? I.vbase + (size_t)(kk - I.k0) * (size_t)n : nullptr; };
-  const bool fused = c->fuse_pcg && I.precond && I.defl == nullptr && I.deflR == nullptr && (!c->has_comm || c->peer_ok);
+  const bool fused = c->fuse_pcg && c->fused_ok && !(c->global_mode && I.A == OP_SCHUR) && I.precond && I.defl == nullptr && I.deflR == nullptr && (!c->has_comm || c->peer_ok);
   if (fused) {
     // four launches per iteration: local operator, assembly (+exchange) fused with the vector update;
     // kernel durations are sampled on every 16th iteration only (an event between two kernels would
@@ -1263,22 +1454,30 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
       else launch_gemv(c, c->d_sd.p, I.p, false, c->d_loc.p, done_at, k);
       if (timed) kt->end(0, ev);
       {
-        const unsigned int target = ++c->gsync_launches * nbk;
+        // the counters advance only once the launch is known to be enqueued (a failed launch must not
+        // leave the grid counter / exchange sequence ahead of the device)
+        const unsigned int target = (c->gsync_launches + 1u) * nbk;
         const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
         auto fn = c->peer_ok ? kb::pcg_fused_xr_kernel<true> : kb::pcg_fused_xr_kernel<false>;
-        CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.Ap, (const double*)I.p, I.x, I.r, c->d_partA.p,
-                                    c->d_partB.p, st, k, c->d_gsync.p, target, X));
+        const cudaError_t le = cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.Ap, (const double*)I.p, I.x, I.r,
+                                                  c->d_partA.p, c->d_partB.p, st, k, c->d_gsync.p, target, X);
+        if (le != cudaSuccess && c->peer_ok) --c->xch_seq;
+        CUDA_TRY(le);
+        ++c->gsync_launches;
       }
       if (timed) kt->begin(1, ev);
       launch_gemv(c, c->d_pinv.p, I.r, true, c->d_loc.p, done_at, k);
       if (timed) kt->end(1, ev);
       {
-        const unsigned int target = ++c->gsync_launches * nbk;
+        const unsigned int target = (c->gsync_launches + 1u) * nbk;
         const kb::XchParams X = c->peer_ok ? next_exchange(c) : kb::XchParams();
         auto fn = c->peer_ok ? kb::pcg_fused_p_kernel<true> : kb::pcg_fused_p_kernel<false>;
-        CUDA_TRY(cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.z, (const double*)I.r, I.p,
-                                    (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, vcol(k), I.hist, k,
-                                    c->d_gsync.p, target, X));
+        const cudaError_t le = cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.z, (const double*)I.r, I.p,
+                                                  (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, vcol(k), I.hist,
+                                                  k, c->d_gsync.p, target, X);
+        if (le != cudaSuccess && c->peer_ok) --c->xch_seq;
+        CUDA_TRY(le);
+        ++c->gsync_launches;
       }
       c->launches += 2;
     }
@@ -1414,8 +1613,7 @@ int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double 
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *it_out = it;
     finish_timings(c, kt, T, launches0, tm);
-    if (fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
-    if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+    throw_on_fail(fail);
   });
 }
 
@@ -1502,8 +1700,7 @@ int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, in
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *it_out = it;
     finish_timings(c, kt, T, launches0, tm);
-    if (fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
-    if (fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+    throw_on_fail(fail);
   });
 }
 
@@ -1709,8 +1906,7 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     CUDA_TRY(cudaMemcpyAsync(hh.data(), dhist.p, nh * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(rr.data(), c->d_res.p + it0, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (hs.fail == 2) throw KbError(KB200_ERR_NCCL, "interface exchange timed out: a peer rank never arrived");
-    if (hs.fail) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+    throw_on_fail(hs.fail);
     const int64_t done = (int64_t)hs.it - it0;
     require(done >= 0 && done <= m, "internal: burst iteration count out of range");
     realign_exchange_slots(c, seq_before, m, done);
@@ -1728,7 +1924,7 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
   return guarded([&]() {
     require(h && stats, "null argument");
     finalize(h);
-    for (int64_t i = 0; i < n && i < 16; ++i) stats[i] = h->stats[i];
+    for (int64_t i = 0; i < n && i < 32; ++i) stats[i] = h->stats[i];
   });
 }
 
@@ -1780,7 +1976,8 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
         c->launches++;
       }
     };
-    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd) || which == 3, "kernel inputs not uploaded");
+    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd) || (which == 3 && c->fused_ok && (!c->has_comm || c->peer_ok)),
+            "kernel inputs not uploaded / fused kernel not available");
     if (which == 3) {  // a state whose done_at does not skip the kernel
       kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, 1.0, 0.0, 1, INT_MAX - 1);
       CUDA_TRY(cudaGetLastError());

@@ -587,25 +587,39 @@ assemble_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// Interface assembly FUSED with the all-reduce over the GPUs of the node (subdomains are sharded over
+// Interface assembly FUSED with the exchange over the GPUs of the node (subdomains are sharded over
 // the ranks, EllipticPdePllDomainDecomposition.jl:11 `@distributed (+)`): every rank owns a receive
-// buffer that its peers map through CUDA IPC (NVLink / NVSwitch peer memory).  Block b of every rank
-// assembles segment b of the rank's partial interface vector, stores it straight into the receive
-// buffers of ALL ranks (one-shot all-gather of partials: n_gamma * 8 B per peer, a few MB in total),
-// publishes a per-block sequence flag (release, system scope) at every peer, waits for the flags of
-// segment b from all ranks and sums the `world` partials in rank order -- identical bits on every rank,
-// so the PCG scalars and iteration counts agree without any further exchange.  The dot product with q
-// is taken on the fly.  No grid-wide barrier, no separate collective launch.
-// Buffers: two data slots used alternately (a rank can run at most one exchange ahead of a peer: it
-// cannot finish exchange k+1 before that peer has pushed k+1, i.e. has left the kernel of exchange k).
+// buffer that its peers map through CUDA IPC (NVLink / NVSwitch peer memory).
+//
+// OWNER-ORDERED COMPACT EXCHANGE.  The reference sums the contributions to an interface node in
+// ascending subdomain order (EllipticPdeDomainDecomposition.jl:740-742); with contiguous shards that is
+// rank-major order.  For every interface node the LOWEST rank touching it sends one entry, the sum of
+// its own contributions in ascending order (a prefix of the reference's sum; the final value when no
+// other rank touches the node -- the vast majority); every HIGHER rank touching the node sends its
+// contributions one by one.  All ranks receive all entries (an all-gather of ~n_gamma doubles in total,
+// not `world` full-length partial vectors) and finish every node's sum in the reference's order: the
+// assembled vector has the SAME BITS on every rank and for every number of GPUs, single GPU included,
+// so the PCG scalars and iteration counts do not depend on the GPU count.
+// The first ceil(m_r / blockDim) blocks of rank r compute and push its m_r entries and publish one flag
+// each (release, system scope) at every peer; every block then waits for all flags of all ranks and
+// gathers its nodes.  No separate collective launch.  Two data slots alternate (a rank can run at most
+// one exchange ahead of a peer: it cannot finish exchange k+1 before that peer has pushed k+1, i.e. has
+// left the kernel of exchange k).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct XchParams {
-  double* data[kMaxPeers];     // receive buffer of every rank: [2 slots][world][n_pad] doubles
-  uint32_t* flags[kMaxPeers];  // flags of every rank: [world sources][nb blocks]
+  double* data[kMaxPeers];     // gathered entries at every rank: [2 slots][m_pad] doubles
+  uint32_t* flags[kMaxPeers];  // flags at every rank: one per send block of every rank [nflags]
+  const int32_t* snd_ptr;      // this rank's send entries: CSR over indices into `loc` (snd_n + 1)
+  const int32_t* snd_src;
+  const int32_t* snd_g;        // interface node whose `base` value the entry starts from, or -1
+  const int32_t* fin_ptr;      // per interface node: entries of the gathered array to sum, in order
+  const int32_t* fin_src;
   int world, rank, slot;
   uint32_t seq;                // sequence number of this exchange (monotone, identical on all ranks)
-  int n_pad;                   // n rounded up to the block size
+  int m_pad;                   // entries per slot
+  int snd_off, snd_n;          // position / number of this rank's entries in the gathered array
+  int flag_off, nflags;        // this rank's first flag / flags of all ranks
   int* fail;                   // set to 2 when a peer does not show up (time-out instead of a hang)
 };
 
@@ -618,22 +632,28 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-// Exchange step of one block (all threads must call): push the rank's partial `a` of entry g to every
-// rank, publish / await the per-block flags, return the sum of the `world` partials in rank order.
-__device__ __forceinline__ double exchange_sum(double a, int g, int n, const XchParams& X) {
-  const int nb = gridDim.x;
-  const size_t seg = ((size_t)X.slot * X.world + X.rank) * (size_t)X.n_pad + (size_t)g;
-  for (int r = 0; r < X.world; ++r) __stcg(X.data[r] + seg, a);
-  __syncthreads();
-  if ((int)threadIdx.x < X.world) {
-    const int r = threadIdx.x;
+// Exchange step of one block (all threads must call): returns the assembled value of interface node g
+// (contributions of ALL subdomains, reference order); see above.
+__device__ __forceinline__ double exchange_gather(int g, int n, const double* loc, const double* base, const XchParams& X) {
+  const int T = blockDim.x;
+  if ((int)blockIdx.x * T < X.snd_n) {  // block-uniform: this block pushes entries
+    const int e = blockIdx.x * T + threadIdx.x;
+    if (e < X.snd_n) {
+      const int gb = X.snd_g[e];
+      double a = (base != nullptr && gb >= 0) ? base[gb] : 0.0;
+      for (int k = X.snd_ptr[e]; k < X.snd_ptr[e + 1]; ++k) a += loc[X.snd_src[k]];
+      const size_t at = (size_t)X.slot * (size_t)X.m_pad + (size_t)(X.snd_off + e);
+      for (int r = 0; r < X.world; ++r) __stcg(X.data[r] + at, a);
+    }
+    __syncthreads();
     // release at system scope: the block's stores to the peers (ordered before this thread by the
     // barrier above) are visible to whoever acquires the flag
-    st_release_sys(X.flags[r] + (size_t)X.rank * nb + blockIdx.x, X.seq);
-    // wait for segment blockIdx.x of source rank r
-    const uint32_t* f = X.flags[X.rank] + (size_t)r * nb + blockIdx.x;
+    if ((int)threadIdx.x < X.world) st_release_sys(X.flags[threadIdx.x] + X.flag_off + blockIdx.x, X.seq);
+  }
+  for (int f = threadIdx.x; f < X.nflags; f += T) {
+    const uint32_t* fp = X.flags[X.rank] + f;
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(f) - X.seq) < 0) {
+    while ((int32_t)(ld_acquire_sys(fp) - X.seq) < 0) {
       if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer never arrived
         if (X.fail != nullptr) *X.fail = 2;
         break;
@@ -643,8 +663,8 @@ __device__ __forceinline__ double exchange_sum(double a, int g, int n, const Xch
   __syncthreads();
   double sum = 0.0;
   if (g < n) {
-    const double* mine = X.data[X.rank] + (size_t)X.slot * X.world * (size_t)X.n_pad + (size_t)g;
-    for (int r = 0; r < X.world; ++r) sum += __ldcg(mine + (size_t)r * X.n_pad);
+    const double* G = X.data[X.rank] + (size_t)X.slot * (size_t)X.m_pad;
+    for (int k = X.fin_ptr[g]; k < X.fin_ptr[g + 1]; ++k) sum += __ldcg(G + X.fin_src[k]);
   }
   return sum;
 }
@@ -666,7 +686,7 @@ assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, 
   __shared__ double red[kVecThreads / 32];
   if (done_at != nullptr && *done_at < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const double sum = exchange_sum(assemble_local(g, n, adj_ptr, adj_src, loc, base), g, n, X);
+  const double sum = exchange_gather(g, n, loc, base, X);
   double prod = 0.0;
   if (g < n) {
     y[g] = sum;
@@ -678,6 +698,19 @@ assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, 
   }
 }
 
+// y = A x for the assembled interface block A_ΓΓ (CSR, n x n): the base of the interface assembly in the
+// global-column operator (apply_global_schur, EllipticPdeDomainDecomposition.jl:604)
+__global__ void __launch_bounds__(kVecThreads)
+spmv_csr_kernel(int n, const int32_t* ptr, const int32_t* col, const double* val, const double* x, double* y,
+                const int* done_at, int iter) {
+  if (done_at != nullptr && *done_at < iter) return;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  double a = 0.0;
+  for (int k = ptr[g]; k < ptr[g + 1]; ++k) a = fma(val[k], x[col[k]], a);
+  y[g] = a;
+}
+
 // part[b] = block partial of dot(a, b)
 __global__ void __launch_bounds__(kVecThreads)
 dot_kernel(int n, const double* a, const double* b, double* part, const int* done_at, int iter) {
@@ -687,6 +720,24 @@ dot_kernel(int n, const double* a, const double* b, double* part, const int* don
   const double prod = (g < n) ? a[g] * b[g] : 0.0;
   const double s = block_reduce_sum(prod, red);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// y = src ; part[b] = block partial of dot(src, q) (optional)   -- tail of the NCCL fallback path
+__global__ void __launch_bounds__(kVecThreads)
+copy_dot_kernel(int n, const double* src, double* y, const double* q, double* part, const int* done_at, int iter) {
+  __shared__ double red[kVecThreads / 32];
+  if (done_at != nullptr && *done_at < iter) return;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double prod = 0.0;
+  if (g < n) {
+    const double v = src[g];
+    y[g] = v;
+    if (q != nullptr) prod = v * q[g];
+  }
+  if (part != nullptr) {
+    const double s = block_reduce_sum(prod, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  }
 }
 
 // r = b - Ax ; partials of r.r (partA) and b.b (partB)                            (cg.jl:83-84, 89)
@@ -806,14 +857,21 @@ pcg_update_p_kernel(int n, int nb, const double* z, double* p, const double* par
 // ---------------------------------------------------------------------------------------------
 // Arrive on the grid counter and wait until `target` arrivals have been counted (counter is monotone:
 // target = launches so far x blocks).  Kernels skipped after convergence still arrive (grid_skip).
-__device__ __forceinline__ void grid_arrive_wait(unsigned int* counter, unsigned int target) {
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* counter, unsigned int target, int* fail) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
     unsigned int v;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      // the host only launches these kernels when the whole grid is co-resident (finalize checks the
+      // occupancy); should that ever not hold, this turns a dead-lock into a reported error after ~4 s
+      if ((int)(v - target) < 0 && clock64() - t0 > 8000000000LL) {
+        if (fail != nullptr) *fail = 3;
+        break;
+      }
     } while ((int)(v - target) < 0);
   }
   __syncthreads();
@@ -843,8 +901,7 @@ pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const
   }
   const int nb = gridDim.x;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  double a = assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
-  if (kX) a = exchange_sum(a, g, n, X);
+  const double a = kX ? exchange_gather(g, n, loc, nullptr, X) : assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
   double pv = 0.0;
   if (g < n) {
     Ap[g] = a;
@@ -852,7 +909,7 @@ pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const
   }
   const double s = block_reduce_sum(a * pv, red);
   if (threadIdx.x == 0) partA[blockIdx.x] = s;
-  grid_arrive_wait(counter, target);
+  grid_arrive_wait(counter, target, &st->fail);
   const double d = sum_partials_cg(partA, nb, red);
   const double rTz = st->rTz;
   const double alpha = rTz / d;
@@ -890,8 +947,7 @@ pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const 
   }
   const int nb = gridDim.x;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  double a = assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
-  if (kX) a = exchange_sum(a, g, n, X);
+  const double a = kX ? exchange_gather(g, n, loc, nullptr, X) : assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
   double rv = 0.0;
   if (g < n) {
     z[g] = a;
@@ -899,7 +955,7 @@ pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const 
   }
   const double s = block_reduce_sum(a * rv, red);
   if (threadIdx.x == 0) partC[blockIdx.x] = s;
-  grid_arrive_wait(counter, target);
+  grid_arrive_wait(counter, target, &st->fail);
   const double rTz_new = sum_partials_cg(partC, nb, red);
   const double rTr = sum_partials_cg(partB, nb, red);
   double beta = 1.0 / st->rTz_old;

@@ -44,6 +44,9 @@ class B200SchurOperator:
         for d in range(d0, d1):
             self.h.update_local_block_values(d, blocks.A_IG[d], blocks.A_GG[d])
             self.h.update_cholesky_values(d, factors[d][1])
+        # the dense S_d of the previous realization are dropped by the library (the reference re-assembles per
+        # realization, EllipticPdeDomainDecomposition.jl:667-695): back to the matrix-free operator
+        self.assembled = False
 
     # LinearMaps.FunctionMap surface
     def __matmul__(self, x):
@@ -73,6 +76,33 @@ class B200SchurOperator:
         self.h.assemble_local_schurs()
         d0, d1 = self.local_range
         return {d: self.h.get_dense_local_schur(d) for d in range(d0, d1)}
+
+
+class B200GlobalSchurOperator(B200SchurOperator):
+    """The operator of apply_global_schur (EllipticPdeDomainDecomposition.jl:596-625) from the outputs of
+    prepare_global_schur (:212-369): A_IΓ,d with global interface columns and the assembled A_ΓΓ.
+    ``S * x`` = A_ΓΓ x - Σ_d A_IΓd' A_IId^{-1} A_IΓd x  (the identity Example03:175 checks)."""
+
+    def __init__(self, sd, A_IG_global, A_GG, factors, device=0, csize=None, options=None):
+        self.sd = sd
+        self.h = capi.Handle(device)
+        if csize is not None:
+            self.h.set_option("csize", csize)
+        for k, v in (options or {}).items():
+            self.h.set_option(k, v)
+        self.h.set_topology([v.size for v in sd.node_Id], [g.size for g in sd.gamma_l2g],
+                            [g + 1 for g in sd.gamma_l2g], sd.node_gamma_cnt)
+        d0, d1 = self.h.local_range()
+        for d in range(d0, d1):
+            self.h.upload_global_blocks(d, A_IG_global[d])
+            self.h.upload_cholesky(d, factors[d][0], factors[d][1])
+        self.h.upload_global_interface_block(A_GG)
+        self.local_range = (d0, d1)
+        self.N = sd.n_gamma
+        self.assembled = False
+
+    def mul(self, x):
+        return self.h.apply_global_schur(x)
 
 
 class B200NeumannNeumann:

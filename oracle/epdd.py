@@ -18,8 +18,47 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from krylov_b200.hostprep.epdd_host import (Subdomains, LocalBlocks, restriction,
-                                            prepare_local_schurs, _element_geometry)
+from dataclasses import dataclass, field
+from typing import List
+
+
+# The oracle keeps its OWN containers and assembly loops: nothing here imports product code, so an
+# error shared with julia-phd-krylov-spdes_b200/hostprep cannot hide behind an identity test.  The
+# host-preparation classes of the product are duck-type compatible (same attribute names).
+@dataclass
+class Subdomains:
+    """Outputs of set_subdomains (EllipticPdeDomainDecomposition.jl:191-192) as arrays, 0-based
+    except node_owner (reference values: -1 interface, 0 Dirichlet, d+1 interior of subdomain d)."""
+    ndom: int
+    nnode: int
+    node_owner: np.ndarray
+    node_gamma: np.ndarray
+    node_gamma_cnt: np.ndarray
+    ind_gamma_g2l: np.ndarray
+    gd_nodes: List[np.ndarray]
+    gamma_l2g: List[np.ndarray]
+    node_Id: List[np.ndarray]
+    elemd: List[np.ndarray] = field(default_factory=list)
+
+    @property
+    def n_gamma(self):
+        return int(self.node_gamma.size)
+
+
+@dataclass
+class LocalBlocks:
+    """Outputs of prepare_local_schurs (:545)."""
+    A_II: list
+    A_IG: list
+    A_GG: list
+    b_I: list
+    b_G: np.ndarray
+
+
+def restriction(sd, d):
+    """R_d: n_Γd x n_Γ boolean gather matrix (the Dict loops at :728-730)."""
+    g = np.asarray(sd.gamma_l2g[d])
+    return sp.csr_matrix((np.ones(g.size), (np.arange(g.size), g)), shape=(g.size, sd.n_gamma))
 
 
 def set_subdomains_ref(cells, cell_neighbors, epart, npart, is_dirichlet):
@@ -163,7 +202,7 @@ def prepare_local_schurs_ref(cells, points, epart, sd: Subdomains, coeff, f_vals
 def prepare_global_schur(cells, points, epart, sd: Subdomains, coeff, f_vals, u_dir):
     """prepare_global_schur (EllipticPdeDomainDecomposition.jl:212-369): same as the local
     version but A_IΓ,d has *global* interface columns and A_ΓΓ is the assembled block."""
-    lb = prepare_local_schurs(cells, points, epart, sd, coeff, f_vals, u_dir)
+    lb = prepare_local_schurs_ref(cells, points, epart, sd, coeff, f_vals, u_dir)
     n_g = sd.n_gamma
     A_IGg, A_GG = [], sp.csc_matrix((n_g, n_g))
     for d in range(sd.ndom):
@@ -306,24 +345,40 @@ def apply_neumann_neumann_schur(PiSd, sd: Subdomains, r):
 # Undecomposed system (cross-check of Example03:204)
 # ---------------------------------------------------------------------------------------------
 def do_isotropic_elliptic_assembly(cells, points, is_dirichlet, coeff, f_vals, u_dir):
-    """Fem/EllipticPde.jl:187-275 restated: global stiffness on non-Dirichlet nodes with the
-    Dirichlet lift and the same load-vector rule.  Returns A (csc), b, free-node list."""
+    """Literal element loop of do_isotropic_elliptic_assembly, Fem/EllipticPde.jl:187-275 (0-based):
+    global stiffness on the non-Dirichlet nodes, Dirichlet lift into the right-hand side (:253-254),
+    load-vector rule (2 f_i + f_j + f_k) * Area / 12 (:259-271).  Pure Python, small meshes only.
+    Returns A (csc), b, free-node list."""
     nnode = points.shape[1]
     nel = cells.shape[1]
-    K, area = _element_geometry(cells, points, coeff)
-    free = np.nonzero(~np.asarray(is_dirichlet, bool))[0]
-    g2l = np.full(nnode, -1, dtype=np.int64)
-    g2l[free] = np.arange(free.size)
-    ni = np.broadcast_to(cells[:, None, :], (3, 3, nel))
-    nj = np.broadcast_to(cells[None, :, :], (3, 3, nel))
-    fi_, fj_ = g2l[ni] >= 0, g2l[nj] >= 0
-    m = fi_ & fj_
-    A = sp.coo_matrix((K[m], (g2l[ni[m]], g2l[nj[m]])), shape=(free.size, free.size)).tocsc()
+    isd = np.asarray(is_dirichlet, bool)
+    free = np.nonzero(~isd)[0]
+    g2l = {int(nd): k for k, nd in enumerate(free)}                      # not_dirichlet_inds_g2l
+    I, J, V = [], [], []
     b = np.zeros(free.size)
-    ml = (~fi_) & fj_
-    np.add.at(b, g2l[nj[ml]], -(K[ml] * u_dir[ni[ml]]))
-    fv = f_vals[cells]
-    db = (2 * fv + fv[[1, 2, 0]] + fv[[2, 0, 1]]) * area[None, :] / 12
-    mf = g2l[cells] >= 0
-    np.add.at(b, g2l[cells[mf]], db[mf])
+    x, y = np.zeros(3), np.zeros(3)
+    dx, dy = np.zeros(3), np.zeros(3)
+    for iel in range(nel):                                               # :209
+        nodes = [int(v) for v in cells[:, iel]]
+        da = 0.0
+        for j, jn in enumerate(nodes):                                   # :214-218
+            x[j], y[j] = points[0, jn], points[1, jn]
+            da += coeff[jn]
+        da /= 3.0
+        dx[0], dx[1], dx[2] = x[2] - x[1], x[0] - x[2], x[1] - x[0]      # :221-226
+        dy[0], dy[1], dy[2] = y[1] - y[2], y[2] - y[0], y[0] - y[1]
+        area = (dx[2] * dy[1] - dx[1] * dy[2]) / 2.0                     # :229
+        for i, inode in enumerate(nodes):                                # :232
+            for j, jnode in enumerate(nodes):
+                kij = da * (dy[i] * dy[j] + dx[i] * dx[j]) / 4 / area    # :241
+                if (not isd[inode]) and (not isd[jnode]):                # :247
+                    I.append(g2l[inode]); J.append(g2l[jnode]); V.append(kij)
+                elif isd[inode] and not isd[jnode]:                      # :253
+                    b[g2l[jnode]] -= u_dir[inode] * kij
+        for i, inode in enumerate(nodes):                                # :259
+            if not isd[inode]:
+                j, k = (i + 1) % 3, (i + 2) % 3
+                b[g2l[inode]] += (2 * f_vals[nodes[i]] + f_vals[nodes[j]] + f_vals[nodes[k]]) * area / 12
+    A = sp.coo_matrix((V, (I, J)), shape=(free.size, free.size)).tocsc()  # sparse(I, J, V) sums duplicates
+    A.sum_duplicates()
     return A, b, free

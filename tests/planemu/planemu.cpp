@@ -280,3 +280,46 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
 extern "C" uint32_t planemu_realigned_exchange_seq(uint32_t seq_now, uint32_t seq_before, int64_t enqueued, int64_t run) {
   return kb::realigned_exchange_seq(seq_now, seq_before, enqueued, run);
 }
+
+// CPU emulation of the owner-ordered compact interface exchange (csrc/xchg_tables.h + the arithmetic of
+// exchange_gather in csrc/kernels.cuh) for `world` ranks: loc_all = concatenation over ALL subdomains of
+// their local interface vectors; y_out[rank * ng + g] = what rank `rank` assembles.  Returns the number
+// of gathered entries (all ranks), or -1 on error.
+#include "../../julia-phd-krylov-spdes_b200/csrc/xchg_tables.h"
+extern "C" int64_t planemu_exchange(int world, int64_t ndom, int64_t ng, const int64_t* n_gd, const int32_t* l2g_cat,
+                                    const double* loc_all, const double* base, int threads, double* y_out,
+                                    int64_t* sent_per_rank) {
+  try {
+    std::vector<std::vector<int32_t>> l2g(ndom);
+    std::vector<int64_t> dom_off(ndom + 1, 0);
+    for (int64_t d = 0; d < ndom; ++d) {
+      l2g[d].assign(l2g_cat + dom_off[d], l2g_cat + dom_off[d] + n_gd[d]);
+      dom_off[d + 1] = dom_off[d] + n_gd[d];
+    }
+    std::vector<const std::vector<int32_t>*> lp(ndom);
+    for (int64_t d = 0; d < ndom; ++d) lp[d] = &l2g[d];
+    std::vector<XchTables> T;
+    for (int r = 0; r < world; ++r) T.push_back(build_xchg_tables(world, r, lp, ng, threads));
+    std::vector<double> gathered((size_t)T[0].m_total, 0.0);
+    for (int r = 0; r < world; ++r) {
+      if (T[r].m_total != T[0].m_total || T[r].fin_src != T[0].fin_src || T[r].off != T[0].off) return -1;  // same layout on every rank
+      const double* loc = loc_all + dom_off[(ndom * r) / world];
+      const int m = T[r].off[r + 1] - T[r].off[r];
+      if (sent_per_rank) sent_per_rank[r] = m;
+      for (int e = 0; e < m; ++e) {
+        double a = (base != nullptr && T[r].snd_g[e] >= 0) ? base[T[r].snd_g[e]] : 0.0;
+        for (int k = T[r].snd_ptr[e]; k < T[r].snd_ptr[e + 1]; ++k) a += loc[T[r].snd_src[k]];
+        gathered[(size_t)T[r].off[r] + e] = a;
+      }
+    }
+    for (int r = 0; r < world; ++r)
+      for (int64_t g = 0; g < ng; ++g) {
+        double s = 0.0;
+        for (int k = T[r].fin_ptr[g]; k < T[r].fin_ptr[g + 1]; ++k) s += gathered[T[r].fin_src[k]];
+        y_out[(size_t)r * ng + g] = s;
+      }
+    return T[0].m_total;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}

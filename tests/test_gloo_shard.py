@@ -73,13 +73,8 @@ def test_exchange_slots_alternate_across_solves_with_skipped_launches():
     import ctypes as C
     import random
     import subprocess
-    emu_dir = os.path.join(ROOT, "tests", "planemu")
-    so = os.path.join(emu_dir, "libplanemu.so")
-    srcs = [os.path.join(emu_dir, "planemu.cpp"), os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc", "plan.cpp")]
-    hdr = os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc", "xchg_seq.h")
-    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs + [hdr]):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + srcs + ["-o", so])
-    lib = C.CDLL(so)
+    from planemu.build import build as build_emu
+    lib = C.CDLL(build_emu())
     lib.planemu_realigned_exchange_seq.restype = C.c_uint32
     lib.planemu_realigned_exchange_seq.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int64]
     for seed in range(100):
@@ -109,3 +104,48 @@ def test_exchange_slots_alternate_across_solves_with_skipped_launches():
                 k = kend
                 done = ran >= want or k >= maxit
             seq = lib.planemu_realigned_exchange_seq(seq, seq_before, k - 1, ran)
+
+
+def test_compact_exchange_reproduces_the_sequential_sum_bit_for_bit():
+    """The owner-ordered compact exchange (csrc/xchg_tables.h, exchange_gather in kernels.cuh) emulated on
+    the CPU through the product's own table builder: for 1..8 ranks every rank assembles exactly the bits of
+    the reference's sequential sum over ascending subdomains (EllipticPdeDomainDecomposition.jl:740-742),
+    with and without a base vector, and all ranks together send little more than n_gamma entries."""
+    import ctypes as C
+    import krylov_b200  # noqa: F401
+    from krylov_b200.hostprep import problem as PB
+    from planemu.build import build as build_emu
+    lib = C.CDLL(build_emu())
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    lib.planemu_exchange.restype = C.c_int64
+    lib.planemu_exchange.argtypes = [C.c_int, C.c_int64, C.c_int64, np.ctypeslib.ndpointer(np.int64, flags="C"),
+                                     np.ctypeslib.ndpointer(np.int32, flags="C"), f64p, C.c_void_p, C.c_int, f64p,
+                                     np.ctypeslib.ndpointer(np.int64, flags="C")]
+    for nx, ndom, jitter in [(33, 4, 0.2), (65, 16, 0.2), (49, 9, 0.0), (65, 13, 0.3)]:
+        sd = PB.build_mesh_and_partition(nx, ndom, jitter)[-1]
+        ng = sd.n_gamma
+        n_gd = np.array([g.size for g in sd.gamma_l2g], dtype=np.int64)
+        l2g = np.concatenate(sd.gamma_l2g).astype(np.int32)
+        rng = np.random.default_rng(nx)
+        # values spread over many magnitudes: any change of the association order changes bits
+        loc = rng.standard_normal(l2g.size) * 10.0 ** rng.integers(-8, 8, l2g.size)
+        base = rng.standard_normal(ng)
+        for with_base in (False, True):
+            seq = base.copy() if with_base else np.zeros(ng)
+            off = 0
+            for d in range(ndom):                       # the reference's loop: ascending subdomains
+                g = sd.gamma_l2g[d]
+                seq[g] += loc[off:off + g.size]
+                off += g.size
+            for world in (1, 2, 3, 4, 8):
+                if world > ndom:
+                    continue
+                y = np.zeros(world * ng)
+                sent = np.zeros(world, dtype=np.int64)
+                m = lib.planemu_exchange(world, ndom, ng, n_gd, l2g, loc, base.ctypes.data if with_base else None, 256, y, sent)
+                assert m >= ng and sent.sum() == m
+                assert m <= l2g.size                     # never more than one entry per contribution
+                if (nx, ndom, world) == (65, 16, 2):     # few rank-crossing nodes: little more than n_gamma entries
+                    assert m <= 1.25 * ng
+                for r in range(world):
+                    assert np.array_equal(y[r * ng:(r + 1) * ng], seq), (nx, ndom, world, r)

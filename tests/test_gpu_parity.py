@@ -92,6 +92,31 @@ def test_interface_maps_bit_for_bit(nx, ndom, csize):
             assert sd.gamma_l2g[d][l] == g
 
 
+def test_global_column_operator_equals_local_operator():
+    """a6: apply_global_schur (:596-625) on the device from prepare_global_schur's blocks (:212-369) -- the
+    reference's own check Example03_EllipticPdeDomainDecomposition.jl:175 (global == local operator) --
+    and a CG / PCG solve through it."""
+    pr, S, M = gpu_ops(65, 16, 4)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    sd = pr.sd
+    A_II, A_IGg, A_GG, b_I, b_G = E.prepare_global_schur(pr.cells, pr.points, pr.epart, sd, pr.coeff, pr.f_vals, pr.u_dir)
+    Sg = fem.B200GlobalSchurOperator(sd, A_IGg, A_GG, pr.factors, csize=4)
+    X = np.random.default_rng(4).standard_normal((sd.n_gamma, 2))
+    Y = Sg * X
+    for k in range(2):
+        assert rel(Y[:, k], E.apply_global_schur(A_II, A_IGg, A_GG, inner, X[:, k])) <= 1e-12
+        assert rel(Y[:, k], S * X[:, k]) <= 1e-12                                   # Example03:175
+    Mg = fem.B200NeumannNeumann(Sg, Pi)
+    xg, itg, _ = solvers.pcg(Sg, bs, np.zeros(sd.n_gamma), Mg)
+    xl, itl, _ = solvers.pcg(S, bs, np.zeros(sd.n_gamma), M)
+    assert abs(itg - itl) <= 1 and np.linalg.norm(xg - xl) <= 1e-6 * np.linalg.norm(xl)
+    with pytest.raises(capi.KB200Error):                                             # a column outside Γ_d
+        bad = A_IGg[0].tolil()
+        other = np.setdiff1d(np.arange(sd.n_gamma), sd.gamma_l2g[0])[0]
+        bad[0, other] = 1.0
+        Sg.h.upload_global_blocks(0, bad.tocsc())
+
+
 def test_golden_vectors_on_gpu():
     g = np.load(GOLD)
     pr, S, M = gpu_ops(33, 4, 2)

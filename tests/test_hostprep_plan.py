@@ -19,10 +19,8 @@ PLAN_SRC = os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc", "plan.cpp")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [EMU_SRC, PLAN_SRC, PLAN_SRC.replace(".cpp", ".h"), os.path.join(os.path.dirname(PLAN_SRC), "xchg_seq.h")]
-    if not os.path.exists(EMU_SO) or any(os.path.getmtime(EMU_SO) < os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", EMU_SRC, PLAN_SRC, "-o", EMU_SO])
-    lib = C.CDLL(EMU_SO)
+    from planemu.build import build as build_emu
+    lib = C.CDLL(build_emu())
     i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
     f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
     lib.planemu_run.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, f64p, i32p, i32p, f64p, i32p, i32p, f64p,
