@@ -41,7 +41,7 @@ class Timings(C.Structure):
 def build(force=False, with_nccl=True):
     """Compile libkrylov_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("api.cu", "plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_seq.h", "xchg_tables.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_tables.h")] + \
         [os.path.join(_HERE, "..", "include", "krylov_b200.h")]
     if not force and os.path.exists(LIB_PATH) and \
             all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):

@@ -21,7 +21,6 @@
 #include "../../include/krylov_b200.h"
 #include "kernels.cuh"
 #include "plan.h"
-#include "xchg_seq.h"
 #include "xchg_tables.h"
 
 namespace {
@@ -128,7 +127,8 @@ struct kb200_ctx {
   int xch_snd_off = 0, xch_snd_n = 0;  // this rank's entries
   int xch_flag_off = 0, xch_nflags = 0;
   DevBuf<int32_t> d_snd_ptr, d_snd_src, d_snd_g, d_fin_ptr, d_fin_src;
-  uint32_t xch_seq = 0;
+  uint32_t xch_launch = 0;             // launches that carry an exchange (skipped ones included): parity selects the counter word
+  DevBuf<uint32_t> d_xcnt;             // device-side ping-pong counter of real exchanges (kernels.cuh)
   bool fused_ok = true;                // the grid of the fused PCG kernels is co-resident (checked at finalize)
   int merge_depth = 0;              // supernode grouping depth of the host analysis (0: automatic)
   int gemv_rows = 0;                // rows per CTA of the dense GEMV (0: automatic)
@@ -146,6 +146,7 @@ struct kb200_ctx {
   bool topo = false, finalized = false, have_pinv = false, have_sd = false;
   // prepare_global_schur variant (EllipticPdeDomainDecomposition.jl:212-369): A_IΓ,d came with global
   // interface columns and the interface block as ONE assembled A_ΓΓ (CSR copy on the device)
+  bool sd_on_device_only = false;   // dense S_d assembled on the device: host copies are fetched lazily
   bool global_mode = false;
   std::vector<int32_t> gg_ptr, gg_col;
   std::vector<double> gg_val;
@@ -156,7 +157,9 @@ struct kb200_ctx {
   std::vector<int64_t> I_base_global;           // per subdomain (+1): offsets in the caller's b_I_concat
   std::vector<int64_t> mat_off;                 // dense block offsets (local)
   std::vector<int32_t> adj_ptr, adj_src, adj_dom, adj_loc;
-  int max_gd = 0, smem_bytes = 0, n_cta = 0;
+  int max_gd = 0, smem_bytes = 0, smem_doubles = 0, n_cta = 0;
+  int smem_limit = 0;   // dynamic shared memory a CTA of the stream kernel may use (opt-in maximum minus static)
+  int rhs_block = 0;    // option: right-hand sides per launch of the multi-vector stream kernel (0: automatic)
   double stats[32] = {0};
   // device pools
   DevBuf<kb::CtaDesc> d_ctas;
@@ -172,6 +175,9 @@ struct kb200_ctx {
   std::vector<std::unique_ptr<DevBuf<double>>> mats;
   std::vector<int64_t> mat_cols;
   DevBuf<double> d_small, d_small2, d_xtmp;
+  DevBuf<double> d_gemm_ws;         // partial tiles of the split tall-skinny products
+  DevBuf<double> d_locm;            // local-interface results of a block of right-hand sides: (sum n_gd) x columns
+  int dense_dmma_min = 4;           // option: fewest right-hand sides for which the dense products run on DMMA
   int debug_timing = 0, dbg_flags = 0;
   int nb = 0;  // blocks of the interface-vector kernels
   int64_t launches = 0;
@@ -224,10 +230,39 @@ bool is_local(const Ctx* c, int64_t d) { return d >= c->d0 && d < c->d1; }
 void invalidate_dense_schur(Ctx* c, DomHost& dh) {
   dh.Sd.clear();
   c->have_sd = false;
+  c->sd_on_device_only = false;
 }
 
 void setup_peer_exchange(Ctx* c);
 void build_exchange_tables(Ctx* c);
+
+// Every instantiation of the stream kernel for `warps` consumer warps (R = 1, 2, 4 right-hand sides)
+template <class F>
+void for_each_stream_kernel(int warps, F&& f) {
+#define KB_ALL_MODES(NW, R)                                                   \
+  f((const void*)kb::schur_stream_kernel<kb::MODE_APPLY, NW, R>);             \
+  f((const void*)kb::schur_stream_kernel<kb::MODE_RHS, NW, R>);               \
+  f((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, NW, R>);           \
+  f((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, NW, R>);
+  if (warps == kb::kWarps) {
+    KB_ALL_MODES(kb::kWarps, 1) KB_ALL_MODES(kb::kWarps, 2) KB_ALL_MODES(kb::kWarps, 4)
+  } else {
+    KB_ALL_MODES(16, 1) KB_ALL_MODES(16, 2) KB_ALL_MODES(16, 4)
+  }
+#undef KB_ALL_MODES
+}
+
+// dynamic shared memory of a stream-kernel CTA for R right-hand sides per launch
+size_t stream_smem_bytes(const Ctx* c, int R) {
+  return ((size_t)c->smem_doubles + kb::kMaxSlots) * 8 * (size_t)R + (size_t)c->stages * kb::kChunkBytes;
+}
+// largest R in {4, 2, 1} not above `want` whose shared-memory vector fits
+int stream_rhs_block(const Ctx* c, int64_t want) {
+  int cap = c->rhs_block > 0 ? c->rhs_block : 4;
+  for (int R = 4; R > 1; R >>= 1)
+    if (R <= cap && R <= want && stream_smem_bytes(c, R) <= (size_t)c->smem_limit) return R;
+  return 1;
+}
 
 // ---- finalize: build plans, upload -------------------------------------------------------------
 void finalize(Ctx* c) {
@@ -342,6 +377,7 @@ void finalize(Ctx* c) {
     n_pkt += (double)plans[k].n_packets;
   }
   c->max_gd = max_gd;
+  c->smem_doubles = max_smem;
   c->smem_bytes = max_smem * 8 + c->stages * kb::kChunkBytes + kb::kMaxSlots * 8;
   c->n_cta = (int)(nloc * c->csize);
   // descriptors with global offsets
@@ -425,7 +461,7 @@ void finalize(Ctx* c) {
     c->d_gtmp.alloc(c->n_gamma);
   }
   if (c->have_pinv) upload_dense(c->d_pinv, true);
-  if (c->have_sd) upload_dense(c->d_sd, false);
+  if (c->have_sd && !c->sd_on_device_only) upload_dense(c->d_sd, false);
   // vectors
   const int64_t ng = c->n_gamma;
   // block size of the interface-vector kernels: few large blocks when every assembly ends in a peer
@@ -475,26 +511,20 @@ void finalize(Ctx* c) {
   // raise it to the device maximum instead of this handle's own requirement
   int smem_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  c->smem_limit = INT_MAX;
   auto set_attr = [&](const void* fn) {
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
     const int dyn_max = smem_optin - (int)fa.sharedSizeBytes;
-    if (c->smem_bytes > dyn_max)
-      throw KbError(KB200_ERR_INPUT, "subdomain too large for the shared-memory vector: raise csize");
+    c->smem_limit = std::min(c->smem_limit, dyn_max);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
     if (c->csize > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   };
-  if (c->warps == kb::kWarps) {
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY, kb::kWarps>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS, kb::kWarps>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, kb::kWarps>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, kb::kWarps>);
-  } else {
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_APPLY, 16>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_RHS, 16>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_BACKSUB, 16>);
-    set_attr((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, 16>);
-  }
+  for_each_stream_kernel(c->warps, set_attr);
+  if (c->smem_bytes > c->smem_limit)
+    throw KbError(KB200_ERR_INPUT, "subdomain too large for the shared-memory vector: raise csize");
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kb::gemm_nn_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kb::kNnMaxK * kb::kNnLd * 8));
   // nvec up to 4096 in the deflated solvers: 3 nvec doubles of dynamic shared memory
   CUDA_TRY(cudaFuncSetAttribute((const void*)kb::small_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 24));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -590,7 +620,9 @@ void setup_peer_exchange(Ctx* c) {
     cudaGetLastError();
   }
   c->peer_ok = ok != 0;
-  c->xch_seq = 0;
+  c->xch_launch = 0;
+  c->d_xcnt.alloc(2);
+  CUDA_TRY(cudaMemset(c->d_xcnt.p, 0, 2 * sizeof(uint32_t)));
 #else
   (void)c;
 #endif
@@ -621,9 +653,16 @@ void build_exchange_tables(Ctx* c) {
 }
 
 // ---- launches ----------------------------------------------------------------------------------
+struct StreamIo {
+  const double* x_gamma = nullptr;  // interface vector(s) in
+  const double* bI = nullptr;       // interior vector(s) in
+  double* uI = nullptr;             // interior vector(s) out
+  double* out_loc = nullptr;        // local-interface vector(s) out
+  int64_t ldx = 0, ldi = 0, ldo = 0;
+};
+
 template <int MODE>
-void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, double* out_loc, const int* done_at,
-                   int iter, int unit_col0 = 0, int ncols = 1) {
+void launch_stream(Ctx* c, const StreamIo& io, const int* done_at, int iter, int R = 1, int unit_col0 = 0, int ngroups = 1) {
   if (c->n_cta == 0) return;
   kb::StreamParams P;
   std::memset(&P, 0, sizeof(P));
@@ -631,10 +670,13 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   P.stream = c->d_stream.p;
   P.l2g = c->d_l2g.p;
   P.imap = c->d_imap.p;
-  P.x_gamma = x_gamma;
-  P.bI = bI;
-  P.uI = uI;
-  P.out_loc = out_loc;
+  P.x_gamma = io.x_gamma;
+  P.bI = io.bI;
+  P.uI = io.uI;
+  P.out_loc = io.out_loc;
+  P.ldx = io.ldx;
+  P.ldi = io.ldi;
+  P.ldo = io.ldo;
   P.sd_pool = c->d_sd.p;
   P.sd_off = c->d_mat_off.p;
   P.done_at = done_at;
@@ -650,11 +692,14 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
     }
     P.dbg = c->d_dbg.p;
   }
+  require(R == 1 || R == 2 || R == 4, "internal: bad right-hand-side block");
+  const size_t smem = stream_smem_bytes(c, R);
+  require(smem <= (size_t)c->smem_limit, "internal: right-hand-side block does not fit the shared-memory vector");
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)c->n_cta, (unsigned)ncols, 1);
+  cfg.gridDim = dim3((unsigned)c->n_cta, (unsigned)ngroups, 1);
   cfg.blockDim = dim3((unsigned)kb::stream_threads(c->warps), 1, 1);
-  cfg.dynamicSmemBytes = (size_t)c->smem_bytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -665,9 +710,28 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = c->pdl_now ? 2 : 1;
-  if (c->warps == kb::kWarps) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps>, P));
-  else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16>, P));
+  if (c->warps == kb::kWarps) {
+    if (R == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 1>, P));
+    else if (R == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 2>, P));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 4>, P));
+  } else {
+    if (R == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16, 1>, P));
+    else if (R == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16, 2>, P));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 16, 4>, P));
+  }
   c->launches++;
+}
+
+// single right-hand side (the call shape of the per-iteration path)
+template <int MODE>
+void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, double* out_loc, const int* done_at,
+                   int iter) {
+  StreamIo io;
+  io.x_gamma = x_gamma;
+  io.bI = bI;
+  io.uI = uI;
+  io.out_loc = out_loc;
+  launch_stream<MODE>(c, io, done_at, iter, 1);
 }
 
 void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double* out_loc, const int* done_at,
@@ -732,8 +796,8 @@ kb::XchParams next_exchange(Ctx* c) {
   X.fin_src = c->d_fin_src.p;
   X.world = c->world;
   X.rank = c->rank;
-  X.seq = ++c->xch_seq;
-  X.slot = (int)(X.seq & 1u);
+  X.cnt = c->d_xcnt.p;
+  X.par = (int)(c->xch_launch++ & 1u);
   X.m_pad = c->xch_mpad;
   X.snd_off = c->xch_snd_off;
   X.snd_n = c->xch_snd_n;
@@ -741,15 +805,6 @@ kb::XchParams next_exchange(Ctx* c) {
   X.nflags = c->xch_nflags;
   X.fail = &c->d_state.p->fail;
   return X;
-}
-
-// Launches skipped on the device after convergence consume exchange numbers without exchanging.  The two
-// receive slots must alternate between consecutive REAL exchanges (see kernels.cuh), so after a stretch of
-// iterations the host -- which knows how many of the enqueued iterations really ran, identically on every
-// rank -- re-aligns the counter: the next exchange takes the slot the last real one did not use.
-void realign_exchange_slots(Ctx* c, uint32_t seq_before, int64_t iters_enqueued, int64_t iters_run) {
-  if (!c->peer_ok) return;
-  c->xch_seq = kb::realigned_exchange_seq(c->xch_seq, seq_before, iters_enqueued, iters_run);
 }
 
 // y = sum_d R_d' loc_d (+ base), optionally partial dot with q.  In multi-rank mode the interface
@@ -857,6 +912,56 @@ void apply_op(Ctx* c, OpKind op, const double* in, double* out, const double* q,
   assemble(c, c->d_loc.p, base, out, q, part, done_at, iter);
 }
 
+// ---- tall-skinny dense products with the recycling bases (FP64 DMMA, kernels.cuh) ------------------------------
+// C (ka x kb, column-major, device) = A[:, 0:ka]' B[:, 0:kb]; A, B: n_gamma rows, leading dimension n_gamma
+void gemm_tn(Ctx* c, int ka, int kb_, const double* A, const double* B, double* C) {
+  const int n = (int)c->n_gamma;
+  if ((int64_t)ka * kb_ < 64) {  // a handful of dot products: the scalar kernel
+    dim3 grid((unsigned)((ka + 15) / 16), (unsigned)((kb_ + 15) / 16));
+    kb::gemm_tn_kernel<<<grid, 256, 0, c->stream>>>(n, ka, kb_, A, n, B, n, C);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return;
+  }
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const int ti = (ka + kb::kTnTM - 1) / kb::kTnTM, tj = (kb_ + kb::kTnTN - 1) / kb::kTnTN;
+  int nsplit = std::max(1, (2 * sms + ti * tj - 1) / (ti * tj));
+  nsplit = std::min(nsplit, std::max(1, n / 256));
+  int rows = (n + nsplit - 1) / nsplit;
+  rows = (rows + 3) & ~3;
+  nsplit = (n + rows - 1) / rows;
+  const int64_t nel = (int64_t)ka * kb_;
+  if ((int64_t)c->d_gemm_ws.n < nel * nsplit) c->d_gemm_ws.alloc((size_t)(nel * nsplit));
+  dim3 grid((unsigned)ti, (unsigned)tj, (unsigned)nsplit);
+  kb::gemm_tn_dmma_kernel<<<grid, 256, 0, c->stream>>>(n, ka, kb_, A, n, B, n, c->d_gemm_ws.p, rows);
+  kb::gemm_tn_reduce_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, c->stream>>>(nel, nsplit, c->d_gemm_ws.p, C);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 2;
+}
+
+// C[:, 0:kq] = A[:, 0:ka] Q (Q: ka x kq column-major, device); C may alias A (V[:, 1:nev] = V (Q Z), eigcg.jl:228)
+void gemm_nn(Ctx* c, int ka, int kq, const double* A, const double* Q, double* C) {
+  const int n = (int)c->n_gamma;
+  if (ka <= kb::kNnMaxK) {  // the row panel of A fits shared memory: A is read once, in place is safe
+    const int kap = (ka + 3) & ~3;
+    const size_t smem = (size_t)kap * kb::kNnLd * 8;
+    kb::gemm_nn_dmma_kernel<<<(unsigned)((n + kb::kNnRows - 1) / kb::kNnRows), 256, smem, c->stream>>>(n, ka, kq, A, n, Q, C, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return;
+  }
+  // wide bases: column-at-a-time kernel through a temporary block
+  DevBuf<double> tmp;
+  tmp.alloc((size_t)n * kq);
+  dim3 grid((unsigned)c->nb, (unsigned)kq);
+  kb::gemm_nn_kernel<<<grid, c->vec_threads, 0, c->stream>>>(n, ka, kq, A, n, Q, tmp.p, n);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+  CUDA_TRY(cudaMemcpyAsync(C, tmp.p, (size_t)n * kq * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
 void h2d(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = nullptr) {
   CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
   if (t) t->h2d_bytes += n * 8;
@@ -866,15 +971,125 @@ void d2h(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = n
   if (t) t->d2h_bytes += n * 8;
 }
 
+// Shared state of a block of independent recurrences (kb200_pcg_multi) seen by the operator applications
+struct MultiCtx {
+  const double* q = nullptr;    // optional: part[j * nb + b] = block partials of dot(out_j, q_j)
+  double* part = nullptr;
+  kb::PcgState* st = nullptr;   // per-column state: columns with st[j].done_at < iter are frozen
+  int iter = 0;
+  const int* all_done = nullptr;  // the shared operator launches exit early when *all_done < iter
+};
+
+void launch_dense_gemm(Ctx* c, const double* mats, bool scale, const double* x, int64_t ldx, int k, double* out_loc, int64_t ldo,
+                       const int* done_at, int iter) {
+  const int64_t nloc = c->d1 - c->d0;
+  if (nloc == 0) return;
+  kb::GemmParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.mats = mats;
+  P.mat_off = c->d_mat_off.p;
+  P.n_gd = c->d_ngd.p;
+  P.G_base = c->d_G_base.p;
+  P.l2g = c->d_l2g.p;
+  P.x = x;
+  P.ldx = ldx;
+  P.inv_cnt = scale ? c->d_inv_cnt.p : nullptr;
+  P.out_loc = out_loc;
+  P.ldo = ldo;
+  P.k = k;
+  P.done_at = done_at;
+  P.iter = iter;
+  dim3 grid((unsigned)((c->max_gd + kb::kGemmBM - 1) / kb::kGemmBM), (unsigned)nloc, 1);
+  if (k <= 8) kb::dense_gemm_kernel<8><<<grid, 256, 0, c->stream>>>(P);
+  else if (k <= 16) kb::dense_gemm_kernel<16><<<grid, 256, 0, c->stream>>>(P);
+  else if (k <= 32) kb::dense_gemm_kernel<32><<<grid, 256, 0, c->stream>>>(P);
+  else kb::dense_gemm_kernel<64><<<grid, 256, 0, c->stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  c->launches++;
+}
+
+// out[:, j] = Op(in[:, j]), j < k, on device blocks (n_gamma x k, leading dimension n_gamma).  The factor stream
+// is read once per R right-hand sides (multi-vector stream kernel), the dense local products run as batched
+// FP64 DMMA GEMMs; the interface assembly runs per column (same arithmetic as the single-vector path).
+void apply_op_multi(Ctx* c, OpKind op, const double* in, double* out, int64_t k, const MultiCtx& mc, KernelTimer* kt) {
+  const int64_t n = c->n_gamma;
+  const int64_t nloc = c->d1 - c->d0;
+  const int64_t Gtot = c->G_base[nloc];
+  const bool dense = op != OP_SCHUR;
+  if (op == OP_SCHUR_DENSE) require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
+  if (op == OP_NN) require(c->have_pinv, "kb200_upload_nn_pinv was not called");
+  if (k == 1 || (c->global_mode && op == OP_SCHUR) || (dense && k < c->dense_dmma_min)) {
+    // column by column through the single-vector kernels
+    for (int64_t j = 0; j < k; ++j) {
+      const int* done = mc.st ? &mc.st[j].done_at : nullptr;
+      apply_op(c, op, in + j * n, out + j * n, mc.q ? mc.q + j * n : nullptr, mc.part ? mc.part + j * c->nb : nullptr, done,
+               mc.iter, kt);
+    }
+    return;
+  }
+  const int64_t kblock = dense ? std::min<int64_t>(k, 64) : 4;
+  if ((int64_t)c->d_locm.n < Gtot * kblock) c->d_locm.alloc((size_t)(Gtot * kblock));
+  const bool timed = kt != nullptr && c->profile;
+  for (int64_t j0 = 0; j0 < k;) {
+    int kb_ = 0;
+    cudaEvent_t ev = nullptr;
+    if (!dense) {
+      kb_ = stream_rhs_block(c, k - j0);
+      StreamIo io;
+      io.x_gamma = in + j0 * n;
+      io.ldx = n;
+      io.out_loc = c->d_locm.p;
+      io.ldo = Gtot;
+      if (timed) kt->begin(0, ev);
+      launch_stream<kb::MODE_APPLY>(c, io, mc.all_done, mc.iter, kb_);
+      if (timed) kt->end(0, ev);
+    } else {
+      kb_ = (int)std::min<int64_t>(64, k - j0);
+      if (timed) kt->begin(op == OP_NN ? 1 : 0, ev);
+      launch_dense_gemm(c, op == OP_NN ? c->d_pinv.p : c->d_sd.p, op == OP_NN, in + j0 * n, n, kb_, c->d_locm.p, Gtot, mc.all_done,
+                        mc.iter);
+      if (timed) kt->end(op == OP_NN ? 1 : 0, ev);
+    }
+    if (!c->has_comm) {
+      dim3 grid((unsigned)c->nb, (unsigned)kb_, 1);
+      kb::assemble_multi_kernel<<<grid, c->vec_threads, 0, c->stream>>>(
+          (int)n, c->d_adj_ptr.p, c->d_adj_src.p, c->d_locm.p, Gtot, out + j0 * n, mc.q ? mc.q + j0 * n : nullptr, n,
+          mc.part ? mc.part + j0 * c->nb : nullptr, mc.st ? mc.st + j0 : nullptr, mc.iter);
+      CUDA_TRY(cudaGetLastError());
+      c->launches++;
+    } else {
+      for (int64_t jj = 0; jj < kb_; ++jj) {
+        const int64_t j = j0 + jj;
+        assemble(c, c->d_locm.p + jj * Gtot, nullptr, out + j * n, mc.q ? mc.q + j * n : nullptr,
+                 mc.part ? mc.part + j * c->nb : nullptr, mc.st ? &mc.st[j].done_at : nullptr, mc.iter);
+      }
+    }
+    j0 += kb_;
+  }
+}
+
 void host_apply(Ctx* c, OpKind op, const double* x, double* y, int64_t nrhs) {
   require(x && y && nrhs >= 1, "null vector or nrhs < 1");
   finalize(c);
   use_device(c);
   const int64_t n = c->n_gamma;
-  for (int64_t k = 0; k < nrhs; ++k) {
-    h2d(c, c->d_x.p, x + k * n, n);
+  if (nrhs == 1) {
+    h2d(c, c->d_x.p, x, n);
     apply_op(c, op, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, nullptr);
-    d2h(c, y + k * n, c->d_Ap.p, n);
+    d2h(c, y, c->d_Ap.p, n);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return;
+  }
+  // blocks of right-hand sides: the factor stream / the dense blocks are read once per block
+  const int64_t kb_ = std::min<int64_t>(nrhs, 64);
+  DevBuf<double> dX, dY;
+  dX.alloc((size_t)(n * kb_));
+  dY.alloc((size_t)(n * kb_));
+  for (int64_t j0 = 0; j0 < nrhs; j0 += kb_) {
+    const int64_t k = std::min(kb_, nrhs - j0);
+    h2d(c, dX.p, x + j0 * n, n * k);
+    apply_op_multi(c, op, dX.p, dY.p, k, MultiCtx(), nullptr);
+    d2h(c, y + j0 * n, dY.p, n * k);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
   }
 }
@@ -1012,6 +1227,12 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "vec_threads") {
       require(!h->finalized && (value == 0 || value == 256 || value == 512 || value == 1024), "vec_threads is 0, 256, 512 or 1024, before the first operation");
       h->vec_threads = (int)value;
+    } else if (k == "rhs_block") {
+      require(value == 0 || value == 1 || value == 2 || value == 4, "rhs_block is 0 (automatic), 1, 2 or 4");
+      h->rhs_block = (int)value;
+    } else if (k == "dense_dmma_min") {
+      require(value >= 2, "dense_dmma_min must be >= 2");
+      h->dense_dmma_min = (int)std::min<int64_t>(value, 1 << 30);
     } else if (k == "pdl") {
       require(value == 0 || value == 1, "pdl is 0 or 1");
       h->pdl = (int)value;
@@ -1242,7 +1463,12 @@ static void store_dense(Ctx* h, int64_t d, const double* M, bool pinv) {
   dst.resize(n * n);
   for (int64_t i = 0; i < n; ++i)
     for (int64_t j = 0; j < n; ++j) dst[i * n + j] = M[i + j * n];  // column-major -> row-major
-  if (pinv) h->have_pinv = true; else h->have_sd = true;
+  if (pinv) {
+    h->have_pinv = true;
+  } else {
+    require(!h->sd_on_device_only, "dense local Schur blocks were assembled on the device: upload all of them or none");
+    h->have_sd = true;
+  }
   if (h->finalized) {
     use_device(h);
     DevBuf<double>& buf = pinv ? h->d_pinv : h->d_sd;
@@ -1316,30 +1542,29 @@ int kb200_assemble_local_schurs(kb200_handle h) {
     finalize(h);
     use_device(h);
     const int64_t nloc = h->d1 - h->d0;
+    if (nloc == 0) {
+      h->have_sd = true;
+      return;
+    }
     if (h->d_sd.p == nullptr) h->d_sd.alloc(h->mat_off[nloc]);
-    const int chunk = 64;
-    for (int col0 = 0; col0 < h->max_gd; col0 += chunk) {
-      const int nc = std::min(chunk, h->max_gd - col0);
-      launch_stream<kb::MODE_UNIT>(h, nullptr, nullptr, nullptr, nullptr, nullptr, 0, col0, nc);
+    // R unit vectors per CTA group (multi-vector stream kernel): the factor is streamed once per R columns;
+    // up to 64 column groups per launch run side by side (they read the same chunks: L2 hits)
+    const int R = stream_rhs_block(h, h->max_gd);
+    const int per_launch = 64 * R;
+    for (int col0 = 0; col0 < h->max_gd; col0 += per_launch) {
+      const int ngroups = (std::min(per_launch, h->max_gd - col0) + R - 1) / R;
+      launch_stream<kb::MODE_UNIT>(h, StreamIo(), nullptr, 0, R, col0, ngroups);
     }
+    // Symmetric(): mirror the upper triangle (EllipticPdeDomainDecomposition.jl:692) on the device; the
+    // symmetric block serves as its own row-major copy
+    dim3 grid(64, (unsigned)nloc, 1);
+    kb::symmetrize_kernel<<<grid, 256, 0, h->stream>>>(h->d_sd.p, h->d_mat_off.p, h->d_ngd.p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    // Symmetric(): mirror the upper triangle (EllipticPdeDomainDecomposition.jl:692), then keep a
-    // row-major copy on the device.  Done on the host: setup path, n_gd^2 per subdomain.
-    std::vector<double> buf;
-    for (int64_t k = 0; k < nloc; ++k) {
-      DomHost& dh = h->doms[h->d0 + k];
-      const int64_t n = dh.n_gd;
-      buf.resize(n * n);
-      CUDA_TRY(cudaMemcpy(buf.data(), h->d_sd.p + h->mat_off[k], (size_t)(n * n) * 8, cudaMemcpyDeviceToHost));
-      dh.Sd.resize(n * n);
-      for (int64_t i = 0; i < n; ++i)
-        for (int64_t j = 0; j < n; ++j) {
-          const double v = (i <= j) ? buf[i + j * n] : buf[j + i * n];  // column-major device block
-          dh.Sd[i * n + j] = v;                                          // symmetric => layout-free
-        }
-      CUDA_TRY(cudaMemcpy(h->d_sd.p + h->mat_off[k], dh.Sd.data(), (size_t)(n * n) * 8, cudaMemcpyHostToDevice));
-    }
+    for (int64_t k = 0; k < nloc; ++k) h->doms[h->d0 + k].Sd.clear();   // host copies are fetched on demand
     h->have_sd = true;
+    h->sd_on_device_only = true;
   });
 }
 
@@ -1347,9 +1572,15 @@ int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out) {
   return guarded([&]() {
     require(h && Sd_out && h->topo, "null argument");
     require(is_local(h, d), "subdomain is not local to this handle");
-    const DomHost& dh = h->doms[d];
-    require((int64_t)dh.Sd.size() == dh.n_gd * dh.n_gd, "dense local Schur not available");
+    require(h->have_sd, "dense local Schur not available");
+    DomHost& dh = h->doms[d];
     const int64_t n = dh.n_gd;
+    if ((int64_t)dh.Sd.size() != n * n) {
+      require(h->sd_on_device_only && h->d_sd.p != nullptr, "dense local Schur not available");
+      use_device(h);
+      dh.Sd.resize((size_t)(n * n));
+      CUDA_TRY(cudaMemcpy(dh.Sd.data(), h->d_sd.p + h->mat_off[d - h->d0], (size_t)(n * n) * 8, cudaMemcpyDeviceToHost));
+    }
     for (int64_t i = 0; i < n; ++i)
       for (int64_t j = 0; j < n; ++j) Sd_out[i + j * n] = dh.Sd[i * n + j];
   });
@@ -1461,7 +1692,7 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
         auto fn = c->peer_ok ? kb::pcg_fused_xr_kernel<true> : kb::pcg_fused_xr_kernel<false>;
         const cudaError_t le = cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.Ap, (const double*)I.p, I.x, I.r,
                                                   c->d_partA.p, c->d_partB.p, st, k, c->d_gsync.p, target, X);
-        if (le != cudaSuccess && c->peer_ok) --c->xch_seq;
+        if (le != cudaSuccess && c->peer_ok) --c->xch_launch;
         CUDA_TRY(le);
         ++c->gsync_launches;
       }
@@ -1475,7 +1706,7 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
         const cudaError_t le = cudaLaunchKernelEx(&vcfg, fn, n, adj_ptr, adj_src, loc, I.z, (const double*)I.r, I.p,
                                                   (const double*)c->d_partB.p, c->d_partC.p, st, c->d_res.p, vcol(k), I.hist,
                                                   k, c->d_gsync.p, target, X);
-        if (le != cudaSuccess && c->peer_ok) --c->xch_seq;
+        if (le != cudaSuccess && c->peer_ok) --c->xch_launch;
         CUDA_TRY(le);
         ++c->gsync_launches;
       }
@@ -1559,7 +1790,6 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   int* h_flag = reinterpret_cast<int*>(c->h_pinned);
   int k = 1;
   bool done = false;
-  const uint32_t seq_before = c->xch_seq;
   while (!done) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
     run_iterations(c, I, k, kend, &kt);
@@ -1571,7 +1801,6 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   }
   *it_out = h_flag[0];
   *fail_out = h_flag[3];
-  realign_exchange_slots(c, seq_before, (int64_t)k - 1, (int64_t)h_flag[0] - 1);   // it starts at 1
 }
 
 static void finish_timings(Ctx* c, KernelTimer& kt, kb200_timings& T, int64_t launches0, kb200_timings* tm) {
@@ -1617,22 +1846,127 @@ int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double 
   });
 }
 
+// Block of independent PCG recurrences on device-resident n x k blocks (kb200_pcg_multi): the operator
+// launches are shared by the columns, the scalars are per column (kernels.cuh, "Independent PCG recurrences").
+struct MultiWork {
+  DevBuf<double> B, X, R, Z, P, AP, partA, partB, partC, res;
+  DevBuf<kb::PcgState> st;
+  DevBuf<int> all_done;
+};
+
+static void pcg_multi_block(Ctx* c, MultiWork& w, int64_t k, int64_t maxit, double rtol, OpKind A, int precond,
+                            std::vector<kb::PcgState>& states_out) {
+  const int n = (int)c->n_gamma;
+  const int64_t ld = n, rs = maxit + 1;
+  const dim3 grid((unsigned)c->nb, (unsigned)k, 1);
+  const int T = c->vec_threads;
+  cudaStream_t s = c->stream;
+  MultiCtx mc;
+  // r = b - A x ; z = M \ r ; p = z                                                (cg.jl:83-90, per column)
+  apply_op_multi(c, A, w.X.p, w.AP.p, k, mc, nullptr);
+  kb::pcg_init_residual_multi_kernel<<<grid, T, 0, s>>>(n, w.B.p, w.AP.p, w.R.p, ld, w.partA.p, w.partB.p);
+  c->launches++;
+  if (precond) {
+    mc.q = w.R.p;
+    mc.part = w.partC.p;
+    apply_op_multi(c, OP_NN, w.R.p, w.Z.p, k, mc, nullptr);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(w.Z.p, w.R.p, (size_t)n * k * 8, cudaMemcpyDeviceToDevice, s));
+    for (int64_t j = 0; j < k; ++j)
+      kb::dot_kernel<<<c->nb, T, 0, s>>>(n, w.R.p + j * ld, w.Z.p + j * ld, w.partC.p + j * c->nb, nullptr, 0);
+    c->launches += k;
+  }
+  kb::pcg_init_direction_multi_kernel<<<grid, T, 0, s>>>(n, w.Z.p, w.P.p, ld, w.partA.p, w.partB.p, w.partC.p, w.st.p, w.res.p, rs,
+                                                          rtol, (int)maxit);
+  kb::pcg_multi_all_done_kernel<<<1, 1, 0, s>>>((int)k, w.st.p, w.all_done.p);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  int* h_flag = reinterpret_cast<int*>(c->h_pinned);
+  int it = 1;
+  bool done = false;
+  while (!done) {
+    const int kend = (int)std::min<int64_t>((int64_t)it + c->check_every, maxit);
+    for (; it < kend; ++it) {
+      MultiCtx m1;
+      m1.st = w.st.p;
+      m1.iter = it;
+      m1.all_done = w.all_done.p;
+      m1.q = w.P.p;
+      m1.part = w.partA.p;
+      apply_op_multi(c, A, w.P.p, w.AP.p, k, m1, nullptr);                              // Ap = A p ; d = p.Ap
+      kb::pcg_update_xr_multi_kernel<<<grid, T, 0, s>>>(n, w.P.p, w.AP.p, w.X.p, w.R.p, ld, w.partA.p, w.partB.p, w.st.p, it);
+      c->launches++;
+      if (precond) {
+        m1.q = w.R.p;
+        m1.part = w.partC.p;
+        apply_op_multi(c, OP_NN, w.R.p, w.Z.p, k, m1, nullptr);                         // z = M \ r ; rTz
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(w.Z.p, w.R.p, (size_t)n * k * 8, cudaMemcpyDeviceToDevice, s));
+        for (int64_t j = 0; j < k; ++j)
+          kb::dot_kernel<<<c->nb, T, 0, s>>>(n, w.R.p + j * ld, w.Z.p + j * ld, w.partC.p + j * c->nb, &w.st.p[j].done_at, it);
+        c->launches += k;
+      }
+      kb::pcg_update_p_multi_kernel<<<grid, T, 0, s>>>(n, w.Z.p, w.P.p, ld, w.partB.p, w.partC.p, w.st.p, w.res.p, rs, it);
+      kb::pcg_multi_all_done_kernel<<<1, 1, 0, s>>>((int)k, w.st.p, w.all_done.p);
+      c->launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_flag, w.all_done.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    done = (h_flag[0] != INT_MAX) || (it >= maxit);
+  }
+  states_out.resize((size_t)k);
+  CUDA_TRY(cudaMemcpyAsync(states_out.data(), w.st.p, (size_t)k * sizeof(kb::PcgState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+}
+
 int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, int64_t maxit, double rtol, int assembled, int precond,
                     int64_t* its, double* res_norm, int64_t res_stride) {
-  // independent recurrences per right-hand side (the reference's sequential loop over RHS,
-  // Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179); round 1: one solve after the other
-  if (!h || !B || !X || !its || nrhs < 1) {
-    g_err = "bad argument";
-    return KB200_ERR_INVALID;
-  }
-  const int64_t n = h->n_gamma;
-  for (int64_t k = 0; k < nrhs; ++k) {
-    std::vector<double> res((size_t)((maxit == 0 ? n : maxit) + 1));
-    int rc = kb200_pcg(h, B + k * n, X + k * n, maxit, rtol, assembled, precond, &its[k], res.data(), nullptr);
-    if (rc != KB200_OK) return rc;
-    if (res_norm) std::copy(res.begin(), res.begin() + std::min<int64_t>(its[k], res_stride), res_norm + k * res_stride);
-  }
-  return KB200_OK;
+  // independent recurrences per right-hand side (the reference's sequential loop over right-hand sides,
+  // Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179), run side by side in blocks of up to 64
+  // columns that share the operator launches
+  return guarded([&]() {
+    require(h && B && X && its && nrhs >= 1, "bad argument");
+    require(res_norm == nullptr || res_stride >= 1, "res_stride must be positive when res_norm is given");
+    finalize(h);
+    use_device(h);
+    Ctx* c = h;
+    const int64_t n = c->n_gamma;
+    if (maxit == 0) maxit = n;
+    require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+    const OpKind A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
+    const int64_t kb_ = std::min<int64_t>(nrhs, 64);
+    MultiWork w;
+    for (DevBuf<double>* v : {&w.B, &w.X, &w.R, &w.Z, &w.P, &w.AP}) v->alloc((size_t)(n * kb_));
+    for (DevBuf<double>* v : {&w.partA, &w.partB, &w.partC}) v->alloc((size_t)(c->nb * kb_));
+    w.res.alloc((size_t)((maxit + 1) * kb_));
+    w.st.alloc((size_t)kb_);
+    w.all_done.alloc(1);
+    std::vector<kb::PcgState> st;
+    std::vector<double> res_h;
+    int first_fail = 0;
+    for (int64_t j0 = 0; j0 < nrhs; j0 += kb_) {
+      const int64_t k = std::min(kb_, nrhs - j0);
+      h2d(c, w.B.p, B + j0 * n, n * k);
+      h2d(c, w.X.p, X + j0 * n, n * k);
+      CUDA_TRY(cudaMemsetAsync(w.st.p, 0, (size_t)k * sizeof(kb::PcgState), c->stream));
+      pcg_multi_block(c, w, k, maxit, rtol, A, precond, st);
+      d2h(c, X + j0 * n, w.X.p, n * k);
+      if (res_norm) {
+        res_h.resize((size_t)((maxit + 1) * k));
+        d2h(c, res_h.data(), w.res.p, (maxit + 1) * k);
+      }
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      for (int64_t j = 0; j < k; ++j) {
+        its[j0 + j] = st[j].it;
+        if (st[j].fail && !first_fail) first_fail = st[j].fail;
+        if (res_norm)
+          std::copy(res_h.begin() + j * (maxit + 1), res_h.begin() + j * (maxit + 1) + std::min<int64_t>(st[j].it, res_stride),
+                    res_norm + (j0 + j) * res_stride);
+      }
+    }
+    throw_on_fail(first_fail);
+  });
 }
 
 int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t maxit, double rtol,
@@ -1663,14 +1997,8 @@ int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, in
     h2d(c, c->d_x.p, x, n, &T);
     CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
     // WtA[ivec, :] = A * W[:, ivec] ; WtAW = WtA * W                                  (defcg.jl:261-268)
-    for (int j = 0; j < k; ++j)
-      apply_op(c, A, dW.p + (size_t)j * n, dAW.p + (size_t)j * n, nullptr, nullptr, nullptr, 0, &kt);
-    {
-      dim3 grid((unsigned)((k + 15) / 16), (unsigned)((k + 15) / 16));
-      kb::gemm_tn_kernel<<<grid, 256, 0, c->stream>>>(n, k, k, dAW.p, n, dW.p, n, dM.p);
-      CUDA_TRY(cudaGetLastError());
-      c->launches++;
-    }
+    apply_op_multi(c, A, dW.p, dAW.p, k, MultiCtx(), &kt);
+    gemm_tn(c, k, k, dAW.p, dW.p, dM.p);
     std::vector<double> Mh((size_t)k * k), Minv;
     CUDA_TRY(cudaMemcpyAsync(Mh.data(), dM.p, Mh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1750,11 +2078,12 @@ int kb200_mat_get(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, doubl
 }
 int kb200_op_apply(kb200_handle h, int which, int64_t src, int64_t scol, int64_t dst, int64_t dcol, int64_t ncols) {
   return guarded([&]() {
-    require(h && which >= 0 && which <= 2, "bad operator");
+    require(h && which >= 0 && which <= 2 && ncols >= 1, "bad operator / column count");
     use_device(h);
-    for (int64_t k = 0; k < ncols; ++k)
-      apply_op(h, which == 0 ? OP_SCHUR : which == 1 ? OP_SCHUR_DENSE : OP_NN, mat_col(h, src, scol + k, 1),
-               mat_col(h, dst, dcol + k, 1), nullptr, nullptr, nullptr, 0, nullptr);
+    const double* in = mat_col(h, src, scol, ncols);
+    double* out = mat_col(h, dst, dcol, ncols);
+    require(in + ncols * h->n_gamma <= out || out + ncols * h->n_gamma <= in, "source and destination columns overlap");
+    apply_op_multi(h, which == 0 ? OP_SCHUR : which == 1 ? OP_SCHUR_DENSE : OP_NN, in, out, ncols, MultiCtx(), nullptr);
   });
 }
 int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, int64_t y, int64_t ycol) {
@@ -1802,11 +2131,7 @@ int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t 
     require(h && C_host && ka >= 1 && kb_ >= 1, "bad argument");
     use_device(h);
     if ((int64_t)h->d_small.n < ka * kb_) h->d_small.alloc((size_t)(ka * kb_));
-    dim3 grid((unsigned)((ka + 15) / 16), (unsigned)((kb_ + 15) / 16));
-    kb::gemm_tn_kernel<<<grid, 256, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kb_, mat_col(h, A, ca, ka), h->n_gamma,
-                                                    mat_col(h, B, cb, kb_), h->n_gamma, h->d_small.p);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
+    gemm_tn(h, (int)ka, (int)kb_, mat_col(h, A, ca, ka), mat_col(h, B, cb, kb_), h->d_small.p);
     d2h(h, C_host, h->d_small.p, ka * kb_);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   });
@@ -1817,15 +2142,8 @@ int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const do
     use_device(h);
     if ((int64_t)h->d_small2.n < ka * kq) h->d_small2.alloc((size_t)(ka * kq));
     CUDA_TRY(cudaMemcpyAsync(h->d_small2.p, Q_host, (size_t)(ka * kq) * 8, cudaMemcpyHostToDevice, h->stream));
-    // the result may overlap A (V[:, 1:nev] = V * QZ, eigcg.jl:228): go through a temporary block
-    DevBuf<double> tmp;
-    tmp.alloc((size_t)(h->n_gamma * kq));
-    dim3 grid((unsigned)h->nb, (unsigned)kq);
-    kb::gemm_nn_kernel<<<grid, h->vec_threads, 0, h->stream>>>((int)h->n_gamma, (int)ka, (int)kq, mat_col(h, A, ca, ka), h->n_gamma,
-                                                               h->d_small2.p, tmp.p, h->n_gamma);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    CUDA_TRY(cudaMemcpyAsync(mat_col(h, Cm, cc, kq), tmp.p, (size_t)(h->n_gamma * kq) * 8, cudaMemcpyDeviceToDevice, h->stream));
+    // the result may overlap A (V[:, 1:nev] = V * QZ, eigcg.jl:228)
+    gemm_nn(h, (int)ka, (int)kq, mat_col(h, A, ca, ka), h->d_small2.p, mat_col(h, Cm, cc, kq));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   });
 }
@@ -1897,7 +2215,6 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     I.k0 = 1;
     kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, rTz, tol, (int)it0, (int)maxit);
     c->launches++;
-    const uint32_t seq_before = c->xch_seq;
     run_iterations(c, I, 1, (int)m + 1, nullptr);
     // one synchronisation per burst: state, alpha/beta history, residual norms
     std::vector<double> hh(nh), rr((size_t)m);
@@ -1909,7 +2226,6 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     throw_on_fail(hs.fail);
     const int64_t done = (int64_t)hs.it - it0;
     require(done >= 0 && done <= m, "internal: burst iteration count out of range");
-    realign_exchange_slots(c, seq_before, m, done);
     for (int64_t j = 0; j < done; ++j) {
       alpha_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1)];
       beta_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1) + 1];

@@ -33,7 +33,10 @@ struct StreamParams {
   const int64_t* sd_off;  // per local subdomain offset into sd_pool
   const int* done_at;     // optional: skip when *done_at < iter (solver already converged)
   int iter;
-  int unit_col0;          // MODE_UNIT: column = unit_col0 + blockIdx.y
+  // R right-hand sides per launch (template parameter of the kernel): column j of the interface vector at
+  // x_gamma + j*ldx, of the interior vectors at bI / uI + j*ldi, of the local-interface output at out_loc + j*ldo
+  int64_t ldx, ldi, ldo;
+  int unit_col0;          // MODE_UNIT: columns unit_col0 + R*blockIdx.y + j
   int nstages;            // ring depth (<= kMaxStages)
   long long* dbg;         // optional: 16 clock64 stamps per CTA (development aid)
   int dbg_flags;          // development aid: 1 = skip packet arithmetic, 2 = skip level barriers
@@ -171,7 +174,27 @@ __device__ __forceinline__ void cluster_level_sync(StreamCtx& cx) {
 // row update) weighs as much as the entry loop: everything the header can precompute is precomputed
 // on the host, the row record and the old destination value are fetched before the loop, the loop is
 // kept at 4 steps per trip (no wide unrolling with its set-up code) and the tail is 2 + 1 steps.
-template <bool kTop>
+// R right-hand sides at once (MULTI-VECTOR kernel, the batched SpMM apply of
+// Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179 / eigcg.jl:212-218): the shared vector holds
+// R interleaved values per slot, S[slot * R + j]; a stream entry (value, 16-bit slot) is read ONCE and applied
+// to the R columns, every column with exactly the association order of the single-vector kernel (so column j
+// of a batched apply has the bits of a single apply of that column).
+// the R values of slot c (16-byte vector loads: S is 16-byte aligned and R is 1, 2 or 4)
+template <int R>
+__device__ __forceinline__ void load_slot(const double* S, uint32_t c, double (&v)[R]) {
+  if (R == 1) {
+    v[0] = S[c];
+  } else {
+#pragma unroll
+    for (int h = 0; h < R / 2; ++h) {
+      const double2 t = reinterpret_cast<const double2*>(S)[c * (R / 2) + h];
+      v[2 * h] = t.x;
+      v[2 * h + 1] = t.y;
+    }
+  }
+}
+
+template <bool kTop, int R>
 __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, double sign) {
   double* S = cx.S;
   const int lane = cx.lane;
@@ -183,21 +206,36 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
   const bool writer = lane < W && (lane & ((1 << tl) - 1)) == 0;
   const uint4 q = *reinterpret_cast<const uint4*>(sl + 16 + 16 * g);
   const uint32_t dst = q.x >> 16, flags = q.y & 0xffffu;
-  const double old = (flags & kRowFresh) ? 0.0 : S[dst];
+  double old[R];
+  load_slot<R>(S, dst, old);
+  if (flags & kRowFresh) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) old[j] = 0.0;
+  }
   // entry (k, lane) at k * W + lane; padding entries are (0.0, col 0)
   const double* vp = reinterpret_cast<const double*>(sl + 16 + 16 * nrows) + lane;
   const uint16_t* cp = reinterpret_cast<const uint16_t*>(sl + hq.w) + lane;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  double a0[R], a1[R], a2[R], a3[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) a0[j] = a1[j] = a2[j] = a3[j] = 0.0;
   if (lane < W) {
     int k = kmax;
 #pragma unroll 1
     for (; k >= 4; k -= 4) {
       const double v0 = vp[0], v1 = vp[W], v2 = vp[2 * W], v3 = vp[3 * W];
       const uint32_t c0 = cp[0], c1 = cp[W], c2 = cp[2 * W], c3 = cp[3 * W];
-      a0 = fma(v0, S[c0], a0);
-      a1 = fma(v1, S[c1], a1);
-      a2 = fma(v2, S[c2], a2);
-      a3 = fma(v3, S[c3], a3);
+      double s0[R], s1[R], s2[R], s3[R];
+      load_slot<R>(S, c0, s0);
+      load_slot<R>(S, c1, s1);
+      load_slot<R>(S, c2, s2);
+      load_slot<R>(S, c3, s3);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        a0[j] = fma(v0, s0[j], a0[j]);
+        a1[j] = fma(v1, s1[j], a1[j]);
+        a2[j] = fma(v2, s2[j], a2[j]);
+        a3[j] = fma(v3, s3[j], a3[j]);
+      }
       vp += 4 * W;
       cp += 4 * W;
     }
@@ -205,30 +243,45 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
     if (k & 2) {
       const double v0 = vp[0], v1 = vp[W];
       const uint32_t c0 = cp[0], c1 = cp[W];
-      a0 = fma(v0, S[c0], a0);
-      a1 = fma(v1, S[c1], a1);
+      double s0[R], s1[R];
+      load_slot<R>(S, c0, s0);
+      load_slot<R>(S, c1, s1);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        a0[j] = fma(v0, s0[j], a0[j]);
+        a1[j] = fma(v1, s1[j], a1[j]);
+      }
       vp += 2 * W;
       cp += 2 * W;
     }
     if (k & 1) {
-      const double v0 = vp[0], s0 = S[cp[0]];
-      if (k & 2) a2 = fma(v0, s0, a2);
-      else a0 = fma(v0, s0, a0);
+      const double v0 = vp[0];
+      const uint32_t c0 = cp[0];
+      double s0[R];
+      load_slot<R>(S, c0, s0);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (k & 2) a2[j] = fma(v0, s0[j], a2[j]);
+        else a0[j] = fma(v0, s0[j], a0[j]);
+      }
     }
   }
-  double acc = (a0 + a1) + (a2 + a3);
-  if (tl >= 1) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  if (tl >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (tl >= 3) acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (tl >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-  if (tl >= 5) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  if (writer) {
-    const double dg = __hiloint2double((int)q.w, (int)q.z);  // 1 / diag
-    const double r = (old - sign * acc) * dg;
-    S[dst] = r;
-    if (kTop && (flags & kRowBcast)) {
-      for (int cc = 0; cc < cx.D->csize; ++cc)
-        if (cc != cx.D->rank) cx.cluster->map_shared_rank(S, cc)[dst] = r;
+  const double dg = __hiloint2double((int)q.w, (int)q.z);  // 1 / diag
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    double acc = (a0[j] + a1[j]) + (a2[j] + a3[j]);
+    if (tl >= 1) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (tl >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (tl >= 3) acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (tl >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    if (tl >= 5) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (writer) {
+      const double r = (old[j] - sign * acc) * dg;
+      S[dst * R + j] = r;
+      if (kTop && (flags & kRowBcast)) {
+        for (int cc = 0; cc < cx.D->csize; ++cc)
+          if (cc != cx.D->rank) cx.cluster->map_shared_rank(S, cc)[dst * R + j] = r;
+      }
     }
   }
 }
@@ -237,7 +290,7 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
 // only its own token list of every chunk: a token is a slice to process or the end of a level
 // (CTA barrier; TOP sections (kTop): barrier over the whole cluster, the rows of a level having been
 // shared out over the CTAs and their results stored into every CTA's replica of the top vector).
-template <bool kTop, int NW>
+template <bool kTop, int NW, int R>
 __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
   const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec];
   const int lane = cx.lane, warp = cx.warp;
@@ -265,7 +318,7 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
         if (cx.dbg_flags & 1) continue;
 #endif
         KB_PROF(const long long ts0 = clock64();)
-        process_slice<kTop>(cx, chunk + t * 16u, sign);
+        process_slice<kTop, R>(cx, chunk + t * 16u, sign);
         __syncwarp();  // the warp's next slice may read these rows (warp-private subtrees)
         KB_PROF(cx.t_slice += clock64() - ts0; cx.n_slice++;)
       }
@@ -279,8 +332,8 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
   }
 }
 
-template <int MODE, int NW>
-__global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schur_stream_kernel(const StreamParams P) {
+template <int MODE, int NW, int R>
+__global__ void __launch_bounds__(stream_threads(NW), (NW == kWarps && R == 1) ? 2 : 1) schur_stream_kernel(const StreamParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ CtaDesc D;
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -289,7 +342,7 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
   pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   double* scratch = reinterpret_cast<double*>(smem_raw + (size_t)P.nstages * kChunkBytes);
-  double* S = scratch + kMaxSlots;
+  double* S = scratch + kMaxSlots * R;   // slot i of column j at S[i * R + j]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.ctas + blockIdx.x);
@@ -305,7 +358,7 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
     mbar_fence_init();
   }
   __syncthreads();
-  for (int i = tid; i < D.smem_doubles; i += blockDim.x) S[i] = 0.0;
+  for (int i = tid; i < D.smem_doubles * R; i += blockDim.x) S[i] = 0.0;
   // everything above touches only static data and this CTA's shared memory: with PDL it overlaps the
   // tail of the previous kernel; from here on the kernel reads what its predecessors wrote
   pdl_wait();
@@ -315,19 +368,31 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
   // ---- inputs ---------------------------------------------------------------------------------
   if (MODE == MODE_APPLY || MODE == MODE_BACKSUB) {
     const int32_t* l2g = P.l2g + D.l2g_off;
-    for (int l = tid; l < D.n_gd; l += blockDim.x) S[D.xd_off + l] = P.x_gamma[l2g[l]];
+    for (int l = tid; l < D.n_gd; l += blockDim.x) {
+      const int32_t g = l2g[l];
+#pragma unroll
+      for (int j = 0; j < R; ++j) S[(D.xd_off + l) * R + j] = P.x_gamma[g + j * P.ldx];
+    }
   }
   if (MODE == MODE_UNIT) {
-    const int col = P.unit_col0 + (int)blockIdx.y;
-    if (tid == 0 && col < D.n_gd) S[D.xd_off + col] = 1.0;
+    const int col0 = P.unit_col0 + (int)blockIdx.y * R;
+    if (tid < R && col0 + tid < D.n_gd) S[(D.xd_off + col0 + tid) * R + tid] = 1.0;
   }
   if (MODE == MODE_RHS || MODE == MODE_BACKSUB) {
     const double* b = P.bI + D.I_base;
     const int32_t* om = P.imap + D.ownmap_off;
-    for (int k = tid; k < D.n_own; k += blockDim.x) S[D.own_off + k] = b[om[k]];
+    for (int k = tid; k < D.n_own; k += blockDim.x) {
+      const int32_t o = om[k];
+#pragma unroll
+      for (int j = 0; j < R; ++j) S[(D.own_off + k) * R + j] = b[o + j * P.ldi];
+    }
     if (rank == 0) {
       const int32_t* tm = P.imap + D.topmap_off;
-      for (int k = tid; k < D.n_top; k += blockDim.x) S[D.top_off + k] = b[tm[k]];
+      for (int k = tid; k < D.n_top; k += blockDim.x) {
+        const int32_t o = tm[k];
+#pragma unroll
+        for (int j = 0; j < R; ++j) S[(D.top_off + k) * R + j] = b[o + j * P.ldi];
+      }
     }
   }
   __syncthreads();
@@ -364,11 +429,11 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
     produce_section(cx, SEC_FWD);
     if (C > 1) produce_section(cx, SEC_PART);
   } else {
-    if (kHasInit) consume_section<false, NW>(cx, SEC_INIT, kInitSign);
+    if (kHasInit) consume_section<false, NW, R>(cx, SEC_INIT, kInitSign);
     stamp(9);
-    consume_section<false, NW>(cx, SEC_FWD, 1.0);
+    consume_section<false, NW, R>(cx, SEC_FWD, 1.0);
     stamp(10);
-    if (C > 1) consume_section<false, NW>(cx, SEC_PART, 1.0);
+    if (C > 1) consume_section<false, NW, R>(cx, SEC_PART, 1.0);
   }
   stamp(1);
   // ---- phase 2: top nodes, shared out over the cluster ----------------------------------------------
@@ -383,22 +448,24 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
       // the partial products of all CTAs, first into the scratch, and only overwrites its replica of
       // the top vector once all CTAs have finished reading (two cluster-wide barriers per pass)
       const double* r0 = cluster.map_shared_rank(S, 0);
-      for (int base = 0; base < D.n_top; base += kMaxSlots) {
-        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += NW * 32) {
-          double a = r0[D.top_off + i];
+      const int ntopR = D.n_top * R;                 // (node, column) pairs, interleaved like S
+      const int topR = D.top_off * R, partR = D.part_off * R;
+      for (int base = 0; base < ntopR; base += kMaxSlots * R) {
+        for (int i = base + tid; i < ntopR && i < base + kMaxSlots * R; i += NW * 32) {
+          double a = r0[topR + i];
           for (int c = 0; c < C; ++c) {
             const double* rs = cluster.map_shared_rank(S, c);
-            a += rs[D.part_off + i];
+            a += rs[partR + i];
           }
           scratch[i - base] = a;
         }
         cluster_level_sync<NW>(cx);
-        for (int i = base + tid; i < D.n_top && i < base + kMaxSlots; i += NW * 32) S[D.top_off + i] = scratch[i - base];
+        for (int i = base + tid; i < ntopR && i < base + kMaxSlots * R; i += NW * 32) S[topR + i] = scratch[i - base];
         cluster_level_sync<NW>(cx);
       }
-      consume_section<true, NW>(cx, SEC_TOPF, 1.0);
+      consume_section<true, NW, R>(cx, SEC_TOPF, 1.0);
       stamp(3);
-      consume_section<true, NW>(cx, SEC_TOPB, 1.0);
+      consume_section<true, NW, R>(cx, SEC_TOPB, 1.0);
     }
     stamp(4);
     stamp(5);
@@ -409,10 +476,10 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
     if (kHasGG && rank == 0) produce_section(cx, SEC_GG);
     if (kHasOut) produce_section(cx, SEC_OUT);
   } else {
-    consume_section<false, NW>(cx, SEC_BWD, 1.0);
+    consume_section<false, NW, R>(cx, SEC_BWD, 1.0);
     stamp(6);
-    if (kHasGG && rank == 0) consume_section<false, NW>(cx, SEC_GG, -1.0);
-    if (kHasOut) consume_section<false, NW>(cx, SEC_OUT, 1.0);
+    if (kHasGG && rank == 0) consume_section<false, NW, R>(cx, SEC_GG, -1.0);
+    if (kHasOut) consume_section<false, NW, R>(cx, SEC_OUT, 1.0);
   }
   __syncthreads();
   stamp(7);
@@ -423,32 +490,40 @@ __global__ void __launch_bounds__(stream_threads(NW), NW == kWarps ? 2 : 1) schu
   if (MODE == MODE_BACKSUB) {
     double* u = P.uI + D.I_base;
     const int32_t* om = P.imap + D.ownmap_off;
-    for (int k = tid; k < D.n_own; k += blockDim.x) u[om[k]] = S[D.own_off + k];
+    for (int k = tid; k < D.n_own; k += blockDim.x) {
+      const int32_t o = om[k];
+#pragma unroll
+      for (int j = 0; j < R; ++j) u[o + j * P.ldi] = S[(D.own_off + k) * R + j];
+    }
     if (rank == 0) {
       const int32_t* tm = P.imap + D.topmap_off;
-      for (int k = tid; k < D.n_top; k += blockDim.x) u[tm[k]] = S[D.top_off + k];
+      for (int k = tid; k < D.n_top; k += blockDim.x) {
+        const int32_t o = tm[k];
+#pragma unroll
+        for (int j = 0; j < R; ++j) u[o + j * P.ldi] = S[(D.top_off + k) * R + j];
+      }
     }
     if (C > 1) cluster.sync();  // nobody leaves while rank 0's top values may still be read
     return;
   }
   if (C > 1) cluster.sync();
   if (rank == 0) {
-    double* o;
-    if (MODE == MODE_UNIT) {
-      const int col = P.unit_col0 + (int)blockIdx.y;
-      o = (col < D.n_gd) ? P.sd_pool + P.sd_off[D.dom] + (int64_t)col * D.n_gd : nullptr;
-    } else {
-      o = P.out_loc + D.G_base;
-    }
-    if (o != nullptr)
-      for (int l = tid; l < D.n_gd; l += blockDim.x) {
-        double a = S[D.out_off + l];
+    const int col0 = P.unit_col0 + (int)blockIdx.y * R;
+    for (int l = tid; l < D.n_gd; l += blockDim.x) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        double a = S[(D.out_off + l) * R + j];
         for (int c = 1; c < C; ++c) {
           const double* rs = cluster.map_shared_rank(S, c);
-          a += rs[D.out_off + l];
+          a += rs[(D.out_off + l) * R + j];
         }
-        o[l] = a;
+        if (MODE == MODE_UNIT) {
+          if (col0 + j < D.n_gd) P.sd_pool[P.sd_off[D.dom] + (int64_t)(col0 + j) * D.n_gd + l] = a;
+        } else {
+          P.out_loc[D.G_base + l + j * P.ldo] = a;
+        }
       }
+    }
   }
   if (C > 1) cluster.sync();
   stamp(8);
@@ -602,9 +677,13 @@ assemble_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const dou
 // so the PCG scalars and iteration counts do not depend on the GPU count.
 // The first ceil(m_r / blockDim) blocks of rank r compute and push its m_r entries and publish one flag
 // each (release, system scope) at every peer; every block then waits for all flags of all ranks and
-// gathers its nodes.  No separate collective launch.  Two data slots alternate (a rank can run at most
-// one exchange ahead of a peer: it cannot finish exchange k+1 before that peer has pushed k+1, i.e. has
-// left the kernel of exchange k).
+// gathers its nodes.  No separate collective launch.  Two data slots alternate between consecutive REAL
+// exchanges (a rank can run at most one exchange ahead of a peer: it cannot finish exchange k+1 before
+// that peer has pushed k+1, i.e. has left the kernel of exchange k).  Launches that the device skips after
+// convergence must not advance the slot: the number of real exchanges is carried ON THE DEVICE in a
+// two-word ping-pong counter -- launch L (host-side launch index, skipped ones included) reads
+// cnt[L & 1] and writes cnt[(L + 1) & 1] (+1 if it really exchanged), so no block of a launch ever reads
+// a word that the same launch writes.  Identical launch sequences on all ranks => identical counters.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct XchParams {
@@ -615,8 +694,9 @@ struct XchParams {
   const int32_t* snd_g;        // interface node whose `base` value the entry starts from, or -1
   const int32_t* fin_ptr;      // per interface node: entries of the gathered array to sum, in order
   const int32_t* fin_src;
-  int world, rank, slot;
-  uint32_t seq;                // sequence number of this exchange (monotone, identical on all ranks)
+  int world, rank;
+  uint32_t* cnt;               // ping-pong counter of REAL exchanges (see above); seq = cnt[par] + 1, slot = seq & 1
+  int par;                     // launch index & 1
   int m_pad;                   // entries per slot
   int snd_off, snd_n;          // position / number of this rank's entries in the gathered array
   int flag_off, nflags;        // this rank's first flag / flags of all ranks
@@ -634,26 +714,34 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 // Exchange step of one block (all threads must call): returns the assembled value of interface node g
 // (contributions of ALL subdomains, reference order); see above.
+// a launch that does not exchange (skipped after convergence) hands the counter on unchanged
+__device__ __forceinline__ void exchange_skip(const XchParams& X) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) X.cnt[X.par ^ 1] = __ldcg(X.cnt + X.par);
+}
+
 __device__ __forceinline__ double exchange_gather(int g, int n, const double* loc, const double* base, const XchParams& X) {
   const int T = blockDim.x;
+  const uint32_t seq = __ldcg(X.cnt + X.par) + 1u;
+  const int slot = (int)(seq & 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) X.cnt[X.par ^ 1] = seq;
   if ((int)blockIdx.x * T < X.snd_n) {  // block-uniform: this block pushes entries
     const int e = blockIdx.x * T + threadIdx.x;
     if (e < X.snd_n) {
       const int gb = X.snd_g[e];
       double a = (base != nullptr && gb >= 0) ? base[gb] : 0.0;
       for (int k = X.snd_ptr[e]; k < X.snd_ptr[e + 1]; ++k) a += loc[X.snd_src[k]];
-      const size_t at = (size_t)X.slot * (size_t)X.m_pad + (size_t)(X.snd_off + e);
+      const size_t at = (size_t)slot * (size_t)X.m_pad + (size_t)(X.snd_off + e);
       for (int r = 0; r < X.world; ++r) __stcg(X.data[r] + at, a);
     }
     __syncthreads();
     // release at system scope: the block's stores to the peers (ordered before this thread by the
     // barrier above) are visible to whoever acquires the flag
-    if ((int)threadIdx.x < X.world) st_release_sys(X.flags[threadIdx.x] + X.flag_off + blockIdx.x, X.seq);
+    if ((int)threadIdx.x < X.world) st_release_sys(X.flags[threadIdx.x] + X.flag_off + blockIdx.x, seq);
   }
   for (int f = threadIdx.x; f < X.nflags; f += T) {
     const uint32_t* fp = X.flags[X.rank] + f;
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(fp) - X.seq) < 0) {
+    while ((int32_t)(ld_acquire_sys(fp) - seq) < 0) {
       if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer never arrived
         if (X.fail != nullptr) *X.fail = 2;
         break;
@@ -663,7 +751,7 @@ __device__ __forceinline__ double exchange_gather(int g, int n, const double* lo
   __syncthreads();
   double sum = 0.0;
   if (g < n) {
-    const double* G = X.data[X.rank] + (size_t)X.slot * (size_t)X.m_pad;
+    const double* G = X.data[X.rank] + (size_t)slot * (size_t)X.m_pad;
     for (int k = X.fin_ptr[g]; k < X.fin_ptr[g + 1]; ++k) sum += __ldcg(G + X.fin_src[k]);
   }
   return sum;
@@ -684,7 +772,10 @@ __global__ void __launch_bounds__(kVecThreads)
 assemble_exchange_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, const double* base,
                          double* y, const double* q, double* part, const int* done_at, int iter, const XchParams X) {
   __shared__ double red[kVecThreads / 32];
-  if (done_at != nullptr && *done_at < iter) return;
+  if (done_at != nullptr && *done_at < iter) {
+    exchange_skip(X);
+    return;
+  }
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const double sum = exchange_gather(g, n, loc, base, X);
   double prod = 0.0;
@@ -897,6 +988,7 @@ pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const
   pdl_wait();
   if (st->done_at < iter) {
     grid_skip(counter);
+    if (kX) exchange_skip(X);
     return;
   }
   const int nb = gridDim.x;
@@ -943,6 +1035,7 @@ pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const 
   pdl_wait();
   if (st->done_at < iter) {
     grid_skip(counter);
+    if (kX) exchange_skip(X);
     return;
   }
   const int nb = gridDim.x;
@@ -1097,6 +1190,363 @@ __global__ void __launch_bounds__(kVecThreads) gemm_nn_kernel(int n, int ka, int
   }
   if (kk < ka) s0 = fma(A[g + (int64_t)kk * lda], __ldg(q + kk), s0);
   Cm[g + (int64_t)j * ldc] = s0 + s1;
+}
+
+}  // namespace kb
+
+// =============================================================================================
+// FP64 tensor-core (DMMA) kernels: the dense contractions of the path -- batched dense local products
+// with several right-hand sides (assembled S_d X_d, EllipticPdeDomainDecomposition.jl:761-785, and
+// Pi S_d (D R)_d, :1361-1386, for the multiple-right-hand-side solves of
+// Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179) and the tall-skinny products with
+// the recycling bases (V'AV eigcg.jl:219, V (Q Z) eigcg.jl:228 / defcg.jl:432, W'A W defcg.jl:268).
+// mma.sync.m8n8k4.f64: A 8x4 (lane l: row l/4, col l%4), B 4x8 (lane l: row l%4, col l/4),
+// C 8x8 (lane l: row l/4, cols 2(l%4), 2(l%4)+1).  Fixed summation order: bit-reproducible.
+// =============================================================================================
+namespace kb {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- batched dense local products with k right-hand sides -------------------------------------
+// out_loc[G_base_d + i + j ldo] = w_i sum_m M_d[i, m] (w_m x[l2g_d[m] + j ldx]),  j < k
+// grid = (row tiles of 64, subdomains); 8 warps, warp w owns rows 8w..8w+7 of the tile and all KP columns
+struct GemmParams {
+  const double* mats;       // row-major n_gd x n_gd blocks (symmetric)
+  const int64_t* mat_off;
+  const int32_t* n_gd;
+  const int64_t* G_base;
+  const int32_t* l2g;
+  const double* x;          // n_gamma x k, column-major
+  int64_t ldx;
+  const double* inv_cnt;    // 1/node_gamma_cnt or nullptr
+  double* out_loc;          // (sum n_gd) x k, column-major
+  int64_t ldo;
+  int k;                    // right-hand sides (<= KP)
+  const int* done_at;
+  int iter;
+};
+constexpr int kGemmBM = 64, kGemmBK = 32;
+
+template <int KP>
+__global__ void __launch_bounds__(256) dense_gemm_kernel(const GemmParams P) {
+  __shared__ double As[kGemmBM][kGemmBK + 4];
+  __shared__ double Xs[kGemmBK][KP + 4];
+  if (P.done_at != nullptr && *P.done_at < P.iter) return;
+  const int d = blockIdx.y;
+  const int n = P.n_gd[d];
+  const int row0 = blockIdx.x * kGemmBM;
+  if (row0 >= n) return;
+  const int64_t gb = P.G_base[d];
+  const int32_t* l2g = P.l2g + gb;
+  const double* M = P.mats + P.mat_off[d];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NF = KP / 8;
+  double c[NF][2];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) c[f][0] = c[f][1] = 0.0;
+  for (int kc = 0; kc < n; kc += kGemmBK) {
+    for (int e = tid; e < kGemmBM * kGemmBK; e += 256) {
+      const int r = e / kGemmBK, cc = e % kGemmBK;
+      const int i = row0 + r, m = kc + cc;
+      As[r][cc] = (i < n && m < n) ? __ldg(M + (int64_t)i * n + m) : 0.0;
+    }
+    for (int e = tid; e < kGemmBK * KP; e += 256) {
+      const int kk = e % kGemmBK, j = e / kGemmBK;
+      const int m = kc + kk;
+      double v = 0.0;
+      if (m < n && j < P.k) {
+        const int g = l2g[m];
+        v = P.x[g + (int64_t)j * P.ldx];
+        if (P.inv_cnt != nullptr) v *= P.inv_cnt[g];
+      }
+      Xs[kk][j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < kGemmBK / 4; ++k4) {
+      const double a = As[warp * 8 + (lane >> 2)][k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const double b = Xs[k4 * 4 + (lane & 3)][f * 8 + (lane >> 2)];
+        dmma884(c[f][0], c[f][1], a, b);
+      }
+    }
+    __syncthreads();
+  }
+  const int i = row0 + warp * 8 + (lane >> 2);
+  if (i < n) {
+    const double w = (P.inv_cnt != nullptr) ? P.inv_cnt[l2g[i]] : 1.0;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int j = f * 8 + 2 * (lane & 3);
+      if (j < P.k) P.out_loc[gb + i + (int64_t)j * P.ldo] = c[f][0] * w;
+      if (j + 1 < P.k) P.out_loc[gb + i + (int64_t)(j + 1) * P.ldo] = c[f][1] * w;
+    }
+  }
+}
+
+// ---- C = A' B, tall-skinny (n rows, ka x kb result), split over row ranges ------------------------
+// CTA tile 64 x 128 of C (8 warps as 2 x 4, 32 x 32 each), rows [r0, r1) of this split; operands straight
+// from global memory (a fragment is 4 consecutive rows of 8 columns: full 32-byte sectors).  Partial tiles go
+// to `part` [nsplit][ka * kb]; gemm_tn_reduce_kernel sums the splits in order.
+constexpr int kTnTM = 64, kTnTN = 128;
+__global__ void __launch_bounds__(256) gemm_tn_dmma_kernel(int n, int ka, int kb, const double* A, int64_t lda, const double* B,
+                                                           int64_t ldb, double* part, int rows_per_split) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * kTnTM + (warp >> 2) * 32, j0 = blockIdx.y * kTnTN + (warp & 3) * 32;
+  const int r0 = blockIdx.z * rows_per_split, r1 = min(n, r0 + rows_per_split);
+  double c[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) c[mi][ni][0] = c[mi][ni][1] = 0.0;
+  // column pointers of this lane's fragments (columns clamped into range; out-of-range results are dropped)
+  const double* ap[4];
+  const double* bp[4];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) ap[mi] = A + (int64_t)min(i0 + mi * 8 + (lane >> 2), ka - 1) * lda + (lane & 3);
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) bp[ni] = B + (int64_t)min(j0 + ni * 8 + (lane >> 2), kb - 1) * ldb + (lane & 3);
+  if (i0 < ka && j0 < kb) {
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = __ldg(ap[mi] + r);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = __ldg(bp[ni] + r);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(c[mi][ni][0], c[mi][ni][1], a[mi], b[ni]);
+    }
+    if (r < r1) {  // tail rows: lanes beyond the range feed zeros
+      const bool ok = r + (lane & 3) < r1;
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = ok ? __ldg(ap[mi] + r) : 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = ok ? __ldg(bp[ni] + r) : 0.0;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(c[mi][ni][0], c[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  double* out = part + (int64_t)blockIdx.z * ka * kb;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int i = i0 + mi * 8 + (lane >> 2), j = j0 + ni * 8 + 2 * (lane & 3);
+      if (i < ka && j < kb) out[i + (int64_t)j * ka] = c[mi][ni][0];
+      if (i < ka && j + 1 < kb) out[i + (int64_t)(j + 1) * ka] = c[mi][ni][1];
+    }
+}
+__global__ void __launch_bounds__(256) gemm_tn_reduce_kernel(int64_t nel, int nsplit, const double* part, double* C) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  double s = 0.0;
+  for (int z = 0; z < nsplit; ++z) s += part[(int64_t)z * nel + e];
+  C[e] = s;
+}
+
+// ---- C[:, 0:kq] = A[:, 0:ka] Q, C may alias A (V[:, 1:nev] = V (Q Z), eigcg.jl:228) -----------------
+// One CTA per panel of 32 rows: the panel of A is staged ONCE in shared memory (A is read exactly once from
+// HBM, and may be overwritten by C afterwards), then 64 output columns at a time: warp w owns 8 columns and
+// the 4 row fragments.  Q (ka x kq, column-major) comes from global memory (L2-resident).  ka <= kNnMaxK.
+constexpr int kNnRows = 32, kNnLd = 36, kNnMaxK = 784;
+__global__ void __launch_bounds__(256) gemm_nn_dmma_kernel(int n, int ka, int kq, const double* A, int64_t lda, const double* Q,
+                                                           double* Cm, int64_t ldc) {
+  extern __shared__ __align__(16) double Ap[];  // [ka][kNnLd]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kNnRows;
+  const int kap = (ka + 3) & ~3;
+  for (int e = threadIdx.x; e < kap * kNnRows; e += 256) {
+    const int kk = e / kNnRows, i = e % kNnRows;
+    Ap[kk * kNnLd + i] = (kk < ka && r0 + i < n) ? A[r0 + i + (int64_t)kk * lda] : 0.0;
+  }
+  __syncthreads();
+  for (int jb = 0; jb < kq; jb += 64) {
+    const int j = jb + warp * 8 + (lane >> 2);          // column of this lane's B fragment
+    const double* qp = Q + (int64_t)min(j, kq - 1) * ka;
+    double c[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) c[mi][0] = c[mi][1] = 0.0;
+    if (jb + warp * 8 < kq) {
+      for (int k0 = 0; k0 < kap; k0 += 4) {
+        const int kk = k0 + (lane & 3);
+        const double b = (kk < ka && j < kq) ? __ldg(qp + kk) : 0.0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) dmma884(c[mi][0], c[mi][1], Ap[kk * kNnLd + mi * 8 + (lane >> 2)], b);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int i = r0 + mi * 8 + (lane >> 2), jc = jb + warp * 8 + 2 * (lane & 3);
+        if (i < n && jc < kq) Cm[i + (int64_t)jc * ldc] = c[mi][0];
+        if (i < n && jc + 1 < kq) Cm[i + (int64_t)(jc + 1) * ldc] = c[mi][1];
+      }
+    }
+  }
+}
+
+}  // namespace kb
+
+// =============================================================================================
+// Independent PCG recurrences for a block of right-hand sides (kb200_pcg_multi): column j of every vector at
+// + j * ld, its scalars in st[j], its block partials at part + j * nb.  grid = (nb, columns).  The operator
+// launches are shared by the columns (multi-vector stream kernel / DMMA dense products), the recurrences are
+// NOT coupled (no block-CG): every column iterates exactly like the reference's sequential loop over
+// right-hand sides (Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179, cg.jl:67-109) and stops
+// on its own; a converged column is frozen.  Same per-column arithmetic as the single-vector kernels above.
+// =============================================================================================
+namespace kb {
+
+__global__ void __launch_bounds__(kVecThreads)
+assemble_multi_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const double* loc, int64_t ldl, double* y,
+                      const double* q, int64_t ld, double* part, const PcgState* st, int iter) {
+  __shared__ double red[kVecThreads / 32];
+  const int j = blockIdx.y;
+  if (st != nullptr && st[j].done_at < iter) return;
+  loc += (int64_t)j * ldl;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double prod = 0.0;
+  if (g < n) {
+    double a = 0.0;
+    for (int k = adj_ptr[g]; k < adj_ptr[g + 1]; ++k) a += loc[adj_src[k]];
+    y[g + (int64_t)j * ld] = a;
+    if (q != nullptr) prod = a * q[g + (int64_t)j * ld];
+  }
+  if (part != nullptr) {
+    const double s = block_reduce_sum(prod, red);
+    if (threadIdx.x == 0) part[(int64_t)j * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+pcg_init_residual_multi_kernel(int n, const double* b, const double* Ax, double* r, int64_t ld, double* partA, double* partB) {
+  __shared__ double red[kVecThreads / 32];
+  const int64_t o = (int64_t)blockIdx.y * ld;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double rr = 0.0, bb = 0.0;
+  if (g < n) {
+    const double rv = b[o + g] - Ax[o + g];
+    r[o + g] = rv;
+    rr = rv * rv;
+    bb = b[o + g] * b[o + g];
+  }
+  const double s1 = block_reduce_sum(rr, red);
+  const double s2 = block_reduce_sum(bb, red);
+  if (threadIdx.x == 0) {
+    partA[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = s1;
+    partB[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = s2;
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+pcg_init_direction_multi_kernel(int n, const double* z, double* p, int64_t ld, const double* partA, const double* partB,
+                                const double* partC, PcgState* st, double* res_norm, int64_t res_stride, double rtol, int maxit) {
+  __shared__ double red[kVecThreads / 32];
+  const int j = blockIdx.y, nb = gridDim.x;
+  const int64_t o = (int64_t)j * ld;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[o + g] = z[o + g];
+  if (blockIdx.x == 0) {
+    const double rTr = sum_partials(partA + (int64_t)j * nb, nb, red);
+    const double bb = sum_partials(partB + (int64_t)j * nb, nb, red);
+    const double rTz = sum_partials(partC + (int64_t)j * nb, nb, red);
+    if (threadIdx.x == 0) {
+      PcgState& s = st[j];
+      s.rTr = rTr;
+      s.rTz = rTz;
+      s.bnorm = sqrt(bb);
+      s.tol = rtol * sqrt(bb);
+      s.it = 1;
+      s.maxit = maxit;
+      s.fail = 0;
+      res_norm[(int64_t)j * res_stride] = sqrt(rTr);
+      s.done_at = ((1 < maxit) && (sqrt(rTr) > s.tol)) ? 0x7fffffff : 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+pcg_update_xr_multi_kernel(int n, const double* p, const double* Ap, double* x, double* r, int64_t ld, const double* partA,
+                           double* partB, PcgState* st, int iter) {
+  __shared__ double red[kVecThreads / 32];
+  const int j = blockIdx.y, nb = gridDim.x;
+  if (st[j].done_at < iter) return;
+  const int64_t o = (int64_t)j * ld;
+  const double d = sum_partials(partA + (int64_t)j * nb, nb, red);
+  const double rTz = st[j].rTz;
+  const double alpha = rTz / d;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double rr = 0.0;
+  if (g < n) {
+    x[o + g] = fma(alpha, p[o + g], x[o + g]);
+    const double rv = fma(-alpha, Ap[o + g], r[o + g]);
+    r[o + g] = rv;
+    rr = rv * rv;
+  }
+  const double s = block_reduce_sum(rr, red);
+  if (threadIdx.x == 0) {
+    partB[(int64_t)j * nb + blockIdx.x] = s;
+    if (blockIdx.x == 0) {
+      st[j].d = d;
+      st[j].alpha = alpha;
+      st[j].rTz_old = rTz;
+      if (!(d > 0.0)) st[j].fail = 1;
+    }
+  }
+}
+
+// (rTz_old is written by block 0 of the xr kernel of the same iteration, a previous launch)
+__global__ void __launch_bounds__(kVecThreads)
+pcg_update_p_multi_kernel(int n, const double* z, double* p, int64_t ld, const double* partB, const double* partC, PcgState* st,
+                          double* res_norm, int64_t res_stride, int iter) {
+  __shared__ double red[kVecThreads / 32];
+  const int j = blockIdx.y, nb = gridDim.x;
+  if (st[j].done_at < iter) return;
+  const int64_t o = (int64_t)j * ld;
+  const double rTr = sum_partials(partB + (int64_t)j * nb, nb, red);
+  const double rTz_new = sum_partials(partC + (int64_t)j * nb, nb, red);
+  double beta = 1.0 / st[j].rTz_old;
+  beta *= rTz_new;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[o + g] = fma(beta, p[o + g], z[o + g]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int it = st[j].it + 1;
+    st[j].it = it;
+    st[j].rTr = rTr;
+    st[j].rTz = rTz_new;
+    st[j].beta = beta;
+    res_norm[(int64_t)j * res_stride + it - 1] = sqrt(rTr);
+    if (!((it < st[j].maxit) && (sqrt(rTr) > st[j].tol))) st[j].done_at = iter;
+  }
+}
+
+// min over the columns' done_at (INT_MAX while any column still runs) -> *all_done_at: lets the shared operator
+// launches of later iterations exit early once every column has converged
+__global__ void pcg_multi_all_done_kernel(int k, const PcgState* st, int* all_done_at) {
+  int v = 0;
+  for (int j = 0; j < k; ++j) v = max(v, st[j].done_at);
+  *all_done_at = v;
+}
+
+// upper triangle -> lower triangle of every dense S_d (Symmetric(), EllipticPdeDomainDecomposition.jl:692);
+// grid = (tiles, subdomains)
+__global__ void __launch_bounds__(256) symmetrize_kernel(double* sd_pool, const int64_t* mat_off, const int32_t* n_gd) {
+  const int d = blockIdx.y;
+  const int64_t n = n_gd[d];
+  double* M = sd_pool + mat_off[d];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e % n, j = e / n;       // column-major (i, j)
+    if (i > j) M[i + j * n] = M[j + i * n];
+  }
 }
 
 }  // namespace kb

@@ -30,6 +30,10 @@ def _L():
         lib.ko_free.argtypes = [C.c_void_p]
         lib.ko_apply_schur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ko_apply_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.ko_set_reverse.argtypes = [C.c_void_p, C.c_int]
+        lib.ko_set_pis.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.ko_assemble_local_schurs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.ko_schur_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ko_pcg.restype = C.c_int32
         lib.ko_pcg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int, C.c_int]
         _lib = lib
@@ -59,6 +63,35 @@ class CpuModel:
             lib.ko_set_dom(self.m, d, G.shape[0], G.shape[1], *[a.ctypes.data for a in arrs],
                            pis.ctypes.data if pis is not None else None)
         lib.ko_finish(self.m)
+
+        self.n_gd = [int(g.size) for g in sd.gamma_l2g]
+        self.n_I = [int(blocks.A_IG[d].shape[0]) for d in range(sd.ndom)]
+
+    def set_reverse_order(self, flag):
+        """Rounding-floor probe: interface sums in descending subdomain order (same mathematics)."""
+        _L().ko_set_reverse(self.m, int(bool(flag)))
+
+    def set_pinv(self, PiSd):
+        """NeumannNeumannSchurPreconditioner blocks from another (e.g. the median) realization."""
+        for d, P in enumerate(PiSd):
+            P = np.asfortranarray(P, dtype=np.float64)
+            _L().ko_set_pis(self.m, d, P.ctypes.data)
+
+    def assemble_local_schurs(self, nthreads=1):
+        """assemble_local_schurs (:667-695): list of dense symmetric S_d."""
+        off = np.concatenate([[0], np.cumsum([n * n for n in self.n_gd])]).astype(np.int64)
+        buf = np.empty(int(off[-1]))
+        _L().ko_assemble_local_schurs(self.m, buf.ctypes.data, off.ctypes.data, nthreads)
+        return [buf[off[d]:off[d + 1]].reshape(self.n_gd[d], self.n_gd[d], order="F") for d in range(len(self.n_gd))]
+
+    def schur_rhs(self, b_I, b_G, nthreads=1):
+        """get_schur_rhs (:835-864)."""
+        off = np.concatenate([[0], np.cumsum(self.n_I)]).astype(np.int64)
+        cat = _f64(np.concatenate(b_I)) if len(b_I) else np.zeros(0)
+        bG = _f64(b_G)
+        out = np.empty(self.n)
+        _L().ko_schur_rhs(self.m, cat.ctypes.data, off.ctypes.data, bG.ctypes.data, out.ctypes.data, nthreads)
+        return out
 
     def apply_schur(self, x, nthreads=1):
         x = _f64(x); y = np.empty(self.n)

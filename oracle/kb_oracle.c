@@ -37,6 +37,7 @@ typedef struct {
   int32_t *cnt;
   ko_dom *dom;
   double *loc; int64_t *gbase;        /* per-subdomain local results */
+  int reverse;                        /* 1: interface sums in DESCENDING subdomain order (rounding-floor probe) */
 } ko_model;
 
 static void *dup_mem(const void *src, size_t bytes) {
@@ -139,7 +140,8 @@ void ko_apply_schur(ko_model *m, const double *x, double *Sx, int nthreads) {
     local_schur(D, xd, m->loc + m->gbase[d]);
   }
   memset(Sx, 0, 8 * (size_t)m->n_gamma);
-  for (int32_t d = 0; d < m->ndom; ++d) {                          /* :740-742, ascending d */
+  for (int32_t dd = 0; dd < m->ndom; ++dd) {                       /* :740-742, ascending d */
+    const int32_t d = m->reverse ? m->ndom - 1 - dd : dd;
     const ko_dom *D = &m->dom[d];
     const double *o = m->loc + m->gbase[d];
     for (int32_t l = 0; l < D->nG; ++l) Sx[D->l2g[l]] += o[l];
@@ -161,10 +163,118 @@ void ko_apply_nn(ko_model *m, const double *r, double *z, int nthreads) {
     }
   }
   memset(z, 0, 8 * (size_t)m->n_gamma);
-  for (int32_t d = 0; d < m->ndom; ++d) {                                                /* :1379-1381 */
+  for (int32_t dd = 0; dd < m->ndom; ++dd) {                                             /* :1379-1381 */
+    const int32_t d = m->reverse ? m->ndom - 1 - dd : dd;
     const ko_dom *D = &m->dom[d];
     const double *o = m->loc + m->gbase[d];
     for (int32_t l = 0; l < D->nG; ++l) z[D->l2g[l]] += o[l] / (double)m->cnt[D->l2g[l]];
+  }
+}
+
+/* Rounding-floor probe: the same algorithm with the interface sums taken in descending subdomain order --
+ * mathematically identical, different rounding.  The distance between the two CPU runs is the floor below
+ * which no implementation of this arithmetic can be compared with another. */
+void ko_set_reverse(ko_model *m, int flag) { m->reverse = flag; }
+
+/* PiS of subdomain d (n_gd x n_gd column-major) set after construction: the constant "median"
+ * preconditioner of Example07_PcgSchurStochasticEllipticPde.jl:152-154 comes from another realization. */
+void ko_set_pis(ko_model *m, int32_t d, const double *PiS) {
+  ko_dom *D = &m->dom[d];
+  free(D->PiS);
+  D->PiS = (double *)dup_mem(PiS, 8 * (size_t)D->nG * (size_t)D->nG);
+}
+
+/* NB right-hand sides at once (interleaved w[k*NB + c]): the factor is streamed once per NB columns */
+#define KO_NB 8
+static void chol_solve_nb(const ko_dom *D, double *w) {
+  const int32_t n = D->nI;
+  for (int32_t j = 0; j < n; ++j) {
+    const int32_t p0 = D->Lp[j], p1 = D->Lp[j + 1];
+    double xj[KO_NB];
+    const double dg = D->Lx[p0];
+    for (int c = 0; c < KO_NB; ++c) { xj[c] = w[(size_t)j * KO_NB + c] / dg; w[(size_t)j * KO_NB + c] = xj[c]; }
+    for (int32_t p = p0 + 1; p < p1; ++p) {
+      const double l = D->Lx[p];
+      double *wi = w + (size_t)D->Li[p] * KO_NB;
+      for (int c = 0; c < KO_NB; ++c) wi[c] -= l * xj[c];
+    }
+  }
+  for (int32_t j = n - 1; j >= 0; --j) {
+    const int32_t p0 = D->Lp[j], p1 = D->Lp[j + 1];
+    double sacc[KO_NB];
+    for (int c = 0; c < KO_NB; ++c) sacc[c] = w[(size_t)j * KO_NB + c];
+    for (int32_t p = p0 + 1; p < p1; ++p) {
+      const double l = D->Lx[p];
+      const double *wi = w + (size_t)D->Li[p] * KO_NB;
+      for (int c = 0; c < KO_NB; ++c) sacc[c] -= l * wi[c];
+    }
+    const double dg = D->Lx[p0];
+    for (int c = 0; c < KO_NB; ++c) w[(size_t)j * KO_NB + c] = sacc[c] / dg;
+  }
+}
+
+/* assemble_local_schurs (EllipticPdeDomainDecomposition.jl:667-695): dense S_d column by column
+ * (S_d e_j by apply_local_schur, here KO_NB unit vectors per pass over the factor), then Symmetric():
+ * the upper triangle mirrored (:692).  Sd: n_gd x n_gd column-major, subdomain d.  Thread-safe across
+ * different subdomains (own scratch). */
+void ko_assemble_local_schur(const ko_model *m, int32_t d, double *Sd) {
+  const ko_dom *D = &m->dom[d];
+  const int32_t nI = D->nI, nG = D->nG;
+  double *w = (double *)malloc(8 * ((size_t)nI + 1) * KO_NB);
+  int32_t *pinv = (int32_t *)malloc(4 * ((size_t)nI + 1));
+  for (int32_t k = 0; k < nI; ++k) pinv[D->perm[k]] = k;
+  for (int32_t j0 = 0; j0 < nG; j0 += KO_NB) {
+    const int nb = (nG - j0 < KO_NB) ? nG - j0 : KO_NB;
+    memset(w, 0, 8 * (size_t)nI * KO_NB);
+    for (int c = 0; c < nb; ++c)                       /* t = A_IG e_j, rows in the factor's ordering */
+      for (int32_t p = D->Gp[j0 + c]; p < D->Gp[j0 + c + 1]; ++p) w[(size_t)pinv[D->Gi[p]] * KO_NB + c] += D->Gx[p];
+    chol_solve_nb(D, w);                               /* v = A_II^{-1} t */
+    for (int c = 0; c < nb; ++c) {
+      double *col = Sd + (size_t)(j0 + c) * nG;
+      memset(col, 0, 8 * (size_t)nG);
+      for (int32_t p = D->Hp[j0 + c]; p < D->Hp[j0 + c + 1]; ++p) col[D->Hi[p]] += D->Hx[p];   /* A_GG e_j */
+      for (int32_t l = 0; l < nG; ++l) {               /* -= A_IG' v */
+        double s = 0.0;
+        for (int32_t p = D->Gp[l]; p < D->Gp[l + 1]; ++p) s += D->Gx[p] * w[(size_t)pinv[D->Gi[p]] * KO_NB + c];
+        col[l] -= s;
+      }
+    }
+  }
+  for (int32_t j = 0; j < nG; ++j)                     /* Symmetric(): upper triangle wins */
+    for (int32_t i = j + 1; i < nG; ++i) Sd[i + (size_t)j * nG] = Sd[j + (size_t)i * nG];
+  free(w);
+  free(pinv);
+}
+
+/* All subdomains under OpenMP: Sd_all = concatenation of the column-major blocks, off[d] their offsets. */
+void ko_assemble_local_schurs(const ko_model *m, double *Sd_all, const int64_t *off, int nthreads) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int32_t d = 0; d < m->ndom; ++d) ko_assemble_local_schur(m, d, Sd_all + off[d]);
+}
+
+/* get_schur_rhs (:835-864): b_schur = b_G - sum_d R_d' A_GI,d A_II,d^{-1} b_I,d, ascending subdomains.
+ * bI_cat = [b_Id[0]; b_Id[1]; ...], bI_off their offsets. */
+void ko_schur_rhs(ko_model *m, const double *bI_cat, const int64_t *bI_off, const double *bG, double *out, int nthreads) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int32_t d = 0; d < m->ndom; ++d) {
+    const ko_dom *D = &m->dom[d];
+    const int32_t nI = D->nI, nG = D->nG;
+    double *t = D->work, *w = D->work + nI, *o = m->loc + m->gbase[d];
+    const double *b = bI_cat + bI_off[d];
+    for (int32_t k = 0; k < nI; ++k) w[k] = b[D->perm[k]];
+    chol_solve(D, w);                                                   /* :853-855 */
+    for (int32_t k = 0; k < nI; ++k) t[D->perm[k]] = w[k];
+    for (int32_t l = 0; l < nG; ++l) {                                  /* :857 */
+      double s = 0.0;
+      for (int32_t p = D->Gp[l]; p < D->Gp[l + 1]; ++p) s += D->Gx[p] * t[D->Gi[p]];
+      o[l] = s;
+    }
+  }
+  memcpy(out, bG, 8 * (size_t)m->n_gamma);                              /* :846-847 */
+  for (int32_t d = 0; d < m->ndom; ++d) {                               /* :858-860 */
+    const ko_dom *D = &m->dom[d];
+    const double *o = m->loc + m->gbase[d];
+    for (int32_t l = 0; l < D->nG; ++l) out[D->l2g[l]] -= o[l];
   }
 }
 

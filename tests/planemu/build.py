@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "julia-phd-krylov-spdes_b200", "csrc")
 SO = os.path.join(HERE, "libplanemu.so")
 SRCS = [os.path.join(HERE, "planemu.cpp"), os.path.join(CSRC, "plan.cpp")]
-DEPS = SRCS + [os.path.join(CSRC, f) for f in ("plan.h", "xchg_seq.h", "xchg_tables.h")]
+DEPS = SRCS + [os.path.join(CSRC, f) for f in ("plan.h", "xchg_tables.h")]
 
 
 def build(force=False):

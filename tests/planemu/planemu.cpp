@@ -11,7 +11,6 @@
 #include <vector>
 
 #include "../../julia-phd-krylov-spdes_b200/csrc/plan.h"
-#include "../../julia-phd-krylov-spdes_b200/csrc/xchg_seq.h"
 
 using namespace kb;
 
@@ -277,10 +276,6 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
 }
 
 // host-side bookkeeping of the multi-GPU exchange (csrc/xchg_seq.h), exposed for the CPU tests
-extern "C" uint32_t planemu_realigned_exchange_seq(uint32_t seq_now, uint32_t seq_before, int64_t enqueued, int64_t run) {
-  return kb::realigned_exchange_seq(seq_now, seq_before, enqueued, run);
-}
-
 // CPU emulation of the owner-ordered compact interface exchange (csrc/xchg_tables.h + the arithmetic of
 // exchange_gather in csrc/kernels.cuh) for `world` ranks: loc_all = concatenation over ALL subdomains of
 // their local interface vectors; y_out[rank * ng + g] = what rank `rank` assembles.  Returns the number

@@ -117,6 +117,106 @@ def test_global_column_operator_equals_local_operator():
         Sg.h.upload_global_blocks(0, bad.tocsc())
 
 
+@pytest.mark.parametrize("nx,ndom,csize", [(65, 16, 4), (97, 9, 4), (33, 4, 1)])
+def test_multi_vector_stream_kernel_bit_identical_per_column(nx, ndom, csize):
+    """K10: the factor stream is read once for R = 2 / 4 right-hand sides (multi-vector stream kernel); column j
+    of a batched apply carries exactly the bits of a single apply of that column, for every R and for ragged
+    column counts (7 = 4 + 2 + 1)."""
+    pr, S, M = gpu_ops(nx, ndom, csize)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    n = pr.sd.n_gamma
+    X = np.random.default_rng(8).standard_normal((n, 7))
+    singles = np.column_stack([S.h.apply_schur(X[:, k].copy()) for k in range(7)])
+    for rb in (0, 4, 2, 1):
+        S.h.set_option("rhs_block", rb)
+        Y = S.h.apply_schur(X)
+        assert np.array_equal(Y, singles), f"rhs_block={rb}"
+    S.h.set_option("rhs_block", 0)
+    for k in (0, 6):
+        assert rel(singles[:, k], E.apply_local_schurs(pr.blocks, inner, pr.sd, X[:, k])) <= 1e-12
+
+
+def test_dense_products_on_dmma_match_oracle():
+    """g1: batched dense local products with several right-hand sides on FP64 tensor cores (DMMA):
+    Neumann-Neumann apply (:1361-1386) and the assembled Schur apply (:761-785), ragged column counts."""
+    pr, S, M = gpu_ops(65, 16, 4)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    sd = pr.sd
+    S.assemble_local_schurs()
+    for ncol in (4, 9, 37, 70):
+        X = np.random.default_rng(ncol).standard_normal((sd.n_gamma, ncol))
+        Z = S.h.apply_nn(X)
+        Y = S.h.apply_schur_assembled(X)
+        for k in (0, ncol // 2, ncol - 1):
+            assert rel(Z[:, k], E.apply_neumann_neumann_schur(Pi, sd, X[:, k])) <= 1e-12
+            assert rel(Y[:, k], E.apply_local_schurs_assembled(Sd, sd, X[:, k])) <= 1e-12
+    # below dense_dmma_min columns the GEMV kernel runs: bit-identical to single applies
+    X = np.random.default_rng(1).standard_normal((sd.n_gamma, 3))
+    assert np.array_equal(S.h.apply_nn(X)[:, 2], S.h.apply_nn(X[:, 2].copy()))
+
+
+def test_tall_skinny_products_on_dmma():
+    """g1: V'AV / V (Q Z) shaped products (eigcg.jl:219, :228; defcg.jl:268, :432) on DMMA, ragged sizes, in place."""
+    pr, S, M = gpu_ops(65, 16, 4)
+    h, n = S.h, pr.sd.n_gamma
+    rng = np.random.default_rng(2)
+    for ka, kb_ in [(40, 40), (70, 33), (9, 130)]:
+        A, B = rng.standard_normal((n, ka)), rng.standard_normal((n, kb_))
+        a, b = h.mat_alloc(ka), h.mat_alloc(kb_)
+        h.mat_set(a, 0, A)
+        h.mat_set(b, 0, B)
+        assert rel(h.op_gemm_tn(a, 0, ka, b, 0, kb_), A.T @ B) <= 1e-12
+        assert rel(h.op_gemm_tn(a, 1, ka - 2, b, 2, kb_ - 3), A[:, 1:ka - 1].T @ B[:, 2:kb_ - 1]) <= 1e-12
+        kq = max(1, ka // 2 + 1)
+        Q = rng.standard_normal((ka, kq))
+        h.op_gemm_nn(a, 0, ka, Q, a, 0)                      # in place: V[:, 1:nev] = V (Q Z)
+        assert rel(h.mat_get(a, 0, kq), A @ Q) <= 1e-12
+        if kq < ka:
+            assert np.array_equal(h.mat_get(a, kq, ka - kq), A[:, kq:])   # columns beyond the result untouched
+        h.mat_free(a)
+        h.mat_free(b)
+
+
+def test_pcg_multi_block_of_right_hand_sides():
+    """g2 / Example11: independent PCG recurrences for a block of right-hand sides that share the operator
+    launches.  With the GEMV preconditioner kernel (dense_dmma_min above the column count) every column is
+    bit-for-bit the sequential single-RHS solve; with the DMMA preconditioner products it agrees to the rounding
+    floor of the solve (iteration count within 1, iterate to 20 x the measured CPU-vs-CPU floor)."""
+    pr, S, M = gpu_ops(65, 16, 4)
+    Aop, Mop, bs = _oracle_callables(pr)
+    n = pr.sd.n_gamma
+    rng = np.random.default_rng(12)
+    B = np.column_stack([bs] + [Aop(rng.standard_normal(n)) for _ in range(5)])
+    ref = [solvers.pcg(S, B[:, j].copy(), np.zeros(n), M) for j in range(6)]
+    S.h.set_option("dense_dmma_min", 1000)
+    X, its, ress = S.h.pcg_multi(B, np.zeros((n, 6)))
+    for j in range(6):
+        assert its[j] == ref[j][1] and np.array_equal(X[:, j], ref[j][0]) and np.array_equal(ress[j], ref[j][2])
+    S.h.set_option("dense_dmma_min", 4)
+    X, its, ress = S.h.pcg_multi(B, np.zeros((n, 6)))
+    (_, _, _), floor_x, floor_r = _pcg_floor(pr)
+    for j in range(6):
+        assert abs(its[j] - ref[j][1]) <= 1
+        assert ress[j][-1] <= 1e-7 * np.linalg.norm(B[:, j])
+        # equal stopping index: the iterates agree to the floor; one iteration apart: both are solutions to the
+        # 1e-7 residual tolerance and differ by what one more iteration changes
+        bound = max(1e-10, 20 * floor_x) if its[j] == ref[j][1] else 1e-6
+        assert np.linalg.norm(X[:, j] - ref[j][0]) <= bound * np.linalg.norm(ref[j][0])
+    # columns stop on their own: a column that starts at the solution stops at it = 1
+    X0 = np.zeros((n, 3))
+    X0[:, 1] = ref[0][0]
+    Bm = np.column_stack([B[:, 1], B[:, 0], B[:, 2]])
+    X, its, _ = S.h.pcg_multi(Bm, X0, maxit=40)
+    assert its[1] <= 3 and its[0] == min(40, ref[1][1]) and its[2] == min(40, ref[2][1])
+    # assembled operator + unpreconditioned variants run through the same driver
+    S.assemble_local_schurs()
+    X, its_a, _ = S.h.pcg_multi(B[:, :4], np.zeros((n, 4)), assembled=True)
+    assert all(abs(int(its_a[j]) - ref[j][1]) <= 1 for j in range(4))
+    X, its_u, _ = S.h.pcg_multi(B[:, :2], np.zeros((n, 2)), precond=False)
+    xu, itu, _ = solvers.cg(S, B[:, 0].copy(), np.zeros(n))
+    assert its_u[0] == itu and np.array_equal(X[:, 0], xu)
+
+
 def test_golden_vectors_on_gpu():
     g = np.load(GOLD)
     pr, S, M = gpu_ops(33, 4, 2)
@@ -369,6 +469,20 @@ def test_update_realization_values_only():
     inner2 = E.ExactInterior(pr2.blocks.A_II)
     assert rel(y2, E.apply_local_schurs(pr2.blocks, inner2, pr2.sd, x)) <= 1e-12
     assert rel(y1, y2) > 1e-3
+    # dense S_d of the previous realization must not survive a value update (the reference re-assembles per
+    # realization, :667-695): the assembled operator fails loudly until it is assembled again
+    S1 = fem.B200SchurOperator(pr1.sd, pr1.blocks, pr1.factors, csize=4)
+    S1.assemble_local_schurs()
+    S1.assembled = True
+    ya = S1 * x
+    S1.update_realization(pr2.blocks, pr2.factors)
+    assert S1.assembled is False
+    with pytest.raises(capi.KB200Error):
+        S1.h.apply_schur_assembled(x)
+    Sd2 = S1.assemble_local_schurs()
+    S1.assembled = True
+    assert rel(S1 * x, y2) <= 1e-11 and rel(ya, y1) <= 1e-11
+    assert rel(Sd2[3], E.assemble_local_schurs(pr2.blocks, inner2)[3]) <= 1e-11
 
 
 def test_fused_defpcg_and_pcg_multi():
