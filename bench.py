@@ -26,6 +26,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torchrun notices):
+# keep a private handle on the real stdout for the JSON line and point fd 1 at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -258,7 +269,7 @@ def main():
     if world == 1 and rank == 0:
         out["cpu_baseline"], out["parity_at_full_size"] = cpu_baseline(args, pr, sd, PiS, b_schur, iters, S=S, M=M)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -413,7 +424,7 @@ def run_reference(args, config):
            "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "ms_per_iteration": t_it * 1e3, "iterations_per_solve": int(iters_full), "relres": relres,
            "full_solve": full, "timed_steps": mode, "timed_wall_s": wall, "prep_s": t_prep}
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 

@@ -214,7 +214,8 @@ int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom,
 /* Average device time (ms) of `reps` back-to-back launches of one kernel on resident data:
  * which = 0 Schur stream kernel, 1 NN GEMV kernel, 2 assembled-Schur GEMV kernel, 3 the fused assembly
  * (+ peer exchange) / vector-update kernel (development probe: it leaves garbage in the work vectors; on
- * several ranks every rank must make the call). */
+ * several ranks every rank must make the call), 4 / 5 the multi-vector stream kernel with 2 / 4 right-hand sides per
+ * pass over the factor, 6..9 the batched DMMA Neumann-Neumann product with 8 / 16 / 32 / 64 right-hand sides. */
 int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
 /* Development aid: with option "debug_timing" = 1 the stream kernel records 16 clock64 stamps per
  * CTA (phase boundaries); this copies them out. */

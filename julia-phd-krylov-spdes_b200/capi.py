@@ -356,7 +356,8 @@ class Handle:
         keys = ["nnz_L", "stream_entries", "stream_rows", "stream_slices", "stream_bytes", "max_levels",
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
                 "consumer_warps", "ring_stages", "merge_depth", "min_block", "fused_pcg_ok", "vec_blocks",
-                "vec_threads", "exchange_entries", "exchange_entries_sent"]
+                "vec_threads", "exchange_entries", "exchange_entries_sent", "host_analyses", "value_refreshes",
+                "value_refs"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):

@@ -78,6 +78,7 @@ struct DomHost {
   std::vector<int32_t> l2g;  // 0-based interface ids
   kb::DomainIn in;           // perm, L, AIG, AGG
   bool have_blocks = false, have_chol = false;
+  bool stale_L = false, stale_blocks = false;   // newer values live in the device pool only (value refresh)
   std::vector<double> PiS, Sd;  // row-major copies of the column-major inputs
 };
 
@@ -146,6 +147,15 @@ struct kb200_ctx {
   bool topo = false, finalized = false, have_pinv = false, have_sd = false;
   // prepare_global_schur variant (EllipticPdeDomainDecomposition.jl:212-369): A_IΓ,d came with global
   // interface columns and the interface block as ONE assembled A_ΓΓ (CSR copy on the device)
+  // value refresh (plan.h): the value pool of the local subdomains and the maps that rewrite the stream from it
+  DevBuf<double> d_pool, d_dwork;
+  DevBuf<kb::ValRef> d_refs;
+  DevBuf<kb::DmapRef> d_dmap;
+  DevBuf<kb::BlockRef> d_blkref;
+  std::vector<int64_t> pool_off;                 // per local subdomain (+1)
+  std::vector<uint32_t> pool_L, pool_G, pool_GG; // segment lengths per local subdomain
+  bool values_dirty = false;                     // new values sit in the pool, the stream still holds the old ones
+  int64_t analyses = 0, refreshes = 0;           // host analyses / device value refreshes run so far (introspection)
   bool sd_on_device_only = false;   // dense S_d assembled on the device: host copies are fetched lazily
   bool global_mode = false;
   std::vector<int32_t> gg_ptr, gg_col;
@@ -265,10 +275,17 @@ int stream_rhs_block(const Ctx* c, int64_t want) {
 }
 
 // ---- finalize: build plans, upload -------------------------------------------------------------
+void refresh_values(Ctx* c);
+void fetch_stale_values(Ctx* c);
+
 void finalize(Ctx* c) {
-  if (c->finalized) return;
+  if (c->finalized) {
+    if (c->values_dirty) refresh_values(c);
+    return;
+  }
   require(c->topo, "kb200_set_topology must be called first");
   use_device(c);
+  fetch_stale_values(c);   // values that only live in the device pool come back before the re-analysis
   const int64_t nloc = c->d1 - c->d0;
   for (int64_t d = c->d0; d < c->d1; ++d)
     require(c->doms[d].have_blocks && c->doms[d].have_chol,
@@ -405,6 +422,68 @@ void finalize(Ctx* c) {
     if (!P.imap.empty())
       CUDA_TRY(cudaMemcpyAsync(c->d_imap.p + mo[k], P.imap.data(), P.imap.size() * 4, cudaMemcpyHostToDevice, s));
   }
+  // value pool + refresh maps (plan.h "VALUE REFRESH"): offsets made global
+  {
+    c->pool_off.assign(nloc + 1, 0);
+    c->pool_L.assign(nloc, 0);
+    c->pool_G.assign(nloc, 0);
+    c->pool_GG.assign(nloc, 0);
+    std::vector<int64_t> dw_off(nloc + 1, 0), ref_off(nloc + 1, 0), map_off(nloc + 1, 0), blk_cnt(nloc + 1, 0);
+    for (int64_t k = 0; k < nloc; ++k) {
+      const auto& P = plans[k];
+      c->pool_L[k] = P.pool_L;
+      c->pool_G[k] = P.pool_G;
+      c->pool_GG[k] = P.pool_GG;
+      c->pool_off[k + 1] = c->pool_off[k] + (int64_t)P.pool_L + P.pool_G + P.pool_GG + P.pool_D;
+      dw_off[k + 1] = dw_off[k] + P.pool_D;
+      ref_off[k + 1] = ref_off[k] + (int64_t)P.refs.size();
+      map_off[k + 1] = map_off[k] + (int64_t)P.dmap.size();
+      blk_cnt[k + 1] = blk_cnt[k] + (int64_t)P.blk_sz.size();
+    }
+    if (c->pool_off[nloc] >= (int64_t)0x7fffffff || so[nloc] / 8 > 0xffffffffull || dw_off[nloc] > (int64_t)0xffffffffu)
+      throw KbError(KB200_ERR_INPUT, "too many factor entries on one GPU for the 32-bit value maps: use more GPUs");
+    c->d_pool.alloc((size_t)c->pool_off[nloc]);
+    c->d_dwork.alloc((size_t)dw_off[nloc]);
+    c->d_refs.alloc((size_t)ref_off[nloc]);
+    c->d_dmap.alloc((size_t)map_off[nloc]);
+    c->d_blkref.alloc((size_t)blk_cnt[nloc]);
+    std::vector<kb::BlockRef> br((size_t)blk_cnt[nloc]);
+    for (int64_t k = 0; k < nloc; ++k) {
+      auto& P = plans[k];
+      const DomHost& dh = c->doms[c->d0 + k];
+      const uint32_t pbase = (uint32_t)c->pool_off[k];
+      const uint32_t dreg = pbase + P.pool_L + P.pool_G + P.pool_GG;   // Dinv region of this subdomain
+      double* pp = c->d_pool.p + c->pool_off[k];
+      if (P.pool_L) CUDA_TRY(cudaMemcpyAsync(pp, dh.in.L.nzval.data(), (size_t)P.pool_L * 8, cudaMemcpyHostToDevice, s));
+      if (P.pool_G) CUDA_TRY(cudaMemcpyAsync(pp + P.pool_L, dh.in.AIG.nzval.data(), (size_t)P.pool_G * 8, cudaMemcpyHostToDevice, s));
+      if (P.pool_GG)
+        CUDA_TRY(cudaMemcpyAsync(pp + P.pool_L + P.pool_G, dh.in.AGG.nzval.data(), (size_t)P.pool_GG * 8, cudaMemcpyHostToDevice, s));
+      const uint32_t s8 = (uint32_t)(so[k] / 8);
+      for (auto& r : P.refs) {
+        r.off8 += s8;
+        r.src = ((r.src & ~kb::kRefRecip) + pbase) | (r.src & kb::kRefRecip);
+      }
+      for (auto& m : P.dmap) {
+        m.dslot += (uint32_t)dw_off[k];
+        m.lidx += pbase;
+      }
+      if (!P.refs.empty())
+        CUDA_TRY(cudaMemcpyAsync(c->d_refs.p + ref_off[k], P.refs.data(), P.refs.size() * sizeof(kb::ValRef), cudaMemcpyHostToDevice, s));
+      if (!P.dmap.empty())
+        CUDA_TRY(cudaMemcpyAsync(c->d_dmap.p + map_off[k], P.dmap.data(), P.dmap.size() * sizeof(kb::DmapRef), cudaMemcpyHostToDevice, s));
+      for (size_t b = 0; b < P.blk_sz.size(); ++b) {
+        kb::BlockRef& R = br[(size_t)blk_cnt[k] + b];
+        R.dwork_off = (uint32_t)dw_off[k] + P.blk_off[b];
+        R.pool_off = dreg + P.blk_off[b];
+        R.sz = P.blk_sz[b];
+        R.pad_ = 0;
+      }
+    }
+    if (!br.empty()) CUDA_TRY(cudaMemcpyAsync(c->d_blkref.p, br.data(), br.size() * sizeof(kb::BlockRef), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // the sources above are host vectors that die with this scope / function
+    c->values_dirty = false;
+    c->analyses++;
+  }
   // interface maps (local subdomains only), ascending subdomain order per interface node
   {
     const int64_t ng = c->n_gamma;
@@ -469,7 +548,10 @@ void finalize(Ctx* c) {
   int sm_count = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const bool auto_threads = c->vec_threads == 0;
-  if (auto_threads) c->vec_threads = c->has_comm ? 1024 : 256;
+  // 256 threads per block for every GPU count: the dot products are reduced block-wise, so one block shape
+  // keeps their bits -- and with them the PCG trajectory -- independent of the number of GPUs (1024-thread
+  // blocks measured within 1 % at 2 GPUs)
+  if (auto_threads) c->vec_threads = 256;
   build_exchange_tables(c);  // multi-rank: send / gather tables of the compact exchange (sets xch_* sizes)
   auto blocks_for = [&](int threads) {
     int nb = (int)((ng + threads - 1) / threads);
@@ -549,7 +631,53 @@ void finalize(Ctx* c) {
   c->stats[18] = c->vec_threads;
   c->stats[19] = c->xch_mpad;
   c->stats[20] = c->xch_snd_n;
+  c->stats[21] = (double)c->analyses;
+  c->stats[22] = (double)c->refreshes;
+  c->stats[23] = (double)c->d_refs.n;
   c->finalized = true;  // host copies of the inputs are kept: value updates re-run the analysis
+}
+
+// New values for the resident stream (plan.h "VALUE REFRESH"): the callers' nzval arrays already sit in the pool.
+void refresh_values(Ctx* c) {
+  use_device(c);
+  cudaStream_t s = c->stream;
+  if (c->d_dmap.n) {
+    CUDA_TRY(cudaMemsetAsync(c->d_dwork.p, 0, c->d_dwork.n * 8, s));
+    kb::refresh_dmap_kernel<<<(unsigned)((c->d_dmap.n + 255) / 256), 256, 0, s>>>((int64_t)c->d_dmap.n, c->d_dmap.p, c->d_pool.p, c->d_dwork.p);
+    kb::refresh_invert_kernel<<<(unsigned)c->d_blkref.n, 128, 0, s>>>(c->d_blkref.p, c->d_dwork.p, c->d_pool.p);
+    c->launches += 2;
+  }
+  if (c->d_refs.n) {
+    kb::refresh_stream_kernel<<<(unsigned)((c->d_refs.n + 255) / 256), 256, 0, s>>>((int64_t)c->d_refs.n, c->d_refs.p, c->d_pool.p,
+                                                                                      reinterpret_cast<double*>(c->d_stream.p));
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  c->values_dirty = false;
+  c->refreshes++;
+}
+
+// Before a re-analysis: values that were only sent to the device pool (kb200_update_*_values on a finalized
+// handle) are copied back into the host-side inputs of the analysis.
+void fetch_stale_values(Ctx* c) {
+  if (c->d_pool.p == nullptr || c->pool_off.empty()) return;
+  const int64_t nloc = c->d1 - c->d0;
+  bool any = false;
+  for (int64_t k = 0; k < nloc && k + 1 < (int64_t)c->pool_off.size(); ++k) {
+    DomHost& dh = c->doms[c->d0 + k];
+    const double* pp = c->d_pool.p + c->pool_off[k];
+    if (dh.stale_L && dh.in.L.nzval.size() == c->pool_L[k]) {
+      CUDA_TRY(cudaMemcpyAsync(dh.in.L.nzval.data(), pp, (size_t)c->pool_L[k] * 8, cudaMemcpyDeviceToHost, c->stream));
+      any = true;
+    }
+    if (dh.stale_blocks && dh.in.AIG.nzval.size() == c->pool_G[k] && dh.in.AGG.nzval.size() == c->pool_GG[k]) {
+      CUDA_TRY(cudaMemcpyAsync(dh.in.AIG.nzval.data(), pp + c->pool_L[k], (size_t)c->pool_G[k] * 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaMemcpyAsync(dh.in.AGG.nzval.data(), pp + c->pool_L[k] + c->pool_G[k], (size_t)c->pool_GG[k] * 8, cudaMemcpyDeviceToHost, c->stream));
+      any = true;
+    }
+    dh.stale_L = dh.stale_blocks = false;
+  }
+  if (any) CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
 // ---- peer-memory interface exchange (multi-rank) -----------------------------------------------
@@ -1326,6 +1454,7 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colp
     csc_from_julia(dh.in.AGG, dh.n_gd, dh.n_gd, AGG_colptr, AGG_rowval, AGG_nzval, "A_GG");
     invalidate_dense_schur(h, dh);
     dh.have_blocks = true;
+    dh.stale_blocks = false;
   });
 }
 
@@ -1349,6 +1478,7 @@ int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const 
     csc_from_julia(dh.in.L, dh.n_I, dh.n_I, L_colptr, L_rowval, L_nzval, "L");
     invalidate_dense_schur(h, dh);
     dh.have_chol = true;
+    dh.stale_L = false;
   });
 }
 
@@ -1432,9 +1562,20 @@ int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzva
     if (!is_local(h, d)) return;
     DomHost& dh = h->doms[d];
     require(dh.have_chol, "kb200_upload_cholesky must come first");
-    std::copy(L_nzval, L_nzval + dh.in.L.nzval.size(), dh.in.L.nzval.begin());
     invalidate_dense_schur(h, dh);
-    h->finalized = false;
+    if (h->finalized) {
+      // values only: straight into the device pool; the stream is rewritten on the device before the next
+      // operation (no host analysis, no re-upload of the stream)
+      use_device(h);
+      const int64_t k = d - h->d0;
+      CUDA_TRY(cudaMemcpyAsync(h->d_pool.p + h->pool_off[k], L_nzval, (size_t)h->pool_L[k] * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffer
+      dh.stale_L = true;
+      h->values_dirty = true;
+    } else {
+      std::copy(L_nzval, L_nzval + dh.in.L.nzval.size(), dh.in.L.nzval.begin());
+      dh.stale_L = false;
+    }
   });
 }
 
@@ -1445,10 +1586,23 @@ int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG
     if (!is_local(h, d)) return;
     DomHost& dh = h->doms[d];
     require(dh.have_blocks, "kb200_upload_local_blocks must come first");
-    std::copy(AIG_nzval, AIG_nzval + dh.in.AIG.nzval.size(), dh.in.AIG.nzval.begin());
-    std::copy(AGG_nzval, AGG_nzval + dh.in.AGG.nzval.size(), dh.in.AGG.nzval.begin());
+    require(!h->global_mode, "value updates of the global-column variant: upload the blocks again");
     invalidate_dense_schur(h, dh);
-    h->finalized = false;
+    if (h->finalized) {
+      use_device(h);
+      const int64_t k = d - h->d0;
+      double* pp = h->d_pool.p + h->pool_off[k] + h->pool_L[k];
+      if (h->pool_G[k]) CUDA_TRY(cudaMemcpyAsync(pp, AIG_nzval, (size_t)h->pool_G[k] * 8, cudaMemcpyHostToDevice, h->stream));
+      if (h->pool_GG[k])
+        CUDA_TRY(cudaMemcpyAsync(pp + h->pool_G[k], AGG_nzval, (size_t)h->pool_GG[k] * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      dh.stale_blocks = true;
+      h->values_dirty = true;
+    } else {
+      std::copy(AIG_nzval, AIG_nzval + dh.in.AIG.nzval.size(), dh.in.AIG.nzval.begin());
+      std::copy(AGG_nzval, AGG_nzval + dh.in.AGG.nzval.size(), dh.in.AGG.nzval.begin());
+      dh.stale_blocks = false;
+    }
   });
 }
 
@@ -2240,6 +2394,8 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
   return guarded([&]() {
     require(h && stats, "null argument");
     finalize(h);
+    h->stats[21] = (double)h->analyses;
+    h->stats[22] = (double)h->refreshes;
     for (int64_t i = 0; i < n && i < 32; ++i) stats[i] = h->stats[i];
   });
 }
@@ -2273,10 +2429,37 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
     use_device(h);
     Ctx* c = h;
     const int n = (int)c->n_gamma;
+    const int64_t Gtot = c->G_base[c->d1 - c->d0];
+    DevBuf<double> xin;   // which >= 4: a block of right-hand sides (zeros: timing only)
+    int R = 1, kcols = 0;
+    if (which == 4 || which == 5) {
+      R = which == 4 ? 2 : 4;
+      require(stream_smem_bytes(c, R) <= (size_t)c->smem_limit, "right-hand-side block does not fit the shared-memory vector");
+      xin.alloc((size_t)n * R);
+      CUDA_TRY(cudaMemsetAsync(xin.p, 0, (size_t)n * R * 8, c->stream));
+      if ((int64_t)c->d_locm.n < Gtot * 4) c->d_locm.alloc((size_t)(Gtot * 4));
+    } else if (which >= 6 && which <= 9) {
+      kcols = which == 6 ? 8 : which == 7 ? 16 : which == 8 ? 32 : 64;
+      xin.alloc((size_t)n * kcols);
+      CUDA_TRY(cudaMemsetAsync(xin.p, 0, (size_t)n * kcols * 8, c->stream));
+      if ((int64_t)c->d_locm.n < Gtot * kcols) c->d_locm.alloc((size_t)(Gtot * kcols));
+    }
     auto once = [&]() {
       if (which == 0) launch_stream<kb::MODE_APPLY>(c, c->d_p.p, nullptr, nullptr, c->d_loc.p, nullptr, 0);
       else if (which == 1) launch_gemv(c, c->d_pinv.p, c->d_r.p, true, c->d_loc.p, nullptr, 0);
       else if (which == 2) launch_gemv(c, c->d_sd.p, c->d_p.p, false, c->d_loc.p, nullptr, 0);
+      else if (which == 4 || which == 5) {
+        // the multi-vector stream kernel with R = 2 / 4 right-hand sides per pass over the factor
+        StreamIo io;
+        io.x_gamma = xin.p;
+        io.ldx = n;
+        io.out_loc = c->d_locm.p;
+        io.ldo = Gtot;
+        launch_stream<kb::MODE_APPLY>(c, io, nullptr, 0, R);
+      } else if (which >= 6) {
+        // the batched DMMA Neumann-Neumann product with 8 / 16 / 32 / 64 right-hand sides
+        launch_dense_gemm(c, c->d_pinv.p, true, xin.p, n, kcols, c->d_locm.p, Gtot, nullptr, 0);
+      }
       else {
         // which == 3: the fused assembly (+ peer exchange) / update kernel alone (development probe: the
         // vectors it updates hold garbage afterwards; on several ranks every rank must make this call)
@@ -2292,7 +2475,8 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
         c->launches++;
       }
     };
-    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd) || (which == 3 && c->fused_ok && (!c->has_comm || c->peer_ok)),
+    require(which == 0 || (which == 1 && c->have_pinv) || (which == 2 && c->have_sd) || (which == 3 && c->fused_ok && (!c->has_comm || c->peer_ok)) ||
+                which == 4 || which == 5 || (which >= 6 && which <= 9 && c->have_pinv),
             "kernel inputs not uploaded / fused kernel not available");
     if (which == 3) {  // a state whose done_at does not skip the kernel
       kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, 1.0, 0.0, 1, INT_MAX - 1);

@@ -1550,3 +1550,59 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(double* sd_pool, const 
 }
 
 }  // namespace kb
+
+// =============================================================================================
+// VALUE REFRESH for a new coefficient realization (plan.h, "VALUE REFRESH"): the stream keeps its structure,
+// only its values are rewritten, on the device.  (1) the in-block entries of L are scattered into the dense
+// diagonal blocks D of the inverted supernode groups, (2) every block is re-inverted with the arithmetic of the
+// host analysis (invert_lower_block in plan.cpp: same order of operations, no FMA contraction -- the refreshed
+// stream has the bits of a stream analysed afresh from the new values), (3) every value slot of the stream is
+// rewritten from the value pool.
+// =============================================================================================
+namespace kb {
+
+__global__ void __launch_bounds__(256) refresh_dmap_kernel(int64_t nmap, const DmapRef* dmap, const double* pool, double* dwork) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nmap) dwork[dmap[e].dslot] = pool[dmap[e].lidx];
+}
+
+struct BlockRef {
+  uint32_t dwork_off;  // D of the block in the workspace (row-major sz x sz)
+  uint32_t pool_off;   // Dinv of the block in the value pool
+  uint32_t sz, pad_;
+};
+
+// one CTA per block, one thread per column of the inverse (a column only depends on itself)
+__global__ void __launch_bounds__(128) refresh_invert_kernel(const BlockRef* blocks, const double* dwork, double* pool) {
+  const BlockRef B = blocks[blockIdx.x];
+  const int sz = (int)B.sz;
+  const double* D = dwork + B.dwork_off;
+  double* Dinv = pool + B.pool_off;
+  for (int c0 = threadIdx.x; c0 < sz; c0 += blockDim.x) {
+    Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
+    for (int i = c0 + 1; i < sz; ++i) {
+      double acc = 0.0;
+      bool any = false;
+      const double* Di = D + (size_t)i * sz;
+      for (int k = c0; k < i; ++k) {
+        const double d = Di[k], v = Dinv[(size_t)k * sz + c0];
+        if (d != 0.0 && v != 0.0) {
+          acc = __dadd_rn(acc, __dmul_rn(d, v));
+          any = true;
+        }
+      }
+      Dinv[(size_t)i * sz + c0] = any ? -acc / Di[i] : 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) refresh_stream_kernel(int64_t nref, const ValRef* refs, const double* pool, double* stream8) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nref) return;
+  const ValRef r = refs[e];
+  double v = pool[r.src & ~kRefRecip];
+  if (r.src & kRefRecip) v = 1.0 / v;
+  stream8[r.off8] = v;
+}
+
+}  // namespace kb

@@ -19,11 +19,21 @@ struct TmpRow {
   int32_t warp;  // consumer warp that owns the row (private phase), -1: rows of a CTA-wide level
   uint32_t ebeg;  // into the builder's scratch entry arrays
   uint32_t len;
+  uint32_t diag_src;  // pool entry the divisor comes from (reciprocal), kNoSrc: a constant
 };
+
+constexpr uint32_t kNoSrc = 0xffffffffu;
 
 struct Scratch {
   std::vector<uint16_t> cols;
   std::vector<double> vals;
+  std::vector<uint32_t> srcs;  // pool entry of every value (value refresh, plan.h)
+};
+
+// a serialised slice + where its values come from (slot offsets relative to the slice start)
+struct SliceBytes {
+  std::vector<uint8_t> b;
+  std::vector<ValRef> refs;
 };
 
 inline int pow2ceil(int v) {
@@ -40,6 +50,7 @@ inline int ilog2(int p) {
 // Byte stream of one CTA.
 struct CtaStream {
   std::vector<uint8_t> bytes;
+  std::vector<ValRef> refs;  // slot offsets relative to the CTA stream
   int64_t n_entries = 0, n_rows = 0, n_packets = 0, lane_steps = 0;
   size_t room() const { return kChunkBytes - (bytes.size() % kChunkBytes); }
   void pad_to_chunk() {
@@ -53,8 +64,8 @@ struct CtaStream {
 };
 
 // Serialise one slice (rows ord[p..q) of `rows`, T lanes per row) -- layout in plan.h.
-std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const std::vector<uint32_t>& ord,
-                                size_t p, size_t q, int T, CtaStream& cs) {
+SliceBytes make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const std::vector<uint32_t>& ord,
+                      size_t p, size_t q, int T, CtaStream& cs) {
   const int nr = (int)(q - p);
   const uint32_t maxlen = rows[ord[p]].len;
   const uint32_t kmax = (maxlen + T - 1) / T;
@@ -62,6 +73,7 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
   // run out get a zero entry (rows of a slice have similar lengths, so this padding is small)
   std::vector<double> pv;
   std::vector<uint16_t> pc;
+  std::vector<uint32_t> ps;
   int64_t real = 0;
   for (uint32_t k = 0; k < kmax; ++k)
     for (int lane = 0; lane < nr * T; ++lane) {
@@ -71,14 +83,17 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
       if (idx < tr.len) {
         pv.push_back(sc.vals[tr.ebeg + idx]);
         pc.push_back(sc.cols[tr.ebeg + idx]);
+        ps.push_back(sc.srcs[tr.ebeg + idx]);
         ++real;
       } else {
         pv.push_back(0.0);
         pc.push_back(0);
+        ps.push_back(kNoSrc);
       }
     }
   if (pv.size() > 65535u || kmax > 65535u) throw std::runtime_error("internal: slice too large");
-  std::vector<uint8_t> b;
+  SliceBytes out;
+  std::vector<uint8_t>& b = out.b;
   auto put = [&](const void* ptr, size_t nb) {
     const uint8_t* u = static_cast<const uint8_t*>(ptr);
     b.insert(b.end(), u, u + nb);
@@ -100,9 +115,13 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
     rr.dst = tr.dst;
     rr.flags = (uint16_t)((tr.kind ? kRowFresh : 0) | (tr.bcast ? kRowBcast : 0));
     rr.diag = 1.0 / tr.diag;  // the device multiplies by the reciprocal
+    if (tr.diag_src != kNoSrc) out.refs.push_back(ValRef{(uint32_t)((b.size() + 8) / 8), tr.diag_src | kRefRecip});
     put(&rr, sizeof(rr));
   }
   if (!pv.empty()) {
+    const uint32_t v0 = (uint32_t)(b.size() / 8);
+    for (size_t k = 0; k < ps.size(); ++k)
+      if (ps[k] != kNoSrc) out.refs.push_back(ValRef{v0 + (uint32_t)k, ps[k]});
     put(pv.data(), pv.size() * 8);
     put(pc.data(), pc.size() * 2);
   }
@@ -113,7 +132,7 @@ std::vector<uint8_t> make_slice(const std::vector<TmpRow>& rows, const Scratch& 
   cs.n_rows += nr;
   cs.n_packets += 1;
   cs.lane_steps += 32 * (int64_t)kmax;
-  return b;
+  return out;
 }
 
 // Chunk under construction: per-warp token lists + slice payloads (see plan.h, "warp programs").
@@ -121,7 +140,7 @@ struct ChunkBuilder {
   int NW;
   CtaStream& cs;
   std::vector<std::vector<uint16_t>> tok;          // per warp: slice index (into `slices`) or kTokBarrier
-  std::vector<std::vector<uint8_t>> slices;
+  std::vector<SliceBytes> slices;
   size_t payload = 0, ntok = 0;
   ChunkBuilder(int nw, CtaStream& s) : NW(nw), cs(s), tok(nw) {}
   static size_t table_bytes(size_t ntokens) { return (size_t)kChunkDirBytes + ((ntokens * 2 + 15) / 16) * 16; }
@@ -138,7 +157,7 @@ struct ChunkBuilder {
     size_t o = tb;
     for (size_t k = 0; k < slices.size(); ++k) {
       off[k] = o;
-      o += slices[k].size();
+      o += slices[k].b.size();
     }
     if (o > (size_t)kChunkBytes) throw std::runtime_error("internal: chunk overflow");
     std::vector<uint16_t> dir(kChunkDirBytes / 2, 0);
@@ -159,7 +178,11 @@ struct ChunkBuilder {
       cs.put((uint16_t)0);
       ++written;
     }
-    for (auto& sl : slices) cs.bytes.insert(cs.bytes.end(), sl.begin(), sl.end());
+    for (size_t k = 0; k < slices.size(); ++k) {
+      const uint32_t at8 = (uint32_t)((base + off[k]) / 8);   // slices start on 16-byte boundaries
+      for (const ValRef& r : slices[k].refs) cs.refs.push_back(ValRef{at8 + r.off8, r.src});
+      cs.bytes.insert(cs.bytes.end(), slices[k].b.begin(), slices[k].b.end());
+    }
     if (cs.bytes.size() - base != o) throw std::runtime_error("internal: chunk size mismatch");
     cs.pad_to_chunk();
     for (auto& t : tok) t.clear();
@@ -167,13 +190,13 @@ struct ChunkBuilder {
     payload = 0;
     ntok = 0;
   }
-  void add_slice(int warp, std::vector<uint8_t>&& b) {
-    if (!fits(1, b.size())) flush();
-    if (!fits(1, b.size())) throw std::runtime_error("internal: slice exceeds a chunk");
+  void add_slice(int warp, SliceBytes&& sb) {
+    if (!fits(1, sb.b.size())) flush();
+    if (!fits(1, sb.b.size())) throw std::runtime_error("internal: slice exceeds a chunk");
     if (slices.size() >= 0xfffe) throw std::runtime_error("internal: too many slices in a chunk");
     tok[warp].push_back((uint16_t)slices.size());
-    payload += b.size();
-    slices.push_back(std::move(b));
+    payload += sb.b.size();
+    slices.push_back(std::move(sb));
     ++ntok;
   }
   void add_barrier() {  // one barrier token in every warp's program
@@ -215,7 +238,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
     return std::min(32, pow2ceil(std::max(1, want)));
   };
   // slices of the rows ord[i..j) (one level, sorted by decreasing length)
-  auto level_slices = [&](const std::vector<uint32_t>& ord, size_t i, size_t j, std::vector<std::vector<uint8_t>>& slices) {
+  auto level_slices = [&](const std::vector<uint32_t>& ord, size_t i, size_t j, std::vector<SliceBytes>& slices) {
     size_t p = i;
     while (p < j) {
       const int T = t_of(rows[ord[p]].len);
@@ -245,7 +268,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
 
   auto emit_shared = [&]() {
     const std::vector<uint32_t> ord = sorted_order([](const TmpRow& r) { return r.warp < 0; });
-    std::vector<std::vector<uint8_t>> slices;  // serialised slices of the current level
+    std::vector<SliceBytes> slices;  // serialised slices of the current level
     size_t i = 0;
     for (int lev = 0; lev < (int)nlevels; ++lev) {
       size_t j = i;
@@ -264,9 +287,9 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
         lane_entries = std::max(1, opt.lane_entries);
       }
       // balance the warps of the level: longest-processing-time first on an estimate of the slice latency
-      auto cost = [](const std::vector<uint8_t>& b) {
+      auto cost = [](const SliceBytes& sb) {
         SliceHdr sh;
-        std::memcpy(&sh, b.data(), sizeof(sh));
+        std::memcpy(&sh, sb.b.data(), sizeof(sh));
         return 150 + 30 * (int)sh.kmax + 40 * (int)sh.tlog2;
       };
       std::vector<size_t> so(slices.size());
@@ -292,7 +315,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
   auto emit_private = [&]() {
     // per warp: the slices of its rows in level order; the chunks take from each warp a share
     // proportional to what it has left, so that the warps advance through the ring at the same pace
-    std::vector<std::vector<std::vector<uint8_t>>> ws(NW);
+    std::vector<std::vector<SliceBytes>> ws(NW);
     std::vector<size_t> tot(NW, 0), nxt(NW, 0), rem(NW, 0);
     for (int w = 0; w < NW; ++w) {
       const std::vector<uint32_t> ord = sorted_order([w](const TmpRow& r) { return r.warp == w; });
@@ -303,7 +326,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
         level_slices(ord, i, j, ws[w]);
         i = j;
       }
-      for (auto& b : ws[w]) tot[w] += b.size();
+      for (auto& b : ws[w]) tot[w] += b.b.size();
       rem[w] = tot[w];
       if (n_private_rows) *n_private_rows += (int64_t)ord.size();
       if (n_private_slices) *n_private_slices += (int64_t)ws[w].size();
@@ -320,7 +343,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
         }
       }
       if (best < 0) break;
-      rem[best] -= ws[best][nxt[best]].size();
+      rem[best] -= ws[best][nxt[best]].b.size();
       cb.add_slice(best, std::move(ws[best][nxt[best]]));
       nxt[best]++;
     }
@@ -359,7 +382,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   }
   for (int i = 0; i < n; ++i) rptr[i + 1] += rptr[i];
   const int64_t nnzl = rptr[n];
-  std::vector<int32_t> rcol(nnzl);
+  std::vector<int32_t> rcol(nnzl), rsrc(nnzl);   // rsrc: position of the entry in L.nzval (value refresh)
   std::vector<double> rval(nnzl);
   {
     std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
@@ -368,6 +391,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         int i = L.rowval[p];
         rcol[fill[i]] = j;
         rval[fill[i]] = L.nzval[p];
+        rsrc[fill[i]] = p;
         fill[i]++;
       }
   }
@@ -527,8 +551,9 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   // group, for an inverse that is only as dense as the factor's own coupling between those supernodes.
   // blk[i] = block index or -1; nodes of a block ascending.
   std::vector<int32_t> blk(n, -1), pos_in_blk(n, -1);
-  struct Block { std::vector<int32_t> nodes; std::vector<double> Dinv; };  // Dinv row-major s x s (lower)
+  struct Block { std::vector<int32_t> nodes; std::vector<double> Dinv; std::vector<char> pat; uint32_t off = 0; };  // Dinv row-major s x s (lower)
   std::vector<Block> blocks;
+  std::vector<DmapRef> dmap_out;
   if (opt.min_block > 0 && n > 0) {
     auto ccount = [&](int j) { return L.colptr[j + 1] - L.colptr[j]; };
     // maximal chains
@@ -580,31 +605,38 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         B.nodes.push_back(j);  // chains are visited in ascending order: nodes ascending
       }
     }
-    for (auto& B : blocks) {
+    uint32_t doff = 0;
+    for (size_t bi = 0; bi < blocks.size(); ++bi) {
+      Block& B = blocks[bi];
       const int sz = (int)B.nodes.size();
       for (int k = 0; k < sz; ++k) pos_in_blk[B.nodes[k]] = k;
+      B.off = doff;
+      doff += (uint32_t)sz * (uint32_t)sz;
       std::vector<double> D((size_t)sz * sz, 0.0);
+      std::vector<char> Dpat((size_t)sz * sz, 0);
       for (int k = 0; k < sz; ++k) {
         const int j = B.nodes[k];
         for (int p = L.colptr[j]; p < L.colptr[j + 1]; ++p) {
           const int i = L.rowval[p];
-          if (blk[i] == blk[j]) D[(size_t)pos_in_blk[i] * sz + k] = L.nzval[p];
+          if (blk[i] == blk[j]) {
+            D[(size_t)pos_in_blk[i] * sz + k] = L.nzval[p];
+            Dpat[(size_t)pos_in_blk[i] * sz + k] = 1;
+            dmap_out.push_back(DmapRef{B.off + (uint32_t)(pos_in_blk[i] * sz + k), (uint32_t)p});
+          }
         }
       }
       B.Dinv.assign((size_t)sz * sz, 0.0);
+      invert_lower_block(sz, D.data(), B.Dinv.data());
+      // STRUCTURAL pattern of the inverse (which entries the stream carries must not depend on the values:
+      // a new realization rewrites values in place): entry (i, c) is present iff some k in [c, i) has D[i,k]
+      // stored and Dinv[k,c] present
+      B.pat.assign((size_t)sz * sz, 0);
       for (int c0 = 0; c0 < sz; ++c0) {
-        B.Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
+        B.pat[(size_t)c0 * sz + c0] = 1;
         for (int i = c0 + 1; i < sz; ++i) {
-          double acc = 0.0;
-          bool any = false;
-          for (int k = c0; k < i; ++k) {
-            const double d = D[(size_t)i * sz + k], v = B.Dinv[(size_t)k * sz + c0];
-            if (d != 0.0 && v != 0.0) {
-              acc += d * v;
-              any = true;
-            }
-          }
-          B.Dinv[(size_t)i * sz + c0] = any ? -acc / D[(size_t)i * sz + i] : 0.0;
+          char any = 0;
+          for (int k = c0; k < i && !any; ++k) any = Dpat[(size_t)i * sz + k] && B.pat[(size_t)k * sz + c0];
+          B.pat[(size_t)i * sz + c0] = any;
         }
       }
     }
@@ -725,7 +757,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     gptr[pinv[v] + 1]++;
   }
   for (int i = 0; i < n; ++i) gptr[i + 1] += gptr[i];
-  std::vector<int32_t> gcol(G.rowval.size());
+  std::vector<int32_t> gcol(G.rowval.size()), gsrc(G.rowval.size());
   std::vector<double> gval(G.rowval.size());
   {
     std::vector<int32_t> fill(gptr.begin(), gptr.end() - 1);
@@ -734,6 +766,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         int i = pinv[G.rowval[p]];
         gcol[fill[i]] = l;
         gval[fill[i]] = G.nzval[p];
+        gsrc[fill[i]] = p;
         fill[i]++;
       }
   }
@@ -742,7 +775,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   std::vector<int32_t> ggptr(ng + 1, 0);
   for (int32_t v : GG.rowval) ggptr[v + 1]++;
   for (int i = 0; i < ng; ++i) ggptr[i + 1] += ggptr[i];
-  std::vector<int32_t> ggcol(GG.rowval.size());
+  std::vector<int32_t> ggcol(GG.rowval.size()), ggsrc(GG.rowval.size());
   std::vector<double> ggval(GG.rowval.size());
   {
     std::vector<int32_t> fill(ggptr.begin(), ggptr.end() - 1);
@@ -751,6 +784,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         int l = GG.rowval[p];
         ggcol[fill[l]] = m;
         ggval[fill[l]] = GG.nzval[p];
+        ggsrc[fill[l]] = p;
         fill[l]++;
       }
   }
@@ -763,8 +797,9 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   Scratch sc;
   std::vector<TmpRow> rows;
   int cur_warp = -1;  // warp of the rows being emitted (-1: CTA-wide levels)
-  auto begin_row = [&](uint16_t dst, double dg, int level, int kind) {
+  auto begin_row = [&](uint16_t dst, double dg, int level, int kind, uint32_t dg_src = kNoSrc) {
     TmpRow r;
+    r.diag_src = dg_src;
     r.warp = cur_warp;
     r.dst = dst;
     r.diag = dg;
@@ -775,9 +810,13 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     r.len = 0;
     rows.push_back(r);
   };
-  auto push = [&](uint16_t col, double v) {
+  // pool layout of the value refresh (plan.h): [L | A_IG | A_GG | Dinv blocks]
+  const uint32_t poolL = 0, poolG = (uint32_t)L.nzval.size(), poolGG = poolG + (uint32_t)G.nzval.size(),
+                 poolD = poolGG + (uint32_t)GG.nzval.size();
+  auto push = [&](uint16_t col, double v, uint32_t src) {
     sc.cols.push_back(col);
     sc.vals.push_back(v);
+    sc.srcs.push_back(src);
     rows.back().len++;
   };
 
@@ -803,6 +842,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
       rows.clear();
       sc.cols.clear();
       sc.vals.clear();
+      sc.srcs.clear();
     };
     auto mine = [&](int node) { return owner[node] == c || (c == 0 && owner[node] < 0); };
 
@@ -810,7 +850,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
     for (int i = 0; i < n; ++i)
       if (mine(i) && gptr[i + 1] > gptr[i]) {
         begin_row(sidx(i), 1.0, 0, 0);
-        for (int p = gptr[i]; p < gptr[i + 1]; ++p) push((uint16_t)(xd_off + gcol[p]), gval[p]);
+        for (int p = gptr[i]; p < gptr[i + 1]; ++p) push((uint16_t)(xd_off + gcol[p]), gval[p], poolG + (uint32_t)gsrc[p]);
       }
     section(SEC_INIT);
     // forward / backward rows of the nodes selected by `sel` (own subtree nodes, or top nodes)
@@ -819,9 +859,9 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         if (!sel(i)) continue;
         cur_warp = wown[i];
         if (blk[i] < 0) {
-          begin_row(sidx(i), diag[i], fe[i], 0);
+          begin_row(sidx(i), diag[i], fe[i], 0, poolL + (uint32_t)L.colptr[i]);
           for (int p = rptr[i]; p < rptr[i + 1]; ++p)
-            if (same_scope(i, rcol[p])) push(xidx(rcol[p]), rval[p]);
+            if (same_scope(i, rcol[p])) push(xidx(rcol[p]), rval[p], poolL + (uint32_t)rsrc[p]);
         } else {
           const Block& B = blocks[blk[i]];
           const int sz = (int)B.nodes.size();
@@ -832,13 +872,13 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
             const int j = rcol[p];
             if (blk[j] == blk[i] || !same_scope(i, j)) continue;
             if (!any) { begin_row(sidx(i), 1.0, fe[i] - 1, 0); any = true; }
-            push(xidx(j), rval[p]);
+            push(xidx(j), rval[p], poolL + (uint32_t)rsrc[p]);
           }
           // step B: x_i = sum_{k in [a, i]} Dinv[i,k] t_k   (fresh write to the scratch slot)
           begin_row(scridx(i), -1.0, fe[i], 1);
           for (int pk = 0; pk <= pi; ++pk) {
-            const double v = B.Dinv[(size_t)pi * sz + pk];
-            if (v != 0.0) push(sidx(B.nodes[pk]), v);
+            const size_t e = (size_t)pi * sz + pk;
+            if (B.pat[e]) push(sidx(B.nodes[pk]), B.Dinv[e], poolD + B.off + (uint32_t)e);
           }
         }
       }
@@ -848,8 +888,8 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
         if (!sel(i)) continue;
         cur_warp = wown[i];
         if (blk[i] < 0) {
-          begin_row(sidx(i), diag[i], be[i], 0);
-          for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) push(sidx(L.rowval[p]), L.nzval[p]);
+          begin_row(sidx(i), diag[i], be[i], 0, poolL + (uint32_t)L.colptr[i]);
+          for (int p = L.colptr[i] + 1; p < L.colptr[i + 1]; ++p) push(sidx(L.rowval[p]), L.nzval[p], poolL + (uint32_t)p);
         } else {
           const Block& B = blocks[blk[i]];
           const int sz = (int)B.nodes.size();
@@ -860,13 +900,13 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
             const int k = L.rowval[p];
             if (blk[k] == blk[i]) continue;
             if (!any) { begin_row(scridx(i), 1.0, be[i] - 1, 0); any = true; }
-            push(sidx(k), L.nzval[p]);
+            push(sidx(k), L.nzval[p], poolL + (uint32_t)p);
           }
           // step B': v_i = sum_{k in [i, b]} Dinv[k,i] t_k   (fresh write to slot i)
           begin_row(sidx(i), -1.0, be[i], 1);
           for (int pk = pi; pk < sz; ++pk) {
-            const double v = B.Dinv[(size_t)pk * sz + pi];
-            if (v != 0.0) push(scridx(B.nodes[pk]), v);
+            const size_t e = (size_t)pk * sz + pi;
+            if (B.pat[e]) push(scridx(B.nodes[pk]), B.Dinv[e], poolD + B.off + (uint32_t)e);
           }
         }
       }
@@ -885,7 +925,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
               begin_row((uint16_t)(part_off + pos[i]), 1.0, 0, 0);
               any = true;
             }
-            push(xidx(rcol[p]), rval[p]);
+            push(xidx(rcol[p]), rval[p], poolL + (uint32_t)rsrc[p]);
           }
       }
     section(SEC_PART);
@@ -943,7 +983,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
       for (int l = 0; l < ng; ++l)
         if (ggptr[l + 1] > ggptr[l]) {
           begin_row((uint16_t)(out_off + l), 1.0, 0, 0);
-          for (int p = ggptr[l]; p < ggptr[l + 1]; ++p) push((uint16_t)(xd_off + ggcol[p]), ggval[p]);
+          for (int p = ggptr[l]; p < ggptr[l + 1]; ++p) push((uint16_t)(xd_off + ggcol[p]), ggval[p], poolGG + (uint32_t)ggsrc[p]);
         }
     section(SEC_GG);
     // SEC_OUT
@@ -956,7 +996,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
             begin_row((uint16_t)(out_off + l), 1.0, 0, 0);
             any = true;
           }
-          push(sidx(i), G.nzval[p]);
+          push(sidx(i), G.nzval[p], poolG + (uint32_t)p);
         }
       }
     }
@@ -964,6 +1004,13 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
 
     // append the CTA stream to the plan's stream pool
     D.stream_off = out.stream.size();
+    {
+      const uint64_t base8 = (uint64_t)out.stream.size() / 8;
+      for (const ValRef& r : cs.refs) {
+        if (base8 + r.off8 > 0xffffffffull) throw std::runtime_error("internal: stream too long for 32-bit value slots");
+        out.refs.push_back(ValRef{(uint32_t)(base8 + r.off8), r.src});
+      }
+    }
     out.stream.insert(out.stream.end(), cs.bytes.begin(), cs.bytes.end());
     out.n_entries += cs.n_entries;
     out.n_rows += cs.n_rows;
@@ -985,6 +1032,34 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
       for (int i = 0; i < n; ++i)
         if (owner[i] < 0) m[pos[i]] = in.perm[i];
       out.imap.insert(out.imap.end(), m.begin(), m.end());
+    }
+  }
+  out.dmap = dmap_out;
+  out.pool_L = (uint32_t)L.nzval.size();
+  out.pool_G = (uint32_t)G.nzval.size();
+  out.pool_GG = (uint32_t)GG.nzval.size();
+  out.pool_D = 0;
+  for (auto& B : blocks) {
+    out.blk_off.push_back(B.off);
+    out.blk_sz.push_back((uint32_t)B.nodes.size());
+    out.pool_D += (uint32_t)(B.nodes.size() * B.nodes.size());
+  }
+}
+
+void invert_lower_block(int sz, const double* D, double* Dinv) {
+  for (int c0 = 0; c0 < sz; ++c0) {
+    Dinv[(size_t)c0 * sz + c0] = 1.0 / D[(size_t)c0 * sz + c0];
+    for (int i = c0 + 1; i < sz; ++i) {
+      double acc = 0.0;
+      bool any = false;
+      for (int k = c0; k < i; ++k) {
+        const double d = D[(size_t)i * sz + k], v = Dinv[(size_t)k * sz + c0];
+        if (d != 0.0 && v != 0.0) {
+          acc += d * v;
+          any = true;
+        }
+      }
+      Dinv[(size_t)i * sz + c0] = any ? -acc / D[(size_t)i * sz + i] : 0.0;
     }
   }
 }

@@ -119,10 +119,34 @@ struct DomainIn {
   Csc AGG;                    // n_gd x n_gd
 };
 
+// VALUE REFRESH (new coefficient realization on the same mesh / partition / ordering, the loop of
+// Example07_PcgSchurStochasticEllipticPde.jl:160-204).  The plan is purely structural: which rows, levels,
+// slices and tokens exist depends only on the sparsity patterns.  Every value the stream holds comes from the
+// subdomain's VALUE POOL
+//     [ L.nzval | A_IG.nzval | A_GG.nzval | Dinv of block 0 (row-major sz x sz) | Dinv of block 1 | ... ]
+// either directly or as a reciprocal (the row divisors): ValRef says which 8-byte slot of the stream takes which
+// pool entry.  For a new realization the caller's nzval arrays are copied into the pool, the supernode blocks
+// are re-inverted (DmapRef: which entry of L sits where in the dense diagonal block D of a block) and the
+// stream slots are rewritten by a scatter kernel -- no host analysis, no re-upload of the stream.
+constexpr uint32_t kRefRecip = 0x80000000u;  // ValRef::src flag: the slot holds 1 / pool[src]
+struct ValRef {
+  uint32_t off8;  // 8-byte slot in the stream (plan-local; made global by the caller)
+  uint32_t src;   // pool entry (plan-local) | kRefRecip
+};
+struct DmapRef {
+  uint32_t dslot;  // entry of the D workspace (Dinv region layout: block offset + row * sz + col)
+  uint32_t lidx;   // entry of L.nzval
+};
+
 struct DomainPlan {
   std::vector<CtaDesc> ctas;      // csize descriptors (offsets local to this plan's pools)
   std::vector<uint8_t> stream;    // concatenated CTA streams (each a multiple of kChunkBytes)
   std::vector<int32_t> imap;      // ownmap / topmap entries
+  // value refresh (see above)
+  std::vector<ValRef> refs;
+  std::vector<DmapRef> dmap;
+  std::vector<uint32_t> blk_off, blk_sz;   // per inverted block: offset in the Dinv region, size
+  uint32_t pool_L = 0, pool_G = 0, pool_GG = 0, pool_D = 0;   // pool segment lengths
   // statistics
   int64_t nnz_L = 0;              // strictly-lower nnz of L
   int64_t n_entries = 0, n_rows = 0, n_packets = 0;   // n_packets = slices
@@ -149,6 +173,11 @@ struct BuildOptions {
 
 // Throws std::runtime_error on malformed input (missing diagonal, not lower triangular, ...).
 void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& out);
+
+// Inverse of the dense lower-triangular diagonal block D (row-major sz x sz, zeros outside the factor's
+// pattern) -- THE arithmetic of the selective inversion, shared by the host analysis and (same order of
+// operations) by the device refresh kernel: column by column, terms with a zero factor skipped.
+void invert_lower_block(int sz, const double* D, double* Dinv);
 
 // Section signs per mode (see kernels.cu)
 enum Mode : int { MODE_APPLY = 0, MODE_RHS = 1, MODE_BACKSUB = 2, MODE_UNIT = 3 };

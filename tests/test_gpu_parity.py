@@ -464,11 +464,25 @@ def test_update_realization_values_only():
     S = fem.B200SchurOperator(pr1.sd, pr1.blocks, pr1.factors, csize=4)
     x = np.random.default_rng(2).standard_normal(pr1.sd.n_gamma)
     y1 = S * x
+    assert S.h.stats()["host_analyses"] == 1 and S.h.stats()["value_refreshes"] == 0
     S.update_realization(pr2.blocks, pr2.factors)
     y2 = S * x
     inner2 = E.ExactInterior(pr2.blocks.A_II)
     assert rel(y2, E.apply_local_schurs(pr2.blocks, inner2, pr2.sd, x)) <= 1e-12
     assert rel(y1, y2) > 1e-3
+    # values only: the symbolic plan (tree cut, levels, slices, tokens) was kept, the stream was rewritten on the
+    # device -- no second host analysis -- and it holds exactly the bits of a stream analysed afresh
+    st = S.h.stats()
+    assert st["host_analyses"] == 1 and st["value_refreshes"] == 1
+    Sfresh = fem.B200SchurOperator(pr2.sd, pr2.blocks, pr2.factors, csize=4)
+    assert np.array_equal(y2, Sfresh * x)
+    assert np.array_equal(S.schur_rhs(pr2.blocks.b_I, pr2.blocks.b_G), Sfresh.schur_rhs(pr2.blocks.b_I, pr2.blocks.b_G))
+    # back to realization 1, then a change of the analysis options: the re-analysis must see the CURRENT values
+    S.update_realization(pr1.blocks, pr1.factors)
+    assert np.array_equal(S * x, y1) and S.h.stats()["value_refreshes"] == 2
+    S.update_realization(pr2.blocks, pr2.factors)
+    S.h.upload_cholesky(0, pr2.factors[0][0], pr2.factors[0][1])      # a re-upload forces a new analysis
+    assert np.array_equal(S * x, y2) and S.h.stats()["host_analyses"] == 2
     # dense S_d of the previous realization must not survive a value update (the reference re-assembles per
     # realization, :667-695): the assembled operator fails loudly until it is assembled again
     S1 = fem.B200SchurOperator(pr1.sd, pr1.blocks, pr1.factors, csize=4)
