@@ -157,6 +157,17 @@ int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, in
 int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t maxit,
                  double rtol, int assembled, int precond, int64_t* it, double* res_norm, kb200_timings* timings);
 
+/* eigpcg(A, b, x, M, nvec, spdim; maxit) of RecyclingKrylovSolvers/eigcg.jl:143-267 and eigdefpcg(A, b, x, M, W, spdim; maxit)
+ * of defcg.jl:337-473, whole solve inside the library: the iterations between two restarts run as one device burst, the
+ * Rayleigh-Ritz restart applies the operator to the spdim basis vectors with the multi-vector stream kernel (eigcg.jl:212-218),
+ * forms V'AV and V (Q Z) with FP64 DMMA kernels (:219, :228) and does the spdim-sized eigen / SVD / rank algebra (:222-227, LAPACK in
+ * the reference) with cuSOLVER on the device.  Return values as the reference: x in place, it, res_norm[0..it), and
+ * V_out = V[:, 1:nvec] (n_gamma x nvec column-major), the approximate least dominant eigenvectors to recycle as W. */
+int kb200_eigpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol,
+                 int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings);
+int kb200_eigdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                    double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings);
+
 /* ---- device-resident vectors and bases (deflated / recycling solvers) ----------------------------- */
 /* defpcg / eigpcg / eigdefpcg (RecyclingKrylovSolvers/defcg.jl:242-308, eigcg.jl:143-267,
  * defcg.jl:337-473) keep their control flow -- including the Rayleigh-Ritz restarts on small dense

@@ -22,7 +22,7 @@ SYMBOLS = [
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_pcg_multi", "kb200_defpcg", "kb200_get_stats", "kb200_get_interface_maps",
     "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
-    "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst",
+    "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst", "kb200_eigpcg", "kb200_eigdefpcg",
 ]
 
 
@@ -41,13 +41,14 @@ class Timings(C.Structure):
 def build(force=False, with_nccl=True):
     """Compile libkrylov_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("api.cu", "plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_tables.h")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "plan.h", "xchg_tables.h", "recycle.cuh")] + \
         [os.path.join(_HERE, "..", "include", "krylov_b200.h")]
     if not force and os.path.exists(LIB_PATH) and \
             all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared"] + srcs + ["-o", LIB_PATH]
+    cmd += ["-lcusolver", "-lcublas"]   # small dense algebra of the Rayleigh-Ritz restarts (csrc/recycle.cuh)
     if with_nccl:
         cmd += ["-DKB200_WITH_NCCL", "-lnccl"]
     subprocess.check_call(cmd)
@@ -63,6 +64,14 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise KB200Error(-100, f"{LIB_PATH} not built: run __graft_entry__.build() "
                                    "(there is no CPU fallback)")
+        # The library links NCCL, cuSOLVER and cuBLAS by soname.  In a Python process that also uses PyTorch (the test /
+        # benchmark harness: torch.distributed for the plumbing) torch's own bundled copies must be the ones that get
+        # loaded -- importing torch after a system libnccl fails on missing symbols -- so torch goes first when it is
+        # installed.  A Julia process has no such concern.
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
         L = C.CDLL(LIB_PATH)
         L.kb200_last_error.restype = C.c_char_p
         _lib = L
@@ -264,6 +273,34 @@ class Handle:
         if isinstance(xin, np.ndarray) and xin is not x:
             xin[...] = x
         return x, it.value, res[:it.value].copy(), tm
+
+    def _recycle(self, fn, b, x, W, nvec, spdim, maxit, rtol, assembled, precond):
+        b = _f64(b)
+        xin = x
+        x = _f64(x)
+        cap = (maxit if maxit else self.n_gamma) + 1
+        res = np.empty(cap)
+        V = np.empty((self.n_gamma, nvec), order="F")
+        it = C.c_int64()
+        tm = Timings()
+        args = [self.h, _p(b, C.c_double), _p(x, C.c_double)]
+        if W is not None:
+            W = np.asfortranarray(W, dtype=np.float64)
+            args.append(_p(W, C.c_double))
+        args += [C.c_int64(nvec), C.c_int64(spdim), C.c_int64(maxit), C.c_double(rtol), int(assembled), int(precond),
+                 C.byref(it), _p(res, C.c_double), _p(V, C.c_double), C.byref(tm)]
+        _chk(fn(*args))
+        if isinstance(xin, np.ndarray) and xin is not x:
+            xin[...] = x
+        return x, it.value, res[:it.value].copy(), V, tm
+
+    def eigpcg(self, b, x, nvec, spdim, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        """kb200_eigpcg: eigcg.jl:143-267, whole solve inside the library.  Returns (x, it, res_norm, V, Timings)."""
+        return self._recycle(lib().kb200_eigpcg, b, x, None, nvec, spdim, maxit, rtol, assembled, precond)
+
+    def eigdefpcg(self, b, x, W, spdim, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        """kb200_eigdefpcg: defcg.jl:337-473, whole solve inside the library."""
+        return self._recycle(lib().kb200_eigdefpcg, b, x, W, np.asarray(W).shape[1], spdim, maxit, rtol, assembled, precond)
 
     def pcg_multi(self, B, X, maxit=0, rtol=1e-7, assembled=False, precond=True):
         B = np.asfortranarray(B, dtype=np.float64)

@@ -1,6 +1,8 @@
 // libkrylov_b200.so: context, uploads, host analysis driver, operators and solvers behind the C ABI
 // declared in include/krylov_b200.h.
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -2302,6 +2304,8 @@ int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const do
   });
 }
 
+#include "recycle.cuh"
+
 int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int64_t W, int64_t AW, int64_t nvec,
                     const double* WtAW, const double* WtAW_inv, const double* WtW, const double* WtW_inv, int64_t m,
                     int64_t V, int64_t vcol0, double rTz, double tol, int64_t it0, int64_t maxit, double* alpha_out,
@@ -2315,23 +2319,12 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
     finalize(h);
     use_device(h);
     Ctx* c = h;
-    const int n = (int)c->n_gamma;
     const int k = (int)nvec;
     m = std::min<int64_t>(m, maxit - it0);
-    if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
-    IterCtx I;
-    I.A = assembled ? OP_SCHUR_DENSE : OP_SCHUR;
-    I.precond = precond;
-    I.x = mat_col(h, wk, 0, 5);
-    I.r = I.x + (size_t)n;
-    I.z = I.x + (size_t)2 * n;
-    I.p = I.x + (size_t)3 * n;
-    I.Ap = I.x + (size_t)4 * n;
-    if (precond) require(c->have_pinv, "kb200_upload_nn_pinv was not called");
-    if (assembled) require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
-    if (V >= 0) I.vbase = mat_col(h, V, vcol0, m);
-    DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2, dhist;
+    DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2;
     Defl D, DR;
+    const Defl* pD = nullptr;
+    const Defl* pDR = nullptr;
     if (k > 0) {
       auto up = [&](DevBuf<double>& b, const double* src) {
         b.alloc((size_t)k * k);
@@ -2348,7 +2341,7 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
       D.Minv = dMinv.p;
       D.y = dy.p;
       D.mu = dmu.p;
-      I.defl = &D;
+      pD = &D;
       if (WtW) {
         up(dM2, WtW);
         up(dM2inv, WtW_inv);
@@ -2359,34 +2352,41 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
         DR.Minv = dM2inv.p;
         DR.y = dy2.p;
         DR.mu = dmu2.p;
-        I.deflR = &DR;
+        pDR = &DR;
       }
     }
-    const size_t nh = (size_t)2 * (size_t)(it0 + m + 2);
-    dhist.alloc(nh);
-    CUDA_TRY(cudaMemsetAsync(dhist.p, 0, nh * 8, c->stream));
-    I.hist = dhist.p;
-    I.k0 = 1;
-    kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, rTz, tol, (int)it0, (int)maxit);
-    c->launches++;
-    run_iterations(c, I, 1, (int)m + 1, nullptr);
-    // one synchronisation per burst: state, alpha/beta history, residual norms
-    std::vector<double> hh(nh), rr((size_t)m);
-    kb::PcgState hs;
-    CUDA_TRY(cudaMemcpyAsync(&hs, c->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(hh.data(), dhist.p, nh * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(rr.data(), c->d_res.p + it0, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    throw_on_fail(hs.fail);
-    const int64_t done = (int64_t)hs.it - it0;
-    require(done >= 0 && done <= m, "internal: burst iteration count out of range");
-    for (int64_t j = 0; j < done; ++j) {
-      alpha_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1)];
-      beta_out[j] = hh[(size_t)2 * (size_t)(it0 + j + 1) + 1];
-      res_out[j] = rr[(size_t)j];
+    BurstOut bo;
+    burst_core(c, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, mat_col(h, wk, 0, 5), pD, pDR, m,
+               V >= 0 ? mat_col(h, V, vcol0, m) : nullptr, rTz, tol, it0, maxit, bo);
+    for (int64_t j = 0; j < bo.done; ++j) {
+      alpha_out[j] = bo.alpha[(size_t)j];
+      beta_out[j] = bo.beta[(size_t)j];
+      res_out[j] = bo.res[(size_t)j];
     }
-    *n_done = done;
-    *rTz_out = hs.rTz;
+    *n_done = bo.done;
+    *rTz_out = bo.rTz;
+  });
+}
+
+int kb200_eigpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol,
+                 int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings) {
+  return guarded([&]() {
+    require(h && b && x && it && res_norm && V_out, "null argument");
+    finalize(h);
+    use_device(h);
+    recycle_solve(h, b, x, nullptr, (int)nvec, (int)spdim, maxit, rtol, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, it, res_norm,
+                  V_out, timings);
+  });
+}
+
+int kb200_eigdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                    double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings) {
+  return guarded([&]() {
+    require(h && b && x && W && it && res_norm && V_out, "null argument");
+    finalize(h);
+    use_device(h);
+    recycle_solve(h, b, x, W, (int)nvec, (int)spdim, maxit, rtol, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, it, res_norm, V_out,
+                  timings);
   });
 }
 

@@ -1,0 +1,502 @@
+// eigpcg / eigdefpcg of RecyclingKrylovSolvers (eigcg.jl:143-267, defcg.jl:337-473) as whole-solve entry points:
+// included by api.cu inside its anonymous namespace (uses Ctx, apply_op, run_iterations, gemm_tn / gemm_nn, ...).
+//
+// Division of labour.  Every n_gamma-sized object (x, r, z, p, Ap, b, tvec, V, AV, W, AW) lives on the GPU.  The
+// iterations between two restarts run as ONE device burst without host synchronisation (burst_core: the plain or
+// deflated recurrence with the V column store and an alpha / beta history from which the host fills the tridiagonal
+// part of V'AV, eigcg.jl:203-244); the restart iteration and the one after it, which touch tvec, are driven from the
+// host over the same kernels.  The Rayleigh-Ritz restart (eigcg.jl:212-231: AV = A V by the multi-vector stream
+// kernel, V'AV and V (Q Z) by the DMMA kernels) does its small dense algebra -- eigenvectors of the spdim x spdim
+// projected matrix, SVD / rank of Y, eigen-decomposition of H -- with cuSOLVER / cuBLAS on the device, the role
+// LAPACK plays in the reference (eigvecs, svd, rank, eigen at eigcg.jl:222-227).
+#pragma once
+// (api.cu includes <cublas_v2.h> and <cusolverDn.h> at file scope)
+
+#define CUSOLVER_TRY(expr)                                                                                   \
+  do {                                                                                                       \
+    cusolverStatus_t s__ = (expr);                                                                           \
+    if (s__ != CUSOLVER_STATUS_SUCCESS)                                                                      \
+      throw KbError(KB200_ERR_CUDA, std::string(#expr) + ": cuSOLVER status " + std::to_string((int)s__));   \
+  } while (0)
+#define CUBLAS_TRY(expr)                                                                                     \
+  do {                                                                                                       \
+    cublasStatus_t s__ = (expr);                                                                             \
+    if (s__ != CUBLAS_STATUS_SUCCESS)                                                                        \
+      throw KbError(KB200_ERR_CUDA, std::string(#expr) + ": cuBLAS status " + std::to_string((int)s__));     \
+  } while (0)
+
+struct DenseLa {
+  cusolverDnHandle_t cs = nullptr;
+  cublasHandle_t cb = nullptr;
+  DevBuf<double> work;
+  DevBuf<int> info;
+  explicit DenseLa(Ctx* c) {
+    CUSOLVER_TRY(cusolverDnCreate(&cs));
+    CUSOLVER_TRY(cusolverDnSetStream(cs, c->stream));
+    CUBLAS_TRY(cublasCreate(&cb));
+    CUBLAS_TRY(cublasSetStream(cb, c->stream));
+    info.alloc(1);
+  }
+  ~DenseLa() {
+    if (cs) cusolverDnDestroy(cs);
+    if (cb) cublasDestroy(cb);
+  }
+  void check_info(Ctx* c, const char* what) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h != 0) throw KbError(KB200_ERR_INTERNAL, std::string(what) + " failed (info = " + std::to_string(h) + ")");
+  }
+  // eigen-decomposition of the symmetric m x m matrix in A (upper triangle read, like Julia's Symmetric()):
+  // eigenvalues ascending in w, eigenvectors overwrite A
+  void syevd(Ctx* c, int m, double* A, int lda, double* w) {
+    int lwork = 0;
+    CUSOLVER_TRY(cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m, A, lda, w, &lwork));
+    if ((int64_t)work.n < lwork) work.alloc((size_t)lwork);
+    CUSOLVER_TRY(cusolverDnDsyevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m, A, lda, w, work.p, lwork, info.p));
+    check_info(c, "syevd");
+  }
+};
+
+// Restart algebra of eigcg.jl:220-228 / defcg.jl:425-432: Tm (m x m, host, column-major, symmetric) -> Q Z (m x nev,
+// device), eigenvalues of H (host), nev.
+static int rayleigh_ritz(Ctx* c, DenseLa& la, const std::vector<double>& Tm, int m, int nvec, DevBuf<double>& dQZ,
+                         std::vector<double>& vals) {
+  cudaStream_t s = c->stream;
+  const int ny = 2 * nvec;
+  DevBuf<double> dT, dE1, dE2, dY, dS, dU, dVT, dQ, dTQ, dH, dw;
+  dT.alloc((size_t)m * m);
+  dE1.alloc((size_t)m * m);
+  dE2.alloc((size_t)std::max(1, m - 1) * std::max(1, m - 1));
+  dY.alloc((size_t)m * ny);
+  dw.alloc((size_t)std::max(m, ny));
+  CUDA_TRY(cudaMemcpyAsync(dT.p, Tm.data(), (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(dE1.p, dT.p, (size_t)m * m * 8, cudaMemcpyDeviceToDevice, s));
+  la.syevd(c, m, dE1.p, m, dw.p);                                        // eigvecs(Tm)
+  CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)m * ny * 8, s));
+  CUDA_TRY(cudaMemcpyAsync(dY.p, dE1.p, (size_t)m * nvec * 8, cudaMemcpyDeviceToDevice, s));   // Y[:, 1:nvec]
+  if (m > 1) {
+    CUDA_TRY(cudaMemcpy2DAsync(dE2.p, (size_t)(m - 1) * 8, dT.p, (size_t)m * 8, (size_t)(m - 1) * 8, (size_t)(m - 1),
+                               cudaMemcpyDeviceToDevice, s));           // Tm[1:m-1, 1:m-1]
+    la.syevd(c, m - 1, dE2.p, m - 1, dw.p);
+    const int take = std::min(nvec, m - 1);
+    CUDA_TRY(cudaMemcpy2DAsync(dY.p + (size_t)nvec * m, (size_t)m * 8, dE2.p, (size_t)(m - 1) * 8, (size_t)(m - 1) * 8, (size_t)take,
+                               cudaMemcpyDeviceToDevice, s));           // Y[1:m-1, nvec+1:end], last row zero
+  }
+  // svd(Y): left singular vectors and singular values; gesvd wants rows >= columns
+  const int mn = std::min(m, ny);
+  dS.alloc((size_t)mn);
+  dQ.alloc((size_t)m * mn);
+  const double one = 1.0, zero = 0.0;
+  if (m >= ny) {
+    dU.alloc((size_t)m * ny);
+    int lwork = 0;
+    CUSOLVER_TRY(cusolverDnDgesvd_bufferSize(la.cs, m, ny, &lwork));
+    if ((int64_t)la.work.n < lwork) la.work.alloc((size_t)lwork);
+    CUSOLVER_TRY(cusolverDnDgesvd(la.cs, 'S', 'N', m, ny, dY.p, m, dS.p, dU.p, m, nullptr, ny, la.work.p, lwork, nullptr, la.info.p));
+    la.check_info(c, "gesvd");
+    CUDA_TRY(cudaMemcpyAsync(dQ.p, dU.p, (size_t)m * mn * 8, cudaMemcpyDeviceToDevice, s));
+  } else {
+    // Y' (ny x m) = U' S V'^T  =>  left singular vectors of Y are the columns of V' = (VT)^T
+    DevBuf<double> dYt;
+    dYt.alloc((size_t)ny * m);
+    CUBLAS_TRY(cublasDgeam(la.cb, CUBLAS_OP_T, CUBLAS_OP_N, ny, m, &one, dY.p, m, &zero, dYt.p, ny, dYt.p, ny));
+    dVT.alloc((size_t)m * m);
+    int lwork = 0;
+    CUSOLVER_TRY(cusolverDnDgesvd_bufferSize(la.cs, ny, m, &lwork));
+    if ((int64_t)la.work.n < lwork) la.work.alloc((size_t)lwork);
+    CUSOLVER_TRY(cusolverDnDgesvd(la.cs, 'N', 'S', ny, m, dYt.p, ny, dS.p, nullptr, ny, dVT.p, m, la.work.p, lwork, nullptr, la.info.p));
+    la.check_info(c, "gesvd");
+    CUBLAS_TRY(cublasDgeam(la.cb, CUBLAS_OP_T, CUBLAS_OP_N, m, m, &one, dVT.p, m, &zero, dQ.p, m, dQ.p, m));
+  }
+  std::vector<double> sv((size_t)mn);
+  CUDA_TRY(cudaMemcpyAsync(sv.data(), dS.p, (size_t)mn * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  // LinearAlgebra.rank default: singular values above min(size) * eps * sigma_max
+  int nev = 0;
+  if (mn > 0 && sv[0] > 0.0) {
+    const double thr = (double)mn * 2.220446049250313e-16 * sv[0];
+    for (int i = 0; i < mn; ++i) nev += sv[i] > thr;
+  }
+  if (nev < 1) throw KbError(KB200_ERR_INTERNAL, "Rayleigh-Ritz restart: Y has rank 0");
+  // H = Q' (Tm Q), Q = U[:, 1:nev]; vals, Z = eigen(Symmetric(H)); Q Z
+  dTQ.alloc((size_t)m * nev);
+  dH.alloc((size_t)nev * nev);
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, m, &one, dT.p, m, dQ.p, m, &zero, dTQ.p, m));
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_T, CUBLAS_OP_N, nev, nev, m, &one, dQ.p, m, dTQ.p, m, &zero, dH.p, nev));
+  la.syevd(c, nev, dH.p, nev, dw.p);
+  vals.resize((size_t)nev);
+  CUDA_TRY(cudaMemcpyAsync(vals.data(), dw.p, (size_t)nev * 8, cudaMemcpyDeviceToHost, s));
+  dQZ.alloc((size_t)m * nev);
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, nev, &one, dQ.p, m, dH.p, nev, &zero, dQZ.p, m));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return nev;
+}
+
+// Dense LU with partial pivoting of a small matrix (host): `WtAW \ .` of defcg.jl:272-274, :284, :301, :407
+struct SmallLu {
+  int k = 0;
+  std::vector<double> lu;
+  std::vector<int> piv;
+  void factor(int kk, const std::vector<double>& A) {
+    k = kk;
+    lu = A;
+    piv.resize((size_t)k);
+    auto a = [&](int i, int j) -> double& { return lu[i + (size_t)j * k]; };
+    for (int c0 = 0; c0 < k; ++c0) {
+      int p = c0;
+      for (int i = c0 + 1; i < k; ++i)
+        if (std::fabs(a(i, c0)) > std::fabs(a(p, c0))) p = i;
+      piv[c0] = p;
+      if (a(p, c0) == 0.0) throw KbError(KB200_ERR_INPUT, "deflation: W' A W is singular (linearly dependent vectors)");
+      if (p != c0)
+        for (int j = 0; j < k; ++j) std::swap(a(p, j), a(c0, j));
+      for (int i = c0 + 1; i < k; ++i) {
+        const double f = a(i, c0) / a(c0, c0);
+        a(i, c0) = f;
+        if (f != 0.0)
+          for (int j = c0 + 1; j < k; ++j) a(i, j) -= f * a(c0, j);
+      }
+    }
+  }
+  void solve(std::vector<double>& b) const {
+    auto a = [&](int i, int j) { return lu[i + (size_t)j * k]; };
+    for (int c0 = 0; c0 < k; ++c0) std::swap(b[c0], b[piv[c0]]);
+    for (int i = 1; i < k; ++i) {
+      double sacc = b[i];
+      for (int j = 0; j < i; ++j) sacc -= a(i, j) * b[j];
+      b[i] = sacc;
+    }
+    for (int i = k - 1; i >= 0; --i) {
+      double sacc = b[i];
+      for (int j = i + 1; j < k; ++j) sacc -= a(i, j) * b[j];
+      b[i] = sacc / a(i, i);
+    }
+  }
+};
+
+// Work vectors of one recycling solve: columns of one device block
+struct RecycleVecs {
+  enum { X = 0, R, Z, P, AP, B, T, NCOL };
+  Ctx* c;
+  int n;
+  DevBuf<double> wk;
+  OpKind A;
+  int precond;
+  RecycleVecs(Ctx* ctx, OpKind a, int pre) : c(ctx), n((int)ctx->n_gamma), A(a), precond(pre) {
+    wk.alloc((size_t)n * NCOL);
+    CUDA_TRY(cudaMemsetAsync(wk.p, 0, (size_t)n * NCOL * 8, c->stream));
+  }
+  double* col(int j) { return wk.p + (size_t)j * n; }
+  void applyA(int src, int dst) { apply_op(c, A, col(src), col(dst), nullptr, nullptr, nullptr, 0, nullptr); }
+  void applyM(int src, int dst) {
+    if (precond) apply_op(c, OP_NN, col(src), col(dst), nullptr, nullptr, nullptr, 0, nullptr);
+    else CUDA_TRY(cudaMemcpyAsync(col(dst), col(src), (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  void axpby(double a, const double* x, double b, double* y) {
+    kb::axpby_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, a, x, b, y);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  void axpby(double a, int x, double b, int y) { axpby(a, col(x), b, col(y)); }
+  // y_host = A[:, 0:k]' x
+  std::vector<double> gemv_t(const double* Am, int k, const double* x) {
+    if ((int64_t)c->d_small.n < k) c->d_small.alloc((size_t)k);
+    kb::gemv_t_kernel<<<(unsigned)k, c->vec_threads, 0, c->stream>>>(n, Am, n, x, c->d_small.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    std::vector<double> y((size_t)k);
+    CUDA_TRY(cudaMemcpyAsync(y.data(), c->d_small.p, (size_t)k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return y;
+  }
+  double dot(int x, int y) { return gemv_t(col(x), 1, col(y))[0]; }
+  // y = b y + a A[:, 0:k] mu
+  void gemv_n(double a, const double* Am, int k, const std::vector<double>& mu, double b, double* y) {
+    if ((int64_t)c->d_small2.n < k) c->d_small2.alloc((size_t)k);
+    CUDA_TRY(cudaMemcpyAsync(c->d_small2.p, mu.data(), (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+    kb::gemv_n_kernel<<<c->nb, c->vec_threads, (size_t)k * 8, c->stream>>>(n, k, a, Am, n, c->d_small2.p, b, y);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // mu is a host temporary
+  }
+  void residual() {  // r = b - A x
+    applyA(X, AP);
+    axpby(1.0, B, 0.0, R);
+    axpby(-1.0, AP, 1.0, R);
+  }
+};
+
+// C (ka x kb, host, column-major) = A[:, 0:ka]' B[:, 0:kb]
+static std::vector<double> gemm_tn_host(Ctx* c, int ka, int kb_, const double* A, const double* B) {
+  if ((int64_t)c->d_small.n < (int64_t)ka * kb_) c->d_small.alloc((size_t)ka * kb_);
+  gemm_tn(c, ka, kb_, A, B, c->d_small.p);
+  std::vector<double> C((size_t)ka * kb_);
+  CUDA_TRY(cudaMemcpyAsync(C.data(), c->d_small.p, C.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return C;
+}
+
+struct BurstOut {
+  int64_t done = 0;
+  double rTz = 0.0;
+  std::vector<double> alpha, beta, res;
+};
+
+// Up to m iterations of the (deflated) recurrence on the device without host synchronisation (kb200_pcg_burst).
+static void burst_core(Ctx* c, OpKind A, int precond, double* wk5, const Defl* D, const Defl* DR, int64_t m, double* vbase,
+                       double rTz, double tol, int64_t it0, int64_t maxit, BurstOut& out) {
+  const int n = (int)c->n_gamma;
+  m = std::min<int64_t>(m, maxit - it0);
+  if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
+  IterCtx I;
+  I.A = A;
+  I.precond = precond;
+  I.x = wk5;
+  I.r = wk5 + (size_t)n;
+  I.z = wk5 + (size_t)2 * n;
+  I.p = wk5 + (size_t)3 * n;
+  I.Ap = wk5 + (size_t)4 * n;
+  if (precond) require(c->have_pinv, "kb200_upload_nn_pinv was not called");
+  if (A == OP_SCHUR_DENSE) require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
+  I.vbase = vbase;
+  I.defl = D;
+  I.deflR = DR;
+  DevBuf<double> dhist;
+  const size_t nh = (size_t)2 * (size_t)(it0 + m + 2);
+  dhist.alloc(nh);
+  CUDA_TRY(cudaMemsetAsync(dhist.p, 0, nh * 8, c->stream));
+  I.hist = dhist.p;
+  I.k0 = 1;
+  kb::pcg_burst_init_kernel<<<1, 1, 0, c->stream>>>(c->d_state.p, rTz, tol, (int)it0, (int)maxit);
+  c->launches++;
+  run_iterations(c, I, 1, (int)m + 1, nullptr);
+  // one synchronisation per burst: state, alpha/beta history, residual norms
+  std::vector<double> hh(nh), rr((size_t)m);
+  kb::PcgState hs;
+  CUDA_TRY(cudaMemcpyAsync(&hs, c->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(hh.data(), dhist.p, nh * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(rr.data(), c->d_res.p + it0, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  throw_on_fail(hs.fail);
+  const int64_t done = (int64_t)hs.it - it0;
+  require(done >= 0 && done <= m, "internal: burst iteration count out of range");
+  out.done = done;
+  out.rTz = hs.rTz;
+  out.alpha.resize((size_t)done);
+  out.beta.resize((size_t)done);
+  out.res.resize((size_t)done);
+  for (int64_t j = 0; j < done; ++j) {
+    out.alpha[j] = hh[(size_t)2 * (size_t)(it0 + j + 1)];
+    out.beta[j] = hh[(size_t)2 * (size_t)(it0 + j + 1) + 1];
+    out.res[j] = rr[(size_t)j];
+  }
+}
+
+// Symmetric(U): the upper triangle of the spdim x spdim accumulator (leading block m) as a full symmetric matrix
+static std::vector<double> sym_upper(const std::vector<double>& VtAV, int ld, int m) {
+  std::vector<double> T((size_t)m * m);
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i <= j; ++i) T[i + (size_t)j * m] = T[j + (size_t)i * m] = VtAV[i + (size_t)j * ld];
+  return T;
+}
+
+// eigpcg (W == nullptr, eigcg.jl:143-267) / eigdefpcg (W given, defcg.jl:337-473).  b, x, W, V_out: host.
+static void recycle_solve(Ctx* c, const double* b, double* x, const double* W, int nvec, int spdim, int64_t maxit, double rtol,
+                          OpKind A, int precond, int64_t* it_out, double* res_norm, double* V_out, kb200_timings* tm) {
+  const int n = (int)c->n_gamma;
+  const bool defl = W != nullptr;
+  require(nvec >= 1 && spdim > nvec && spdim <= 4096, "need 1 <= nvec < spdim <= 4096");
+  require(!defl || spdim > nvec + 1, "eigdefpcg needs spdim > nvec + 1");
+  if (maxit == 0) maxit = n;
+  require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+  kb200_timings T;
+  std::memset(&T, 0, sizeof(T));
+  const int64_t launches0 = c->launches;
+  KernelTimer kt(c);
+  DenseLa la(c);
+  RecycleVecs v(c, A, precond);
+  using RV = RecycleVecs;
+  DevBuf<double> dV, dAV, dW, dAW;
+  dV.alloc((size_t)n * spdim);
+  CUDA_TRY(cudaMemsetAsync(dV.p, 0, (size_t)n * spdim * 8, c->stream));
+  auto Vcol = [&](int j) { return dV.p + (size_t)j * n; };
+  h2d(c, v.col(RV::B), b, n, &T);
+  h2d(c, v.col(RV::X), x, n, &T);
+  CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+  std::vector<double> VtAV((size_t)spdim * spdim, 0.0);
+  auto VA = [&](int i, int j) -> double& { return VtAV[i + (size_t)j * spdim]; };
+  std::vector<double> WtAW, WtW, WtAW_inv, WtW_inv;
+  SmallLu luA, luW;
+  DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2;
+  Defl D, DR;
+  if (defl) {
+    dW.alloc((size_t)n * nvec);
+    dAW.alloc((size_t)n * nvec);
+    h2d(c, dW.p, W, (int64_t)n * nvec, &T);
+    apply_op_multi(c, A, dW.p, dAW.p, nvec, MultiCtx(), &kt);                      // WtA' = A W        defcg.jl:357-360
+    WtAW = gemm_tn_host(c, nvec, nvec, dAW.p, dW.p);
+    WtW = gemm_tn_host(c, nvec, nvec, dW.p, dW.p);
+    luA.factor(nvec, WtAW);
+    luW.factor(nvec, WtW);
+    invert_small(nvec, WtAW, WtAW_inv);
+    invert_small(nvec, WtW, WtW_inv);
+    auto up = [&](DevBuf<double>& buf, const std::vector<double>& src) {
+      buf.alloc(src.size());
+      CUDA_TRY(cudaMemcpyAsync(buf.p, src.data(), src.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    };
+    up(dM, WtAW);
+    up(dMinv, WtAW_inv);
+    up(dM2, WtW);
+    up(dM2inv, WtW_inv);
+    dy.alloc(nvec);
+    dmu.alloc(nvec);
+    dy2.alloc(nvec);
+    dmu2.alloc(nvec);
+    D.k = nvec;
+    D.W = dW.p;
+    D.AW = dAW.p;
+    D.M = dM.p;
+    D.Minv = dMinv.p;
+    D.y = dy.p;
+    D.mu = dmu.p;
+    DR = D;
+    DR.M = dM2.p;
+    DR.Minv = dM2inv.p;
+    DR.y = dy2.p;
+    DR.mu = dmu2.p;
+    v.residual();                                                                   // x += W (WtAW \ W'r)  :362-366
+    std::vector<double> mu = v.gemv_t(dW.p, nvec, v.col(RV::R));
+    luA.solve(mu);
+    v.gemv_n(1.0, dW.p, nvec, mu, 1.0, v.col(RV::X));
+  } else {
+    dAV.alloc((size_t)n * spdim);
+  }
+  std::vector<double> res((size_t)maxit + 1);
+  int64_t it = 1;
+  v.residual();
+  double rTr = v.dot(RV::R, RV::R);
+  v.applyM(RV::R, RV::Z);
+  double rTz = v.dot(RV::R, RV::Z);
+  v.axpby(1.0, RV::Z, 0.0, RV::P);
+  if (defl) {                                                                       // p = z - W (WtAW \ WtA z)   :380-382
+    std::vector<double> mu = v.gemv_t(dAW.p, nvec, v.col(RV::Z));
+    luA.solve(mu);
+    v.gemv_n(-1.0, dW.p, nvec, mu, 1.0, v.col(RV::P));
+  }
+  res[0] = std::sqrt(rTr);
+  int ivec = 0;
+  bool first_restart = true, just_restarted = false;
+  if (defl) {
+    for (int j = 0; j < nvec; ++j)
+      for (int i = 0; i < nvec; ++i) VA(i, j) = WtAW[i + (size_t)j * nvec];        // :390
+    CUDA_TRY(cudaMemcpyAsync(dV.p, dW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));   // V[:, 1:nvec] = W
+    ivec = nvec;
+  }
+  v.axpby(1.0 / std::sqrt(rTz), v.col(RV::Z), 0.0, Vcol(ivec));                     // V[:, ivec] = z / sqrt(rTz)
+  double hlpr = 0.0;
+  double bb = 0.0;
+  for (int i = 0; i < n; ++i) bb += b[i] * b[i];
+  const double tol = rtol * std::sqrt(bb);                                          // eps * norm2(b)
+  auto restart = [&](int m) -> int {   // Rayleigh-Ritz on the leading m x m block; V[:, 1:nev] = V (Q Z)
+    DevBuf<double> dQZ;
+    std::vector<double> vals;
+    const int nev = rayleigh_ritz(c, la, sym_upper(VtAV, spdim, m), m, nvec, dQZ, vals);
+    gemm_nn(c, m, nev, dV.p, dQZ.p, dV.p);
+    std::fill(VtAV.begin(), VtAV.end(), 0.0);
+    for (int j = 0; j < nev; ++j) VA(j, j) = vals[j];
+    return nev;
+  };
+  while (it < maxit && res[it - 1] > tol) {                                         // eigcg.jl:185 / defcg.jl:400
+    const bool can_burst = defl ? (ivec < spdim - 1) : (!just_restarted && ivec < spdim - 1);
+    if (can_burst) {
+      BurstOut bo;
+      burst_core(c, A, precond, v.col(RV::X), defl ? &D : nullptr, defl ? &DR : nullptr, spdim - 1 - ivec, Vcol(ivec + 1), rTz, tol, it,
+                 maxit, bo);
+      for (int64_t j = 0; j < bo.done; ++j) {
+        it += 1;
+        res[it - 1] = bo.res[j];
+        VA(ivec, ivec) += 1.0 / bo.alpha[j];                                        // :206 / :417
+        ivec += 1;                                                                  // V[:, ivec] stored by the device
+        VA(ivec - 1, ivec) = -std::sqrt(bo.beta[j]) / bo.alpha[j];
+        VA(ivec, ivec) = bo.beta[j] / bo.alpha[j];
+      }
+      rTz = bo.rTz;
+      if (bo.done) just_restarted = false;
+      continue;
+    }
+    v.applyA(RV::P, RV::AP);
+    const double d = v.dot(RV::P, RV::AP);
+    if (!(d > 0.0)) throw KbError(KB200_ERR_NOT_SPD, "p'Ap <= 0 encountered: operator is not positive definite along p");
+    const double alpha = rTz / d;
+    double beta = 1.0 / rTz;
+    v.axpby(alpha, RV::P, 1.0, RV::X);
+    v.axpby(-alpha, RV::AP, 1.0, RV::R);
+    if (defl) {                                                                     // r -= W (WtW \ W'r)   defcg.jl:407
+      std::vector<double> mu2 = v.gemv_t(dW.p, nvec, v.col(RV::R));
+      luW.solve(mu2);
+      v.gemv_n(-1.0, dW.p, nvec, mu2, 1.0, v.col(RV::R));
+    }
+    rTr = v.dot(RV::R, RV::R);
+    v.applyM(RV::R, RV::Z);
+    if (!defl && just_restarted) hlpr = std::sqrt(rTz);                             // eigcg.jl:194-196
+    rTz = v.dot(RV::R, RV::Z);
+    beta *= rTz;
+    if (!defl && ivec == spdim - 1) v.axpby(-beta, RV::AP, 1.0, RV::T);             // tvec -= beta Ap   :199-201
+    v.axpby(1.0, RV::Z, beta, RV::P);
+    if (defl) {
+      std::vector<double> mu = v.gemv_t(dAW.p, nvec, v.col(RV::Z));
+      luA.solve(mu);
+      v.gemv_n(-1.0, dW.p, nvec, mu, 1.0, v.col(RV::P));
+    }
+    it += 1;
+    res[it - 1] = std::sqrt(rTr);
+    VA(ivec, ivec) += 1.0 / alpha;                                                  // :206 / :417
+    if (!defl && just_restarted) {
+      v.axpby(1.0, RV::AP, 1.0, RV::T);                                             // tvec += Ap        :208
+      const int nev = ivec;
+      std::vector<double> col = v.gemv_t(dV.p, nev, v.col(RV::T));                  // :210
+      for (int i = 0; i < nev; ++i) VA(i, ivec) = col[i] / hlpr;
+      just_restarted = false;
+    }
+    if (ivec == spdim - 1) {                                                        // restart        :214 / :419
+      if (!defl) {
+        apply_op_multi(c, A, dV.p, dAV.p, spdim, MultiCtx(), &kt);                  // AV = A V        :215-218
+        VtAV = gemm_tn_host(c, spdim, spdim, dV.p, dAV.p);                          // V'AV            :219
+      } else if (first_restart) {
+        std::vector<double> blk = gemm_tn_host(c, nvec, spdim - nvec, dAW.p, Vcol(nvec));   // WtA V   defcg.jl:421-423
+        for (int j = 0; j < spdim - nvec; ++j)
+          for (int i = 0; i < nvec; ++i) VA(i, nvec + j) = blk[i + (size_t)j * nvec];
+        first_restart = false;
+      }
+      const int nev = restart(spdim);
+      ivec = nev;
+      v.axpby(1.0 / std::sqrt(rTz), v.col(RV::Z), 0.0, Vcol(ivec));
+      VA(ivec, ivec) = beta / alpha;
+      if (!defl) v.axpby(-beta, RV::AP, 0.0, RV::T);                                // tvec = -beta Ap   :240
+      just_restarted = true;
+    } else {
+      just_restarted = false;
+      ivec += 1;
+      v.axpby(1.0 / std::sqrt(rTz), v.col(RV::Z), 0.0, Vcol(ivec));
+      VA(ivec - 1, ivec) = -std::sqrt(beta) / alpha;
+      VA(ivec, ivec) = beta / alpha;
+    }
+  }
+  if (!just_restarted && ivec + 1 > nvec) {                                         // eigcg.jl:251-264 / defcg.jl:450-466
+    const int m = ivec;
+    if (defl && first_restart && m > nvec) {
+      std::vector<double> blk = gemm_tn_host(c, nvec, m - nvec, dAW.p, Vcol(nvec));
+      for (int j = 0; j < m - nvec; ++j)
+        for (int i = 0; i < nvec; ++i) VA(i, nvec + j) = blk[i + (size_t)j * nvec];
+    }
+    if (m >= 2) restart(m);
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+  d2h(c, x, v.col(RV::X), n, &T);
+  d2h(c, V_out, dV.p, (int64_t)n * nvec, &T);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  std::copy(res.begin(), res.begin() + it, res_norm);
+  *it_out = it;
+  finish_timings(c, kt, T, launches0, tm);
+}

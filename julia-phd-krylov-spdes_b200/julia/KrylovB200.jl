@@ -175,322 +175,87 @@ cg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}; maxit::Int=0) =
 
 
 # ---------------------------------------------------------------------------------------------------
-# Deflated / recycling solvers (defcg.jl:242-308, eigcg.jl:143-267, defcg.jl:337-473).
-# The reference's loops are kept; every n_Γ-sized array becomes a column of a device block
-# (kb200_mat_alloc) and the BLAS-1/2 calls become kb200_op_* calls; eigpcg / eigdefpcg run the
-# iterations between two restarts as device bursts (kb200_pcg_burst) and keep the reference's own LAPACK
-# lines for the Rayleigh-Ritz restarts (eigvecs / rank / svd / eigen, eigcg.jl:220-228) on the small host
-# matrix VtAV.  `defpcg` here is the host-driven pattern; kb200_defpcg (one ccall) runs it on the device.
+# Deflated / recycling solvers (defcg.jl:242-308, eigcg.jl:143-267, defcg.jl:337-473): ONE ccall each.
+# The whole solve runs inside libkrylov_b200.so -- device bursts between the restarts, AV = A V with the
+# multi-vector stream kernel, V'AV and V (Q Z) on FP64 tensor cores, the spdim-sized eigen / svd / rank algebra
+# of eigcg.jl:222-227 with cuSOLVER.  Signatures and return tuples are RecyclingKrylovSolvers' own.
 # ---------------------------------------------------------------------------------------------------
-module DeviceOps
-using ..KrylovB200: LIB, chk, B200SchurOperator
-mat_alloc(S, ncols) = (id = Ref{Int64}(0); chk(ccall((:kb200_mat_alloc, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}), S.h, ncols, id)); id[])
-mat_free(S, id) = chk(ccall((:kb200_mat_free, LIB), Cint, (Ptr{Cvoid}, Int64), S.h, id))
-mat_set(S, id, col0, A::VecOrMat{Float64}) = chk(ccall((:kb200_mat_set, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}), S.h, id, col0, size(A, 2), A))
-mat_get!(out::VecOrMat{Float64}, S, id, col0) = (chk(ccall((:kb200_mat_get, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}), S.h, id, col0, size(out, 2), out)); out)
-apply(S, which, src, scol, dst, dcol, ncols=1) = chk(ccall((:kb200_op_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Int64), S.h, which, src, scol, dst, dcol, ncols))
-axpby(S, a, x, xc, b, y, yc) = chk(ccall((:kb200_op_axpby, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Float64, Int64, Int64), S.h, a, x, xc, b, y, yc))
-dot(S, x, xc, y, yc) = (o = Ref{Float64}(0); chk(ccall((:kb200_op_dot, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ref{Float64}), S.h, x, xc, y, yc, o)); o[])
-gemv_t(S, A, col0, k, x, xc) = (y = Vector{Float64}(undef, k); chk(ccall((:kb200_op_gemv_t, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}), S.h, A, col0, k, x, xc, y)); y)
-gemv_n(S, a, A, col0, k, mu, b, y, yc) = chk(ccall((:kb200_op_gemv_n, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Int64, Ptr{Float64}, Float64, Int64, Int64), S.h, a, A, col0, k, mu, b, y, yc))
-gemm_tn(S, A, ca, ka, B, cb, kb) = (C = Matrix{Float64}(undef, ka, kb); chk(ccall((:kb200_op_gemm_tn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Float64}), S.h, A, ca, ka, B, cb, kb, C)); C)
-gemm_nn(S, A, ca, ka, Q::Matrix{Float64}, C, cc) = chk(ccall((:kb200_op_gemm_nn, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Int64), S.h, A, ca, ka, Q, size(Q, 2), C, cc))
-# Up to m iterations of the (deflated) recurrence on the device without host synchronisation: the body
-# of the loops eigcg.jl:185-246 / defcg.jl:400-448 between two restarts (see ../solvers.py: eigpcg,
-# eigdefpcg).  Returns (n_done, alpha, beta, res, rTz); V[:, vcol0 + j] receives z / sqrt(rTz).
-function pcg_burst(S, precond::Bool, wk, m, rTz, tol, it0, maxit; V=-1, vcol0=0, W=-1, AW=-1, nvec=0,
-                   WtAW::Union{Matrix{Float64},Nothing}=nothing, WtW::Union{Matrix{Float64},Nothing}=nothing)
-  al = Vector{Float64}(undef, m); be = similar(al); rs = similar(al)
-  nd = Ref{Int64}(0); rz = Ref{Float64}(0)
-  ptr(A) = A === nothing ? Ptr{Float64}(C_NULL) : pointer(A)
-  A1i = WtAW === nothing ? nothing : inv(WtAW); A2i = WtW === nothing ? nothing : inv(WtW)
-  GC.@preserve WtAW WtW A1i A2i chk(ccall((:kb200_pcg_burst, LIB), Cint,
-      (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64,
-       Int64, Int64, Float64, Float64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Float64}),
-      S.h, S.assembled ? 1 : 0, precond ? 1 : 0, wk, W, AW, nvec, ptr(WtAW), ptr(A1i), ptr(WtW), ptr(A2i), m,
-      V, vcol0, rTz, tol, it0, maxit, al, be, rs, nd, rz))
-  k = nd[]
-  return k, al[1:k], be[1:k], rs[1:k], rz[]
-end
-end
-
 """
     defpcg(S, b, x, W, M; maxit=0) -> (x, it, res_norm)          # defcg.jl:242-308
 """
 function defpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, W::Matrix{Float64},
                 M::Union{B200NeumannNeumann,Nothing}; maxit::Int=0)
-  D = DeviceOps
-  n, nvec = size(W)
-  op = S.assembled ? 1 : 0
-  X, R, Z, P, AP, B = 0, 1, 2, 3, 4, 5                       # columns of the work block (0-based)
-  wk = D.mat_alloc(S, 7); Wd = D.mat_alloc(S, nvec); AWd = D.mat_alloc(S, nvec)
-  try
-    D.mat_set(S, Wd, 0, W); D.mat_set(S, wk, B, b); D.mat_set(S, wk, X, x)
-    D.apply(S, op, Wd, 0, AWd, 0, nvec)                       # WtA[ivec, :] .= A * W[:, ivec]   (:261-264)
-    WtAW = D.gemm_tn(S, AWd, 0, nvec, Wd, 0, nvec)            # :268
-    resid!() = (D.apply(S, op, wk, X, wk, AP); D.axpby(S, 1.0, wk, B, 0.0, wk, R); D.axpby(S, -1.0, wk, AP, 1.0, wk, R))
-    precond!() = M === nothing ? D.axpby(S, 1.0, wk, R, 0.0, wk, Z) : D.apply(S, 2, wk, R, wk, Z)
-    resid!()
-    mu = WtAW \ D.gemv_t(S, Wd, 0, nvec, wk, R)               # :272-274
-    D.gemv_n(S, 1.0, Wd, 0, nvec, mu, 1.0, wk, X)             # x .+= W * mu
-    maxit == 0 ? maxit = n : nothing
-    res_norm = Vector{Float64}(undef, maxit + 1)
-    it = 1
-    resid!()
-    rTr = D.dot(S, wk, R, wk, R); res_norm[it] = sqrt(rTr)
-    precond!()
-    rTz = D.dot(S, wk, R, wk, Z)
-    mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)              # :284
-    D.axpby(S, 1.0, wk, Z, 0.0, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)
-    tol = eps_rtol * norm(b)
-    while (it < maxit) && (res_norm[it] > tol)                # :290
-      D.apply(S, op, wk, P, wk, AP)
-      d = D.dot(S, wk, P, wk, AP)
-      alpha = rTz / d
-      beta = 1. / rTz
-      D.axpby(S, alpha, wk, P, 1.0, wk, X)
-      D.axpby(S, -alpha, wk, AP, 1.0, wk, R)
-      rTr = D.dot(S, wk, R, wk, R)
-      precond!()
-      rTz = D.dot(S, wk, R, wk, Z)
-      beta *= rTz
-      mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)            # :301
-      D.axpby(S, 1.0, wk, Z, beta, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)   # :302
-      it += 1
-      res_norm[it] = sqrt(rTr)
-    end
-    D.mat_get!(x, S, wk, X)
-    return x, it, res_norm[1:it]
-  finally
-    D.mat_free(S, wk); D.mat_free(S, Wd); D.mat_free(S, AWd)
-  end
-end
-export defpcg
-
-# Restart algebra of eigcg.jl:220-228 / defcg.jl:425-432, the reference's own LAPACK lines on the small host
-# matrix: returns (Q*Z, vals, nev).
-function rayleigh_ritz(Tm::Symmetric{Float64,Matrix{Float64}}, nvec::Int)
-  m = size(Tm, 1)
-  Y = zeros(m, 2 * nvec)
-  Y[:, 1:nvec] = eigvecs(Tm)[:, 1:nvec]
-  Y[1:m-1, nvec+1:end] = eigvecs(Symmetric(Tm[1:m-1, 1:m-1]))[:, 1:nvec]
-  nev = rank(Y)
-  Q = svd(Y).U[:, 1:nev]
-  H = Q' * (Tm * Q)
-  vals, Z = eigen(Symmetric(H))
-  return Q * Z, vals, nev
+  cap = (maxit == 0 ? S.N : maxit) + 1
+  res = Vector{Float64}(undef, cap); it = Ref{Int64}(0); tm = Timings()
+  chk(ccall((:kb200_defpcg, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Float64, Cint, Cint, Ref{Int64}, Ptr{Float64}, Ref{Timings}),
+            S.h, b, x, W, size(W, 2), maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1, it, res, tm))
+  return x, Int(it[]), res[1:it[]]
 end
 
 """
     eigpcg(S, b, x, M, nvec, spdim; maxit=0) -> (x, it, res_norm, V[:, 1:nvec])      # eigcg.jl:143-267
-
-The reference's loop with every n_Γ-sized array on the device.  The iterations between two restarts are
-plain PCG steps that append a column to V and two entries to V'AV: they run as ONE device burst
-(kb200_pcg_burst, no host synchronisation inside); the restart iteration and the one after it, which
-touch `tvec` and the Rayleigh-Ritz algebra, are driven from here.  Mirror of ../solvers.py::eigpcg
-(tested against the oracle on the GPU and, through a numpy twin of the block API, on the CPU).
 """
-function eigpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64},
-                M::Union{B200NeumannNeumann,Nothing}, nvec::Int, spdim::Int; maxit::Int=0)
-  D = DeviceOps
-  n = length(x)
-  op = S.assembled ? 1 : 0
-  X, R, Z, P, AP, B, T = 0, 1, 2, 3, 4, 5, 6                 # columns of the work block (0-based)
-  wk = D.mat_alloc(S, 7); Vd = D.mat_alloc(S, spdim); AVd = D.mat_alloc(S, spdim)
-  try
-    VtAV = zeros(spdim, spdim)
-    D.mat_set(S, wk, B, b); D.mat_set(S, wk, X, x)
-    maxit == 0 ? maxit = n : nothing
-    res_norm = Vector{Float64}(undef, maxit + 1)
-    precond!() = M === nothing ? D.axpby(S, 1.0, wk, R, 0.0, wk, Z) : D.apply(S, 2, wk, R, wk, Z)
-    it = 1
-    D.apply(S, op, wk, X, wk, AP); D.axpby(S, 1.0, wk, B, 0.0, wk, R); D.axpby(S, -1.0, wk, AP, 1.0, wk, R)
-    rTr = D.dot(S, wk, R, wk, R)
-    precond!()
-    rTz = D.dot(S, wk, R, wk, Z)
-    D.axpby(S, 1.0, wk, Z, 0.0, wk, P)
-    res_norm[it] = sqrt(rTr)
-    ivec = 1                                                  # 1-based column of V, as in the reference
-    D.axpby(S, 1.0 / sqrt(rTz), wk, Z, 0.0, Vd, ivec - 1)
-    just_restarted = false
-    hlpr = 0.0
-    tol = eps_rtol * norm(b)
-    while (it < maxit) && (res_norm[it] > tol)                # eigcg.jl:185
-      if !just_restarted && ivec < spdim
-        nd, al, be, rs, rTz = D.pcg_burst(S, M !== nothing, wk, spdim - ivec, rTz, tol, it, maxit; V=Vd, vcol0=ivec)
-        for j in 1:nd
-          it += 1
-          res_norm[it] = rs[j]
-          VtAV[ivec, ivec] += 1.0 / al[j]                     # :203
-          ivec += 1                                           # V[:, ivec] was stored by the device
-          VtAV[ivec-1, ivec] = -sqrt(be[j]) / al[j]
-          VtAV[ivec, ivec] = be[j] / al[j]
-        end
-        continue
-      end
-      D.apply(S, op, wk, P, wk, AP)
-      d = D.dot(S, wk, P, wk, AP)
-      alpha = rTz / d
-      beta = 1.0 / rTz
-      D.axpby(S, alpha, wk, P, 1.0, wk, X)
-      D.axpby(S, -alpha, wk, AP, 1.0, wk, R)
-      rTr = D.dot(S, wk, R, wk, R)
-      precond!()
-      just_restarted && (hlpr = sqrt(rTz))                    # :194-196
-      rTz = D.dot(S, wk, R, wk, Z)
-      beta *= rTz
-      ivec == spdim && D.axpby(S, -beta, wk, AP, 1.0, wk, T)  # tvec .-= beta * Ap   :199-201
-      D.axpby(S, 1.0, wk, Z, beta, wk, P)
-      it += 1
-      res_norm[it] = sqrt(rTr)
-      VtAV[ivec, ivec] += 1.0 / alpha
-      if just_restarted
-        D.axpby(S, 1.0, wk, AP, 1.0, wk, T)                   # tvec .+= Ap          :205
-        nev = ivec - 1
-        VtAV[1:nev, ivec] = D.gemv_t(S, Vd, 0, nev, wk, T) ./ hlpr
-        just_restarted = false
-      end
-      if ivec == spdim                                        # :211
-        D.apply(S, op, Vd, 0, AVd, 0, spdim)                  # AV = A * V
-        VtAV .= D.gemm_tn(S, Vd, 0, spdim, AVd, 0, spdim)     # V'AV
-        QZ, vals, nev = rayleigh_ritz(Symmetric(VtAV), nvec)
-        D.gemm_nn(S, Vd, 0, spdim, QZ, Vd, 0)                 # V[:, 1:nev] = V * (Q * Z)
-        ivec = nev + 1
-        D.axpby(S, 1.0 / sqrt(rTz), wk, Z, 0.0, Vd, ivec - 1)
-        VtAV .= 0
-        for j in 1:nev
-          VtAV[j, j] = vals[j]
-        end
-        VtAV[ivec, ivec] = beta / alpha
-        D.axpby(S, -beta, wk, AP, 0.0, wk, T)                 # tvec .= -beta * Ap   :237
-        just_restarted = true
-      else
-        ivec += 1
-        D.axpby(S, 1.0 / sqrt(rTz), wk, Z, 0.0, Vd, ivec - 1)
-        VtAV[ivec-1, ivec] = -sqrt(beta) / alpha
-        VtAV[ivec, ivec] = beta / alpha
-      end
-    end
-    if !just_restarted && ivec > nvec                         # :248-264
-      m = ivec - 1
-      QZ, vals, nev = rayleigh_ritz(Symmetric(VtAV[1:m, 1:m]), nvec)
-      D.gemm_nn(S, Vd, 0, m, QZ, Vd, 0)
-    end
-    D.mat_get!(x, S, wk, X)
-    Vout = Matrix{Float64}(undef, n, nvec)
-    D.mat_get!(Vout, S, Vd, 0)
-    return x, it, res_norm[1:it], Vout
-  finally
-    D.mat_free(S, wk); D.mat_free(S, Vd); D.mat_free(S, AVd)
-  end
+function eigpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, M::Union{B200NeumannNeumann,Nothing},
+                nvec::Int, spdim::Int; maxit::Int=0)
+  cap = (maxit == 0 ? S.N : maxit) + 1
+  res = Vector{Float64}(undef, cap); it = Ref{Int64}(0); tm = Timings()
+  V = Matrix{Float64}(undef, S.N, nvec)
+  chk(ccall((:kb200_eigpcg, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Float64, Cint, Cint, Ref{Int64}, Ptr{Float64}, Ptr{Float64}, Ref{Timings}),
+            S.h, b, x, nvec, spdim, maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1, it, res, V, tm))
+  return x, Int(it[]), res[1:it[]], V
 end
 
 """
     eigdefpcg(S, b, x, M, W, spdim; maxit=0) -> (x, it, res_norm, V[:, 1:nvec])      # defcg.jl:337-473
-
-Deflated with W and recycling; all iterations but the restart ones run as device bursts with the
-deflation (p -= W (WtAW \\ (WtA z)), defcg.jl:301-302) and the projection r -= W (WtW \\ (W'r)) (:407) on
-the device.  Mirror of ../solvers.py::eigdefpcg.
 """
-function eigdefpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64},
-                   M::Union{B200NeumannNeumann,Nothing}, W::Matrix{Float64}, spdim::Int; maxit::Int=0)
-  D = DeviceOps
-  n, nvec = size(W)
-  op = S.assembled ? 1 : 0
-  X, R, Z, P, AP, B = 0, 1, 2, 3, 4, 5
-  wk = D.mat_alloc(S, 7); Wd = D.mat_alloc(S, nvec); AWd = D.mat_alloc(S, nvec); Vd = D.mat_alloc(S, spdim)
-  try
-    D.mat_set(S, Wd, 0, W); D.mat_set(S, wk, B, b); D.mat_set(S, wk, X, x)
-    D.apply(S, op, Wd, 0, AWd, 0, nvec)                       # :357-360
-    WtAW = D.gemm_tn(S, AWd, 0, nvec, Wd, 0, nvec)
-    WtW = D.gemm_tn(S, Wd, 0, nvec, Wd, 0, nvec)
-    resid!() = (D.apply(S, op, wk, X, wk, AP); D.axpby(S, 1.0, wk, B, 0.0, wk, R); D.axpby(S, -1.0, wk, AP, 1.0, wk, R))
-    precond!() = M === nothing ? D.axpby(S, 1.0, wk, R, 0.0, wk, Z) : D.apply(S, 2, wk, R, wk, Z)
-    resid!()
-    mu = WtAW \ D.gemv_t(S, Wd, 0, nvec, wk, R)
-    D.gemv_n(S, 1.0, Wd, 0, nvec, mu, 1.0, wk, X)
-    VtAV = zeros(spdim, spdim)
-    first_restart = true
-    maxit == 0 ? maxit = n : nothing
-    res_norm = Vector{Float64}(undef, maxit + 1)
-    it = 1
-    resid!()
-    rTr = D.dot(S, wk, R, wk, R)
-    precond!()
-    rTz = D.dot(S, wk, R, wk, Z)
-    mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)
-    D.axpby(S, 1.0, wk, Z, 0.0, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)
-    res_norm[it] = sqrt(rTr)
-    VtAV[1:nvec, 1:nvec] = WtAW                               # :390
-    D.gemm_nn(S, Wd, 0, nvec, Matrix{Float64}(I, nvec, nvec), Vd, 0)   # V[:, 1:nvec] = W
-    just_restarted = false
-    ivec = nvec + 1
-    D.axpby(S, 1.0 / sqrt(rTz), wk, Z, 0.0, Vd, ivec - 1)
-    tol = eps_rtol * norm(b)
-    while (it < maxit) && (res_norm[it] > tol)                # :400
-      if ivec < spdim
-        nd, al, be, rs, rTz = D.pcg_burst(S, M !== nothing, wk, spdim - ivec, rTz, tol, it, maxit; V=Vd, vcol0=ivec,
-                                          W=Wd, AW=AWd, nvec=nvec, WtAW=WtAW, WtW=WtW)
-        for j in 1:nd
-          it += 1
-          res_norm[it] = rs[j]
-          VtAV[ivec, ivec] += 1.0 / al[j]                     # :417
-          ivec += 1
-          VtAV[ivec-1, ivec] = -sqrt(be[j]) / al[j]
-          VtAV[ivec, ivec] = be[j] / al[j]
-        end
-        nd > 0 && (just_restarted = false)
-        continue
-      end
-      # restart iteration (ivec == spdim)
-      D.apply(S, op, wk, P, wk, AP)
-      d = D.dot(S, wk, P, wk, AP)
-      alpha = rTz / d
-      beta = 1.0 / rTz
-      D.axpby(S, alpha, wk, P, 1.0, wk, X)
-      D.axpby(S, -alpha, wk, AP, 1.0, wk, R)
-      mu2 = WtW \ D.gemv_t(S, Wd, 0, nvec, wk, R)             # r -= W (WtW \ W'r)   :407
-      D.gemv_n(S, -1.0, Wd, 0, nvec, mu2, 1.0, wk, R)
-      rTr = D.dot(S, wk, R, wk, R)
-      precond!()
-      rTz = D.dot(S, wk, R, wk, Z)
-      beta *= rTz
-      mu = WtAW \ D.gemv_t(S, AWd, 0, nvec, wk, Z)
-      D.axpby(S, 1.0, wk, Z, beta, wk, P); D.gemv_n(S, -1.0, Wd, 0, nvec, mu, 1.0, wk, P)
-      it += 1
-      res_norm[it] = sqrt(rTr)
-      VtAV[ivec, ivec] += 1.0 / alpha
-      if first_restart                                        # :420-423
-        VtAV[1:nvec, nvec+1:spdim] = D.gemm_tn(S, AWd, 0, nvec, Vd, nvec, spdim - nvec)
-        first_restart = false
-      end
-      QZ, vals, nev = rayleigh_ritz(Symmetric(VtAV), nvec)
-      D.gemm_nn(S, Vd, 0, spdim, QZ, Vd, 0)
-      ivec = nev + 1
-      D.axpby(S, 1.0 / sqrt(rTz), wk, Z, 0.0, Vd, ivec - 1)
-      VtAV .= 0
-      for j in 1:nev
-        VtAV[j, j] = vals[j]
-      end
-      VtAV[ivec, ivec] = beta / alpha
-      just_restarted = true
-    end
-    if !just_restarted && ivec > nvec                         # :450-466
-      m = ivec - 1
-      if first_restart && m > nvec
-        VtAV[1:nvec, nvec+1:m] = D.gemm_tn(S, AWd, 0, nvec, Vd, nvec, m - nvec)
-      end
-      QZ, vals, nev = rayleigh_ritz(Symmetric(VtAV[1:m, 1:m]), nvec)
-      D.gemm_nn(S, Vd, 0, m, QZ, Vd, 0)
-    end
-    D.mat_get!(x, S, wk, X)
-    Vout = Matrix{Float64}(undef, n, nvec)
-    D.mat_get!(Vout, S, Vd, 0)
-    return x, it, res_norm[1:it], Vout
-  finally
-    D.mat_free(S, wk); D.mat_free(S, Wd); D.mat_free(S, AWd); D.mat_free(S, Vd)
-  end
+function eigdefpcg(S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, M::Union{B200NeumannNeumann,Nothing},
+                   W::Matrix{Float64}, spdim::Int; maxit::Int=0)
+  nvec = size(W, 2)
+  cap = (maxit == 0 ? S.N : maxit) + 1
+  res = Vector{Float64}(undef, cap); it = Ref{Int64}(0); tm = Timings()
+  V = Matrix{Float64}(undef, S.N, nvec)
+  chk(ccall((:kb200_eigdefpcg, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Float64, Cint, Cint, Ref{Int64}, Ptr{Float64}, Ptr{Float64}, Ref{Timings}),
+            S.h, b, x, W, nvec, spdim, maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1, it, res, V, tm))
+  return x, Int(it[]), res[1:it[]], V
 end
-export eigpcg, eigdefpcg
+
+"""
+    pcg(S, B::Matrix, X::Matrix, M; maxit=0) -> (X, its, res_norms)
+
+Independent recurrences for the columns of B (the loop over right-hand sides of
+Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179) sharing the operator launches.
+"""
+function pcg(S::B200SchurOperator, B::Matrix{Float64}, X::Matrix{Float64}, M::Union{B200NeumannNeumann,Nothing}; maxit::Int=0)
+  nrhs = size(B, 2)
+  stride = (maxit == 0 ? S.N : maxit) + 1
+  its = zeros(Int64, nrhs); res = zeros(Float64, stride, nrhs)
+  chk(ccall((:kb200_pcg_multi, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Float64, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Int64),
+            S.h, B, X, nrhs, maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1, its, res, stride))
+  return X, its, [res[1:its[k], k] for k in 1:nrhs]
+end
+
+"""
+    update_realization!(S, A_IΓdd, A_ΓΓdd, F)
+
+New coefficient realization on the same mesh / partition / ordering (the loop of Example07:160-204): values only.
+The symbolic plan on the GPU is kept; the resident stream is rewritten on the device before the next operation.
+`F[d]` must be a factorization with the SAME permutation and pattern (e.g. `cholesky!(F[d], A_IIdd[d])`).
+"""
+function update_realization!(S::B200SchurOperator, A_IΓdd, A_ΓΓdd, F)
+  for d in 1:length(F)
+    L = sparse(F[d].L)
+    chk(ccall((:kb200_update_local_block_values, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+              S.h, d - 1, A_IΓdd[d].nzval, A_ΓΓdd[d].nzval))
+    chk(ccall((:kb200_update_cholesky_values, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), S.h, d - 1, L.nzval))
+  end
+  S.assembled = false     # dense S_d of the previous realization are dropped by the library
+  return S
+end
+
+export defpcg, eigpcg, eigdefpcg, update_realization!
 
 end # module

@@ -1,11 +1,12 @@
 """RecyclingKrylovSolvers signatures dispatching on the B200 operator / preconditioner types.
 
-``pcg`` / ``cg`` (cg.jl:67-109, 14-50) run the whole solve inside libkrylov_b200.so.  ``defpcg``,
-``eigpcg`` and ``eigdefpcg`` (defcg.jl:242-308, eigcg.jl:143-267, defcg.jl:337-473) keep the
-reference's control flow here, line for line, but every n_Γ-sized object lives on the GPU (blocks of
-kb200_mat_alloc) and only scalars and nvec / spdim-sized dense data reach the host, where the small
-dense algebra (``WtAW \\ .``, the Rayleigh-Ritz restarts: eigen / svd / rank) uses LAPACK as the
-reference does.  Return tuples are the reference's: (x, it, res_norm[, V[:, 1:nvec]])."""
+``pcg`` / ``cg`` (cg.jl:67-109, 14-50), ``defpcg`` (defcg.jl:242-308), ``eigpcg`` (eigcg.jl:143-267) and ``eigdefpcg``
+(defcg.jl:337-473) are ONE C-ABI call each: the whole solve, restarts included, runs inside libkrylov_b200.so.
+Return tuples are the reference's: (x, it, res_norm[, V[:, 1:nvec]]).
+
+The ``*_hostloop`` variants keep the reference's control flow in the host language over the device-resident block
+primitives (kb200_mat_* / kb200_op_* / kb200_pcg_burst; small dense algebra with LAPACK as in the reference); they are
+the cross-checks of the whole-solve entry points (tests/test_gpu_parity.py), not the product path."""
 import numpy as np
 
 from .fem import B200NeumannNeumann, B200SchurOperator
@@ -156,9 +157,25 @@ def defpcg_hostloop(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann = None,
         dv.free()
 
 
-def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, burst=True):
-    """eigcg.jl:143-267.  Returns (x, it, res_norm, V[:, 1:nvec]).  burst=False: every iteration driven
-    from the host (the cross-check of the device bursts)."""
+def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, return_timings=False):
+    """eigcg.jl:143-267, whole solve inside the library (kb200_eigpcg).  Returns (x, it, res_norm, V[:, 1:nvec])."""
+    if M is not None and M.S is not A:
+        raise ValueError("preconditioner and operator live on different handles")
+    x, it, res, V, tm = A.h.eigpcg(b, x, nvec, spdim, maxit=maxit, rtol=EPS, assembled=A.assembled, precond=M is not None)
+    return (x, it, res, V, tm) if return_timings else (x, it, res, V)
+
+
+def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0, return_timings=False):
+    """defcg.jl:337-473, whole solve inside the library (kb200_eigdefpcg).  Returns (x, it, res_norm, V[:, 1:nvec])."""
+    if M is not None and M.S is not A:
+        raise ValueError("preconditioner and operator live on different handles")
+    x, it, res, V, tm = A.h.eigdefpcg(b, x, W, spdim, maxit=maxit, rtol=EPS, assembled=A.assembled, precond=M is not None)
+    return (x, it, res, V, tm) if return_timings else (x, it, res, V)
+
+
+def eigpcg_hostloop(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, burst=True):
+    """eigcg.jl:143-267 with the control flow in the host language (cross-check of kb200_eigpcg).  burst=False: every
+    iteration driven from the host (the cross-check of the device bursts)."""
     n = x.size
     dv = _Dev(A, M)
     h = dv.h
@@ -246,8 +263,8 @@ def eigpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit
         dv.free()
 
 
-def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0, burst=True):
-    """defcg.jl:337-473.  Returns (x, it, res_norm, V[:, 1:nvec]).  burst=False: host-driven iterations."""
+def eigdefpcg_hostloop(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit=0, burst=True):
+    """defcg.jl:337-473 with the control flow in the host language (cross-check of kb200_eigdefpcg)."""
     n, nvec = W.shape
     dv = _Dev(A, M)
     h = dv.h

@@ -552,8 +552,8 @@ def test_recycling_solvers_device_bursts_match_host_driven_iterations():
     Aop, Mop, bs = _oracle_callables(pr)
     n = pr.sd.n_gamma
     nvec, spdim = 8, 24
-    xa, ita, resa, Va = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim, burst=True)
-    xb, itb, resb, Vb = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim, burst=False)
+    xa, ita, resa, Va = solvers.eigpcg_hostloop(S, bs, np.zeros(n), M, nvec, spdim, burst=True)
+    xb, itb, resb, Vb = solvers.eigpcg_hostloop(S, bs, np.zeros(n), M, nvec, spdim, burst=False)
     assert ita == itb
     # the first iterations agree to rounding (1e-16); the dot products of the two paths are summed in different
     # orders, and the one-level NN-PCG recurrence on a lognormal field amplifies that
@@ -562,13 +562,27 @@ def test_recycling_solvers_device_bursts_match_host_driven_iterations():
     assert np.linalg.norm(xa - xb) <= 1e-5 * np.linalg.norm(xb)
     assert _subspace_gap(Va[:, :4], Vb[:, :4]) <= 2e-2
     b2 = Aop(np.random.default_rng(5).standard_normal(n))
-    x2a, it2a, res2a, V2a = solvers.eigdefpcg(S, b2, np.zeros(n), M, Va, spdim, burst=True)
-    x2b, it2b, res2b, V2b = solvers.eigdefpcg(S, b2, np.zeros(n), M, Va, spdim, burst=False)
+    x2a, it2a, res2a, V2a = solvers.eigdefpcg_hostloop(S, b2, np.zeros(n), M, Va, spdim, burst=True)
+    x2b, it2b, res2b, V2b = solvers.eigdefpcg_hostloop(S, b2, np.zeros(n), M, Va, spdim, burst=False)
     assert abs(it2a - it2b) <= 1
     k = min(it2a, it2b)
     assert np.abs(res2a[:k] - res2b[:k]).max() <= 1e-4 * res2b.max()
     assert np.linalg.norm(x2a - x2b) <= 1e-5 * np.linalg.norm(x2b)
     assert res2a[-1] <= 1e-7 * np.linalg.norm(b2)
     # a burst that hits maxit stops there
-    x3, it3, res3, _ = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim, maxit=7)
+    x3, it3, res3, _ = solvers.eigpcg_hostloop(S, bs, np.zeros(n), M, nvec, spdim, maxit=7)
     assert it3 == 7 and res3.size == 7
+    # the whole-solve C entry points (kb200_eigpcg / kb200_eigdefpcg: same control flow in C++, Rayleigh-Ritz algebra
+    # with cuSOLVER instead of LAPACK) against the host-language loop over the same kernels
+    xc, itc, resc, Vc = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim)
+    assert abs(itc - ita) <= 1 and Vc.shape == (n, nvec)
+    assert np.abs(resc[:6] - resa[:6]).max() <= 1e-12 * resa.max()
+    k = min(itc, ita)
+    assert np.abs(resc[:k] - resa[:k]).max() <= 1e-4 * resa.max()
+    assert np.linalg.norm(xc - xa) <= 1e-5 * np.linalg.norm(xa)
+    assert _subspace_gap(Vc[:, :4], Va[:, :4]) <= 2e-2
+    x2c, it2c, res2c, V2c = solvers.eigdefpcg(S, b2, np.zeros(n), M, Va, spdim)
+    assert abs(it2c - it2a) <= 1 and res2c[-1] <= 1e-7 * np.linalg.norm(b2)
+    assert np.linalg.norm(x2c - x2a) <= 1e-5 * np.linalg.norm(x2a)
+    x3c, it3c, res3c, _ = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim, maxit=7)
+    assert it3c == 7 and res3c.size == 7

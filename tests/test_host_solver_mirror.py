@@ -131,7 +131,7 @@ def test_eigpcg_and_eigdefpcg_mirror_the_oracle(burst):
     M = _Pre(S)
     Aop, Mop = (lambda v: A @ v), (lambda r: Minv @ r)
     xo, ito, reso, Vo = OS.eigpcg(Aop, b, np.zeros(n), Mop, nvec, spdim)
-    x, it, res, V = solvers.eigpcg(S, b, np.zeros(n), M, nvec, spdim, burst=burst)
+    x, it, res, V = solvers.eigpcg_hostloop(S, b, np.zeros(n), M, nvec, spdim, burst=burst)
     assert it == ito and V.shape == (n, nvec)
     assert np.abs(res - reso).max() <= 1e-9 * reso.max()
     assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
@@ -141,7 +141,7 @@ def test_eigpcg_and_eigdefpcg_mirror_the_oracle(burst):
     b2 = np.random.default_rng(9).standard_normal(n)
     x2o, it2o, res2o, V2o = OS.eigdefpcg(Aop, b2, np.zeros(n), Mop, Vo, spdim)
     h.bursts = 0
-    x2, it2, res2, V2 = solvers.eigdefpcg(S, b2, np.zeros(n), M, Vo, spdim, burst=burst)
+    x2, it2, res2, V2 = solvers.eigdefpcg_hostloop(S, b2, np.zeros(n), M, Vo, spdim, burst=burst)
     assert it2 == it2o and np.abs(res2 - res2o).max() <= 1e-8 * res2o.max()
     assert np.linalg.norm(x2 - x2o) <= 1e-8 * np.linalg.norm(x2o)
     assert (h.bursts > 0) == burst
@@ -160,7 +160,7 @@ def test_burst_respects_maxit_and_restart_boundaries():
     # indexes past its 3 x 3 minor, eigcg.jl:251-256 -- not a case it supports)
     for maxit in (2, 7, 9, 10, 11, 23):
         xo, ito, reso, Vo = OS.eigpcg(lambda v: A @ v, b, np.zeros(n), lambda r: Minv @ r, nvec, spdim, maxit=maxit)
-        x, it, res, V = solvers.eigpcg(S, b, np.zeros(n), M, nvec, spdim, maxit=maxit)
+        x, it, res, V = solvers.eigpcg_hostloop(S, b, np.zeros(n), M, nvec, spdim, maxit=maxit)
         assert it == ito == min(maxit, it) and res.size == it
         assert np.abs(res - reso).max() <= 1e-9 * reso.max()
 
