@@ -1,4 +1,4 @@
-"""Development probe (GPU): Example07-style loop at the benchmark size -- new realization -> value-only update of the
+"""Example07-style loop (Example07_PcgSchurStochasticEllipticPde.jl:160-204, 273) on the GPU: Example07-style loop at the benchmark size -- new realization -> value-only update of the
 resident stream -> solve; reports the update time next to the solve time (f1 entry)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
