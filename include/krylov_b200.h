@@ -11,7 +11,8 @@
  *  - sparse matrices are Julia-native SparseMatrixCSC{Float64,Int}: Int64 **1-based** colptr /
  *    rowval + Float64 nzval; index maps are Int64 1-based; dense matrices are column-major;
  *  - the library copies every input during the call and never keeps or frees caller memory;
- *  - one handle = one GPU = one calling thread at a time (Julia's synchronous ccall model);
+ *  - one handle = one calling thread at a time (Julia's synchronous ccall model); a handle drives one GPU
+ *    (kb200_create, kb200_create_dist: one process per GPU) or several (kb200_create_multi: one process);
  *  - there is no CPU fallback: without a usable CUDA device kb200_create fails.
  */
 #ifndef KRYLOV_B200_H
@@ -61,6 +62,16 @@ int kb200_create(int device_id, kb200_handle* out);
  * All ranks must issue the same sequence of operator applications / solves. */
 int kb200_nccl_unique_id(void* out128);
 int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, kb200_handle* out);
+/* ONE process, several GPUs of one box (the reference's examples are a single Julia process; SURVEY 8(b)
+ * `kb200_create(ngpus, device_ids)`): the handle owns one member context per GPU (device_ids == NULL: devices
+ * 0 .. ngpus-1) and one host thread per member.  Every call of this header made on the handle is carried out by
+ * all members at once -- subdomains sharded as for kb200_create_dist, per-subdomain uploads taken by the owning
+ * member, interface sums inside the fused assembly + peer-memory exchange kernels (buffers mapped with
+ * cudaDeviceEnablePeerAccess; no NCCL, no fallback: creation of the exchange fails without peer access) -- and the
+ * caller's output buffers are written once.  Results are bit-identical to the multi-process handle and, for the
+ * operators, to a single-GPU handle (owner-ordered sums).  The device-resident block API (kb200_mat_*, kb200_op_*,
+ * kb200_pcg_burst) and the development aids are not available on such a handle; the whole-solve entry points are. */
+int kb200_create_multi(int ngpus, const int* device_ids, kb200_handle* out);
 int kb200_destroy(kb200_handle h);
 /* Tunables (0 = automatic where it applies): "csize" (CTAs per subdomain cluster: 1,2,4,8,16),
  * "warps" (consumer warps of the stream kernel: 8, or 16 with one CTA per SM), "stages" (ring depth,
@@ -228,6 +239,10 @@ int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom,
  * several ranks every rank must make the call), 4 / 5 the multi-vector stream kernel with 2 / 4 right-hand sides per
  * pass over the factor, 6..9 the batched DMMA Neumann-Neumann product with 8 / 16 / 32 / 64 right-hand sides. */
 int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
+/* Test aid: the Rayleigh-Ritz restart algebra of eigpcg / eigdefpcg (eigcg.jl:220-228) alone, on a symmetric m x m matrix
+ * Tm (column-major): QZ_out (m x 2 nvec), vals_out (2 nvec), *nev_out = rank found. */
+int kb200_debug_rayleigh_ritz(kb200_handle h, const double* Tm, int64_t m, int64_t nvec, double* QZ_out, double* vals_out,
+                              int64_t* nev_out);
 /* Development aid: with option "debug_timing" = 1 the stream kernel records 16 clock64 stamps per
  * CTA (phase boundaries); this copies them out. */
 int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n);

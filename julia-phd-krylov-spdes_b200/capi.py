@@ -22,7 +22,8 @@ SYMBOLS = [
     "kb200_get_dense_local_schur", "kb200_pcg", "kb200_pcg_multi", "kb200_defpcg", "kb200_get_stats", "kb200_get_interface_maps",
     "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
-    "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst", "kb200_eigpcg", "kb200_eigdefpcg",
+    "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst", "kb200_eigpcg", "kb200_eigdefpcg", "kb200_debug_rayleigh_ritz",
+    "kb200_create_multi",
 ]
 
 
@@ -105,9 +106,12 @@ def _csc_julia(A):
 class Handle:
     """Owns one kb200_handle."""
 
-    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None, devices=None):
         self.h = C.c_void_p()
-        if world > 1:
+        if devices is not None:                 # one process, several GPUs (kb200_create_multi)
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _chk(lib().kb200_create_multi(len(devices), ids, C.byref(self.h)))
+        elif world > 1:
             buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
             _chk(lib().kb200_create_dist(device, rank, world, buf, C.byref(self.h)))
         else:
@@ -386,6 +390,16 @@ class Handle:
                                    C.byref(nd), C.byref(rz)))
         k = nd.value
         return k, al[:k], be[:k], rs[:k], rz.value
+
+    def debug_rayleigh_ritz(self, Tm, nvec):
+        Tm = np.asfortranarray(Tm, dtype=np.float64)
+        m = Tm.shape[0]
+        QZ = np.zeros((m, 2 * nvec), order="F")
+        vals = np.zeros(2 * nvec)
+        nev = C.c_int64()
+        _chk(lib().kb200_debug_rayleigh_ritz(self.h, _p(Tm, C.c_double), C.c_int64(m), C.c_int64(nvec), _p(QZ, C.c_double),
+                                             _p(vals, C.c_double), C.byref(nev)))
+        return QZ[:, :nev.value].copy(), vals[:nev.value].copy(), nev.value
 
     def stats(self):
         s = np.zeros(32)

@@ -6,11 +6,15 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -108,9 +112,16 @@ void csc_from_julia(kb::Csc& m, int64_t nrow, int64_t ncol, const int64_t* colpt
 
 }  // namespace
 
+struct KbGroup;
+
 struct kb200_ctx {
   int device = 0, rank = 0, world = 1;  // rank/world define the subdomain shard
-  bool has_comm = false;                // collectives only when an NCCL communicator exists
+  bool has_comm = false;                // several ranks share the interface: NCCL communicator or in-process group
+  // single-process multi-GPU handle (kb200_create_multi): the handle the caller holds owns a group of member
+  // contexts, one per GPU, each driven by its own host thread; a member other than the first drops its host outputs
+  KbGroup* grp = nullptr;
+  KbGroup* member_of = nullptr;
+  bool mute = false;
   cudaStream_t stream = nullptr;
 #ifdef KB200_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -244,6 +255,140 @@ void invalidate_dense_schur(Ctx* c, DomHost& dh) {
   c->have_sd = false;
   c->sd_on_device_only = false;
 }
+
+}  // namespace
+
+// ---- single-process multi-GPU handle ------------------------------------------------------------
+// The reference's examples are ONE Julia process (sketch of the parallel version:
+// Fem/EllipticPdePllDomainDecomposition.jl:1-18).  A group holds one member context per GPU, each the same
+// object a rank of the multi-process handle is (rank = position, world = group size), and one host thread per
+// member that executes the member's share of every call: the calls of the C ABI are forwarded to all members at
+// once, the first member writes the caller's outputs.  The members exchange interface data exactly like the
+// ranks of the multi-process handle (fused assembly + peer-memory exchange kernels); their receive buffers are
+// mapped with cudaDeviceEnablePeerAccess instead of CUDA IPC, and the set-up rendezvous that the multi-process
+// handle runs through NCCL happens between the threads.  No NCCL in this mode.
+struct KbGroup {
+  int n = 0;
+  std::vector<kb200_ctx*> members;
+  // set-up rendezvous between the member threads
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, acc = 1, result = 1;
+  uint64_t gen = 0;
+  void* xch_ptr[kb::kMaxPeers] = {};
+  int xch_dev[kb::kMaxPeers] = {};
+  // min over the members' values; every member must call it (a member that failed earlier turns into a time-out)
+  int agree_min(int v) {
+    std::unique_lock<std::mutex> lk(mu);
+    acc = arrived == 0 ? v : std::min(acc, v);
+    if (++arrived == n) {
+      result = acc;
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+      return result;
+    }
+    const uint64_t g = gen;
+    if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g; })) {
+      --arrived;
+      throw KbError(KB200_ERR_INTERNAL, "multi-GPU handle: a member never reached the set-up rendezvous");
+    }
+    return result;
+  }
+  // worker threads
+  std::vector<std::thread> threads;
+  std::mutex jmu;
+  std::condition_variable jcv, dcv;
+  std::function<int(kb200_ctx*, bool)> job;
+  uint64_t job_gen = 0;
+  int done = 0;
+  bool stop = false;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+  void worker(int i) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<int(kb200_ctx*, bool)> f;
+      {
+        std::unique_lock<std::mutex> lk(jmu);
+        jcv.wait(lk, [&] { return stop || job_gen != seen; });
+        if (stop) return;
+        seen = job_gen;
+        f = job;
+      }
+      int r = KB200_ERR_INTERNAL;
+      std::string e;
+      try {
+        r = f(members[i], i == 0);
+        if (r != KB200_OK) e = g_err;
+      } catch (const std::exception& ex) {
+        e = ex.what();
+      } catch (...) {
+        e = "unknown error";
+      }
+      {
+        std::lock_guard<std::mutex> lk(jmu);
+        rc[i] = r;
+        err[i] = e;
+        if (++done == n) dcv.notify_all();
+      }
+    }
+  }
+  void start() {
+    rc.assign(n, 0);
+    err.assign(n, std::string());
+    for (int i = 0; i < n; ++i) threads.emplace_back([this, i] { worker(i); });
+  }
+  // run f(member, is_first) on every member's thread at once; first failure (in member order) is reported
+  int run(const std::function<int(kb200_ctx*, bool)>& f) {
+    {
+      std::lock_guard<std::mutex> lk(jmu);
+      job = f;
+      done = 0;
+      ++job_gen;
+    }
+    jcv.notify_all();
+    {
+      std::unique_lock<std::mutex> lk(jmu);
+      dcv.wait(lk, [&] { return done == n; });
+    }
+    for (int i = 0; i < n; ++i)
+      if (rc[i] != KB200_OK) {
+        g_err = "GPU " + std::to_string(members[i]->device) + " (member " + std::to_string(i) + "): " + err[i];
+        return rc[i];
+      }
+    return KB200_OK;
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(jmu);
+      stop = true;
+    }
+    jcv.notify_all();
+    for (auto& t : threads) t.join();
+    threads.clear();
+  }
+};
+
+// forward a call of the C ABI on a group handle to every member (inside `call`, `h` names the member and `lead`
+// tells whether it is the one that writes the caller's outputs)
+#define KB_GROUP(call)                                                                        \
+  do {                                                                                        \
+    if (h && h->grp)                                                                          \
+      return h->grp->run([&](kb200_handle h, bool lead) -> int {                              \
+        (void)lead;                                                                           \
+        return (call);                                                                        \
+      });                                                                                     \
+  } while (0)
+#define KB_GROUP_UNSUPPORTED(what)                                                            \
+  do {                                                                                        \
+    if (h && h->grp) {                                                                        \
+      g_err = what " is not available on a multi-GPU handle (kb200_create_multi)";            \
+      return KB200_ERR_INVALID;                                                               \
+    }                                                                                         \
+  } while (0)
+
+namespace {
 
 void setup_peer_exchange(Ctx* c);
 void build_exchange_tables(Ctx* c);
@@ -687,7 +832,12 @@ void fetch_stale_values(Ctx* c) {
 // with cudaIpcGetMemHandle; the handles travel through one ncclAllGather and are opened with
 // cudaIpcOpenMemHandle (peer access over NVLink).  Any failure on any rank (agreed through an
 // all-reduce) leaves the NCCL path in charge.
+void setup_peer_exchange_group(Ctx* c);
 void setup_peer_exchange(Ctx* c) {
+  if (c->member_of) {
+    setup_peer_exchange_group(c);
+    return;
+  }
 #ifdef KB200_WITH_NCCL
   if (!c->has_comm || c->world < 2 || c->world > kb::kMaxPeers || !c->peer_exchange || c->xch_own) return;
   const int W = c->world;
@@ -756,6 +906,70 @@ void setup_peer_exchange(Ctx* c) {
 #else
   (void)c;
 #endif
+}
+
+// Members of a single-process multi-GPU handle: same buffers, mapped with cudaDeviceEnablePeerAccess (CUDA IPC
+// handles cannot be opened by the process that exported them); the rendezvous runs between the member threads.
+void setup_peer_exchange_group(Ctx* c) {
+  KbGroup* g = c->member_of;
+  if (c->world < 2 || c->xch_own) return;
+  require(c->world <= kb::kMaxPeers, "multi-GPU handle: too many members");
+  const int W = c->world;
+  const size_t data_bytes = (size_t)2 * c->xch_mpad * sizeof(double);
+  const size_t flag_bytes = (size_t)std::max(c->xch_nflags, 1) * sizeof(uint32_t);
+  c->xch_flags_off = data_bytes;
+  int ok = 1;
+  if (cudaMalloc(&c->xch_own, data_bytes + flag_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    c->xch_own = nullptr;
+    ok = 0;
+  }
+  if (ok) {
+    CUDA_TRY(cudaMemset(c->xch_own, 0, data_bytes + flag_bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->xch_ptr[c->rank] = c->xch_own;
+    g->xch_dev[c->rank] = c->device;
+  }
+  ok = g->agree_min(ok);  // every buffer is allocated, zeroed and published
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      void* p = nullptr;
+      int dev = 0;
+      {
+        std::lock_guard<std::mutex> lk(g->mu);
+        p = g->xch_ptr[r];
+        dev = g->xch_dev[r];
+      }
+      if (r != c->rank && dev != c->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, dev) != cudaSuccess || !can) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        cudaGetLastError();
+      }
+      c->xch_peer[r] = p;
+    }
+  }
+  ok = g->agree_min(ok);
+  if (!ok) {
+    std::memset(c->xch_peer, 0, sizeof(c->xch_peer));
+    if (c->xch_own) cudaFree(c->xch_own);
+    c->xch_own = nullptr;
+    cudaGetLastError();
+    throw KbError(KB200_ERR_CUDA, "multi-GPU handle: peer access between the devices of the handle is unavailable "
+                                  "(use one process per GPU with kb200_create_dist, which can fall back to NCCL)");
+  }
+  c->peer_ok = true;
+  c->xch_launch = 0;
+  c->d_xcnt.alloc(2);
+  CUDA_TRY(cudaMemset(c->d_xcnt.p, 0, 2 * sizeof(uint32_t)));
 }
 
 // Send / gather tables of the owner-ordered compact exchange (kernels.cuh, xchg_tables.h).
@@ -903,6 +1117,7 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
 }
 
 void allreduce(Ctx* c, double* v, int64_t n) {
+  if (c->member_of) throw KbError(KB200_ERR_INTERNAL, "multi-GPU handle without peer exchange");  // never set up that way
 #ifdef KB200_WITH_NCCL
   if (c->has_comm) NCCL_TRY(ncclAllReduce(v, v, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
 #else
@@ -1097,6 +1312,7 @@ void h2d(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = n
   if (t) t->h2d_bytes += n * 8;
 }
 void d2h(Ctx* c, double* dst, const double* src, int64_t n, kb200_timings* t = nullptr) {
+  if (c->mute) return;  // member of a multi-GPU handle other than the first: the first one writes the caller's buffer
   CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   if (t) t->d2h_bytes += n * 8;
 }
@@ -1295,13 +1511,64 @@ int kb200_create_dist(int device_id, int rank, int world, const void* nccl_id, k
   });
 }
 
+int kb200_create_multi(int ngpus, const int* device_ids, kb200_handle* out) {
+  return guarded([&]() {
+    require(out != nullptr && ngpus >= 1 && ngpus <= kb::kMaxPeers, "need 1 <= ngpus <= 8 and a handle pointer");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) throw KbError(KB200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    std::unique_ptr<Ctx> lead(new Ctx());
+    std::unique_ptr<KbGroup> g(new KbGroup());
+    g->n = ngpus;
+    try {
+      for (int i = 0; i < ngpus; ++i) {
+        const int dev = device_ids ? device_ids[i] : i;
+        kb200_handle m = nullptr;
+        if (kb200_create(dev, &m) != KB200_OK) throw KbError(KB200_ERR_CUDA, g_err);
+        m->rank = i;
+        m->world = ngpus;
+        m->has_comm = ngpus > 1;
+        m->member_of = g.get();
+        m->mute = i > 0;
+        g->members.push_back(m);
+      }
+    } catch (...) {
+      for (Ctx* m : g->members) kb200_destroy(m);
+      throw;
+    }
+    lead->device = g->members[0]->device;
+    g->start();
+    lead->grp = g.release();
+    *out = lead.release();
+  });
+}
+
 int kb200_destroy(kb200_handle h) {
+  if (h && h->grp) {
+    KbGroup* g = h->grp;
+    // all members idle first (a receive buffer must outlive every peer's last store), then tear down one by one
+    g->run([](kb200_handle m, bool) -> int {
+      cudaSetDevice(m->device);
+      cudaStreamSynchronize(m->stream);
+      return KB200_OK;
+    });
+    g->shutdown();
+    int rc = KB200_OK;
+    for (Ctx* m : g->members) {
+      const int r = kb200_destroy(m);
+      if (r != KB200_OK) rc = r;
+    }
+    delete g;
+    delete h;
+    return rc;
+  }
   return guarded([&]() {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int r = 0; r < kb::kMaxPeers; ++r)
-      if (h->xch_peer[r] && h->xch_peer[r] != h->xch_own) cudaIpcCloseMemHandle(h->xch_peer[r]);
+    if (!h->member_of)
+      for (int r = 0; r < kb::kMaxPeers; ++r)
+        if (h->xch_peer[r] && h->xch_peer[r] != h->xch_own) cudaIpcCloseMemHandle(h->xch_peer[r]);
     if (h->xch_own) cudaFree(h->xch_own);
 #ifdef KB200_WITH_NCCL
     if (h->comm) ncclCommDestroy(h->comm);
@@ -1317,6 +1584,7 @@ int kb200_destroy(kb200_handle h) {
 }
 
 int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
+  KB_GROUP(kb200_set_option(h, name, value));
   return guarded([&]() {
     require(h && name, "null argument");
     const std::string k(name);
@@ -1397,6 +1665,7 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
 
 int kb200_set_topology(kb200_handle h, int64_t ndom, int64_t n_gamma, const int64_t* n_I, const int64_t* n_gd,
                        const int64_t* const* gamma_l2g, const int64_t* node_gamma_cnt) {
+  KB_GROUP(kb200_set_topology(h, ndom, n_gamma, n_I, n_gd, gamma_l2g, node_gamma_cnt));
   return guarded([&]() {
     require(h && n_I && n_gd && gamma_l2g && node_gamma_cnt, "null argument");
     require(!h->topo, "topology already set");
@@ -1434,6 +1703,16 @@ int kb200_set_topology(kb200_handle h, int64_t ndom, int64_t n_gamma, const int6
 }
 
 int kb200_local_range(kb200_handle h, int64_t* d0, int64_t* d1) {
+  if (h && h->grp) {  // the handle as a whole owns every subdomain
+    Ctx* m0 = h->grp->members[0];
+    if (!d0 || !d1 || !m0->topo) {
+      g_err = "topology not set";
+      return KB200_ERR_INVALID;
+    }
+    *d0 = 0;
+    *d1 = m0->ndom;
+    return KB200_OK;
+  }
   return guarded([&]() {
     require(h && d0 && d1 && h->topo, "topology not set");
     *d0 = h->d0;
@@ -1444,6 +1723,7 @@ int kb200_local_range(kb200_handle h, int64_t* d0, int64_t* d1) {
 int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colptr, const int64_t* AIG_rowval,
                               const double* AIG_nzval, const int64_t* AGG_colptr, const int64_t* AGG_rowval,
                               const double* AGG_nzval) {
+  KB_GROUP(kb200_upload_local_blocks(h, d, AIG_colptr, AIG_rowval, AIG_nzval, AGG_colptr, AGG_rowval, AGG_nzval));
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
@@ -1462,6 +1742,7 @@ int kb200_upload_local_blocks(kb200_handle h, int64_t d, const int64_t* AIG_colp
 
 int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const int64_t* L_colptr,
                           const int64_t* L_rowval, const double* L_nzval) {
+  KB_GROUP(kb200_upload_cholesky(h, d, perm, L_colptr, L_rowval, L_nzval));
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
@@ -1486,6 +1767,7 @@ int kb200_upload_cholesky(kb200_handle h, int64_t d, const int64_t* perm, const 
 
 int kb200_upload_global_blocks(kb200_handle h, int64_t d, const int64_t* AIGg_colptr, const int64_t* AIGg_rowval,
                                const double* AIGg_nzval) {
+  KB_GROUP(kb200_upload_global_blocks(h, d, AIGg_colptr, AIGg_rowval, AIGg_nzval));
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
@@ -1527,6 +1809,7 @@ int kb200_upload_global_blocks(kb200_handle h, int64_t d, const int64_t* AIGg_co
 
 int kb200_upload_global_interface_block(kb200_handle h, const int64_t* AGG_colptr, const int64_t* AGG_rowval,
                                         const double* AGG_nzval) {
+  KB_GROUP(kb200_upload_global_interface_block(h, AGG_colptr, AGG_rowval, AGG_nzval));
   return guarded([&]() {
     require(h && h->topo, "topology not set");
     kb::Csc m;
@@ -1551,6 +1834,7 @@ int kb200_upload_global_interface_block(kb200_handle h, const int64_t* AGG_colpt
 }
 
 int kb200_apply_global_schur(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  KB_GROUP(kb200_apply_global_schur(h, x, y, nrhs));
   return guarded([&]() {
     require(h && h->global_mode, "kb200_upload_global_blocks / kb200_upload_global_interface_block were not called");
     host_apply(h, OP_SCHUR, x, y, nrhs);
@@ -1558,6 +1842,7 @@ int kb200_apply_global_schur(kb200_handle h, const double* x, double* y, int64_t
 }
 
 int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzval) {
+  KB_GROUP(kb200_update_cholesky_values(h, d, L_nzval));
   return guarded([&]() {
     require(h && h->topo && L_nzval, "null argument");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
@@ -1582,6 +1867,7 @@ int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzva
 }
 
 int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval) {
+  KB_GROUP(kb200_update_local_block_values(h, d, AIG_nzval, AGG_nzval));
   return guarded([&]() {
     require(h && h->topo && AIG_nzval && AGG_nzval, "null argument");
     require(d >= 0 && d < h->ndom, "subdomain index out of range");
@@ -1640,13 +1926,16 @@ static void store_dense(Ctx* h, int64_t d, const double* M, bool pinv) {
 }
 
 int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS) {
+  KB_GROUP(kb200_upload_nn_pinv(h, d, PiS));
   return guarded([&]() { store_dense(h, d, PiS, true); });
 }
 int kb200_upload_dense_local_schur(kb200_handle h, int64_t d, const double* Sd) {
+  KB_GROUP(kb200_upload_dense_local_schur(h, d, Sd));
   return guarded([&]() { store_dense(h, d, Sd, false); });
 }
 
 int kb200_finalize(kb200_handle h) {
+  KB_GROUP(kb200_finalize(h));
   return guarded([&]() {
     require(h != nullptr, "null handle");
     finalize(h);
@@ -1654,16 +1943,20 @@ int kb200_finalize(kb200_handle h) {
 }
 
 int kb200_apply_schur(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  KB_GROUP(kb200_apply_schur(h, x, y, nrhs));
   return guarded([&]() { require(h, "null handle"); host_apply(h, OP_SCHUR, x, y, nrhs); });
 }
 int kb200_apply_schur_assembled(kb200_handle h, const double* x, double* y, int64_t nrhs) {
+  KB_GROUP(kb200_apply_schur_assembled(h, x, y, nrhs));
   return guarded([&]() { require(h, "null handle"); host_apply(h, OP_SCHUR_DENSE, x, y, nrhs); });
 }
 int kb200_apply_nn(kb200_handle h, const double* r, double* z, int64_t nrhs) {
+  KB_GROUP(kb200_apply_nn(h, r, z, nrhs));
   return guarded([&]() { require(h, "null handle"); host_apply(h, OP_NN, r, z, nrhs); });
 }
 
 int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_gamma, double* b_schur) {
+  KB_GROUP(kb200_schur_rhs(h, b_I_concat, b_gamma, b_schur));
   return guarded([&]() {
     require(h && b_I_concat && b_gamma && b_schur, "null argument");
     finalize(h);
@@ -1679,6 +1972,7 @@ int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_ga
 }
 
 int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b_I_concat, double* u_I_concat) {
+  KB_GROUP(kb200_back_substitute(h, u_gamma, b_I_concat, u_I_concat));
   return guarded([&]() {
     require(h && u_gamma && b_I_concat && u_I_concat, "null argument");
     finalize(h);
@@ -1687,12 +1981,13 @@ int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b
     h2d(h, h->d_x.p, u_gamma, h->n_gamma);
     launch_stream<kb::MODE_BACKSUB>(h, h->d_x.p, h->d_bI.p, h->d_uI.p, nullptr, nullptr, 0);
     const int64_t off = h->I_base_global[h->d0], len = h->I_base_global[h->d1] - off;
-    d2h(h, u_I_concat + off, h->d_uI.p, len);
+    CUDA_TRY(cudaMemcpyAsync(u_I_concat + off, h->d_uI.p, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));  // own slice
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   });
 }
 
 int kb200_assemble_local_schurs(kb200_handle h) {
+  KB_GROUP(kb200_assemble_local_schurs(h));
   return guarded([&]() {
     require(h != nullptr, "null handle");
     finalize(h);
@@ -1725,6 +2020,12 @@ int kb200_assemble_local_schurs(kb200_handle h) {
 }
 
 int kb200_get_dense_local_schur(kb200_handle h, int64_t d, double* Sd_out) {
+  if (h && h->grp) {  // served by the member that owns the subdomain
+    for (Ctx* m : h->grp->members)
+      if (m->topo && is_local(m, d)) return kb200_get_dense_local_schur(m, d, Sd_out);
+    g_err = "subdomain index out of range";
+    return KB200_ERR_INVALID;
+  }
   return guarded([&]() {
     require(h && Sd_out && h->topo, "null argument");
     require(is_local(h, d), "subdomain is not local to this handle");
@@ -1975,6 +2276,11 @@ static void finish_timings(Ctx* c, KernelTimer& kt, kb200_timings& T, int64_t la
 
 int kb200_pcg(kb200_handle h, const double* b, double* x, int64_t maxit, double rtol, int assembled, int precond,
               int64_t* it_out, double* res_norm, kb200_timings* tm) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      int64_t it_dummy = 0;
+      return kb200_pcg(m, b, x, maxit, rtol, assembled, precond, lead ? it_out : &it_dummy, res_norm, lead ? tm : nullptr);
+    });
   return guarded([&]() {
     require(h && b && x && it_out && res_norm, "null argument");
     finalize(h);
@@ -2078,6 +2384,13 @@ static void pcg_multi_block(Ctx* c, MultiWork& w, int64_t k, int64_t maxit, doub
 
 int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, int64_t maxit, double rtol, int assembled, int precond,
                     int64_t* its, double* res_norm, int64_t res_stride) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      std::vector<int64_t> its_dummy;
+      if (!lead && nrhs > 0) its_dummy.resize((size_t)nrhs);
+      return kb200_pcg_multi(m, B, X, nrhs, maxit, rtol, assembled, precond, lead ? its : its_dummy.data(), lead ? res_norm : nullptr,
+                             res_stride);
+    });
   // independent recurrences per right-hand side (the reference's sequential loop over right-hand sides,
   // Example11_EigInitPcgEllipticPdeMultipleRhs_Functions.jl:140-179), run side by side in blocks of up to 64
   // columns that share the operator launches
@@ -2127,6 +2440,11 @@ int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, in
 
 int kb200_defpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t maxit, double rtol,
                  int assembled, int precond, int64_t* it_out, double* res_norm, kb200_timings* tm) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      int64_t it_dummy = 0;
+      return kb200_defpcg(m, b, x, W, nvec, maxit, rtol, assembled, precond, lead ? it_out : &it_dummy, res_norm, lead ? tm : nullptr);
+    });
   return guarded([&]() {
     require(h && b && x && W && it_out && res_norm && nvec >= 1 && nvec <= 4096, "bad argument");
     finalize(h);
@@ -2196,6 +2514,7 @@ static double* mat_col(Ctx* h, int64_t id, int64_t col, int64_t ncols) {
 }
 
 int kb200_mat_alloc(kb200_handle h, int64_t ncols, int64_t* id) {
+  KB_GROUP_UNSUPPORTED("kb200_mat_alloc");
   return guarded([&]() {
     require(h && id && ncols >= 1, "bad argument");
     finalize(h);
@@ -2209,6 +2528,7 @@ int kb200_mat_alloc(kb200_handle h, int64_t ncols, int64_t* id) {
   });
 }
 int kb200_mat_free(kb200_handle h, int64_t id) {
+  KB_GROUP_UNSUPPORTED("kb200_mat_free");
   return guarded([&]() {
     require(h && id >= 0 && id < (int64_t)h->mats.size(), "bad matrix id");
     use_device(h);
@@ -2217,6 +2537,7 @@ int kb200_mat_free(kb200_handle h, int64_t id) {
   });
 }
 int kb200_mat_set(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, const double* host) {
+  KB_GROUP_UNSUPPORTED("kb200_mat_set");
   return guarded([&]() {
     require(h && host, "null argument");
     use_device(h);
@@ -2225,6 +2546,7 @@ int kb200_mat_set(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, const
   });
 }
 int kb200_mat_get(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, double* host) {
+  KB_GROUP_UNSUPPORTED("kb200_mat_get");
   return guarded([&]() {
     require(h && host, "null argument");
     use_device(h);
@@ -2233,6 +2555,7 @@ int kb200_mat_get(kb200_handle h, int64_t id, int64_t col0, int64_t ncols, doubl
   });
 }
 int kb200_op_apply(kb200_handle h, int which, int64_t src, int64_t scol, int64_t dst, int64_t dcol, int64_t ncols) {
+  KB_GROUP_UNSUPPORTED("kb200_op_apply");
   return guarded([&]() {
     require(h && which >= 0 && which <= 2 && ncols >= 1, "bad operator / column count");
     use_device(h);
@@ -2243,6 +2566,7 @@ int kb200_op_apply(kb200_handle h, int which, int64_t src, int64_t scol, int64_t
   });
 }
 int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, int64_t y, int64_t ycol) {
+  KB_GROUP_UNSUPPORTED("kb200_op_axpby");
   return guarded([&]() {
     require(h != nullptr, "null handle");
     use_device(h);
@@ -2253,6 +2577,7 @@ int kb200_op_axpby(kb200_handle h, double a, int64_t x, int64_t xcol, double b, 
   });
 }
 int kb200_op_gemv_t(kb200_handle h, int64_t A, int64_t col0, int64_t k, int64_t x, int64_t xcol, double* y_host) {
+  KB_GROUP_UNSUPPORTED("kb200_op_gemv_t");
   return guarded([&]() {
     require(h && y_host && k >= 1, "bad argument");
     use_device(h);
@@ -2266,10 +2591,12 @@ int kb200_op_gemv_t(kb200_handle h, int64_t A, int64_t col0, int64_t k, int64_t 
   });
 }
 int kb200_op_dot(kb200_handle h, int64_t x, int64_t xcol, int64_t y, int64_t ycol, double* out) {
+  KB_GROUP_UNSUPPORTED("kb200_op_dot");
   return kb200_op_gemv_t(h, x, xcol, 1, y, ycol, out);
 }
 int kb200_op_gemv_n(kb200_handle h, double a, int64_t A, int64_t col0, int64_t k, const double* mu_host, double b, int64_t y,
                     int64_t ycol) {
+  KB_GROUP_UNSUPPORTED("kb200_op_gemv_n");
   return guarded([&]() {
     require(h && mu_host && k >= 1, "bad argument");
     use_device(h);
@@ -2283,6 +2610,7 @@ int kb200_op_gemv_n(kb200_handle h, double a, int64_t A, int64_t col0, int64_t k
   });
 }
 int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t B, int64_t cb, int64_t kb_, double* C_host) {
+  KB_GROUP_UNSUPPORTED("kb200_op_gemm_tn");
   return guarded([&]() {
     require(h && C_host && ka >= 1 && kb_ >= 1, "bad argument");
     use_device(h);
@@ -2293,6 +2621,7 @@ int kb200_op_gemm_tn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, int64_t 
   });
 }
 int kb200_op_gemm_nn(kb200_handle h, int64_t A, int64_t ca, int64_t ka, const double* Q_host, int64_t kq, int64_t Cm, int64_t cc) {
+  KB_GROUP_UNSUPPORTED("kb200_op_gemm_nn");
   return guarded([&]() {
     require(h && Q_host && ka >= 1 && kq >= 1, "bad argument");
     use_device(h);
@@ -2310,6 +2639,7 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
                     const double* WtAW, const double* WtAW_inv, const double* WtW, const double* WtW_inv, int64_t m,
                     int64_t V, int64_t vcol0, double rTz, double tol, int64_t it0, int64_t maxit, double* alpha_out,
                     double* beta_out, double* res_out, int64_t* n_done, double* rTz_out) {
+  KB_GROUP_UNSUPPORTED("kb200_pcg_burst");
   return guarded([&]() {
     require(h && alpha_out && beta_out && res_out && n_done && rTz_out, "null argument");
     require(m >= 1 && it0 >= 1 && maxit > it0 && maxit < INT_MAX && nvec >= 0 && nvec <= 4096, "bad argument");
@@ -2368,8 +2698,31 @@ int kb200_pcg_burst(kb200_handle h, int assembled, int precond, int64_t wk, int6
   });
 }
 
+/* Development / test aid: the Rayleigh-Ritz restart algebra (eigcg.jl:220-228) on a given symmetric m x m matrix. */
+int kb200_debug_rayleigh_ritz(kb200_handle h, const double* Tm, int64_t m, int64_t nvec, double* QZ_out, double* vals_out, int64_t* nev_out) {
+  KB_GROUP_UNSUPPORTED("kb200_debug_rayleigh_ritz");
+  return guarded([&]() {
+    require(h && Tm && QZ_out && vals_out && nev_out && m >= 2 && nvec >= 1, "bad argument");
+    finalize(h);
+    use_device(h);
+    DenseLa la(h);
+    std::vector<double> T(Tm, Tm + m * m), vals;
+    DevBuf<double> dQZ;
+    const int nev = rayleigh_ritz(h, la, T, (int)m, (int)nvec, dQZ, vals);
+    CUDA_TRY(cudaMemcpy(QZ_out, dQZ.p, (size_t)m * nev * 8, cudaMemcpyDeviceToHost));
+    std::copy(vals.begin(), vals.end(), vals_out);
+    *nev_out = nev;
+  });
+}
+
 int kb200_eigpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol,
                  int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      int64_t it_dummy = 0;
+      return kb200_eigpcg(m, b, x, nvec, spdim, maxit, rtol, assembled, precond, lead ? it : &it_dummy, res_norm, V_out,
+                          lead ? timings : nullptr);
+    });
   return guarded([&]() {
     require(h && b && x && it && res_norm && V_out, "null argument");
     finalize(h);
@@ -2381,6 +2734,12 @@ int kb200_eigpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64
 
 int kb200_eigdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
                     double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* V_out, kb200_timings* timings) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      int64_t it_dummy = 0;
+      return kb200_eigdefpcg(m, b, x, W, nvec, spdim, maxit, rtol, assembled, precond, lead ? it : &it_dummy, res_norm, V_out,
+                             lead ? timings : nullptr);
+    });
   return guarded([&]() {
     require(h && b && x && W && it && res_norm && V_out, "null argument");
     finalize(h);
@@ -2391,6 +2750,19 @@ int kb200_eigdefpcg(kb200_handle h, const double* b, double* x, const double* W,
 }
 
 int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
+  if (h && h->grp) {  // every member finalizes; the numbers are the first member's, the sizes summed over the members
+    const int rc = h->grp->run([&](kb200_handle m, bool) -> int {
+      double tmp[32];
+      return kb200_get_stats(m, tmp, 32);
+    });
+    if (rc != KB200_OK) return rc;
+    double acc[32];
+    for (int i = 0; i < 32; ++i) acc[i] = h->grp->members[0]->stats[i];
+    for (size_t k = 1; k < h->grp->members.size(); ++k)
+      for (int i : {0, 1, 2, 3, 4, 8, 10, 23}) acc[i] += h->grp->members[k]->stats[i];
+    for (int64_t i = 0; stats && i < n && i < 32; ++i) stats[i] = acc[i];
+    return KB200_OK;
+  }
   return guarded([&]() {
     require(h && stats, "null argument");
     finalize(h);
@@ -2401,6 +2773,10 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
 }
 
 int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom, int64_t* adj_loc) {
+  if (h && h->grp) {  // the maps are global: every member holds the same copy
+    const int rc = h->grp->run([&](kb200_handle m, bool) -> int { return kb200_finalize(m); });
+    return rc != KB200_OK ? rc : kb200_get_interface_maps(h->grp->members[0], adj_ptr, adj_dom, adj_loc);
+  }
   return guarded([&]() {
     require(h && adj_ptr && adj_dom && adj_loc, "null argument");
     finalize(h);
@@ -2413,6 +2789,7 @@ int kb200_get_interface_maps(kb200_handle h, int64_t* adj_ptr, int64_t* adj_dom,
 }
 
 int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n) {
+  KB_GROUP_UNSUPPORTED("kb200_debug_stamps");
   return guarded([&]() {
     require(h && out, "null argument");
     use_device(h);
@@ -2423,6 +2800,7 @@ int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n) {
 }
 
 int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
+  KB_GROUP_UNSUPPORTED("kb200_time_kernel");
   return guarded([&]() {
     require(h && avg_ms && reps >= 1, "bad argument");
     finalize(h);

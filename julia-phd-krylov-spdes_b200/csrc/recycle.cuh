@@ -119,6 +119,9 @@ static int rayleigh_ritz(Ctx* c, DenseLa& la, const std::vector<double>& Tm, int
     for (int i = 0; i < mn; ++i) nev += sv[i] > thr;
   }
   if (nev < 1) throw KbError(KB200_ERR_INTERNAL, "Rayleigh-Ritz restart: Y has rank 0");
+  if (std::getenv("KB200_DEBUG_RR"))
+    std::fprintf(stderr, "[rr C] m %d nev %d sv0 %.3e sv[nev-1] %.3e sv[next] %.3e sv[last] %.3e\n", m, nev, sv[0], sv[nev - 1],
+                 nev < mn ? sv[nev] : -1.0, sv[mn - 1]);
   // H = Q' (Tm Q), Q = U[:, 1:nev]; vals, Z = eigen(Symmetric(H)); Q Z
   dTQ.alloc((size_t)m * nev);
   dH.alloc((size_t)nev * nev);
@@ -130,6 +133,8 @@ static int rayleigh_ritz(Ctx* c, DenseLa& la, const std::vector<double>& Tm, int
   dQZ.alloc((size_t)m * nev);
   CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, nev, &one, dQ.p, m, dH.p, nev, &zero, dQZ.p, m));
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (std::getenv("KB200_DEBUG_RR"))
+    std::fprintf(stderr, "[rr C]   vals %.6e %.6e %.6e ... %.6e\n", vals[0], vals[std::min(1, nev - 1)], vals[std::min(2, nev - 1)], vals[nev - 1]);
   return nev;
 }
 
@@ -496,7 +501,7 @@ static void recycle_solve(Ctx* c, const double* b, double* x, const double* W, i
   d2h(c, x, v.col(RV::X), n, &T);
   d2h(c, V_out, dV.p, (int64_t)n * nvec, &T);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  std::copy(res.begin(), res.begin() + it, res_norm);
+  if (!c->mute) std::copy(res.begin(), res.begin() + it, res_norm);
   *it_out = it;
   finish_timings(c, kt, T, launches0, tm);
 }

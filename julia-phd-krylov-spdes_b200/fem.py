@@ -15,11 +15,12 @@ from . import capi
 
 class B200SchurOperator:
     def __init__(self, sd, blocks, factors, device=0, csize=None, rank=0, world=1, nccl_id=None,
-                 profile=False, options=None):
+                 profile=False, options=None, devices=None):
         """sd: Subdomains (set_subdomains); blocks: LocalBlocks (prepare_local_schurs);
-        factors: [(perm, L)] Cholesky factors of A_II,d (F.p, sparse(F.L))."""
+        factors: [(perm, L)] Cholesky factors of A_II,d (F.p, sparse(F.L)).
+        devices=[0, 1, ...]: one process driving several GPUs (kb200_create_multi)."""
         self.sd = sd
-        self.h = capi.Handle(device, rank, world, nccl_id)
+        self.h = capi.Handle(device, rank, world, nccl_id, devices=devices)
         if csize is not None:
             self.h.set_option("csize", csize)
         if profile:

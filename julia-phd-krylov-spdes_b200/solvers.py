@@ -98,6 +98,11 @@ def _rayleigh_ritz(Tm, nvec):
     Q = np.linalg.svd(Y, full_matrices=False)[0][:, :nev]
     H = _sym(Q.T @ (Tm @ Q))
     vals, Z = np.linalg.eigh(H)
+    import os
+    if os.environ.get("KB200_DEBUG_RR"):
+        sv = np.linalg.svd(Y, compute_uv=False)
+        print(f"[rr py] m {m} nev {nev} sv0 {sv[0]:.3e} sv[nev-1] {sv[nev-1]:.3e} sv[next] {sv[nev] if nev < sv.size else -1:.3e} sv[last] {sv[-1]:.3e}\n"
+              f"[rr py]   vals {vals[0]:.6e} {vals[1]:.6e} {vals[2]:.6e} ... {vals[-1]:.6e}", flush=True)
     return Q @ Z, vals, nev
 
 
