@@ -243,6 +243,18 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms);
  * Tm (column-major): QZ_out (m x 2 nvec), vals_out (2 nvec), *nev_out = rank found. */
 int kb200_debug_rayleigh_ritz(kb200_handle h, const double* Tm, int64_t m, int64_t nvec, double* QZ_out, double* vals_out,
                               int64_t* nev_out);
+/* ---- LORASC preconditioner of the full system (next row f2) ------------------------------------
+ * LorascPreconditioner / apply_lorasc (EllipticPdeDomainDecomposition.jl:1406-1428, :1908-1976; `\` :1980-1982, ldiv!
+ * :1984-1995): u = apply_lorasc(x) on the (interior..., interface) splitting of the full system.
+ * kb200_upload_lorasc takes chol_A_ΓΓ as Julia extracts it (F.p, sparse(F.L) of cholesky(A_ΓΓ), :1525) and the nev
+ * correction vectors E (n_Γ x nev, column-major, :1418, as prepare_lorasc_precond :1502-1676 leaves them -- that set-up
+ * stays on the host); the interior factors and A_IΓ,d are the ones already on the handle.  kb200_apply_lorasc:
+ * x_I_concat / u_I_concat are the interior parts concatenated in subdomain order (x_Id[idom], :1921-1926), x_gamma /
+ * u_gamma the interface parts; the gather / scatter through not_dirichlet_inds_g2l (:1921-1933, :1963-1973) is the
+ * caller's (host-language) side.  Works on single-GPU and kb200_create_multi handles. */
+int kb200_upload_lorasc(kb200_handle h, const int64_t* perm, const int64_t* L_colptr, const int64_t* L_rowval,
+                        const double* L_nzval, const double* E, int64_t nev);
+int kb200_apply_lorasc(kb200_handle h, const double* x_I_concat, const double* x_gamma, double* u_I_concat, double* u_gamma);
 /* Development aid: with option "debug_timing" = 1 the stream kernel records 16 clock64 stamps per
  * CTA (phase boundaries); this copies them out. */
 int kb200_debug_stamps(kb200_handle h, long long* out, int64_t n);

@@ -23,7 +23,7 @@ SYMBOLS = [
     "kb200_time_kernel", "kb200_debug_stamps", "kb200_mat_alloc", "kb200_mat_free", "kb200_mat_set",
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
     "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst", "kb200_eigpcg", "kb200_eigdefpcg", "kb200_debug_rayleigh_ritz",
-    "kb200_create_multi",
+    "kb200_create_multi", "kb200_upload_lorasc", "kb200_apply_lorasc",
 ]
 
 
@@ -400,6 +400,21 @@ class Handle:
         _chk(lib().kb200_debug_rayleigh_ritz(self.h, _p(Tm, C.c_double), C.c_int64(m), C.c_int64(nvec), _p(QZ, C.c_double),
                                              _p(vals, C.c_double), C.byref(nev)))
         return QZ[:, :nev.value].copy(), vals[:nev.value].copy(), nev.value
+
+    def upload_lorasc(self, perm, L, E):
+        """chol_A_ΓΓ as (F.p, sparse(F.L)) and the correction vectors E (n_Γ x nev)."""
+        p1 = _i64(np.asarray(perm) + 1)
+        cp, rv, nz = _csc_julia(L)
+        E = np.asfortranarray(E, dtype=np.float64).reshape(self.n_gamma, -1)
+        self._lorasc_keep = (p1, cp, rv, nz, E)
+        _chk(lib().kb200_upload_lorasc(self.h, _p(p1, C.c_int64), _p(cp, C.c_int64), _p(rv, C.c_int64), _p(nz, C.c_double),
+                                       _p(E, C.c_double), C.c_int64(E.shape[1])))
+
+    def apply_lorasc(self, x_I_concat, x_gamma):
+        xi, xg = _f64(x_I_concat), _f64(x_gamma)
+        ui, ug = np.zeros(int(self.n_I.sum())), np.zeros(self.n_gamma)
+        _chk(lib().kb200_apply_lorasc(self.h, _p(xi, C.c_double), _p(xg, C.c_double), _p(ui, C.c_double), _p(ug, C.c_double)))
+        return ui, ug
 
     def stats(self):
         s = np.zeros(32)

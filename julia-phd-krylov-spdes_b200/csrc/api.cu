@@ -122,6 +122,11 @@ struct kb200_ctx {
   KbGroup* grp = nullptr;
   KbGroup* member_of = nullptr;
   bool mute = false;
+  // LORASC preconditioner of the full system (kb200_upload_lorasc): the interface factor runs as a one-"subdomain"
+  // child handle of its own, the low-rank correction vectors stay on the host
+  kb200_ctx* iface = nullptr;
+  std::vector<double> lor_E;
+  int64_t lor_nev = 0, lor_n = 0;
   cudaStream_t stream = nullptr;
 #ifdef KB200_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -206,6 +211,7 @@ struct kb200_ctx {
   int64_t launches = 0;
   std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};  // convergence polls of pcg_core
   double* h_pinned = nullptr;  // staging for small reads
 };
 
@@ -1193,6 +1199,9 @@ enum OpKind { OP_SCHUR = 0, OP_SCHUR_DENSE = 1, OP_NN = 2 };
 struct KernelTimer {
   Ctx* c;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[2];
+  std::vector<int> span_iter[2];   // PCG iteration a sample belongs to (0: outside the loop)
+  int cur_iter = 0;                // set by the iteration loop before it samples
+  int max_iter = INT_MAX;          // samples of iterations enqueued past convergence (skipped on the device) do not count
   size_t used = 0;
   explicit KernelTimer(Ctx* ctx) : c(ctx) {}
   cudaEvent_t get() {
@@ -1212,12 +1221,19 @@ struct KernelTimer {
     cudaEvent_t b = get();
     CUDA_TRY(cudaEventRecord(b, c->stream));
     spans[which].emplace_back(a, b);
+    span_iter[which].push_back(cur_iter);
+  }
+  int64_t count(int which) const {
+    int64_t m = 0;
+    for (int it : span_iter[which]) m += it <= max_iter;
+    return m;
   }
   double total(int which) {
     double t = 0;
-    for (auto& s : spans[which]) {
+    for (size_t i = 0; i < spans[which].size(); ++i) {
+      if (span_iter[which][i] > max_iter) continue;
       float ms = 0;
-      CUDA_TRY(cudaEventElapsedTime(&ms, s.first, s.second));
+      CUDA_TRY(cudaEventElapsedTime(&ms, spans[which][i].first, spans[which][i].second));
       t += ms;
     }
     return t;
@@ -1544,6 +1560,10 @@ int kb200_create_multi(int ngpus, const int* device_ids, kb200_handle* out) {
 }
 
 int kb200_destroy(kb200_handle h) {
+  if (h && h->iface) {
+    kb200_destroy(h->iface);
+    h->iface = nullptr;
+  }
   if (h && h->grp) {
     KbGroup* g = h->grp;
     // all members idle first (a receive buffer must outlive every peer's last store), then tear down one by one
@@ -1576,6 +1596,8 @@ int kb200_destroy(kb200_handle h) {
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
+    for (cudaEvent_t e : h->ev_poll)
+      if (e) cudaEventDestroy(e);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     cudaStream_t s = h->stream;
     delete h;
@@ -2136,6 +2158,7 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
     c->pdl_now = c->pdl != 0;
     for (; k < kend; ++k) {
       const bool timed = kt != nullptr && c->profile != 0 && (k % 16 == 1);
+      if (kt) kt->cur_iter = k;
       cudaEvent_t ev = nullptr;
       if (timed) kt->begin(0, ev);
       if (I.A == OP_SCHUR) launch_stream<kb::MODE_APPLY>(c, I.p, nullptr, nullptr, c->d_loc.p, done_at, k);
@@ -2173,6 +2196,7 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
     return;
   }
   for (; k < kend; ++k) {
+    if (kt) kt->cur_iter = k;
     apply_op(c, I.A, I.p, I.Ap, I.p, c->d_partA.p, done_at, k, kt);                       // Ap = A p ; d = p.Ap
     kb::pcg_update_xr_kernel<<<c->nb, c->vec_threads, 0, c->stream>>>(n, c->nb, I.p, I.Ap, I.x, I.r, c->d_partA.p,
                                                                       c->d_partB.p, st, k);
@@ -2244,19 +2268,42 @@ static void pcg_core(Ctx* c, int64_t maxit, double rtol, OpKind A, int precond, 
   I.p = c->d_p.p;
   I.Ap = c->d_Ap.p;
   I.defl = defl;
-  int* h_flag = reinterpret_cast<int*>(c->h_pinned);
+  // Convergence polls without a pipeline bubble: the next stretch of check_every iterations is enqueued BEFORE the host
+  // waits for the state the previous stretch left behind (kernels enqueued past convergence exit on their first
+  // instructions), so the device never idles while the host reads {it, done_at, maxit, fail}.
+  int* flags[2] = {reinterpret_cast<int*>(c->h_pinned), reinterpret_cast<int*>(c->h_pinned) + 16};
+  for (int s = 0; s < 2; ++s)
+    if (!c->ev_poll[s]) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_poll[s], cudaEventDisableTiming));
   int k = 1;
-  bool done = false;
-  while (!done) {
+  auto enqueue = [&](int s) {
     const int kend = (int)std::min<int64_t>((int64_t)k + c->check_every, maxit);
     run_iterations(c, I, k, kend, &kt);
     k = kend;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h_flag, &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    done = (h_flag[1] != INT_MAX) || (h_flag[3] != 0) || (k >= maxit);   // {it, done_at, maxit, fail}
+    CUDA_TRY(cudaMemcpyAsync(flags[s], &st->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_poll[s], c->stream));
+  };
+  int cur = 0;
+  enqueue(cur);
+  int* h_flag = flags[cur];
+  for (;;) {
+    const int k_cur = k;                      // iterations enqueued up to and including stretch `cur`
+    const bool more = k < maxit;
+    if (more) enqueue(cur ^ 1);
+    CUDA_TRY(cudaEventSynchronize(c->ev_poll[cur]));
+    h_flag = flags[cur];
+    const bool done = (h_flag[1] != INT_MAX) || (h_flag[3] != 0) || (k_cur >= maxit);
+    if (done) {
+      if (more) {                             // drain the stretch enqueued ahead; its copy holds the final state
+        CUDA_TRY(cudaEventSynchronize(c->ev_poll[cur ^ 1]));
+        h_flag = flags[cur ^ 1];
+      }
+      break;
+    }
+    cur ^= 1;
   }
   *it_out = h_flag[0];
+  kt.max_iter = h_flag[0] - 1;   // `it` starts at 1: iterations 1 .. it-1 ran
   *fail_out = h_flag[3];
 }
 
@@ -2267,8 +2314,8 @@ static void finish_timings(Ctx* c, KernelTimer& kt, kb200_timings& T, int64_t la
   if (c->profile) {
     T.schur_ms = kt.total(0);
     T.nn_ms = kt.total(1);
-    T.schur_launches = (int64_t)kt.spans[0].size();
-    T.nn_launches = (int64_t)kt.spans[1].size();
+    T.schur_launches = kt.count(0);
+    T.nn_launches = kt.count(1);
   }
   T.kernel_launches = c->launches - launches0;
   if (tm) *tm = T;
@@ -2868,6 +2915,78 @@ int kb200_time_kernel(kb200_handle h, int which, int reps, double* avg_ms) {
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
     *avg_ms = ms / reps;
+  });
+}
+
+// ---- LORASC preconditioner of the full system (EllipticPdeDomainDecomposition.jl:1406-1428, :1908-1976) ----------
+// apply_lorasc is a composition of pieces this library already has, plus one solve with the factor of the ASSEMBLED
+// interface block A_ΓΓ:
+//   z_Γ = x_Γ - sum_d A_IΓd' (A_IId \ x_Id)            (:1935-1942)  == get_schur_rhs with (b_I, b_Γ) = (x_I, x_Γ)
+//   x_Γ = chol(A_ΓΓ) \ z_Γ                              (:1950)       -> the stream kernel on a child handle whose only
+//                                                                       "subdomain" has A_II = A_ΓΓ and an empty coupling
+//   x_Γ += sum_k (E_k' z_Γ) E_k                         (:1953-1957)  (host: n_Γ x nev, a few MFLOP)
+//   x_Id = A_IId \ (x_Id - A_IΓd x_Γ)                   (:1938, :1959-1961) == get_subdomain_solutions with b_I = x_I
+// The set-up (generalized eigenpairs of (S, A_ΓΓ), :1502-1676) stays on the host like KrylovKit in the reference.
+int kb200_upload_lorasc(kb200_handle h, const int64_t* perm, const int64_t* L_colptr, const int64_t* L_rowval,
+                        const double* L_nzval, const double* E, int64_t nev) {
+  return guarded([&]() {
+    require(h && perm && L_colptr && nev >= 0 && (nev == 0 || E), "bad argument");
+    Ctx* base = h->grp ? h->grp->members[0] : h;
+    require(base->topo, "kb200_set_topology must be called first");
+    const int64_t n = base->n_gamma;
+    require(n >= 1, "empty interface");
+    if (h->iface) {
+      kb200_destroy(h->iface);
+      h->iface = nullptr;
+    }
+    const int64_t one = 1, nI = n;
+    const int64_t l2g0[1] = {1};
+    const int64_t* l2g[1] = {l2g0};
+    const int64_t aig_colptr[2] = {1, 1};          // n x 1 coupling block without entries
+    const int64_t agg_colptr[2] = {1, 2}, agg_row[1] = {1};
+    const double agg_val[1] = {1.0};
+    std::string last;
+    for (int cs : {1, 2, 4, 8, 16}) {              // smallest cluster whose shared-memory vectors hold the interface
+      kb200_handle ch = nullptr;
+      if (kb200_create(base->device, &ch) != KB200_OK) throw KbError(KB200_ERR_CUDA, g_err);
+      int rc = kb200_set_option(ch, "csize", cs);
+      if (rc == KB200_OK) rc = kb200_set_topology(ch, 1, 1, &nI, &one, l2g, &one);
+      if (rc == KB200_OK) rc = kb200_upload_local_blocks(ch, 0, aig_colptr, nullptr, nullptr, agg_colptr, agg_row, agg_val);
+      if (rc == KB200_OK) rc = kb200_upload_cholesky(ch, 0, perm, L_colptr, L_rowval, L_nzval);
+      if (rc == KB200_OK) rc = kb200_finalize(ch);
+      if (rc == KB200_OK) {
+        h->iface = ch;
+        break;
+      }
+      last = g_err;
+      kb200_destroy(ch);
+      const bool too_big = last.find("too large") != std::string::npos || last.find("does not fit") != std::string::npos;
+      if (rc != KB200_ERR_INPUT || !too_big) throw KbError(rc, last);
+    }
+    if (!h->iface) throw KbError(KB200_ERR_INPUT, "interface factor does not fit the shared-memory vectors of a 16-CTA cluster: " + last);
+    h->lor_E.assign(E, E + (size_t)(n * nev));
+    h->lor_nev = nev;
+    h->lor_n = n;
+  });
+}
+
+int kb200_apply_lorasc(kb200_handle h, const double* x_I_concat, const double* x_gamma, double* u_I_concat, double* u_gamma) {
+  return guarded([&]() {
+    require(h && x_I_concat && x_gamma && u_I_concat && u_gamma, "null argument");
+    require(h->iface != nullptr, "kb200_upload_lorasc was not called");
+    const int64_t n = h->lor_n, nev = h->lor_nev;
+    std::vector<double> z((size_t)n), w((size_t)n);
+    const double zero = 0.0;
+    if (kb200_schur_rhs(h, x_I_concat, x_gamma, z.data()) != KB200_OK) throw KbError(KB200_ERR_INTERNAL, g_err);
+    if (kb200_back_substitute(h->iface, &zero, z.data(), w.data()) != KB200_OK) throw KbError(KB200_ERR_INTERNAL, g_err);
+    for (int64_t k = 0; k < nev; ++k) {                                   // rank-one corrections, in order (:1953-1957)
+      const double* e = h->lor_E.data() + (size_t)(k * n);
+      double val = 0.0;
+      for (int64_t i = 0; i < n; ++i) val += e[i] * z[(size_t)i];
+      for (int64_t i = 0; i < n; ++i) w[(size_t)i] += val * e[i];
+    }
+    if (kb200_back_substitute(h, w.data(), x_I_concat, u_I_concat) != KB200_OK) throw KbError(KB200_ERR_INTERNAL, g_err);
+    std::copy(w.begin(), w.end(), u_gamma);
   });
 }
 

@@ -126,3 +126,32 @@ class B200NeumannNeumann:
     def ldiv_inplace(self, r):  # ldiv!(M, r)
         r[...] = self.solve(r.copy())
         return r
+
+
+class B200Lorasc:
+    """LorascPreconditioner (EllipticPdeDomainDecomposition.jl:1406-1428) for the full system, applied on the GPU(s) of
+    ``S`` (kb200_apply_lorasc): interior factors and A_IΓ,d are the ones ``S`` already holds; ``chol_A_GG`` = (F.p,
+    sparse(F.L)) of cholesky(A_ΓΓ) (:1525) and ``E`` (n_Γ x nev) the correction vectors of prepare_lorasc_precond
+    (:1502-1676), both prepared on the host as in the reference.  ``free`` = the non-Dirichlet nodes in the order of
+    not_dirichlet_inds_g2l: the vectors ``solve`` takes and returns are indexed like the reference's (:1921-1933)."""
+
+    def __init__(self, S, chol_A_GG, E, free):
+        self.S = S
+        sd = S.sd
+        S.h.upload_lorasc(chol_A_GG[0], chol_A_GG[1], E)
+        g2l = np.full(sd.nnode, -1, dtype=np.int64)
+        g2l[np.asarray(free)] = np.arange(len(free))
+        self.idx_I = g2l[np.concatenate(sd.node_Id)] if sd.ndom else np.zeros(0, np.int64)   # x_Id[idom], concatenated
+        self.idx_G = g2l[sd.node_gamma]
+        self.n = len(free)
+
+    def solve(self, x):        # Πlorasc \ x  (:1980-1982)
+        u_I, u_G = self.S.h.apply_lorasc(x[self.idx_I], x[self.idx_G])
+        u = np.empty(self.n)
+        u[self.idx_I] = u_I
+        u[self.idx_G] = u_G
+        return u
+
+    def ldiv_into(self, z, r):  # ldiv!(z, Πlorasc, r)  (:1984-1988)
+        z[...] = self.solve(r)
+        return z
