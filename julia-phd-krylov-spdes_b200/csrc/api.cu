@@ -2466,7 +2466,13 @@ int kb200_pcg_multi(kb200_handle h, const double* B, double* X, int64_t nrhs, in
       h2d(c, w.B.p, B + j0 * n, n * k);
       h2d(c, w.X.p, X + j0 * n, n * k);
       CUDA_TRY(cudaMemsetAsync(w.st.p, 0, (size_t)k * sizeof(kb::PcgState), c->stream));
+      // a peer that never shows up is recorded in the handle's own state by the exchange kernels, not in the columns'
+      CUDA_TRY(cudaMemsetAsync(&c->d_state.p->fail, 0, sizeof(int), c->stream));
       pcg_multi_block(c, w, k, maxit, rtol, A, precond, st);
+      int xfail = 0;
+      CUDA_TRY(cudaMemcpyAsync(&xfail, &c->d_state.p->fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (xfail == 2) throw_on_fail(2);
       d2h(c, X + j0 * n, w.X.p, n * k);
       if (res_norm) {
         res_h.resize((size_t)((maxit + 1) * k));

@@ -257,3 +257,105 @@ def eigdefpcg(A, b, x, M, W, spdim, maxit=0, eps=EPS):
             QZ, vals, nev = _rayleigh_ritz(Tm, Tm[:m - 1, :m - 1], nvec)
             V[:, :nev] = V[:, :m] @ QZ
     return x, it, res_norm[:it].copy(), V[:, :nvec].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Post-hoc Rayleigh-Ritz / harmonic-Ritz recycling: rrpcg / rrdefpcg (rrdefpcg.jl:204-275, :48-151)
+# and hrpcg / hrdefpcg (hrdefpcg.jl:217-295, :48-164).
+#
+# The reference fills the search-space columns only while `it <= cap` (cap = spdim, or spdim - nvec with a deflation
+# basis) and then projects with ALL cap columns: when the solve stops earlier the remaining columns are uninitialised
+# memory (`Array{T,2}(undef, ...)`).  That is undefined behaviour, not an algorithm; this restatement (and the library)
+# projects onto the m = min(it, cap) columns that exist.  eigen(A, B) of two Symmetric matrices is LAPACK's sygvd:
+# ascending eigenvalues, B-orthonormal eigenvectors (scipy.linalg.eigh(A, B) is the same routine).
+# ---------------------------------------------------------------------------------------------
+def _posthoc(A, b, x, M, W, nvec, spdim, maxit, eps, harmonic):
+    import scipy.linalg as sla
+    n = x.size
+    defl = W is not None
+    if defl:
+        nvec = W.shape[1]
+        WtA = np.empty((nvec, n))
+        for iv in range(nvec):                               # rrdefpcg.jl:73-76
+            WtA[iv, :] = A(W[:, iv])
+        WtAW = _sym(WtA @ W)                                 # :80-81 Symmetric()
+        WtW = _sym(W.T @ W)                                  # :82-83
+        r = b - A(x)                                         # :86-89
+        x += W @ np.linalg.solve(WtAW, W.T @ r)
+    cap = spdim - nvec if defl else spdim
+    C = np.zeros((n, cap))                                   # Z (RR) or P (HR)
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    res_norm[0] = np.sqrt(rTr)
+    z = M(r)
+    rTz = r @ z
+    p = z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else z.copy()       # :97-98
+    C[:, 0] = p if harmonic else z / rTz ** 0.5                              # :99 / hrdefpcg.jl:101
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:             # :104
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        if defl:
+            r -= W @ np.linalg.solve(WtW, W.T @ r)           # :111
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        p = beta * p + z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else beta * p + z   # :116-117
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+        if it <= cap:                                        # :120-122
+            C[:, it - 1] = p if harmonic else z / rTz ** 0.5
+    m = min(it, cap)
+    C = C[:, :m]
+    AC = np.column_stack([A(C[:, j]) for j in range(m)])     # :127-133
+    k0 = nvec if defl else 0
+    T = np.zeros((k0 + m, k0 + m))
+    V = np.column_stack([W, C]) if defl else C
+    if not harmonic:                                         # rrdefpcg.jl:124-146
+        if defl:
+            T[:k0, :k0] = WtAW
+            T[:k0, k0:] = WtA @ C
+        T[k0:, k0:] = C.T @ AC
+        vals, vecs = np.linalg.eigh(_sym(T))                 # eigen(VtAV, I)
+    else:                                                    # hrdefpcg.jl:124-157
+        MAC = np.column_stack([M(AC[:, j]) for j in range(m)])
+        G = np.zeros_like(T)
+        if defl:
+            MAW = np.column_stack([M(WtA[iv, :]) for iv in range(nvec)])
+            G[:k0, :k0] = WtA @ MAW
+            G[:k0, k0:] = WtA @ MAC
+            T[:k0, :k0] = WtAW
+        G[k0:, k0:] = AC.T @ MAC
+        T[k0 + np.arange(m), k0 + np.arange(m)] = np.einsum("ij,ij->j", C, AC)
+        vals, vecs = sla.eigh(_sym(G), _sym(T))              # eigen(VtAinvMAV, VtAV)
+    nret = nvec
+    W2 = V @ vecs[:, :nret]                                  # :148-150
+    return x, it, res_norm[:it].copy(), W2
+
+
+def rrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """rrdefpcg.jl:204-275."""
+    return _posthoc(A, b, x, M, None, nvec, spdim, maxit, eps, False)
+
+
+def rrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """rrdefpcg.jl:48-151 (positional order of the reference: A, b, x, W, M, spdim)."""
+    return _posthoc(A, b, x, M, W, W.shape[1], spdim, maxit, eps, False)
+
+
+def hrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """hrdefpcg.jl:217-295."""
+    return _posthoc(A, b, x, M, None, nvec, spdim, maxit, eps, True)
+
+
+def hrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """hrdefpcg.jl:48-164."""
+    return _posthoc(A, b, x, M, W, W.shape[1], spdim, maxit, eps, True)
