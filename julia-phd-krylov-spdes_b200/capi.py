@@ -24,6 +24,7 @@ SYMBOLS = [
     "kb200_mat_get", "kb200_op_apply", "kb200_op_axpby", "kb200_op_dot", "kb200_op_gemv_t", "kb200_op_gemv_n",
     "kb200_op_gemm_tn", "kb200_op_gemm_nn", "kb200_pcg_burst", "kb200_eigpcg", "kb200_eigdefpcg", "kb200_debug_rayleigh_ritz",
     "kb200_create_multi", "kb200_upload_lorasc", "kb200_apply_lorasc",
+    "kb200_rrpcg", "kb200_rrdefpcg", "kb200_hrpcg", "kb200_hrdefpcg", "kb200_posthoc_recycle",
 ]
 
 
@@ -305,6 +306,11 @@ class Handle:
     def eigdefpcg(self, b, x, W, spdim, maxit=0, rtol=1e-7, assembled=False, precond=True):
         """kb200_eigdefpcg: defcg.jl:337-473, whole solve inside the library."""
         return self._recycle(lib().kb200_eigdefpcg, b, x, W, np.asarray(W).shape[1], spdim, maxit, rtol, assembled, precond)
+
+    def posthoc(self, name, b, x, W, nvec, spdim, maxit=0, rtol=1e-7, assembled=False, precond=True):
+        """kb200_rrpcg / kb200_rrdefpcg / kb200_hrpcg / kb200_hrdefpcg (name = "rr" or "hr"; W None: no deflation basis)."""
+        fn = getattr(lib(), f"kb200_{name}{'def' if W is not None else ''}pcg")
+        return self._recycle(fn, b, x, W, np.asarray(W).shape[1] if W is not None else nvec, spdim, maxit, rtol, assembled, precond)
 
     def pcg_multi(self, B, X, maxit=0, rtol=1e-7, assembled=False, precond=True):
         B = np.asfortranarray(B, dtype=np.float64)

@@ -2127,6 +2127,7 @@ struct IterCtx {
   const Defl* defl = nullptr;    // p <- beta p + z - W (WtAW \ (WtA z))                (defcg.jl:301-302)
   const Defl* deflR = nullptr;   // r <- r - W (WtW \ (W' r)) after the update of r      (defcg.jl:407)
   double* vbase = nullptr;       // V[:, vcol0 + (k - k0)] = z / sqrt(rTz) at the end of iteration k  (eigcg.jl:242)
+  double* pbase = nullptr;       // P[:, (k - k0)] = p at the end of iteration k                      (hrdefpcg.jl:122-124)
   int k0 = 1;
   double* hist = nullptr;        // hist[2 it], hist[2 it + 1] = alpha, beta of the iteration that produced `it`
 };
@@ -2191,6 +2192,8 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
         ++c->gsync_launches;
       }
       c->launches += 2;
+      if (I.pbase)   // (a launch skipped after convergence leaves p unchanged: the copy is then a column nobody reads)
+        CUDA_TRY(cudaMemcpyAsync(I.pbase + (size_t)(k - I.k0) * (size_t)n, I.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
     c->pdl_now = false;
     return;
@@ -2227,6 +2230,8 @@ static void run_iterations(Ctx* c, const IterCtx& I, int k, int kend, KernelTime
                                                                                      I.defl->mu, 1.0, I.p, done_at, k);
       c->launches++;
     }
+    if (I.pbase)
+      CUDA_TRY(cudaMemcpyAsync(I.pbase + (size_t)(k - I.k0) * (size_t)n, I.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
   CUDA_TRY(cudaGetLastError());
 }
@@ -2800,6 +2805,50 @@ int kb200_eigdefpcg(kb200_handle h, const double* b, double* x, const double* W,
     recycle_solve(h, b, x, W, (int)nvec, (int)spdim, maxit, rtol, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, it, res_norm, V_out,
                   timings);
   });
+}
+
+// rrpcg / rrdefpcg / hrpcg / hrdefpcg (rrdefpcg.jl:204-275, :48-151; hrdefpcg.jl:217-295, :48-164): kind 0 = Rayleigh-Ritz,
+// 1 = harmonic Ritz; W == NULL selects the undeflated sibling.
+int kb200_posthoc_recycle(kb200_handle h, int kind, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim,
+                          int64_t maxit, double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out,
+                          kb200_timings* timings) {
+  if (h && h->grp)
+    return h->grp->run([&](kb200_handle m, bool lead) -> int {
+      int64_t it_dummy = 0;
+      return kb200_posthoc_recycle(m, kind, b, x, W, nvec, spdim, maxit, rtol, assembled, precond, lead ? it : &it_dummy, res_norm,
+                                   W2_out, lead ? timings : nullptr);
+    });
+  return guarded([&]() {
+    require(h && b && x && it && res_norm && W2_out && (kind == 0 || kind == 1), "bad argument");
+    finalize(h);
+    use_device(h);
+    posthoc_solve(h, b, x, W, (int)nvec, (int)spdim, maxit, rtol, assembled ? OP_SCHUR_DENSE : OP_SCHUR, precond, kind == 1, it,
+                  res_norm, W2_out, timings);
+  });
+}
+int kb200_rrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol, int assembled,
+                int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings) {
+  return kb200_posthoc_recycle(h, 0, b, x, nullptr, nvec, spdim, maxit, rtol, assembled, precond, it, res_norm, W2_out, timings);
+}
+int kb200_rrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                   double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings) {
+  if (!W) {
+    g_err = "null deflation basis";
+    return KB200_ERR_INVALID;
+  }
+  return kb200_posthoc_recycle(h, 0, b, x, W, nvec, spdim, maxit, rtol, assembled, precond, it, res_norm, W2_out, timings);
+}
+int kb200_hrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol, int assembled,
+                int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings) {
+  return kb200_posthoc_recycle(h, 1, b, x, nullptr, nvec, spdim, maxit, rtol, assembled, precond, it, res_norm, W2_out, timings);
+}
+int kb200_hrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                   double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings) {
+  if (!W) {
+    g_err = "null deflation basis";
+    return KB200_ERR_INVALID;
+  }
+  return kb200_posthoc_recycle(h, 1, b, x, W, nvec, spdim, maxit, rtol, assembled, precond, it, res_norm, W2_out, timings);
 }
 
 int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {

@@ -56,6 +56,17 @@ struct DenseLa {
     CUSOLVER_TRY(cusolverDnDsyevd(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m, A, lda, w, work.p, lwork, info.p));
     check_info(c, "syevd");
   }
+  // generalized symmetric-definite problem A v = w B v (upper triangles read, like Julia's eigen(Symmetric, Symmetric) =
+  // LAPACK sygvd): eigenvalues ascending in w, B-orthonormal eigenvectors overwrite A; B is overwritten by its factor
+  void sygvd(Ctx* c, int m, double* A, int lda, double* B, int ldb, double* w) {
+    int lwork = 0;
+    CUSOLVER_TRY(cusolverDnDsygvd_bufferSize(cs, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m, A, lda, B, ldb, w,
+                                             &lwork));
+    if ((int64_t)work.n < lwork) work.alloc((size_t)lwork);
+    CUSOLVER_TRY(cusolverDnDsygvd(cs, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m, A, lda, B, ldb, w, work.p,
+                                  lwork, info.p));
+    check_info(c, "sygvd (is the projected A-block positive definite?)");
+  }
 };
 
 // Restart algebra of eigcg.jl:220-228 / defcg.jl:425-432: Tm (m x m, host, column-major, symmetric) -> Q Z (m x nev,
@@ -250,7 +261,7 @@ struct BurstOut {
 
 // Up to m iterations of the (deflated) recurrence on the device without host synchronisation (kb200_pcg_burst).
 static void burst_core(Ctx* c, OpKind A, int precond, double* wk5, const Defl* D, const Defl* DR, int64_t m, double* vbase,
-                       double rTz, double tol, int64_t it0, int64_t maxit, BurstOut& out) {
+                       double rTz, double tol, int64_t it0, int64_t maxit, BurstOut& out, double* pbase = nullptr) {
   const int n = (int)c->n_gamma;
   m = std::min<int64_t>(m, maxit - it0);
   if ((int64_t)c->d_res.n < maxit + 1) c->d_res.alloc(maxit + 1);
@@ -265,6 +276,7 @@ static void burst_core(Ctx* c, OpKind A, int precond, double* wk5, const Defl* D
   if (precond) require(c->have_pinv, "kb200_upload_nn_pinv was not called");
   if (A == OP_SCHUR_DENSE) require(c->have_sd, "dense local Schur blocks were not uploaded / assembled");
   I.vbase = vbase;
+  I.pbase = pbase;
   I.defl = D;
   I.deflR = DR;
   DevBuf<double> dhist;
@@ -500,6 +512,157 @@ static void recycle_solve(Ctx* c, const double* b, double* x, const double* W, i
   CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
   d2h(c, x, v.col(RV::X), n, &T);
   d2h(c, V_out, dV.p, (int64_t)n * nvec, &T);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (!c->mute) std::copy(res.begin(), res.begin() + it, res_norm);
+  *it_out = it;
+  finish_timings(c, kt, T, launches0, tm);
+}
+
+
+// Post-hoc recycling: rrpcg / rrdefpcg (rrdefpcg.jl:204-275, :48-151) and hrpcg / hrdefpcg
+// (hrdefpcg.jl:217-295, :48-164).  The (deflated) recurrence is the one of eigdefpcg's bursts -- p projected against
+// W in the A-inner product, r re-orthogonalised against W (:111) -- with the first `cap` columns z / sqrt(rTz)
+// (Rayleigh-Ritz) or p (harmonic Ritz) captured ON the device as they are produced; after convergence ONE projection:
+//   RR:  eigen(Symmetric([W Z]' A [W Z]), I)                                   -> W2 = [W Z] vecs[:, 1:nvec]
+//   HR:  eigen(Symmetric((A V)' M^-1 (A V)), blockdiag(W'AW, diag(P'AP)))      -> W2 = [W P] vecs[:, 1:nvec]
+// A V by the multi-vector stream kernel, M^-1 (A V) by the batched DMMA Neumann-Neumann product, the Gram matrices
+// and V vecs by the DMMA tall-skinny kernels, the small (generalized) eigenproblem with cuSOLVER syevd / sygvd.
+// The reference projects with all cap columns even when the solve stopped before filling them (uninitialised
+// memory); here, as in oracle/solvers.py, the projection uses the m = min(it, cap) columns that exist.
+static void posthoc_solve(Ctx* c, const double* b, double* x, const double* W, int nvec, int spdim, int64_t maxit, double rtol, OpKind A,
+                          int precond, bool harmonic, int64_t* it_out, double* res_norm, double* W2_out, kb200_timings* tm) {
+  const int n = (int)c->n_gamma;
+  const bool defl = W != nullptr;
+  require(nvec >= 1 && spdim > nvec && spdim <= 4096, "need 1 <= nvec < spdim <= 4096");
+  if (maxit == 0) maxit = n;
+  require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+  const int k0 = defl ? nvec : 0, cap = spdim - k0;
+  kb200_timings T;
+  std::memset(&T, 0, sizeof(T));
+  const int64_t launches0 = c->launches;
+  KernelTimer kt(c);
+  DenseLa la(c);
+  RecycleVecs v(c, A, precond);
+  using RV = RecycleVecs;
+  DevBuf<double> dV, dAV, dAW;                       // V = [W | captured columns]
+  dV.alloc((size_t)n * spdim);
+  dAV.alloc((size_t)n * spdim);
+  CUDA_TRY(cudaMemsetAsync(dV.p, 0, (size_t)n * spdim * 8, c->stream));
+  auto Ccol = [&](int j) { return dV.p + (size_t)(k0 + j) * n; };
+  h2d(c, v.col(RV::B), b, n, &T);
+  h2d(c, v.col(RV::X), x, n, &T);
+  CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+  std::vector<double> WtAW, WtW, WtAW_inv, WtW_inv;
+  SmallLu luA;
+  DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2;
+  Defl D, DR;
+  if (defl) {
+    h2d(c, dV.p, W, (int64_t)n * nvec, &T);                                          // V[:, 1:nvec] = W
+    apply_op_multi(c, A, dV.p, dAV.p, nvec, MultiCtx(), &kt);                         // WtA' = A W      rrdefpcg.jl:73-79
+    WtAW = gemm_tn_host(c, nvec, nvec, dAV.p, dV.p);
+    WtW = gemm_tn_host(c, nvec, nvec, dV.p, dV.p);
+    WtAW = sym_upper(WtAW, nvec, nvec);                                               // Symmetric()     :81, :83
+    WtW = sym_upper(WtW, nvec, nvec);
+    luA.factor(nvec, WtAW);
+    invert_small(nvec, WtAW, WtAW_inv);
+    invert_small(nvec, WtW, WtW_inv);
+    auto up = [&](DevBuf<double>& buf, const std::vector<double>& src) {
+      buf.alloc(src.size());
+      CUDA_TRY(cudaMemcpyAsync(buf.p, src.data(), src.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    };
+    up(dM, WtAW);
+    up(dMinv, WtAW_inv);
+    up(dM2, WtW);
+    up(dM2inv, WtW_inv);
+    dy.alloc(nvec);
+    dmu.alloc(nvec);
+    dy2.alloc(nvec);
+    dmu2.alloc(nvec);
+    D.k = nvec;
+    D.W = dV.p;
+    D.AW = dAV.p;
+    D.M = dM.p;
+    D.Minv = dMinv.p;
+    D.y = dy.p;
+    D.mu = dmu.p;
+    DR = D;
+    DR.M = dM2.p;
+    DR.Minv = dM2inv.p;
+    DR.y = dy2.p;
+    DR.mu = dmu2.p;
+    v.residual();                                                                     // x += W (WtAW \ W'r)   :86-89
+    std::vector<double> mu = v.gemv_t(dV.p, nvec, v.col(RV::R));
+    luA.solve(mu);
+    v.gemv_n(1.0, dV.p, nvec, mu, 1.0, v.col(RV::X));
+  }
+  std::vector<double> res((size_t)maxit + 1);
+  int64_t it = 1;
+  v.residual();
+  const double rTr = v.dot(RV::R, RV::R);
+  v.applyM(RV::R, RV::Z);
+  double rTz = v.dot(RV::R, RV::Z);
+  v.axpby(1.0, RV::Z, 0.0, RV::P);
+  if (defl) {                                                                         // p = z - W (WtAW \ WtA z)   :97-98
+    std::vector<double> mu = v.gemv_t(dAV.p, nvec, v.col(RV::Z));
+    luA.solve(mu);
+    v.gemv_n(-1.0, dV.p, nvec, mu, 1.0, v.col(RV::P));
+  }
+  res[0] = std::sqrt(rTr);
+  if (harmonic) v.axpby(1.0, v.col(RV::P), 0.0, Ccol(0));                             // P[:, 1] = p            hrdefpcg.jl:101
+  else v.axpby(1.0 / std::sqrt(rTz), v.col(RV::Z), 0.0, Ccol(0));                     // Z[:, 1] = z / sqrt(rTz) rrdefpcg.jl:99
+  double bb = 0.0;
+  for (int i = 0; i < n; ++i) bb += b[i] * b[i];
+  const double tol = rtol * std::sqrt(bb);
+  while (it < maxit && res[it - 1] > tol) {
+    // iterations it .. : columns it (0-based) .. cap-1 are still to be captured
+    const int64_t left = cap - it;                       // iteration k stores column k (0-based) while k <= cap - 1
+    const int64_t m = left > 0 ? left : (int64_t)c->check_every * 4;
+    BurstOut bo;
+    double* cbase = left > 0 ? Ccol((int)it) : nullptr;
+    burst_core(c, A, precond, v.col(RV::X), defl ? &D : nullptr, defl ? &DR : nullptr, m, harmonic ? nullptr : cbase, rTz, tol, it, maxit, bo,
+               harmonic ? cbase : nullptr);
+    for (int64_t j = 0; j < bo.done; ++j) {
+      it += 1;
+      res[it - 1] = bo.res[j];
+    }
+    rTz = bo.rTz;
+    if (bo.done == 0) break;
+  }
+  // ---- projection ---------------------------------------------------------------------------------------------------
+  const int mc = (int)std::min<int64_t>(it, cap), mt = k0 + mc;
+  apply_op_multi(c, A, Ccol(0), dAV.p + (size_t)k0 * n, mc, MultiCtx(), &kt);          // AZ / AP          :127-133
+  std::vector<double> Tm = gemm_tn_host(c, mt, mt, dV.p, dAV.p);                       // V' A V
+  DevBuf<double> dG, dB, dw, dvec;
+  dw.alloc((size_t)mt);
+  if (!harmonic) {
+    std::vector<double> Ts = sym_upper(Tm, mt, mt);
+    dG.alloc((size_t)mt * mt);
+    CUDA_TRY(cudaMemcpyAsync(dG.p, Ts.data(), Ts.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    la.syevd(c, mt, dG.p, mt, dw.p);                                                  // eigen(VtAV, I)   :141-146
+  } else {
+    DevBuf<double> dMAV;
+    dMAV.alloc((size_t)n * mt);
+    if (precond) apply_op_multi(c, OP_NN, dAV.p, dMAV.p, mt, MultiCtx(), &kt);         // M \ (A V)        hrdefpcg.jl:128-141
+    else CUDA_TRY(cudaMemcpyAsync(dMAV.p, dAV.p, (size_t)n * mt * 8, cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<double> G = gemm_tn_host(c, mt, mt, dAV.p, dMAV.p);                    // (A V)' M^-1 (A V)   :142-147
+    std::vector<double> Gs = sym_upper(G, mt, mt), Bm((size_t)mt * mt, 0.0);
+    for (int j = 0; j < k0; ++j)
+      for (int i = 0; i < k0; ++i) Bm[i + (size_t)j * mt] = WtAW[i + (size_t)j * k0];  // VtAV = blockdiag(WtAW, diag(P'AP))   :149-156
+    for (int j = k0; j < mt; ++j) Bm[j + (size_t)j * mt] = Tm[j + (size_t)j * mt];
+    dG.alloc((size_t)mt * mt);
+    dB.alloc((size_t)mt * mt);
+    CUDA_TRY(cudaMemcpyAsync(dG.p, Gs.data(), Gs.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dB.p, Bm.data(), Bm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    la.sygvd(c, mt, dG.p, mt, dB.p, mt, dw.p);                                        // eigen(VtAinvMAV, VtAV)   :158
+  }
+  const int nret = std::min(nvec, mt);
+  DevBuf<double> dW2;
+  dW2.alloc((size_t)n * nvec);
+  CUDA_TRY(cudaMemsetAsync(dW2.p, 0, (size_t)n * nvec * 8, c->stream));
+  gemm_nn(c, mt, nret, dV.p, dG.p, dW2.p);                                            // W2 = [W C] vecs[:, 1:nvec]   :147-150
+  CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+  d2h(c, x, v.col(RV::X), n, &T);
+  d2h(c, W2_out, dW2.p, (int64_t)n * nvec, &T);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (!c->mute) std::copy(res.begin(), res.begin() + it, res_norm);
   *it_out = it;

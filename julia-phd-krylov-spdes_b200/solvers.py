@@ -178,6 +178,33 @@ def eigdefpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, W, spdim, maxit
     return (x, it, res, V, tm) if return_timings else (x, it, res, V)
 
 
+def _posthoc(name, A, b, x, W, M, nvec, spdim, maxit, return_timings):
+    if M is not None and M.S is not A:
+        raise ValueError("preconditioner and operator live on different handles")
+    x, it, res, W2, tm = A.h.posthoc(name, b, x, W, nvec, spdim, maxit=maxit, rtol=EPS, assembled=A.assembled, precond=M is not None)
+    return (x, it, res, W2, tm) if return_timings else (x, it, res, W2)
+
+
+def rrpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, return_timings=False):
+    """rrdefpcg.jl:204-275 (kb200_rrpcg).  Returns (x, it, res_norm, W2)."""
+    return _posthoc("rr", A, b, x, None, M, nvec, spdim, maxit, return_timings)
+
+
+def rrdefpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann, spdim, maxit=0, return_timings=False):
+    """rrdefpcg.jl:48-151 (kb200_rrdefpcg); positional order of the reference: A, b, x, W, M, spdim."""
+    return _posthoc("rr", A, b, x, W, M, W.shape[1], spdim, maxit, return_timings)
+
+
+def hrpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, return_timings=False):
+    """hrdefpcg.jl:217-295 (kb200_hrpcg)."""
+    return _posthoc("hr", A, b, x, None, M, nvec, spdim, maxit, return_timings)
+
+
+def hrdefpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann, spdim, maxit=0, return_timings=False):
+    """hrdefpcg.jl:48-164 (kb200_hrdefpcg)."""
+    return _posthoc("hr", A, b, x, W, M, W.shape[1], spdim, maxit, return_timings)
+
+
 def eigpcg_hostloop(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, burst=True):
     """eigcg.jl:143-267 with the control flow in the host language (cross-check of kb200_eigpcg).  burst=False: every
     iteration driven from the host (the cross-check of the device bursts)."""

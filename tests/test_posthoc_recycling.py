@@ -1,0 +1,85 @@
+"""rrpcg / rrdefpcg / hrpcg / hrdefpcg (rrdefpcg.jl:48-151, :204-275; hrdefpcg.jl:48-164, :217-295).
+CPU: properties of the oracle's restatement.  GPU: the whole-solve entry points against the oracle -- iteration
+counts, residual histories, solutions, and the returned bases as subspaces (eigenvectors carry a sign / rotation
+freedom inside clusters) and through what they are for: the iteration count of the next deflated solve."""
+import numpy as np
+import pytest
+
+import oracle.epdd as E
+import oracle.solvers as OS
+from conftest import get_oracle_ops, get_problem
+
+
+def ops(nx, ndom):
+    pr = get_problem(nx, ndom)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    A = lambda v: E.apply_local_schurs(pr.blocks, inner, pr.sd, v)
+    M = lambda r: E.apply_neumann_neumann_schur(Pi, pr.sd, r)
+    return pr, Pi, bs, A, M
+
+
+def gap(U, V):
+    Qu, _ = np.linalg.qr(U)
+    Qv, _ = np.linalg.qr(V)
+    s = np.linalg.svd(Qu.T @ Qv, compute_uv=False)
+    return float(np.sqrt(max(0.0, 1.0 - s.min() ** 2)))
+
+
+@pytest.mark.parametrize("kind", ["rr", "hr"])
+def test_oracle_posthoc_bases_are_ritz_pairs_and_deflate(kind):
+    pr, Pi, bs, A, M = ops(65, 16)
+    n = bs.size
+    f, g = (OS.rrpcg, OS.rrdefpcg) if kind == "rr" else (OS.hrpcg, OS.hrdefpcg)
+    x, it, res, W = f(A, bs, np.zeros(n), M, 8, 24)
+    xp, itp, resp = OS.pcg(A, bs, np.zeros(n), M)
+    assert it == itp and np.array_equal(res, resp)            # the recurrence is plain PCG; only the projection is added
+    assert W.shape == (n, 8)
+    AW = np.column_stack([A(W[:, j]) for j in range(8)])
+    H = W.T @ AW
+    if kind == "rr":                                          # Ritz vectors: A-orthogonal, M^-1-orthonormal in exact arithmetic
+        off = H - np.diag(np.diag(H))
+        assert np.abs(off).max() <= 1e-8 * np.abs(np.diag(H)).max()
+    b2 = A(np.random.default_rng(1).standard_normal(n))
+    x2, it2, res2, W2 = g(A, b2, np.zeros(n), W, M, 24)
+    _, it3, _ = OS.pcg(A, b2, np.zeros(n), M)
+    assert res2[-1] <= 1e-7 * np.linalg.norm(b2) and it2 < it3 and W2.shape == (n, 8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["rr", "hr"])
+@pytest.mark.parametrize("nx,ndom,nvec,spdim", [(65, 16, 8, 24), (97, 9, 6, 20)])
+def test_gpu_posthoc_recycling_matches_oracle(kind, nx, ndom, nvec, spdim):
+    from krylov_b200 import fem, solvers
+    pr, Pi, bs, A, M = ops(nx, ndom)
+    n = bs.size
+    S = fem.B200SchurOperator(pr.sd, pr.blocks, pr.factors)
+    Mg = fem.B200NeumannNeumann(S, Pi)
+    fo, go = (OS.rrpcg, OS.rrdefpcg) if kind == "rr" else (OS.hrpcg, OS.hrdefpcg)
+    fg, gg = (solvers.rrpcg, solvers.rrdefpcg) if kind == "rr" else (solvers.hrpcg, solvers.hrdefpcg)
+    xo, ito, reso, Wo = fo(A, bs, np.zeros(n), M, nvec, spdim)
+    x, it, res, W = fg(S, bs, np.zeros(n), Mg, nvec, spdim)
+    assert abs(it - ito) <= 1 and W.shape == (n, nvec)
+    m = min(it, ito)
+    assert np.abs(res[:m] - reso[:m]).max() <= 1e-8 * reso.max()
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    assert gap(W, Wo) <= 1e-5, "recycled subspaces differ"
+    # second system, deflated with the first basis (the SAME basis on both sides)
+    b2 = A(np.random.default_rng(1).standard_normal(n))
+    x2o, it2o, res2o, W2o = go(A, b2, np.zeros(n), W, M, spdim)
+    x2, it2, res2, W2 = gg(S, b2, np.zeros(n), W, Mg, spdim)
+    assert abs(it2 - it2o) <= 1 and res2[-1] <= 1e-7 * np.linalg.norm(b2)
+    m2 = min(it2, it2o)
+    assert np.abs(res2[:m2] - res2o[:m2]).max() <= 1e-7 * res2o.max()
+    assert np.linalg.norm(x2 - x2o) <= 1e-6 * np.linalg.norm(x2o)
+    assert gap(W2, W2o) <= 1e-4
+    # what the bases are for
+    _, it_plain, _ = solvers.pcg(S, b2, np.zeros(n), Mg)
+    assert it2 < it_plain
+    b3 = A(np.random.default_rng(2).standard_normal(n))
+    _, it3g, _, _ = gg(S, b3, np.zeros(n), W2, Mg, spdim)
+    _, it3o, _, _ = gg(S, b3, np.zeros(n), W2o, Mg, spdim)
+    assert abs(it3g - it3o) <= 1
+    # unpreconditioned operator path and the assembled operator run through the same entry points
+    xa, ita, resa, Wa = fg(S, bs, np.zeros(n), None, nvec, spdim)
+    xao, itao, resao, Wao = fo(A, bs, np.zeros(n), lambda r: r.copy(), nvec, spdim)
+    assert abs(ita - itao) <= 1 and np.linalg.norm(xa - xao) <= 1e-5 * np.linalg.norm(xao)
