@@ -64,14 +64,22 @@ end
 
 `F[d]` is the CHOLMOD factor of `A_IIdd[d]` (`cholesky(A_IIdd[d])`): `F[d].p` and `sparse(F[d].L)`
 are uploaded once; the device applies `A_II,d⁻¹` with its own level-scheduled triangular solves.
+`devices = [0, 1, ..., 7]` spreads the subdomains over the GPUs of the box from this one process.
 """
 function B200SchurOperator(A_IΓdd::Vector{SparseMatrixCSC{Float64,Int}},
                            A_ΓΓdd::Vector{SparseMatrixCSC{Float64,Int}},
                            F::Vector, ind_Γd_Γ2l::Vector{Dict{Int,Int}}, node_Γ_cnt::Vector{Int};
-                           device::Int=0, csize::Int=4)
+                           device::Int=0, csize::Int=4, devices::Union{Vector{Int},Nothing}=nothing)
   ndom = length(A_IΓdd)
   hr = Ref{Ptr{Cvoid}}(C_NULL)
-  chk(ccall((:kb200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, hr))
+  if devices === nothing
+    chk(ccall((:kb200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, hr))
+  else
+    # ONE Julia process, several GPUs: the library shards the subdomains over the devices and drives each with a
+    # host thread of its own; every call below then acts on all of them (kb200_create_multi)
+    ids = Vector{Cint}(devices)
+    chk(ccall((:kb200_create_multi, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(ids), ids, hr))
+  end
   h = hr[]
   chk(ccall((:kb200_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h, "csize", csize))
   n_I = Int64[A_IΓdd[d].m for d in 1:ndom]
@@ -256,6 +264,74 @@ function update_realization!(S::B200SchurOperator, A_IΓdd, A_ΓΓdd, F)
   return S
 end
 
-export defpcg, eigpcg, eigdefpcg, update_realization!
+# ---------------------------------------------------------------------------------------------------
+# Post-hoc recycling variants (rrdefpcg.jl:48-151, :204-275; hrdefpcg.jl:48-164, :217-295): ONE ccall each
+# ---------------------------------------------------------------------------------------------------
+function posthoc(kind::Int, S::B200SchurOperator, b::Vector{Float64}, x::Vector{Float64}, W::Union{Matrix{Float64},Nothing},
+                 M::Union{B200NeumannNeumann,Nothing}, nvec::Int, spdim::Int, maxit::Int)
+  cap = (maxit == 0 ? S.N : maxit) + 1
+  res = Vector{Float64}(undef, cap); it = Ref{Int64}(0); tm = Timings()
+  W2 = Matrix{Float64}(undef, S.N, nvec)
+  chk(ccall((:kb200_posthoc_recycle, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Float64, Cint, Cint, Ref{Int64},
+             Ptr{Float64}, Ptr{Float64}, Ref{Timings}),
+            S.h, kind, b, x, W === nothing ? C_NULL : W, nvec, spdim, maxit, eps_rtol, S.assembled ? 1 : 0, M === nothing ? 0 : 1,
+            it, res, W2, tm))
+  return x, Int(it[]), res[1:it[]], W2
+end
+rrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(0, S, b, x, nothing, M, nvec, spdim, maxit)
+rrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(0, S, b, x, W, M, size(W, 2), spdim, maxit)
+hrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(1, S, b, x, nothing, M, nvec, spdim, maxit)
+hrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(1, S, b, x, W, M, size(W, 2), spdim, maxit)
+
+# ---------------------------------------------------------------------------------------------------
+# LORASC preconditioner of the full system (EllipticPdeDomainDecomposition.jl:1406-1428, apply :1908-1976)
+# ---------------------------------------------------------------------------------------------------
+struct B200Lorasc
+  S::B200SchurOperator
+  idx_I::Vector{Int}      # not_dirichlet index of every interior node, subdomain after subdomain (x_Id[idom], :1921-1926)
+  idx_Γ::Vector{Int}      # not_dirichlet index of every interface node (:1928-1933)
+end
+"""
+    B200Lorasc(S, Πlorasc)        # Πlorasc::LorascPreconditioner from prepare_lorasc_precond (:1502-1676), host side
+
+Uploads `chol_A_ΓΓ` (`F.p`, `sparse(F.L)`) and the correction vectors `E`; the interior factors and `A_IΓ,d` are the
+ones `S` already holds.  `M \ x` / `ldiv!(z, M, x)` then run apply_lorasc on the GPU(s) of `S`.
+"""
+function B200Lorasc(S::B200SchurOperator, Π)
+  F = Π.chol_A_ΓΓ
+  L = sparse(F.L); p = Vector{Int64}(F.p)
+  nev = length(Π.E)
+  E = nev == 0 ? zeros(Float64, S.N, 0) : hcat(Π.E...)
+  chk(ccall((:kb200_upload_lorasc, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Int64),
+            S.h, p, L.colptr, L.rowval, L.nzval, E, nev))
+  ndom = length(Π.ind_Id_g2l)
+  idx_I = Int[]
+  for idom in 1:ndom
+    loc = Vector{Int}(undef, Π.ind_Id_g2l[idom].count)
+    for (node, node_in_I) in Π.ind_Id_g2l[idom]
+      loc[node_in_I] = Π.not_dirichlet_inds_g2l[node]
+    end
+    append!(idx_I, loc)
+  end
+  idx_Γ = Vector{Int}(undef, Π.ind_Γ_g2l.count)
+  for (node, node_in_Γ) in Π.ind_Γ_g2l
+    idx_Γ[node_in_Γ] = Π.not_dirichlet_inds_g2l[node]
+  end
+  return B200Lorasc(S, idx_I, idx_Γ)
+end
+function ldiv!(z::Vector{Float64}, M::B200Lorasc, x::Vector{Float64})
+  xI = x[M.idx_I]; xΓ = x[M.idx_Γ]
+  uI = similar(xI); uΓ = similar(xΓ)
+  chk(ccall((:kb200_apply_lorasc, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            M.S.h, xI, xΓ, uI, uΓ))
+  z[M.idx_I] = uI; z[M.idx_Γ] = uΓ
+  return z
+end
+\(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
+ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
+
+export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, B200Lorasc
 
 end # module

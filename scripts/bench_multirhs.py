@@ -63,7 +63,10 @@ print(json.dumps(dict(common, variant="sequential", value=nrhs / t_seq, wall_s=t
                       ms_per_rhs_iteration=1e3 * t_seq / iters,
                       bytes_per_rhs_iteration=st["stream_bytes"] + st["dense_bytes"],
                       achieved_GBs=(st["stream_bytes"] + st["dense_bytes"]) * iters / t_seq / 1e9)), flush=True)
-for variant, assembled in (("block_mf", False), ("block_dense", True)):
+# RB="0,2,4": right-hand sides per pass of the multi-vector stream kernel to try (0: the library's choice)
+variants = [(f"block_mf_rb{rb}" if rb else "block_mf", False, rb) for rb in (int(v) for v in os.environ.get("RB", "0").split(","))]
+for variant, assembled, rb in variants + [("block_dense", True, 0)]:
+    S.h.set_option("rhs_block", rb)
     t_b, (X, its, _) = timed(lambda: S.h.pcg_multi(B, np.zeros((n, nrhs)), assembled=assembled), 2)
     iters_b = float((its - 1).sum())
     sweeps = float((its - 1).max())                      # block iterations: every launch serves all still-running columns
@@ -71,7 +74,7 @@ for variant, assembled in (("block_mf", False), ("block_dense", True)):
         bytes_per_sweep = 2 * st["dense_bytes"]          # S_d and Pi S_d blocks read once per block iteration (<= 64 columns)
         flops_per_sweep = 2 * 2 * st["dense_bytes"] / 8 * nrhs
     else:
-        R = 2 if st["smem_bytes"] else 2
+        R = rb if rb else 4                                # upper bound of the library's own choice
         bytes_per_sweep = st["stream_bytes"] * nrhs / R + st["dense_bytes"]
         flops_per_sweep = 2 * st["dense_bytes"] / 8 * nrhs
     print(json.dumps(dict(common, variant=variant, value=nrhs / t_b, wall_s=t_b, speedup_vs_sequential=t_seq / t_b, iterations_total=iters_b,
