@@ -146,10 +146,8 @@ def main():
     d0, d1 = (sd.ndom * rank) // world, (sd.ndom * (rank + 1)) // world
     pr = PB.realization(base, ireal=1, dom_range=(d0, d1))
     pr0 = PB.realization(base, ireal=0, median=True, dom_range=(d0, d1))       # "median" operator (Example07:89)
-    if world > 1:   # every rank assembled only its own elements: complete b_Γ by a sum over ranks
-        bg = torch.from_numpy(pr.blocks.b_G).cuda()
-        dist.all_reduce(bg)
-        pr.blocks.b_G = bg.cpu().numpy()
+    if world > 1:   # every rank assembled only its own elements: b_Γ of the whole mesh, with the bits of the 1-GPU assembly
+        pr.blocks.b_G = PB.interface_rhs(base, pr.coeff, pr.f_vals, pr.u_dir)
     log(f"[rank {rank}] host preparation {time.time() - t0:.1f}s (n_gamma={sd.n_gamma}, local subdomains {d0}:{d1})")
 
     t0 = time.time()

@@ -409,6 +409,8 @@ void for_each_stream_kernel(int warps, F&& f) {
   f((const void*)kb::schur_stream_kernel<kb::MODE_UNIT, NW, R>);
   if (warps == kb::kWarps) {
     KB_ALL_MODES(kb::kWarps, 1) KB_ALL_MODES(kb::kWarps, 2) KB_ALL_MODES(kb::kWarps, 4)
+  } else if (warps == 24) {
+    KB_ALL_MODES(24, 1)   // single right-hand side only (800 threads: the multi-vector variants need too many registers)
   } else {
     KB_ALL_MODES(16, 1) KB_ALL_MODES(16, 2) KB_ALL_MODES(16, 4)
   }
@@ -421,6 +423,7 @@ size_t stream_smem_bytes(const Ctx* c, int R) {
 }
 // largest R in {4, 2, 1} not above `want` whose shared-memory vector fits
 int stream_rhs_block(const Ctx* c, int64_t want) {
+  if (c->warps == 24) return 1;
   int cap = c->rhs_block > 0 ? c->rhs_block : 4;
   for (int R = 4; R > 1; R >>= 1)
     if (R <= cap && R <= want && stream_smem_bytes(c, R) <= (size_t)c->smem_limit) return R;
@@ -459,7 +462,7 @@ void finalize(Ctx* c) {
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     if (c->warps == 0) c->warps = (nloc * c->csize <= sms) ? 16 : kb::kWarps;
-    if (c->stages == 0) c->stages = (c->warps == 16) ? 6 : 3;
+    if (c->stages == 0) c->stages = (c->warps >= 16) ? 6 : 3;
   }
   opt.warps = c->warps;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
@@ -481,7 +484,7 @@ void finalize(Ctx* c) {
   std::vector<Try> tries;
   if (c->merge_depth > 0 || c->min_block >= 0) {
     tries.push_back({c->merge_depth > 0 ? c->merge_depth : 1, c->min_block >= 0 ? c->min_block : 4});
-  } else if (c->warps == 16) {
+  } else if (c->warps >= 16) {
     tries.push_back({3, 4});   // one CTA per SM: room for the scratch slots of deep groups
   } else {
     tries.push_back({2, 4});
@@ -1060,7 +1063,10 @@ void launch_stream(Ctx* c, const StreamIo& io, const int* done_at, int iter, int
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = c->pdl_now ? 2 : 1;
-  if (c->warps == kb::kWarps) {
+  if (c->warps == 24) {
+    require(R == 1, "internal: 24-warp stream kernel takes one right-hand side");
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, 24, 1>, P));
+  } else if (c->warps == kb::kWarps) {
     if (R == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 1>, P));
     else if (R == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 2>, P));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::schur_stream_kernel<MODE, kb::kWarps, 4>, P));
@@ -1663,7 +1669,8 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       require(!h->finalized && (value == 0 || value == 1), "peer_exchange is 0 or 1, before the first operation");
       h->peer_exchange = (int)value;
     } else if (k == "warps") {
-      require(!h->finalized && (value == 0 || value == 8 || value == 16), "warps is 0 (automatic), 8 or 16, before the first operation");
+      require(!h->finalized && (value == 0 || value == 8 || value == 16 || value == 24),
+              "warps is 0 (automatic), 8, 16 or 24, before the first operation");
       h->warps = (int)value;
     } else if (k == "warp_private") {
       require(!h->finalized && (value == 0 || value == 1), "warp_private is 0 or 1, before the first operation");

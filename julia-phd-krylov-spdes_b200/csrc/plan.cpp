@@ -217,7 +217,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
                   bool private_first = true, int64_t* n_private_rows = nullptr, int64_t* n_private_slices = nullptr) {
   cs.pad_to_chunk();
   chunk0 = (uint32_t)(cs.bytes.size() / kChunkBytes);
-  const int NW = (opt.warps == 16) ? 16 : kWarps;
+  const int NW = (opt.warps == 16 || opt.warps == 24) ? opt.warps : kWarps;
   int maxlev = -1;
   bool any_private = false;
   for (auto& r : rows) {
@@ -492,7 +492,7 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
   // ---- warp-private subtrees: the bottom of every CTA's own forest, cut into subtrees that are
   // bin-packed onto the consumer warps (wown = warp, or -1 for the "upper" own nodes and the top) ----
   std::vector<int32_t> wown(n, -1);
-  const int NWp = (opt.warps == 16) ? 16 : kWarps;
+  const int NWp = (opt.warps == 16 || opt.warps == 24) ? opt.warps : kWarps;
   if (opt.warp_private && n > 0) {
     std::vector<char> upper(n, 0);
     std::vector<int32_t> wroot(n, -1);

@@ -67,7 +67,8 @@ enum Section : int {
 // between its slices (tokens without barriers).  Forward sweep: private part first, one barrier,
 // then the levels of the remaining ("upper") own nodes; backward sweep: upper levels first.
 constexpr uint16_t kTokBarrier = 0xffffu;
-constexpr int kChunkDirBytes = 48;  // room for (16 + 1) first-token indices, 16-byte aligned
+constexpr int kChunkDirBytes = 64;  // room for (24 + 1) first-token indices, 16-byte aligned
+constexpr int kMaxConsumerWarps = 24;
 constexpr int kMaxSlots = 256;     // scratch doubles used when the top right-hand side is combined (passes of kMaxSlots)
 struct alignas(16) SliceHdr {
   uint16_t nent;    // stored entries = kmax * nrows * T
@@ -166,7 +167,7 @@ struct BuildOptions {
   int max_block = 1024;
   int merge_depth = 1;        // supernodes of `merge_depth` consecutive depths of the supernode tree share one inverted block
   int max_smem_doubles = 28000;
-  int warps = kWarps;         // consumer warps of the kernel that will run the plan (8 or 16): slot k of a level -> warp k % warps
+  int warps = kWarps;         // consumer warps of the kernel that will run the plan (8, 16 or 24): slot k of a level -> warp k % warps
   int warp_private = 0;       // 1: subtrees near the leaves are processed warp-privately (no CTA barriers)
   int private_split = 2;      // aim at about private_split x kWarps private subtrees per CTA
 };

@@ -59,6 +59,16 @@ def realization(base, ireal=1, median=False, factorize=True, dom_range=None):
                    f_vals, u_dir, coeff)
 
 
+def interface_rhs(base, coeff, f_vals, u_dir):
+    """b_Γ of the WHOLE mesh from the elements that touch an interface node only (a few percent of the mesh).  The
+    accumulation of prepare_local_schurs is element-major, and elements without an interface node add nothing to b_Γ, so
+    the result has the bits of the full assembly -- every rank of a sharded run can compute it by itself instead of
+    summing per-rank partials in a rank-dependent order."""
+    cells, points, markers, neighbors, epart, npart, sd = base
+    touch = (sd.ind_gamma_g2l[cells] >= 0).any(axis=0)
+    return epdd_host.prepare_local_schurs(cells[:, touch], points, epart[touch], sd, coeff, f_vals, u_dir).b_G
+
+
 def build_problem(nx, ndom, ireal=1, jitter=0.2, median=False):
     return realization(build_mesh_and_partition(nx, ndom, jitter), ireal, median)
 

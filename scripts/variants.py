@@ -26,7 +26,7 @@ sd = base[-1]
 d0, d1 = (sd.ndom * rank) // world, (sd.ndom * (rank + 1)) // world
 pr = PB.realization(base, ireal=1, dom_range=(d0, d1))
 if world > 1:
-    bg = torch.from_numpy(pr.blocks.b_G).cuda(); dist.all_reduce(bg); pr.blocks.b_G = bg.cpu().numpy()
+    pr.blocks.b_G = PB.interface_rhs(base, pr.coeff, pr.f_vals, pr.u_dir)
 # OPTS="shard_world=8+shard_rank=3": emulate the per-GPU shard of a multi-GPU run on one GPU
 opts = {k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("OPTS", "").split("+") if kv)}
 if "shard_world" in opts:

@@ -194,7 +194,7 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
     if (const char* e = std::getenv("KB200_PRIVATE_SPLIT")) opt.private_split = std::atoi(e);
     DomainPlan P;
     build_domain_plan(in, opt, P);
-    const int NW = (opt.warps == 16) ? 16 : kWarps;
+    const int NW = (opt.warps == 16 || opt.warps == 24) ? opt.warps : kWarps;
     Emu E(P, NW);
     const int C = csize;
     const CtaDesc& D0 = P.ctas[0];

@@ -130,3 +130,18 @@ def test_compact_exchange_reproduces_the_sequential_sum_bit_for_bit():
                     assert m <= 1.25 * ng
                 for r in range(world):
                     assert np.array_equal(y[r * ng:(r + 1) * ng], seq), (nx, ndom, world, r)
+
+
+def test_interface_rhs_of_a_sharded_run_has_the_bits_of_the_full_assembly():
+    """bench.py on several ranks: every rank assembles only its own subdomains' elements; b_Γ of the whole mesh comes
+    from the interface-touching elements alone and must equal the 1-GPU assembly bit for bit (so that the iteration
+    count of the benchmark solve does not depend on the number of GPUs), as must the local b_I."""
+    from krylov_b200.hostprep import problem as PB
+    base = PB.build_mesh_and_partition(65, 16)
+    full = PB.realization(base, ireal=1, factorize=False)
+    bg = PB.interface_rhs(base, full.coeff, full.f_vals, full.u_dir)
+    assert np.array_equal(bg, full.blocks.b_G)
+    part = PB.realization(base, ireal=1, factorize=False, dom_range=(4, 8))
+    for d in range(4, 8):
+        assert np.array_equal(part.blocks.b_I[d], full.blocks.b_I[d])
+        assert (part.blocks.A_IG[d] != full.blocks.A_IG[d]).nnz == 0
