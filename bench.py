@@ -107,10 +107,14 @@ def main():
     ap.add_argument("--ndom", type=int, default=256)
     ap.add_argument("--csize", type=int, default=0, help="CTAs per subdomain cluster (0 = automatic)")
     ap.add_argument("--maxit", type=int, default=5000)
+    ap.add_argument("--ordering", default="nd", choices=["nd", "mmd"],
+                    help="fill-reducing ordering of the host-side Cholesky stand-in: geometric nested dissection (default) or "
+                         "minimum degree (what CHOLMOD's AMD gives a Julia caller); both arms use the same factors")
     ap.add_argument("--cpu-sample-iters", type=int, default=300,
                     help="PCG iterations of the bounded CPU sample (cpu_baseline / parity at the benchmark size)")
     args = ap.parse_args()
 
+    os.environ["KB200_HOST_ORDERING"] = args.ordering
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,6 +179,8 @@ def main():
         execution["exchange_entries_sent_by_rank0"] = int(stats["exchange_entries_sent"])
     else:
         execution["parallelism"] = "1 GPU, all subdomains local"
+    execution["host_ordering"] = args.ordering
+    execution["nnz_L"] = int(stats["nnz_L"])
     execution["fused_pcg_kernels"] = bool(stats["fused_pcg_ok"])
     execution["kernel"] = {"cluster_size": int(stats["csize"]), "consumer_warps": int(stats["consumer_warps"]),
                         "ring_stages": int(stats["ring_stages"]), "ctas": int(stats["n_cta"]),

@@ -994,21 +994,23 @@ pcg_fused_xr_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const
   const int nb = gridDim.x;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const double a = kX ? exchange_gather(g, n, loc, nullptr, X) : assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
-  double pv = 0.0;
+  double pv = 0.0, xv = 0.0, rold = 0.0;
   if (g < n) {
     Ap[g] = a;
     pv = p[g];
+    xv = x[g];     // fetched before the grid-wide wait: their latency hides behind it
+    rold = r[g];
   }
+  const double rTz = st->rTz;
   const double s = block_reduce_sum(a * pv, red);
   if (threadIdx.x == 0) partA[blockIdx.x] = s;
   grid_arrive_wait(counter, target, &st->fail);
   const double d = sum_partials_cg(partA, nb, red);
-  const double rTz = st->rTz;
   const double alpha = rTz / d;
   double rr = 0.0;
   if (g < n) {
-    x[g] = fma(alpha, pv, x[g]);
-    const double rv = fma(-alpha, a, r[g]);
+    x[g] = fma(alpha, pv, xv);
+    const double rv = fma(-alpha, a, rold);
     r[g] = rv;
     rr = rv * rv;
   }
@@ -1041,20 +1043,23 @@ pcg_fused_p_kernel(int n, const int32_t* adj_ptr, const int32_t* adj_src, const 
   const int nb = gridDim.x;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const double a = kX ? exchange_gather(g, n, loc, nullptr, X) : assemble_local(g, n, adj_ptr, adj_src, loc, nullptr);
-  double rv = 0.0;
+  double rv = 0.0, pold = 0.0;
   if (g < n) {
     z[g] = a;
     rv = r[g];
+    pold = p[g];   // fetched before the grid-wide wait
   }
+  const double rTz_old = st->rTz_old;
   const double s = block_reduce_sum(a * rv, red);
   if (threadIdx.x == 0) partC[blockIdx.x] = s;
+  // r.r of this iteration: its partials were written by the previous launch, so they can be summed before the wait
+  const double rTr = sum_partials_cg(partB, nb, red);
   grid_arrive_wait(counter, target, &st->fail);
   const double rTz_new = sum_partials_cg(partC, nb, red);
-  const double rTr = sum_partials_cg(partB, nb, red);
-  double beta = 1.0 / st->rTz_old;
+  double beta = 1.0 / rTz_old;
   beta *= rTz_new;
   if (g < n) {
-    p[g] = fma(beta, p[g], a);
+    p[g] = fma(beta, pold, a);
     if (vcol != nullptr) vcol[g] = a / sqrt(rTz_new);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

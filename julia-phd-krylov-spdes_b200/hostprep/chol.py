@@ -75,13 +75,26 @@ def cholesky(A, perm):
     return sp.csc_matrix((Lx, Li, Lp), shape=(n, n)), parent
 
 
-def factor_subdomains(A_II, points, node_Id, leaf=8, threads=None):
-    """[(perm, L)] for every subdomain; ND ordering from the interior nodes' coordinates."""
+def mmd_order(A):
+    """Minimum-degree permutation (perm[new] = old) of A' + A from SuperLU's ordering step -- the kind of ordering
+    CHOLMOD's default AMD gives the reference's `cholesky(A_IIdd[d])` (EllipticPdeDomainDecomposition.jl:1536)."""
+    import scipy.sparse.linalg as spla
+    lu = spla.splu(sp.csc_matrix(A), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    return np.argsort(np.asarray(lu.perm_c)).astype(np.int32)
+
+
+def factor_subdomains(A_II, points, node_Id, leaf=8, threads=None, ordering=None):
+    """[(perm, L)] for every subdomain.  ordering "nd" (default): geometric nested dissection from the interior nodes'
+    coordinates; "mmd": minimum degree (KB200_HOST_ORDERING selects it when the argument is not given)."""
+    ordering = ordering or os.environ.get("KB200_HOST_ORDERING", "nd")
+    if ordering not in ("nd", "mmd"):
+        raise ValueError("ordering is 'nd' or 'mmd'")
+
     def one(d):
         nodes = node_Id[d]
         if A_II[d].shape[0] == 0 or A_II[d].nnz == 0:
             return np.zeros(0, np.int32), sp.csc_matrix((0, 0))
-        p = nd_order(A_II[d], points[0, nodes], points[1, nodes], leaf)
+        p = mmd_order(A_II[d]) if ordering == "mmd" else nd_order(A_II[d], points[0, nodes], points[1, nodes], leaf)
         L, _ = cholesky(A_II[d], p)
         return p, L
     threads = threads or min(32, os.cpu_count() or 1)

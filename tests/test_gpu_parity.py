@@ -586,3 +586,40 @@ def test_recycling_solvers_device_bursts_match_host_driven_iterations():
     assert np.linalg.norm(x2c - x2a) <= 1e-5 * np.linalg.norm(x2a)
     x3c, it3c, res3c, _ = solvers.eigpcg(S, bs, np.zeros(n), M, nvec, spdim, maxit=7)
     assert it3c == 7 and res3c.size == 7
+
+
+@pytest.mark.parametrize("nx,ndom", [(65, 16), (97, 9)])
+def test_factors_from_a_minimum_degree_ordering(nx, ndom):
+    """a15: a Julia caller uploads CHOLMOD's (F.p, sparse(F.L)), an AMD-type ordering the library did not choose.
+    Same operators / solve from minimum-degree factors (SuperLU's MMD on A' + A) as from the oracle, and a value-only
+    refresh on that pattern."""
+    from krylov_b200.hostprep import chol
+    pr = get_problem(nx, ndom)
+    inner, Sd, Pi, bs = get_oracle_ops(pr)
+    sd, lb = pr.sd, pr.blocks
+    factors = chol.factor_subdomains(lb.A_II, pr.points, sd.node_Id, ordering="mmd")
+    assert sum(f[1].nnz for f in factors) != sum(f[1].nnz for f in pr.factors)       # really another ordering
+    S = fem.B200SchurOperator(sd, lb, factors)
+    M = fem.B200NeumannNeumann(S, Pi)
+    x = np.random.default_rng(7).standard_normal(sd.n_gamma)
+    assert rel(S * x, E.apply_local_schurs(lb, inner, sd, x)) <= 1e-12
+    assert rel(S.schur_rhs(lb.b_I, lb.b_G), bs) <= 1e-12
+    uI = S.subdomain_solutions(x, lb.b_I)
+    uIr = E.get_subdomain_solutions(x, lb, inner, sd)
+    assert max(np.abs(a - b).max() for a, b in zip(uI, uIr)) <= 1e-11 * max(np.abs(u).max() for u in uIr)
+    xg, it, res = solvers.pcg(S, bs, np.zeros(sd.n_gamma), M)
+    xo, ito, reso = OS.pcg(lambda v: E.apply_local_schurs(lb, inner, sd, v), bs, np.zeros(sd.n_gamma),
+                           lambda r: E.apply_neumann_neumann_schur(Pi, sd, r))
+    assert abs(it - ito) <= 1 and np.linalg.norm(xg - xo) <= 1e-6 * np.linalg.norm(xo)
+    got = S.assemble_local_schurs()
+    assert max(rel(got[d], Sd[d]) for d in range(ndom)) <= 1e-11
+    # new realization, values only, on the minimum-degree pattern
+    pr2 = get_problem(nx, ndom, ireal=2)
+    f2 = []
+    for d in range(ndom):
+        L2, _ = chol.cholesky(pr2.blocks.A_II[d], factors[d][0])
+        f2.append((factors[d][0], L2))
+    S.update_realization(pr2.blocks, f2)
+    inner2 = E.ExactInterior(pr2.blocks.A_II)
+    assert rel(S * x, E.apply_local_schurs(pr2.blocks, inner2, sd, x)) <= 1e-12
+    assert S.h.stats()["host_analyses"] == 1.0
