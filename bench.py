@@ -185,7 +185,8 @@ def main():
     execution["kernel"] = {"cluster_size": int(stats["csize"]), "consumer_warps": int(stats["consumer_warps"]),
                         "ring_stages": int(stats["ring_stages"]), "ctas": int(stats["n_cta"]),
                         "supernode_merge_depth": int(stats["merge_depth"]), "min_block": int(stats["min_block"]),
-                        "levels_per_sweep": int(stats["max_levels"])}
+                        "levels_per_sweep": int(stats["max_levels"]), "l2_prefetch_chunks": int(stats["l2_prefetch_chunks"]),
+                        "nn_blocks_l2_persisting_hit_ratio": float(stats["l2_persist_hit_ratio"])}
     log(f"[rank {rank}] device setup {time.time() - t0:.1f}s; stream {stats['stream_bytes'] / 1e9:.2f} GB, "
         f"levels {stats['max_levels']:.0f}, smem/CTA {stats['smem_bytes']:.0f} B, CTAs {stats['n_cta']:.0f}")
 
@@ -223,6 +224,7 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    execution["kernel"]["nn_blocks_l2_persisting_hit_ratio"] = float(S.h.stats()["l2_persist_hit_ratio"])   # set by the first GEMV launch
     per_rank = None
     if world > 1:
         t = torch.tensor([dev_ms, wall_s], dtype=torch.float64, device="cuda")
@@ -258,7 +260,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "schur_stream_kernel<MODE_APPLY>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "stream_bytes_per_launch": float(stats["stream_bytes"]), "peak_source": peak_src,
+                     "stream_bytes_per_launch": float(stats["stream_read_bytes"]),
+                     "stream_bytes_resident": float(stats["stream_bytes"]), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
                      # launch durations are sampled (every 16th iteration is bracketed by events; an event between
                      # two kernels would serialise the programmatic dependent launch chain of the others)

@@ -429,7 +429,7 @@ class Handle:
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
                 "consumer_warps", "ring_stages", "merge_depth", "min_block", "fused_pcg_ok", "vec_blocks",
                 "vec_threads", "exchange_entries", "exchange_entries_sent", "host_analyses", "value_refreshes",
-                "value_refs"]
+                "value_refs", "stream_read_bytes", "l2_persist_hit_ratio", "l2_prefetch_chunks"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):
@@ -441,10 +441,11 @@ class Handle:
         n = int(ptr[-1])
         return ptr, dom[:n], loc[:n]
 
-    def debug_stamps(self, n_cta):
-        out = np.zeros(n_cta * 64, dtype=np.int64)
+    def debug_stamps(self, n_cta, slots=64):
+        """slots: clock stamps per CTA (64; 320 in a -DKB200_SLICE_PROF build of the library)."""
+        out = np.zeros(n_cta * slots, dtype=np.int64)
         _chk(lib().kb200_debug_stamps(self.h, _p(out, C.c_int64), C.c_int64(out.size)))
-        return out.reshape(n_cta, 64)
+        return out.reshape(n_cta, slots)
 
     def time_kernel(self, which, reps=10):
         ms = C.c_double()

@@ -136,6 +136,15 @@ struct kb200_ctx {
   int warp_private = -1, private_split = 0;
   int adaptive_lanes = -1, lane_min = 0, lane_max = 0;
   int warps = 0;  // consumer warps per CTA of the stream kernel: 8 or 16 (0: automatic)
+  bool plan_warp_private = false;
+  int l2_prefetch = -1;             // option: L2 prefetch distance of the stream kernel in chunks (-1: automatic, 0: off, <= 32)
+  int l2_prefetch_mode = 0;         // option: 0 = bulk prefetch per chunk, 1 = line prefetches
+  int l2_prefetch_now = 0;          // the distance launches use (set by finalize / the option)
+  int l2_persist = -1;              // option: Neumann-Neumann blocks in the persisting L2 (-1: automatic = when at least half of them fits)
+  const double* l2_window_for = nullptr;
+  size_t l2_window_bytes = 0;
+  float l2_hit_ratio = 0.0f;
+  bool stages_auto = true;   // ring depth picked by finalize (option stages = 0)
   // interface exchange over peer memory (CUDA IPC, NVLink): fused into the assembly kernel
   int peer_exchange = 1;  // option: 0 = always use the NCCL all-reduce
   bool peer_ok = false;
@@ -192,6 +201,7 @@ struct kb200_ctx {
   // device pools
   DevBuf<kb::CtaDesc> d_ctas;
   DevBuf<uint8_t> d_stream;
+  DevBuf<uint16_t> d_chunk_units;   // used 16-byte units of every chunk of d_stream
   DevBuf<int32_t> d_l2g, d_imap, d_adj_ptr, d_adj_src, d_ngd;
   DevBuf<int64_t> d_G_base, d_mat_off;
   DevBuf<double> d_pinv, d_sd, d_inv_cnt;
@@ -418,8 +428,15 @@ void for_each_stream_kernel(int warps, F&& f) {
 }
 
 // dynamic shared memory of a stream-kernel CTA for R right-hand sides per launch
+// ring depth of a launch with R right-hand sides: the depth chosen for one right-hand side, less when the R-fold
+// shared vector needs the room (never below 3 stages, 2 for shallow rings)
+int stream_stages(const Ctx* c, int R) {
+  if (R == 1 || !c->stages_auto) return c->stages;
+  const int64_t room = (int64_t)c->smem_limit - ((int64_t)c->smem_doubles + kb::kMaxSlots) * 8 * R;
+  return (int)std::max<int64_t>(std::min<int64_t>(c->stages, room / kb::kChunkBytes), std::min(c->stages, 3));
+}
 size_t stream_smem_bytes(const Ctx* c, int R) {
-  return ((size_t)c->smem_doubles + kb::kMaxSlots) * 8 * (size_t)R + (size_t)c->stages * kb::kChunkBytes;
+  return ((size_t)c->smem_doubles + kb::kMaxSlots) * 8 * (size_t)R + (size_t)stream_stages(c, R) * kb::kChunkBytes;
 }
 // largest R in {4, 2, 1} not above `want` whose shared-memory vector fits
 int stream_rhs_block(const Ctx* c, int64_t want) {
@@ -462,7 +479,8 @@ void finalize(Ctx* c) {
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     if (c->warps == 0) c->warps = (nloc * c->csize <= sms) ? 16 : kb::kWarps;
-    if (c->stages == 0) c->stages = (c->warps >= 16) ? 6 : 3;
+    c->stages_auto = c->stages == 0;
+    if (c->stages == 0) c->stages = (c->warps >= 16) ? 6 : 3;   // one CTA per SM: deepened below once the vector size is known
   }
   opt.warps = c->warps;
   if (c->lane_entries > 0) opt.lane_entries = c->lane_entries;
@@ -551,6 +569,14 @@ void finalize(Ctx* c) {
   }
   c->max_gd = max_gd;
   c->smem_doubles = max_smem;
+  if (c->stages_auto && c->warps >= 16) {
+    // one CTA per SM: the ring takes what the shared-memory vector leaves (measured on the per-GPU shard of the
+    // 8-GPU run: 4 / 6 / 8 stages = 115 / 96 / 94 us -- the prefetch distance has to cover a dependency level)
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const int64_t room = (int64_t)optin - 2048 - ((int64_t)max_smem + kb::kMaxSlots) * 8;   // 2 KB: static shared memory
+    c->stages = (int)std::max<int64_t>(2, std::min<int64_t>(kb::kMaxStages, room / kb::kChunkBytes));
+  }
   c->smem_bytes = max_smem * 8 + c->stages * kb::kChunkBytes + kb::kMaxSlots * 8;
   c->n_cta = (int)(nloc * c->csize);
   // descriptors with global offsets
@@ -571,6 +597,19 @@ void finalize(Ctx* c) {
   c->d_ctas.upload(ctas, s);
   c->d_stream.alloc(so[nloc], 256);
   c->d_imap.alloc(mo[nloc]);
+  {
+    std::vector<uint16_t> units;
+    units.reserve(so[nloc] / kb::kChunkBytes);
+    double read_bytes = 0.0;
+    for (int64_t k = 0; k < nloc; ++k) {
+      if (plans[k].chunk_units.size() * (size_t)kb::kChunkBytes != plans[k].stream.size())
+        throw KbError(KB200_ERR_INTERNAL, "chunk table does not match the stream");
+      for (uint16_t u : plans[k].chunk_units) read_bytes += 16.0 * u;
+      units.insert(units.end(), plans[k].chunk_units.begin(), plans[k].chunk_units.end());
+    }
+    c->d_chunk_units.upload(units, s);
+    c->stats[24] = read_bytes;
+  }
   for (int64_t k = 0; k < nloc; ++k) {
     auto& P = plans[k];
     if (!P.stream.empty())
@@ -782,6 +821,17 @@ void finalize(Ctx* c) {
   c->stats[11] = c->peer_ok ? 1.0 : 0.0;
   c->stats[12] = c->warps;
   c->stats[13] = c->stages;
+  if (c->l2_prefetch < 0) {
+    // automatic L2 prefetch distance (measured, 4M DOF / 256 subdomains, scripts/probe_stages.py): with two CTAs per
+    // SM the ring is only 3 chunks deep and a bulk L2 prefetch 3 chunks ahead of the copy extends the look-ahead
+    // (stream kernel 613 -> 559 us; 8 chunks 606, 13 chunks 736: the prefetches share the SM's bulk-copy engine with
+    // the copies).  With one CTA per SM the 9-deep ring already covers a dependency level and every prefetch costs
+    // (88 -> 102 us on the per-GPU shard of the 8-GPU run): off.
+    c->l2_prefetch_now = (c->warps == kb::kWarps) ? 3 : 0;
+  } else {
+    c->l2_prefetch_now = c->l2_prefetch;
+  }
+  c->stats[26] = c->l2_prefetch_now;
   c->stats[16] = c->fused_ok ? 1.0 : 0.0;
   c->stats[17] = c->nb;
   c->stats[18] = c->vec_threads;
@@ -1021,6 +1071,7 @@ void launch_stream(Ctx* c, const StreamIo& io, const int* done_at, int iter, int
   std::memset(&P, 0, sizeof(P));
   P.ctas = c->d_ctas.p;
   P.stream = c->d_stream.p;
+  P.chunk_units = c->d_chunk_units.p;
   P.l2g = c->d_l2g.p;
   P.imap = c->d_imap.p;
   P.x_gamma = io.x_gamma;
@@ -1035,7 +1086,9 @@ void launch_stream(Ctx* c, const StreamIo& io, const int* done_at, int iter, int
   P.done_at = done_at;
   P.iter = iter;
   P.unit_col0 = unit_col0;
-  P.nstages = c->stages;
+  P.nstages = stream_stages(c, R);
+  P.prefetch_chunks = c->l2_prefetch_now;
+  P.prefetch_mode = c->l2_prefetch_mode;
   P.dbg = nullptr;
   P.dbg_flags = c->dbg_flags;
   if (c->debug_timing) {
@@ -1108,23 +1161,53 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
   // rows per CTA: 32 measured best from 32 to 256 local subdomains (8 / 16 / 64 slower: profiles/README.md)
   P.rows_per_cta = c->gemv_rows > 0 ? c->gemv_rows : kb::kGemvRowsPerCta;
   dim3 grid((unsigned)((c->max_gd + P.rows_per_cta - 1) / P.rows_per_cta), (unsigned)nloc, 1);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)c->max_gd * 8;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (c->pdl_now) {
-    cudaLaunchConfig_t cfg;
-    std::memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(256, 1, 1);
-    cfg.dynamicSmemBytes = (size_t)c->max_gd * 8;
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::dense_gemv_kernel, P));
-  } else {
-    kb::dense_gemv_kernel<<<grid, 256, (size_t)c->max_gd * 8, c->stream>>>(P);
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
-  CUDA_TRY(cudaGetLastError());
+  // The Neumann-Neumann blocks are read once per iteration, the factor stream (7.5 x their size) in between.
+  // Where they fit (the per-GPU shard of a multi-GPU run: 57 MB of the 126 MB L2 at 4M DOF / 8 GPUs) they are kept
+  // in the persisting part of the L2: the access-policy window of THIS launch marks their lines persisting, the
+  // stream kernel's bulk copies (no window) cannot evict them.  Larger pools keep the fraction that fits.
+  if (c->l2_persist != 0 && mats == c->d_pinv.p && mats != nullptr) {
+    if (c->l2_window_for != mats) {
+      int max_persist = 0, max_window = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device));
+      CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
+      const size_t bytes = (size_t)c->mat_off[nloc] * 8;
+      c->l2_window_bytes = std::min(bytes, (size_t)std::max(max_window, 0));
+      c->l2_hit_ratio = 0.0f;
+      if (max_persist > 0 && c->l2_window_bytes > 0) {
+        const size_t set_aside = (size_t)max_persist;
+        CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+        c->l2_hit_ratio = (float)std::min(1.0, 0.95 * (double)set_aside / (double)c->l2_window_bytes);
+        if (c->l2_persist < 0 && c->l2_hit_ratio < 0.5f) c->l2_hit_ratio = 0.0f;   // automatic: only when it pays
+      }
+      c->l2_window_for = mats;
+      c->stats[25] = c->l2_hit_ratio;
+    }
+    if (c->l2_hit_ratio > 0.0f) {
+      attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[na].val.accessPolicyWindow.base_ptr = const_cast<double*>(mats);
+      attr[na].val.accessPolicyWindow.num_bytes = c->l2_window_bytes;
+      attr[na].val.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
+      attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      ++na;
+    }
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kb::dense_gemv_kernel, P));
   c->launches++;
 }
 
@@ -1591,6 +1674,7 @@ int kb200_destroy(kb200_handle h) {
   return guarded([&]() {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->l2_window_for != nullptr && h->l2_hit_ratio > 0.0f) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     cudaStreamSynchronize(h->stream);
     if (!h->member_of)
       for (int r = 0; r < kb::kMaxPeers; ++r)
@@ -1672,6 +1756,17 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
       require(!h->finalized && (value == 0 || value == 8 || value == 16 || value == 24),
               "warps is 0 (automatic), 8, 16 or 24, before the first operation");
       h->warps = (int)value;
+    } else if (k == "l2_prefetch") {
+      require(value >= -1 && value <= 32, "l2_prefetch is -1 (automatic) or a distance of 0..32 chunks");
+      h->l2_prefetch = (int)value;
+      if (value >= 0) h->l2_prefetch_now = (int)value;
+    } else if (k == "l2_prefetch_mode") {
+      require(value == 0 || value == 1, "l2_prefetch_mode is 0 or 1");
+      h->l2_prefetch_mode = (int)value;
+    } else if (k == "l2_persist") {
+      require(value == -1 || value == 0 || value == 1, "l2_persist is -1 (automatic), 0 or 1");
+      h->l2_persist = (int)value;
+      h->l2_window_for = nullptr;
     } else if (k == "warp_private") {
       require(!h->finalized && (value == 0 || value == 1), "warp_private is 0 or 1, before the first operation");
       h->warp_private = (int)value;
@@ -2868,7 +2963,7 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
     double acc[32];
     for (int i = 0; i < 32; ++i) acc[i] = h->grp->members[0]->stats[i];
     for (size_t k = 1; k < h->grp->members.size(); ++k)
-      for (int i : {0, 1, 2, 3, 4, 8, 10, 23}) acc[i] += h->grp->members[k]->stats[i];
+      for (int i : {0, 1, 2, 3, 4, 8, 10, 23, 24}) acc[i] += h->grp->members[k]->stats[i];
     for (int64_t i = 0; stats && i < n && i < 32; ++i) stats[i] = acc[i];
     return KB200_OK;
   }

@@ -23,6 +23,7 @@ namespace cg = cooperative_groups;
 struct StreamParams {
   const CtaDesc* ctas;
   const uint8_t* stream;  // packet streams of all CTAs (chunk aligned)
+  const uint16_t* chunk_units;  // used 16-byte units of every chunk of the pool (plan.h): only those are copied
   const int32_t* l2g;
   const int32_t* imap;
   const double* x_gamma;  // interface vector (MODE_APPLY / MODE_BACKSUB)
@@ -38,15 +39,20 @@ struct StreamParams {
   int64_t ldx, ldi, ldo;
   int unit_col0;          // MODE_UNIT: columns unit_col0 + R*blockIdx.y + j
   int nstages;            // ring depth (<= kMaxStages)
+  int prefetch_chunks;    // L2 prefetch distance of the producer warp in chunks (0: off, <= 32)
+  int prefetch_mode;      // 0: cp.async.bulk.prefetch.L2 per chunk, 1: prefetch.global.L2 per 128-byte line
   long long* dbg;         // optional: 16 clock64 stamps per CTA (development aid)
   int dbg_flags;          // development aid: 1 = skip packet arithmetic, 2 = skip level barriers
 };
 
 constexpr int kMaxStages = 12;
-constexpr int kDbgSlots = 64;  // clock stamps per CTA: 16 phase stamps + 4 counters per consumer warp (KB200_SLICE_PROF)
 #ifdef KB200_SLICE_PROF
+// instrumented build: 16 phase stamps + 4 counters per consumer warp (slots 16..47) + from slot 64 on the clock of
+// consumer warp 0 at every section start (stored negated) and after every level barrier
+constexpr int kDbgSlots = 320;
 #define KB_PROF(x) x
 #else
+constexpr int kDbgSlots = 64;  // clock stamps per CTA: 16 phase stamps
 #define KB_PROF(x)
 #endif
 // consumer warps per CTA: kWarps (8; two CTAs per SM) or 16 (one CTA per SM, for grids that leave SMs
@@ -110,22 +116,71 @@ struct StreamCtx {
   cg::cluster_group* cluster;
   uint32_t stage, phase;   // ring position (same sequence on both sides); phase = parity of the stage's use count
   uint32_t nst;
+  // producer warp: sliding window over the chunk-size table (lane l holds the entry of chunk ubase + l in
+  // ucur and of chunk ubase + 32 + l in unxt, fetched one window ahead of its use)
+  const uint16_t* units;
+  uint32_t nchunks, ubase, ucur, unxt;
+  int pf_mode;             // 0: bulk prefetches, 1: line prefetches
+  uint32_t pf, pf_done;    // L2 prefetch distance in chunks (0: off) / first chunk not yet asked for
   int dbg_flags;
   int warp, lane;
-  KB_PROF(long long t_slice; long long n_slice; long long t_bar; long long t_wait;)
+  KB_PROF(long long t_slice; long long n_slice; long long t_bar; long long t_wait; long long* lvlp; int nlvl;)
 };
 
 // Producer warp: stream the chunks of one section into the ring.
+__device__ __forceinline__ uint32_t window_load(const StreamCtx& cx, uint32_t first) {
+  const uint32_t i = first + (uint32_t)cx.lane;
+  return i < cx.nchunks ? (uint32_t)__ldg(cx.units + i) : 0u;
+}
+// L2 prefetch of a byte range (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void produce_section(StreamCtx& cx, int sec) {
   const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec];
   for (uint32_t ch = c0; ch < c1; ++ch) {
     const uint32_t stage = cx.stage;
+    // bytes of the chunk that carry data (the padding behind them stays in HBM)
+    while (ch >= cx.ubase + 32u) {  // (twice only when a whole window was skipped with its section)
+      cx.ubase += 32u;
+      cx.ucur = cx.unxt;
+      cx.unxt = window_load(cx, cx.ubase + 32u);
+    }
+    const uint32_t bytes = __shfl_sync(0xffffffffu, cx.ucur, (int)(ch - cx.ubase)) * 16u;
+    // L2 PREFETCH.  The CTAs of a launch walk the same program on similar subdomains: they sit in the latency-bound
+    // small levels together and ask for the data-heavy levels together, so HBM idles and saturates in turns while
+    // the ring (a few chunks) cannot look further ahead.  The producer therefore asks the L2 for the chunks up to
+    // `pf` ahead of the one it copies: HBM streams at its own pace into the 126 MB L2, the bulk copies of the
+    // data-heavy levels then run at L2 speed.  (The window holds the sizes of chunks ubase .. ubase + 63.)
+    if (cx.pf > 0u) {
+      if (cx.pf_done < ch + 1u) cx.pf_done = ch + 1u;
+      const uint32_t target = min(min(ch + 1u + cx.pf, cx.nchunks), cx.ubase + 64u);
+      while (cx.pf_done < target) {
+        if (cx.pf_mode == 0) {   // one bulk prefetch per chunk (they share the SM's bulk-copy engine with the real copies)
+          const uint32_t mine = cx.pf_done + (uint32_t)cx.lane;
+          const uint32_t rel = mine - cx.ubase;     // < 64 + 32
+          const uint32_t lo = __shfl_sync(0xffffffffu, cx.ucur, (int)(rel & 31u));
+          const uint32_t hi = __shfl_sync(0xffffffffu, cx.unxt, (int)(rel & 31u));
+          const uint32_t u = rel < 32u ? lo : hi;
+          if (mine < target && u != 0u) prefetch_l2(cx.gstream + (size_t)mine * kChunkBytes, u * 16u);
+          cx.pf_done = min(cx.pf_done + 32u, target);
+        } else {                 // line prefetches from the producer warp's own load pipe (128 B per lane and instruction)
+          const uint32_t rel = cx.pf_done - cx.ubase;   // < 64
+          const uint32_t nb = (rel < 32u ? __shfl_sync(0xffffffffu, cx.ucur, (int)rel)
+                                         : __shfl_sync(0xffffffffu, cx.unxt, (int)(rel - 32u))) * 16u;
+          const uint8_t* src = cx.gstream + (size_t)cx.pf_done * kChunkBytes;
+          for (uint32_t o = (uint32_t)cx.lane * 128u; o < nb; o += 32u * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+          cx.pf_done += 1u;
+        }
+      }
+    }
     // the producer waits for the previous use of the stage to be released: parity phase^1; the very
     // first pass over the ring finds the barriers in their initial phase, which try_wait(1) accepts
     mbar_wait(&cx.empty_bar[stage], cx.phase ^ 1u);
     if (cx.lane == 0) {
-      mbar_expect_tx(&cx.full_bar[stage], kChunkBytes);
-      tma_load_1d(cx.ring + stage * kChunkBytes, cx.gstream + (size_t)ch * kChunkBytes, kChunkBytes, &cx.full_bar[stage]);
+      mbar_expect_tx(&cx.full_bar[stage], bytes);
+      tma_load_1d(cx.ring + stage * kChunkBytes, cx.gstream + (size_t)ch * kChunkBytes, bytes, &cx.full_bar[stage]);
     }
     __syncwarp();
     if (++cx.stage == cx.nst) {
@@ -214,7 +269,9 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
   }
   // entry (k, lane) at k * W + lane; padding entries are (0.0, col 0)
   const double* vp = reinterpret_cast<const double*>(sl + 16 + 16 * nrows) + lane;
-  const uint16_t* cp = reinterpret_cast<const uint16_t*>(sl + hq.w) + lane;
+  // columns: one 32-bit word per lane and PAIR of steps (low half = even step): half the shared-memory
+  // wavefronts and load instructions of a 16-bit load per step
+  const uint32_t* cp = reinterpret_cast<const uint32_t*>(sl + hq.w) + lane;
   double a0[R], a1[R], a2[R], a3[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) a0[j] = a1[j] = a2[j] = a3[j] = 0.0;
@@ -223,7 +280,8 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
 #pragma unroll 1
     for (; k >= 4; k -= 4) {
       const double v0 = vp[0], v1 = vp[W], v2 = vp[2 * W], v3 = vp[3 * W];
-      const uint32_t c0 = cp[0], c1 = cp[W], c2 = cp[2 * W], c3 = cp[3 * W];
+      const uint32_t cc0 = cp[0], cc1 = cp[W];
+      const uint32_t c0 = cc0 & 0xffffu, c1 = cc0 >> 16, c2 = cc1 & 0xffffu, c3 = cc1 >> 16;
       double s0[R], s1[R], s2[R], s3[R];
       load_slot<R>(S, c0, s0);
       load_slot<R>(S, c1, s1);
@@ -237,12 +295,13 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
         a3[j] = fma(v3, s3[j], a3[j]);
       }
       vp += 4 * W;
-      cp += 4 * W;
+      cp += 2 * W;
     }
     // association of the sums: step j feeds accumulator j & 3 (the emulator follows the same rule)
     if (k & 2) {
       const double v0 = vp[0], v1 = vp[W];
-      const uint32_t c0 = cp[0], c1 = cp[W];
+      const uint32_t cc0 = cp[0];
+      const uint32_t c0 = cc0 & 0xffffu, c1 = cc0 >> 16;
       double s0[R], s1[R];
       load_slot<R>(S, c0, s0);
       load_slot<R>(S, c1, s1);
@@ -252,11 +311,11 @@ __device__ __forceinline__ void process_slice(StreamCtx& cx, const uint8_t* sl, 
         a1[j] = fma(v1, s1[j], a1[j]);
       }
       vp += 2 * W;
-      cp += 2 * W;
+      cp += W;
     }
     if (k & 1) {
       const double v0 = vp[0];
-      const uint32_t c0 = cp[0];
+      const uint32_t c0 = cp[0] & 0xffffu;
       double s0[R];
       load_slot<R>(S, c0, s0);
 #pragma unroll
@@ -294,6 +353,7 @@ template <bool kTop, int NW, int R>
 __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double sign) {
   const uint32_t c0 = cx.D->sec_chunk0[sec], c1 = cx.D->sec_chunk1[sec];
   const int lane = cx.lane, warp = cx.warp;
+  KB_PROF(if (cx.lvlp != nullptr && warp == 0 && lane == 0 && cx.nlvl < kDbgSlots - 64) cx.lvlp[cx.nlvl++] = -clock64();)
   for (uint32_t ch = c0; ch < c1; ++ch) {
     const uint32_t stage = cx.stage;
     KB_PROF(const long long tw0 = clock64();)
@@ -309,6 +369,7 @@ __device__ __forceinline__ void consume_section(StreamCtx& cx, int sec, double s
 #ifdef KB200_SLICE_PROF
         if (kTop) cluster_level_sync<NW>(cx);
         else if (!(cx.dbg_flags & 2)) consumer_barrier<NW>();
+        if (cx.lvlp != nullptr && warp == 0 && lane == 0 && cx.nlvl < kDbgSlots - 64) cx.lvlp[cx.nlvl++] = clock64();
 #else
         if (kTop) cluster_level_sync<NW>(cx);
         else consumer_barrier<NW>();
@@ -411,11 +472,23 @@ __global__ void __launch_bounds__(stream_threads(NW), (NW == kWarps && R == 1) ?
   cx.stage = 0;
   cx.phase = 0;
   cx.nst = (uint32_t)P.nstages;
+  cx.units = P.chunk_units + D.stream_off / kChunkBytes;
+  cx.nchunks = D.sec_chunk1[NSEC - 1];
+  cx.ubase = 0;
+  cx.ucur = cx.unxt = 0;
+  cx.pf = (uint32_t)P.prefetch_chunks;
+  cx.pf_mode = P.prefetch_mode;
+  cx.pf_done = 0;
   cx.dbg_flags = P.dbg_flags;
   cx.warp = warp;
   cx.lane = lane;
-  KB_PROF(cx.t_slice = 0; cx.n_slice = 0; cx.t_bar = 0; cx.t_wait = 0;)
+  KB_PROF(cx.t_slice = 0; cx.n_slice = 0; cx.t_bar = 0; cx.t_wait = 0; cx.nlvl = 0;
+          cx.lvlp = P.dbg != nullptr ? P.dbg + (size_t)blockIdx.x * kDbgSlots + 64 : nullptr;)
   const bool producer = warp == NW;
+  if (producer) {
+    cx.ucur = window_load(cx, 0u);
+    cx.unxt = window_load(cx, 32u);
+  }
   auto stamp = [&](int i) { if (P.dbg != nullptr && tid == 0) P.dbg[(size_t)blockIdx.x * kDbgSlots + i] = clock64(); };
   stamp(0);
   constexpr bool kHasInit = MODE == MODE_APPLY || MODE == MODE_UNIT || MODE == MODE_BACKSUB;

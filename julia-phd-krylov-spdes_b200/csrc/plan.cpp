@@ -51,6 +51,7 @@ inline int ilog2(int p) {
 struct CtaStream {
   std::vector<uint8_t> bytes;
   std::vector<ValRef> refs;  // slot offsets relative to the CTA stream
+  std::vector<uint16_t> chunk_units;  // used 16-byte units of every chunk (see DomainPlan::chunk_units)
   int64_t n_entries = 0, n_rows = 0, n_packets = 0, lane_steps = 0;
   size_t room() const { return kChunkBytes - (bytes.size() % kChunkBytes); }
   void pad_to_chunk() {
@@ -64,8 +65,8 @@ struct CtaStream {
 };
 
 // Serialise one slice (rows ord[p..q) of `rows`, T lanes per row) -- layout in plan.h.
-SliceBytes make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const std::vector<uint32_t>& ord,
-                      size_t p, size_t q, int T, CtaStream& cs) {
+SliceBytes make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptions& opt,
+                      const std::vector<uint32_t>& ord, size_t p, size_t q, int T, CtaStream& cs) {
   const int nr = (int)(q - p);
   const uint32_t maxlen = rows[ord[p]].len;
   const uint32_t kmax = (maxlen + T - 1) / T;
@@ -75,22 +76,68 @@ SliceBytes make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const 
   std::vector<uint16_t> pc;
   std::vector<uint32_t> ps;
   int64_t real = 0;
-  for (uint32_t k = 0; k < kmax; ++k)
+  // WHICH entry of its row a lane takes at a step is free (any order of a row's terms is a valid sum; the order
+  // chosen here is the association order of the plan, followed by the device and by the emulator alike).  It is
+  // chosen against shared-memory bank conflicts of the gathered S[col]: a 64-bit load of a warp is served per
+  // half-warp, in as many passes as distinct 8-byte words of one bank pair (slot mod 16) are requested; lanes
+  // reading the same slot share a pass.  Greedy: every lane takes the first remaining entry of its row whose
+  // bank pair is still free in its half-warp at this step (or whose slot is already being read there).
+  // Position (k, t) of a row holds a real entry iff k * T + t < len, as before; padding entries repeat a slot of
+  // their half-warp (value 0).
+  std::vector<std::vector<uint32_t>> left(nr);   // remaining entries of every row, original order
+  for (int g = 0; g < nr; ++g) {
+    const TmpRow& tr = rows[ord[p + g]];
+    left[g].resize(tr.len);
+    for (uint32_t e = 0; e < tr.len; ++e) left[g][e] = tr.ebeg + e;
+  }
+  for (uint32_t k = 0; k < kmax; ++k) {
+    int owner_slot[2][16];
+    for (auto& h : owner_slot)
+      for (int& v : h) v = -1;
+    const size_t step0 = pv.size();
+    std::vector<int> pad_lanes;
     for (int lane = 0; lane < nr * T; ++lane) {
-      const int g = lane / T, t = lane % T;
+      const int g = lane / T, t = lane % T, half = lane / 16;
       const TmpRow& tr = rows[ord[p + g]];
       const uint32_t idx = k * T + t;
       if (idx < tr.len) {
-        pv.push_back(sc.vals[tr.ebeg + idx]);
-        pc.push_back(sc.cols[tr.ebeg + idx]);
-        ps.push_back(sc.srcs[tr.ebeg + idx]);
+        std::vector<uint32_t>& rem = left[g];
+        size_t pick = 0;
+        if (opt.avoid_bank_conflicts) {
+          for (size_t q = 0; q < rem.size(); ++q) {
+            const int col = sc.cols[rem[q]];
+            const int o = owner_slot[half][col & 15];
+            if (o < 0 || o == col) {
+              pick = q;
+              break;
+            }
+          }
+        }
+        const uint32_t e = rem[pick];
+        rem.erase(rem.begin() + (std::ptrdiff_t)pick);
+        const int col = sc.cols[e];
+        if (owner_slot[half][col & 15] < 0) owner_slot[half][col & 15] = col;
+        pv.push_back(sc.vals[e]);
+        pc.push_back(sc.cols[e]);
+        ps.push_back(sc.srcs[e]);
         ++real;
       } else {
         pv.push_back(0.0);
         pc.push_back(0);
         ps.push_back(kNoSrc);
+        pad_lanes.push_back(lane);
       }
     }
+    if (opt.avoid_bank_conflicts)
+      for (int lane : pad_lanes) {   // a padding lane re-reads a slot its half-warp reads anyway
+        const int half = lane / 16;
+        for (int l2 = half * 16; l2 < std::min(nr * T, half * 16 + 16); ++l2)
+          if (ps[step0 + (size_t)l2] != kNoSrc) {
+            pc[step0 + (size_t)lane] = pc[step0 + (size_t)l2];
+            break;
+          }
+      }
+  }
   if (pv.size() > 65535u || kmax > 65535u) throw std::runtime_error("internal: slice too large");
   SliceBytes out;
   std::vector<uint8_t>& b = out.b;
@@ -123,7 +170,16 @@ SliceBytes make_slice(const std::vector<TmpRow>& rows, const Scratch& sc, const 
     for (size_t k = 0; k < ps.size(); ++k)
       if (ps[k] != kNoSrc) out.refs.push_back(ValRef{v0 + (uint32_t)k, ps[k]});
     put(pv.data(), pv.size() * 8);
-    put(pc.data(), pc.size() * 2);
+    // columns: one 32-bit word per lane and pair of steps (low half = even step; an odd last step is repeated)
+    const size_t Wd = (size_t)nr * T;
+    std::vector<uint32_t> pc2(((size_t)kmax + 1) / 2 * Wd);
+    for (size_t pr = 0; pr < ((size_t)kmax + 1) / 2; ++pr)
+      for (size_t lane = 0; lane < Wd; ++lane) {
+        const uint32_t lo = pc[(2 * pr) * Wd + lane];
+        const uint32_t hi = (2 * pr + 1 < kmax) ? pc[(2 * pr + 1) * Wd + lane] : lo;
+        pc2[pr * Wd + lane] = lo | (hi << 16);
+      }
+    put(pc2.data(), pc2.size() * 4);
   }
   while (b.size() % 16) b.push_back(0);
   if (b.size() + (size_t)kChunkDirBytes + 16 > (size_t)kChunkBytes)
@@ -184,6 +240,8 @@ struct ChunkBuilder {
       cs.bytes.insert(cs.bytes.end(), slices[k].b.begin(), slices[k].b.end());
     }
     if (cs.bytes.size() - base != o) throw std::runtime_error("internal: chunk size mismatch");
+    if (cs.chunk_units.size() != base / kChunkBytes) throw std::runtime_error("internal: chunk table out of phase");
+    cs.chunk_units.push_back((uint16_t)((o + 15) / 16));
     cs.pad_to_chunk();
     for (auto& t : tok) t.clear();
     slices.clear();
@@ -250,7 +308,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
       while (q < j && (int)(q - p) < cap && t_of(rows[ord[q]].len) == T &&
              (rows[ord[q]].len >= min_len || len0 - rows[ord[q]].len <= 1))
         ++q;
-      slices.push_back(make_slice(rows, sc, ord, p, q, T, cs));
+      slices.push_back(make_slice(rows, sc, opt, ord, p, q, T, cs));
       p = q;
     }
   };
@@ -296,6 +354,7 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
       std::iota(so.begin(), so.end(), (size_t)0);
       std::stable_sort(so.begin(), so.end(), [&](size_t a, size_t b) { return cost(slices[a]) > cost(slices[b]); });
       std::vector<int64_t> load(NW, 0);
+      std::vector<int> owner(slices.size(), 0);
       // rotate the starting warp with the level so that no warp always gets the heaviest slice
       for (size_t k : so) {
         int best = lev % NW;
@@ -304,7 +363,34 @@ void emit_section(std::vector<TmpRow>& rows, const Scratch& sc, const BuildOptio
           if (load[w] < load[best]) best = w;
         }
         load[best] += cost(slices[k]);
-        cb.add_slice(best, std::move(slices[k]));
+        owner[k] = best;
+      }
+      // Placement into chunks.  A slice cannot straddle a chunk boundary, and the stream is HBM traffic: what is
+      // left of a chunk when the next slice does not fit is read for nothing (12 % of the stream when slices are
+      // placed strictly in order).  The order of the slices of a level inside the stream is free (a warp finds
+      // its slices through its token list), so the tail of a chunk takes the heaviest remaining slice of the
+      // level that still fits (first fit, decreasing cost); a chunk is only closed when none does.
+      if (opt.fill_chunks) {
+        std::vector<char> placed(slices.size(), 0);
+        size_t left = slices.size(), first = 0;
+        while (left > 0) {
+          bool any = false;
+          for (size_t q = first; q < so.size(); ++q) {
+            const size_t k = so[q];
+            if (placed[k] || !cb.fits(1, slices[k].b.size())) continue;
+            cb.add_slice(owner[k], std::move(slices[k]));
+            placed[k] = 1;
+            --left;
+            any = true;
+          }
+          while (first < so.size() && placed[so[first]]) ++first;
+          if (!any) {
+            if (cb.empty()) throw std::runtime_error("internal: slice exceeds a chunk");
+            cb.flush();
+          }
+        }
+      } else {
+        for (size_t k : so) cb.add_slice(owner[k], std::move(slices[k]));
       }
       cb.add_barrier();
       i = j;
@@ -1012,6 +1098,8 @@ void build_domain_plan(const DomainIn& in, const BuildOptions& opt, DomainPlan& 
       }
     }
     out.stream.insert(out.stream.end(), cs.bytes.begin(), cs.bytes.end());
+    if (cs.chunk_units.size() * (size_t)kChunkBytes != cs.bytes.size()) throw std::runtime_error("internal: chunk table size");
+    out.chunk_units.insert(out.chunk_units.end(), cs.chunk_units.begin(), cs.chunk_units.end());
     out.n_entries += cs.n_entries;
     out.n_rows += cs.n_rows;
     out.n_packets += cs.n_packets;

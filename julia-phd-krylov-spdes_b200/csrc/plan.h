@@ -59,7 +59,8 @@ enum Section : int {
 // (longest-processing-time first on a latency estimate).  Every warp's program holds the same
 // sequence of barrier tokens.
 // Chunk:  [kChunkDirBytes: (NW+1) x uint16 first token of every warp][tokens, padded to 16 B][slices]
-// Slice:  [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][nent x uint16]  (+ padding to 16 B)
+// Slice:  [SliceHdr 16 B][nrows x RowRec 16 B][nent x double][ceil(kmax / 2) x nrows*T x uint32: the columns of
+//          two consecutive steps of a lane, low half = even step]  (+ padding to 16 B)
 //
 // Optionally (BuildOptions::warp_private) the bottom of the elimination forest is processed
 // warp-privately: the CTA's own nodes are cut once more into small subtrees that are bin-packed onto
@@ -77,7 +78,7 @@ struct alignas(16) SliceHdr {
   uint8_t nrows;
   uint16_t pad0_;
   uint32_t width;     // active lanes = nrows << tlog2 (precomputed for the device)
-  uint32_t cols_off;  // byte offset of the uint16 column indices from the slice start
+  uint32_t cols_off;  // byte offset of the packed column indices from the slice start
 };
 static_assert(sizeof(SliceHdr) == 16, "SliceHdr must be 16 bytes");
 
@@ -142,6 +143,9 @@ struct DmapRef {
 struct DomainPlan {
   std::vector<CtaDesc> ctas;      // csize descriptors (offsets local to this plan's pools)
   std::vector<uint8_t> stream;    // concatenated CTA streams (each a multiple of kChunkBytes)
+  // bytes of every chunk that carry data, in 16-byte units (directory + tokens + slices): the producer warp
+  // copies only those -- the padding behind them (a slice never straddles a chunk) is not HBM traffic
+  std::vector<uint16_t> chunk_units;
   std::vector<int32_t> imap;      // ownmap / topmap entries
   // value refresh (see above)
   std::vector<ValRef> refs;
@@ -168,6 +172,8 @@ struct BuildOptions {
   int merge_depth = 1;        // supernodes of `merge_depth` consecutive depths of the supernode tree share one inverted block
   int max_smem_doubles = 28000;
   int warps = kWarps;         // consumer warps of the kernel that will run the plan (8, 16 or 24): slot k of a level -> warp k % warps
+  int avoid_bank_conflicts = 1;  // 1: the entries of a row are dealt to the steps against bank conflicts of the gathered S[col]
+  int fill_chunks = 1;        // 1: the tail of a chunk takes any slice of the level that still fits (0: strict order)
   int warp_private = 0;       // 1: subtrees near the leaves are processed warp-privately (no CTA barriers)
   int private_split = 2;      // aim at about private_split x kWarps private subtrees per CTA
 };

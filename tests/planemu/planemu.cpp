@@ -51,6 +51,11 @@ struct Emu {
         for (int v = 0; v < NW; ++v)
           if (dir[v] > dir[v + 1]) throw std::runtime_error("chunk directory not monotone");
         if ((size_t)kChunkDirBytes + (size_t)dir[NW] * 2 > (size_t)kChunkBytes) throw std::runtime_error("token table too large");
+        {
+          const size_t gch = (size_t)(chunk_ptr(c, k.ch) - P.stream.data()) / kChunkBytes;
+          if (gch >= P.chunk_units.size() || (size_t)kChunkDirBytes + (size_t)dir[NW] * 2 > (size_t)P.chunk_units[gch] * 16)
+            throw std::runtime_error("token table beyond the copied part of its chunk");
+        }
         k.tok = dir[w];
         k.end = dir[w + 1];
         if (k.tok < k.end) return;
@@ -99,8 +104,13 @@ struct Emu {
         std::memcpy(&sh, t.sl, sizeof(sh));
         const int T = 1 << sh.tlog2;
         if (sh.tlog2 > 5 || sh.nrows * T > 32 || sh.nrows == 0) throw std::runtime_error("bad slice shape");
-        const size_t bytes = sizeof(SliceHdr) + (size_t)sh.nrows * sizeof(RowRec) + (size_t)sh.nent * 10;
+        const size_t bytes = sizeof(SliceHdr) + (size_t)sh.nrows * sizeof(RowRec) + (size_t)sh.nent * 8 +
+                             ((size_t)sh.kmax + 1) / 2 * ((size_t)sh.nrows * T) * 4;
         if ((size_t)(t.sl - t.chunk) + bytes > (size_t)kChunkBytes) throw std::runtime_error("slice exceeds its chunk");
+        // the producer copies only the used part of a chunk (DomainPlan::chunk_units)
+        const size_t gch = (size_t)(t.chunk - P.stream.data()) / kChunkBytes;
+        if (gch >= P.chunk_units.size() || (size_t)(t.sl - t.chunk) + bytes > (size_t)P.chunk_units[gch] * 16)
+          throw std::runtime_error("slice beyond the copied part of its chunk");
         const RowRec* rr = reinterpret_cast<const RowRec*>(t.sl + sizeof(SliceHdr));
         for (int g = 0; g < sh.nrows; ++g) {
           if (rr[g].dst >= D.smem_doubles) throw std::runtime_error("dst out of range");
@@ -127,7 +137,8 @@ struct Emu {
         const int T = 1 << sh.tlog2;
         const RowRec* rr = reinterpret_cast<const RowRec*>(t.sl + sizeof(SliceHdr));
         const double* vals = reinterpret_cast<const double*>(t.sl + sizeof(SliceHdr) + sh.nrows * sizeof(RowRec));
-        const uint16_t* cols = reinterpret_cast<const uint16_t*>(vals + sh.nent);
+        const uint32_t* cols2 = reinterpret_cast<const uint32_t*>(vals + sh.nent);   // a lane's columns of two steps per word
+        if (reinterpret_cast<const uint8_t*>(cols2) != t.sl + sh.cols_off) throw std::runtime_error("cols_off mismatch");
         std::vector<std::array<double, 4>> part(32, std::array<double, 4>{0, 0, 0, 0});
         const uint32_t Wact = (uint32_t)sh.nrows * T;
         if ((uint32_t)sh.kmax * Wact != sh.nent) throw std::runtime_error("slice entry count mismatch");
@@ -140,7 +151,8 @@ struct Emu {
           for (uint32_t lane = 0; lane < Wact; ++lane) {
             const int g = lane / T, tt = lane % T;
             const uint32_t pos = k * Wact + lane;
-            const uint32_t col = cols[pos];
+            const uint32_t word = cols2[(k / 2) * Wact + lane];
+            const uint32_t col = (k & 1) ? (word >> 16) : (word & 0xffffu);
             if (col >= (uint32_t)D.smem_doubles) throw std::runtime_error("col out of range");
             if (k * T + tt < rr[g].len) {
               if (mine_dst[col]) throw std::runtime_error("a slice reads a value it produces");
@@ -259,6 +271,11 @@ extern "C" int planemu_run(int n_I, int n_gd, const int32_t* perm, const int32_t
       stats[6] = (double)P.n_rows;
       stats[7] = (double)D0.smem_doubles;
       stats[8] = (double)P.stream.size();
+      {
+        double rb = 0.0;
+        for (uint16_t u : P.chunk_units) rb += 16.0 * u;
+        if (std::getenv("KB200_STATS_READ_BYTES")) stats[8] = rb;   // bytes the producer copies
+      }
       stats[11] = (double)P.lane_steps;
       stats[12] = (double)P.n_private_rows;
       stats[13] = (double)P.n_private_slices;

@@ -85,4 +85,13 @@ def test_gpu_posthoc_recycling_matches_oracle(kind, nx, ndom, nvec, spdim):
     # unpreconditioned operator path and the assembled operator run through the same entry points
     xa, ita, resa, Wa = fg(S, bs, np.zeros(n), None, nvec, spdim)
     xao, itao, resao, Wao = fo(A, bs, np.zeros(n), lambda r: r.copy(), nvec, spdim)
-    assert abs(ita - itao) <= 1 and np.linalg.norm(xa - xao) <= 1e-5 * np.linalg.norm(xao)
+    # Unpreconditioned CG on the lognormal Schur complement takes ~200 ill-conditioned iterations: the stopping index
+    # of the ORACLE itself moves by a few iterations when its operator input is perturbed by one ulp (198 .. 201 at
+    # 97^2 / 9).  The GPU is held to the envelope of those CPU runs +- 1 and to 20 x their distance in x.
+    its, dx = [itao], [0.0]
+    for e in (2.0 ** -52, -2.0 ** -52, 2.0 ** -51):
+        xp, itp, _, _ = fo(lambda v, e=e: A(v * (1.0 + e)), bs, np.zeros(n), lambda r: r.copy(), nvec, spdim)
+        its.append(itp)
+        dx.append(np.linalg.norm(xp - xao) / np.linalg.norm(xao))
+    assert min(its) - 1 <= ita <= max(its) + 1
+    assert np.linalg.norm(xa - xao) <= max(1e-5, 20 * max(dx)) * np.linalg.norm(xao)
