@@ -141,7 +141,7 @@ struct kb200_ctx {
   int l2_prefetch_mode = 0;         // option: 0 = bulk prefetch per chunk, 1 = line prefetches
   int l2_prefetch_now = 0;          // the distance launches use (set by finalize / the option)
   int l2_persist = -1;              // option: Neumann-Neumann blocks in the persisting L2 (-1: automatic = when at least half of them fits)
-  const double* l2_window_for = nullptr;
+  size_t l2_set_aside = 0, l2_max_window = 0;   // persisting L2 carve-out of the device / largest window, set by finalize
   size_t l2_window_bytes = 0;
   float l2_hit_ratio = 0.0f;
   bool stages_auto = true;   // ring depth picked by finalize (option stages = 0)
@@ -450,6 +450,7 @@ int stream_rhs_block(const Ctx* c, int64_t want) {
 // ---- finalize: build plans, upload -------------------------------------------------------------
 void refresh_values(Ctx* c);
 void fetch_stale_values(Ctx* c);
+void update_l2_window(Ctx* c);
 
 void finalize(Ctx* c) {
   if (c->finalized) {
@@ -736,6 +737,16 @@ void finalize(Ctx* c) {
   }
   if (c->have_pinv) upload_dense(c->d_pinv, true);
   if (c->have_sd && !c->sd_on_device_only) upload_dense(c->d_sd, false);
+  if (c->l2_persist != 0) {   // persisting L2 carve-out for the Neumann-Neumann blocks (launch_gemv)
+    int max_persist = 0, max_window = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
+    if (max_persist > 0 && max_window > 0) {
+      CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+      c->l2_set_aside = (size_t)max_persist;
+      c->l2_max_window = (size_t)max_window;
+    }
+  }
   // vectors
   const int64_t ng = c->n_gamma;
   // block size of the interface-vector kernels: few large blocks when every assembly ends in a peer
@@ -840,6 +851,7 @@ void finalize(Ctx* c) {
   c->stats[21] = (double)c->analyses;
   c->stats[22] = (double)c->refreshes;
   c->stats[23] = (double)c->d_refs.n;
+  update_l2_window(c);
   c->finalized = true;  // host copies of the inputs are kept: value updates re-run the analysis
 }
 
@@ -1143,6 +1155,22 @@ void launch_stream(Ctx* c, const double* x_gamma, const double* bI, double* uI, 
   launch_stream<MODE>(c, io, done_at, iter, 1);
 }
 
+// Access-policy window of the Neumann-Neumann blocks (see launch_gemv).  No CUDA call that could synchronise the
+// device is made here: the set-aside itself is sized once, in finalize (a device-wide synchronisation while a peer's
+// exchange kernel waits for this member's next launch would stall members that share a device).
+void update_l2_window(Ctx* c) {
+  c->l2_window_bytes = 0;
+  c->l2_hit_ratio = 0.0f;
+  const int64_t nloc = c->d1 - c->d0;
+  if (c->l2_persist == 0 || c->d_pinv.p == nullptr || c->l2_set_aside == 0 || nloc <= 0) return;
+  const size_t bytes = (size_t)c->mat_off[nloc] * 8;
+  c->l2_window_bytes = std::min(bytes, c->l2_max_window);
+  if (c->l2_window_bytes == 0) return;
+  c->l2_hit_ratio = (float)std::min(1.0, 0.95 * (double)c->l2_set_aside / (double)c->l2_window_bytes);
+  if (c->l2_persist < 0 && c->l2_hit_ratio < 0.5f) c->l2_hit_ratio = 0.0f;   // automatic: only when it pays
+  c->stats[25] = c->l2_hit_ratio;
+}
+
 void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double* out_loc, const int* done_at,
                  int iter) {
   const int64_t nloc = c->d1 - c->d0;
@@ -1178,32 +1206,14 @@ void launch_gemv(Ctx* c, const double* mats, const double* x, bool scale, double
   // Where they fit (the per-GPU shard of a multi-GPU run: 57 MB of the 126 MB L2 at 4M DOF / 8 GPUs) they are kept
   // in the persisting part of the L2: the access-policy window of THIS launch marks their lines persisting, the
   // stream kernel's bulk copies (no window) cannot evict them.  Larger pools keep the fraction that fits.
-  if (c->l2_persist != 0 && mats == c->d_pinv.p && mats != nullptr) {
-    if (c->l2_window_for != mats) {
-      int max_persist = 0, max_window = 0;
-      CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device));
-      CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device));
-      const size_t bytes = (size_t)c->mat_off[nloc] * 8;
-      c->l2_window_bytes = std::min(bytes, (size_t)std::max(max_window, 0));
-      c->l2_hit_ratio = 0.0f;
-      if (max_persist > 0 && c->l2_window_bytes > 0) {
-        const size_t set_aside = (size_t)max_persist;
-        CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
-        c->l2_hit_ratio = (float)std::min(1.0, 0.95 * (double)set_aside / (double)c->l2_window_bytes);
-        if (c->l2_persist < 0 && c->l2_hit_ratio < 0.5f) c->l2_hit_ratio = 0.0f;   // automatic: only when it pays
-      }
-      c->l2_window_for = mats;
-      c->stats[25] = c->l2_hit_ratio;
-    }
-    if (c->l2_hit_ratio > 0.0f) {
-      attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
-      attr[na].val.accessPolicyWindow.base_ptr = const_cast<double*>(mats);
-      attr[na].val.accessPolicyWindow.num_bytes = c->l2_window_bytes;
-      attr[na].val.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
-      attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      ++na;
-    }
+  if (c->l2_persist != 0 && mats == c->d_pinv.p && mats != nullptr && c->l2_hit_ratio > 0.0f) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[na].val.accessPolicyWindow.base_ptr = const_cast<double*>(mats);
+    attr[na].val.accessPolicyWindow.num_bytes = c->l2_window_bytes;
+    attr[na].val.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
+    attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
@@ -1524,11 +1534,23 @@ void host_apply(Ctx* c, OpKind op, const double* x, double* y, int64_t nrhs) {
   finalize(c);
   use_device(c);
   const int64_t n = c->n_gamma;
+  // an exchange kernel that gave up on a peer (time-out) must not pass for a result
+  const bool watch = c->world > 1;
+  int xfail = 0;
+  auto arm = [&]() {
+    if (watch) CUDA_TRY(cudaMemsetAsync(&c->d_state.p->fail, 0, sizeof(int), c->stream));
+  };
+  auto check = [&]() {
+    if (watch) CUDA_TRY(cudaMemcpyAsync(&xfail, &c->d_state.p->fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (xfail == 2) throw_on_fail(2);
+  };
   if (nrhs == 1) {
     h2d(c, c->d_x.p, x, n);
+    arm();
     apply_op(c, op, c->d_x.p, c->d_Ap.p, nullptr, nullptr, nullptr, 0, nullptr);
     d2h(c, y, c->d_Ap.p, n);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    check();
     return;
   }
   // blocks of right-hand sides: the factor stream / the dense blocks are read once per block
@@ -1539,9 +1561,10 @@ void host_apply(Ctx* c, OpKind op, const double* x, double* y, int64_t nrhs) {
   for (int64_t j0 = 0; j0 < nrhs; j0 += kb_) {
     const int64_t k = std::min(kb_, nrhs - j0);
     h2d(c, dX.p, x + j0 * n, n * k);
+    arm();
     apply_op_multi(c, op, dX.p, dY.p, k, MultiCtx(), nullptr);
     d2h(c, y + j0 * n, dY.p, n * k);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    check();
   }
 }
 
@@ -1674,7 +1697,7 @@ int kb200_destroy(kb200_handle h) {
   return guarded([&]() {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->l2_window_for != nullptr && h->l2_hit_ratio > 0.0f) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
+    if (h->l2_set_aside != 0 && h->l2_hit_ratio > 0.0f) cudaCtxResetPersistingL2Cache();   // hand the set-aside lines back
     cudaStreamSynchronize(h->stream);
     if (!h->member_of)
       for (int r = 0; r < kb::kMaxPeers; ++r)
@@ -1766,7 +1789,7 @@ int kb200_set_option(kb200_handle h, const char* name, int64_t value) {
     } else if (k == "l2_persist") {
       require(value == -1 || value == 0 || value == 1, "l2_persist is -1 (automatic), 0 or 1");
       h->l2_persist = (int)value;
-      h->l2_window_for = nullptr;
+      if (h->finalized) update_l2_window(h);
     } else if (k == "warp_private") {
       require(!h->finalized && (value == 0 || value == 1), "warp_private is 0 or 1, before the first operation");
       h->warp_private = (int)value;
@@ -2046,6 +2069,7 @@ static void store_dense(Ctx* h, int64_t d, const double* M, bool pinv) {
     CUDA_TRY(cudaMemcpyAsync(buf.p + h->mat_off[d - h->d0], dst.data(), dst.size() * 8, cudaMemcpyHostToDevice,
                              h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (pinv) update_l2_window(h);
   }
 }
 

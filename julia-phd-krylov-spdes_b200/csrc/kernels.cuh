@@ -622,6 +622,18 @@ struct GemvParams {
 };
 constexpr int kGemvRowsPerCta = 32;
 
+// the 16 loads of one 512-column stretch of a row, issued back to back (clamped addresses: a load beyond the row
+// end is multiplied by zero later)
+__device__ __forceinline__ void gemv_load16(const double* mrow, int j0, int lane, int n, double (&m)[16]) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    // unconditional volatile load: left to the compiler, each load is sunk next to its FMA and the row is read one
+    // latency at a time
+    const int j = min(j0 + lane + 32 * u, n - 1);
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(m[u]) : "l"(mrow + j));
+  }
+}
+
 __global__ void __launch_bounds__(256, 4) dense_gemv_kernel(const GemvParams P) {
   extern __shared__ double xs[];
   pdl_trigger();
@@ -632,8 +644,16 @@ __global__ void __launch_bounds__(256, 4) dense_gemv_kernel(const GemvParams P) 
   const int rpc = P.rows_per_cta;
   const int row0 = blockIdx.x * rpc;
   if (row0 >= n) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gb = P.G_base[d];
   const int32_t* l2g = P.l2g + gb;
+  const double* M = P.mats + P.mat_off[d];
+  // The matrix does not depend on x: the first row of every warp is requested BEFORE the gather of x_d (two
+  // dependent loads and a barrier), so the DRAM latency of the row and the staging of the vector overlap -- on the
+  // per-GPU shards of a multi-GPU run (a few rows per warp) that is most of the kernel.
+  double m[16];
+  const bool have0 = row0 + warp < n && warp < rpc;
+  if (have0) gemv_load16(M + (int64_t)(row0 + warp) * n, 0, lane, n, m);
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int g = l2g[j];
     double v = P.x[g];
@@ -641,8 +661,6 @@ __global__ void __launch_bounds__(256, 4) dense_gemv_kernel(const GemvParams P) 
     xs[j] = v;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double* M = P.mats + P.mat_off[d];
   for (int r = warp; r < rpc; r += 8) {
     const int i = row0 + r;
     if (i >= n) break;
@@ -651,14 +669,7 @@ __global__ void __launch_bounds__(256, 4) dense_gemv_kernel(const GemvParams P) 
     // 16 loads per lane in flight (a whole row of up to 512 entries at once): the kernel is bound by memory
     // latency, not by arithmetic; element j = j0 + lane + 32 u feeds accumulator u & 3 (fixed order)
     for (int j0 = 0; j0 < n; j0 += 512) {
-      double m[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        // clamped address, unconditional volatile load: the 16 loads are issued back to back (left to the
-        // compiler, each load is sunk next to its FMA and the row is read one latency at a time)
-        const int j = min(j0 + lane + 32 * u, n - 1);
-        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(m[u]) : "l"(mrow + j));
-      }
+      if (r != warp || j0 != 0) gemv_load16(mrow, j0, lane, n, m);   // (the first stretch of the first row is already here)
       __syncwarp();  // keeps the arithmetic below the block of loads
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
