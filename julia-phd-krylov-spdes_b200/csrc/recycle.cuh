@@ -668,3 +668,168 @@ static void posthoc_solve(Ctx* c, const double* b, double* x, const double* W, i
   *it_out = it;
   finish_timings(c, kt, T, launches0, tm);
 }
+
+// Thick-restart variants (trrrpcg / trrrdefpcg, trrrdefpcg.jl:234-355 / :48-199; trhrpcg / trhrdefpcg,
+// trhrdefpcg.jl:247-389 / :48-208): the recurrence of posthoc_solve (deflated by the ORIGINAL basis W throughout, device
+// bursts capturing Z = z / sqrt(r'z) or P = p columns), but the window of captured columns is cyclic and EVERY time it
+// is full the recycle basis W2 is replaced by the nvec lowest (harmonic) Ritz vectors of [W2 | window].  Without a
+// deflation basis the first window has spdim columns and projects onto them alone; later windows have spdim - nvec.
+// Device layout: V = [W2 (nvec columns) | window (spdim columns)], AV likewise.  A solve that stops before its first
+// window is full returns W2 = W (deflated variants) or zeros (the reference returns uninitialised memory there).  The
+// harmonic variants keep the reference's structural zeros in V'AV (blockdiag(W2'AW2, diag(P'AP)), trhrdefpcg.jl:170-177).
+static void thick_restart_solve(Ctx* c, const double* b, double* x, const double* W, int nvec, int spdim, int64_t maxit, double rtol, OpKind A,
+                                int precond, bool harmonic, int64_t* it_out, double* res_norm, double* W2_out, kb200_timings* tm) {
+  const int n = (int)c->n_gamma;
+  const bool defl = W != nullptr;
+  require(nvec >= 1 && spdim > nvec && spdim <= 4096, "need 1 <= nvec < spdim <= 4096");
+  if (maxit == 0) maxit = n;
+  require(maxit >= 1 && maxit < INT_MAX, "bad maxit");
+  kb200_timings T;
+  std::memset(&T, 0, sizeof(T));
+  const int64_t launches0 = c->launches;
+  KernelTimer kt(c);
+  DenseLa la(c);
+  RecycleVecs v(c, A, precond);
+  using RV = RecycleVecs;
+  const int ncols = nvec + spdim;
+  DevBuf<double> dV, dAV, dMAV, dW, dAW, dW2new;
+  dV.alloc((size_t)n * ncols);
+  dAV.alloc((size_t)n * ncols);
+  dW2new.alloc((size_t)n * nvec);
+  CUDA_TRY(cudaMemsetAsync(dV.p, 0, (size_t)n * ncols * 8, c->stream));
+  auto Ccol = [&](int j) { return dV.p + (size_t)(nvec + j) * n; };
+  h2d(c, v.col(RV::B), b, n, &T);
+  h2d(c, v.col(RV::X), x, n, &T);
+  CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+  std::vector<double> WtAW, WtW, WtAW_inv, WtW_inv, W2tAW2;
+  SmallLu luA;
+  DevBuf<double> dM, dMinv, dM2, dM2inv, dy, dmu, dy2, dmu2;
+  Defl D, DR;
+  if (defl) {
+    dW.alloc((size_t)n * nvec);
+    dAW.alloc((size_t)n * nvec);
+    h2d(c, dW.p, W, (int64_t)n * nvec, &T);
+    apply_op_multi(c, A, dW.p, dAW.p, nvec, MultiCtx(), &kt);                          // WtA' = A W          trrrdefpcg.jl:80-86
+    WtAW = sym_upper(gemm_tn_host(c, nvec, nvec, dAW.p, dW.p), nvec, nvec);            // Symmetric()         :87-90
+    WtW = sym_upper(gemm_tn_host(c, nvec, nvec, dW.p, dW.p), nvec, nvec);
+    W2tAW2 = WtAW;                                                                     // W2 = W              :91-93
+    CUDA_TRY(cudaMemcpyAsync(dV.p, dW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dAV.p, dAW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    luA.factor(nvec, WtAW);
+    invert_small(nvec, WtAW, WtAW_inv);
+    invert_small(nvec, WtW, WtW_inv);
+    auto up = [&](DevBuf<double>& buf, const std::vector<double>& src) {
+      buf.alloc(src.size());
+      CUDA_TRY(cudaMemcpyAsync(buf.p, src.data(), src.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    };
+    up(dM, WtAW);
+    up(dMinv, WtAW_inv);
+    up(dM2, WtW);
+    up(dM2inv, WtW_inv);
+    dy.alloc(nvec);
+    dmu.alloc(nvec);
+    dy2.alloc(nvec);
+    dmu2.alloc(nvec);
+    D.k = nvec;
+    D.W = dW.p;
+    D.AW = dAW.p;
+    D.M = dM.p;
+    D.Minv = dMinv.p;
+    D.y = dy.p;
+    D.mu = dmu.p;
+    DR = D;
+    DR.M = dM2.p;
+    DR.Minv = dM2inv.p;
+    DR.y = dy2.p;
+    DR.mu = dmu2.p;
+    v.residual();                                                                      // x += W (WtAW \ W'r)   :96-99
+    std::vector<double> mu = v.gemv_t(dW.p, nvec, v.col(RV::R));
+    luA.solve(mu);
+    v.gemv_n(1.0, dW.p, nvec, mu, 1.0, v.col(RV::X));
+  }
+  std::vector<double> res((size_t)maxit + 1);
+  int64_t it = 1;
+  v.residual();
+  const double rTr = v.dot(RV::R, RV::R);
+  v.applyM(RV::R, RV::Z);
+  double rTz = v.dot(RV::R, RV::Z);
+  v.axpby(1.0, RV::Z, 0.0, RV::P);
+  if (defl) {                                                                          // p = z - W (WtAW \ WtA z)   :108-109
+    std::vector<double> mu = v.gemv_t(dAW.p, nvec, v.col(RV::Z));
+    luA.solve(mu);
+    v.gemv_n(-1.0, dW.p, nvec, mu, 1.0, v.col(RV::P));
+  }
+  res[0] = std::sqrt(rTr);
+  if (harmonic) v.axpby(1.0, v.col(RV::P), 0.0, Ccol(0));                              // P[:, 1] = p
+  else v.axpby(1.0 / std::sqrt(rTz), v.col(RV::Z), 0.0, Ccol(0));                      // Z[:, 1] = z / sqrt(rTz)   :110
+  double bb = 0.0;
+  for (int i = 0; i < n; ++i) bb += b[i] * b[i];
+  const double tol = rtol * std::sqrt(bb);
+  bool restarted = false;
+  int wcap = defl ? spdim - nvec : spdim;     // columns of the current window
+  int col = 1;                                // columns of the window filled so far
+  DevBuf<double> dG, dB, dw;
+  while (it < maxit && res[it - 1] > tol) {
+    BurstOut bo;
+    double* cbase = Ccol(col);
+    burst_core(c, A, precond, v.col(RV::X), defl ? &D : nullptr, defl ? &DR : nullptr, wcap - col, harmonic ? nullptr : cbase, rTz, tol, it,
+               maxit, bo, harmonic ? cbase : nullptr);
+    for (int64_t j = 0; j < bo.done; ++j) {
+      it += 1;
+      res[it - 1] = bo.res[j];
+    }
+    rTz = bo.rTz;
+    col += (int)bo.done;
+    if (bo.done == 0) break;
+    if (col < wcap) continue;
+    // ---- the window is full: project onto [W2 | window]                                  :127-171 / trhrdefpcg.jl:127-190
+    const bool with_w2 = defl || restarted;
+    const int k0 = with_w2 ? nvec : 0, mt = k0 + wcap;
+    double* Vp = with_w2 ? dV.p : Ccol(0);
+    double* AVp = with_w2 ? dAV.p : dAV.p + (size_t)nvec * n;
+    if (with_w2 && restarted) apply_op_multi(c, A, dV.p, dAV.p, nvec, MultiCtx(), &kt);    // W2tA = A W2 (W2 changed)
+    apply_op_multi(c, A, Ccol(0), dAV.p + (size_t)nvec * n, wcap, MultiCtx(), &kt);        // AZ / AP
+    std::vector<double> Tm = gemm_tn_host(c, mt, mt, Vp, AVp);                            // V' A V
+    if (with_w2 && restarted) {
+      W2tAW2.assign((size_t)nvec * nvec, 0.0);
+      // (A W2)' W2, upper triangle mirrored, like Symmetric(W2tA * W2)
+      std::vector<double> Gm = gemm_tn_host(c, nvec, nvec, dAV.p, dV.p);
+      W2tAW2 = sym_upper(Gm, nvec, nvec);
+    }
+    dw.alloc((size_t)mt);
+    dG.alloc((size_t)mt * mt);
+    if (!harmonic) {
+      std::vector<double> Ts = sym_upper(Tm, mt, mt);
+      for (int j = 0; j < k0; ++j)
+        for (int i2 = 0; i2 < k0; ++i2) Ts[i2 + (size_t)j * mt] = W2tAW2[i2 + (size_t)j * k0];
+      CUDA_TRY(cudaMemcpyAsync(dG.p, Ts.data(), Ts.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      la.syevd(c, mt, dG.p, mt, dw.p);                                                  // eigen(VtAV, I)
+    } else {
+      if ((int64_t)dMAV.n < (int64_t)n * mt) dMAV.alloc((size_t)n * ncols);
+      if (precond) apply_op_multi(c, OP_NN, AVp, dMAV.p, mt, MultiCtx(), &kt);           // M \ (A V)
+      else CUDA_TRY(cudaMemcpyAsync(dMAV.p, AVp, (size_t)n * mt * 8, cudaMemcpyDeviceToDevice, c->stream));
+      std::vector<double> Gs = sym_upper(gemm_tn_host(c, mt, mt, AVp, dMAV.p), mt, mt), Bm((size_t)mt * mt, 0.0);   // (A V)' M^-1 (A V)
+      for (int j = 0; j < k0; ++j)
+        for (int i2 = 0; i2 < k0; ++i2) Bm[i2 + (size_t)j * mt] = W2tAW2[i2 + (size_t)j * k0];
+      for (int j = k0; j < mt; ++j) Bm[j + (size_t)j * mt] = Tm[j + (size_t)j * mt];    // diag(P' A P)
+      dB.alloc((size_t)mt * mt);
+      CUDA_TRY(cudaMemcpyAsync(dG.p, Gs.data(), Gs.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      CUDA_TRY(cudaMemcpyAsync(dB.p, Bm.data(), Bm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      la.sygvd(c, mt, dG.p, mt, dB.p, mt, dw.p);                                        // eigen(VtAinvMAV, VtAV)
+    }
+    CUDA_TRY(cudaMemsetAsync(dW2new.p, 0, (size_t)n * nvec * 8, c->stream));
+    gemm_nn(c, mt, std::min(nvec, mt), Vp, dG.p, dW2new.p);                             // W2 = [W2 window] vecs[:, 1:nvec]
+    CUDA_TRY(cudaMemcpyAsync(dV.p, dW2new.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    restarted = true;
+    wcap = spdim - nvec;
+    col = 0;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
+  d2h(c, x, v.col(RV::X), n, &T);
+  if (defl || restarted) d2h(c, W2_out, dV.p, (int64_t)n * nvec, &T);
+  else std::fill(W2_out, W2_out + (size_t)n * nvec, 0.0);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (!c->mute) std::copy(res.begin(), res.begin() + it, res_norm);
+  *it_out = it;
+  finish_timings(c, kt, T, launches0, tm);
+}

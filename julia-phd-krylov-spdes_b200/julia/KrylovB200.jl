@@ -283,6 +283,11 @@ rrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = post
 rrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(0, S, b, x, W, M, size(W, 2), spdim, maxit)
 hrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(1, S, b, x, nothing, M, nvec, spdim, maxit)
 hrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(1, S, b, x, W, M, size(W, 2), spdim, maxit)
+# thick-restart siblings (trrrdefpcg.jl:48-199, :234-355; trhrdefpcg.jl:48-208, :247-389): kinds 2 / 3 of the same entry point
+trrrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(2, S, b, x, nothing, M, nvec, spdim, maxit)
+trrrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(2, S, b, x, W, M, size(W, 2), spdim, maxit)
+trhrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(3, S, b, x, nothing, M, nvec, spdim, maxit)
+trhrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(3, S, b, x, W, M, size(W, 2), spdim, maxit)
 
 # ---------------------------------------------------------------------------------------------------
 # LORASC preconditioner of the full system (EllipticPdeDomainDecomposition.jl:1406-1428, apply :1908-1976)
@@ -332,6 +337,6 @@ end
 \(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
 ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
 
-export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, B200Lorasc
+export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, B200Lorasc
 
 end # module

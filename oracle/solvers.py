@@ -359,3 +359,125 @@ def hrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
 def hrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
     """hrdefpcg.jl:48-164."""
     return _posthoc(A, b, x, M, W, W.shape[1], spdim, maxit, eps, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Thick-restart Rayleigh-Ritz / harmonic-Ritz recycling (SURVEY 8(f3)): trrrpcg / trrrdefpcg (trrrdefpcg.jl:234-355,
+# :48-199) and trhrpcg / trhrdefpcg (trhrdefpcg.jl:247-389, :48-208).
+#
+# The recurrence is that of the post-hoc variants above (deflated by the ORIGINAL basis W throughout); the search-space
+# columns are written cyclically and every time the window is full the recycle basis W2 is replaced by the nvec lowest
+# (harmonic) Ritz vectors of [W2 | window].  Without a deflation basis the first window has spdim columns and projects
+# onto them alone; later windows have spdim - nvec columns.  A solve that stops before its first window is full
+# returns W2 = W (deflated variants) -- the reference's trrrpcg / trhrpcg return uninitialised memory in that case,
+# this restatement (and the library) return zeros.  The harmonic variants keep the reference's structural zeros: the
+# (W2, P) blocks of V'AV are not computed (trhrdefpcg.jl:170-177), although W2 stops being A-conjugate to the window
+# after the first restart.
+# ---------------------------------------------------------------------------------------------
+def _thick_restart(A, b, x, M, W, nvec, spdim, maxit, eps, harmonic):
+    import scipy.linalg as sla
+    n = x.size
+    defl = W is not None
+    if defl:
+        nvec = W.shape[1]
+        WtA = np.empty((nvec, n))
+        for iv in range(nvec):
+            WtA[iv, :] = A(W[:, iv])
+        WtAW = _sym(WtA @ W)
+        WtW = _sym(W.T @ W)
+        W2, W2tA, W2tAW2 = W.copy(), WtA.copy(), WtAW.copy()
+        r = b - A(x)
+        x += W @ np.linalg.solve(WtAW, W.T @ r)
+    else:
+        W2 = np.zeros((n, nvec))
+    wcap = spdim - nvec if defl else spdim                  # columns of the current window
+    C = np.zeros((n, spdim))
+    restarted = False
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    res_norm[0] = np.sqrt(rTr)
+    z = M(r)
+    rTz = r @ z
+    p = z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else z.copy()
+    C[:, 0] = p if harmonic else z / rTz ** 0.5
+    col = 1                                                  # columns of the window filled so far
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        if defl:
+            r -= W @ np.linalg.solve(WtW, W.T @ r)
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        p = beta * p + z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else beta * p + z
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+        C[:, col] = p if harmonic else z / rTz ** 0.5        # ivec of the reference = col + 1
+        col += 1
+        if col < wcap:
+            continue
+        # ---- the window is full: project ------------------------------------------------------------------------
+        Cw = C[:, :wcap]
+        ACw = np.column_stack([A(Cw[:, j]) for j in range(wcap)])
+        with_w2 = defl or restarted
+        if with_w2 and restarted:                            # W2 changed at the last restart: A W2 again
+            for iv in range(nvec):
+                W2tA[iv, :] = A(W2[:, iv])
+            W2tAW2 = _sym(W2tA @ W2)
+        k0 = nvec if with_w2 else 0
+        mt = k0 + wcap
+        V = np.column_stack([W2, Cw]) if with_w2 else Cw
+        T = np.zeros((mt, mt))
+        if not harmonic:
+            if with_w2:
+                T[:k0, :k0] = W2tAW2
+                T[:k0, k0:] = W2tA @ Cw
+            T[k0:, k0:] = Cw.T @ ACw
+            vals, vecs = np.linalg.eigh(_sym(T))             # eigen(VtAV, I)
+        else:
+            MACw = np.column_stack([M(ACw[:, j]) for j in range(wcap)])
+            G = np.zeros((mt, mt))
+            if with_w2:
+                MAW2 = np.column_stack([M(W2tA[iv, :]) for iv in range(nvec)])
+                G[:k0, :k0] = W2tA @ MAW2
+                G[:k0, k0:] = W2tA @ MACw
+                T[:k0, :k0] = W2tAW2
+            G[k0:, k0:] = ACw.T @ MACw
+            T[k0 + np.arange(wcap), k0 + np.arange(wcap)] = np.einsum("ij,ij->j", Cw, ACw)
+            vals, vecs = sla.eigh(_sym(G), _sym(T))          # eigen(VtAinvMAV, VtAV)
+        W2 = V @ vecs[:, :nvec]
+        if not defl and not restarted:
+            W2tA = np.empty((nvec, n))
+        restarted = True
+        wcap = spdim - nvec
+        col = 0
+    return x, it, res_norm[:it].copy(), W2
+
+
+def trrrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """trrrdefpcg.jl:234-355."""
+    return _thick_restart(A, b, x, M, None, nvec, spdim, maxit, eps, False)
+
+
+def trrrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """trrrdefpcg.jl:48-199 (positional order of the reference: A, b, x, W, M, spdim)."""
+    return _thick_restart(A, b, x, M, W, W.shape[1], spdim, maxit, eps, False)
+
+
+def trhrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """trhrdefpcg.jl:247-389."""
+    return _thick_restart(A, b, x, M, None, nvec, spdim, maxit, eps, True)
+
+
+def trhrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """trhrdefpcg.jl:48-208."""
+    return _thick_restart(A, b, x, M, W, W.shape[1], spdim, maxit, eps, True)
