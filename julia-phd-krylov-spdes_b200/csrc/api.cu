@@ -924,7 +924,8 @@ void setup_peer_exchange(Ctx* c) {
     ok = 0;
   }
   if (ok) {
-    CUDA_TRY(cudaMemset(c->xch_own, 0, data_bytes + flag_bytes));
+    CUDA_TRY(cudaMemset(c->xch_own, 0xff, data_bytes));   // every entry "empty" (kernels.cuh: kXchEmpty)
+    CUDA_TRY(cudaMemset(static_cast<uint8_t*>(c->xch_own) + data_bytes, 0, flag_bytes));
     CUDA_TRY(cudaDeviceSynchronize());
     if (cudaIpcGetMemHandle(&mine, c->xch_own) != cudaSuccess) {
       cudaGetLastError();
@@ -996,7 +997,8 @@ void setup_peer_exchange_group(Ctx* c) {
     ok = 0;
   }
   if (ok) {
-    CUDA_TRY(cudaMemset(c->xch_own, 0, data_bytes + flag_bytes));
+    CUDA_TRY(cudaMemset(c->xch_own, 0xff, data_bytes));   // every entry "empty" (kernels.cuh: kXchEmpty)
+    CUDA_TRY(cudaMemset(static_cast<uint8_t*>(c->xch_own) + data_bytes, 0, flag_bytes));
     CUDA_TRY(cudaDeviceSynchronize());
   }
   {
