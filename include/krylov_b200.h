@@ -253,7 +253,11 @@ int kb200_debug_rayleigh_ritz(kb200_handle h, const double* Tm, int64_t m, int64
  * trrrpcg / trrrdefpcg (trrrdefpcg.jl:234-355, :48-199) and trhrpcg / trhrdefpcg (trhrdefpcg.jl:247-389, :48-208): the
  * thick-restart siblings -- the window of captured columns is cyclic and every time it is full W2 becomes the nvec
  * lowest (harmonic) Ritz vectors of [W2 | window]; a solve that stops before its first window is full returns W2 = W
- * (deflated) or zeros.  The locally-optimal variants (lotr*) are not built. */
+ * (deflated) or zeros.
+ * lotrrrpcg / lotrrrdefpcg (lotrrrdefpcg.jl:252-389, :48-214) and lotrhrpcg / lotrhrdefpcg (lotrhrdefpcg.jl:267-428,
+ * :48-229): the locally-optimal thick-restart siblings -- the projection is the restart of eigCG (eigcg.jl:220-228)
+ * applied to the pencil of the search space [W2 | window], W2 carries nvec..2 nvec columns inside the solve and its
+ * first nvec columns are returned; spdim >= 2 nvec + 2. */
 int kb200_rrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol, int assembled,
                 int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
 int kb200_rrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
@@ -270,8 +274,16 @@ int kb200_trhrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int6
                   int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
 int kb200_trhrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
                      double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
-/* all of them behind one entry: kind 0 = Rayleigh-Ritz, 1 = harmonic Ritz, 2 = thick-restart Rayleigh-Ritz, 3 = thick-restart
- * harmonic Ritz; W == NULL: no deflation basis */
+int kb200_lotrrrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol, int assembled,
+                    int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
+int kb200_lotrrrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                       double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
+int kb200_lotrhrpcg(kb200_handle h, const double* b, double* x, int64_t nvec, int64_t spdim, int64_t maxit, double rtol, int assembled,
+                    int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
+int kb200_lotrhrdefpcg(kb200_handle h, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim, int64_t maxit,
+                       double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out, kb200_timings* timings);
+/* all of them behind one entry: kind 0 = Rayleigh-Ritz, 1 = harmonic Ritz, 2 / 3 = their thick-restart siblings, 4 / 5 = the
+ * locally-optimal thick-restart ones; W == NULL: no deflation basis */
 int kb200_posthoc_recycle(kb200_handle h, int kind, const double* b, double* x, const double* W, int64_t nvec, int64_t spdim,
                           int64_t maxit, double rtol, int assembled, int precond, int64_t* it, double* res_norm, double* W2_out,
                           kb200_timings* timings);

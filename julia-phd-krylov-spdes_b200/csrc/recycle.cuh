@@ -149,6 +149,85 @@ static int rayleigh_ritz(Ctx* c, DenseLa& la, const std::vector<double>& Tm, int
   return nev;
 }
 
+// The same restart for a pencil (G, B) -- the locally-optimal thick-restart variants (lotrrrdefpcg.jl:153-165,
+// lotrhrdefpcg.jl:163-177): Y = [lowest nvec eigenvectors of (G, B) | those of the leading (m-1) blocks, last row zero],
+// nev = rank(Y), Q = left singular vectors, eigen(Q'GQ, Q'BQ) -> Q Z (m x nev, device).  Bm empty: B = identity.
+// H and Q'BQ are symmetrised (upper triangles read), see oracle/solvers.py::_lo_thick_restart.
+static int rayleigh_ritz_pencil(Ctx* c, DenseLa& la, const std::vector<double>& Gm, const std::vector<double>& Bm, int m, int nvec,
+                                DevBuf<double>& dQZ) {
+  cudaStream_t s = c->stream;
+  const bool gen = !Bm.empty();
+  const int ny = 2 * nvec;
+  require(m >= ny, "locally-optimal restart needs spdim >= 2 nvec");
+  DevBuf<double> dG, dB, dE1, dB1, dE2, dB2, dY, dS, dU, dGQ, dH, dHB, dw;
+  dG.alloc((size_t)m * m);
+  dE1.alloc((size_t)m * m);
+  dE2.alloc((size_t)std::max(1, m - 1) * std::max(1, m - 1));
+  dY.alloc((size_t)m * ny);
+  dw.alloc((size_t)m);
+  CUDA_TRY(cudaMemcpyAsync(dG.p, Gm.data(), (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(dE1.p, dG.p, (size_t)m * m * 8, cudaMemcpyDeviceToDevice, s));
+  if (gen) {
+    dB.alloc((size_t)m * m);
+    dB1.alloc((size_t)m * m);
+    dB2.alloc((size_t)std::max(1, m - 1) * std::max(1, m - 1));
+    CUDA_TRY(cudaMemcpyAsync(dB.p, Bm.data(), (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dB1.p, dB.p, (size_t)m * m * 8, cudaMemcpyDeviceToDevice, s));
+    la.sygvd(c, m, dE1.p, m, dB1.p, m, dw.p);
+  } else {
+    la.syevd(c, m, dE1.p, m, dw.p);
+  }
+  CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)m * ny * 8, s));
+  CUDA_TRY(cudaMemcpyAsync(dY.p, dE1.p, (size_t)m * nvec * 8, cudaMemcpyDeviceToDevice, s));   // Y[:, 1:nvec]
+  if (m > 1) {
+    CUDA_TRY(cudaMemcpy2DAsync(dE2.p, (size_t)(m - 1) * 8, dG.p, (size_t)m * 8, (size_t)(m - 1) * 8, (size_t)(m - 1),
+                               cudaMemcpyDeviceToDevice, s));
+    if (gen) {
+      CUDA_TRY(cudaMemcpy2DAsync(dB2.p, (size_t)(m - 1) * 8, dB.p, (size_t)m * 8, (size_t)(m - 1) * 8, (size_t)(m - 1),
+                                 cudaMemcpyDeviceToDevice, s));
+      la.sygvd(c, m - 1, dE2.p, m - 1, dB2.p, m - 1, dw.p);
+    } else {
+      la.syevd(c, m - 1, dE2.p, m - 1, dw.p);
+    }
+    const int take = std::min(nvec, m - 1);
+    CUDA_TRY(cudaMemcpy2DAsync(dY.p + (size_t)nvec * m, (size_t)m * 8, dE2.p, (size_t)(m - 1) * 8, (size_t)(m - 1) * 8, (size_t)take,
+                               cudaMemcpyDeviceToDevice, s));
+  }
+  dS.alloc((size_t)ny);
+  dU.alloc((size_t)m * ny);
+  int lwork = 0;
+  CUSOLVER_TRY(cusolverDnDgesvd_bufferSize(la.cs, m, ny, &lwork));
+  if ((int64_t)la.work.n < lwork) la.work.alloc((size_t)lwork);
+  CUSOLVER_TRY(cusolverDnDgesvd(la.cs, 'S', 'N', m, ny, dY.p, m, dS.p, dU.p, m, nullptr, ny, la.work.p, lwork, nullptr, la.info.p));
+  la.check_info(c, "gesvd");
+  std::vector<double> sv((size_t)ny);
+  CUDA_TRY(cudaMemcpyAsync(sv.data(), dS.p, (size_t)ny * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int nev = 0;
+  if (sv[0] > 0.0) {
+    const double thr = (double)ny * 2.220446049250313e-16 * sv[0];   // LinearAlgebra.rank default
+    for (int i = 0; i < ny; ++i) nev += sv[i] > thr;
+  }
+  if (nev < 1) throw KbError(KB200_ERR_INTERNAL, "locally-optimal restart: Y has rank 0");
+  const double one = 1.0, zero = 0.0;
+  dGQ.alloc((size_t)m * nev);
+  dH.alloc((size_t)nev * nev);
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, m, &one, dG.p, m, dU.p, m, &zero, dGQ.p, m));
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_T, CUBLAS_OP_N, nev, nev, m, &one, dU.p, m, dGQ.p, m, &zero, dH.p, nev));
+  if (gen) {
+    dHB.alloc((size_t)nev * nev);
+    CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, m, &one, dB.p, m, dU.p, m, &zero, dGQ.p, m));
+    CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_T, CUBLAS_OP_N, nev, nev, m, &one, dU.p, m, dGQ.p, m, &zero, dHB.p, nev));
+    la.sygvd(c, nev, dH.p, nev, dHB.p, nev, dw.p);
+  } else {
+    la.syevd(c, nev, dH.p, nev, dw.p);
+  }
+  dQZ.alloc((size_t)m * nev);
+  CUBLAS_TRY(cublasDgemm(la.cb, CUBLAS_OP_N, CUBLAS_OP_N, m, nev, nev, &one, dU.p, m, dH.p, nev, &zero, dQZ.p, m));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return nev;
+}
+
 // Dense LU with partial pivoting of a small matrix (host): `WtAW \ .` of defcg.jl:272-274, :284, :301, :407
 struct SmallLu {
   int k = 0;
@@ -677,8 +756,13 @@ static void posthoc_solve(Ctx* c, const double* b, double* x, const double* W, i
 // Device layout: V = [W2 (nvec columns) | window (spdim columns)], AV likewise.  A solve that stops before its first
 // window is full returns W2 = W (deflated variants) or zeros (the reference returns uninitialised memory there).  The
 // harmonic variants keep the reference's structural zeros in V'AV (blockdiag(W2'AW2, diag(P'AP)), trhrdefpcg.jl:170-177).
+//
+// lo = true: the locally-optimal variants (lotrrrpcg / lotrrrdefpcg, lotrrrdefpcg.jl:252-389 / :48-214; lotrhrpcg /
+// lotrhrdefpcg, lotrhrdefpcg.jl:267-428 / :48-229): the projection is the eigCG-type restart of rayleigh_ritz_pencil,
+// W2 carries nev in [nvec, 2 nvec] columns (stored right in front of the window so that [W2 | window] stays
+// contiguous), the window has spdim - nev columns and the first nvec columns of W2 are returned.
 static void thick_restart_solve(Ctx* c, const double* b, double* x, const double* W, int nvec, int spdim, int64_t maxit, double rtol, OpKind A,
-                                int precond, bool harmonic, int64_t* it_out, double* res_norm, double* W2_out, kb200_timings* tm) {
+                                int precond, bool harmonic, bool lo, int64_t* it_out, double* res_norm, double* W2_out, kb200_timings* tm) {
   const int n = (int)c->n_gamma;
   const bool defl = W != nullptr;
   require(nvec >= 1 && spdim > nvec && spdim <= 4096, "need 1 <= nvec < spdim <= 4096");
@@ -691,13 +775,18 @@ static void thick_restart_solve(Ctx* c, const double* b, double* x, const double
   DenseLa la(c);
   RecycleVecs v(c, A, precond);
   using RV = RecycleVecs;
-  const int ncols = nvec + spdim;
+  const int w2cap = lo ? 2 * nvec : nvec;     // columns reserved for W2 in front of the window
+  const int ncols = w2cap + spdim;
+  if (lo) require(spdim >= 2 * nvec + 2, "locally-optimal thick restart needs spdim >= 2 nvec + 2");
   DevBuf<double> dV, dAV, dMAV, dW, dAW, dW2new;
   dV.alloc((size_t)n * ncols);
   dAV.alloc((size_t)n * ncols);
-  dW2new.alloc((size_t)n * nvec);
+  dW2new.alloc((size_t)n * w2cap);
   CUDA_TRY(cudaMemsetAsync(dV.p, 0, (size_t)n * ncols * 8, c->stream));
-  auto Ccol = [&](int j) { return dV.p + (size_t)(nvec + j) * n; };
+  int nev = defl ? nvec : 0;                  // columns of W2 inside the search space
+  auto Ccol = [&](int j) { return dV.p + (size_t)(w2cap + j) * n; };
+  auto W2p = [&]() { return dV.p + (size_t)(w2cap - nev) * n; };
+  auto AW2p = [&]() { return dAV.p + (size_t)(w2cap - nev) * n; };
   h2d(c, v.col(RV::B), b, n, &T);
   h2d(c, v.col(RV::X), x, n, &T);
   CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
@@ -713,8 +802,8 @@ static void thick_restart_solve(Ctx* c, const double* b, double* x, const double
     WtAW = sym_upper(gemm_tn_host(c, nvec, nvec, dAW.p, dW.p), nvec, nvec);            // Symmetric()         :87-90
     WtW = sym_upper(gemm_tn_host(c, nvec, nvec, dW.p, dW.p), nvec, nvec);
     W2tAW2 = WtAW;                                                                     // W2 = W              :91-93
-    CUDA_TRY(cudaMemcpyAsync(dV.p, dW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(dAV.p, dAW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(W2p(), dW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(AW2p(), dAW.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
     luA.factor(nvec, WtAW);
     invert_small(nvec, WtAW, WtAW_inv);
     invert_small(nvec, WtW, WtW_inv);
@@ -766,7 +855,7 @@ static void thick_restart_solve(Ctx* c, const double* b, double* x, const double
   for (int i = 0; i < n; ++i) bb += b[i] * b[i];
   const double tol = rtol * std::sqrt(bb);
   bool restarted = false;
-  int wcap = defl ? spdim - nvec : spdim;     // columns of the current window
+  int wcap = spdim - nev;                     // columns of the current window
   int col = 1;                                // columns of the window filled so far
   DevBuf<double> dG, dB, dw;
   while (it < maxit && res[it - 1] > tol) {
@@ -783,50 +872,56 @@ static void thick_restart_solve(Ctx* c, const double* b, double* x, const double
     if (bo.done == 0) break;
     if (col < wcap) continue;
     // ---- the window is full: project onto [W2 | window]                                  :127-171 / trhrdefpcg.jl:127-190
-    const bool with_w2 = defl || restarted;
-    const int k0 = with_w2 ? nvec : 0, mt = k0 + wcap;
-    double* Vp = with_w2 ? dV.p : Ccol(0);
-    double* AVp = with_w2 ? dAV.p : dAV.p + (size_t)nvec * n;
-    if (with_w2 && restarted) apply_op_multi(c, A, dV.p, dAV.p, nvec, MultiCtx(), &kt);    // W2tA = A W2 (W2 changed)
-    apply_op_multi(c, A, Ccol(0), dAV.p + (size_t)nvec * n, wcap, MultiCtx(), &kt);        // AZ / AP
-    std::vector<double> Tm = gemm_tn_host(c, mt, mt, Vp, AVp);                            // V' A V
-    if (with_w2 && restarted) {
-      W2tAW2.assign((size_t)nvec * nvec, 0.0);
-      // (A W2)' W2, upper triangle mirrored, like Symmetric(W2tA * W2)
-      std::vector<double> Gm = gemm_tn_host(c, nvec, nvec, dAV.p, dV.p);
-      W2tAW2 = sym_upper(Gm, nvec, nvec);
-    }
+    const int k0 = nev, mt = k0 + wcap;      // mt == spdim
+    double* Vp = W2p();
+    double* AVp = AW2p();
+    if (k0 > 0 && restarted) apply_op_multi(c, A, Vp, AVp, k0, MultiCtx(), &kt);             // W2tA = A W2 (W2 changed)
+    apply_op_multi(c, A, Ccol(0), dAV.p + (size_t)w2cap * n, wcap, MultiCtx(), &kt);         // AZ / AP
+    std::vector<double> Tm = gemm_tn_host(c, mt, mt, Vp, AVp);                               // V' A V
+    if (k0 > 0 && restarted) W2tAW2 = sym_upper(gemm_tn_host(c, k0, k0, AVp, Vp), k0, k0);   // Symmetric(W2tA * W2)
     dw.alloc((size_t)mt);
     dG.alloc((size_t)mt * mt);
+    std::vector<double> Gs, Bm;
     if (!harmonic) {
-      std::vector<double> Ts = sym_upper(Tm, mt, mt);
+      Gs = sym_upper(Tm, mt, mt);
       for (int j = 0; j < k0; ++j)
-        for (int i2 = 0; i2 < k0; ++i2) Ts[i2 + (size_t)j * mt] = W2tAW2[i2 + (size_t)j * k0];
-      CUDA_TRY(cudaMemcpyAsync(dG.p, Ts.data(), Ts.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      la.syevd(c, mt, dG.p, mt, dw.p);                                                  // eigen(VtAV, I)
+        for (int i2 = 0; i2 < k0; ++i2) Gs[i2 + (size_t)j * mt] = W2tAW2[i2 + (size_t)j * k0];
     } else {
       if ((int64_t)dMAV.n < (int64_t)n * mt) dMAV.alloc((size_t)n * ncols);
-      if (precond) apply_op_multi(c, OP_NN, AVp, dMAV.p, mt, MultiCtx(), &kt);           // M \ (A V)
+      if (precond) apply_op_multi(c, OP_NN, AVp, dMAV.p, mt, MultiCtx(), &kt);               // M \ (A V)
       else CUDA_TRY(cudaMemcpyAsync(dMAV.p, AVp, (size_t)n * mt * 8, cudaMemcpyDeviceToDevice, c->stream));
-      std::vector<double> Gs = sym_upper(gemm_tn_host(c, mt, mt, AVp, dMAV.p), mt, mt), Bm((size_t)mt * mt, 0.0);   // (A V)' M^-1 (A V)
+      Gs = sym_upper(gemm_tn_host(c, mt, mt, AVp, dMAV.p), mt, mt);                          // (A V)' M^-1 (A V)
+      Bm.assign((size_t)mt * mt, 0.0);
       for (int j = 0; j < k0; ++j)
         for (int i2 = 0; i2 < k0; ++i2) Bm[i2 + (size_t)j * mt] = W2tAW2[i2 + (size_t)j * k0];
-      for (int j = k0; j < mt; ++j) Bm[j + (size_t)j * mt] = Tm[j + (size_t)j * mt];    // diag(P' A P)
-      dB.alloc((size_t)mt * mt);
-      CUDA_TRY(cudaMemcpyAsync(dG.p, Gs.data(), Gs.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      CUDA_TRY(cudaMemcpyAsync(dB.p, Bm.data(), Bm.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      la.sygvd(c, mt, dG.p, mt, dB.p, mt, dw.p);                                        // eigen(VtAinvMAV, VtAV)
+      for (int j = k0; j < mt; ++j) Bm[j + (size_t)j * mt] = Tm[j + (size_t)j * mt];         // diag(P' A P)
     }
-    CUDA_TRY(cudaMemsetAsync(dW2new.p, 0, (size_t)n * nvec * 8, c->stream));
-    gemm_nn(c, mt, std::min(nvec, mt), Vp, dG.p, dW2new.p);                             // W2 = [W2 window] vecs[:, 1:nvec]
-    CUDA_TRY(cudaMemcpyAsync(dV.p, dW2new.p, (size_t)n * nvec * 8, cudaMemcpyDeviceToDevice, c->stream));
+    int nev_new = nvec;
+    CUDA_TRY(cudaMemsetAsync(dW2new.p, 0, (size_t)n * w2cap * 8, c->stream));
+    if (lo) {
+      DevBuf<double> dQZ;
+      nev_new = rayleigh_ritz_pencil(c, la, Gs, Bm, mt, nvec, dQZ);
+      gemm_nn(c, mt, nev_new, Vp, dQZ.p, dW2new.p);                                          // W2 = [W2 window] Q Z
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(dG.p, Gs.data(), Gs.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      if (!harmonic) {
+        la.syevd(c, mt, dG.p, mt, dw.p);                                                     // eigen(VtAV, I)
+      } else {
+        dB.alloc((size_t)mt * mt);
+        CUDA_TRY(cudaMemcpyAsync(dB.p, Bm.data(), Bm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        la.sygvd(c, mt, dG.p, mt, dB.p, mt, dw.p);                                           // eigen(VtAinvMAV, VtAV)
+      }
+      gemm_nn(c, mt, std::min(nvec, mt), Vp, dG.p, dW2new.p);                                // W2 = [W2 window] vecs[:, 1:nvec]
+    }
+    nev = nev_new;
+    CUDA_TRY(cudaMemcpyAsync(W2p(), dW2new.p, (size_t)n * nev * 8, cudaMemcpyDeviceToDevice, c->stream));
     restarted = true;
-    wcap = spdim - nvec;
+    wcap = spdim - nev;
     col = 0;
   }
   CUDA_TRY(cudaEventRecord(c->ev_b, c->stream));
   d2h(c, x, v.col(RV::X), n, &T);
-  if (defl || restarted) d2h(c, W2_out, dV.p, (int64_t)n * nvec, &T);
+  if (defl || restarted) d2h(c, W2_out, W2p(), (int64_t)n * nvec, &T);   // the first nvec columns of W2
   else std::fill(W2_out, W2_out + (size_t)n * nvec, 0.0);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (!c->mute) std::copy(res.begin(), res.begin() + it, res_norm);

@@ -288,6 +288,11 @@ trrrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = po
 trrrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(2, S, b, x, W, M, size(W, 2), spdim, maxit)
 trhrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(3, S, b, x, nothing, M, nvec, spdim, maxit)
 trhrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(3, S, b, x, W, M, size(W, 2), spdim, maxit)
+# locally-optimal thick-restart siblings (lotrrrdefpcg.jl:48-214, :252-389; lotrhrdefpcg.jl:48-229, :267-428): kinds 4 / 5
+lotrrrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(4, S, b, x, nothing, M, nvec, spdim, maxit)
+lotrrrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(4, S, b, x, W, M, size(W, 2), spdim, maxit)
+lotrhrpcg(S::B200SchurOperator, b, x, M, nvec::Int, spdim::Int; maxit::Int=0) = posthoc(5, S, b, x, nothing, M, nvec, spdim, maxit)
+lotrhrdefpcg(S::B200SchurOperator, b, x, W::Matrix{Float64}, M, spdim::Int; maxit::Int=0) = posthoc(5, S, b, x, W, M, size(W, 2), spdim, maxit)
 
 # ---------------------------------------------------------------------------------------------------
 # LORASC preconditioner of the full system (EllipticPdeDomainDecomposition.jl:1406-1428, apply :1908-1976)
@@ -337,6 +342,6 @@ end
 \(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
 ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
 
-export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, B200Lorasc
+export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
 
 end # module

@@ -225,6 +225,26 @@ def trhrdefpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann, spdim, maxi
     return _posthoc("trhr", A, b, x, W, M, W.shape[1], spdim, maxit, return_timings)
 
 
+def lotrrrpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, return_timings=False):
+    """lotrrrdefpcg.jl:252-389 (kb200_lotrrrpcg): locally-optimal thick-restart Rayleigh-Ritz recycling."""
+    return _posthoc("lotrrr", A, b, x, None, M, nvec, spdim, maxit, return_timings)
+
+
+def lotrrrdefpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann, spdim, maxit=0, return_timings=False):
+    """lotrrrdefpcg.jl:48-214 (kb200_lotrrrdefpcg)."""
+    return _posthoc("lotrrr", A, b, x, W, M, W.shape[1], spdim, maxit, return_timings)
+
+
+def lotrhrpcg(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, return_timings=False):
+    """lotrhrdefpcg.jl:267-428 (kb200_lotrhrpcg): locally-optimal thick-restart harmonic-Ritz recycling."""
+    return _posthoc("lotrhr", A, b, x, None, M, nvec, spdim, maxit, return_timings)
+
+
+def lotrhrdefpcg(A: B200SchurOperator, b, x, W, M: B200NeumannNeumann, spdim, maxit=0, return_timings=False):
+    """lotrhrdefpcg.jl:48-229 (kb200_lotrhrdefpcg)."""
+    return _posthoc("lotrhr", A, b, x, W, M, W.shape[1], spdim, maxit, return_timings)
+
+
 def eigpcg_hostloop(A: B200SchurOperator, b, x, M: B200NeumannNeumann, nvec, spdim, maxit=0, burst=True):
     """eigcg.jl:143-267 with the control flow in the host language (cross-check of kb200_eigpcg).  burst=False: every
     iteration driven from the host (the cross-check of the device bursts)."""

@@ -481,3 +481,139 @@ def trhrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
 def trhrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
     """trhrdefpcg.jl:48-208."""
     return _thick_restart(A, b, x, M, W, W.shape[1], spdim, maxit, eps, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Locally-optimal thick-restart variants (SURVEY 8(f3)): lotrrrpcg / lotrrrdefpcg (lotrrrdefpcg.jl:252-389, :48-214)
+# and lotrhrpcg / lotrhrdefpcg (lotrhrdefpcg.jl:267-428, :48-229).
+#
+# As the thick-restart variants above, with the restart of eigCG in place of the plain projection: the new basis spans
+# the nvec lowest (harmonic) Ritz vectors of the search space [W2 | window] AND those of its leading (spdim - 1) block
+# (eigcg.jl:220-228 applied to the projected matrices), so W2 carries nev in [nvec, 2 nvec] columns, the window has
+# spdim - nev and the first nvec columns of W2 are returned.  Reading of the reference where it is inconsistent: the
+# blocks of the projected matrices follow nev (lotrrrdefpcg.jl:146 mixes nvec and nev in the mirrored block, which
+# Symmetric() never reads); H = Q'(T Q) and G = Q'(B Q) are symmetrised (Julia's eigen takes the symmetric path only
+# when they are symmetric to the last bit; otherwise it returns the same eigenvectors with another column scaling --
+# the span, which is what a deflation basis is, does not change).
+# ---------------------------------------------------------------------------------------------
+def _rayleigh_ritz_general(G, B, nvec):
+    """eigCG-type restart for the pencil (G, B), B = None for the identity: returns (Q Z, nev)."""
+    import scipy.linalg as sla
+    m = G.shape[0]
+    eig = (lambda g, b: np.linalg.eigh(g)[1]) if B is None else (lambda g, b: sla.eigh(g, b)[1])
+    Y = np.zeros((m, 2 * nvec))
+    Y[:, :nvec] = eig(G, B)[:, :nvec]
+    Y[:m - 1, nvec:] = eig(G[:m - 1, :m - 1], None if B is None else B[:m - 1, :m - 1])[:, :nvec]
+    nev = _julia_rank(Y)
+    Q = np.linalg.svd(Y, full_matrices=False)[0][:, :nev]
+    H = _sym(Q.T @ (G @ Q))
+    if B is None:
+        Z = np.linalg.eigh(H)[1]
+    else:
+        Z = sla.eigh(H, _sym(Q.T @ (B @ Q)))[1]
+    return Q @ Z, nev
+
+
+def _lo_thick_restart(A, b, x, M, W, nvec, spdim, maxit, eps, harmonic):
+    n = x.size
+    defl = W is not None
+    if defl:
+        nvec = W.shape[1]
+        WtA = np.empty((nvec, n))
+        for iv in range(nvec):
+            WtA[iv, :] = A(W[:, iv])
+        WtAW = _sym(WtA @ W)
+        WtW = _sym(W.T @ W)
+        W2 = W.copy()
+        r = b - A(x)
+        x += W @ np.linalg.solve(WtAW, W.T @ r)
+    else:
+        W2 = np.zeros((n, nvec))
+    nev = nvec if defl else 0                                # columns of W2 inside the search space
+    restarted = False
+    C = np.zeros((n, spdim))
+    maxit = n if maxit == 0 else maxit
+    res_norm = np.empty(max(n, maxit) + 1)
+    it = 1
+    r = b - A(x)
+    rTr = r @ r
+    res_norm[0] = np.sqrt(rTr)
+    z = M(r)
+    rTz = r @ z
+    p = z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else z.copy()
+    C[:, 0] = p if harmonic else z / rTz ** 0.5
+    col = 1
+    tol = eps * np.linalg.norm(b)
+    while it < maxit and res_norm[it - 1] > tol:
+        Ap = A(p)
+        d = p @ Ap
+        alpha = rTz / d
+        beta = 1.0 / rTz
+        x += alpha * p
+        r -= alpha * Ap
+        if defl:
+            r -= W @ np.linalg.solve(WtW, W.T @ r)
+        rTr = r @ r
+        z = M(r)
+        rTz = r @ z
+        beta *= rTz
+        p = beta * p + z - W @ np.linalg.solve(WtAW, WtA @ z) if defl else beta * p + z
+        it += 1
+        res_norm[it - 1] = np.sqrt(rTr)
+        C[:, col] = p if harmonic else z / rTz ** 0.5
+        col += 1
+        wcap = spdim - nev
+        if col < wcap:
+            continue
+        # ---- the window is full: eigCG-type restart on [W2 | window] --------------------------------------------------
+        Cw = C[:, :wcap]
+        ACw = np.column_stack([A(Cw[:, j]) for j in range(wcap)])
+        V = np.column_stack([W2[:, :nev], Cw]) if nev else Cw
+        T = np.zeros((spdim, spdim))
+        if nev:
+            W2tA = np.vstack([A(W2[:, iv]) for iv in range(nev)])
+            W2tAW2 = _sym(W2tA @ W2[:, :nev])
+        if not harmonic:
+            if nev:
+                T[:nev, :nev] = W2tAW2
+                T[:nev, nev:] = W2tA @ Cw
+            T[nev:, nev:] = Cw.T @ ACw
+            QZ, nev_new = _rayleigh_ritz_general(_sym(T), None, nvec)
+        else:
+            MACw = np.column_stack([M(ACw[:, j]) for j in range(wcap)])
+            G = np.zeros((spdim, spdim))
+            if nev:
+                MAW2 = np.column_stack([M(W2tA[iv, :]) for iv in range(nev)])
+                G[:nev, :nev] = W2tA @ MAW2
+                G[:nev, nev:] = W2tA @ MACw
+                T[:nev, :nev] = W2tAW2
+            G[nev:, nev:] = ACw.T @ MACw
+            T[nev + np.arange(wcap), nev + np.arange(wcap)] = np.einsum("ij,ij->j", Cw, ACw)
+            QZ, nev_new = _rayleigh_ritz_general(_sym(G), _sym(T), nvec)
+        W2 = V @ QZ
+        nev = nev_new
+        restarted = True
+        col = 0
+    if not defl and not restarted:
+        return x, it, res_norm[:it].copy(), np.zeros((n, nvec))
+    return x, it, res_norm[:it].copy(), W2[:, :nvec].copy()
+
+
+def lotrrrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """lotrrrdefpcg.jl:252-389."""
+    return _lo_thick_restart(A, b, x, M, None, nvec, spdim, maxit, eps, False)
+
+
+def lotrrrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """lotrrrdefpcg.jl:48-214 (positional order of the reference: A, b, x, W, M, spdim)."""
+    return _lo_thick_restart(A, b, x, M, W, W.shape[1], spdim, maxit, eps, False)
+
+
+def lotrhrpcg(A, b, x, M, nvec, spdim, maxit=0, eps=EPS):
+    """lotrhrdefpcg.jl:267-428."""
+    return _lo_thick_restart(A, b, x, M, None, nvec, spdim, maxit, eps, True)
+
+
+def lotrhrdefpcg(A, b, x, W, M, spdim, maxit=0, eps=EPS):
+    """lotrhrdefpcg.jl:48-229."""
+    return _lo_thick_restart(A, b, x, M, W, W.shape[1], spdim, maxit, eps, True)
