@@ -118,6 +118,20 @@ int kb200_upload_global_interface_block(kb200_handle h, const int64_t* AGG_colpt
  * re-runs the host analysis and refreshes the device streams (round 1: full rebuild, ~1-2 s at 4M DOF). */
 int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzval);
 int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval);
+/* ---- numeric re-factorisation on the device (next row f1) ----------------------------------------
+ * Example07_PcgSchurStochasticEllipticPde.jl:160-204 refills A_II,d and calls cholesky() per realization
+ * (EllipticPdeDomainDecomposition.jl:389-546, :1536).  With these two calls the factorisation itself moves to the
+ * GPU: the permutation and the pattern of the factor uploaded once by kb200_upload_cholesky ARE the symbolic
+ * factorisation; kb200_upload_interior_pattern gives the pattern of A_II,d (SparseMatrixCSC colptr / rowval, Int64
+ * 1-based, both triangles or one, rows of a column sorted), kb200_refactor_interior its new values (nzval, same
+ * pattern).  Before the next operation a level-scheduled numeric Cholesky (dot-product form, one launch per
+ * dependency level, all local subdomains at once, deterministic sums) recomputes the values of L_d in the resident
+ * value pool, after which the value refresh of kb200_update_cholesky_values re-inverts the supernode blocks and
+ * rewrites the stream.  All local subdomains must have been given values at least once before the first operation
+ * that follows; a non-positive pivot is reported as KB200_ERR_INPUT.  A_IΓ,d / A_ΓΓ,d still arrive through
+ * kb200_update_local_block_values. */
+int kb200_upload_interior_pattern(kb200_handle h, int64_t d, const int64_t* colptr, const int64_t* rowval);
+int kb200_refactor_interior(kb200_handle h, int64_t d, const double* A_II_nzval);
 /* ΠSd[d] of NeumannNeumannSchurPreconditioner (:1125), n_gd x n_gd column-major. */
 int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS);
 /* Dense local Schur complement S_d (assemble_local_schurs, :667-695), n_gd x n_gd column-major. */

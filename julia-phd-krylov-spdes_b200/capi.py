@@ -27,6 +27,7 @@ SYMBOLS = [
     "kb200_rrpcg", "kb200_rrdefpcg", "kb200_hrpcg", "kb200_hrdefpcg", "kb200_posthoc_recycle",
     "kb200_trrrpcg", "kb200_trrrdefpcg", "kb200_trhrpcg", "kb200_trhrdefpcg",
     "kb200_lotrrrpcg", "kb200_lotrrrdefpcg", "kb200_lotrhrpcg", "kb200_lotrhrdefpcg",
+    "kb200_upload_interior_pattern", "kb200_refactor_interior",
 ]
 
 
@@ -189,6 +190,18 @@ class Handle:
         L.sort_indices()
         lx = _f64(L.data)
         _chk(lib().kb200_update_cholesky_values(self.h, C.c_int64(d), _p(lx, C.c_double)))
+
+    def upload_interior_pattern(self, d, A_II):
+        """kb200_upload_interior_pattern: pattern of A_II,d for the device-side numeric re-factorisation."""
+        cp, ri, _ = _csc_julia(A_II)
+        _chk(lib().kb200_upload_interior_pattern(self.h, C.c_int64(d), _p(cp, C.c_int64), _p(ri, C.c_int64)))
+
+    def refactor_interior(self, d, A_II):
+        """kb200_refactor_interior: new values of A_II,d (same pattern); L_d is recomputed on the device."""
+        A = A_II.tocsc()
+        A.sort_indices()
+        ax = _f64(A.data)
+        _chk(lib().kb200_refactor_interior(self.h, C.c_int64(d), _p(ax, C.c_double)))
 
     def update_local_block_values(self, d, A_IG, A_GG):
         g, hh = A_IG.tocsc(), A_GG.tocsc()
@@ -433,7 +446,7 @@ class Handle:
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
                 "consumer_warps", "ring_stages", "merge_depth", "min_block", "fused_pcg_ok", "vec_blocks",
                 "vec_threads", "exchange_entries", "exchange_entries_sent", "host_analyses", "value_refreshes",
-                "value_refs", "stream_read_bytes", "l2_persist_hit_ratio", "l2_prefetch_chunks"]
+                "value_refs", "stream_read_bytes", "l2_persist_hit_ratio", "l2_prefetch_chunks", "device_refactorizations"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):

@@ -85,6 +85,11 @@ struct DomHost {
   kb::DomainIn in;           // perm, L, AIG, AGG
   bool have_blocks = false, have_chol = false;
   bool stale_L = false, stale_blocks = false;   // newer values live in the device pool only (value refresh)
+  // numeric re-factorisation on the device (kb200_upload_interior_pattern / kb200_refactor_interior): per entry of L
+  // (CSC order) the position of A_II[perm[i], perm[j]] in the caller's nzval array, -1 where A_II has no entry
+  std::vector<int32_t> asrc;
+  int64_t a_nnz = 0;
+  bool have_apat = false, have_avals = false;
   std::vector<double> PiS, Sd;  // row-major copies of the column-major inputs
 };
 
@@ -177,6 +182,14 @@ struct kb200_ctx {
   // value refresh (plan.h): the value pool of the local subdomains and the maps that rewrite the stream from it
   DevBuf<double> d_pool, d_dwork;
   DevBuf<kb::ValRef> d_refs;
+  // numeric re-factorisation on the device (kernels.cuh: chol_level_kernel)
+  DevBuf<int32_t> d_fa_order, d_fa_Lrow, d_fa_Lcol, d_fa_asrc, d_fa_rptr, d_fa_rcol, d_fa_diag;
+  DevBuf<uint32_t> d_fa_epos, d_fa_rpos;
+  DevBuf<double> d_fa_A;
+  DevBuf<int> d_fa_fail;
+  std::vector<int64_t> fa_lvl_ptr, fa_abase;   // entries per dependency level / offset of every local subdomain's A_II values
+  bool fa_ready = false, fa_dirty = false;
+  int64_t refactorizations = 0;
   DevBuf<kb::DmapRef> d_dmap;
   DevBuf<kb::BlockRef> d_blkref;
   std::vector<int64_t> pool_off;                 // per local subdomain (+1)
@@ -451,6 +464,7 @@ int stream_rhs_block(const Ctx* c, int64_t want) {
 void refresh_values(Ctx* c);
 void fetch_stale_values(Ctx* c);
 void update_l2_window(Ctx* c);
+void run_refactor(Ctx* c);
 
 void finalize(Ctx* c) {
   if (c->finalized) {
@@ -843,6 +857,7 @@ void finalize(Ctx* c) {
     c->l2_prefetch_now = c->l2_prefetch;
   }
   c->stats[26] = c->l2_prefetch_now;
+  c->fa_ready = false;   // (a re-analysis moves the pool: the tables of the device-side factorisation are rebuilt on demand)
   c->stats[16] = c->fused_ok ? 1.0 : 0.0;
   c->stats[17] = c->nb;
   c->stats[18] = c->vec_threads;
@@ -859,6 +874,7 @@ void finalize(Ctx* c) {
 void refresh_values(Ctx* c) {
   use_device(c);
   cudaStream_t s = c->stream;
+  if (c->fa_dirty) run_refactor(c);   // new A_II values staged: the factor's values are recomputed on the device first
   if (c->d_dmap.n) {
     CUDA_TRY(cudaMemsetAsync(c->d_dwork.p, 0, c->d_dwork.n * 8, s));
     kb::refresh_dmap_kernel<<<(unsigned)((c->d_dmap.n + 255) / 256), 256, 0, s>>>((int64_t)c->d_dmap.n, c->d_dmap.p, c->d_pool.p, c->d_dwork.p);
@@ -873,6 +889,135 @@ void refresh_values(Ctx* c) {
   CUDA_TRY(cudaGetLastError());
   c->values_dirty = false;
   c->refreshes++;
+}
+
+// Tables of the device-side numeric Cholesky (kernels.cuh: chol_level_kernel), global over the local subdomains.
+constexpr int kCholLongRow = 48;   // rows of the factor longer than this are handled by one warp per entry
+void build_refactor_tables(Ctx* c) {
+  const int64_t nloc = c->d1 - c->d0;
+  int64_t nrows = 0, nent = 0, na = 0;
+  c->fa_abase.assign(nloc + 1, 0);
+  for (int64_t k = 0; k < nloc; ++k) {
+    const DomHost& dh = c->doms[c->d0 + k];
+    require(dh.have_apat, "kb200_refactor_interior: every local subdomain needs kb200_upload_interior_pattern first");
+    require((int64_t)dh.in.L.nzval.size() == (int64_t)c->pool_L[k] && dh.asrc.size() == dh.in.L.nzval.size(),
+            "kb200_refactor_interior: the factor pattern changed since kb200_upload_interior_pattern");
+    nrows += dh.n_I;
+    nent += (int64_t)dh.in.L.nzval.size();
+    na += dh.a_nnz;
+    c->fa_abase[k + 1] = na;
+  }
+  require(nent < (int64_t)0x7fffffff && na < (int64_t)0x7fffffff && nrows < (int64_t)0x7fffffff, "too many factor entries on one GPU");
+  std::vector<int32_t> Lrow((size_t)nent), Lcol((size_t)nent), asrc((size_t)nent), rptr((size_t)nrows + 1, 0), rcol((size_t)nent),
+      diag((size_t)nrows), order((size_t)nent), lev_of_entry((size_t)nent);
+  std::vector<uint32_t> epos((size_t)nent), rpos((size_t)nent);
+  int64_t rbase = 0, ebase = 0;
+  int maxlev = 0;
+  for (int64_t k = 0; k < nloc; ++k) {
+    const DomHost& dh = c->doms[c->d0 + k];
+    const kb::Csc& L = dh.in.L;
+    const int32_t n = L.ncol;
+    // CSR view: rows filled column by column => columns ascending, the diagonal last
+    std::vector<int32_t> cnt((size_t)n, 0);
+    for (int32_t j = 0; j < n; ++j)
+      for (int32_t p = L.colptr[j]; p < L.colptr[j + 1]; ++p) cnt[L.rowval[p]]++;
+    for (int32_t i = 0; i < n; ++i) rptr[(size_t)(rbase + i + 1)] = rptr[(size_t)(rbase + i)] + cnt[i];
+    std::vector<int32_t> fill((size_t)n);
+    for (int32_t i = 0; i < n; ++i) fill[i] = rptr[(size_t)(rbase + i)];
+    std::vector<int32_t> lev((size_t)n, 0);
+    for (int32_t j = 0; j < n; ++j) {
+      // level of column j: all columns its row touches are final (rows of k < j were filled by earlier columns)
+      int lv = 0;
+      for (int32_t q = rptr[(size_t)(rbase + j)]; q < fill[j]; ++q) lv = std::max(lv, lev[rcol[q] - rbase] + 1);
+      lev[j] = lv;
+      maxlev = std::max(maxlev, lv);
+      for (int32_t p = L.colptr[j]; p < L.colptr[j + 1]; ++p) {
+        const int32_t i = L.rowval[p];
+        const int64_t E = ebase + p;
+        if (i < j) throw KbError(KB200_ERR_INPUT, "factor is not lower triangular");
+        if (i == j) diag[(size_t)(rbase + j)] = (int32_t)E;
+        Lrow[E] = (int32_t)(rbase + i);
+        Lcol[E] = (int32_t)(rbase + j);
+        epos[E] = (uint32_t)(c->pool_off[k] + p);
+        asrc[E] = dh.asrc[p] >= 0 ? (int32_t)(c->fa_abase[k] + dh.asrc[p]) : -1;
+        lev_of_entry[E] = lv;
+        const int32_t q = fill[i]++;
+        rcol[q] = (int32_t)(rbase + j);
+        rpos[q] = epos[E];
+      }
+    }
+    rbase += n;
+    ebase += (int64_t)L.nzval.size();
+  }
+  // entries by level, inside a level those of columns with a short row first (one thread per entry) and those with a
+  // long row last (one warp per entry): key = 2 * level + long; counting sort, stable
+  for (int64_t E = 0; E < nent; ++E) {
+    const int32_t j = Lcol[E];
+    const bool lng = rptr[(size_t)j + 1] - rptr[(size_t)j] > kCholLongRow;
+    lev_of_entry[E] = 2 * lev_of_entry[E] + (lng ? 1 : 0);
+  }
+  maxlev = 2 * maxlev + 1;
+  c->fa_lvl_ptr.assign((size_t)maxlev + 2, 0);
+  for (int64_t E = 0; E < nent; ++E) c->fa_lvl_ptr[(size_t)lev_of_entry[E] + 1]++;
+  for (int l = 0; l <= maxlev; ++l) c->fa_lvl_ptr[(size_t)l + 1] += c->fa_lvl_ptr[l];
+  {
+    std::vector<int64_t> at(c->fa_lvl_ptr.begin(), c->fa_lvl_ptr.end() - 1);
+    for (int64_t E = 0; E < nent; ++E) order[(size_t)at[lev_of_entry[E]]++] = (int32_t)E;
+  }
+  cudaStream_t s = c->stream;
+  c->d_fa_order.upload(order, s);
+  c->d_fa_Lrow.upload(Lrow, s);
+  c->d_fa_Lcol.upload(Lcol, s);
+  c->d_fa_asrc.upload(asrc, s);
+  c->d_fa_rptr.upload(rptr, s);
+  c->d_fa_rcol.upload(rcol, s);
+  c->d_fa_diag.upload(diag, s);
+  c->d_fa_epos.upload(epos, s);
+  c->d_fa_rpos.upload(rpos, s);
+  c->d_fa_A.alloc((size_t)na);
+  c->d_fa_fail.alloc(1);
+  CUDA_TRY(cudaMemsetAsync(c->d_fa_fail.p, 0, sizeof(int), s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  c->fa_ready = true;
+}
+
+// Level-scheduled numeric Cholesky of all local subdomains on the device: the staged A_II values -> the L segment of the
+// value pool (the value refresh then re-inverts the supernode blocks and rewrites the stream).
+void run_refactor(Ctx* c) {
+  const int64_t nloc = c->d1 - c->d0;
+  for (int64_t k = 0; k < nloc; ++k)
+    require(c->doms[c->d0 + k].have_avals, "kb200_refactor_interior must have been called for every local subdomain");
+  kb::CholParams P;
+  P.order = c->d_fa_order.p;
+  P.Lrow = c->d_fa_Lrow.p;
+  P.Lcol = c->d_fa_Lcol.p;
+  P.epos = c->d_fa_epos.p;
+  P.asrc = c->d_fa_asrc.p;
+  P.rptr = c->d_fa_rptr.p;
+  P.rcol = c->d_fa_rcol.p;
+  P.rpos = c->d_fa_rpos.p;
+  P.diag_e = c->d_fa_diag.p;
+  P.A = c->d_fa_A.p;
+  P.pool = c->d_pool.p;
+  P.fail = c->d_fa_fail.p;
+  cudaStream_t s = c->stream;
+  for (size_t l = 0; l + 1 < c->fa_lvl_ptr.size(); ++l) {
+    const int64_t e0 = c->fa_lvl_ptr[l], e1 = c->fa_lvl_ptr[l + 1];
+    if (e1 <= e0) continue;
+    if (l % 2 == 0) kb::chol_level_kernel<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, s>>>(P, e0, e1);
+    else kb::chol_level_warp_kernel<<<(unsigned)((e1 - e0 + 7) / 8), 256, 0, s>>>(P, e0, e1);   // 8 warps = 8 entries per block
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  int fail = 0;
+  CUDA_TRY(cudaMemcpyAsync(&fail, c->d_fa_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  c->fa_dirty = false;
+  if (fail) {
+    CUDA_TRY(cudaMemsetAsync(c->d_fa_fail.p, 0, sizeof(int), s));
+    throw KbError(KB200_ERR_INPUT, "kb200_refactor_interior: a pivot is not positive (A_II,d is not positive definite)");
+  }
+  c->refactorizations++;
 }
 
 // Before a re-analysis: values that were only sent to the device pool (kb200_update_*_values on a finalized
@@ -2015,6 +2160,70 @@ int kb200_update_cholesky_values(kb200_handle h, int64_t d, const double* L_nzva
   });
 }
 
+int kb200_upload_interior_pattern(kb200_handle h, int64_t d, const int64_t* colptr, const int64_t* rowval) {
+  KB_GROUP(kb200_upload_interior_pattern(h, d, colptr, rowval));
+  return guarded([&]() {
+    require(h && h->topo && colptr && rowval, "null argument");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    require(dh.have_chol, "kb200_upload_cholesky must come first (its permutation and pattern are the symbolic factorisation)");
+    const int64_t n = dh.n_I;
+    require(colptr[0] == 1, "A_II: colptr must be 1-based");
+    const int64_t nnz = colptr[n] - 1;
+    require(nnz >= n && nnz < (int64_t)0x7fffffff, "A_II: bad nnz");
+    // position of (row r, column cidx) of A_II (0-based), -1 if absent (rows of a column sorted, as Julia keeps them)
+    auto find = [&](int64_t r, int64_t cidx) -> int64_t {
+      const int64_t* b = rowval + (colptr[cidx] - 1);
+      const int64_t* e = rowval + (colptr[cidx + 1] - 1);
+      const int64_t* it = std::lower_bound(b, e, r + 1);
+      return (it != e && *it == r + 1) ? (int64_t)(it - rowval) : -1;
+    };
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t p = colptr[j] - 1; p + 1 < colptr[j + 1] - 1; ++p)
+        require(rowval[p] < rowval[p + 1], "A_II: row indices of a column must be sorted");
+    const kb::Csc& L = dh.in.L;
+    dh.asrc.assign(L.nzval.size(), -1);
+    int64_t found = 0;
+    for (int32_t j = 0; j < L.ncol; ++j)
+      for (int32_t p = L.colptr[j]; p < L.colptr[j + 1]; ++p) {
+        const int64_t oi = dh.in.perm[L.rowval[p]], oj = dh.in.perm[j];
+        int64_t at = find(oi, oj);
+        if (at < 0) at = find(oj, oi);   // one triangle stored
+        if (L.rowval[p] == j) require(at >= 0, "A_II: missing diagonal entry");
+        dh.asrc[p] = (int32_t)at;
+        found += at >= 0;
+      }
+    require(2 * found - n >= nnz || found >= nnz, "A_II has entries outside the pattern of the uploaded factor");
+    dh.a_nnz = nnz;
+    dh.have_apat = true;
+    dh.have_avals = false;
+    h->fa_ready = false;
+  });
+}
+
+int kb200_refactor_interior(kb200_handle h, int64_t d, const double* A_II_nzval) {
+  KB_GROUP(kb200_refactor_interior(h, d, A_II_nzval));
+  return guarded([&]() {
+    require(h && h->topo && A_II_nzval, "null argument");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    if (!h->finalized) finalize(h);   // the value pool and the stream must exist (pending refreshes wait for the next operation)
+    if (!is_local(h, d)) return;
+    use_device(h);
+    DomHost& dh = h->doms[d];
+    require(dh.have_apat, "kb200_upload_interior_pattern must come first");
+    if (!h->fa_ready) build_refactor_tables(h);
+    invalidate_dense_schur(h, dh);
+    const int64_t k = d - h->d0;
+    CUDA_TRY(cudaMemcpyAsync(h->d_fa_A.p + h->fa_abase[k], A_II_nzval, (size_t)dh.a_nnz * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffer
+    dh.have_avals = true;
+    dh.stale_L = true;          // the factor's newest values will live in the device pool only
+    h->fa_dirty = true;
+    h->values_dirty = true;
+  });
+}
+
 int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval) {
   KB_GROUP(kb200_update_local_block_values(h, d, AIG_nzval, AGG_nzval));
   return guarded([&]() {
@@ -3056,6 +3265,7 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
     finalize(h);
     h->stats[21] = (double)h->analyses;
     h->stats[22] = (double)h->refreshes;
+    h->stats[27] = (double)h->refactorizations;
     for (int64_t i = 0; i < n && i < 32; ++i) stats[i] = h->stats[i];
   });
 }

@@ -603,6 +603,108 @@ __global__ void __launch_bounds__(stream_threads(NW), (NW == kWarps && R == 1) ?
 }
 
 // ---------------------------------------------------------------------------------------------
+// Numeric Cholesky with a fixed symbolic pattern, batched over the subdomains (next row f1: the re-factorisation of
+// A_II,d for a new coefficient realization, Example07_PcgSchurStochasticEllipticPde.jl:160-204 calls cholesky() per
+// realization; EllipticPdeDomainDecomposition.jl:389-546 refills A_II,d).  Dot-product (up-looking) form on the pattern
+// of the uploaded factor: L[i,j] = (A[i,j] - sum_{k<j} L[i,k] L[j,k]) / L[j,j], L[j,j] = sqrt(A[j,j] - sum_k L[j,k]^2).
+// Columns are grouped into dependency levels (level(j) = 1 + max level of the columns row j touches); ONE launch per
+// level handles the entries of that level's columns of all subdomains, one thread per entry: it walks row j of the
+// factor (CSR view of the same values) and finds the matching entries of row i with a monotone scan (the pattern of
+// row i contains that of row j below j -- fill).  Every sum runs in ascending column order: deterministic.
+// All index arrays are global over the local subdomains (rows of all subdomains numbered consecutively).
+// ---------------------------------------------------------------------------------------------
+struct CholParams {
+  const int32_t* order;    // entries of the factor sorted by the level of their column
+  const int32_t* Lrow;     // per entry: (global) row i
+  const int32_t* Lcol;     // per entry: (global) column j
+  const uint32_t* epos;    // per entry: index of its value in the pool
+  const int32_t* asrc;     // per entry: index of A[i,j] in the staged values, -1 where A has no entry
+  const int32_t* rptr;     // CSR of the factor pattern: row pointers (global rows), columns ascending, diagonal last
+  const int32_t* rcol;     // (global) column of every CSR entry
+  const uint32_t* rpos;    // pool index of every CSR entry
+  const int32_t* diag_e;   // per (global) row j: entry id of (j, j)
+  const double* A;         // staged values of A_II of all local subdomains
+  double* pool;
+  int* fail;               // set to 1 when a pivot is not positive
+};
+__global__ void __launch_bounds__(256) chol_level_kernel(const CholParams P, int64_t e0, int64_t e1) {
+  const int64_t idx = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= e1) return;
+  const int32_t E = P.order[idx];
+  const int32_t i = P.Lrow[E], j = P.Lcol[E];
+  const int32_t qj0 = P.rptr[j], qj1 = P.rptr[j + 1] - 1;   // row j below the diagonal: [qj0, qj1)
+  double sjj = P.A[P.asrc[P.diag_e[j]]];
+  for (int32_t q = qj0; q < qj1; ++q) {
+    const double v = P.pool[P.rpos[q]];
+    sjj = fma(-v, v, sjj);
+  }
+  if (!(sjj > 0.0)) {
+    *P.fail = 1;
+    sjj = 1.0;
+  }
+  const double ljj = sqrt(sjj);
+  if (i == j) {
+    P.pool[P.epos[E]] = ljj;
+    return;
+  }
+  const int32_t a = P.asrc[E];
+  double sij = a >= 0 ? P.A[a] : 0.0;
+  int32_t p = P.rptr[i];
+  const int32_t pend = P.rptr[i + 1];
+  for (int32_t q = qj0; q < qj1; ++q) {
+    const int32_t k = P.rcol[q];
+    while (p < pend && P.rcol[p] < k) ++p;
+    if (p < pend && P.rcol[p] == k) sij = fma(-P.pool[P.rpos[p]], P.pool[P.rpos[q]], sij);
+  }
+  P.pool[P.epos[E]] = sij / ljj;
+}
+// The same for the entries of columns whose row is long (the separator rows: hundreds of entries): one WARP per entry,
+// the lanes stride over row j and find their partner in row i by binary search; lane sums in ascending order, then a
+// butterfly -- deterministic.  (One thread per entry walks such rows one dependent load at a time: the ~130 levels of
+// the top separators took 0.3 s of a 4M-DOF re-factorisation.)
+__global__ void __launch_bounds__(256) chol_level_warp_kernel(const CholParams P, int64_t e0, int64_t e1) {
+  const int64_t idx = e0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x & 31;
+  if (idx >= e1) return;   // (whole warps leave together)
+  const int32_t E = P.order[idx];
+  const int32_t i = P.Lrow[E], j = P.Lcol[E];
+  const int32_t qj0 = P.rptr[j], qj1 = P.rptr[j + 1] - 1;
+  const int32_t pi0 = P.rptr[i], pend = P.rptr[i + 1];
+  double pjj = 0.0, pij = 0.0;
+  for (int32_t q = qj0 + lane; q < qj1; q += 32) {
+    const double v = P.pool[P.rpos[q]];
+    pjj = fma(v, v, pjj);
+    if (i != j) {
+      const int32_t k = P.rcol[q];
+      int32_t lo = pi0, hi = pend;   // first position of row i with column >= k
+      while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (P.rcol[mid] < k) lo = mid + 1;
+        else hi = mid;
+      }
+      if (lo < pend && P.rcol[lo] == k) pij = fma(P.pool[P.rpos[lo]], v, pij);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    pjj += __shfl_xor_sync(0xffffffffu, pjj, o);
+    pij += __shfl_xor_sync(0xffffffffu, pij, o);
+  }
+  if (lane != 0) return;
+  double sjj = P.A[P.asrc[P.diag_e[j]]] - pjj;
+  if (!(sjj > 0.0)) {
+    *P.fail = 1;
+    sjj = 1.0;
+  }
+  const double ljj = sqrt(sjj);
+  if (i == j) {
+    P.pool[P.epos[E]] = ljj;
+    return;
+  }
+  const int32_t a = P.asrc[E];
+  P.pool[P.epos[E]] = ((a >= 0 ? P.A[a] : 0.0) - pij) / ljj;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched dense GEMV over subdomains:  out_loc[G_base+i] = w_i * sum_j M_d[i,j] * (w_j * x[l2g[j]])
 // with w = 1/cnt (Neumann-Neumann) or 1 (assembled local Schur).  M_d row-major.
 // grid = (row tiles, subdomains)

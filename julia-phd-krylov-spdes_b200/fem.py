@@ -49,6 +49,23 @@ class B200SchurOperator:
         # realization, EllipticPdeDomainDecomposition.jl:667-695): back to the matrix-free operator
         self.assembled = False
 
+    def enable_device_refactorization(self, A_II):
+        """Pattern of every local A_II,d (kb200_upload_interior_pattern): from now on a new realization needs no host
+        Cholesky -- ``refactor_realization`` recomputes the factors' values on the GPU."""
+        d0, d1 = self.local_range
+        for d in range(d0, d1):
+            self.h.upload_interior_pattern(d, A_II[d])
+
+    def refactor_realization(self, blocks):
+        """New coefficient realization on the same mesh / partition / ordering with the numeric Cholesky on the device
+        (kb200_refactor_interior; the reference calls cholesky(A_IIdd[d]) per realization, Example07:160-204 /
+        EllipticPdeDomainDecomposition.jl:1536)."""
+        d0, d1 = self.local_range
+        for d in range(d0, d1):
+            self.h.update_local_block_values(d, blocks.A_IG[d], blocks.A_GG[d])
+            self.h.refactor_interior(d, blocks.A_II[d])
+        self.assembled = False
+
     # LinearMaps.FunctionMap surface
     def __matmul__(self, x):
         return self.mul(x)

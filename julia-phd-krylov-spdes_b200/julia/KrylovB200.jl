@@ -264,6 +264,32 @@ function update_realization!(S::B200SchurOperator, A_IΓdd, A_ΓΓdd, F)
   return S
 end
 
+"""
+    enable_device_refactorization!(S, A_IIdd)
+    refactor_realization!(S, A_IIdd, A_IΓdd, A_ΓΓdd)
+
+Numeric re-factorisation on the GPU: the permutation and pattern of the factors uploaded at construction are the symbolic
+factorisation; a new realization sends the values of `A_IIdd[d]` (7 per row) instead of a host `cholesky()` and the values
+of `sparse(F.L)` (33 per row).
+"""
+function enable_device_refactorization!(S::B200SchurOperator, A_IIdd)
+  for d in 1:length(A_IIdd)
+    A = A_IIdd[d]
+    chk(ccall((:kb200_upload_interior_pattern, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}),
+              S.h, d - 1, Vector{Int64}(A.colptr), Vector{Int64}(A.rowval)))
+  end
+  return S
+end
+function refactor_realization!(S::B200SchurOperator, A_IIdd, A_IΓdd, A_ΓΓdd)
+  for d in 1:length(A_IIdd)
+    chk(ccall((:kb200_update_local_block_values, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+              S.h, d - 1, A_IΓdd[d].nzval, A_ΓΓdd[d].nzval))
+    chk(ccall((:kb200_refactor_interior, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), S.h, d - 1, A_IIdd[d].nzval))
+  end
+  S.assembled = false
+  return S
+end
+
 # ---------------------------------------------------------------------------------------------------
 # Post-hoc recycling variants (rrdefpcg.jl:48-151, :204-275; hrdefpcg.jl:48-164, :217-295): ONE ccall each
 # ---------------------------------------------------------------------------------------------------
@@ -342,6 +368,6 @@ end
 \(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
 ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
 
-export defpcg, eigpcg, eigdefpcg, update_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
+export defpcg, eigpcg, eigdefpcg, update_realization!, enable_device_refactorization!, refactor_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
 
 end # module

@@ -37,7 +37,33 @@ for rep in range(4):
     out.append({"rep": rep, "update_call_s": t_up, "first_op_incl_refresh_s": t_rhs, "solve_s": t_solve, "it": int(it),
                 "solve_device_ms": tm.solve_ms, "host_analyses": st["host_analyses"], "value_refreshes": st["value_refreshes"]})
     print(json.dumps(out[-1]), flush=True)
+# The same loop with the numeric Cholesky on the device (kb200_refactor_interior): the host sends the values of A_II,d,
+# A_IΓ,d, A_ΓΓ,d -- no host factorisation, no factor upload.  For comparison: the host-side factorisation of all
+# subdomains (what a caller of the value-only path pays per realization before it can call update_realization).
+from krylov_b200.hostprep import chol
+t0 = time.perf_counter()
+chol.factor_subdomains(prs[1].blocks.A_II, base[1], sd.node_Id)
+t_host_chol = time.perf_counter() - t0
+S.enable_device_refactorization(prs[0].blocks.A_II)
+for rep in range(4):
+    pr = prs[(rep + 1) % 2]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    S.refactor_realization(pr.blocks)
+    t_up = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = S.schur_rhs(pr.blocks.b_I, pr.blocks.b_G)          # first operation: device Cholesky + refresh
+    t_rhs = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    x, it, res, tm = solvers.pcg(S, b, np.zeros(sd.n_gamma), M, maxit=5000, return_timings=True)
+    t_solve = time.perf_counter() - t0
+    st = S.h.stats()
+    out.append({"rep": rep, "mode": "device_refactorization", "update_call_s": t_up, "first_op_incl_cholesky_and_refresh_s": t_rhs,
+                "solve_s": t_solve, "it": int(it), "host_analyses": st["host_analyses"], "device_refactorizations": st["device_refactorizations"],
+                "host_cholesky_all_subdomains_s": t_host_chol})
+    print(json.dumps(out[-1]), flush=True)
 nnzL = sum(f[1].nnz for f in prs[0].factors)
 print(json.dumps({"nx": nx, "ndom": ndom, "nnz_L": nnzL, "bytes_uploaded_per_update": 8 * (nnzL + sum(a.nnz for a in prs[0].blocks.A_IG) + sum(a.nnz for a in prs[0].blocks.A_GG)),
-                  "value_refs": st["value_refs"], "update_over_solve": out[-1]["update_call_s"] / out[-1]["solve_s"],
-                  "update_plus_refresh_over_solve": (out[-1]["update_call_s"] + out[-1]["first_op_incl_refresh_s"]) / out[-1]["solve_s"]}), flush=True)
+                  "value_refs": st["value_refs"], "update_over_solve": out[3]["update_call_s"] / out[3]["solve_s"],
+                  "update_plus_refresh_over_solve": (out[3]["update_call_s"] + out[3]["first_op_incl_refresh_s"]) / out[3]["solve_s"],
+                  "device_refactorization_update_plus_first_op_over_solve": (out[-1]["update_call_s"] + out[-1]["first_op_incl_cholesky_and_refresh_s"]) / out[-1]["solve_s"]}), flush=True)

@@ -623,3 +623,43 @@ def test_factors_from_a_minimum_degree_ordering(nx, ndom):
     inner2 = E.ExactInterior(pr2.blocks.A_II)
     assert rel(S * x, E.apply_local_schurs(pr2.blocks, inner2, sd, x)) <= 1e-12
     assert S.h.stats()["host_analyses"] == 1.0
+
+
+def test_device_refactorization_of_a_new_realization():
+    """f1: the numeric Cholesky of a new realization on the device (kb200_upload_interior_pattern /
+    kb200_refactor_interior) -- the host sends A_II,d values, not factors."""
+    from krylov_b200.hostprep import problem as PB
+    base = PB.build_mesh_and_partition(65, 16)
+    pr1 = PB.realization(base, ireal=1)
+    pr2 = PB.realization(base, ireal=2)
+    S = fem.B200SchurOperator(pr1.sd, pr1.blocks, pr1.factors, csize=4)
+    x = np.random.default_rng(2).standard_normal(pr1.sd.n_gamma)
+    y1 = S * x
+    S.enable_device_refactorization(pr1.blocks.A_II)
+    S.refactor_realization(pr2.blocks)
+    y2 = S * x
+    inner2 = E.ExactInterior(pr2.blocks.A_II)
+    assert rel(y2, E.apply_local_schurs(pr2.blocks, inner2, pr2.sd, x)) <= 1e-12
+    st = S.h.stats()
+    assert st["host_analyses"] == 1 and st["device_refactorizations"] == 1 and st["value_refreshes"] == 1
+    # against the stream built from the host's factors of the same realization: the factors agree to rounding
+    Shost = fem.B200SchurOperator(pr2.sd, pr2.blocks, pr2.factors, csize=4)
+    assert rel(y2, Shost * x) <= 1e-13
+    bs2 = S.schur_rhs(pr2.blocks.b_I, pr2.blocks.b_G)
+    assert rel(bs2, Shost.schur_rhs(pr2.blocks.b_I, pr2.blocks.b_G)) <= 1e-12
+    u = S.subdomain_solutions(x, pr2.blocks.b_I)
+    uh = Shost.subdomain_solutions(x, pr2.blocks.b_I)
+    assert max(rel(a, b) for a, b in zip(u, uh)) <= 1e-11
+    # back to realization 1 through the device factorisation: the operator of the first stream, to rounding
+    S.refactor_realization(pr1.blocks)
+    assert rel(S * x, y1) <= 1e-13 and S.h.stats()["device_refactorizations"] == 2
+    # a re-analysis (new option set through a re-upload) must see the values the DEVICE computed
+    S.h.upload_cholesky(0, pr1.factors[0][0], pr1.factors[0][1])
+    S.enable_device_refactorization(pr1.blocks.A_II)
+    assert rel(S * x, y1) <= 1e-13 and S.h.stats()["host_analyses"] == 2
+    # an indefinite block is reported, not factorised
+    bad = [A.copy() for A in pr2.blocks.A_II]
+    bad[5] = -bad[5]
+    S.h.refactor_interior(5, bad[5])
+    with pytest.raises(capi.KB200Error):
+        S * x
