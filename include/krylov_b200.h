@@ -132,6 +132,30 @@ int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG
  * kb200_update_local_block_values. */
 int kb200_upload_interior_pattern(kb200_handle h, int64_t d, const int64_t* colptr, const int64_t* rowval);
 int kb200_refactor_interior(kb200_handle h, int64_t d, const double* A_II_nzval);
+/* ---- re-assembly of the local blocks on the device (next row f1) ---------------------------------
+ * The element loop of prepare_local_schurs (EllipticPdeDomainDecomposition.jl:430-497) for a new coefficient, on the
+ * GPU: a realization then costs the host ONE vector (`coeff`, one double per mesh node) instead of the three nzval
+ * arrays of every subdomain.  The loop nest of the reference visits "contributions" in a fixed order -- element iel
+ * (1-based), vertex i (outer), vertex j (inner) -- and pushes ΔK_ij = Δa (Δy_i Δy_j + Δx_i Δx_j) / 4 / Area (:470)
+ * onto the triplet list of one of the three blocks; sparse() (:540-543) adds the duplicates of an entry in the order
+ * they were pushed.  The caller describes exactly that:
+ *   kb200_upload_assembly_mesh: `cells` (3 x nel, Int64 1-based, column-major as the reference's array) and `points`
+ *     (2 x nnode) of Mesh.jl:49-91;
+ *   kb200_upload_assembly_map(h, d, which, nnz, ptr, src): for block `which` of subdomain d (0: A_II,d  1: A_IΓ,d
+ *     2: A_ΓΓ,d) and every stored entry p of its nzval array (CSC order, the pattern uploaded before) the
+ *     contributions src[ptr[p] .. ptr[p+1]-1] (ptr 1-based like colptr, nnz + 1 entries), each the 1-based position
+ *     9 (iel - 1) + 3 (i - 1) + j of a contribution in the loop nest, in ascending order;
+ *   kb200_assemble_realization(h, coeff): coeff[nnode] -> Δa per element as :437-446 (sum of the three vertex values in
+ *     the order of `cells`, divided by 3), ΔK_ij with the reference's association order and no fused multiply-adds,
+ *     duplicates added in ascending contribution order: the values have the BITS of prepare_local_schurs.  A_IΓ,d /
+ *     A_ΓΓ,d go straight to the value pool, A_II,d to the staging area of kb200_refactor_interior (which must have
+ *     been prepared with kb200_upload_interior_pattern); the next operation runs the numeric Cholesky and the
+ *     stream refresh on the device.  The right-hand sides b_I,d / b_Γ (:499-536) stay with the caller.
+ *   kb200_get_local_block_values reads the current values back (any pointer may be null; A_II only once staged). */
+int kb200_upload_assembly_mesh(kb200_handle h, int64_t nnode, int64_t nel, const int64_t* cells, const double* points);
+int kb200_upload_assembly_map(kb200_handle h, int64_t d, int which, int64_t nnz, const int64_t* ptr, const int64_t* src);
+int kb200_assemble_realization(kb200_handle h, const double* coeff);
+int kb200_get_local_block_values(kb200_handle h, int64_t d, double* AII_nzval, double* AIG_nzval, double* AGG_nzval);
 /* ΠSd[d] of NeumannNeumannSchurPreconditioner (:1125), n_gd x n_gd column-major. */
 int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS);
 /* Dense local Schur complement S_d (assemble_local_schurs, :667-695), n_gd x n_gd column-major. */

@@ -28,6 +28,7 @@ SYMBOLS = [
     "kb200_trrrpcg", "kb200_trrrdefpcg", "kb200_trhrpcg", "kb200_trhrdefpcg",
     "kb200_lotrrrpcg", "kb200_lotrrrdefpcg", "kb200_lotrhrpcg", "kb200_lotrhrdefpcg",
     "kb200_upload_interior_pattern", "kb200_refactor_interior",
+    "kb200_upload_assembly_mesh", "kb200_upload_assembly_map", "kb200_assemble_realization", "kb200_get_local_block_values",
 ]
 
 
@@ -202,6 +203,35 @@ class Handle:
         A.sort_indices()
         ax = _f64(A.data)
         _chk(lib().kb200_refactor_interior(self.h, C.c_int64(d), _p(ax, C.c_double)))
+
+    def upload_assembly_mesh(self, cells, points):
+        """kb200_upload_assembly_mesh: `cells` (3 x nel, 0-based here) and `points` (2 x nnode) of the mesh."""
+        cl = _i64(np.asarray(cells).T) + 1                   # column-major 3 x nel, 1-based, as the reference's array
+        pt = _f64(np.asarray(points).T)                      # column-major 2 x nnode
+        self._as_nnode = int(pt.shape[0])
+        _chk(lib().kb200_upload_assembly_mesh(self.h, C.c_int64(pt.shape[0]), C.c_int64(cl.shape[0]),
+                                              _p(cl, C.c_int64), _p(pt, C.c_double)))
+
+    def upload_assembly_map(self, d, which, ptr, src):
+        """kb200_upload_assembly_map: contributions of every stored entry of block `which` (0 A_II, 1 A_IΓ, 2 A_ΓΓ) of
+        subdomain d; `ptr` / `src` 0-based here (hostprep.epdd_host.assembly_maps)."""
+        pp, ss = _i64(ptr) + 1, _i64(src) + 1
+        _chk(lib().kb200_upload_assembly_map(self.h, C.c_int64(d), C.c_int(which), C.c_int64(pp.size - 1),
+                                             _p(pp, C.c_int64), _p(ss, C.c_int64)))
+
+    def assemble_realization(self, coeff):
+        """kb200_assemble_realization: new coefficient (one value per mesh node) -> values of all local blocks on the device."""
+        cf = _f64(coeff)
+        if cf.size != getattr(self, "_as_nnode", -1):
+            raise KB200Error(-2, "coeff must hold one value per mesh node of kb200_upload_assembly_mesh")
+        _chk(lib().kb200_assemble_realization(self.h, _p(cf, C.c_double)))
+
+    def get_local_block_values(self, d, nnz_II=0, nnz_IG=0, nnz_GG=0):
+        """kb200_get_local_block_values: current nzval arrays on the device (an array of size 0 is not fetched)."""
+        a, g, hh = np.empty(nnz_II), np.empty(nnz_IG), np.empty(nnz_GG)
+        _chk(lib().kb200_get_local_block_values(self.h, C.c_int64(d), _p(a, C.c_double) if nnz_II else None,
+                                                _p(g, C.c_double) if nnz_IG else None, _p(hh, C.c_double) if nnz_GG else None))
+        return a, g, hh
 
     def update_local_block_values(self, d, A_IG, A_GG):
         g, hh = A_IG.tocsc(), A_GG.tocsc()
@@ -446,7 +476,8 @@ class Handle:
                 "max_top", "smem_bytes", "n_cta", "csize", "dense_bytes", "peer_exchange",
                 "consumer_warps", "ring_stages", "merge_depth", "min_block", "fused_pcg_ok", "vec_blocks",
                 "vec_threads", "exchange_entries", "exchange_entries_sent", "host_analyses", "value_refreshes",
-                "value_refs", "stream_read_bytes", "l2_persist_hit_ratio", "l2_prefetch_chunks", "device_refactorizations"]
+                "value_refs", "stream_read_bytes", "l2_persist_hit_ratio", "l2_prefetch_chunks", "device_refactorizations",
+                "device_assemblies"]
         return {k: s[i] for i, k in enumerate(keys)}
 
     def interface_maps(self):

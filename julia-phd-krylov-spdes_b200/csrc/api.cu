@@ -90,6 +90,11 @@ struct DomHost {
   std::vector<int32_t> asrc;
   int64_t a_nnz = 0;
   bool have_apat = false, have_avals = false;
+  // re-assembly on the device (kb200_upload_assembly_map): per stored entry of A_II / A_IΓ / A_ΓΓ its contributions
+  // (0-based offsets / positions 9 e + 3 i + j in the reference's loop nest)
+  std::vector<int64_t> as_ptr[3];
+  std::vector<int32_t> as_src[3];
+  bool as_have[3] = {false, false, false};
   std::vector<double> PiS, Sd;  // row-major copies of the column-major inputs
 };
 
@@ -190,6 +195,14 @@ struct kb200_ctx {
   std::vector<int64_t> fa_lvl_ptr, fa_abase;   // entries per dependency level / offset of every local subdomain's A_II values
   bool fa_ready = false, fa_dirty = false;
   int64_t refactorizations = 0;
+  // re-assembly of the local blocks on the device (kernels.cuh: assemble_values_kernel)
+  DevBuf<int32_t> d_as_cells, d_as_srcA, d_as_srcP;
+  DevBuf<double> d_as_pts, d_as_coeff;
+  DevBuf<int64_t> d_as_ptrA, d_as_ptrP;     // contributions of the entries staged for the Cholesky / of the pool entries
+  DevBuf<uint32_t> d_as_dstP;               // pool index of every A_IΓ / A_ΓΓ entry
+  int64_t as_nnode = 0, as_nel = 0, as_nA = 0, as_nP = 0;
+  bool as_mesh = false, as_ready = false;
+  int64_t assemblies = 0;
   DevBuf<kb::DmapRef> d_dmap;
   DevBuf<kb::BlockRef> d_blkref;
   std::vector<int64_t> pool_off;                 // per local subdomain (+1)
@@ -858,6 +871,7 @@ void finalize(Ctx* c) {
   }
   c->stats[26] = c->l2_prefetch_now;
   c->fa_ready = false;   // (a re-analysis moves the pool: the tables of the device-side factorisation are rebuilt on demand)
+  c->as_ready = false;
   c->stats[16] = c->fused_ok ? 1.0 : 0.0;
   c->stats[17] = c->nb;
   c->stats[18] = c->vec_threads;
@@ -979,6 +993,66 @@ void build_refactor_tables(Ctx* c) {
   CUDA_TRY(cudaMemsetAsync(c->d_fa_fail.p, 0, sizeof(int), s));
   CUDA_TRY(cudaStreamSynchronize(s));
   c->fa_ready = true;
+  c->as_ready = false;   // (the staging area of the A_II values was re-allocated)
+}
+
+// Tables of the device-side re-assembly (kernels.cuh: assemble_values_kernel), global over the local subdomains: the
+// entries of A_II,d land in the staging area of the numeric Cholesky (d_fa_A, subdomain after subdomain), those of
+// A_IΓ,d / A_ΓΓ,d in their segments of the value pool.
+void build_assembly_tables(Ctx* c) {
+  const int64_t nloc = c->d1 - c->d0;
+  int64_t nA = 0, nP = 0, cA = 0, cP = 0;
+  for (int64_t k = 0; k < nloc; ++k) {
+    const DomHost& dh = c->doms[c->d0 + k];
+    require(dh.as_have[0] && dh.as_have[1] && dh.as_have[2],
+            "kb200_assemble_realization: every local subdomain needs kb200_upload_assembly_map for its three blocks first");
+    require((int64_t)dh.as_ptr[0].size() == dh.a_nnz + 1, "assembly map of A_II does not match the pattern of kb200_upload_interior_pattern");
+    require((int64_t)dh.as_ptr[1].size() == (int64_t)c->pool_G[k] + 1 && (int64_t)dh.as_ptr[2].size() == (int64_t)c->pool_GG[k] + 1,
+            "assembly maps of A_IG / A_GG do not match the patterns of kb200_upload_local_blocks");
+    nA += dh.a_nnz;
+    nP += (int64_t)c->pool_G[k] + c->pool_GG[k];
+    cA += dh.as_ptr[0].back();
+    cP += dh.as_ptr[1].back() + dh.as_ptr[2].back();
+  }
+  require(nA == c->fa_abase[nloc], "internal: staging area of the A_II values out of step");
+  std::vector<int64_t> ptrA((size_t)nA + 1, 0), ptrP((size_t)nP + 1, 0);
+  std::vector<int32_t> srcA((size_t)cA), srcP((size_t)cP);
+  std::vector<uint32_t> dstP((size_t)nP);
+  int64_t sA = 0, sP = 0, qA = 0, qP = 0;
+  for (int64_t k = 0; k < nloc; ++k) {
+    const DomHost& dh = c->doms[c->d0 + k];
+    for (int w = 0; w < 3; ++w) {
+      const std::vector<int64_t>& pt = dh.as_ptr[w];
+      const std::vector<int32_t>& sr = dh.as_src[w];
+      const int64_t nz = (int64_t)pt.size() - 1;
+      for (int32_t v : sr) require((int64_t)v < 9 * c->as_nel, "assembly map refers to an element outside the mesh of kb200_upload_assembly_mesh");
+      if (w == 0) {
+        for (int64_t p = 0; p < nz; ++p) ptrA[(size_t)(sA + p + 1)] = qA + pt[(size_t)p + 1];
+        std::copy(sr.begin(), sr.end(), srcA.begin() + qA);
+        sA += nz;
+        qA += pt.back();
+      } else {
+        const int64_t base = c->pool_off[k] + c->pool_L[k] + (w == 2 ? (int64_t)c->pool_G[k] : 0);
+        for (int64_t p = 0; p < nz; ++p) {
+          ptrP[(size_t)(sP + p + 1)] = qP + pt[(size_t)p + 1];
+          dstP[(size_t)(sP + p)] = (uint32_t)(base + p);
+        }
+        std::copy(sr.begin(), sr.end(), srcP.begin() + qP);
+        sP += nz;
+        qP += pt.back();
+      }
+    }
+  }
+  cudaStream_t s = c->stream;
+  c->d_as_ptrA.upload(ptrA, s);
+  c->d_as_srcA.upload(srcA, s);
+  c->d_as_ptrP.upload(ptrP, s);
+  c->d_as_srcP.upload(srcP, s);
+  c->d_as_dstP.upload(dstP, s);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  c->as_nA = nA;
+  c->as_nP = nP;
+  c->as_ready = true;
 }
 
 // Level-scheduled numeric Cholesky of all local subdomains on the device: the staged A_II values -> the L segment of the
@@ -2224,6 +2298,137 @@ int kb200_refactor_interior(kb200_handle h, int64_t d, const double* A_II_nzval)
   });
 }
 
+int kb200_upload_assembly_mesh(kb200_handle h, int64_t nnode, int64_t nel, const int64_t* cells, const double* points) {
+  KB_GROUP(kb200_upload_assembly_mesh(h, nnode, nel, cells, points));
+  return guarded([&]() {
+    require(h && cells && points, "null argument");
+    require(nnode > 0 && nel > 0 && nnode < (int64_t)0x7fffffff && 9 * nel < (int64_t)0x7fffffff, "mesh size out of range");
+    use_device(h);
+    std::vector<int32_t> cl((size_t)(3 * nel));
+    for (int64_t q = 0; q < 3 * nel; ++q) {
+      require(cells[q] >= 1 && cells[q] <= nnode, "cells: node index out of range (1-based expected)");
+      cl[(size_t)q] = (int32_t)(cells[q] - 1);
+    }
+    h->d_as_cells.upload(cl, h->stream);
+    h->d_as_pts.alloc((size_t)(2 * nnode));
+    CUDA_TRY(cudaMemcpyAsync(h->d_as_pts.p, points, (size_t)(2 * nnode) * 8, cudaMemcpyHostToDevice, h->stream));
+    h->d_as_coeff.alloc((size_t)nnode);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->as_nnode = nnode;
+    h->as_nel = nel;
+    h->as_mesh = true;
+    h->as_ready = false;
+  });
+}
+
+int kb200_upload_assembly_map(kb200_handle h, int64_t d, int which, int64_t nnz, const int64_t* ptr, const int64_t* src) {
+  KB_GROUP(kb200_upload_assembly_map(h, d, which, nnz, ptr, src));
+  return guarded([&]() {
+    require(h && h->topo && ptr, "null argument");
+    require(d >= 0 && d < h->ndom, "subdomain index out of range");
+    require(which >= 0 && which <= 2, "which: 0 = A_II, 1 = A_IG, 2 = A_GG");
+    require(nnz >= 0 && ptr[0] == 1, "assembly map: ptr must be 1-based with nnz + 1 entries");
+    if (!is_local(h, d)) return;
+    DomHost& dh = h->doms[d];
+    const int64_t nc = ptr[nnz] - 1;
+    require(nc >= 0 && nc < (int64_t)0x7fffffff && (nc == 0 || src), "assembly map: bad number of contributions");
+    std::vector<int64_t>& pt = dh.as_ptr[which];
+    std::vector<int32_t>& sr = dh.as_src[which];
+    pt.resize((size_t)nnz + 1);
+    for (int64_t p = 0; p <= nnz; ++p) {
+      require(p == 0 || ptr[p] >= ptr[p - 1], "assembly map: ptr not monotone");
+      pt[(size_t)p] = ptr[p] - 1;
+    }
+    sr.resize((size_t)nc);
+    for (int64_t q = 0; q < nc; ++q) {
+      require(src[q] >= 1 && src[q] < (int64_t)0x7fffffff, "assembly map: contribution index out of range (1-based expected)");
+      sr[(size_t)q] = (int32_t)(src[q] - 1);
+    }
+    for (int64_t p = 0; p < nnz; ++p)
+      for (int64_t q = pt[(size_t)p] + 1; q < pt[(size_t)p + 1]; ++q)
+        require(sr[(size_t)q - 1] < sr[(size_t)q], "assembly map: the contributions of an entry must ascend (the order sparse() adds them in)");
+    dh.as_have[which] = true;
+    h->as_ready = false;
+  });
+}
+
+int kb200_assemble_realization(kb200_handle h, const double* coeff) {
+  KB_GROUP(kb200_assemble_realization(h, coeff));
+  return guarded([&]() {
+    require(h && h->topo && coeff, "null argument");
+    require(h->as_mesh, "kb200_upload_assembly_mesh must come first");
+    require(!h->global_mode, "device re-assembly is not available for the global-column variant");
+    if (!h->finalized) finalize(h);   // the value pool must exist
+    use_device(h);
+    const int64_t nloc = h->d1 - h->d0;
+    for (int64_t k = 0; k < nloc; ++k)
+      require(h->doms[h->d0 + k].have_apat, "kb200_assemble_realization: every local subdomain needs kb200_upload_interior_pattern first");
+    if (!h->fa_ready) build_refactor_tables(h);
+    if (!h->as_ready) build_assembly_tables(h);
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d_as_coeff.p, coeff, (size_t)h->as_nnode * 8, cudaMemcpyHostToDevice, s));
+    kb::AsmParams P;
+    P.cells = h->d_as_cells.p;
+    P.pts = h->d_as_pts.p;
+    P.coeff = h->d_as_coeff.p;
+    if (h->as_nA) {
+      P.ptr = h->d_as_ptrA.p;
+      P.src = h->d_as_srcA.p;
+      P.dst = nullptr;
+      P.out = h->d_fa_A.p;
+      P.n = h->as_nA;
+      kb::assemble_values_kernel<<<(unsigned)((h->as_nA + 255) / 256), 256, 0, s>>>(P);
+      h->launches++;
+    }
+    if (h->as_nP) {
+      P.ptr = h->d_as_ptrP.p;
+      P.src = h->d_as_srcP.p;
+      P.dst = h->d_as_dstP.p;
+      P.out = h->d_pool.p;
+      P.n = h->as_nP;
+      kb::assemble_values_kernel<<<(unsigned)((h->as_nP + 255) / 256), 256, 0, s>>>(P);
+      h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));   // the caller may reuse its buffer
+    for (int64_t k = 0; k < nloc; ++k) {
+      DomHost& dh = h->doms[h->d0 + k];
+      invalidate_dense_schur(h, dh);
+      dh.have_avals = true;
+      dh.stale_L = dh.stale_blocks = true;   // the newest values live on the device only
+    }
+    h->fa_dirty = true;
+    h->values_dirty = true;
+    h->assemblies++;
+  });
+}
+
+int kb200_get_local_block_values(kb200_handle h, int64_t d, double* AII_nzval, double* AIG_nzval, double* AGG_nzval) {
+  if (h && h->grp) {  // served by the member that owns the subdomain
+    for (Ctx* m : h->grp->members)
+      if (m->topo && is_local(m, d)) return kb200_get_local_block_values(m, d, AII_nzval, AIG_nzval, AGG_nzval);
+    g_err = "subdomain index out of range";
+    return KB200_ERR_INVALID;
+  }
+  return guarded([&]() {
+    require(h && h->topo, "null argument");
+    require(is_local(h, d), "subdomain is not local to this handle");
+    require(h->finalized && h->d_pool.p != nullptr, "kb200_get_local_block_values: the handle is not finalized");
+    use_device(h);
+    const DomHost& dh = h->doms[d];
+    const int64_t k = d - h->d0;
+    if (AII_nzval) {
+      require(h->fa_ready && dh.have_avals, "A_II values were never staged on the device (kb200_refactor_interior / kb200_assemble_realization)");
+      CUDA_TRY(cudaMemcpyAsync(AII_nzval, h->d_fa_A.p + h->fa_abase[k], (size_t)dh.a_nnz * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    const double* pp = h->d_pool.p + h->pool_off[k] + h->pool_L[k];
+    if (AIG_nzval && h->pool_G[k]) CUDA_TRY(cudaMemcpyAsync(AIG_nzval, pp, (size_t)h->pool_G[k] * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (AGG_nzval && h->pool_GG[k])
+      CUDA_TRY(cudaMemcpyAsync(AGG_nzval, pp + h->pool_G[k], (size_t)h->pool_GG[k] * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  });
+}
+
 int kb200_update_local_block_values(kb200_handle h, int64_t d, const double* AIG_nzval, const double* AGG_nzval) {
   KB_GROUP(kb200_update_local_block_values(h, d, AIG_nzval, AGG_nzval));
   return guarded([&]() {
@@ -3266,6 +3471,7 @@ int kb200_get_stats(kb200_handle h, double* stats, int64_t n) {
     h->stats[21] = (double)h->analyses;
     h->stats[22] = (double)h->refreshes;
     h->stats[27] = (double)h->refactorizations;
+    h->stats[28] = (double)h->assemblies;
     for (int64_t i = 0; i < n && i < 32; ++i) stats[i] = h->stats[i];
   });
 }

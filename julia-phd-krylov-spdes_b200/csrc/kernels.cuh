@@ -705,6 +705,55 @@ __global__ void __launch_bounds__(256) chol_level_warp_kernel(const CholParams P
 }
 
 // ---------------------------------------------------------------------------------------------
+// Re-assembly of the local blocks for a new coefficient (kb200_assemble_realization): the element loop of
+// prepare_local_schurs, EllipticPdeDomainDecomposition.jl:430-497, in gather form.  One thread per stored entry of a
+// block; its contributions are positions 9 e + 3 i + j of the reference's loop nest (element e, vertices i, j) in
+// ascending order = the order in which sparse() (:540-543) adds the duplicates.  Every operation is the reference's,
+// in its association order, with explicitly rounded multiplies / adds (no contraction into fused multiply-adds, which
+// Julia does not apply either): the values have the bits of the host assembly.
+// ---------------------------------------------------------------------------------------------
+struct AsmParams {
+  const int32_t* cells;   // 3 x nel, 0-based node ids, column-major like the reference's `cells`
+  const double* pts;      // 2 x nnode
+  const double* coeff;    // nnode
+  const int64_t* ptr;     // per entry: its contributions [ptr[s], ptr[s + 1])
+  const int32_t* src;     // 9 e + 3 i + j, 0-based
+  const uint32_t* dst;    // per entry: index in `out` (nullptr: s itself)
+  double* out;
+  int64_t n;
+};
+__device__ __forceinline__ double pick3(int k, double a0, double a1, double a2) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
+__global__ void __launch_bounds__(256) assemble_values_kernel(const AsmParams P) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n) return;
+  double acc = 0.0;
+  const int64_t q0 = P.ptr[s], q1 = P.ptr[s + 1];
+  for (int64_t q = q0; q < q1; ++q) {
+    const int32_t c = P.src[q];
+    const int32_t e = c / 9, ij = c - 9 * e, i = ij / 3, j = ij - 3 * i;
+    const int32_t n0 = P.cells[3 * (int64_t)e], n1 = P.cells[3 * (int64_t)e + 1], n2 = P.cells[3 * (int64_t)e + 2];
+    const double x0 = P.pts[2 * (int64_t)n0], y0 = P.pts[2 * (int64_t)n0 + 1];
+    const double x1 = P.pts[2 * (int64_t)n1], y1 = P.pts[2 * (int64_t)n1 + 1];
+    const double x2 = P.pts[2 * (int64_t)n2], y2 = P.pts[2 * (int64_t)n2 + 1];
+    // :437-446   Δa = 0.; Δa += coeff[jnode] (three times); Δa /= 3.
+    double da = __dadd_rn(__dadd_rn(__dadd_rn(0.0, P.coeff[n0]), P.coeff[n1]), P.coeff[n2]);
+    da = __ddiv_rn(da, 3.0);
+    // :449-454   (1-based Δx[1..3], Δy[1..3] of the reference = dx0..2, dy0..2)
+    const double dx0 = __dsub_rn(x2, x1), dx1 = __dsub_rn(x0, x2), dx2 = __dsub_rn(x1, x0);
+    const double dy0 = __dsub_rn(y1, y2), dy1 = __dsub_rn(y2, y0), dy2 = __dsub_rn(y0, y1);
+    // :457       Area = (Δx[3] * Δy[2] - Δx[2] * Δy[3]) / 2.
+    const double area = __ddiv_rn(__dsub_rn(__dmul_rn(dx2, dy1), __dmul_rn(dx1, dy2)), 2.0);
+    // :470       ΔKij = Δa * (Δy[i] * Δy[j] + Δx[i] * Δx[j]) / 4 / Area
+    const double dyi = pick3(i, dy0, dy1, dy2), dyj = pick3(j, dy0, dy1, dy2);
+    const double dxi = pick3(i, dx0, dx1, dx2), dxj = pick3(j, dx0, dx1, dx2);
+    const double g = __dadd_rn(__dmul_rn(dyi, dyj), __dmul_rn(dxi, dxj));
+    const double k = __ddiv_rn(__ddiv_rn(__dmul_rn(da, g), 4.0), area);
+    acc = q == q0 ? k : __dadd_rn(acc, k);
+  }
+  P.out[P.dst ? P.dst[s] : s] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched dense GEMV over subdomains:  out_loc[G_base+i] = w_i * sum_j M_d[i,j] * (w_j * x[l2g[j]])
 // with w = 1/cnt (Neumann-Neumann) or 1 (assembled local Schur).  M_d row-major.
 // grid = (row tiles, subdomains)

@@ -66,6 +66,24 @@ class B200SchurOperator:
             self.h.refactor_interior(d, blocks.A_II[d])
         self.assembled = False
 
+    def enable_device_assembly(self, cells, points, epart, A_II):
+        """Mesh + contribution lists of every local block (kb200_upload_assembly_mesh / kb200_upload_assembly_map) on top
+        of ``enable_device_refactorization``: from now on a new realization is ONE vector -- ``assemble_realization(coeff)``
+        runs the element loop of prepare_local_schurs (:430-497), the numeric Cholesky and the stream refresh on the GPU."""
+        from .hostprep import epdd_host
+        self.enable_device_refactorization(A_II)
+        d0, d1 = self.local_range
+        maps = epdd_host.assembly_maps(cells, epart, self.sd, dom_range=(d0, d1))
+        self.h.upload_assembly_mesh(cells, points)
+        for d in range(d0, d1):
+            for which in range(3):
+                self.h.upload_assembly_map(d, which, maps.ptr[d][which], maps.src[d][which])
+
+    def assemble_realization(self, coeff):
+        """New coefficient realization from the nodal coefficient alone (kb200_assemble_realization)."""
+        self.h.assemble_realization(coeff)
+        self.assembled = False
+
     # LinearMaps.FunctionMap surface
     def __matmul__(self, x):
         return self.mul(x)

@@ -226,6 +226,102 @@ def prepare_local_schurs(cells, points, epart, sd: Subdomains, coeff, f_vals, u_
 
 
 
+@dataclass
+class AssemblyMaps:
+    """Gather form of the element loop of prepare_local_schurs (:430-497) for kb200_upload_assembly_map: per subdomain
+    and block (0: A_II, 1: A_IΓ, 2: A_ΓΓ) and per stored entry of the block (CSC order, rows sorted) the contributions
+    src[ptr[p]:ptr[p+1]] (0-based here; the ABI takes both 1-based), each the position 9 e + 3 i + j of a contribution in
+    the reference's loop nest (element e, vertex i outer, vertex j inner), ascending = the order in which sparse()
+    (:540-543) adds the duplicates of an entry."""
+    ptr: List[List[np.ndarray]]     # [d][which] -> int64 (nnz + 1)
+    src: List[List[np.ndarray]]     # [d][which] -> int64 (number of contributions)
+
+
+def assembly_maps(cells, epart, sd: Subdomains, dom_range=None) -> AssemblyMaps:
+    """Contribution lists of every stored entry of A_II,d / A_IΓ,d / A_ΓΓ,d (same routing as prepare_local_schurs,
+    :472-497; purely structural: mesh, partition and index maps, no coefficient)."""
+    ndom, nnode = sd.ndom, sd.nnode
+    nel = cells.shape[1]
+    owner = sd.node_owner
+    n_Id = np.array([v.size for v in sd.node_Id])
+    n_gd = np.array([v.size for v in sd.gd_nodes])
+    iptr = np.concatenate([[0], np.cumsum(n_Id)])
+    gptr = np.concatenate([[0], np.cumsum(n_gd)])
+    cat_I = np.full(nnode, -1, dtype=np.int64)
+    for d in range(ndom):
+        cat_I[sd.node_Id[d]] = iptr[d] + np.arange(n_Id[d])
+    gk = np.concatenate([d * np.int64(nnode) + sd.gd_nodes[d] for d in range(ndom)]) if ndom else np.zeros(0, np.int64)
+    go = np.argsort(gk)
+    gk_s = gk[go]
+
+    def cat_G(dom, node):
+        key = dom * np.int64(nnode) + node
+        pos = np.minimum(np.searchsorted(gk_s, key), gk_s.size - 1)
+        if not np.all(gk_s[pos] == key):
+            raise KeyError("interface node of an element is missing from its subdomain's Γ_d")
+        return go[pos]
+
+    e_ids = np.arange(nel, dtype=np.int64)
+    if dom_range is not None:
+        e_ids = e_ids[(epart >= dom_range[0]) & (epart < dom_range[1])]
+    en = cells[:, e_ids]                                     # (3, m)
+    oi = owner[en]
+    m = e_ids.size
+    ni = np.broadcast_to(en[:, None, :], (3, 3, m))
+    nj = np.broadcast_to(en[None, :, :], (3, 3, m))
+    o_i = np.broadcast_to(oi[:, None, :], (3, 3, m))
+    o_j = np.broadcast_to(oi[None, :, :], (3, 3, m))
+    dom = np.broadcast_to(epart[e_ids][None, None, :], (3, 3, m))
+    cid = (9 * e_ids[None, None, :] + 3 * np.arange(3)[:, None, None] + np.arange(3)[None, :, None])   # (i, j, e)
+
+    def lists(mask, rows, cols, rptr, cptr):
+        c = cid[mask]
+        o = np.lexsort((c, rows, cols))                      # column, then row, then contribution order
+        r_s, c_s, id_s = rows[o], cols[o], c[o]
+        new = np.ones(o.size, dtype=bool)
+        new[1:] = (r_s[1:] != r_s[:-1]) | (c_s[1:] != c_s[:-1])
+        start = np.flatnonzero(new)                          # first contribution of every stored entry
+        ent_col = c_s[start]
+        ptr_all = np.concatenate([start, [o.size]]).astype(np.int64)
+        out_p, out_s = [], []
+        e_lo = np.searchsorted(ent_col, cptr[:-1], side="left")
+        e_hi = np.searchsorted(ent_col, cptr[1:], side="left")
+        for d in range(ndom):
+            a, b = e_lo[d], e_hi[d]
+            pp = ptr_all[a:b + 1] - ptr_all[a]
+            out_p.append(pp.copy())
+            out_s.append(id_s[ptr_all[a]:ptr_all[b]].astype(np.int64))
+        return out_p, out_s
+
+    m_gg = (o_i == -1) & (o_j == -1)
+    m_ii = (o_i > 0) & (o_j > 0)
+    m_ig = (o_i > 0) & (o_j == -1)
+    p0, s0 = lists(m_ii, cat_I[ni[m_ii]], cat_I[nj[m_ii]], iptr, iptr)
+    p1, s1 = lists(m_ig, cat_I[ni[m_ig]], cat_G(dom[m_ig], nj[m_ig]), iptr, gptr)
+    p2, s2 = lists(m_gg, cat_G(dom[m_gg], ni[m_gg]), cat_G(dom[m_gg], nj[m_gg]), gptr, gptr)
+    return AssemblyMaps([[p0[d], p1[d], p2[d]] for d in range(ndom)], [[s0[d], s1[d], s2[d]] for d in range(ndom)])
+
+
+def assemble_values_from_map(cells, points, coeff, ptr, src):
+    """What kb200_assemble_realization computes for one block, on the host (numpy): ΔK of every contribution as :437-470,
+    duplicates added in ascending contribution order.  Test twin of kernels.cuh::assemble_values_kernel."""
+    e = src // 9
+    i = (src % 9) // 3
+    j = src % 3
+    ue, inv = np.unique(e, return_inverse=True)
+    K, _ = _element_geometry(cells[:, ue], points, coeff)
+    v = K[i, j, inv]
+    n = ptr.size - 1
+    cnt = np.diff(ptr)
+    acc = np.zeros(n)
+    has = cnt > 0
+    acc[has] = v[ptr[:-1][has]]
+    for r in range(1, int(cnt.max()) if n else 0):
+        mk = cnt > r
+        acc[mk] = acc[mk] + v[ptr[:-1][mk] + r]
+    return acc
+
+
 def restriction(sd: Subdomains, d):
     """R_d: n_Γd x n_Γ boolean gather matrix (the Dict loops at :728-730)."""
     g = sd.gamma_l2g[d]

@@ -69,6 +69,36 @@ def interface_rhs(base, coeff, f_vals, u_dir):
     return epdd_host.prepare_local_schurs(cells[:, touch], points, epart[touch], sd, coeff, f_vals, u_dir).b_G
 
 
+class RhsUpdater:
+    """b_I,d / b_Γ of prepare_local_schurs (:499-536) for a new coefficient WITHOUT assembling the blocks (the companion of
+    kb200_assemble_realization, which leaves the right-hand sides with the caller).  Only the Dirichlet lift (:499-508)
+    depends on the coefficient, and only in the entries of nodes that share an element with a Dirichlet node; the
+    accumulation is element-major, so re-running the element loop over ALL elements of those nodes (a boundary layer,
+    O(sqrt(nel)) elements) reproduces their entries with the bits of the full assembly, and every other entry is the
+    load vector, computed once."""
+
+    def __init__(self, base, f_vals, u_dir):
+        cells, points, markers, neighbors, epart, npart, sd = base
+        self.base, self.f_vals, self.u_dir = base, f_vals, u_dir
+        is_dir = sd.node_owner == 0
+        el_dir = is_dir[cells].any(axis=0)
+        tgt = np.zeros(sd.nnode, dtype=bool)
+        tgt[cells[:, el_dir].ravel()] = True
+        tgt &= ~is_dir                                       # nodes whose entry carries lift terms
+        self.layer = tgt[cells].any(axis=0)                  # every element of such a node
+        static = epdd_host.prepare_local_schurs(cells, points, epart, sd, np.ones(sd.nnode), f_vals, u_dir)
+        self.b_G0, self.b_I0 = static.b_G, static.b_I
+        self.mask_G = tgt[sd.node_gamma]
+        self.mask_I = [tgt[sd.node_Id[d]] for d in range(sd.ndom)]
+
+    def __call__(self, coeff):
+        cells, points, markers, neighbors, epart, npart, sd = self.base
+        part = epdd_host.prepare_local_schurs(cells[:, self.layer], points, epart[self.layer], sd, coeff, self.f_vals, self.u_dir)
+        b_G = np.where(self.mask_G, part.b_G, self.b_G0)
+        b_I = [np.where(self.mask_I[d], part.b_I[d], self.b_I0[d]) for d in range(sd.ndom)]
+        return b_I, b_G
+
+
 def build_problem(nx, ndom, ireal=1, jitter=0.2, median=False):
     return realization(build_mesh_and_partition(nx, ndom, jitter), ireal, median)
 

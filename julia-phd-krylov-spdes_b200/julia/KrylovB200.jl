@@ -112,7 +112,6 @@ end
 # S * x and mul!(y, S, x): what cg.jl:83 and cg.jl:93 call on the reference's FunctionMap
 # (apply_local_schurs, EllipticPdeDomainDecomposition.jl:711-747 / :761-785).
 function mul!(y::Vector{Float64}, S::B200SchurOperator, x::Vector{Float64})
-  f = S.assembled ? :kb200_apply_schur_assembled : :kb200_apply_schur
   if S.assembled
     chk(ccall((:kb200_apply_schur_assembled, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), S.h, x, y, 1))
   else
@@ -290,6 +289,58 @@ function refactor_realization!(S::B200SchurOperator, A_IIdd, A_IΓdd, A_ΓΓdd)
   return S
 end
 
+"""
+    enable_device_assembly!(S, cells, points, epart, node_owner, ind_Id_g2l, ind_Γd_g2l, A_IIdd, A_IΓdd, A_ΓΓdd)
+    assemble_realization!(S, coeff)
+
+The element loop of prepare_local_schurs (EllipticPdeDomainDecomposition.jl:430-497) on the GPU: after the one-time
+set-up a new realization is ONE vector, the nodal coefficient `coeff` (the `Array{Float64,1}` branch of :440-441); the
+blocks are re-assembled with the bits of `sparse(I, J, V)` (:540-543), the numeric Cholesky and the stream refresh follow
+on the device.  The set-up replays the routing of the loop nest (:459-497) once to tell the library, for every stored
+entry of A_IIdd[d] / A_IΓdd[d] / A_ΓΓdd[d], which contributions `9 (iel - 1) + 3 (i - 1) + j` it is the sum of.
+The right-hand sides (b_Id, b_Γ) remain the caller's (only their Dirichlet-lift terms depend on the coefficient).
+"""
+function enable_device_assembly!(S::B200SchurOperator, cells::Array{Int,2}, points::Array{Float64,2}, epart::Array{Int,1},
+                                 node_owner::Array{Int,1}, ind_Id_g2l::Vector{Dict{Int,Int}}, ind_Γd_g2l::Vector{Dict{Int,Int}},
+                                 A_IIdd, A_IΓdd, A_ΓΓdd)
+  enable_device_refactorization!(S, A_IIdd)
+  ndom = length(A_IIdd)
+  nel = size(cells, 2)
+  chk(ccall((:kb200_upload_assembly_mesh, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Float64}),
+            S.h, size(points, 2), nel, cells, points))
+  # position of entry (r, c) in the nzval array of a SparseMatrixCSC (rows of a column are sorted)
+  pos(A, r, c) = (rg = A.colptr[c]:A.colptr[c+1]-1; rg[searchsortedfirst(view(A.rowval, rg), r)])
+  lists = [[[Int64[] for _ in 1:length(A[d].nzval)] for A in (A_IIdd, A_IΓdd, A_ΓΓdd)] for d in 1:ndom]
+  for iel in 1:nel                                            # the traversal of :430-497
+    idom = epart[iel]
+    for (i, inode) in enumerate(cells[:, iel]), (j, jnode) in enumerate(cells[:, iel])
+      io, jo = node_owner[inode], node_owner[jnode]
+      (io == 0 || jo == 0) && continue
+      c = 9 * (iel - 1) + 3 * (i - 1) + j
+      if io == -1 && jo == -1
+        push!(lists[idom][3][pos(A_ΓΓdd[idom], ind_Γd_g2l[idom][inode], ind_Γd_g2l[idom][jnode])], c)
+      elseif io > 0 && jo > 0
+        push!(lists[idom][1][pos(A_IIdd[idom], ind_Id_g2l[idom][inode], ind_Id_g2l[idom][jnode])], c)
+      elseif io > 0 && jo == -1
+        push!(lists[idom][2][pos(A_IΓdd[idom], ind_Id_g2l[idom][inode], ind_Γd_g2l[idom][jnode])], c)
+      end
+    end
+  end
+  for d in 1:ndom, which in 1:3
+    l = lists[d][which]
+    ptr = Int64[1]; for v in l; push!(ptr, ptr[end] + length(v)); end
+    src = isempty(l) ? Int64[] : reduce(vcat, l)
+    chk(ccall((:kb200_upload_assembly_map, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Int64, Ptr{Int64}, Ptr{Int64}),
+              S.h, d - 1, which - 1, length(l), ptr, src))
+  end
+  return S
+end
+function assemble_realization!(S::B200SchurOperator, coeff::Vector{Float64})
+  chk(ccall((:kb200_assemble_realization, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), S.h, coeff))
+  S.assembled = false
+  return S
+end
+
 # ---------------------------------------------------------------------------------------------------
 # Post-hoc recycling variants (rrdefpcg.jl:48-151, :204-275; hrdefpcg.jl:48-164, :217-295): ONE ccall each
 # ---------------------------------------------------------------------------------------------------
@@ -368,6 +419,6 @@ end
 \(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
 ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
 
-export defpcg, eigpcg, eigdefpcg, update_realization!, enable_device_refactorization!, refactor_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
+export defpcg, eigpcg, eigdefpcg, update_realization!, enable_device_refactorization!, refactor_realization!, enable_device_assembly!, assemble_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
 
 end # module

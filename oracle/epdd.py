@@ -187,16 +187,30 @@ def prepare_local_schurs_ref(cells, points, epart, sd: Subdomains, coeff, f_vals
                 b_G[sd.ind_gamma_g2l[inode]] += db
             elif io > 0:
                 b_I[idom][ind_Id[idom][inode]] += db
-    A_II = [sp.coo_matrix((II[d][2], (II[d][0], II[d][1])), shape=(n_Id[d], n_Id[d])).tocsc()
-            for d in range(ndom)]
-    A_IG = [sp.coo_matrix((IG[d][2], (IG[d][0], IG[d][1])), shape=(n_Id[d], n_gd[d])).tocsc()
-            for d in range(ndom)]
-    A_GG = [sp.coo_matrix((GG[d][2], (GG[d][0], GG[d][1])), shape=(n_gd[d], n_gd[d])).tocsc()
-            for d in range(ndom)]
-    for m in A_II + A_IG + A_GG:
-        m.sum_duplicates()
-        m.sort_indices()
+    A_II = [julia_sparse(II[d][0], II[d][1], II[d][2], (n_Id[d], n_Id[d])) for d in range(ndom)]     # :540-543
+    A_IG = [julia_sparse(IG[d][0], IG[d][1], IG[d][2], (n_Id[d], n_gd[d])) for d in range(ndom)]
+    A_GG = [julia_sparse(GG[d][0], GG[d][1], GG[d][2], (n_gd[d], n_gd[d])) for d in range(ndom)]
     return LocalBlocks(A_II, A_IG, A_GG, b_I, b_G)
+
+
+def julia_sparse(I, J, V, shape):
+    """`sparse(I, J, V, m, n)` of Julia's SparseArrays (the call at :540-543): CSC with sorted rows in which the
+    duplicates of an entry are combined with `+` in the order they appear in the triplet lists (sparse! counting-sorts
+    the triplets by row -- a stable sort -- and folds repeated (row, column) pairs from left to right into the first
+    one).  scipy's coo -> csc conversion makes no such promise, and for the diagonal entries (up to eight element
+    contributions) the order decides the last bit."""
+    acc = {}
+    for i, j, v in zip(I, J, V):
+        k = (int(j), int(i))
+        acc[k] = acc[k] + v if k in acc else v
+    keys = sorted(acc)
+    indptr = np.zeros(shape[1] + 1, dtype=np.int64)
+    for j, _ in keys:
+        indptr[j + 1] += 1
+    indptr = np.cumsum(indptr)
+    indices = np.array([i for _, i in keys], dtype=np.int64)
+    data = np.array([acc[k] for k in keys], dtype=np.float64)
+    return sp.csc_matrix((data, indices, indptr), shape=shape)
 
 
 def prepare_global_schur(cells, points, epart, sd: Subdomains, coeff, f_vals, u_dir):

@@ -62,8 +62,42 @@ for rep in range(4):
                 "solve_s": t_solve, "it": int(it), "host_analyses": st["host_analyses"], "device_refactorizations": st["device_refactorizations"],
                 "host_cholesky_all_subdomains_s": t_host_chol})
     print(json.dumps(out[-1]), flush=True)
+# The same loop with the ASSEMBLY on the device as well (kb200_assemble_realization): the host sends one vector, the nodal
+# coefficient; the right-hand sides come from the boundary layer (hostprep.problem.RhsUpdater).  For comparison: the host
+# assembly of all blocks (prepare_local_schurs, numpy-vectorised stand-in of the reference's element loop) that the two
+# loops above need per realization before their update calls -- not counted in their numbers.
+cells, points, epart = base[0], base[1], base[4]
+t0 = time.perf_counter()
+PB.realization(base, ireal=2, factorize=False)
+t_host_asm = time.perf_counter() - t0
+t0 = time.perf_counter()
+S.enable_device_assembly(cells, points, epart, prs[0].blocks.A_II)
+t_enable = time.perf_counter() - t0
+rhs = PB.RhsUpdater(base, prs[0].f_vals, prs[0].u_dir)
+for rep in range(4):
+    pr = prs[(rep + 1) % 2]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    S.assemble_realization(pr.coeff)
+    t_up = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b_I, b_G = rhs(pr.coeff)
+    t_b = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = S.schur_rhs(b_I, b_G)                               # first operation: device Cholesky + refresh
+    t_rhs = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    x, it, res, tm = solvers.pcg(S, b, np.zeros(sd.n_gamma), M, maxit=5000, return_timings=True)
+    t_solve = time.perf_counter() - t0
+    st = S.h.stats()
+    out.append({"rep": rep, "mode": "device_assembly", "assemble_call_s": t_up, "host_rhs_s": t_b,
+                "first_op_incl_cholesky_and_refresh_s": t_rhs, "solve_s": t_solve, "it": int(it),
+                "host_analyses": st["host_analyses"], "device_assemblies": st["device_assemblies"],
+                "bytes_uploaded": 8 * pr.coeff.size, "host_assembly_all_blocks_s": t_host_asm, "enable_once_s": t_enable})
+    print(json.dumps(out[-1]), flush=True)
 nnzL = sum(f[1].nnz for f in prs[0].factors)
 print(json.dumps({"nx": nx, "ndom": ndom, "nnz_L": nnzL, "bytes_uploaded_per_update": 8 * (nnzL + sum(a.nnz for a in prs[0].blocks.A_IG) + sum(a.nnz for a in prs[0].blocks.A_GG)),
                   "value_refs": st["value_refs"], "update_over_solve": out[3]["update_call_s"] / out[3]["solve_s"],
                   "update_plus_refresh_over_solve": (out[3]["update_call_s"] + out[3]["first_op_incl_refresh_s"]) / out[3]["solve_s"],
-                  "device_refactorization_update_plus_first_op_over_solve": (out[-1]["update_call_s"] + out[-1]["first_op_incl_cholesky_and_refresh_s"]) / out[-1]["solve_s"]}), flush=True)
+                  "device_refactorization_update_plus_first_op_over_solve": (out[7]["update_call_s"] + out[7]["first_op_incl_cholesky_and_refresh_s"]) / out[7]["solve_s"],
+                  "device_assembly_all_steps_over_solve": (out[-1]["assemble_call_s"] + out[-1]["host_rhs_s"] + out[-1]["first_op_incl_cholesky_and_refresh_s"]) / out[-1]["solve_s"]}), flush=True)
