@@ -86,6 +86,20 @@ try:
     out["block_api"] = "allowed"
 except Exception as e:
     out["block_api"] = "refused" if "multi-GPU handle" in str(e) else str(e)
+# realization 2 from its nodal coefficient alone (device assembly + numeric Cholesky, every member its own subdomains)
+# against a single-GPU handle fed with the host's blocks and factors of that realization
+pr2 = PB.realization((pr.cells, pr.points, pr.markers, pr.neighbors, pr.epart, pr.npart, sd), ireal=2)
+S.enable_device_assembly(pr.cells, pr.points, pr.epart, lb.A_II)
+S.assemble_realization(pr2.coeff)
+S2 = fem.B200SchurOperator(sd, pr2.blocks, pr2.factors, device=0)
+out["asm_vs_single"] = rel(S * x, S2 * x)
+dl = sd.ndom - 1
+blk = [pr2.blocks.A_II[dl].tocsc(), pr2.blocks.A_IG[dl].tocsc(), pr2.blocks.A_GG[dl].tocsc()]
+for A in blk:
+    A.sort_indices()
+got = S.h.get_local_block_values(dl, *[A.nnz for A in blk])
+out["asm_values"] = max(rel(g, A.data) for g, A in zip(got, blk))
+out["asm_count"] = S.h.stats()["device_assemblies"]
 print("RESULT " + json.dumps(out))
 """
 
@@ -114,6 +128,7 @@ def _check(o, members, full=True):
     assert abs(o["eigpcg_it"][0] - o["eigpcg_it"][1]) <= 1 and o["eigpcg_x"] <= 1e-6 and o["eigpcg_V"][1] == 4
     assert o["dense_sd"] <= 1e-11 and o["assembled_apply"] <= 1e-11
     assert o["block_api"] == "refused"
+    assert o["asm_vs_single"] <= 1e-12 and o["asm_values"] <= 4e-16 and o["asm_count"] == 1.0
     if members > 1:
         assert o["peer"] == 1.0, "the members must exchange through peer memory"
     else:
