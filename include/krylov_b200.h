@@ -153,11 +153,24 @@ int kb200_refactor_interior(kb200_handle h, int64_t d, const double* A_II_nzval)
  *     A_ΓΓ,d go straight to the value pool, A_II,d to the staging area of kb200_refactor_interior (which must have
  *     been prepared with kb200_upload_interior_pattern); the next operation runs the numeric Cholesky and the
  *     stream refresh on the device.  The right-hand sides b_I,d / b_Γ (:499-536) stay with the caller.
- *   kb200_get_local_block_values reads the current values back (any pointer may be null; A_II only once staged). */
+ *   kb200_get_local_block_values reads the current values back (any pointer may be null; A_II only once staged).
+ *   kb200_upload_rhs_map (optional) puts the right-hand sides b_I,d / b_Γ of the same loop (:499-536) on the device too.
+ *     Only the Dirichlet-lift terms (:499-508) depend on the coefficient, and only in the entries of nodes that share
+ *     an element with a Dirichlet node; the caller passes the load vector once (bI0_concat: sum_d n_I,d entries in
+ *     subdomain order, bG0: n_gamma entries; what prepare_local_schurs returns for ANY coefficient is fine, the nt
+ *     entries below are overwritten) and, for each of those nt entries, tgt[t] = its 1-based index in [b_I ; b_Γ]
+ *     and its terms src/val[ptr[t] .. ptr[t+1]-1] (ptr 1-based) in the order the loop nest applies them:
+ *     src > 0: `b -= ΔK_src * val` (val = uexact at the Dirichlet vertex, src the contribution index as above),
+ *     src = 0: `b += val` (val = Δb of :524-526).  After that every kb200_assemble_realization also assembles the
+ *     right-hand sides (bit for bit the reference's), kb200_schur_rhs(h, NULL, NULL, b_schur) and
+ *     kb200_back_substitute(h, u_gamma, NULL, u_I) use them, kb200_get_rhs reads them back. */
 int kb200_upload_assembly_mesh(kb200_handle h, int64_t nnode, int64_t nel, const int64_t* cells, const double* points);
 int kb200_upload_assembly_map(kb200_handle h, int64_t d, int which, int64_t nnz, const int64_t* ptr, const int64_t* src);
 int kb200_assemble_realization(kb200_handle h, const double* coeff);
 int kb200_get_local_block_values(kb200_handle h, int64_t d, double* AII_nzval, double* AIG_nzval, double* AGG_nzval);
+int kb200_upload_rhs_map(kb200_handle h, const double* bI0_concat, const double* bG0, int64_t nt, const int64_t* tgt,
+                         const int64_t* ptr, const int64_t* src, const double* val);
+int kb200_get_rhs(kb200_handle h, double* b_I_concat, double* b_gamma);
 /* ΠSd[d] of NeumannNeumannSchurPreconditioner (:1125), n_gd x n_gd column-major. */
 int kb200_upload_nn_pinv(kb200_handle h, int64_t d, const double* PiS);
 /* Dense local Schur complement S_d (assemble_local_schurs, :667-695), n_gd x n_gd column-major. */
@@ -176,7 +189,8 @@ int kb200_apply_schur_assembled(kb200_handle h, const double* x, double* y, int6
 /* z = M \ r: apply_neumann_neumann_schur / `\` / ldiv! (:1361-1403). */
 int kb200_apply_nn(kb200_handle h, const double* r, double* z, int64_t nrhs);
 /* b_schur = b_Γ - Σ_d R_d' A_ΓI,d A_II,d^{-1} b_I,d : get_schur_rhs (:835-864).
- * b_I_concat = [b_Id[1]; b_Id[2]; ...] (all subdomains, every rank). */
+ * b_I_concat = [b_Id[1]; b_Id[2]; ...] (all subdomains, every rank).  b_I_concat = b_gamma = NULL (here), b_I_concat =
+ * NULL (kb200_back_substitute): the right-hand sides the device assembled (kb200_upload_rhs_map). */
 int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_gamma, double* b_schur);
 /* u_I,d = A_II,d^{-1} (b_I,d - A_IΓ,d u_Γ): get_subdomain_solutions (:1014-1025). */
 int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b_I_concat,

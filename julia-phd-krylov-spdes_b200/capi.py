@@ -29,6 +29,7 @@ SYMBOLS = [
     "kb200_lotrrrpcg", "kb200_lotrrrdefpcg", "kb200_lotrhrpcg", "kb200_lotrhrdefpcg",
     "kb200_upload_interior_pattern", "kb200_refactor_interior",
     "kb200_upload_assembly_mesh", "kb200_upload_assembly_map", "kb200_assemble_realization", "kb200_get_local_block_values",
+    "kb200_upload_rhs_map", "kb200_get_rhs",
 ]
 
 
@@ -233,6 +234,20 @@ class Handle:
                                                 _p(g, C.c_double) if nnz_IG else None, _p(hh, C.c_double) if nnz_GG else None))
         return a, g, hh
 
+    def upload_rhs_map(self, bI0_concat, bG0, tgt, ptr, src, val):
+        """kb200_upload_rhs_map: load vector + the terms of the entries with Dirichlet-lift contributions; `tgt` / `ptr`
+        0-based here, `src` = contribution id (0-based) or -1 for a load term (hostprep.epdd_host.rhs_maps)."""
+        b0, g0 = _f64(bI0_concat), _f64(bG0)
+        tt, pp, ss, vv = _i64(tgt) + 1, _i64(ptr) + 1, _i64(src) + 1, _f64(val)
+        _chk(lib().kb200_upload_rhs_map(self.h, _p(b0, C.c_double), _p(g0, C.c_double), C.c_int64(tt.size),
+                                        _p(tt, C.c_int64), _p(pp, C.c_int64), _p(ss, C.c_int64), _p(vv, C.c_double)))
+
+    def get_rhs(self):
+        """kb200_get_rhs: (b_I concatenated over the subdomains, b_Γ) of the last kb200_assemble_realization."""
+        bI, bG = np.zeros(int(np.sum(self.n_I))), np.zeros(self.n_gamma)
+        _chk(lib().kb200_get_rhs(self.h, _p(bI, C.c_double), _p(bG, C.c_double)))
+        return bI, bG
+
     def update_local_block_values(self, d, A_IG, A_GG):
         g, hh = A_IG.tocsc(), A_GG.tocsc()
         g.sort_indices()
@@ -269,15 +284,23 @@ class Handle:
     def apply_nn(self, r):
         return self._apply(lib().kb200_apply_nn, r)
 
-    def schur_rhs(self, b_I_concat, b_gamma):
-        bi, bg = _f64(b_I_concat), _f64(b_gamma)
+    def schur_rhs(self, b_I_concat=None, b_gamma=None):
+        """kb200_schur_rhs; without arguments: the right-hand sides the device assembled (kb200_upload_rhs_map)."""
         out = np.empty(self.n_gamma)
+        if b_I_concat is None and b_gamma is None:
+            _chk(lib().kb200_schur_rhs(self.h, None, None, _p(out, C.c_double)))
+            return out
+        bi, bg = _f64(b_I_concat), _f64(b_gamma)
         _chk(lib().kb200_schur_rhs(self.h, _p(bi, C.c_double), _p(bg, C.c_double), _p(out, C.c_double)))
         return out
 
-    def back_substitute(self, u_gamma, b_I_concat):
-        ug, bi = _f64(u_gamma), _f64(b_I_concat)
+    def back_substitute(self, u_gamma, b_I_concat=None):
+        ug = _f64(u_gamma)
         out = np.zeros(int(self.n_I.sum()))
+        if b_I_concat is None:
+            _chk(lib().kb200_back_substitute(self.h, _p(ug, C.c_double), None, _p(out, C.c_double)))
+            return out
+        bi = _f64(b_I_concat)
         _chk(lib().kb200_back_substitute(self.h, _p(ug, C.c_double), _p(bi, C.c_double), _p(out, C.c_double)))
         return out
 

@@ -203,6 +203,14 @@ struct kb200_ctx {
   int64_t as_nnode = 0, as_nel = 0, as_nA = 0, as_nP = 0;
   bool as_mesh = false, as_ready = false;
   int64_t assemblies = 0;
+  // right-hand sides on the device (kb200_upload_rhs_map): [b_I of the local subdomains | b_Γ]; static image (load vector),
+  // the entries with Dirichlet-lift terms are recomputed by assemble_rhs_kernel after every kb200_assemble_realization
+  DevBuf<double> d_rhs, d_rhs0, d_rt_val;
+  DevBuf<int64_t> d_rt_ptr;
+  DevBuf<int32_t> d_rt_src;
+  DevBuf<uint32_t> d_rt_dst;
+  int64_t rt_n = 0;
+  bool rhs_map = false, rhs_ready = false;
   DevBuf<kb::DmapRef> d_dmap;
   DevBuf<kb::BlockRef> d_blkref;
   std::vector<int64_t> pool_off;                 // per local subdomain (+1)
@@ -2389,6 +2397,24 @@ int kb200_assemble_realization(kb200_handle h, const double* coeff) {
       kb::assemble_values_kernel<<<(unsigned)((h->as_nP + 255) / 256), 256, 0, s>>>(P);
       h->launches++;
     }
+    if (h->rhs_map) {   // right-hand sides of the same coefficient: static image, then the entries with lift terms
+      CUDA_TRY(cudaMemcpyAsync(h->d_rhs.p, h->d_rhs0.p, h->d_rhs.n * 8, cudaMemcpyDeviceToDevice, s));
+      if (h->rt_n) {
+        kb::RhsParams R;
+        R.cells = h->d_as_cells.p;
+        R.pts = h->d_as_pts.p;
+        R.coeff = h->d_as_coeff.p;
+        R.ptr = h->d_rt_ptr.p;
+        R.src = h->d_rt_src.p;
+        R.val = h->d_rt_val.p;
+        R.dst = h->d_rt_dst.p;
+        R.out = h->d_rhs.p;
+        R.n = h->rt_n;
+        kb::assemble_rhs_kernel<<<(unsigned)((h->rt_n + 127) / 128), 128, 0, s>>>(R);
+        h->launches++;
+      }
+      h->rhs_ready = true;
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s));   // the caller may reuse its buffer
     for (int64_t k = 0; k < nloc; ++k) {
@@ -2400,6 +2426,68 @@ int kb200_assemble_realization(kb200_handle h, const double* coeff) {
     h->fa_dirty = true;
     h->values_dirty = true;
     h->assemblies++;
+  });
+}
+
+int kb200_upload_rhs_map(kb200_handle h, const double* bI0_concat, const double* bG0, int64_t nt, const int64_t* tgt,
+                         const int64_t* ptr, const int64_t* src, const double* val) {
+  KB_GROUP(kb200_upload_rhs_map(h, bI0_concat, bG0, nt, tgt, ptr, src, val));
+  return guarded([&]() {
+    require(h && h->topo && bI0_concat && bG0, "null argument");
+    require(nt >= 0 && (nt == 0 || (tgt && ptr && src && val)), "null argument");
+    require(nt == 0 || ptr[0] == 1, "rhs map: ptr must be 1-based with nt + 1 entries");
+    use_device(h);
+    const int64_t nItot = h->I_base_global[h->ndom], ng = h->n_gamma;
+    const int64_t off = h->I_base_global[h->d0], len = h->I_base_global[h->d1] - off;
+    require(len + ng < (int64_t)0xffffffffLL, "too many right-hand-side entries on one GPU");
+    std::vector<int64_t> lp(1, 0);
+    std::vector<int32_t> ls;
+    std::vector<double> lv;
+    std::vector<uint32_t> ld;
+    for (int64_t t = 0; t < nt; ++t) {
+      require(ptr[t + 1] >= ptr[t], "rhs map: ptr not monotone");
+      const int64_t g = tgt[t] - 1;
+      require(g >= 0 && g < nItot + ng, "rhs map: target out of range (1-based index into [b_I ; b_Γ] expected)");
+      int64_t dst;
+      if (g >= nItot) dst = len + (g - nItot);
+      else if (g >= off && g < off + len) dst = g - off;
+      else continue;   // interior entry of a subdomain that lives on another GPU
+      for (int64_t q = ptr[t] - 1; q < ptr[t + 1] - 1; ++q) {
+        require(src[q] >= 0 && src[q] < (int64_t)0x7fffffff, "rhs map: contribution index out of range");
+        ls.push_back((int32_t)(src[q] - 1));   // 0 = load term -> -1
+        lv.push_back(val[q]);
+      }
+      lp.push_back((int64_t)ls.size());
+      ld.push_back((uint32_t)dst);
+    }
+    std::vector<double> img((size_t)(len + ng));
+    std::copy(bI0_concat + off, bI0_concat + off + len, img.begin());
+    std::copy(bG0, bG0 + ng, img.begin() + len);
+    cudaStream_t s = h->stream;
+    h->d_rhs0.upload(img, s);
+    h->d_rhs.alloc(img.size());
+    h->d_rt_ptr.upload(lp, s);
+    h->d_rt_src.upload(ls, s);
+    h->d_rt_val.upload(lv, s);
+    h->d_rt_dst.upload(ld, s);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->rt_n = (int64_t)ld.size();
+    h->rhs_map = true;
+    h->rhs_ready = false;
+  });
+}
+
+int kb200_get_rhs(kb200_handle h, double* b_I_concat, double* b_gamma) {
+  KB_GROUP(kb200_get_rhs(h, b_I_concat, b_gamma));
+  return guarded([&]() {
+    require(h && h->topo, "null argument");
+    require(h->rhs_ready, "no device right-hand sides: kb200_upload_rhs_map and kb200_assemble_realization come first");
+    use_device(h);
+    const int64_t off = h->I_base_global[h->d0], len = h->I_base_global[h->d1] - off;
+    if (b_I_concat && len)   // own slice
+      CUDA_TRY(cudaMemcpyAsync(b_I_concat + off, h->d_rhs.p, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (b_gamma) d2h(h, b_gamma, h->d_rhs.p + len, h->n_gamma);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
   });
 }
 
@@ -2522,12 +2610,19 @@ int kb200_apply_nn(kb200_handle h, const double* r, double* z, int64_t nrhs) {
 int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_gamma, double* b_schur) {
   KB_GROUP(kb200_schur_rhs(h, b_I_concat, b_gamma, b_schur));
   return guarded([&]() {
-    require(h && b_I_concat && b_gamma && b_schur, "null argument");
+    require(h && b_schur && ((b_I_concat && b_gamma) || (!b_I_concat && !b_gamma)), "null argument");
     finalize(h);
     use_device(h);
     const int64_t n = h->n_gamma;
-    bI_to_device(h, b_I_concat);
-    h2d(h, h->d_b.p, b_gamma, n);
+    if (b_I_concat) {
+      bI_to_device(h, b_I_concat);
+      h2d(h, h->d_b.p, b_gamma, n);
+    } else {   // the right-hand sides the device assembled for the last kb200_assemble_realization
+      require(h->rhs_ready, "no device right-hand sides: kb200_upload_rhs_map and kb200_assemble_realization come first");
+      const int64_t len = h->I_base_global[h->d1] - h->I_base_global[h->d0];
+      if (len) CUDA_TRY(cudaMemcpyAsync(h->d_bI.p, h->d_rhs.p, (size_t)len * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(h->d_b.p, h->d_rhs.p + len, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
     launch_stream<kb::MODE_RHS>(h, nullptr, h->d_bI.p, nullptr, h->d_loc.p, nullptr, 0);
     assemble(h, h->d_loc.p, h->d_b.p, h->d_Ap.p, nullptr, nullptr, nullptr, 0);
     d2h(h, b_schur, h->d_Ap.p, n);
@@ -2538,10 +2633,16 @@ int kb200_schur_rhs(kb200_handle h, const double* b_I_concat, const double* b_ga
 int kb200_back_substitute(kb200_handle h, const double* u_gamma, const double* b_I_concat, double* u_I_concat) {
   KB_GROUP(kb200_back_substitute(h, u_gamma, b_I_concat, u_I_concat));
   return guarded([&]() {
-    require(h && u_gamma && b_I_concat && u_I_concat, "null argument");
+    require(h && u_gamma && u_I_concat, "null argument");
     finalize(h);
     use_device(h);
-    bI_to_device(h, b_I_concat);
+    if (b_I_concat) {
+      bI_to_device(h, b_I_concat);
+    } else {   // b_I of the last kb200_assemble_realization, on the device
+      require(h->rhs_ready, "no device right-hand sides: kb200_upload_rhs_map and kb200_assemble_realization come first");
+      const int64_t len = h->I_base_global[h->d1] - h->I_base_global[h->d0];
+      if (len) CUDA_TRY(cudaMemcpyAsync(h->d_bI.p, h->d_rhs.p, (size_t)len * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
     h2d(h, h->d_x.p, u_gamma, h->n_gamma);
     launch_stream<kb::MODE_BACKSUB>(h, h->d_x.p, h->d_bI.p, h->d_uI.p, nullptr, nullptr, 0);
     const int64_t off = h->I_base_global[h->d0], len = h->I_base_global[h->d1] - off;

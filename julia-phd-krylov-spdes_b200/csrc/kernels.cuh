@@ -723,34 +723,64 @@ struct AsmParams {
   int64_t n;
 };
 __device__ __forceinline__ double pick3(int k, double a0, double a1, double a2) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
+// ΔK_ij of contribution c = 9 e + 3 i + j (:437-470), every operation rounded on its own
+__device__ __forceinline__ double element_stiffness(const int32_t* __restrict__ cells, const double* __restrict__ pts,
+                                                    const double* __restrict__ coeff, int32_t c) {
+  const int32_t e = c / 9, ij = c - 9 * e, i = ij / 3, j = ij - 3 * i;
+  const int32_t n0 = cells[3 * (int64_t)e], n1 = cells[3 * (int64_t)e + 1], n2 = cells[3 * (int64_t)e + 2];
+  const double x0 = pts[2 * (int64_t)n0], y0 = pts[2 * (int64_t)n0 + 1];
+  const double x1 = pts[2 * (int64_t)n1], y1 = pts[2 * (int64_t)n1 + 1];
+  const double x2 = pts[2 * (int64_t)n2], y2 = pts[2 * (int64_t)n2 + 1];
+  // :437-446   Δa = 0.; Δa += coeff[jnode] (three times); Δa /= 3.
+  double da = __dadd_rn(__dadd_rn(__dadd_rn(0.0, coeff[n0]), coeff[n1]), coeff[n2]);
+  da = __ddiv_rn(da, 3.0);
+  // :449-454   (1-based Δx[1..3], Δy[1..3] of the reference = dx0..2, dy0..2)
+  const double dx0 = __dsub_rn(x2, x1), dx1 = __dsub_rn(x0, x2), dx2 = __dsub_rn(x1, x0);
+  const double dy0 = __dsub_rn(y1, y2), dy1 = __dsub_rn(y2, y0), dy2 = __dsub_rn(y0, y1);
+  // :457       Area = (Δx[3] * Δy[2] - Δx[2] * Δy[3]) / 2.
+  const double area = __ddiv_rn(__dsub_rn(__dmul_rn(dx2, dy1), __dmul_rn(dx1, dy2)), 2.0);
+  // :470       ΔKij = Δa * (Δy[i] * Δy[j] + Δx[i] * Δx[j]) / 4 / Area
+  const double dyi = pick3(i, dy0, dy1, dy2), dyj = pick3(j, dy0, dy1, dy2);
+  const double dxi = pick3(i, dx0, dx1, dx2), dxj = pick3(j, dx0, dx1, dx2);
+  const double g = __dadd_rn(__dmul_rn(dyi, dyj), __dmul_rn(dxi, dxj));
+  return __ddiv_rn(__ddiv_rn(__dmul_rn(da, g), 4.0), area);
+}
 __global__ void __launch_bounds__(256) assemble_values_kernel(const AsmParams P) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P.n) return;
   double acc = 0.0;
   const int64_t q0 = P.ptr[s], q1 = P.ptr[s + 1];
   for (int64_t q = q0; q < q1; ++q) {
-    const int32_t c = P.src[q];
-    const int32_t e = c / 9, ij = c - 9 * e, i = ij / 3, j = ij - 3 * i;
-    const int32_t n0 = P.cells[3 * (int64_t)e], n1 = P.cells[3 * (int64_t)e + 1], n2 = P.cells[3 * (int64_t)e + 2];
-    const double x0 = P.pts[2 * (int64_t)n0], y0 = P.pts[2 * (int64_t)n0 + 1];
-    const double x1 = P.pts[2 * (int64_t)n1], y1 = P.pts[2 * (int64_t)n1 + 1];
-    const double x2 = P.pts[2 * (int64_t)n2], y2 = P.pts[2 * (int64_t)n2 + 1];
-    // :437-446   Δa = 0.; Δa += coeff[jnode] (three times); Δa /= 3.
-    double da = __dadd_rn(__dadd_rn(__dadd_rn(0.0, P.coeff[n0]), P.coeff[n1]), P.coeff[n2]);
-    da = __ddiv_rn(da, 3.0);
-    // :449-454   (1-based Δx[1..3], Δy[1..3] of the reference = dx0..2, dy0..2)
-    const double dx0 = __dsub_rn(x2, x1), dx1 = __dsub_rn(x0, x2), dx2 = __dsub_rn(x1, x0);
-    const double dy0 = __dsub_rn(y1, y2), dy1 = __dsub_rn(y2, y0), dy2 = __dsub_rn(y0, y1);
-    // :457       Area = (Δx[3] * Δy[2] - Δx[2] * Δy[3]) / 2.
-    const double area = __ddiv_rn(__dsub_rn(__dmul_rn(dx2, dy1), __dmul_rn(dx1, dy2)), 2.0);
-    // :470       ΔKij = Δa * (Δy[i] * Δy[j] + Δx[i] * Δx[j]) / 4 / Area
-    const double dyi = pick3(i, dy0, dy1, dy2), dyj = pick3(j, dy0, dy1, dy2);
-    const double dxi = pick3(i, dx0, dx1, dx2), dxj = pick3(j, dx0, dx1, dx2);
-    const double g = __dadd_rn(__dmul_rn(dyi, dyj), __dmul_rn(dxi, dxj));
-    const double k = __ddiv_rn(__ddiv_rn(__dmul_rn(da, g), 4.0), area);
+    const double k = element_stiffness(P.cells, P.pts, P.coeff, P.src[q]);
     acc = q == q0 ? k : __dadd_rn(acc, k);
   }
   P.out[P.dst ? P.dst[s] : s] = acc;
+}
+// Right-hand sides b_I,d / b_Γ of the same loop (:499-536) for the entries that carry Dirichlet-lift terms (the nodes next
+// to the boundary; every other entry is the coefficient-independent load vector, copied from a static image first).
+// One thread per entry; its terms in the reference's order: src >= 0: `b -= ΔK_c * uexact` (:502 / :506, val = uexact at
+// the Dirichlet vertex), src < 0: `b += Δb` (:529 / :533, val = Δb of :524-526).
+struct RhsParams {
+  const int32_t* cells;
+  const double* pts;
+  const double* coeff;
+  const int64_t* ptr;     // per entry: its terms [ptr[t], ptr[t + 1])
+  const int32_t* src;
+  const double* val;
+  const uint32_t* dst;    // per entry: index in `out`
+  double* out;
+  int64_t n;
+};
+__global__ void __launch_bounds__(128) assemble_rhs_kernel(const RhsParams P) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.n) return;
+  double acc = 0.0;
+  for (int64_t q = P.ptr[t]; q < P.ptr[t + 1]; ++q) {
+    const int32_t c = P.src[q];
+    if (c < 0) acc = __dadd_rn(acc, P.val[q]);
+    else acc = __dsub_rn(acc, __dmul_rn(element_stiffness(P.cells, P.pts, P.coeff, c), P.val[q]));
+  }
+  P.out[P.dst[t]] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -79,6 +79,14 @@ class B200SchurOperator:
             for which in range(3):
                 self.h.upload_assembly_map(d, which, maps.ptr[d][which], maps.src[d][which])
 
+    def enable_device_rhs(self, cells, points, epart, f_vals, u_dir):
+        """Right-hand sides on the device as well (kb200_upload_rhs_map): after this ``assemble_realization`` also assembles
+        b_I,d / b_Γ (:499-536), and ``schur_rhs()`` / ``subdomain_solutions(u_gamma)`` without right-hand-side arguments use
+        them."""
+        from .hostprep import epdd_host
+        m = epdd_host.rhs_maps(cells, points, epart, self.sd, f_vals, u_dir)
+        self.h.upload_rhs_map(m.bI0, m.bG0, m.tgt, m.ptr, m.src, m.val)
+
     def assemble_realization(self, coeff):
         """New coefficient realization from the nodal coefficient alone (kb200_assemble_realization)."""
         self.h.assemble_realization(coeff)
@@ -99,13 +107,15 @@ class B200SchurOperator:
         return y
 
     # get_schur_rhs / get_subdomain_solutions (EllipticPdeDomainDecomposition.jl:835-864, 1014-1025)
-    def schur_rhs(self, b_I, b_gamma):
+    def schur_rhs(self, b_I=None, b_gamma=None):
+        if b_I is None and b_gamma is None:            # the right-hand sides of the last assemble_realization (device)
+            return self.h.schur_rhs()
         return self.h.schur_rhs(np.concatenate(b_I) if len(b_I) else np.zeros(0), b_gamma)
 
-    def subdomain_solutions(self, u_gamma, b_I):
-        u = self.h.back_substitute(u_gamma, np.concatenate(b_I))
-        ptr = np.concatenate([[0], np.cumsum([v.size for v in b_I])])
-        return [u[ptr[d]:ptr[d + 1]] for d in range(len(b_I))]
+    def subdomain_solutions(self, u_gamma, b_I=None):
+        u = self.h.back_substitute(u_gamma, None if b_I is None else np.concatenate(b_I))
+        ptr = np.concatenate([[0], np.cumsum([v.size for v in self.sd.node_Id])])
+        return [u[ptr[d]:ptr[d + 1]] for d in range(self.sd.ndom)]
 
     # assemble_local_schurs (:667-695): dense S_d computed on the device
     def assemble_local_schurs(self):

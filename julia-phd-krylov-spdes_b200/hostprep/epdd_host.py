@@ -322,6 +322,89 @@ def assemble_values_from_map(cells, points, coeff, ptr, src):
     return acc
 
 
+@dataclass
+class RhsMaps:
+    """Arguments of kb200_upload_rhs_map (0-based here): the load vector (bI0 concatenated over the subdomains, bG0) and,
+    for the entries that carry Dirichlet-lift terms (:499-508), their index `tgt` in [b_I ; b_Γ] and their terms
+    src/val[ptr[t]:ptr[t+1]] in the order of the reference's loop nest -- src >= 0: `b -= ΔK_src * val` (val = uexact at
+    the Dirichlet vertex), src = -1: `b += val` (val = Δb of :524-526)."""
+    bI0: np.ndarray
+    bG0: np.ndarray
+    tgt: np.ndarray
+    ptr: np.ndarray
+    src: np.ndarray
+    val: np.ndarray
+
+
+def rhs_maps(cells, points, epart, sd: Subdomains, f_vals, u_dir) -> RhsMaps:
+    """Right-hand-side part of prepare_local_schurs (:499-536) in gather form.  Only entries of nodes that share an
+    element with a Dirichlet node depend on the coefficient; everything else is the load vector."""
+    nnode, owner = sd.nnode, sd.node_owner
+    is_dir = owner == 0
+    el_dir = is_dir[cells].any(axis=0)
+    tnode = np.zeros(nnode, dtype=bool)
+    tnode[cells[:, el_dir].ravel()] = True
+    tnode &= ~is_dir
+    layer = np.flatnonzero(tnode[cells].any(axis=0))          # every element of such a node, ascending
+    static = prepare_local_schurs(cells, points, epart, sd, np.ones(nnode), f_vals, u_dir)
+    bI0 = np.concatenate(static.b_I) if sd.ndom else np.zeros(0)
+    n_Id = np.array([v.size for v in sd.node_Id])
+    iptr = np.concatenate([[0], np.cumsum(n_Id)])
+    cat_I = np.full(nnode, -1, dtype=np.int64)
+    for d in range(sd.ndom):
+        cat_I[sd.node_Id[d]] = iptr[d] + np.arange(n_Id[d])
+    tidx = np.where(owner == -1, iptr[-1] + sd.ind_gamma_g2l, np.where(owner > 0, cat_I, -1))
+    en = cells[:, layer]                                       # (3, m)
+    oi = owner[en]
+    m = layer.size
+    ii = np.arange(3)[:, None, None]
+    jj = np.arange(3)[None, :, None]
+    lift = (oi[:, None, :] == 0) & (oi[None, :, :] != 0) & tnode[en][None, :, :]          # (i, j, e): :499
+    shape = (3, 3, m)
+    l_tgt = np.broadcast_to(tidx[en][None, :, :], shape)[lift]
+    l_src = np.broadcast_to(9 * layer[None, None, :] + 3 * ii + jj, shape)[lift]
+    l_val = np.broadcast_to(u_dir[en][:, None, :], shape)[lift]
+    l_seq = np.broadcast_to(12 * layer[None, None, :] + 3 * ii + jj, shape)[lift]
+    _, area = _element_geometry(en, points, np.ones(nnode))
+    fi = f_vals[en]
+    db = (2 * fi + fi[[1, 2, 0]] + fi[[2, 0, 1]]) * area[None, :] / 12                   # :524-526
+    load = (oi != 0) & tnode[en]
+    d_tgt = tidx[en][load]
+    d_val = db[load]
+    d_seq = np.broadcast_to(12 * layer[None, :] + 9 + np.arange(3)[:, None], (3, m))[load]
+    tg = np.concatenate([l_tgt, d_tgt])
+    sr = np.concatenate([l_src, np.full(d_tgt.size, -1, dtype=np.int64)])
+    vl = np.concatenate([l_val, d_val])
+    sq = np.concatenate([l_seq, d_seq])
+    o = np.lexsort((sq, tg))
+    tg, sr, vl = tg[o], sr[o], vl[o]
+    new = np.ones(tg.size, dtype=bool)
+    new[1:] = tg[1:] != tg[:-1]
+    start = np.flatnonzero(new)
+    return RhsMaps(bI0, static.b_G, tg[start].astype(np.int64), np.concatenate([start, [tg.size]]).astype(np.int64),
+                   sr.astype(np.int64), vl.astype(np.float64))
+
+
+def assemble_rhs_from_map(cells, points, coeff, m: RhsMaps):
+    """What kb200_assemble_realization computes for the right-hand sides, on the host (numpy): the load vector with the
+    entries of `m.tgt` recomputed term by term in order.  Test twin of kernels.cuh::assemble_rhs_kernel."""
+    out = np.concatenate([m.bI0, m.bG0])
+    lift = m.src >= 0
+    term = m.val.copy()
+    if lift.any():
+        c = m.src[lift]
+        ue, inv = np.unique(c // 9, return_inverse=True)
+        K, _ = _element_geometry(cells[:, ue], points, coeff)
+        term[lift] = -(K[(c % 9) // 3, c % 3, inv] * m.val[lift])
+    cnt = np.diff(m.ptr)
+    acc = np.zeros(m.tgt.size)
+    for r in range(int(cnt.max()) if cnt.size else 0):
+        mk = cnt > r
+        acc[mk] = acc[mk] + term[m.ptr[:-1][mk] + r]
+    out[m.tgt] = acc
+    return out[:m.bI0.size], out[m.bI0.size:]
+
+
 def restriction(sd: Subdomains, d):
     """R_d: n_Γd x n_Γ boolean gather matrix (the Dict loops at :728-730)."""
     g = sd.gamma_l2g[d]

@@ -335,6 +335,66 @@ function enable_device_assembly!(S::B200SchurOperator, cells::Array{Int,2}, poin
   end
   return S
 end
+"""
+    enable_device_rhs!(S, cells, points, epart, node_owner, ind_Id_g2l, ind_Γ_g2l, b_Id, b_Γ, f, uexact)
+
+Right-hand sides of prepare_local_schurs (:499-536) on the GPU as well: `b_Id`, `b_Γ` as returned for ANY coefficient give
+the load vector; the entries of nodes that share an element with a Dirichlet node are re-assembled per realization from
+their ordered terms (`b -= ΔKij * uexact(...)` at :502/:506, `b += Δb` at :529/:533).  Afterwards
+`get_schur_rhs(S)` and `get_subdomain_solutions(S, u_Γ)` need no right-hand-side arguments.
+"""
+function enable_device_rhs!(S::B200SchurOperator, cells::Array{Int,2}, points::Array{Float64,2}, epart::Array{Int,1},
+                            node_owner::Array{Int,1}, ind_Id_g2l::Vector{Dict{Int,Int}}, ind_Γ_g2l::Dict{Int,Int},
+                            b_Id::Vector{Vector{Float64}}, b_Γ::Vector{Float64}, f::Function, uexact::Function)
+  nel = size(cells, 2)
+  off = cumsum(vcat(0, S.n_I)); nItot = off[end]
+  index(idom, node) = node_owner[node] == -1 ? nItot + ind_Γ_g2l[node] : off[idom] + ind_Id_g2l[idom][node]
+  terms = Dict{Int,Vector{Tuple{Int64,Float64}}}()              # target index => ordered (src, val)
+  touched = falses(length(node_owner))                          # nodes with a lift term
+  for iel in 1:nel, inode in cells[:, iel]
+    node_owner[inode] == 0 && (touched[cells[:, iel]] .= true)
+  end
+  for iel in 1:nel                                              # the traversal of :430-536
+    nodes = cells[:, iel]
+    any(touched[nodes]) || continue
+    idom = epart[iel]
+    x = points[1, nodes]; y = points[2, nodes]
+    for (i, inode) in enumerate(nodes), (j, jnode) in enumerate(nodes)
+      (node_owner[inode] == 0 && node_owner[jnode] != 0 && touched[jnode]) || continue
+      push!(get!(terms, index(idom, jnode), Tuple{Int64,Float64}[]), (9 * (iel - 1) + 3 * (i - 1) + j, uexact(x[i], y[i])))
+    end
+    Δx = (x[3] - x[2], x[1] - x[3], x[2] - x[1]); Δy = (y[2] - y[3], y[3] - y[1], y[1] - y[2])
+    Area = (Δx[3] * Δy[2] - Δx[2] * Δy[3]) / 2.
+    for (i, inode) in enumerate(nodes)
+      (node_owner[inode] != 0 && touched[inode]) || continue
+      j = i % 3 + 1; k = (i + 1) % 3 + 1
+      Δb = (2 * f(x[i], y[i]) + f(x[j], y[j]) + f(x[k], y[k])) * Area / 12
+      push!(get!(terms, index(idom, inode), Tuple{Int64,Float64}[]), (0, Δb))
+    end
+  end
+  tgt = sort(collect(keys(terms)))
+  ptr = Int64[1]; src = Int64[]; val = Float64[]
+  for t in tgt
+    for (s, v) in terms[t]; push!(src, s); push!(val, v); end
+    push!(ptr, length(src) + 1)
+  end
+  chk(ccall((:kb200_upload_rhs_map, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+            S.h, vcat(b_Id...), b_Γ, length(tgt), Vector{Int64}(tgt), ptr, src, val))
+  return S
+end
+# get_schur_rhs / get_subdomain_solutions on the right-hand sides the device assembled
+function get_schur_rhs(S::B200SchurOperator)
+  out = Vector{Float64}(undef, S.N)
+  chk(ccall((:kb200_schur_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), S.h, C_NULL, C_NULL, out))
+  return out
+end
+function get_subdomain_solutions(S::B200SchurOperator, u_Γ::Vector{Float64})
+  u = Vector{Float64}(undef, sum(S.n_I))
+  chk(ccall((:kb200_back_substitute, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), S.h, u_Γ, C_NULL, u))
+  off = cumsum(vcat(0, S.n_I))
+  return [u[off[d]+1:off[d+1]] for d in 1:length(S.n_I)]
+end
 function assemble_realization!(S::B200SchurOperator, coeff::Vector{Float64})
   chk(ccall((:kb200_assemble_realization, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), S.h, coeff))
   S.assembled = false
@@ -419,6 +479,6 @@ end
 \(M::B200Lorasc, x::Vector{Float64}) = ldiv!(similar(x), M, x)
 ldiv!(M::B200Lorasc, x::Vector{Float64}) = (x .= M \ copy(x))
 
-export defpcg, eigpcg, eigdefpcg, update_realization!, enable_device_refactorization!, refactor_realization!, enable_device_assembly!, assemble_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
+export defpcg, eigpcg, eigdefpcg, update_realization!, enable_device_refactorization!, refactor_realization!, enable_device_assembly!, enable_device_rhs!, assemble_realization!, rrpcg, rrdefpcg, hrpcg, hrdefpcg, trrrpcg, trrrdefpcg, trhrpcg, trhrdefpcg, lotrrrpcg, lotrrrdefpcg, lotrhrpcg, lotrhrdefpcg, B200Lorasc
 
 end # module

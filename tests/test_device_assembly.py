@@ -76,6 +76,28 @@ def test_right_hand_sides_of_a_new_coefficient_from_the_boundary_layer(nx, ndom)
     assert all(np.array_equal(a, b) for a, b in zip(b_I, pr.blocks.b_I))
 
 
+@pytest.mark.parametrize("nx,ndom,jitter", [(17, 4, 0.0), (25, 5, 0.2)])
+def test_rhs_maps_reproduce_the_literal_transcription_bit_for_bit(nx, ndom, jitter):
+    """Right-hand sides in gather form (kb200_upload_rhs_map): load vector + ordered terms of the boundary-layer entries,
+    with a non-constant f and uexact so that every term is distinguishable."""
+    cells, pts, epart, sd = _case(nx, ndom, jitter)
+    rng = np.random.default_rng(7)
+    coeff = np.exp(M.lognormal_field(pts, 3))
+    f = -1.0 + 0.1 * rng.standard_normal(pts.shape[1])
+    u = 0.734 + 0.1 * rng.standard_normal(pts.shape[1])
+    ref = E.prepare_local_schurs_ref(cells, pts, epart, sd, coeff, f, u)
+    m = H.rhs_maps(cells, pts, epart, sd, f, u)
+    assert np.all(np.diff(m.tgt) > 0) and m.ptr[0] == 0 and m.ptr[-1] == m.src.size and np.all(np.diff(m.ptr) >= 1)
+    assert m.tgt.size < 0.7 * (m.bI0.size + m.bG0.size)
+    bI, bG = H.assemble_rhs_from_map(cells, pts, coeff, m)
+    assert np.array_equal(bI, np.concatenate(ref.b_I)) and np.array_equal(bG, ref.b_G)
+    # another coefficient through the same maps
+    coeff2 = np.exp(M.lognormal_field(pts, 4))
+    ref2 = E.prepare_local_schurs_ref(cells, pts, epart, sd, coeff2, f, u)
+    bI2, bG2 = H.assemble_rhs_from_map(cells, pts, coeff2, m)
+    assert np.array_equal(bI2, np.concatenate(ref2.b_I)) and np.array_equal(bG2, ref2.b_G)
+
+
 def rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
@@ -121,3 +143,14 @@ def test_device_assembly_of_a_new_realization(nx, ndom, csize):
     # back to realization 1 from its coefficient alone: the operator of the first stream, to rounding
     S.assemble_realization(pr1.coeff)
     assert rel(S * x, y1) <= 1e-12 and S.h.stats()["device_assemblies"] == 2
+    # right-hand sides on the device as well: bit for bit the host's, and the same b_schur / back-substitution
+    with pytest.raises(Exception):
+        S.schur_rhs()                                         # no map yet
+    S.enable_device_rhs(cells, points, epart, pr1.f_vals, pr1.u_dir)
+    for pr in (pr2, pr1):
+        S.assemble_realization(pr.coeff)
+        bI, bG = S.h.get_rhs()
+        assert np.array_equal(bI, np.concatenate(pr.blocks.b_I)) and np.array_equal(bG, pr.blocks.b_G)
+        assert np.array_equal(S.schur_rhs(), S.schur_rhs(pr.blocks.b_I, pr.blocks.b_G))
+        ua, ub = S.subdomain_solutions(x), S.subdomain_solutions(x, pr.blocks.b_I)
+        assert all(np.array_equal(a, b) for a, b in zip(ua, ub))

@@ -100,6 +100,12 @@ for A in blk:
 got = S.h.get_local_block_values(dl, *[A.nnz for A in blk])
 out["asm_values"] = max(rel(g, A.data) for g, A in zip(got, blk))
 out["asm_count"] = S.h.stats()["device_assemblies"]
+# ... and the right-hand sides of that realization (every member its own slice of b_I, the first one b_Γ)
+S.enable_device_rhs(pr.cells, pr.points, pr.epart, pr.f_vals, pr.u_dir)
+S.assemble_realization(pr2.coeff)
+bI, bG = S.h.get_rhs()
+out["rhs_dev_bits"] = bool(np.array_equal(bI, np.concatenate(pr2.blocks.b_I)) and np.array_equal(bG, pr2.blocks.b_G))
+out["rhs_dev_schur"] = rel(S.schur_rhs(), S2.schur_rhs(pr2.blocks.b_I, pr2.blocks.b_G))
 print("RESULT " + json.dumps(out))
 """
 
@@ -129,6 +135,7 @@ def _check(o, members, full=True):
     assert o["dense_sd"] <= 1e-11 and o["assembled_apply"] <= 1e-11
     assert o["block_api"] == "refused"
     assert o["asm_vs_single"] <= 1e-12 and o["asm_values"] <= 4e-16 and o["asm_count"] == 1.0
+    assert o["rhs_dev_bits"] and o["rhs_dev_schur"] <= 1e-12
     if members > 1:
         assert o["peer"] == 1.0, "the members must exchange through peer memory"
     else:
