@@ -8,14 +8,20 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libkb_oracle.so")
+# KB_ORACLE_VARIANT=fma: the same source compiled with fused multiply-adds (products enter the sums unrounded, as on the
+# GPU); KB_ORACLE_VARIANT=ldot: the inner products of PCG accumulated in extended precision; KB_ORACLE_VARIANT=tdot: in plain doubles but
+# summed as a tree (the shape of the GPU's block partials) -- further CPU arithmetics
+# for the rounding-floor probes of DESIGN.md section 2; the default build has neither.
+_VARIANT = os.environ.get("KB_ORACLE_VARIANT", "")
+_SO = os.path.join(_HERE, "libkb_oracle" + ("_" + _VARIANT if _VARIANT else "") + ".so")
+_FLAGS = {"": [], "fma": ["-mfma", "-ffp-contract=fast"], "ldot": ["-DKO_LONG_DOT"], "tdot": ["-DKO_TREE_DOT"]}[_VARIANT]
 _lib = None
 
 
 def build(force=False):
     src = os.path.join(_HERE, "kb_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", src, "-o", _SO, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared"] + _FLAGS + [src, "-o", _SO, "-lm"])
     return _SO
 
 

@@ -278,10 +278,38 @@ void ko_schur_rhs(ko_model *m, const double *bI_cat, const int64_t *bI_off, cons
   }
 }
 
+/* KO_LONG_DOT (cpu_model.py, KB_ORACLE_VARIANT=ldot): the three inner products of an iteration accumulated in 80-bit
+ * extended precision -- a rounding-floor probe (how far does the stopping index move when ONLY the PCG scalars are more
+ * accurate, as the tree-shaped block sums of the GPU make them), never the default build. */
 static double dot(const double *a, const double *b, int32_t n) {
+#ifdef KO_LONG_DOT
+  long double s = 0.0L;
+  for (int32_t i = 0; i < n; ++i) s += (long double)a[i] * (long double)b[i];
+  return (double)s;
+#elif defined(KO_TREE_DOT)
+  /* KB_ORACLE_VARIANT=tdot: plain doubles, summed as a tree (blocks of 256 entries: 32 strided lane sums combined by a
+   * butterfly, then the block sums pairwise) -- the SHAPE of the GPU's block partials, not their exact order */
+  const int32_t nb = (n + 255) / 256;
+  double *part = (double *)malloc(8 * (size_t)(nb > 0 ? nb : 1));
+  for (int32_t blk = 0; blk < nb; ++blk) {
+    double lane[32];
+    for (int l = 0; l < 32; ++l) lane[l] = 0.0;
+    const int32_t i1 = (blk + 1) * 256 < n ? (blk + 1) * 256 : n;
+    for (int32_t i = blk * 256; i < i1; ++i) lane[i & 31] += a[i] * b[i];
+    for (int o = 16; o > 0; o >>= 1)
+      for (int l = 0; l < o; ++l) lane[l] += lane[l + o];
+    part[blk] = lane[0];
+  }
+  for (int32_t w = 1; w < nb; w <<= 1)
+    for (int32_t k = 0; k + w < nb; k += 2 * w) part[k] += part[k + w];
+  const double s = nb > 0 ? part[0] : 0.0;
+  free(part);
+  return s;
+#else
   double s = 0.0;
   for (int32_t i = 0; i < n; ++i) s += a[i] * b[i];
   return s;
+#endif
 }
 
 /* cg.jl:67-109.  res_norm must hold maxit + 1 entries.  Returns it (= iterations + 1). */

@@ -1,6 +1,7 @@
 """pcg / defpcg / eigpcg / eigdefpcg restatements (cg.jl:67-109, defcg.jl:242-308, 337-473,
 eigcg.jl:143-267) on small SPD systems."""
 import numpy as np
+import pytest
 
 import oracle.solvers as OS
 
@@ -57,3 +58,33 @@ def test_eigpcg_recovers_least_dominant_eigenvectors_and_eigdefpcg_uses_them():
     assert it_def < it_plain
     assert np.linalg.norm(A @ x2 - b2) <= 5e-7 * np.linalg.norm(b2)
     assert V2.shape == (n, nvec)
+
+
+@pytest.mark.parametrize("variant", ["fma", "ldot", "tdot"])
+def test_cpu_port_arithmetic_variants_agree_on_a_small_solve(variant):
+    """The builds of oracle/kb_oracle.c used for the rounding-floor probes of DESIGN.md section 2 (fused multiply-adds,
+    extended-precision / tree-shaped inner products) are the same algorithm: same stopping index and solution as the
+    default build where the recurrence is short enough for rounding not to matter."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from conftest import get_problem, get_oracle_ops\n"
+        "from oracle.cpu_model import CpuModel\n"
+        "pr = get_problem(33, 4); inner, Sd, Pi, bs = get_oracle_ops(pr)\n"
+        "cm = CpuModel(pr.sd, pr.blocks, pr.factors, Pi)\n"
+        "x, it, res = cm.pcg(bs, np.zeros(pr.sd.n_gamma))\n"
+        "print('RESULT ' + json.dumps({'it': int(it), 'x': x.tolist()}))\n") % (root, os.path.join(root, "tests"))
+    outs = []
+    for v in ("", variant):
+        env = dict(os.environ, KB_ORACLE_VARIANT=v)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:]))
+    assert abs(outs[0]["it"] - outs[1]["it"]) <= 1
+    a, b = np.array(outs[0]["x"]), np.array(outs[1]["x"])
+    assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(a)
