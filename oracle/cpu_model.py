@@ -8,27 +8,36 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# KB_ORACLE_VARIANT=fma: the same source compiled with fused multiply-adds (products enter the sums unrounded, as on the
-# GPU); KB_ORACLE_VARIANT=ldot: the inner products of PCG accumulated in extended precision; KB_ORACLE_VARIANT=tdot: in plain doubles but
-# summed as a tree (the shape of the GPU's block partials) -- further CPU arithmetics
-# for the rounding-floor probes of DESIGN.md section 2; the default build has neither.
+# Arithmetic variants of the same source (rounding-floor probes of DESIGN.md section 2; the default build has none):
+#   fma   fused multiply-adds everywhere (products enter the sums unrounded, as on the GPU)
+#   ldot  the three inner products of a PCG iteration accumulated in extended precision
+#   tdot  ... in plain doubles, but summed as a tree (the shape of the GPU's block partials)
+# KB_ORACLE_VARIANT selects the variant every call uses; CpuModel.pcg(variant=...) runs one solve with another variant
+# on the same model (the variants share every data structure).
+_FLAGS = {"": [], "fma": ["-mfma", "-ffp-contract=fast"], "ldot": ["-DKO_LONG_DOT"], "tdot": ["-DKO_TREE_DOT"]}
 _VARIANT = os.environ.get("KB_ORACLE_VARIANT", "")
-_SO = os.path.join(_HERE, "libkb_oracle" + ("_" + _VARIANT if _VARIANT else "") + ".so")
-_FLAGS = {"": [], "fma": ["-mfma", "-ffp-contract=fast"], "ldot": ["-DKO_LONG_DOT"], "tdot": ["-DKO_TREE_DOT"]}[_VARIANT]
-_lib = None
+_libs = {}
 
 
-def build(force=False):
-    src = os.path.join(_HERE, "kb_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared"] + _FLAGS + [src, "-o", _SO, "-lm"])
-    return _SO
+def _so(variant):
+    return os.path.join(_HERE, "libkb_oracle" + ("_" + variant if variant else "") + ".so")
 
 
-def _L():
-    global _lib
-    if _lib is None:
-        lib = C.CDLL(build())
+_SO = _so(_VARIANT)
+
+
+def build(force=False, variant=None):
+    variant = _VARIANT if variant is None else variant
+    src, so = os.path.join(_HERE, "kb_oracle.c"), _so(variant)
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared"] + _FLAGS[variant] + [src, "-o", so, "-lm"])
+    return so
+
+
+def _L(variant=None):
+    variant = _VARIANT if variant is None else variant
+    if variant not in _libs:
+        lib = C.CDLL(build(variant=variant))
         lib.ko_new.restype = C.c_void_p
         lib.ko_new.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
         lib.ko_set_dom.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 12
@@ -42,8 +51,8 @@ def _L():
         lib.ko_schur_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ko_pcg.restype = C.c_int32
         lib.ko_pcg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int, C.c_int]
-        _lib = lib
-    return _lib
+        _libs[variant] = lib
+    return _libs[variant]
 
 
 def _i32(a):
@@ -109,11 +118,11 @@ class CpuModel:
         _L().ko_apply_nn(self.m, r.ctypes.data, z.ctypes.data, nthreads)
         return z
 
-    def pcg(self, b, x, maxit=0, eps=1e-7, nthreads=1, precond=True):
+    def pcg(self, b, x, maxit=0, eps=1e-7, nthreads=1, precond=True, variant=None):
         b = _f64(b); x = _f64(x).copy()
         cap = (maxit if maxit else self.n) + 1
         res = np.empty(cap)
-        it = _L().ko_pcg(self.m, b.ctypes.data, x.ctypes.data, maxit, eps, res.ctypes.data, nthreads, int(precond))
+        it = _L(variant).ko_pcg(self.m, b.ctypes.data, x.ctypes.data, maxit, eps, res.ctypes.data, nthreads, int(precond))
         return x, it, res[:it].copy()
 
     def __del__(self):

@@ -25,3 +25,6 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    fs = d["full_solve"]
+    assert fs["converged"] and abs(fs["it_tree_shaped_inner_products"] - fs["it"]) <= 1
+
