@@ -348,6 +348,18 @@ def cpu_baseline(args, pr, sd, PiS, b_schur, iters, threads=None, S=None, M=None
         xr, itr, resr = cm.pcg(b_schur, np.zeros(sd.n_gamma), maxit=k + 1, nthreads=cores)
         cm.set_reverse_order(False)
         m = min(itg, itc, itr)
+        tree = None
+        try:   # the CPU port with its three inner products summed as a tree: the arithmetic whose
+            # converged solve stops where the GPU's does (1972 / 1973 at 4M DOF against 2008 with term-by-term sums)
+            xt, itt, rest = cm.pcg(b_schur, np.zeros(sd.n_gamma), maxit=k + 1, nthreads=cores, variant="tdot")
+            mt = min(m, itt)
+            tree = {"x_rel_diff_gpu_vs_cpu_at_common_index": float(np.linalg.norm(xg - xt) / np.linalg.norm(xt)) if itt == itg else None,
+                    "x_rel_diff_cpu_tree_vs_cpu_sequential": float(np.linalg.norm(xt - xc) / np.linalg.norm(xc)) if itt == itc else None,
+                    "res_norm_history_rel_diff_gpu_vs_cpu": {str(i): float(np.abs(resg[:i] - rest[:i]).max() / rest[:i].max())
+                                                             for i in (5, 10, 20, 50, 100, 200, mt) if i <= mt},
+                    "note": "same comparison against the CPU port with r'z, p'Ap, r'r summed as a tree (KB_ORACLE_VARIANT=tdot)"}
+        except Exception as e:   # a probe, never a reason to lose the line
+            tree = {"error": str(e)[:200]}
 
         def hist_diff(a, b, upto):
             return float(np.abs(a[:upto] - b[:upto]).max() / b[:upto].max())
@@ -360,6 +372,7 @@ def cpu_baseline(args, pr, sd, PiS, b_schur, iters, threads=None, S=None, M=None
                   "res_norm_history_rel_diff_gpu_vs_cpu": {str(i): hist_diff(resg, resc, i) for i in marks},
                   "res_norm_history_rel_diff_floor_cpu_vs_cpu_reordered": {str(i): hist_diff(resr, resc, i) for i in marks},
                   "relres_at_common_index": float(resc[m - 1] / np.linalg.norm(b_schur)),
+                  "cpu_port_with_tree_shaped_inner_products": tree,
                   "note": "all solves stopped at the same iteration index (maxit); history differences are maxima over the first "
                           "i iterations relative to the largest residual norm; the floor is the CPU port against itself with "
                           "reordered interface sums; the converged CPU solve and its iteration count are in the reference arm's "
