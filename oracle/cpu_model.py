@@ -12,9 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 #   fma   fused multiply-adds everywhere (products enter the sums unrounded, as on the GPU)
 #   ldot  the three inner products of a PCG iteration accumulated in extended precision
 #   tdot  ... in plain doubles, but summed as a tree (the shape of the GPU's block partials)
+#   bdot  ... in plain doubles with the 16 running sums of a SIMD BLAS ddot (what Julia's dot() does at least)
 # KB_ORACLE_VARIANT selects the variant every call uses; CpuModel.pcg(variant=...) runs one solve with another variant
 # on the same model (the variants share every data structure).
-_FLAGS = {"": [], "fma": ["-mfma", "-ffp-contract=fast"], "ldot": ["-DKO_LONG_DOT"], "tdot": ["-DKO_TREE_DOT"]}
+_FLAGS = {"": [], "fma": ["-mfma", "-ffp-contract=fast"], "ldot": ["-DKO_LONG_DOT"], "tdot": ["-DKO_TREE_DOT"], "bdot": ["-DKO_BLAS_DOT"]}
 _VARIANT = os.environ.get("KB_ORACLE_VARIANT", "")
 _libs = {}
 

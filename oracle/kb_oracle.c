@@ -305,6 +305,19 @@ static double dot(const double *a, const double *b, int32_t n) {
   const double s = nb > 0 ? part[0] : 0.0;
   free(part);
   return s;
+#elif defined(KO_BLAS_DOT)
+  /* KB_ORACLE_VARIANT=bdot: the summation shape of a single-threaded SIMD BLAS ddot (OpenBLAS Haswell micro-kernel: four
+   * vector accumulators of four doubles over 16 entries per step, horizontal sum, sequential tail) -- what Julia's
+   * dot() does at least (OpenBLAS also splits n > 10000 over its threads) */
+  double acc[16];
+  for (int l = 0; l < 16; ++l) acc[l] = 0.0;
+  const int32_t n16 = n & ~15;
+  for (int32_t i = 0; i < n16; i += 16)
+    for (int l = 0; l < 16; ++l) acc[l] += a[i + l] * b[i + l];
+  for (int l = 0; l < 4; ++l) acc[l] = (acc[l] + acc[l + 4]) + (acc[l + 8] + acc[l + 12]);
+  double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  for (int32_t i = n16; i < n; ++i) s += a[i] * b[i];
+  return s;
 #else
   double s = 0.0;
   for (int32_t i = 0; i < n; ++i) s += a[i] * b[i];
