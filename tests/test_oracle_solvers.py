@@ -60,7 +60,7 @@ def test_eigpcg_recovers_least_dominant_eigenvectors_and_eigdefpcg_uses_them():
     assert V2.shape == (n, nvec)
 
 
-@pytest.mark.parametrize("variant", ["fma", "ldot", "tdot"])
+@pytest.mark.parametrize("variant", ["fma", "ldot", "tdot", "bdot"])
 def test_cpu_port_arithmetic_variants_agree_on_a_small_solve(variant):
     """The builds of oracle/kb_oracle.c used for the rounding-floor probes of DESIGN.md section 2 (fused multiply-adds,
     extended-precision / tree-shaped inner products) are the same algorithm: same stopping index and solution as the
