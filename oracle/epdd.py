@@ -13,6 +13,9 @@ for the two index-map / assembly routines:
 Interior solves are done exactly (sparse direct), i.e. the reference run with
 ``preconds`` = exact Cholesky factors so that its inner IterativeSolvers.cg
 converges in one step.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or data for this path and cannot run here (no Julia);
+this restatement is pinned by the reference's in-script identities and self-generated goldens only.
 """
 import numpy as np
 import scipy.sparse as sp

@@ -5,6 +5,9 @@ eigdefpcg, following cg.jl:67-109, defcg.jl:242-308, eigcg.jl:143-267 and defcg.
 LinearMaps.FunctionMap and preconditioner objects.  ``EPS`` is the reference's hard-wired
 relative residual tolerance (RecyclingKrylovSolvers.jl:21).  As in the reference, ``it`` starts
 at 1 (it = iterations + 1), ``res_norm`` has ``it`` entries and ``x`` is updated in place.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or data for this path and cannot run here (no Julia);
+this restatement is pinned by the reference's in-script identities and self-generated goldens only.
 """
 import numpy as np
 
