@@ -5,6 +5,7 @@ floating subdomains; plus the committed golden vectors."""
 import os
 
 import numpy as np
+import pytest
 import scipy.sparse.linalg as spla
 
 import oracle.epdd as E
@@ -76,3 +77,27 @@ def test_golden_vectors():
     assert it == int(g["pcg_it"])
     assert abs(res - g["pcg_res"]).max() <= 1e-9 * res[0]
     assert np.linalg.norm(ug - g["pcg_x"]) <= 1e-9 * np.linalg.norm(ug)
+
+
+@pytest.mark.parametrize("nx,n_gamma,it_nn,it_cg", [(33, 177, 8, 28), (65, 369, 9, 41)])
+def test_constant_coefficient_counts_of_the_survey_prototype(nx, n_gamma, it_nn, it_cg):
+    """The only numbers about this path that were NOT produced by this repository: SURVEY.md 8(c) lists, for a throwaway
+    prototype written from the reference during the survey (structured mesh, 4 x 4 square subdomains, a = 1, f = -1,
+    u = 0.734 on the boundary, exact interior solves, pinv(rcond = sqrt(eps)), tolerance 1e-7), the interface size and the
+    iteration counts `it` (reference convention) of Neumann-Neumann PCG and of unpreconditioned CG.  The oracle reproduces
+    them exactly on the unjittered mesh (the lognormal rows of that table depend on the prototype's random field)."""
+    from krylov_b200.hostprep import epdd_host as H
+    from krylov_b200.hostprep import mesh as M
+    cells, pts, mk, nb = M.structured_mesh(nx, jitter=0.0)
+    epart, npart = M.rcb_partition(cells, pts, 16)
+    sd = H.set_subdomains(cells, nb, epart, npart, mk == 1)
+    nn = pts.shape[1]
+    lb = E.prepare_local_schurs_ref(cells, pts, epart, sd, np.ones(nn), -np.ones(nn), 0.734 * np.ones(nn)) if nx <= 33 else \
+        H.prepare_local_schurs(cells, pts, epart, sd, np.ones(nn), -np.ones(nn), 0.734 * np.ones(nn))
+    inner = E.ExactInterior(lb.A_II)
+    Pi = E.prepare_neumann_neumann_schur_precond(E.assemble_local_schurs(lb, inner))
+    bs = E.get_schur_rhs(lb, inner, sd)
+    A = lambda v: E.apply_local_schurs(lb, inner, sd, v)   # noqa: E731
+    assert sd.n_gamma == n_gamma
+    assert OS.pcg(A, bs, np.zeros(n_gamma), lambda r: E.apply_neumann_neumann_schur(Pi, sd, r))[1] == it_nn
+    assert OS.pcg(A, bs, np.zeros(n_gamma), lambda r: r.copy())[1] == it_cg
