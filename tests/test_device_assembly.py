@@ -98,6 +98,28 @@ def test_rhs_maps_reproduce_the_literal_transcription_bit_for_bit(nx, ndom, jitt
     assert np.array_equal(bI2, np.concatenate(ref2.b_I)) and np.array_equal(bG2, ref2.b_G)
 
 
+@pytest.mark.parametrize("seed,ndom,rule", [(0, 5, "min"), (1, 9, "max"), (2, 12, "min")])
+def test_assembly_and_rhs_maps_on_jagged_partitions(seed, ndom, rule):
+    """Irregular (METIS-like) partitions -- jagged interfaces, nodes shared by three and more subdomains, interface nodes
+    on the Dirichlet layer: blocks and right-hand sides in gather form are still the bits of the literal transcription."""
+    from test_oracle_maps import _region_growing_partition
+    cells, pts, mk, nb = M.structured_mesh(21, jitter=0.15)
+    epart, npart = _region_growing_partition(cells, nb, ndom, seed, rule)
+    sd = H.set_subdomains(cells, nb, epart, npart, mk == 1)
+    rng = np.random.default_rng(seed)
+    coeff = np.exp(M.lognormal_field(pts, 5))
+    f = -1.0 + 0.1 * rng.standard_normal(pts.shape[1])
+    u = 0.734 + 0.1 * rng.standard_normal(pts.shape[1])
+    ref = E.prepare_local_schurs_ref(cells, pts, epart, sd, coeff, f, u)
+    maps = H.assembly_maps(cells, epart, sd)
+    for d in range(ndom):
+        for w, A in enumerate((ref.A_II[d], ref.A_IG[d], ref.A_GG[d])):
+            assert maps.ptr[d][w].size == A.nnz + 1
+            assert np.array_equal(H.assemble_values_from_map(cells, pts, coeff, maps.ptr[d][w], maps.src[d][w]), A.data)
+    bI, bG = H.assemble_rhs_from_map(cells, pts, coeff, H.rhs_maps(cells, pts, epart, sd, f, u))
+    assert np.array_equal(bI, np.concatenate(ref.b_I)) and np.array_equal(bG, ref.b_G)
+
+
 def rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
